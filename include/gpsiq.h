@@ -1,0 +1,164 @@
+/* gpsiq.h — C-ABI of the B200 GPS L1 C/A baseband I/Q synthesizer.
+ *
+ * The reference (Mictronics/pluto-gps-sim) has no plugin / operator / FFI
+ * interface for its hot path: the per-sample loop is inline in main()
+ * between pthread_mutex_lock (plutogpssim.c:2689) and pthread_cond_signal
+ * (plutogpssim.c:2757).  The seam is therefore defined by DATA:
+ *
+ *   inputs   the chan[MAX_CHAN] fields the loop reads {prn, ca, f_carr, f_code,
+ *            carr_phase, code_phase, dwrd, iword, ibit, icode, dataBit, codeCA},
+ *            gain[MAX_CHAN] and delt — all written by the per-epoch refresh at
+ *            plutogpssim.c:2656-2687 (computeCodePhase, plutogpssim.c:1754-1787)
+ *            and, for carr_phase, by allocateChannel (plutogpssim.c:1964);
+ *   outputs  iq_buff[2*NUM_SAMPLES] (plutogpssim.c:2754-2755) and the advanced
+ *            chan[i].carr_phase (plutogpssim.c:2741-2746), the only loop state
+ *            the reference reads again in the next epoch.
+ *
+ * A drop-in replaces plutogpssim.c:2690-2756 by gpsiq_make_desc() per active
+ * channel + gpsiq_synth() into iq_buff (INTEGRATION.md shows the patch).
+ *
+ * Conventions: plain C, int status returns (0 = GPSIQ_OK, negative = error,
+ * text via gpsiq_strerror / gpsiq_last_error), caller-owned buffers, one
+ * context per CUDA device, calls on one context are not re-entrant, different
+ * contexts may be driven from different threads.  There is NO CPU fallback:
+ * without a usable CUDA device gpsiq_create fails with GPSIQ_ERR_CUDA.
+ */
+#ifndef GPSIQ_H
+#define GPSIQ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPSIQ_OK 0
+#define GPSIQ_ERR_ARG (-1)      /* bad argument / out-of-contract descriptor */
+#define GPSIQ_ERR_CUDA (-2)     /* CUDA runtime error (see gpsiq_last_error) */
+#define GPSIQ_ERR_NOMEM (-3)
+#define GPSIQ_ERR_CAPACITY (-4) /* n_epochs > cfg.max_epochs */
+
+/* carrier NCO arithmetic */
+#define GPSIQ_CARRIER_FLOAT 0 /* shipped build: FLOAT_CARR_PHASE defined, plutogpssim.h:12; binary64 recurrence plutogpssim.c:2697, 2741-2746 */
+#define GPSIQ_CARRIER_INT32 1 /* compiled-out #else branch: uint32 phase, plutogpssim.c:2699, 2748, 1966-1967, 2675 */
+
+/* gpsiq_chan_desc.flags */
+#define GPSIQ_FLAG_RESET_CARRIER 1u /* slot was (re)allocated: start from carr_phase0 (plutogpssim.c:1964) */
+
+/* synthesis kernel selection (gpsiq_config.kernel) */
+#define GPSIQ_KERNEL_AUTO 0
+#define GPSIQ_KERNEL_LANE_PER_CHANNEL 1 /* warp = sample tile, lane = channel, true FP64 steps */
+#define GPSIQ_KERNEL_FIXED_POINT 2      /* thread = sample run, integer NCO segments */
+
+#define GPSIQ_MAX_CHAN 32
+#define GPSIQ_CA_LEN 1023
+
+/* One per channel slot per epoch: the state the reference's loop starts from.
+ * All doubles are bit copies of what the host computed — the kernels never
+ * re-derive them.  64 bytes. */
+typedef struct gpsiq_chan_desc {
+    int32_t prn;         /* 1..32; <=0 = inactive slot                       plutogpssim.h:153 */
+    int32_t ms0;         /* iword*600 + ibit*20 + icode at sample 0          plutogpssim.c:1769-1778 */
+    uint64_t navbits;    /* bit k = NAV data bit number (ms0/20 + k), i.e.
+                            (dwrd[b/30] >> (29 - b%30)) & 1, b = ms0/20 + k   plutogpssim.c:1781, 2732 */
+    double code_phase0;  /* chips, [0,1023)                                  plutogpssim.c:1770 */
+    double code_step;    /* f_code*delt evaluated in binary64 on the host    plutogpssim.c:2709 */
+    double carr_step;    /* FLOAT: f_carr*delt (cycles/sample)               plutogpssim.c:2741
+                            INT32: (int)round(512*65536*f_carr*delt)         plutogpssim.c:2675 */
+    double carr_phase0;  /* used iff flags & GPSIQ_FLAG_RESET_CARRIER.
+                            FLOAT: cycles in [0,1); INT32: the uint32 phase  plutogpssim.c:1964-1967 */
+    double gain;         /* path_loss*ant_gain                               plutogpssim.c:2685 */
+    uint32_t flags;
+    uint32_t reserved;
+} gpsiq_chan_desc;
+
+typedef struct gpsiq_config {
+    int32_t device;            /* CUDA device ordinal */
+    int32_t max_chan;          /* slots per epoch: 12 (plutogpssim.h:21) .. GPSIQ_MAX_CHAN */
+    int32_t samples_per_epoch; /* 300000 = NUM_SAMPLES, plutogpssim.c:43-44 */
+    int32_t carrier_mode;      /* GPSIQ_CARRIER_* */
+    int32_t max_epochs;        /* capacity of one gpsiq_synth call */
+    int32_t tile_samples;      /* 0 = default; checkpoint / CTA tile length */
+    int32_t kernel;            /* GPSIQ_KERNEL_* */
+    int32_t reserved[9];
+} gpsiq_config;
+
+typedef struct gpsiq_ctx gpsiq_ctx;
+
+int gpsiq_create(gpsiq_ctx **ctx, const gpsiq_config *cfg);
+void gpsiq_destroy(gpsiq_ctx *ctx);
+
+/* Synthesize n_epochs consecutive epochs.  desc is [n_epochs][max_chan] in
+ * HOST memory; iq_out receives n_epochs*samples_per_epoch interleaved
+ * little-endian int16 I,Q pairs in HOST memory (pinned memory from
+ * gpsiq_host_alloc makes the copies asynchronous), or may be NULL to leave the
+ * result in the context's device buffer (gpsiq_device_iq).  Blocking: returns
+ * when iq_out is complete.  The carrier phase of every slot continues from the
+ * previous call (or from gpsiq_set_carrier / a RESET_CARRIER descriptor).
+ * Replaces plutogpssim.c:2690-2756 for n_epochs epochs at once. */
+int gpsiq_synth(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc, int n_epochs, int16_t *iq_out);
+
+/* Same, all-device and asynchronous: desc_dev and iq_dev are DEVICE pointers
+ * (iq_dev 16-byte aligned), work is enqueued on cuda_stream (a cudaStream_t;
+ * NULL = the context's own stream) and the call returns without waiting. */
+int gpsiq_synth_device(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc_dev, int n_epochs, int16_t *iq_dev,
+                       void *cuda_stream);
+
+/* Carrier phase per slot after the last synthesized epoch (max_chan values;
+ * INT32 mode: the uint32 phase as a double) — chan[i].carr_phase after
+ * plutogpssim.c:2741-2748.  Used for time-slice hand-off between GPUs. */
+int gpsiq_get_carrier(gpsiq_ctx *ctx, double *carr_phase);
+int gpsiq_set_carrier(gpsiq_ctx *ctx, const double *carr_phase);
+/* Post-epoch carrier phase of every (epoch, slot) of the last call
+ * ([n_epochs][max_chan]); parity aid. */
+int gpsiq_get_carrier_trace(gpsiq_ctx *ctx, double *trace, int n_epochs);
+
+/* Device buffer holding the last gpsiq_synth result when iq_out was NULL. */
+int16_t *gpsiq_device_iq(gpsiq_ctx *ctx);
+
+/* Order-independent 64-bit checksum of each epoch of an I/Q stream in DEVICE
+ * memory (sum over samples of mix64(index, I|Q<<16)); lets multi-GB runs be
+ * compared with the oracle without a device-to-host copy of the stream.
+ * sums_out: n_epochs values in HOST memory. */
+int gpsiq_checksum_device(gpsiq_ctx *ctx, const int16_t *iq_dev, int n_epochs, uint64_t *sums_out);
+
+/* Host helper: fold the reference's per-channel loop inputs into a descriptor.
+ * Arguments are the chan[i] fields after computeCodePhase (plutogpssim.c:1754-1787),
+ * gain[i] (plutogpssim.c:2685) and delt (plutogpssim.c:2397).  dwrd is the
+ * reference's 60-word NAV buffer (30-bit words, plutogpssim.h:166) passed as
+ * 64-bit values ('unsigned long' on LP64).  carr_phase_is_new != 0 marks a slot
+ * whose carr_phase was just initialised by allocateChannel.  Pure host code. */
+int gpsiq_make_desc(gpsiq_chan_desc *out, int carrier_mode, int prn, double f_carr, double f_code, double delt,
+                    double carr_phase, double code_phase, const uint64_t *dwrd60, int iword, int ibit, int icode,
+                    double gain, int carr_phase_is_new);
+
+/* Host execution of the exact NCO fast-forward the scan kernels run on the
+ * device (csrc/nco_scan.cuh): advances *phase by `count` steps of the code
+ * (mode 0: plutogpssim.c:2709-2713) or carrier (mode 1: plutogpssim.c:2741-2746)
+ * recurrence and adds the number of code wraps to *wraps.  Diagnostic / test aid. */
+int gpsiq_nco_advance(int mode, double *phase, double step, int64_t count, int64_t *wraps);
+
+/* Pinned host memory for descriptors / I/Q (cudaHostAlloc). */
+void *gpsiq_host_alloc(size_t bytes);
+void gpsiq_host_free(void *p);
+
+/* Number of CUDA kernel launches issued by this context so far. */
+int64_t gpsiq_launch_count(const gpsiq_ctx *ctx);
+/* Device time (ms, CUDA events on the context's stream) spent in the synthesis
+ * kernel / in all kernels of the last gpsiq_synth call. */
+int gpsiq_last_timing(const gpsiq_ctx *ctx, float *synth_kernel_ms, float *all_kernels_ms);
+
+const char *gpsiq_strerror(int status);
+const char *gpsiq_last_error(const gpsiq_ctx *ctx);
+const char *gpsiq_version(void);
+
+/* The 512-entry carrier tables and the C/A code the kernels use (host copies),
+ * for parity checks against plutogpssim.c:93-161 and plutogpssim.c:207-244. */
+void gpsiq_get_tables(int32_t *sin512, int32_t *cos512);
+int gpsiq_get_ca_code(int prn, uint8_t *chips1023);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPSIQ_H */

@@ -1,0 +1,92 @@
+/* TEST INFRASTRUCTURE — capture backend standing in for libiio/libad9361/libcurl.
+ *
+ * Linked with the UNMODIFIED reference object (oracle/Makefile target
+ * _ref/ref_verbatim).  iio_buffer_push() is where the reference hands a
+ * 300 000-sample buffer to the SDR (plutogpssim.c:2146-2158); here it appends
+ * the buffer to $FAKE_IIO_OUT instead.  The reference's mutex/condvar
+ * handshake is timing based, so a fast consumer sees the calloc'ed all-zero
+ * buffer first and may see an epoch twice: a push is kept
+ * only if it differs from the previously kept one and is not all zero.
+ * After $FAKE_IIO_EPOCHS kept buffers push() returns -1, which sends the
+ * reference through its own shutdown path (plutogpssim.c:2153-2156,
+ * 2181-2184).  Nothing here is part of the product path.
+ */
+#define _GNU_SOURCE
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "stubs/iio.h"
+#include "stubs/ad9361.h"
+#include "stubs/curl/curl.h"
+
+struct iio_buffer {
+    size_t bytes;
+    char *data;
+    char *prev;
+    long kept, pushes, limit;
+    FILE *out;
+};
+
+static int dummy_ctx, dummy_dev, dummy_chn;
+
+struct iio_context *iio_create_default_context(void) { return (struct iio_context *) &dummy_ctx; }
+struct iio_context *iio_create_network_context(const char *h) { (void) h; return (struct iio_context *) &dummy_ctx; }
+struct iio_context *iio_create_context_from_uri(const char *u) { (void) u; return (struct iio_context *) &dummy_ctx; }
+void iio_context_destroy(struct iio_context *c) { (void) c; }
+void iio_strerror(int err, char *dst, size_t len) { snprintf(dst, len, "fake iio error %d", err); }
+unsigned int iio_context_get_devices_count(const struct iio_context *c) { (void) c; return 2; }
+struct iio_device *iio_context_find_device(const struct iio_context *c, const char *n) {
+    (void) c; (void) n; return (struct iio_device *) &dummy_dev;
+}
+int iio_device_set_kernel_buffers_count(const struct iio_device *d, unsigned int nb) { (void) d; (void) nb; return 0; }
+struct iio_channel *iio_device_find_channel(const struct iio_device *d, const char *n, bool o) {
+    (void) d; (void) n; (void) o; return (struct iio_channel *) &dummy_chn;
+}
+ssize_t iio_channel_attr_write(const struct iio_channel *c, const char *a, const char *s) { (void) c; (void) a; (void) s; return 0; }
+int iio_channel_attr_write_longlong(const struct iio_channel *c, const char *a, long long v) { (void) c; (void) a; (void) v; return 0; }
+int iio_channel_attr_write_double(const struct iio_channel *c, const char *a, double v) { (void) c; (void) a; (void) v; return 0; }
+int iio_channel_attr_write_bool(const struct iio_channel *c, const char *a, bool v) { (void) c; (void) a; (void) v; return 0; }
+void iio_channel_enable(struct iio_channel *c) { (void) c; }
+void iio_channel_disable(struct iio_channel *c) { (void) c; }
+int ad9361_set_bb_rate(struct iio_device *d, unsigned long r) { (void) d; (void) r; return 0; }
+
+struct iio_buffer *iio_device_create_buffer(const struct iio_device *d, size_t samples, bool cyclic) {
+    (void) d; (void) cyclic;
+    struct iio_buffer *b = calloc(1, sizeof *b);
+    const char *path = getenv("FAKE_IIO_OUT");
+    const char *lim = getenv("FAKE_IIO_EPOCHS");
+    b->bytes = samples * 4;               /* interleaved int16 I,Q */
+    b->data = calloc(1, b->bytes);
+    b->prev = calloc(1, b->bytes);
+    b->limit = lim ? atol(lim) : 10;
+    b->out = path ? fopen(path, "wb") : NULL;
+    return b;
+}
+
+void *iio_buffer_start(const struct iio_buffer *b) { return b->data; }
+
+ssize_t iio_buffer_push(struct iio_buffer *b) {
+    b->pushes++;
+    if (memcmp(b->data, b->prev, b->bytes) != 0) {   /* prev starts all-zero: zero pushes are dropped too */
+        if (b->out) fwrite(b->data, 1, b->bytes, b->out);
+        memcpy(b->prev, b->data, b->bytes);
+        b->kept++;
+    }
+    if (b->kept >= b->limit) return -1;
+    return (ssize_t) b->bytes;
+}
+
+void iio_buffer_destroy(struct iio_buffer *b) {
+    fprintf(stderr, "fake_iio: %ld pushes, %ld kept\n", b->pushes, b->kept);
+    if (b->out) fclose(b->out);
+    free(b->data); free(b->prev); free(b);
+}
+
+CURLcode curl_global_init(long f) { (void) f; return CURLE_OK; }
+void curl_global_cleanup(void) {}
+CURL *curl_easy_init(void) { return NULL; }
+CURLcode curl_easy_setopt(CURL *h, CURLoption o, ...) { (void) h; (void) o; return CURLE_OK; }
+CURLcode curl_easy_perform(CURL *h) { (void) h; return CURLE_GOT_NOTHING; }
+void curl_easy_cleanup(CURL *h) { (void) h; }

@@ -1,0 +1,148 @@
+"""ctypes binding of the C-ABI in include/gpsiq.h (libgpsiq.so, built in-tree).
+
+There is no fallback: if the shared library is missing or cannot be loaded this
+module raises at import time, and ``Synthesizer`` raises if no CUDA device can
+be opened.  Nothing here touches ``oracle/``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgpsiq.so")
+
+OK = 0
+ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_CAPACITY = -1, -2, -3, -4
+CARRIER_FLOAT, CARRIER_INT32 = 0, 1
+FLAG_RESET_CARRIER = 1
+KERNEL_AUTO, KERNEL_LANE_PER_CHANNEL, KERNEL_FIXED_POINT = 0, 1, 2
+MAX_CHAN = 32
+NCO_CODE, NCO_CARRIER = 0, 1
+
+# numpy view of gpsiq_chan_desc (64 bytes, include/gpsiq.h)
+DESC_DTYPE = np.dtype(
+    [
+        ("prn", "<i4"),
+        ("ms0", "<i4"),
+        ("navbits", "<u8"),
+        ("code_phase0", "<f8"),
+        ("code_step", "<f8"),
+        ("carr_step", "<f8"),
+        ("carr_phase0", "<f8"),
+        ("gain", "<f8"),
+        ("flags", "<u4"),
+        ("reserved", "<u4"),
+    ]
+)
+assert DESC_DTYPE.itemsize == 64
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("device", C.c_int32),
+        ("max_chan", C.c_int32),
+        ("samples_per_epoch", C.c_int32),
+        ("carrier_mode", C.c_int32),
+        ("max_epochs", C.c_int32),
+        ("tile_samples", C.c_int32),
+        ("kernel", C.c_int32),
+        ("reserved", C.c_int32 * 9),
+    ]
+
+
+# every symbol include/gpsiq.h declares: name -> (restype, argtypes)
+_vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
+_d = C.c_double
+SYMBOLS = {
+    "gpsiq_create": (_i, [C.POINTER(_vp), C.POINTER(Config)]),
+    "gpsiq_destroy": (None, [_vp]),
+    "gpsiq_synth": (_i, [_vp, _vp, _i, _vp]),
+    "gpsiq_synth_device": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "gpsiq_get_carrier": (_i, [_vp, _vp]),
+    "gpsiq_set_carrier": (_i, [_vp, _vp]),
+    "gpsiq_get_carrier_trace": (_i, [_vp, _vp, _i]),
+    "gpsiq_device_iq": (_vp, [_vp]),
+    "gpsiq_checksum_device": (_i, [_vp, _vp, _i, _vp]),
+    "gpsiq_make_desc": (_i, [_vp, _i, _i, _d, _d, _d, _d, _d, _vp, _i, _i, _i, _d, _i]),
+    "gpsiq_nco_advance": (_i, [_i, C.POINTER(_d), _d, _i64, C.POINTER(_i64)]),
+    "gpsiq_host_alloc": (_vp, [C.c_size_t]),
+    "gpsiq_host_free": (None, [_vp]),
+    "gpsiq_launch_count": (_i64, [_vp]),
+    "gpsiq_last_timing": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "gpsiq_strerror": (C.c_char_p, [_i]),
+    "gpsiq_last_error": (C.c_char_p, [_vp]),
+    "gpsiq_version": (C.c_char_p, []),
+    "gpsiq_get_tables": (None, [_vp, _vp]),
+    "gpsiq_get_ca_code": (_i, [_i, _vp]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+class GpsiqError(RuntimeError):
+    def __init__(self, status, detail=""):
+        self.status = status
+        msg = lib.gpsiq_strerror(status).decode()
+        super().__init__("%s (%d)%s" % (msg, status, ": " + detail if detail else ""))
+
+
+def check(status, ctx=None):
+    if status != OK:
+        raise GpsiqError(status, lib.gpsiq_last_error(ctx).decode())
+
+
+def version():
+    return lib.gpsiq_version().decode()
+
+
+def tables():
+    s = np.zeros(512, np.int32)
+    c = np.zeros(512, np.int32)
+    lib.gpsiq_get_tables(s.ctypes.data, c.ctypes.data)
+    return s, c
+
+
+def ca_code(prn):
+    chips = np.zeros(1023, np.uint8)
+    check(lib.gpsiq_get_ca_code(int(prn), chips.ctypes.data))
+    return chips
+
+
+def nco_advance(mode, phase, step, count):
+    """Host run of the scan the kernels use; returns (phase, wraps)."""
+    x = _d(phase)
+    w = _i64(0)
+    check(lib.gpsiq_nco_advance(int(mode), C.byref(x), float(step), int(count), C.byref(w)))
+    return x.value, w.value
+
+
+def make_desc(carrier_mode, prn, f_carr, f_code, delt, carr_phase, code_phase, dwrd60, iword, ibit, icode, gain,
+              carr_phase_is_new):
+    """gpsiq_make_desc for one slot -> numpy record (DESC_DTYPE)."""
+    out = np.zeros(1, DESC_DTYPE)
+    d = np.ascontiguousarray(dwrd60, dtype=np.uint64)
+    assert d.size == 60
+    check(
+        lib.gpsiq_make_desc(
+            out.ctypes.data, int(carrier_mode), int(prn), float(f_carr), float(f_code), float(delt),
+            float(carr_phase), float(code_phase), d.ctypes.data, int(iword), int(ibit), int(icode), float(gain),
+            int(bool(carr_phase_is_new)),
+        )
+    )
+    return out[0]

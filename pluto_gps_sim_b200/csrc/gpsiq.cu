@@ -1,0 +1,594 @@
+// gpsiq.cu — sm_100a kernels + C-ABI (include/gpsiq.h) of the GPS L1 C/A
+// baseband I/Q synthesizer.  Replaces the reference's per-sample loop,
+// /root/reference/plutogpssim.c:2689-2756, for whole batches of 0.1 s epochs.
+//
+// Pipeline for one batch of E epochs x C channel slots x N samples/epoch
+// (all on one stream, no host synchronisation in between):
+//
+//   k_prepare       (E*C CTAs)   per-(epoch,slot) amplitude LUT
+//                                lut[k] = ((int)(cos[k]*gain), (int)(sin[k]*gain))
+//                                == plutogpssim.c:2701-2702 with the +-1 BPSK sign
+//                                factored out (trunc is odd-symmetric)
+//   k_scan_code     (E*C threads) exact code-NCO state at every tile boundary
+//                                (restarts every epoch: plutogpssim.c:1770)
+//   k_scan_carrier  (C threads)  exact carrier-NCO state at every tile boundary;
+//                                serial over the epochs of the batch because
+//                                carr_phase chains across epochs (plutogpssim.c:2741)
+//   k_synth_*       (E*tiles)    the per-sample work: chip lookup, NAV bit,
+//                                carrier LUT, across-channel accumulate, int16 pack
+//
+// See DESIGN.md for the data layout and the roofline of each kernel.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/gpsiq.h"
+#include "nco_scan.cuh"
+
+using namespace gpsiq;
+
+// ---------------------------------------------------------------------------
+// tables
+// ---------------------------------------------------------------------------
+#include "carrier_tables.inc"  // static const int16_t k_sin512[512], k_cos512[512] (generated, tools/gen_tables.py)
+
+__constant__ int16_t c_sin512[512];
+__constant__ int16_t c_cos512[512];
+
+// C/A code bitmaps: 32 words per PRN, bit (i&31) of word (i>>5) = chip i.
+#define CA_WORDS 32
+
+// IS-GPS-200 Table 3-I code phase selection: G2i = stage a XOR stage b of G2.
+static const unsigned char k_g2_taps[32][2] = {
+    {2, 6}, {3, 7}, {4, 8}, {5, 9}, {1, 9}, {2, 10}, {1, 8}, {2, 9}, {3, 10}, {2, 3}, {3, 4},
+    {5, 6}, {6, 7}, {7, 8}, {8, 9}, {9, 10}, {1, 4}, {2, 5}, {3, 6}, {4, 7}, {5, 8}, {6, 9},
+    {1, 3}, {4, 6}, {5, 7}, {6, 8}, {7, 9}, {8, 10}, {1, 6}, {2, 7}, {3, 8}, {4, 9}};
+
+// Same sequence as the reference's codegen (plutogpssim.c:207-244), which uses
+// the equivalent "G2 delay" formulation; tests compare the two chip for chip.
+static void ca_generate(int prn, uint8_t* chips) {
+    unsigned g1 = 0x3ff, g2 = 0x3ff;  // bit s-1 = stage s
+    const int a = k_g2_taps[prn - 1][0] - 1, b = k_g2_taps[prn - 1][1] - 1;
+    for (int i = 0; i < GPSIQ_CA_LEN; i++) {
+        unsigned o1 = (g1 >> 9) & 1u;
+        unsigned o2 = ((g2 >> a) ^ (g2 >> b)) & 1u;
+        chips[i] = (uint8_t) (o1 ^ o2);
+        unsigned f1 = ((g1 >> 2) ^ (g1 >> 9)) & 1u;
+        unsigned f2 = ((g2 >> 1) ^ (g2 >> 2) ^ (g2 >> 5) ^ (g2 >> 7) ^ (g2 >> 8) ^ (g2 >> 9)) & 1u;
+        g1 = ((g1 << 1) | f1) & 0x3ff;
+        g2 = ((g2 << 1) | f2) & 0x3ff;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+struct gpsiq_ctx {
+    gpsiq_config cfg;
+    int C, N, T, ntiles, E;
+    cudaStream_t stream;
+    cudaEvent_t ev_begin, ev_synth0, ev_synth1, ev_end;
+    gpsiq_chan_desc* d_desc;
+    int2* d_lut;          // [E][C][512]
+    double* d_code_ck;    // [E][ntiles][C]
+    int* d_wrap_ck;       // [E][ntiles][C]
+    double* d_carr_ck;    // [E][ntiles][C]   (INT32 mode: uint32 phase as double)
+    double* d_carr_state; // [C]
+    double* d_carr_trace; // [E][C]
+    uint32_t* d_ca;       // [33][CA_WORDS]
+    int16_t* d_iq;        // [E][N][2]
+    unsigned long long* d_sums;
+    int* d_err;
+    int last_epochs;
+    int64_t launches;
+    float synth_ms, all_ms;
+    char err[256];
+};
+
+static char g_err[256];
+
+static int fail(gpsiq_ctx* ctx, int code, const char* what, cudaError_t ce) {
+    char* dst = ctx ? ctx->err : g_err;
+    if (ce != cudaSuccess)
+        snprintf(dst, 256, "%s: %s", what, cudaGetErrorString(ce));
+    else
+        snprintf(dst, 256, "%s", what);
+    return code;
+}
+
+#define CU(call)                                                             \
+    do {                                                                     \
+        cudaError_t ce_ = (call);                                            \
+        if (ce_ != cudaSuccess) return fail(ctx, GPSIQ_ERR_CUDA, #call, ce_); \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// k_prepare: amplitude LUT per (epoch, slot)
+// ---------------------------------------------------------------------------
+__global__ void k_prepare(const gpsiq_chan_desc* __restrict__ desc, int2* __restrict__ lut, int* __restrict__ err) {
+    const int ec = blockIdx.x;
+    const gpsiq_chan_desc d = desc[ec];
+    int2* out = lut + (size_t) ec * 512;
+    if (d.prn <= 0) return;
+    if (d.prn > 32 || !(d.code_phase0 >= 0.0 && d.code_phase0 < 1023.0) || !(d.code_step > 0.0 && d.code_step < 1023.0)) {
+        if (threadIdx.x == 0) atomicExch(err, 1 + ec);
+        return;
+    }
+    for (int k = threadIdx.x; k < 512; k += blockDim.x) {
+        // (int)(+-1 * table * gain) == +-(int)(table * gain): int->double is exact,
+        // one rounding in the product, truncation toward zero (plutogpssim.c:2701-2702)
+        int ip = __double2int_rz(__dmul_rn((double) c_cos512[k], d.gain));
+        int qp = __double2int_rz(__dmul_rn((double) c_sin512[k], d.gain));
+        out[k] = make_int2(ip, qp);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_scan_code: exact code phase + wrap count at every tile start
+// ---------------------------------------------------------------------------
+__global__ void k_scan_code(const gpsiq_chan_desc* __restrict__ desc, double* __restrict__ code_ck,
+                            int* __restrict__ wrap_ck, int EC, int C, int N, int T, int ntiles) {
+    const int ec = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ec >= EC) return;
+    const int e = ec / C, c = ec - e * C;
+    const gpsiq_chan_desc d = desc[ec];
+    if (d.prn <= 0) return;
+    double x = d.code_phase0;
+    int wraps = 0;
+    for (int t = 0; t < ntiles; t++) {
+        const size_t o = ((size_t) e * ntiles + t) * C + c;
+        code_ck[o] = x;
+        wrap_ck[o] = wraps;
+        const int len = min(T, N - t * T);
+        nco_advance<NCO_CODE>(x, d.code_step, len, wraps);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_scan_carrier: exact carrier phase at every tile start, chained over epochs
+// ---------------------------------------------------------------------------
+__global__ void k_scan_carrier(const gpsiq_chan_desc* __restrict__ desc, double* __restrict__ carr_ck,
+                               double* __restrict__ carr_state, double* __restrict__ carr_trace, int E, int C, int N,
+                               int T, int ntiles, int carrier_mode) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double x = carr_state[c];
+    uint32_t u = (uint32_t) x;
+    int dummy = 0;
+    for (int e = 0; e < E; e++) {
+        const gpsiq_chan_desc d = desc[(size_t) e * C + c];
+        if (d.prn <= 0) {
+            carr_trace[(size_t) e * C + c] = (carrier_mode == GPSIQ_CARRIER_FLOAT) ? x : (double) u;
+            continue;
+        }
+        if (d.flags & GPSIQ_FLAG_RESET_CARRIER) {
+            x = d.carr_phase0;
+            u = (uint32_t) d.carr_phase0;
+        }
+        if (carrier_mode == GPSIQ_CARRIER_FLOAT) {
+            for (int t = 0; t < ntiles; t++) {
+                carr_ck[((size_t) e * ntiles + t) * C + c] = x;
+                const int len = min(T, N - t * T);
+                nco_advance<NCO_CARRIER>(x, d.carr_step, len, dummy);
+            }
+            carr_trace[(size_t) e * C + c] = x;
+        } else {
+            const uint32_t step = (uint32_t) (int32_t) d.carr_step;  // closed form mod 2^32 (plutogpssim.c:2748)
+            for (int t = 0; t < ntiles; t++)
+                carr_ck[((size_t) e * ntiles + t) * C + c] = (double) (u + step * (uint32_t) (t * T));
+            u += step * (uint32_t) N;
+            carr_trace[(size_t) e * C + c] = (double) u;
+        }
+    }
+    carr_state[c] = (carrier_mode == GPSIQ_CARRIER_FLOAT) ? x : (double) u;
+}
+
+// ---------------------------------------------------------------------------
+// k_synth_lanes: warp = one tile of samples, lane = channel slot.
+// Executes the very IEEE additions the reference executes, starting from the
+// exact tile-start state; the across-satellite accumulate (plutogpssim.c:2705-2706)
+// is a warp reduction.  Simple and exact by construction; kept as the
+// cross-check for the fixed-point kernel.
+// ---------------------------------------------------------------------------
+#define LANES_WARPS 4
+
+__global__ void __launch_bounds__(LANES_WARPS * 32)
+k_synth_lanes(const gpsiq_chan_desc* __restrict__ desc, const int2* __restrict__ lut,
+              const double* __restrict__ code_ck, const int* __restrict__ wrap_ck,
+              const double* __restrict__ carr_ck, const uint32_t* __restrict__ ca, int16_t* __restrict__ iq,
+              int C, int N, int T, int ntiles, int tile_groups, int carrier_mode) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int2* s_lut = reinterpret_cast<int2*>(smem_raw);                       // [C][512]
+    uint32_t* s_ca = reinterpret_cast<uint32_t*>(s_lut + (size_t) C * 512); // [C][33]
+
+    const int e = blockIdx.x / tile_groups;
+    const int tg = blockIdx.x - e * tile_groups;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const gpsiq_chan_desc* de = desc + (size_t) e * C;
+
+    for (int i = threadIdx.x; i < C * 512; i += blockDim.x) s_lut[i] = lut[(size_t) e * C * 512 + i];
+    for (int i = threadIdx.x; i < C * CA_WORDS; i += blockDim.x) {
+        const int c = i / CA_WORDS, w = i - c * CA_WORDS;
+        const int prn = de[c].prn;
+        s_ca[c * 33 + w] = (prn > 0 && prn <= 32) ? ca[prn * CA_WORDS + w] : 0u;
+    }
+    __syncthreads();
+
+    const int t = tg * LANES_WARPS + warp;
+    if (t >= ntiles) return;
+    const int n0 = t * T;
+    const int len = min(T, N - n0);
+
+    const bool active = (lane < C) && (de[lane < C ? lane : 0].prn > 0);
+    double cp = 0.0, ph = 0.0, cstep = 0.0, pstep = 0.0;
+    uint32_t uph = 0, ustep = 0;
+    uint64_t navbits = 0;
+    int icode = 0, kbit = 0;
+    if (active) {
+        const gpsiq_chan_desc d = de[lane];
+        const size_t o = ((size_t) e * ntiles + t) * C + lane;
+        cp = code_ck[o];
+        const int w = wrap_ck[o] + d.ms0 % 20;
+        kbit = w / 20;
+        icode = w - kbit * 20;
+        ph = carr_ck[o];
+        uph = (uint32_t) ph;
+        cstep = d.code_step;
+        pstep = d.carr_step;
+        ustep = (uint32_t) (int32_t) d.carr_step;
+        navbits = d.navbits;
+    }
+    const int2* my_lut = s_lut + (size_t) (active ? lane : 0) * 512;
+    const uint32_t* my_ca = s_ca + (active ? lane : 0) * 33;
+    uint32_t* out = reinterpret_cast<uint32_t*>(iq) + (size_t) e * N + n0;
+
+    uint32_t keep = 0;
+    for (int n = 0; n < len; n++) {
+        int vi = 0, vq = 0;
+        if (active) {
+            int it;
+            if (carrier_mode == GPSIQ_CARRIER_FLOAT)
+                it = min(__double2int_rd(__dmul_rn(ph, 512.0)), 511);  // plutogpssim.c:2697 (511 clamp: ph==1.0 corner)
+            else
+                it = (int) ((uph >> 16) & 0x1ff);                       // plutogpssim.c:2699
+            const int chipi = __double2int_rz(cp);                      // plutogpssim.c:2737
+            const uint32_t chip = (my_ca[chipi >> 5] >> (chipi & 31)) & 1u;
+            const uint32_t nav = (uint32_t) (navbits >> kbit) & 1u;     // plutogpssim.c:2732
+            const int2 a = my_lut[it];
+            const bool neg = (chip != nav);                             // (2b-1)(2c-1) = +1 iff b == c
+            vi = neg ? -a.x : a.x;
+            vq = neg ? -a.y : a.y;
+            // code NCO + NAV counters, plutogpssim.c:2709-2734
+            cp = __dadd_rn(cp, cstep);
+            if (cp >= 1023.0) {
+                cp = __dadd_rn(cp, -1023.0);
+                if (++icode >= 20) { icode = 0; kbit++; }
+            }
+            // carrier NCO, plutogpssim.c:2741-2748
+            if (carrier_mode == GPSIQ_CARRIER_FLOAT) {
+                ph = __dadd_rn(ph, pstep);
+                if (ph >= 1.0) ph = __dadd_rn(ph, -1.0);
+                else if (ph < 0.0) ph = __dadd_rn(ph, 1.0);
+            } else {
+                uph += ustep;
+            }
+        }
+        const int si = __reduce_add_sync(0xffffffffu, vi);
+        const int sq = __reduce_add_sync(0xffffffffu, vq);
+        // (short) casts of plutogpssim.c:2754-2755: keep the low 16 bits of each sum
+        const uint32_t word = ((uint32_t) si & 0xffffu) | ((uint32_t) sq << 16);
+        if ((n & 31) == lane) keep = word;
+        if ((n & 31) == 31 || n == len - 1) {
+            const int base = n & ~31;
+            if (base + lane <= n) out[base + lane] = keep;  // 128 B per warp, coalesced
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_checksum: order-independent per-epoch checksum of an I/Q stream
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
+    x ^= x >> 27; x *= 0x94d049bb133111ebULL;
+    x ^= x >> 31;
+    return x;
+}
+
+__global__ void k_checksum(const uint32_t* __restrict__ iq, unsigned long long* __restrict__ sums, int N) {
+    const int e = blockIdx.y;
+    const uint32_t* p = iq + (size_t) e * N;
+    unsigned long long acc = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
+        acc += mix64(((unsigned long long) (uint32_t) i << 32) | p[i]);
+    for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sums[e], acc);
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char* gpsiq_version(void) { return "gpsiq 0.1 (sm_100a)"; }
+
+const char* gpsiq_strerror(int s) {
+    switch (s) {
+        case GPSIQ_OK: return "ok";
+        case GPSIQ_ERR_ARG: return "bad argument";
+        case GPSIQ_ERR_CUDA: return "CUDA error";
+        case GPSIQ_ERR_NOMEM: return "out of memory";
+        case GPSIQ_ERR_CAPACITY: return "batch exceeds max_epochs";
+        default: return "unknown status";
+    }
+}
+
+const char* gpsiq_last_error(const gpsiq_ctx* ctx) { return ctx ? ctx->err : g_err; }
+
+void gpsiq_get_tables(int32_t* s, int32_t* c) {
+    for (int i = 0; i < 512; i++) { s[i] = k_sin512[i]; c[i] = k_cos512[i]; }
+}
+
+int gpsiq_get_ca_code(int prn, uint8_t* chips) {
+    if (prn < 1 || prn > 32 || !chips) return GPSIQ_ERR_ARG;
+    ca_generate(prn, chips);
+    return GPSIQ_OK;
+}
+
+int gpsiq_make_desc(gpsiq_chan_desc* out, int carrier_mode, int prn, double f_carr, double f_code, double delt,
+                    double carr_phase, double code_phase, const uint64_t* dwrd60, int iword, int ibit, int icode,
+                    double gain, int carr_phase_is_new) {
+    if (!out) return GPSIQ_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    if (prn <= 0) return GPSIQ_OK;
+    if (prn > 32 || !dwrd60 || iword < 0 || ibit < 0 || ibit >= 30 || icode < 0 || icode >= 20) return GPSIQ_ERR_ARG;
+    out->prn = prn;
+    out->ms0 = iword * 600 + ibit * 20 + icode;
+    // NAV bit window: bit k = data bit number (iword*30 + ibit + k); words past the
+    // reference's 60-word buffer read as 0 (the reference would over-read, App. A)
+    uint64_t nb = 0;
+    const int b0 = iword * 30 + ibit;
+    for (int k = 0; k < 64; k++) {
+        const int b = b0 + k, w = b / 30;
+        if (w >= 60) break;
+        nb |= ((dwrd60[w] >> (29 - b % 30)) & 1ULL) << k;
+    }
+    out->navbits = nb;
+    out->code_phase0 = code_phase;
+    volatile double cs = f_code * delt;  // the very product of plutogpssim.c:2709, one rounding
+    volatile double ps = f_carr * delt;  // plutogpssim.c:2741
+    out->code_step = cs;
+    if (carrier_mode == GPSIQ_CARRIER_FLOAT) {
+        out->carr_step = ps;
+    } else {
+        volatile double q = 512.0 * 65536.0 * f_carr;
+        q = q * delt;                                  // left-to-right, plutogpssim.c:2675
+        out->carr_step = (double) (int) round(q);
+    }
+    out->carr_phase0 = carr_phase;
+    out->gain = gain;
+    out->flags = carr_phase_is_new ? GPSIQ_FLAG_RESET_CARRIER : 0u;
+    return GPSIQ_OK;
+}
+
+int gpsiq_nco_advance(int mode, double* phase, double step, int64_t count, int64_t* wraps) {
+    if (!phase || count < 0 || (mode != NCO_CODE && mode != NCO_CARRIER)) return GPSIQ_ERR_ARG;
+    double x = *phase;
+    int w = 0;
+    int64_t wtot = 0;
+    while (count > 0) {
+        const int chunk = count > (1 << 30) ? (1 << 30) : (int) count;
+        w = 0;
+        if (mode == NCO_CODE) nco_advance<NCO_CODE>(x, step, chunk, w);
+        else nco_advance<NCO_CARRIER>(x, step, chunk, w);
+        wtot += w;
+        count -= chunk;
+    }
+    *phase = x;
+    if (wraps) *wraps += wtot;
+    return GPSIQ_OK;
+}
+
+void* gpsiq_host_alloc(size_t bytes) {
+    void* p = NULL;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return NULL;
+    return p;
+}
+void gpsiq_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
+    gpsiq_ctx* ctx = NULL;
+    if (!out || !cfg) return fail(NULL, GPSIQ_ERR_ARG, "gpsiq_create: null argument", cudaSuccess);
+    *out = NULL;
+    if (cfg->max_chan < 1 || cfg->max_chan > GPSIQ_MAX_CHAN || cfg->samples_per_epoch < 1 || cfg->max_epochs < 1 ||
+        (cfg->carrier_mode != GPSIQ_CARRIER_FLOAT && cfg->carrier_mode != GPSIQ_CARRIER_INT32) || cfg->tile_samples < 0)
+        return fail(NULL, GPSIQ_ERR_ARG, "gpsiq_create: bad config", cudaSuccess);
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev < 1)
+        return fail(NULL, GPSIQ_ERR_CUDA, "gpsiq_create: no CUDA device (there is no CPU fallback)", ce);
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(NULL, GPSIQ_ERR_ARG, "gpsiq_create: bad device", cudaSuccess);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) {
+        snprintf(g_err, sizeof g_err, "gpsiq_create: device %d is sm_%d%d; this build is sm_100a only", cfg->device,
+                 prop.major, prop.minor);
+        return GPSIQ_ERR_CUDA;
+    }
+    ctx = (gpsiq_ctx*) calloc(1, sizeof *ctx);
+    if (!ctx) return GPSIQ_ERR_NOMEM;
+    ctx->cfg = *cfg;
+    ctx->C = cfg->max_chan;
+    ctx->N = cfg->samples_per_epoch;
+    ctx->E = cfg->max_epochs;
+    ctx->T = cfg->tile_samples ? cfg->tile_samples : 1024;
+    ctx->T = (ctx->T + 31) & ~31;
+    ctx->ntiles = (ctx->N + ctx->T - 1) / ctx->T;
+    CU(cudaSetDevice(cfg->device));
+    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&ctx->ev_begin));
+    CU(cudaEventCreate(&ctx->ev_synth0));
+    CU(cudaEventCreate(&ctx->ev_synth1));
+    CU(cudaEventCreate(&ctx->ev_end));
+    const size_t EC = (size_t) ctx->E * ctx->C;
+    const size_t ck = EC * ctx->ntiles;
+    CU(cudaMalloc(&ctx->d_desc, EC * sizeof(gpsiq_chan_desc)));
+    CU(cudaMalloc(&ctx->d_lut, EC * 512 * sizeof(int2)));
+    CU(cudaMalloc(&ctx->d_code_ck, ck * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_wrap_ck, ck * sizeof(int)));
+    CU(cudaMalloc(&ctx->d_carr_ck, ck * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_carr_state, ctx->C * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_carr_trace, EC * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_ca, 33 * CA_WORDS * sizeof(uint32_t)));
+    CU(cudaMalloc(&ctx->d_iq, (size_t) ctx->E * ctx->N * 4));
+    CU(cudaMalloc(&ctx->d_sums, (size_t) ctx->E * sizeof(unsigned long long)));
+    CU(cudaMalloc(&ctx->d_err, sizeof(int)));
+    CU(cudaMemset(ctx->d_carr_state, 0, ctx->C * sizeof(double)));
+    CU(cudaMemset(ctx->d_err, 0, sizeof(int)));
+    CU(cudaMemcpyToSymbol(c_sin512, k_sin512, sizeof k_sin512));
+    CU(cudaMemcpyToSymbol(c_cos512, k_cos512, sizeof k_cos512));
+    uint32_t h_ca[33 * CA_WORDS];
+    memset(h_ca, 0, sizeof h_ca);
+    for (int prn = 1; prn <= 32; prn++) {
+        uint8_t chips[GPSIQ_CA_LEN];
+        ca_generate(prn, chips);
+        for (int i = 0; i < GPSIQ_CA_LEN; i++) h_ca[prn * CA_WORDS + (i >> 5)] |= (uint32_t) chips[i] << (i & 31);
+    }
+    CU(cudaMemcpy(ctx->d_ca, h_ca, sizeof h_ca, cudaMemcpyHostToDevice));
+    const size_t smem_lanes = (size_t) ctx->C * 512 * sizeof(int2) + (size_t) ctx->C * 33 * 4;
+    CU(cudaFuncSetAttribute(k_synth_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_lanes));
+    *out = ctx;
+    return GPSIQ_OK;
+}
+
+void gpsiq_destroy(gpsiq_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_desc); cudaFree(ctx->d_lut); cudaFree(ctx->d_code_ck); cudaFree(ctx->d_wrap_ck);
+    cudaFree(ctx->d_carr_ck); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_carr_trace); cudaFree(ctx->d_ca);
+    cudaFree(ctx->d_iq); cudaFree(ctx->d_sums); cudaFree(ctx->d_err);
+    cudaEventDestroy(ctx->ev_begin); cudaEventDestroy(ctx->ev_synth0);
+    cudaEventDestroy(ctx->ev_synth1); cudaEventDestroy(ctx->ev_end);
+    cudaStreamDestroy(ctx->stream);
+    free(ctx);
+}
+
+static int enqueue(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, int16_t* iq_dev, cudaStream_t st,
+                   bool timed) {
+    const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
+    const int EC = n_epochs * C;
+    if (timed) CU(cudaEventRecord(ctx->ev_begin, st));
+    k_prepare<<<EC, 128, 0, st>>>(desc_dev, ctx->d_lut, ctx->d_err);
+    k_scan_code<<<(EC + 63) / 64, 64, 0, st>>>(desc_dev, ctx->d_code_ck, ctx->d_wrap_ck, EC, C, N, T, ntiles);
+    k_scan_carrier<<<1, 32, 0, st>>>(desc_dev, ctx->d_carr_ck, ctx->d_carr_state, ctx->d_carr_trace, n_epochs, C, N, T,
+                                     ntiles, ctx->cfg.carrier_mode);
+    if (timed) CU(cudaEventRecord(ctx->ev_synth0, st));
+    const int tile_groups = (ntiles + LANES_WARPS - 1) / LANES_WARPS;
+    const size_t smem = (size_t) C * 512 * sizeof(int2) + (size_t) C * 33 * 4;
+    k_synth_lanes<<<n_epochs * tile_groups, LANES_WARPS * 32, smem, st>>>(
+        desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, ctx->d_carr_ck, ctx->d_ca, iq_dev, C, N, T, ntiles,
+        tile_groups, ctx->cfg.carrier_mode);
+    if (timed) {
+        CU(cudaEventRecord(ctx->ev_synth1, st));
+        CU(cudaEventRecord(ctx->ev_end, st));
+    }
+    ctx->launches += 4;
+    ctx->last_epochs = n_epochs;
+    CU(cudaGetLastError());
+    return GPSIQ_OK;
+}
+
+static int check_device_error(gpsiq_ctx* ctx) {
+    int h = 0;
+    CU(cudaMemcpyAsync(&h, ctx->d_err, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (h) {
+        CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+        snprintf(ctx->err, sizeof ctx->err, "descriptor %d (epoch*max_chan+slot) is out of contract", h - 1);
+        return GPSIQ_ERR_ARG;
+    }
+    return GPSIQ_OK;
+}
+
+int gpsiq_synth(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc, int n_epochs, int16_t* iq_out) {
+    if (!ctx || !desc || n_epochs < 1) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_synth: bad argument", cudaSuccess);
+    if (n_epochs > ctx->E) return fail(ctx, GPSIQ_ERR_CAPACITY, "gpsiq_synth: n_epochs > max_epochs", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaMemcpyAsync(ctx->d_desc, desc, (size_t) n_epochs * ctx->C * sizeof(gpsiq_chan_desc), cudaMemcpyHostToDevice,
+                       ctx->stream));
+    int rc = enqueue(ctx, ctx->d_desc, n_epochs, ctx->d_iq, ctx->stream, true);
+    if (rc) return rc;
+    if (iq_out)
+        CU(cudaMemcpyAsync(iq_out, ctx->d_iq, (size_t) n_epochs * ctx->N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = check_device_error(ctx);
+    if (rc) return rc;
+    CU(cudaEventElapsedTime(&ctx->synth_ms, ctx->ev_synth0, ctx->ev_synth1));
+    CU(cudaEventElapsedTime(&ctx->all_ms, ctx->ev_begin, ctx->ev_end));
+    return GPSIQ_OK;
+}
+
+int gpsiq_synth_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, int16_t* iq_dev, void* stream) {
+    if (!ctx || !desc_dev || !iq_dev || n_epochs < 1 || ((uintptr_t) iq_dev & 15))
+        return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_synth_device: bad argument", cudaSuccess);
+    if (n_epochs > ctx->E) return fail(ctx, GPSIQ_ERR_CAPACITY, "gpsiq_synth_device: n_epochs > max_epochs", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    return enqueue(ctx, desc_dev, n_epochs, iq_dev, stream ? (cudaStream_t) stream : ctx->stream, false);
+}
+
+int gpsiq_get_carrier(gpsiq_ctx* ctx, double* p) {
+    if (!ctx || !p) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_get_carrier: bad argument", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(p, ctx->d_carr_state, ctx->C * sizeof(double), cudaMemcpyDeviceToHost));
+    return GPSIQ_OK;
+}
+
+int gpsiq_set_carrier(gpsiq_ctx* ctx, const double* p) {
+    if (!ctx || !p) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_set_carrier: bad argument", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(ctx->d_carr_state, p, ctx->C * sizeof(double), cudaMemcpyHostToDevice));
+    return GPSIQ_OK;
+}
+
+int gpsiq_get_carrier_trace(gpsiq_ctx* ctx, double* trace, int n_epochs) {
+    if (!ctx || !trace || n_epochs < 1 || n_epochs > ctx->E)
+        return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_get_carrier_trace: bad argument", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(trace, ctx->d_carr_trace, (size_t) n_epochs * ctx->C * sizeof(double), cudaMemcpyDeviceToHost));
+    return GPSIQ_OK;
+}
+
+int16_t* gpsiq_device_iq(gpsiq_ctx* ctx) { return ctx ? ctx->d_iq : NULL; }
+
+int gpsiq_checksum_device(gpsiq_ctx* ctx, const int16_t* iq_dev, int n_epochs, uint64_t* sums_out) {
+    if (!ctx || !iq_dev || !sums_out || n_epochs < 1 || n_epochs > ctx->E)
+        return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_checksum_device: bad argument", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemsetAsync(ctx->d_sums, 0, (size_t) n_epochs * 8, ctx->stream));
+    dim3 grid(64, n_epochs);
+    k_checksum<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(iq_dev), ctx->d_sums, ctx->N);
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(sums_out, ctx->d_sums, (size_t) n_epochs * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GPSIQ_OK;
+}
+
+int64_t gpsiq_launch_count(const gpsiq_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gpsiq_last_timing(const gpsiq_ctx* ctx, float* synth_ms, float* all_ms) {
+    if (!ctx) return GPSIQ_ERR_ARG;
+    if (synth_ms) *synth_ms = ctx->synth_ms;
+    if (all_ms) *all_ms = ctx->all_ms;
+    return GPSIQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+"""Host-side handle on the CUDA synthesizer (one context per GPU).
+
+The reference has no operator interface for its hot loop (it is inline in
+``main``, plutogpssim.c:2689-2756); this class is the Python face of the seam
+defined in include/gpsiq.h: per-epoch channel descriptors in, interleaved int16
+I/Q out, carrier phase carried between calls exactly like ``chan[i].carr_phase``.
+All arithmetic happens in libgpsiq.so on the GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+NUM_SAMPLES = 300000  # plutogpssim.c:43-44: TX_SAMPLE_FREQ/10, independent of -s
+
+
+class Synthesizer:
+    def __init__(self, max_chan=12, samples_per_epoch=NUM_SAMPLES, max_epochs=100, carrier_mode=capi.CARRIER_FLOAT,
+                 device=0, tile_samples=0, kernel=capi.KERNEL_AUTO):
+        cfg = capi.Config()
+        cfg.device = device
+        cfg.max_chan = max_chan
+        cfg.samples_per_epoch = samples_per_epoch
+        cfg.carrier_mode = carrier_mode
+        cfg.max_epochs = max_epochs
+        cfg.tile_samples = tile_samples
+        cfg.kernel = kernel
+        self._ctx = C.c_void_p()
+        capi.check(capi.lib.gpsiq_create(C.byref(self._ctx), C.byref(cfg)))
+        self.max_chan = max_chan
+        self.samples_per_epoch = samples_per_epoch
+        self.max_epochs = max_epochs
+        self.carrier_mode = carrier_mode
+        self.device = device
+
+    # -- lifetime ---------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            capi.lib.gpsiq_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- synthesis --------------------------------------------------------
+    def _desc_array(self, desc):
+        d = np.ascontiguousarray(desc, dtype=capi.DESC_DTYPE)
+        if d.ndim == 1:
+            d = d.reshape(-1, self.max_chan)
+        if d.ndim != 2 or d.shape[1] != self.max_chan:
+            raise ValueError("descriptors must be [n_epochs][max_chan=%d]" % self.max_chan)
+        return d
+
+    def synth(self, desc, out=None, keep_on_device=False):
+        """Host buffers in, host buffers out (H2D + kernels + D2H, blocking).
+
+        desc: [n_epochs][max_chan] records of capi.DESC_DTYPE.
+        Returns int16 array [n_epochs, samples_per_epoch, 2] (I, Q)."""
+        d = self._desc_array(desc)
+        n = d.shape[0]
+        if keep_on_device:
+            capi.check(capi.lib.gpsiq_synth(self._ctx, d.ctypes.data, n, None), self._ctx)
+            return None
+        if out is None:
+            out = np.empty((n, self.samples_per_epoch, 2), np.int16)
+        assert out.dtype == np.int16 and out.size >= n * self.samples_per_epoch * 2 and out.flags.c_contiguous
+        capi.check(capi.lib.gpsiq_synth(self._ctx, d.ctypes.data, n, out.ctypes.data), self._ctx)
+        return out
+
+    def synth_ptr(self, desc_ptr, n_epochs, iq_ptr):
+        """Raw host pointers (e.g. pinned memory) -- the call bench.py times end to end."""
+        capi.check(capi.lib.gpsiq_synth(self._ctx, desc_ptr, n_epochs, iq_ptr), self._ctx)
+
+    def synth_device(self, desc_dev_ptr, n_epochs, iq_dev_ptr, stream_ptr=None):
+        """All-device, asynchronous on `stream_ptr` (a cudaStream_t as int)."""
+        capi.check(capi.lib.gpsiq_synth_device(self._ctx, desc_dev_ptr, n_epochs, iq_dev_ptr, stream_ptr), self._ctx)
+
+    def device_iq_ptr(self):
+        return capi.lib.gpsiq_device_iq(self._ctx)
+
+    def checksum_device(self, iq_dev_ptr, n_epochs):
+        sums = np.zeros(n_epochs, np.uint64)
+        capi.check(capi.lib.gpsiq_checksum_device(self._ctx, iq_dev_ptr, n_epochs, sums.ctypes.data), self._ctx)
+        return sums
+
+    # -- carrier state ----------------------------------------------------
+    @property
+    def carrier(self):
+        p = np.zeros(self.max_chan, np.float64)
+        capi.check(capi.lib.gpsiq_get_carrier(self._ctx, p.ctypes.data), self._ctx)
+        return p
+
+    @carrier.setter
+    def carrier(self, value):
+        p = np.ascontiguousarray(value, dtype=np.float64)
+        assert p.size == self.max_chan
+        capi.check(capi.lib.gpsiq_set_carrier(self._ctx, p.ctypes.data), self._ctx)
+
+    def carrier_trace(self, n_epochs):
+        t = np.zeros((n_epochs, self.max_chan), np.float64)
+        capi.check(capi.lib.gpsiq_get_carrier_trace(self._ctx, t.ctypes.data, n_epochs), self._ctx)
+        return t
+
+    # -- bookkeeping ------------------------------------------------------
+    @property
+    def launch_count(self):
+        return int(capi.lib.gpsiq_launch_count(self._ctx))
+
+    def last_timing(self):
+        a, b = C.c_float(0), C.c_float(0)
+        capi.check(capi.lib.gpsiq_last_timing(self._ctx, C.byref(a), C.byref(b)), self._ctx)
+        return a.value, b.value
+
+
+def checksum_host(iq):
+    """numpy mirror of gpsiq_checksum_device for one epoch (int16 [N,2] or [2N])."""
+    w = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1).view(np.uint32).astype(np.uint64)
+    idx = np.arange(w.size, dtype=np.uint64)
+    x = (idx << np.uint64(32)) | w
+    with np.errstate(over="ignore"):
+        x ^= x >> np.uint64(30)
+        x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(27)
+        x *= np.uint64(0x94D049BB133111EB)
+        x ^= x >> np.uint64(31)
+        return np.uint64(np.sum(x, dtype=np.uint64))

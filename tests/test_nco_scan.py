@@ -1,0 +1,79 @@
+"""The product's exact NCO fast-forward (csrc/nco_scan.cuh, run on the host via
+gpsiq_nco_advance) must equal the literal per-sample recurrences of
+plutogpssim.c:2709-2713 / 2741-2746 (oracle_*_nco) bit for bit."""
+import random
+import struct
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from pluto_gps_sim_b200 import capi
+
+
+def bits(x):
+    return struct.unpack("<q", struct.pack("<d", x))[0]
+
+
+FS = [2.6e6, 3.0e6, 10.0e6, 1.0e6]
+
+
+def test_code_nco_random():
+    rng = random.Random(1234)
+    for trial in range(120):
+        fs = rng.choice(FS)
+        f_carr = rng.uniform(-6000, 6000)
+        f_code = 1.023e6 + f_carr / 1540.0
+        step = f_code * (1.0 / fs)
+        x0 = rng.uniform(0, 1023) if trial % 5 else rng.choice([0.0, 1e-9, 0.5, 1022.999999, 511.99999999])
+        n = rng.choice([1, 2, 3, 7, 300000, 123457, 1000000])
+        want, ww = ol.oracle_code_nco(x0, step, n)
+        got, gw = capi.nco_advance(capi.NCO_CODE, x0, step, n)
+        assert bits(got) == bits(want) and gw == ww, (trial, x0, step, n)
+
+
+def test_carrier_nco_random():
+    rng = random.Random(99)
+    for trial in range(160):
+        fs = rng.choice(FS)
+        kind = trial % 4
+        if kind == 0:
+            f = rng.uniform(-6000, 6000)
+        elif kind == 1:
+            f = rng.uniform(-3, 3)
+        elif kind == 2:
+            f = rng.choice([-1, 1]) * 2.0 ** rng.randint(-8, 12)
+        else:
+            f = rng.uniform(-400, 400)
+        step = f * (1.0 / fs)
+        x0 = rng.random() if trial % 7 else rng.choice([0.0, 0.5, 0.25, 0.999999999999, 2.0 ** -30])
+        n = rng.choice([1, 2, 5, 300000, 777777, 3000000])
+        want = ol.oracle_carr_nco(x0, step, n)
+        got, _ = capi.nco_advance(capi.NCO_CARRIER, x0, step, n)
+        assert bits(got) == bits(want), (trial, x0, step, n)
+
+
+def test_carrier_nco_exact_ties_and_stuck_phase():
+    # step = (m + 1/2) ulp of [0.5,1): every add is a rounding tie
+    for m in (1, 2, 3, 1001):
+        step = (m + 0.5) * 2.0 ** -53
+        for x0 in (0.5, 0.5 + 2.0 ** -53, 0.75):
+            want = ol.oracle_carr_nco(x0, step, 100000)
+            got, _ = capi.nco_advance(capi.NCO_CARRIER, x0, step, 100000)
+            assert bits(got) == bits(want)
+    # step below half an ulp: the phase stops moving
+    got, _ = capi.nco_advance(capi.NCO_CARRIER, 0.75, 2.0 ** -60, 1000000)
+    assert got == 0.75 == ol.oracle_carr_nco(0.75, 2.0 ** -60, 1000000)
+
+
+def test_scan_matches_reference_epoch_chain():
+    """Chain the carrier scan over the golden static scenario: each epoch's end
+    phase must equal the reference's own post-loop carr_phase."""
+    meta = ol.load_golden_meta("static12")
+    desc = ol.load_golden_desc("static12")
+    n = meta["samples_per_epoch"]
+    ph = desc[0]["carr_phase0"].copy()
+    for e in range(desc.shape[0]):
+        for c in range(desc.shape[1]):
+            ph[c], _ = capi.nco_advance(capi.NCO_CARRIER, ph[c], desc[e, c]["carr_step"], n)
+            assert ph[c].hex() == meta["carr_phase_end_hex"][e][c]
