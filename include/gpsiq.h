@@ -143,11 +143,27 @@ int gpsiq_nco_advance(int mode, double *phase, double step, int64_t count, int64
 void *gpsiq_host_alloc(size_t bytes);
 void gpsiq_host_free(void *p);
 
+/* The two phases of gpsiq_synth_device, separately, for time-sliced multi-GPU
+ * runs: scan = amplitude LUTs + exact NCO state at every tile boundary (this is
+ * what advances the carrier state, so the next slice's owner can be handed the
+ * phases before the per-sample work starts); render = the per-sample synthesis
+ * from the checkpoints of the immediately preceding scan of the same batch. */
+int gpsiq_scan_device(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc_dev, int n_epochs, void *cuda_stream);
+int gpsiq_render_device(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc_dev, int n_epochs, int16_t *iq_dev,
+                        void *cuda_stream);
+/* Copy the carrier state (max_chan doubles) to / from DEVICE memory on a stream
+ * (e.g. the buffer of an NCCL send / recv). */
+int gpsiq_carrier_to_device(gpsiq_ctx *ctx, double *dst_dev, void *cuda_stream);
+int gpsiq_carrier_from_device(gpsiq_ctx *ctx, const double *src_dev, void *cuda_stream);
+
 /* Number of CUDA kernel launches issued by this context so far. */
 int64_t gpsiq_launch_count(const gpsiq_ctx *ctx);
-/* Device time (ms, CUDA events on the context's stream) spent in the synthesis
- * kernel / in all kernels of the last gpsiq_synth call. */
-int gpsiq_last_timing(const gpsiq_ctx *ctx, float *synth_kernel_ms, float *all_kernels_ms);
+/* Device-side timing (CUDA events on the launching stream).  After
+ * gpsiq_timing_begin every synth call records events around its scan phase and
+ * its synthesis kernel (up to 64 calls); gpsiq_timing_collect waits for them and
+ * returns the number of recorded calls and the summed durations in ms. */
+int gpsiq_timing_begin(gpsiq_ctx *ctx);
+int gpsiq_timing_collect(gpsiq_ctx *ctx, int *n_steps, float *scan_ms, float *synth_ms);
 
 const char *gpsiq_strerror(int status);
 const char *gpsiq_last_error(const gpsiq_ctx *ctx);

@@ -69,7 +69,12 @@ SYMBOLS = {
     "gpsiq_host_alloc": (_vp, [C.c_size_t]),
     "gpsiq_host_free": (None, [_vp]),
     "gpsiq_launch_count": (_i64, [_vp]),
-    "gpsiq_last_timing": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "gpsiq_timing_begin": (_i, [_vp]),
+    "gpsiq_timing_collect": (_i, [_vp, C.POINTER(_i), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "gpsiq_scan_device": (_i, [_vp, _vp, _i, _vp]),
+    "gpsiq_render_device": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "gpsiq_carrier_to_device": (_i, [_vp, _vp, _vp]),
+    "gpsiq_carrier_from_device": (_i, [_vp, _vp, _vp]),
     "gpsiq_strerror": (C.c_char_p, [_i]),
     "gpsiq_last_error": (C.c_char_p, [_vp]),
     "gpsiq_version": (C.c_char_p, []),

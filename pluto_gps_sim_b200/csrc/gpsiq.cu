@@ -65,11 +65,14 @@ static void ca_generate(int prn, uint8_t* chips) {
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
+#define TIMING_RING 64
+
 struct gpsiq_ctx {
     gpsiq_config cfg;
     int C, N, T, ntiles, E;
     cudaStream_t stream;
-    cudaEvent_t ev_begin, ev_synth0, ev_synth1, ev_end;
+    cudaEvent_t ev[TIMING_RING][3];  // per recorded step: begin, scans done (= synth start), synth done
+    int ev_count;                    // steps recorded since gpsiq_timing_begin
     gpsiq_chan_desc* d_desc;
     int2* d_lut;          // [E][C][512]
     double* d_code_ck;    // [E][ntiles][C]
@@ -83,7 +86,6 @@ struct gpsiq_ctx {
     int* d_err;
     int last_epochs;
     int64_t launches;
-    float synth_ms, all_ms;
     char err[256];
 };
 
@@ -430,10 +432,8 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
     ctx->ntiles = (ctx->N + ctx->T - 1) / ctx->T;
     CU(cudaSetDevice(cfg->device));
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CU(cudaEventCreate(&ctx->ev_begin));
-    CU(cudaEventCreate(&ctx->ev_synth0));
-    CU(cudaEventCreate(&ctx->ev_synth1));
-    CU(cudaEventCreate(&ctx->ev_end));
+    for (int i = 0; i < TIMING_RING; i++)
+        for (int j = 0; j < 3; j++) CU(cudaEventCreate(&ctx->ev[i][j]));
     const size_t EC = (size_t) ctx->E * ctx->C;
     const size_t ck = EC * ctx->ntiles;
     CU(cudaMalloc(&ctx->d_desc, EC * sizeof(gpsiq_chan_desc)));
@@ -472,35 +472,50 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
     cudaFree(ctx->d_desc); cudaFree(ctx->d_lut); cudaFree(ctx->d_code_ck); cudaFree(ctx->d_wrap_ck);
     cudaFree(ctx->d_carr_ck); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_carr_trace); cudaFree(ctx->d_ca);
     cudaFree(ctx->d_iq); cudaFree(ctx->d_sums); cudaFree(ctx->d_err);
-    cudaEventDestroy(ctx->ev_begin); cudaEventDestroy(ctx->ev_synth0);
-    cudaEventDestroy(ctx->ev_synth1); cudaEventDestroy(ctx->ev_end);
+    for (int i = 0; i < TIMING_RING; i++)
+        for (int j = 0; j < 3; j++) cudaEventDestroy(ctx->ev[i][j]);
     cudaStreamDestroy(ctx->stream);
     free(ctx);
 }
 
-static int enqueue(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, int16_t* iq_dev, cudaStream_t st,
-                   bool timed) {
+// Phase 1: amplitude LUTs + exact NCO checkpoints for the batch (advances the carrier state).
+static int enqueue_scan(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, cudaStream_t st) {
     const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
     const int EC = n_epochs * C;
-    if (timed) CU(cudaEventRecord(ctx->ev_begin, st));
+    if (ctx->ev_count < TIMING_RING) CU(cudaEventRecord(ctx->ev[ctx->ev_count][0], st));
     k_prepare<<<EC, 128, 0, st>>>(desc_dev, ctx->d_lut, ctx->d_err);
     k_scan_code<<<(EC + 63) / 64, 64, 0, st>>>(desc_dev, ctx->d_code_ck, ctx->d_wrap_ck, EC, C, N, T, ntiles);
     k_scan_carrier<<<1, 32, 0, st>>>(desc_dev, ctx->d_carr_ck, ctx->d_carr_state, ctx->d_carr_trace, n_epochs, C, N, T,
                                      ntiles, ctx->cfg.carrier_mode);
-    if (timed) CU(cudaEventRecord(ctx->ev_synth0, st));
+    ctx->launches += 3;
+    ctx->last_epochs = n_epochs;
+    CU(cudaGetLastError());
+    return GPSIQ_OK;
+}
+
+// Phase 2: the per-sample synthesis from the checkpoints of the last scan.
+static int enqueue_render(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, int16_t* iq_dev,
+                          cudaStream_t st) {
+    const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
+    if (ctx->ev_count < TIMING_RING) CU(cudaEventRecord(ctx->ev[ctx->ev_count][1], st));
     const int tile_groups = (ntiles + LANES_WARPS - 1) / LANES_WARPS;
     const size_t smem = (size_t) C * 512 * sizeof(int2) + (size_t) C * 33 * 4;
     k_synth_lanes<<<n_epochs * tile_groups, LANES_WARPS * 32, smem, st>>>(
         desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, ctx->d_carr_ck, ctx->d_ca, iq_dev, C, N, T, ntiles,
         tile_groups, ctx->cfg.carrier_mode);
-    if (timed) {
-        CU(cudaEventRecord(ctx->ev_synth1, st));
-        CU(cudaEventRecord(ctx->ev_end, st));
+    if (ctx->ev_count < TIMING_RING) {
+        CU(cudaEventRecord(ctx->ev[ctx->ev_count][2], st));
+        ctx->ev_count++;
     }
-    ctx->launches += 4;
-    ctx->last_epochs = n_epochs;
+    ctx->launches += 1;
     CU(cudaGetLastError());
     return GPSIQ_OK;
+}
+
+static int enqueue(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, int16_t* iq_dev, cudaStream_t st) {
+    int rc = enqueue_scan(ctx, desc_dev, n_epochs, st);
+    if (rc) return rc;
+    return enqueue_render(ctx, desc_dev, n_epochs, iq_dev, st);
 }
 
 static int check_device_error(gpsiq_ctx* ctx) {
@@ -521,15 +536,11 @@ int gpsiq_synth(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc, int n_epochs, int16
     CU(cudaSetDevice(ctx->cfg.device));
     CU(cudaMemcpyAsync(ctx->d_desc, desc, (size_t) n_epochs * ctx->C * sizeof(gpsiq_chan_desc), cudaMemcpyHostToDevice,
                        ctx->stream));
-    int rc = enqueue(ctx, ctx->d_desc, n_epochs, ctx->d_iq, ctx->stream, true);
+    int rc = enqueue(ctx, ctx->d_desc, n_epochs, ctx->d_iq, ctx->stream);
     if (rc) return rc;
     if (iq_out)
         CU(cudaMemcpyAsync(iq_out, ctx->d_iq, (size_t) n_epochs * ctx->N * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    rc = check_device_error(ctx);
-    if (rc) return rc;
-    CU(cudaEventElapsedTime(&ctx->synth_ms, ctx->ev_synth0, ctx->ev_synth1));
-    CU(cudaEventElapsedTime(&ctx->all_ms, ctx->ev_begin, ctx->ev_end));
-    return GPSIQ_OK;
+    return check_device_error(ctx);
 }
 
 int gpsiq_synth_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, int16_t* iq_dev, void* stream) {
@@ -537,7 +548,38 @@ int gpsiq_synth_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_ep
         return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_synth_device: bad argument", cudaSuccess);
     if (n_epochs > ctx->E) return fail(ctx, GPSIQ_ERR_CAPACITY, "gpsiq_synth_device: n_epochs > max_epochs", cudaSuccess);
     CU(cudaSetDevice(ctx->cfg.device));
-    return enqueue(ctx, desc_dev, n_epochs, iq_dev, stream ? (cudaStream_t) stream : ctx->stream, false);
+    return enqueue(ctx, desc_dev, n_epochs, iq_dev, stream ? (cudaStream_t) stream : ctx->stream);
+}
+
+int gpsiq_scan_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, void* stream) {
+    if (!ctx || !desc_dev || n_epochs < 1) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_scan_device: bad argument", cudaSuccess);
+    if (n_epochs > ctx->E) return fail(ctx, GPSIQ_ERR_CAPACITY, "gpsiq_scan_device: n_epochs > max_epochs", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    return enqueue_scan(ctx, desc_dev, n_epochs, stream ? (cudaStream_t) stream : ctx->stream);
+}
+
+int gpsiq_render_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, int16_t* iq_dev, void* stream) {
+    if (!ctx || !desc_dev || !iq_dev || n_epochs < 1 || n_epochs != ctx->last_epochs || ((uintptr_t) iq_dev & 15))
+        return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_render_device: bad argument (must follow gpsiq_scan_device of the same batch)",
+                    cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    return enqueue_render(ctx, desc_dev, n_epochs, iq_dev, stream ? (cudaStream_t) stream : ctx->stream);
+}
+
+int gpsiq_carrier_to_device(gpsiq_ctx* ctx, double* dst_dev, void* stream) {
+    if (!ctx || !dst_dev) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_carrier_to_device: bad argument", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaMemcpyAsync(dst_dev, ctx->d_carr_state, ctx->C * sizeof(double), cudaMemcpyDeviceToDevice,
+                       stream ? (cudaStream_t) stream : ctx->stream));
+    return GPSIQ_OK;
+}
+
+int gpsiq_carrier_from_device(gpsiq_ctx* ctx, const double* src_dev, void* stream) {
+    if (!ctx || !src_dev) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_carrier_from_device: bad argument", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaMemcpyAsync(ctx->d_carr_state, src_dev, ctx->C * sizeof(double), cudaMemcpyDeviceToDevice,
+                       stream ? (cudaStream_t) stream : ctx->stream));
+    return GPSIQ_OK;
 }
 
 int gpsiq_get_carrier(gpsiq_ctx* ctx, double* p) {
@@ -584,10 +626,27 @@ int gpsiq_checksum_device(gpsiq_ctx* ctx, const int16_t* iq_dev, int n_epochs, u
 
 int64_t gpsiq_launch_count(const gpsiq_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-int gpsiq_last_timing(const gpsiq_ctx* ctx, float* synth_ms, float* all_ms) {
+int gpsiq_timing_begin(gpsiq_ctx* ctx) {
     if (!ctx) return GPSIQ_ERR_ARG;
-    if (synth_ms) *synth_ms = ctx->synth_ms;
-    if (all_ms) *all_ms = ctx->all_ms;
+    ctx->ev_count = 0;
+    return GPSIQ_OK;
+}
+
+int gpsiq_timing_collect(gpsiq_ctx* ctx, int* n_steps, float* scan_ms, float* synth_ms) {
+    if (!ctx) return GPSIQ_ERR_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < ctx->ev_count; i++) {
+        float t = 0.f;
+        CU(cudaEventSynchronize(ctx->ev[i][2]));
+        CU(cudaEventElapsedTime(&t, ctx->ev[i][0], ctx->ev[i][1]));
+        a += t;
+        CU(cudaEventElapsedTime(&t, ctx->ev[i][1], ctx->ev[i][2]));
+        b += t;
+    }
+    if (n_steps) *n_steps = ctx->ev_count;
+    if (scan_ms) *scan_ms = a;
+    if (synth_ms) *synth_ms = b;
     return GPSIQ_OK;
 }
 

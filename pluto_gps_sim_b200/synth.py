@@ -116,10 +116,27 @@ class Synthesizer:
     def launch_count(self):
         return int(capi.lib.gpsiq_launch_count(self._ctx))
 
-    def last_timing(self):
-        a, b = C.c_float(0), C.c_float(0)
-        capi.check(capi.lib.gpsiq_last_timing(self._ctx, C.byref(a), C.byref(b)), self._ctx)
-        return a.value, b.value
+    def timing_begin(self):
+        capi.check(capi.lib.gpsiq_timing_begin(self._ctx), self._ctx)
+
+    def timing_collect(self):
+        """-> (recorded calls, scan-phase ms, synthesis-kernel ms), CUDA events on the launching stream."""
+        n, a, b = C.c_int(0), C.c_float(0), C.c_float(0)
+        capi.check(capi.lib.gpsiq_timing_collect(self._ctx, C.byref(n), C.byref(a), C.byref(b)), self._ctx)
+        return n.value, a.value, b.value
+
+    # -- time-slice phases (multi-GPU) --------------------------------------
+    def scan_device(self, desc_dev_ptr, n_epochs, stream_ptr=None):
+        capi.check(capi.lib.gpsiq_scan_device(self._ctx, desc_dev_ptr, n_epochs, stream_ptr), self._ctx)
+
+    def render_device(self, desc_dev_ptr, n_epochs, iq_dev_ptr, stream_ptr=None):
+        capi.check(capi.lib.gpsiq_render_device(self._ctx, desc_dev_ptr, n_epochs, iq_dev_ptr, stream_ptr), self._ctx)
+
+    def carrier_to_device(self, dst_dev_ptr, stream_ptr=None):
+        capi.check(capi.lib.gpsiq_carrier_to_device(self._ctx, dst_dev_ptr, stream_ptr), self._ctx)
+
+    def carrier_from_device(self, src_dev_ptr, stream_ptr=None):
+        capi.check(capi.lib.gpsiq_carrier_from_device(self._ctx, src_dev_ptr, stream_ptr), self._ctx)
 
 
 def checksum_host(iq):

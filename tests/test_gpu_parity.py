@@ -1,0 +1,147 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called
+through the C-ABI, against the oracle and the committed reference goldens."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from pluto_gps_sim_b200 import Synthesizer, capi, checksum_host
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = [capi.KERNEL_LANE_PER_CHANNEL]
+
+
+def first_diff(a, b):
+    bad = np.argwhere(a != b)
+    return None if len(bad) == 0 else tuple(bad[0])
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_config1_static12_bit_exact_vs_reference_golden(kernel):
+    """BASELINE config[1] == config[0]: 1 s, 12 channels, 2.6 MS/s."""
+    meta = ol.load_golden_meta("static12")
+    desc = ol.load_golden_desc("static12")
+    with Synthesizer(max_chan=12, max_epochs=10, kernel=kernel) as s:
+        iq = s.synth(desc)
+        trace = s.carrier_trace(10)
+        assert s.launch_count >= 4
+    assert ol.sha256(iq) == meta["iq_sha256"], first_diff(iq, ol.oracle_synth(desc, 300000)[0])
+    want = np.array([[float.fromhex(h) for h in row] for row in meta["carr_phase_end_hex"]])
+    assert np.array_equal(trace, want)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_config3_allsky32_bit_exact_vs_reference_golden(kernel):
+    meta = ol.load_golden_meta("allsky32")
+    desc = ol.load_golden_desc("allsky32")
+    with Synthesizer(max_chan=32, max_epochs=20, kernel=kernel) as s:
+        iq = s.synth(desc)
+    assert ol.sha256(iq) == meta["iq_sha256"], first_diff(iq, ol.oracle_synth(desc, 300000)[0])
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_config2_circle_310_epochs_batched_with_carry(kernel):
+    """User motion, 310 epochs across the 30 s refresh, in uneven batches: the
+    carrier phase must carry between calls like chan[i].carr_phase does."""
+    meta = ol.load_golden_meta("circle12")
+    desc = ol.load_golden_desc("circle12")
+    sums = []
+    with Synthesizer(max_chan=12, max_epochs=128, kernel=kernel) as s:
+        e = 0
+        for n in (1, 7, 128, 100, 74):
+            s.synth(desc[e:e + n], keep_on_device=True)
+            sums += [int(x) for x in s.checksum_device(s.device_iq_ptr(), n)]
+            e += n
+    assert e == 310
+    assert sums == meta["epoch_checksums"]
+
+
+@pytest.mark.parametrize("tile", [32, 96, 1024, 4096, 300000])
+def test_tile_size_independence(tile):
+    desc = ol.load_golden_desc("static12")[:2]
+    want, _ = ol.oracle_synth(desc, 50000)
+    with Synthesizer(max_chan=12, samples_per_epoch=50000, max_epochs=2, tile_samples=tile) as s:
+        got = s.synth(desc)
+    assert first_diff(got, want) is None
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 1000, 4097])
+def test_ragged_epoch_lengths(n):
+    desc = ol.load_golden_desc("allsky32")[:3]
+    want, _ = ol.oracle_synth(desc, n)
+    with Synthesizer(max_chan=32, samples_per_epoch=n, max_epochs=3) as s:
+        got = s.synth(desc)
+    assert first_diff(got, want) is None
+
+
+def test_inactive_slots_and_empty_epoch():
+    desc = ol.load_golden_desc("static12")[:2].copy()
+    desc[0, 3]["prn"] = 0
+    desc[1, :]["prn"] = 0          # an epoch with no satellites: all-zero I/Q
+    want, _ = ol.oracle_synth(desc, 20000)
+    with Synthesizer(max_chan=12, samples_per_epoch=20000, max_epochs=2) as s:
+        got = s.synth(desc)
+    assert first_diff(got, want) is None
+    assert not got[1].any()
+
+
+def test_integer_carrier_mode_vs_oracle():
+    """The reference's compiled-out uint32 carrier (plutogpssim.c:2699, 2748)."""
+    dump = np.load(os.path.join(ol.GOLDEN, "static12_dump.npy"))[:3]
+    desc = np.zeros(dump.shape, capi.DESC_DTYPE)
+    for e in range(dump.shape[0]):
+        for c in range(dump.shape[1]):
+            r = dump[e, c]
+            ph = float(np.uint32(512.0 * 65536.0 * r["carr_phase"]))     # plutogpssim.c:1967
+            desc[e, c] = capi.make_desc(capi.CARRIER_INT32, r["prn"], r["f_carr"], r["f_code"], r["delt"], ph,
+                                        r["code_phase"], r["dwrd"].astype(np.uint64), r["iword"], r["ibit"],
+                                        r["icode"], r["gain"], e == 0)
+    want, wt = ol.oracle_synth(desc, 100000, carrier_mode=1)
+    with Synthesizer(max_chan=12, samples_per_epoch=100000, max_epochs=3, carrier_mode=capi.CARRIER_INT32) as s:
+        got = s.synth(desc)
+        gt = s.carrier_trace(3)
+    assert first_diff(got, want) is None
+    assert np.array_equal(gt, wt)
+
+
+def test_set_get_carrier_handoff():
+    """Time-slice hand-off: synthesizing epochs [5,10) on a fresh context seeded
+    with the carrier phases after epoch 4 equals the second half of one run."""
+    meta = ol.load_golden_meta("static12")
+    desc = ol.load_golden_desc("static12")
+    with Synthesizer(max_chan=12, max_epochs=10) as a:
+        a.synth(desc[:5], keep_on_device=True)
+        ph = a.carrier
+    with Synthesizer(max_chan=12, max_epochs=10) as b:
+        b.carrier = ph
+        iq = b.synth(desc[5:])
+    assert [int(checksum_host(iq[e])) for e in range(5)] == meta["epoch_checksums"][5:]
+
+
+def test_out_of_contract_descriptor_is_rejected():
+    desc = ol.load_golden_desc("static12")[:1].copy()
+    desc[0, 2]["code_phase0"] = 2000.0
+    with Synthesizer(max_chan=12, samples_per_epoch=1000, max_epochs=1) as s:
+        with pytest.raises(capi.GpsiqError) as ei:
+            s.synth(desc)
+        assert ei.value.status == capi.ERR_ARG
+    with Synthesizer(max_chan=12, samples_per_epoch=1000, max_epochs=1) as s:
+        with pytest.raises(capi.GpsiqError) as ei:
+            s.synth(ol.load_golden_desc("static12")[:2])
+        assert ei.value.status == capi.ERR_CAPACITY
+
+
+def test_device_path_with_torch_buffers():
+    import torch
+
+    meta = ol.load_golden_meta("static12")
+    desc = ol.load_golden_desc("static12")
+    d = torch.from_numpy(desc.view(np.uint8).reshape(-1).copy()).cuda()
+    out = torch.empty(10 * 300000 * 2, dtype=torch.int16, device="cuda")
+    with Synthesizer(max_chan=12, max_epochs=10) as s:
+        st = torch.cuda.current_stream().cuda_stream
+        s.synth_device(d.data_ptr(), 10, out.data_ptr(), st)
+        torch.cuda.synchronize()
+    assert ol.sha256(out.cpu().numpy()) == meta["iq_sha256"]
