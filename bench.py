@@ -199,6 +199,8 @@ def ours_arm(args):
     d_first = torch.from_numpy(first.view(np.uint8).reshape(-1)).cuda()
     d_desc = torch.from_numpy(desc.view(np.uint8).reshape(-1)).cuda()
     d_out = torch.empty(samples_per_step * 2, dtype=torch.int16, device="cuda")
+    stream = torch.cuda.Stream()                 # everything below is enqueued on this stream
+    torch.cuda.set_stream(stream)
     engine = GpuSliceEngine(synth)
     runner = TimeSliceRunner(engine, rank, world)
 

@@ -100,8 +100,8 @@ void gpsiq_destroy(gpsiq_ctx *ctx);
 int gpsiq_synth(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc, int n_epochs, int16_t *iq_out);
 
 /* Same, all-device and asynchronous: desc_dev and iq_dev are DEVICE pointers
- * (iq_dev 16-byte aligned), work is enqueued on cuda_stream (a cudaStream_t;
- * NULL = the context's own stream) and the call returns without waiting. */
+ * (iq_dev 16-byte aligned), work is enqueued on cuda_stream (a cudaStream_t, used
+ * as given: NULL is the CUDA default stream) and the call returns without waiting. */
 int gpsiq_synth_device(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc_dev, int n_epochs, int16_t *iq_dev,
                        void *cuda_stream);
 

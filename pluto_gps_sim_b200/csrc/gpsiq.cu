@@ -132,8 +132,10 @@ __global__ void k_prepare(const gpsiq_chan_desc* __restrict__ desc, int2* __rest
 // ---------------------------------------------------------------------------
 __global__ void k_scan_code(const gpsiq_chan_desc* __restrict__ desc, double* __restrict__ code_ck,
                             int* __restrict__ wrap_ck, int EC, int C, int N, int T, int ntiles) {
-    const int ec = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ec >= EC) return;
+    // one chain per warp, lane 0 only: the scan is branchy and data dependent,
+    // chains sharing a warp would serialise each other's paths
+    const int ec = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ec >= EC || (threadIdx.x & 31)) return;
     const int e = ec / C, c = ec - e * C;
     const gpsiq_chan_desc d = desc[ec];
     if (d.prn <= 0) return;
@@ -154,8 +156,8 @@ __global__ void k_scan_code(const gpsiq_chan_desc* __restrict__ desc, double* __
 __global__ void k_scan_carrier(const gpsiq_chan_desc* __restrict__ desc, double* __restrict__ carr_ck,
                                double* __restrict__ carr_state, double* __restrict__ carr_trace, int E, int C, int N,
                                int T, int ntiles, int carrier_mode) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one chain per warp, lane 0
+    if (c >= C || (threadIdx.x & 31)) return;
     double x = carr_state[c];
     uint32_t u = (uint32_t) x;
     int dummy = 0;
@@ -484,8 +486,8 @@ static int enqueue_scan(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_e
     const int EC = n_epochs * C;
     if (ctx->ev_count < TIMING_RING) CU(cudaEventRecord(ctx->ev[ctx->ev_count][0], st));
     k_prepare<<<EC, 128, 0, st>>>(desc_dev, ctx->d_lut, ctx->d_err);
-    k_scan_code<<<(EC + 63) / 64, 64, 0, st>>>(desc_dev, ctx->d_code_ck, ctx->d_wrap_ck, EC, C, N, T, ntiles);
-    k_scan_carrier<<<1, 32, 0, st>>>(desc_dev, ctx->d_carr_ck, ctx->d_carr_state, ctx->d_carr_trace, n_epochs, C, N, T,
+    k_scan_code<<<(EC + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_code_ck, ctx->d_wrap_ck, EC, C, N, T, ntiles);
+    k_scan_carrier<<<C, 32, 0, st>>>(desc_dev, ctx->d_carr_ck, ctx->d_carr_state, ctx->d_carr_trace, n_epochs, C, N, T,
                                      ntiles, ctx->cfg.carrier_mode);
     ctx->launches += 3;
     ctx->last_epochs = n_epochs;
@@ -548,14 +550,14 @@ int gpsiq_synth_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_ep
         return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_synth_device: bad argument", cudaSuccess);
     if (n_epochs > ctx->E) return fail(ctx, GPSIQ_ERR_CAPACITY, "gpsiq_synth_device: n_epochs > max_epochs", cudaSuccess);
     CU(cudaSetDevice(ctx->cfg.device));
-    return enqueue(ctx, desc_dev, n_epochs, iq_dev, stream ? (cudaStream_t) stream : ctx->stream);
+    return enqueue(ctx, desc_dev, n_epochs, iq_dev, (cudaStream_t) stream);
 }
 
 int gpsiq_scan_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, void* stream) {
     if (!ctx || !desc_dev || n_epochs < 1) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_scan_device: bad argument", cudaSuccess);
     if (n_epochs > ctx->E) return fail(ctx, GPSIQ_ERR_CAPACITY, "gpsiq_scan_device: n_epochs > max_epochs", cudaSuccess);
     CU(cudaSetDevice(ctx->cfg.device));
-    return enqueue_scan(ctx, desc_dev, n_epochs, stream ? (cudaStream_t) stream : ctx->stream);
+    return enqueue_scan(ctx, desc_dev, n_epochs, (cudaStream_t) stream);
 }
 
 int gpsiq_render_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, int16_t* iq_dev, void* stream) {
@@ -563,14 +565,14 @@ int gpsiq_render_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_e
         return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_render_device: bad argument (must follow gpsiq_scan_device of the same batch)",
                     cudaSuccess);
     CU(cudaSetDevice(ctx->cfg.device));
-    return enqueue_render(ctx, desc_dev, n_epochs, iq_dev, stream ? (cudaStream_t) stream : ctx->stream);
+    return enqueue_render(ctx, desc_dev, n_epochs, iq_dev, (cudaStream_t) stream);
 }
 
 int gpsiq_carrier_to_device(gpsiq_ctx* ctx, double* dst_dev, void* stream) {
     if (!ctx || !dst_dev) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_carrier_to_device: bad argument", cudaSuccess);
     CU(cudaSetDevice(ctx->cfg.device));
     CU(cudaMemcpyAsync(dst_dev, ctx->d_carr_state, ctx->C * sizeof(double), cudaMemcpyDeviceToDevice,
-                       stream ? (cudaStream_t) stream : ctx->stream));
+                       (cudaStream_t) stream));
     return GPSIQ_OK;
 }
 
@@ -578,7 +580,7 @@ int gpsiq_carrier_from_device(gpsiq_ctx* ctx, const double* src_dev, void* strea
     if (!ctx || !src_dev) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_carrier_from_device: bad argument", cudaSuccess);
     CU(cudaSetDevice(ctx->cfg.device));
     CU(cudaMemcpyAsync(ctx->d_carr_state, src_dev, ctx->C * sizeof(double), cudaMemcpyDeviceToDevice,
-                       stream ? (cudaStream_t) stream : ctx->stream));
+                       (cudaStream_t) stream));
     return GPSIQ_OK;
 }
 
