@@ -81,7 +81,7 @@ typedef struct gpsiq_config {
     int32_t max_epochs;        /* capacity of one gpsiq_synth call */
     int32_t tile_samples;      /* 0 = default; checkpoint / CTA tile length */
     int32_t kernel;            /* GPSIQ_KERNEL_* */
-    int32_t reserved[9];
+    int32_t reserved[9];       /* reserved[0]: 1 = serial carrier scan (cross-check of the parallel one); rest 0 */
 } gpsiq_config;
 
 typedef struct gpsiq_ctx gpsiq_ctx;
@@ -139,6 +139,15 @@ int gpsiq_make_desc(gpsiq_chan_desc *out, int carrier_mode, int prn, double f_ca
  * recurrence and adds the number of code wraps to *wraps.  Diagnostic / test aid. */
 int gpsiq_nco_advance(int mode, double *phase, double step, int64_t count, int64_t *wraps);
 
+/* Host execution of the parallel carrier scan (speculate / translate / verify,
+ * csrc/nco_scan.cuh) for one channel over n_epochs epochs with per-epoch steps:
+ * writes the exact phase at every tile start ([n_epochs][ceil(N/T)]), the final
+ * phase and the number of epochs that fell back to the serial scan.  est_err is
+ * added to the start-phase estimate of every epoch (0 = what the device does) so
+ * tests can force both the translated and the fallback path.  Diagnostic aid. */
+int gpsiq_carrier_chain_host(const double *steps, int n_epochs, int N, int T, double x0, double est_err,
+                             double *ck_out, double *x_end_out, int *n_fallback);
+
 /* Pinned host memory for descriptors / I/Q (cudaHostAlloc). */
 void *gpsiq_host_alloc(size_t bytes);
 void gpsiq_host_free(void *p);
@@ -158,6 +167,8 @@ int gpsiq_carrier_from_device(gpsiq_ctx *ctx, const double *src_dev, void *cuda_
 
 /* Number of CUDA kernel launches issued by this context so far. */
 int64_t gpsiq_launch_count(const gpsiq_ctx *ctx);
+/* (epoch, slot) pairs whose carrier scan fell back to the serial path so far. */
+int gpsiq_carrier_fallbacks(gpsiq_ctx *ctx, int64_t *count);
 /* Device-side timing (CUDA events on the launching stream).  After
  * gpsiq_timing_begin every synth call records events around its scan phase and
  * its synthesis kernel (up to 64 calls); gpsiq_timing_collect waits for them and

@@ -66,9 +66,11 @@ SYMBOLS = {
     "gpsiq_checksum_device": (_i, [_vp, _vp, _i, _vp]),
     "gpsiq_make_desc": (_i, [_vp, _i, _i, _d, _d, _d, _d, _d, _vp, _i, _i, _i, _d, _i]),
     "gpsiq_nco_advance": (_i, [_i, C.POINTER(_d), _d, _i64, C.POINTER(_i64)]),
+    "gpsiq_carrier_chain_host": (_i, [_vp, _i, _i, _i, _d, _d, _vp, C.POINTER(_d), C.POINTER(_i)]),
     "gpsiq_host_alloc": (_vp, [C.c_size_t]),
     "gpsiq_host_free": (None, [_vp]),
     "gpsiq_launch_count": (_i64, [_vp]),
+    "gpsiq_carrier_fallbacks": (_i, [_vp, C.POINTER(_i64)]),
     "gpsiq_timing_begin": (_i, [_vp]),
     "gpsiq_timing_collect": (_i, [_vp, C.POINTER(_i), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "gpsiq_scan_device": (_i, [_vp, _vp, _i, _vp]),
@@ -135,6 +137,17 @@ def nco_advance(mode, phase, step, count):
     w = _i64(0)
     check(lib.gpsiq_nco_advance(int(mode), C.byref(x), float(step), int(count), C.byref(w)))
     return x.value, w.value
+
+
+def carrier_chain_host(steps, N, T, x0, est_err=0.0):
+    """Host run of the speculate/translate/verify carrier scan -> (ck [E][ntiles], x_end, n_fallback)."""
+    st = np.ascontiguousarray(steps, dtype=np.float64)
+    ntiles = (N + T - 1) // T
+    ck = np.zeros((st.size, ntiles), np.float64)
+    xe, fb = _d(0), _i(0)
+    check(lib.gpsiq_carrier_chain_host(st.ctypes.data, st.size, N, T, float(x0), float(est_err), ck.ctypes.data,
+                                       C.byref(xe), C.byref(fb)))
+    return ck, xe.value, fb.value
 
 
 def make_desc(carrier_mode, prn, f_carr, f_code, delt, carr_phase, code_phase, dwrd60, iword, ibit, icode, gain,

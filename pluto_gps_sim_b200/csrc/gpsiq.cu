@@ -77,7 +77,11 @@ struct gpsiq_ctx {
     int2* d_lut;          // [E][C][512]
     double* d_code_ck;    // [E][ntiles][C]
     int* d_wrap_ck;       // [E][ntiles][C]
-    double* d_carr_ck;    // [E][ntiles][C]   (INT32 mode: uint32 phase as double)
+    double* d_carr_ck;    // [2][E][ntiles][C] two speculation planes (INT32 mode: uint32 phase as double, plane 0)
+    CarrSpec* d_spec;     // [E][C][2]
+    CarrInfo* d_info;     // [E][C]
+    int* d_fallbacks;     // epochs that fell back to the serial carrier scan (diagnostic counter)
+    size_t ck_plane;      // elements per plane
     double* d_carr_state; // [C]
     double* d_carr_trace; // [E][C]
     uint32_t* d_ca;       // [33][CA_WORDS]
@@ -154,8 +158,8 @@ __global__ void k_scan_code(const gpsiq_chan_desc* __restrict__ desc, double* __
 // k_scan_carrier: exact carrier phase at every tile start, chained over epochs
 // ---------------------------------------------------------------------------
 __global__ void k_scan_carrier(const gpsiq_chan_desc* __restrict__ desc, double* __restrict__ carr_ck,
-                               double* __restrict__ carr_state, double* __restrict__ carr_trace, int E, int C, int N,
-                               int T, int ntiles, int carrier_mode) {
+                               double* __restrict__ carr_state, double* __restrict__ carr_trace,
+                               CarrInfo* __restrict__ info, int E, int C, int N, int T, int ntiles, int carrier_mode) {
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one chain per warp, lane 0
     if (c >= C || (threadIdx.x & 31)) return;
     double x = carr_state[c];
@@ -170,6 +174,10 @@ __global__ void k_scan_carrier(const gpsiq_chan_desc* __restrict__ desc, double*
         if (d.flags & GPSIQ_FLAG_RESET_CARRIER) {
             x = d.carr_phase0;
             u = (uint32_t) d.carr_phase0;
+        }
+        {
+            CarrInfo inf; inf.delta = 0.0; inf.n1 = N; inf.variant = 0;  // every tile reads the exact plane 0
+            info[(size_t) e * C + c] = inf;
         }
         if (carrier_mode == GPSIQ_CARRIER_FLOAT) {
             for (int t = 0; t < ntiles; t++) {
@@ -189,6 +197,67 @@ __global__ void k_scan_carrier(const gpsiq_chan_desc* __restrict__ desc, double*
     carr_state[c] = (carrier_mode == GPSIQ_CARRIER_FLOAT) ? x : (double) u;
 }
 
+
+// ---------------------------------------------------------------------------
+// Parallel carrier scan (FLOAT mode), see nco_scan.cuh "speculate -> translate -> verify".
+// k_carr_speculate: one chain per (epoch, slot, parity variant), all independent.
+// k_carr_chain    : one chain per slot, serial over epochs, O(one carrier cycle) per epoch.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double est_advance_dev(double x, double d, int N) {
+    double t = fma((double) N, d, x);
+    t -= floor(t);
+    return (t >= 0.0 && t < 1.0) ? t : 0.0;
+}
+
+__global__ void k_carr_speculate(const gpsiq_chan_desc* __restrict__ desc, const double* __restrict__ carr_state,
+                                 double* __restrict__ carr_ck, size_t ck_plane, CarrSpec* __restrict__ spec, int E,
+                                 int C, int N, int T, int ntiles) {
+    const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (chain >= E * C * 2 || (threadIdx.x & 31)) return;
+    const int v = chain & 1, ec = chain >> 1;
+    const int e = ec / C, c = ec - e * C;
+    const gpsiq_chan_desc d = desc[ec];
+    CarrSpec out;
+    out.margin = -1.0; out.n1 = -1; out.xw1 = 0.0; out.xend = 0.0; out.pad = 0;
+    if (d.prn > 0 && !(v == 1 && d.carr_step >= 0.0) && carr_step_speculable(d.carr_step)) {
+        // estimated start phase: chain the batch's epochs in closed form (one rounding per epoch)
+        double x = carr_state[c];
+        for (int k = 0; k < e; k++) {
+            const gpsiq_chan_desc* dk = desc + (size_t) k * C + c;
+            if (dk->prn <= 0) continue;
+            if (dk->flags & GPSIQ_FLAG_RESET_CARRIER) x = dk->carr_phase0;
+            x = est_advance_dev(x, dk->carr_step, N);
+        }
+        if (d.flags & GPSIQ_FLAG_RESET_CARRIER) x = d.carr_phase0;
+        spec_scan_epoch(x, d.carr_step, N, T, v, carr_ck + (size_t) v * ck_plane + (size_t) e * ntiles * C + c,
+                        (size_t) C, out);
+    }
+    spec[(size_t) ec * 2 + v] = out;
+}
+
+__global__ void k_carr_chain(const gpsiq_chan_desc* __restrict__ desc, const CarrSpec* __restrict__ spec,
+                             double* __restrict__ carr_ck, double* __restrict__ carr_state,
+                             double* __restrict__ carr_trace, CarrInfo* __restrict__ info, int* __restrict__ fallbacks,
+                             int E, int C, int N, int T, int ntiles) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= C || (threadIdx.x & 31)) return;
+    double x = carr_state[c];
+    int fb = 0;
+    for (int e = 0; e < E; e++) {
+        const size_t ec = (size_t) e * C + c;
+        const gpsiq_chan_desc d = desc[ec];
+        if (d.prn <= 0) { carr_trace[ec] = x; continue; }
+        if (d.flags & GPSIQ_FLAG_RESET_CARRIER) x = d.carr_phase0;
+        CarrInfo inf;
+        x = chain_epoch(x, d.carr_step, N, T, spec[ec * 2], spec[ec * 2 + 1], carr_ck + (size_t) e * ntiles * C + c,
+                        (size_t) C, inf, fb);
+        info[ec] = inf;
+        carr_trace[ec] = x;
+    }
+    carr_state[c] = x;
+    if (fb) atomicAdd(fallbacks, fb);
+}
+
 // ---------------------------------------------------------------------------
 // k_synth_lanes: warp = one tile of samples, lane = channel slot.
 // Executes the very IEEE additions the reference executes, starting from the
@@ -201,7 +270,8 @@ __global__ void k_scan_carrier(const gpsiq_chan_desc* __restrict__ desc, double*
 __global__ void __launch_bounds__(LANES_WARPS * 32)
 k_synth_lanes(const gpsiq_chan_desc* __restrict__ desc, const int2* __restrict__ lut,
               const double* __restrict__ code_ck, const int* __restrict__ wrap_ck,
-              const double* __restrict__ carr_ck, const uint32_t* __restrict__ ca, int16_t* __restrict__ iq,
+              const double* __restrict__ carr_ck, size_t ck_plane, const CarrInfo* __restrict__ info,
+              const uint32_t* __restrict__ ca, int16_t* __restrict__ iq,
               int C, int N, int T, int ntiles, int tile_groups, int carrier_mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int2* s_lut = reinterpret_cast<int2*>(smem_raw);                       // [C][512]
@@ -237,7 +307,9 @@ k_synth_lanes(const gpsiq_chan_desc* __restrict__ desc, const int2* __restrict__
         const int w = wrap_ck[o] + d.ms0 % 20;
         kbit = w / 20;
         icode = w - kbit * 20;
-        ph = carr_ck[o];
+        const CarrInfo inf = info[(size_t) e * C + lane];
+        if (n0 < inf.n1 || inf.n1 >= N) ph = carr_ck[o];                               // exact plane
+        else ph = __dadd_rn(carr_ck[(size_t) inf.variant * ck_plane + o], inf.delta);  // speculative plane, translated
         uph = (uint32_t) ph;
         cstep = d.code_step;
         pstep = d.carr_step;
@@ -395,6 +467,46 @@ int gpsiq_nco_advance(int mode, double* phase, double step, int64_t count, int64
     return GPSIQ_OK;
 }
 
+// Estimated start phase of epoch e for the speculative scan: the previous
+// state advanced by N*step in one rounding (no per-sample drift).
+static inline double est_advance(double x, double d, int N) {
+    double t = fma((double) N, d, x);
+    t -= floor(t);
+    return (t >= 0.0 && t < 1.0) ? t : 0.0;
+}
+
+int gpsiq_carrier_chain_host(const double* steps, int n_epochs, int N, int T, double x0, double est_err, double* ck_out,
+                             double* x_end_out, int* n_fallback) {
+    if (!steps || !ck_out || n_epochs < 1 || N < 1 || T < 1) return GPSIQ_ERR_ARG;
+    const int ntiles = (N + T - 1) / T;
+    double* plane[2];
+    plane[0] = (double*) malloc(sizeof(double) * ntiles * 2);
+    if (!plane[0]) return GPSIQ_ERR_NOMEM;
+    plane[1] = plane[0] + ntiles;
+    double x = x0, xe = x0;
+    int fb = 0;
+    for (int e = 0; e < n_epochs; e++) {
+        const double d = steps[e];
+        CarrSpec s0, s1;
+        s1.margin = -1.0; s1.n1 = -1; s1.xw1 = 0; s1.xend = 0;
+        double est = xe + est_err;                       // what the device would guess, plus injected error
+        est -= floor(est);
+        spec_scan_epoch(est, d, N, T, 0, plane[0], 1, s0);
+        if (d < 0.0) spec_scan_epoch(est, d, N, T, 1, plane[1], 1, s1);
+        CarrInfo info;
+        x = chain_epoch(x, d, N, T, s0, s1, plane[0], 1, info, fb);
+        for (int t = 0; t < ntiles; t++) {
+            const bool exact = (t * T < info.n1) || info.n1 >= N;
+            ck_out[(size_t) e * ntiles + t] = exact ? plane[0][t] : plane[info.variant][t] + info.delta;
+        }
+        xe = est_advance(xe, d, N);
+    }
+    free(plane[0]);
+    if (x_end_out) *x_end_out = x;
+    if (n_fallback) *n_fallback = fb;
+    return GPSIQ_OK;
+}
+
 void* gpsiq_host_alloc(size_t bytes) {
     void* p = NULL;
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return NULL;
@@ -442,7 +554,12 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
     CU(cudaMalloc(&ctx->d_lut, EC * 512 * sizeof(int2)));
     CU(cudaMalloc(&ctx->d_code_ck, ck * sizeof(double)));
     CU(cudaMalloc(&ctx->d_wrap_ck, ck * sizeof(int)));
-    CU(cudaMalloc(&ctx->d_carr_ck, ck * sizeof(double)));
+    ctx->ck_plane = ck;
+    CU(cudaMalloc(&ctx->d_carr_ck, 2 * ck * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_spec, EC * 2 * sizeof(CarrSpec)));
+    CU(cudaMalloc(&ctx->d_info, EC * sizeof(CarrInfo)));
+    CU(cudaMalloc(&ctx->d_fallbacks, sizeof(int)));
+    CU(cudaMemset(ctx->d_fallbacks, 0, sizeof(int)));
     CU(cudaMalloc(&ctx->d_carr_state, ctx->C * sizeof(double)));
     CU(cudaMalloc(&ctx->d_carr_trace, EC * sizeof(double)));
     CU(cudaMalloc(&ctx->d_ca, 33 * CA_WORDS * sizeof(uint32_t)));
@@ -472,7 +589,7 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_desc); cudaFree(ctx->d_lut); cudaFree(ctx->d_code_ck); cudaFree(ctx->d_wrap_ck);
-    cudaFree(ctx->d_carr_ck); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_carr_trace); cudaFree(ctx->d_ca);
+    cudaFree(ctx->d_carr_ck); cudaFree(ctx->d_spec); cudaFree(ctx->d_info); cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_carr_trace); cudaFree(ctx->d_ca);
     cudaFree(ctx->d_iq); cudaFree(ctx->d_sums); cudaFree(ctx->d_err);
     for (int i = 0; i < TIMING_RING; i++)
         for (int j = 0; j < 3; j++) cudaEventDestroy(ctx->ev[i][j]);
@@ -487,9 +604,18 @@ static int enqueue_scan(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_e
     if (ctx->ev_count < TIMING_RING) CU(cudaEventRecord(ctx->ev[ctx->ev_count][0], st));
     k_prepare<<<EC, 128, 0, st>>>(desc_dev, ctx->d_lut, ctx->d_err);
     k_scan_code<<<(EC + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_code_ck, ctx->d_wrap_ck, EC, C, N, T, ntiles);
-    k_scan_carrier<<<C, 32, 0, st>>>(desc_dev, ctx->d_carr_ck, ctx->d_carr_state, ctx->d_carr_trace, n_epochs, C, N, T,
-                                     ntiles, ctx->cfg.carrier_mode);
-    ctx->launches += 3;
+    if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && ctx->cfg.reserved[0] == 0) {
+        const int chains = EC * 2;
+        k_carr_speculate<<<(chains + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_carr_state, ctx->d_carr_ck, ctx->ck_plane,
+                                                         ctx->d_spec, n_epochs, C, N, T, ntiles);
+        k_carr_chain<<<C, 32, 0, st>>>(desc_dev, ctx->d_spec, ctx->d_carr_ck, ctx->d_carr_state, ctx->d_carr_trace,
+                                       ctx->d_info, ctx->d_fallbacks, n_epochs, C, N, T, ntiles);
+        ctx->launches += 4;
+    } else {  // INT32 carrier (closed form) or the serial float scan (cfg.reserved[0] = 1, cross-check)
+        k_scan_carrier<<<C, 32, 0, st>>>(desc_dev, ctx->d_carr_ck, ctx->d_carr_state, ctx->d_carr_trace, ctx->d_info,
+                                         n_epochs, C, N, T, ntiles, ctx->cfg.carrier_mode);
+        ctx->launches += 3;
+    }
     ctx->last_epochs = n_epochs;
     CU(cudaGetLastError());
     return GPSIQ_OK;
@@ -503,8 +629,8 @@ static int enqueue_render(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n
     const int tile_groups = (ntiles + LANES_WARPS - 1) / LANES_WARPS;
     const size_t smem = (size_t) C * 512 * sizeof(int2) + (size_t) C * 33 * 4;
     k_synth_lanes<<<n_epochs * tile_groups, LANES_WARPS * 32, smem, st>>>(
-        desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, ctx->d_carr_ck, ctx->d_ca, iq_dev, C, N, T, ntiles,
-        tile_groups, ctx->cfg.carrier_mode);
+        desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, ctx->d_carr_ck, ctx->ck_plane, ctx->d_info, ctx->d_ca,
+        iq_dev, C, N, T, ntiles, tile_groups, ctx->cfg.carrier_mode);
     if (ctx->ev_count < TIMING_RING) {
         CU(cudaEventRecord(ctx->ev[ctx->ev_count][2], st));
         ctx->ev_count++;
@@ -627,6 +753,16 @@ int gpsiq_checksum_device(gpsiq_ctx* ctx, const int16_t* iq_dev, int n_epochs, u
 }
 
 int64_t gpsiq_launch_count(const gpsiq_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gpsiq_carrier_fallbacks(gpsiq_ctx* ctx, int64_t* count) {
+    if (!ctx || !count) return GPSIQ_ERR_ARG;
+    int h = 0;
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(&h, ctx->d_fallbacks, sizeof h, cudaMemcpyDeviceToHost));
+    *count = h;
+    return GPSIQ_OK;
+}
 
 int gpsiq_timing_begin(gpsiq_ctx* ctx) {
     if (!ctx) return GPSIQ_ERR_ARG;

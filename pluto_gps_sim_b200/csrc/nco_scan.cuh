@@ -129,3 +129,237 @@ GPSIQ_HD void nco_advance(double& x, double d, int count, int& wraps) {
 }
 
 }  // namespace gpsiq
+
+// ===========================================================================
+// Parallel exact carrier scan: speculate -> translate -> verify
+// ===========================================================================
+// The carrier phase never restarts (plutogpssim.c:2741-2746; only allocation
+// re-seeds it, plutogpssim.c:1964), so its exact value at epoch e depends on
+// every sample before it: one serial chain per channel across the whole
+// stream.  Scanning it segment by segment is latency bound on a GPU.  This
+// scheme makes all but O(1 carrier cycle) of each epoch parallel:
+//
+//  (1) SPECULATE (spec_scan_epoch, one chain per (epoch, channel), all in
+//      parallel): scan the epoch from an ESTIMATED start phase.  After the
+//      first wrap of the run the state sits on a coarse grid: a wrap leaves a
+//      multiple of 2^-52 (step > 0: the sum was rounded in [1,2), and x-1 is
+//      exact) or of 2^-53 (step < 0: RN(y+1.0) lands in [0.5,1)).
+//  (2) TRANSLATE.  Let x'_n be the speculative states from that first wrap on
+//      and x_n the true ones, x_n1 = x'_n1 + D with D a multiple of 2^-52.
+//      Every rounding in the recurrence is to a grid 2^-52 or finer, so D is an
+//      EVEN multiple of every grid below 1.0 and RN(x'+D+d) = RN(x'+d)+D, ties
+//      included -- provided every decision (binade of each sum, wrap or not)
+//      comes out the same for both runs.  Then x_n = x'_n + D for the rest of
+//      the epoch, and that sum is exact in binary64 (same binade, D on its grid).
+//      step > 0 needs one exclusion: sums in [1,2) round to 2^-52, of which D
+//      may be an odd multiple; a tie there needs step == 0 (mod 2^-53), so such
+//      epochs (1 in ~2^9) are not speculated.  step < 0 wraps leave multiples of
+//      2^-53: the speculation is run for both parities and the one making D a
+//      multiple of 2^-52 is used.
+//  (3) VERIFY (chain_epoch, serial per channel, O(one carrier cycle) per
+//      epoch): from the exact epoch start run the exact scan up to the first
+//      wrap; require the same wrap index as the speculation and |D| below the
+//      speculation's decision margin (the smallest distance of any speculative
+//      sum to a power of two / zero, minus rounding slack).  If so the epoch's
+//      end state is xend' + D; otherwise (or if not speculated) the epoch is
+//      scanned serially.  Exactness never depends on the estimate's quality,
+//      only the speed does.
+namespace gpsiq {
+
+GPSIQ_HD double pow2_of(int64_t biased_exp) { return bits_f64(biased_exp << 52); }
+
+// distance of |r| to the nearest power of two (the ends of its binade), minus one ulp of slack
+GPSIQ_HD double binade_margin(double r) {
+    const int64_t b = f64_bits(r) & 0x7fffffffffffffffLL;
+    const int64_t e = b >> 52;
+    if (e == 0 || e >= 2046) return -1.0;  // zero / denormal / huge: no margin
+    const double ar = bits_f64(b);
+    const double lo = pow2_of(e), hi = pow2_of(e + 1);
+    const double m = (ar - lo < hi - ar) ? ar - lo : hi - ar;  // both differences are exact
+    return m - pow2_of(e - 52);
+}
+
+struct CarrSpec {   // result of one speculative epoch scan
+    double xw1;     // state right after the first wrap of the run (sample index n1)
+    double xend;    // state after the last sample of the epoch
+    double margin;  // decision margin from n1 on; <= 0: unusable
+    int n1;         // index of the first sample whose state follows a wrap; N if the run never wraps
+    int pad;
+};
+
+// One step with margin tracking (TRACK) -- same arithmetic as nco_step<NCO_CARRIER>.
+template <bool TRACK>
+GPSIQ_HD bool carr_step(double& x, double d, double& margin) {
+    double y = add_rn(x, d);
+    bool w = false;
+    if (TRACK) { const double m = binade_margin(y); if (m < margin) margin = m; }
+    if (y >= 1.0) { y = add_rn(y, -1.0); w = true; }
+    else if (y < 0.0) {
+        y = add_rn(y, 1.0); w = true;
+        if (TRACK) { const double m = ((1.0 - y < y - 0.5) ? 1.0 - y : y - 0.5) - 0x1p-53; if (m < margin) margin = m; }
+    }
+    x = y;
+    return w;
+}
+
+// Advance up to `count` carrier steps; with stop_at_wrap, return right after
+// the first step that wrapped.  Returns the number of steps taken.
+template <bool TRACK>
+GPSIQ_HD int carr_advance(double& x, double d, int count, bool stop_at_wrap, bool& wrapped, double& margin) {
+    const int count0 = count;
+    wrapped = false;
+    while (count > 0) {
+        const double x0 = x;
+        bool w = carr_step<TRACK>(x, d, margin);
+        count--;
+        if (w) { wrapped = true; if (stop_at_wrap) break; continue; }
+        if (count < 3) continue;
+        const int64_t b0 = f64_bits(x0), b1 = f64_bits(x);
+        if ((b0 >> 52) != (b1 >> 52)) continue;
+        w = carr_step<TRACK>(x, d, margin);
+        count--;
+        if (w) { wrapped = true; if (stop_at_wrap) break; continue; }
+        const int64_t b2 = f64_bits(x);
+        if ((b2 >> 52) != (b1 >> 52)) continue;
+        const int64_t delta = b2 - b1;
+        if (delta == 0) { count = 0; break; }
+        int64_t k, edge;
+        if (delta > 0) {
+            edge = ((b2 >> 52) + 1) << 52;
+            if (BITS_1 < edge) edge = BITS_1;
+            k = floor_div_pos(edge - 1 - b2, delta);
+        } else {
+            edge = (b2 >> 52) << 52;
+            k = floor_div_pos(b2 - edge - 1, -delta);
+        }
+        if (k > count) k = count;
+        x = bits_f64(b2 + k * delta);
+        count -= (int) k;
+        if (TRACK) {
+            // the last iterate of the run is the one closest to the edge it approaches
+            const double xe = bits_f64(edge);
+            const double m = (delta > 0 ? xe - x : x - xe) - pow2_of(b2 >> 52) * 0x1p-52;
+            if (m < margin) margin = m;
+        }
+    }
+    return count0 - count;
+}
+
+// true if an epoch with this step may be speculated
+GPSIQ_HD bool carr_step_speculable(double d) {
+    const int64_t b = f64_bits(d) & 0x7fffffffffffffffLL;
+    const int64_t e = b >> 52;
+    if (e == 0 || e >= 1021) return false;               // zero/denormal, or |d| >= 0.25
+    if (d > 0.0) {
+        // exclude d == 0 (mod 2^-53): lowest set bit of |d| at 2^-53 or above
+        const int64_t m = (b & 0xfffffffffffffLL) | (1LL << 52);
+        int tz = 0;
+        while (!((m >> tz) & 1)) tz++;
+        if ((int) e - 1075 + tz >= -53) return false;
+    }
+    return true;
+}
+
+// (1) speculative scan of one epoch from x (an estimate of the epoch's start
+// phase).  ck[t*ck_stride] receives the state at the start of tile t.
+GPSIQ_HD void spec_scan_epoch(double x, double d, int N, int T, int variant, double* ck, size_t ck_stride,
+                              CarrSpec& out) {
+    const int ntiles = (N + T - 1) / T;
+    double margin = 1.0;
+    bool seen_wrap = false;
+    int n = 0;
+    out.n1 = N;
+    out.xw1 = 0.0;
+    for (int t = 0; t < ntiles; t++) {
+        ck[(size_t) t * ck_stride] = x;
+        int remaining = (T < N - t * T) ? T : N - t * T;
+        while (remaining > 0) {
+            bool w;
+            int steps;
+            if (!seen_wrap) {
+                double dummy = 1.0;
+                steps = carr_advance<false>(x, d, remaining, true, w, dummy);
+                if (w) {
+                    seen_wrap = true;
+                    if (variant == 1) x = (x + 0x1p-53 < 1.0) ? x + 0x1p-53 : x - 0x1p-53;  // other parity of the 2^-53 grid
+                    if (!(x >= 0.0 && x < 1.0)) margin = -1.0;
+                    out.n1 = n + steps;
+                    out.xw1 = x;
+                }
+            } else {
+                steps = carr_advance<true>(x, d, remaining, false, w, margin);
+            }
+            remaining -= steps;
+            n += steps;
+        }
+    }
+    out.xend = x;
+    out.margin = (seen_wrap && carr_step_speculable(d)) ? margin : -1.0;
+}
+
+struct CarrInfo {   // per (epoch, channel): how the renderer obtains tile-start phases
+    double delta;   // translation for tiles starting at or after n1
+    int n1;         // tiles starting before n1 read the exact plane 0; N = all exact
+    int variant;    // speculative plane (0/1) for the translated tiles
+};
+
+// (3) exact chaining of one epoch from the exact start x; returns the exact end
+// state.  ck0 is plane 0 of the checkpoint array for this (epoch, channel).
+GPSIQ_HD double chain_epoch(double x, double d, int N, int T, const CarrSpec& s0, const CarrSpec& s1, double* ck0,
+                            size_t ck_stride, CarrInfo& info, int& fell_back) {
+    const int ntiles = (N + T - 1) / T;
+    int n = 0, t = 0, remaining = 0;
+    bool wrapped = false;
+    double dummy = 1.0;
+    // exact head: up to and including the first wrap
+    for (; t < ntiles && !wrapped; t++) {
+        ck0[(size_t) t * ck_stride] = x;
+        remaining = (T < N - t * T) ? T : N - t * T;
+        while (remaining > 0 && !wrapped) {
+            const int steps = carr_advance<false>(x, d, remaining, true, wrapped, dummy);
+            remaining -= steps;
+            n += steps;
+        }
+    }
+    info.delta = 0.0;
+    info.n1 = N;
+    info.variant = 0;
+    if (!wrapped) return x;  // the whole epoch was the head (low Doppler)
+    // try the translation
+    if (s0.margin > 0.0 && n == s0.n1) {
+        const CarrSpec* s = &s0;
+        int v = 0;
+        double diff = x - s0.xw1;  // exact: both on the 2^-53 grid and close
+        double q = diff * 0x1p52;
+        if (d < 0.0 && q != (double) (long long) q && s1.margin > 0.0 && n == s1.n1) {
+            s = &s1; v = 1;
+            diff = x - s1.xw1;
+            q = diff * 0x1p52;
+        }
+        const double ad = diff < 0.0 ? -diff : diff;
+        if (q == (double) (long long) q && ad < s->margin - 0x1p-50) {
+            info.delta = diff;
+            info.n1 = n;
+            info.variant = v;
+            return add_rn(s->xend, diff);
+        }
+    }
+    // fallback: finish the epoch serially, exact checkpoints for the remaining tiles
+    fell_back++;
+    bool w;
+    while (remaining > 0) {
+        const int steps = carr_advance<false>(x, d, remaining, false, w, dummy);
+        remaining -= steps;
+    }
+    for (; t < ntiles; t++) {
+        ck0[(size_t) t * ck_stride] = x;
+        remaining = (T < N - t * T) ? T : N - t * T;
+        while (remaining > 0) {
+            const int steps = carr_advance<false>(x, d, remaining, false, w, dummy);
+            remaining -= steps;
+        }
+    }
+    return x;
+}
+
+}  // namespace gpsiq

@@ -17,7 +17,7 @@ NUM_SAMPLES = 300000  # plutogpssim.c:43-44: TX_SAMPLE_FREQ/10, independent of -
 
 class Synthesizer:
     def __init__(self, max_chan=12, samples_per_epoch=NUM_SAMPLES, max_epochs=100, carrier_mode=capi.CARRIER_FLOAT,
-                 device=0, tile_samples=0, kernel=capi.KERNEL_AUTO):
+                 device=0, tile_samples=0, kernel=capi.KERNEL_AUTO, serial_carrier_scan=False):
         cfg = capi.Config()
         cfg.device = device
         cfg.max_chan = max_chan
@@ -26,6 +26,7 @@ class Synthesizer:
         cfg.max_epochs = max_epochs
         cfg.tile_samples = tile_samples
         cfg.kernel = kernel
+        cfg.reserved[0] = 1 if serial_carrier_scan else 0
         self._ctx = C.c_void_p()
         capi.check(capi.lib.gpsiq_create(C.byref(self._ctx), C.byref(cfg)))
         self.max_chan = max_chan
@@ -115,6 +116,12 @@ class Synthesizer:
     @property
     def launch_count(self):
         return int(capi.lib.gpsiq_launch_count(self._ctx))
+
+    @property
+    def carrier_fallbacks(self):
+        n = C.c_int64(0)
+        capi.check(capi.lib.gpsiq_carrier_fallbacks(self._ctx, C.byref(n)), self._ctx)
+        return n.value
 
     def timing_begin(self):
         capi.check(capi.lib.gpsiq_timing_begin(self._ctx), self._ctx)

@@ -106,6 +106,24 @@ def test_integer_carrier_mode_vs_oracle():
     assert np.array_equal(gt, wt)
 
 
+def test_parallel_and_serial_carrier_scan_agree():
+    """The speculate/translate/verify carrier scan vs the plain serial chain on the
+    device: same stream, same carrier trace; and the fast path is really taken."""
+    meta = ol.load_golden_meta("circle12")
+    desc = ol.load_golden_desc("circle12")[:64]
+    with Synthesizer(max_chan=12, max_epochs=64) as a, Synthesizer(max_chan=12, max_epochs=64, serial_carrier_scan=True) as b:
+        a.synth(desc, keep_on_device=True)
+        b.synth(desc, keep_on_device=True)
+        sa = a.checksum_device(a.device_iq_ptr(), 64)
+        sb = b.checksum_device(b.device_iq_ptr(), 64)
+        assert np.array_equal(a.carrier_trace(64), b.carrier_trace(64))
+        n_active = int((desc["prn"] > 0).sum())
+        assert a.carrier_fallbacks < n_active // 4, a.carrier_fallbacks
+        assert b.carrier_fallbacks == 0
+    assert [int(x) for x in sa] == meta["epoch_checksums"][:64]
+    assert np.array_equal(sa, sb)
+
+
 def test_set_get_carrier_handoff():
     """Time-slice hand-off: synthesizing epochs [5,10) on a fresh context seeded
     with the carrier phases after epoch 4 equals the second half of one run."""

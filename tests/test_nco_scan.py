@@ -77,3 +77,48 @@ def test_scan_matches_reference_epoch_chain():
         for c in range(desc.shape[1]):
             ph[c], _ = capi.nco_advance(capi.NCO_CARRIER, ph[c], desc[e, c]["carr_step"], n)
             assert ph[c].hex() == meta["carr_phase_end_hex"][e][c]
+
+
+def _literal_checkpoints(steps, N, T, x0):
+    nt = (N + T - 1) // T
+    ck = np.zeros((len(steps), nt))
+    x = x0
+    for e, d in enumerate(steps):
+        for t in range(nt):
+            ck[e, t] = x
+            x = ol.oracle_carr_nco(x, d, min(T, N - t * T))
+    return ck, x
+
+
+@pytest.mark.parametrize("seed", [5, 6])
+def test_parallel_carrier_scan_speculate_translate_verify(seed):
+    """The parallel carrier scan (speculative epoch scans from estimated start
+    phases, translated onto the exact chain, serial fallback) gives the literal
+    recurrence's state at every tile boundary -- whatever the estimate error."""
+    rng = random.Random(seed)
+    translated = 0
+    for trial in range(30):
+        fs = rng.choice([2.6e6, 3e6, 1e7])
+        E = rng.choice([3, 8, 20])
+        N = rng.choice([300000, 100000, 4097])
+        T = rng.choice([1024, 2048, 512])
+        f0 = rng.uniform(-5000, 5000) if trial % 3 else rng.uniform(-30, 30)
+        steps = [(f0 + rng.uniform(-2, 2)) * (1.0 / fs) for _ in range(E)]
+        x0 = rng.random()
+        err = rng.choice([0.0, 0.0, 1e-12, 1e-9, 1e-6, 1e-3])
+        want, wx = _literal_checkpoints(steps, N, T, x0)
+        got, gx, fb = capi.carrier_chain_host(steps, N, T, x0, err)
+        assert np.array_equal(got.view(np.int64), want.view(np.int64)), (trial, f0, E, N, T, err)
+        assert bits(gx) == bits(wx)
+        translated += E - fb
+    assert translated > 100          # the fast path is actually exercised
+
+
+def test_parallel_carrier_scan_unspeculable_steps():
+    """Steps that are multiples of 2^-53 (ties possible in [1,2)) and huge steps are never speculated."""
+    N, T = 50000, 1024
+    for d in (3.0 * 2.0 ** -12, 2.0 ** -9, -2.0 ** -9, 0.3, -0.26, 5 * 2.0 ** -53):
+        want, wx = _literal_checkpoints([d, d, d], N, T, 0.123456789)
+        got, gx, fb = capi.carrier_chain_host([d, d, d], N, T, 0.123456789, 0.0)
+        assert np.array_equal(got.view(np.int64), want.view(np.int64)), d
+        assert bits(gx) == bits(wx)
