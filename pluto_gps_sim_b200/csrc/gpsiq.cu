@@ -78,6 +78,7 @@ struct gpsiq_ctx {
     double* d_code_ck;    // [E][ntiles][C]
     int* d_wrap_ck;       // [E][ntiles][C]
     double* d_carr_ck;    // [2][E][ntiles][C] two speculation planes (INT32 mode: uint32 phase as double, plane 0)
+    BinadeTab* d_tab;     // [E][C][2]  (0 = code NCO, 1 = carrier NCO)
     CarrSpec* d_spec;     // [E][C][2]
     CarrInfo* d_info;     // [E][C]
     int* d_fallbacks;     // epochs that fell back to the serial carrier scan (diagnostic counter)
@@ -113,11 +114,16 @@ static int fail(gpsiq_ctx* ctx, int code, const char* what, cudaError_t ce) {
 // ---------------------------------------------------------------------------
 // k_prepare: amplitude LUT per (epoch, slot)
 // ---------------------------------------------------------------------------
-__global__ void k_prepare(const gpsiq_chan_desc* __restrict__ desc, int2* __restrict__ lut, int* __restrict__ err) {
+__global__ void k_prepare(const gpsiq_chan_desc* __restrict__ desc, int2* __restrict__ lut,
+                          BinadeTab* __restrict__ tab, int carrier_mode, int* __restrict__ err) {
     const int ec = blockIdx.x;
     const gpsiq_chan_desc d = desc[ec];
     int2* out = lut + (size_t) ec * 512;
     if (d.prn <= 0) return;
+    // per-binade fixed-point increments of the two NCOs for this epoch's steps (nco_scan.cuh)
+    if (threadIdx.x == 0) build_binade_tab<NCO_CODE>(d.code_step, tab[(size_t) ec * 2]);
+    if (threadIdx.x == 32 && carrier_mode == GPSIQ_CARRIER_FLOAT)
+        build_binade_tab<NCO_CARRIER>(d.carr_step, tab[(size_t) ec * 2 + 1]);
     if (d.prn > 32 || !(d.code_phase0 >= 0.0 && d.code_phase0 < 1023.0) || !(d.code_step > 0.0 && d.code_step < 1023.0)) {
         if (threadIdx.x == 0) atomicExch(err, 1 + ec);
         return;
@@ -134,8 +140,9 @@ __global__ void k_prepare(const gpsiq_chan_desc* __restrict__ desc, int2* __rest
 // ---------------------------------------------------------------------------
 // k_scan_code: exact code phase + wrap count at every tile start
 // ---------------------------------------------------------------------------
-__global__ void k_scan_code(const gpsiq_chan_desc* __restrict__ desc, double* __restrict__ code_ck,
-                            int* __restrict__ wrap_ck, int EC, int C, int N, int T, int ntiles) {
+__global__ void k_scan_code(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
+                            double* __restrict__ code_ck, int* __restrict__ wrap_ck, int EC, int C, int N, int T,
+                            int ntiles) {
     // one chain per warp, lane 0 only: the scan is branchy and data dependent,
     // chains sharing a warp would serialise each other's paths
     const int ec = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -145,19 +152,21 @@ __global__ void k_scan_code(const gpsiq_chan_desc* __restrict__ desc, double* __
     if (d.prn <= 0) return;
     double x = d.code_phase0;
     int wraps = 0;
+    const BinadeTab tab = tabs[(size_t) ec * 2];
     for (int t = 0; t < ntiles; t++) {
         const size_t o = ((size_t) e * ntiles + t) * C + c;
         code_ck[o] = x;
         wrap_ck[o] = wraps;
         const int len = min(T, N - t * T);
-        nco_advance<NCO_CODE>(x, d.code_step, len, wraps);
+        nco_advance<NCO_CODE>(x, d.code_step, tab, len, wraps);
     }
 }
 
 // ---------------------------------------------------------------------------
 // k_scan_carrier: exact carrier phase at every tile start, chained over epochs
 // ---------------------------------------------------------------------------
-__global__ void k_scan_carrier(const gpsiq_chan_desc* __restrict__ desc, double* __restrict__ carr_ck,
+__global__ void k_scan_carrier(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
+                               double* __restrict__ carr_ck,
                                double* __restrict__ carr_state, double* __restrict__ carr_trace,
                                CarrInfo* __restrict__ info, int E, int C, int N, int T, int ntiles, int carrier_mode) {
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one chain per warp, lane 0
@@ -180,10 +189,11 @@ __global__ void k_scan_carrier(const gpsiq_chan_desc* __restrict__ desc, double*
             info[(size_t) e * C + c] = inf;
         }
         if (carrier_mode == GPSIQ_CARRIER_FLOAT) {
+            const BinadeTab tab = tabs[((size_t) e * C + c) * 2 + 1];
             for (int t = 0; t < ntiles; t++) {
                 carr_ck[((size_t) e * ntiles + t) * C + c] = x;
                 const int len = min(T, N - t * T);
-                nco_advance<NCO_CARRIER>(x, d.carr_step, len, dummy);
+                nco_advance<NCO_CARRIER>(x, d.carr_step, tab, len, dummy);
             }
             carr_trace[(size_t) e * C + c] = x;
         } else {
@@ -209,7 +219,8 @@ __device__ __forceinline__ double est_advance_dev(double x, double d, int N) {
     return (t >= 0.0 && t < 1.0) ? t : 0.0;
 }
 
-__global__ void k_carr_speculate(const gpsiq_chan_desc* __restrict__ desc, const double* __restrict__ carr_state,
+__global__ void k_carr_speculate(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
+                                 const double* __restrict__ carr_state,
                                  double* __restrict__ carr_ck, size_t ck_plane, CarrSpec* __restrict__ spec, int E,
                                  int C, int N, int T, int ntiles) {
     const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -229,13 +240,15 @@ __global__ void k_carr_speculate(const gpsiq_chan_desc* __restrict__ desc, const
             x = est_advance_dev(x, dk->carr_step, N);
         }
         if (d.flags & GPSIQ_FLAG_RESET_CARRIER) x = d.carr_phase0;
-        spec_scan_epoch(x, d.carr_step, N, T, v, carr_ck + (size_t) v * ck_plane + (size_t) e * ntiles * C + c,
+        const BinadeTab tab = tabs[(size_t) ec * 2 + 1];
+        spec_scan_epoch(x, d.carr_step, tab, N, T, v, carr_ck + (size_t) v * ck_plane + (size_t) e * ntiles * C + c,
                         (size_t) C, out);
     }
     spec[(size_t) ec * 2 + v] = out;
 }
 
-__global__ void k_carr_chain(const gpsiq_chan_desc* __restrict__ desc, const CarrSpec* __restrict__ spec,
+__global__ void k_carr_chain(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
+                             const CarrSpec* __restrict__ spec,
                              double* __restrict__ carr_ck, double* __restrict__ carr_state,
                              double* __restrict__ carr_trace, CarrInfo* __restrict__ info, int* __restrict__ fallbacks,
                              int E, int C, int N, int T, int ntiles) {
@@ -249,7 +262,7 @@ __global__ void k_carr_chain(const gpsiq_chan_desc* __restrict__ desc, const Car
         if (d.prn <= 0) { carr_trace[ec] = x; continue; }
         if (d.flags & GPSIQ_FLAG_RESET_CARRIER) x = d.carr_phase0;
         CarrInfo inf;
-        x = chain_epoch(x, d.carr_step, N, T, spec[ec * 2], spec[ec * 2 + 1], carr_ck + (size_t) e * ntiles * C + c,
+        x = chain_epoch(x, d.carr_step, tabs[ec * 2 + 1], N, T, spec[ec * 2], spec[ec * 2 + 1], carr_ck + (size_t) e * ntiles * C + c,
                         (size_t) C, inf, fb);
         info[ec] = inf;
         carr_trace[ec] = x;
@@ -454,11 +467,14 @@ int gpsiq_nco_advance(int mode, double* phase, double step, int64_t count, int64
     double x = *phase;
     int w = 0;
     int64_t wtot = 0;
+    BinadeTab tab;
+    if (mode == NCO_CODE) build_binade_tab<NCO_CODE>(step, tab);
+    else build_binade_tab<NCO_CARRIER>(step, tab);
     while (count > 0) {
         const int chunk = count > (1 << 30) ? (1 << 30) : (int) count;
         w = 0;
-        if (mode == NCO_CODE) nco_advance<NCO_CODE>(x, step, chunk, w);
-        else nco_advance<NCO_CARRIER>(x, step, chunk, w);
+        if (mode == NCO_CODE) nco_advance<NCO_CODE>(x, step, tab, chunk, w);
+        else nco_advance<NCO_CARRIER>(x, step, tab, chunk, w);
         wtot += w;
         count -= chunk;
     }
@@ -491,10 +507,12 @@ int gpsiq_carrier_chain_host(const double* steps, int n_epochs, int N, int T, do
         s1.margin = -1.0; s1.n1 = -1; s1.xw1 = 0; s1.xend = 0;
         double est = xe + est_err;                       // what the device would guess, plus injected error
         est -= floor(est);
-        spec_scan_epoch(est, d, N, T, 0, plane[0], 1, s0);
-        if (d < 0.0) spec_scan_epoch(est, d, N, T, 1, plane[1], 1, s1);
+        BinadeTab tab;
+        build_binade_tab<NCO_CARRIER>(d, tab);
+        spec_scan_epoch(est, d, tab, N, T, 0, plane[0], 1, s0);
+        if (d < 0.0) spec_scan_epoch(est, d, tab, N, T, 1, plane[1], 1, s1);
         CarrInfo info;
-        x = chain_epoch(x, d, N, T, s0, s1, plane[0], 1, info, fb);
+        x = chain_epoch(x, d, tab, N, T, s0, s1, plane[0], 1, info, fb);
         for (int t = 0; t < ntiles; t++) {
             const bool exact = (t * T < info.n1) || info.n1 >= N;
             ck_out[(size_t) e * ntiles + t] = exact ? plane[0][t] : plane[info.variant][t] + info.delta;
@@ -556,6 +574,7 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
     CU(cudaMalloc(&ctx->d_wrap_ck, ck * sizeof(int)));
     ctx->ck_plane = ck;
     CU(cudaMalloc(&ctx->d_carr_ck, 2 * ck * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_tab, EC * 2 * sizeof(BinadeTab)));
     CU(cudaMalloc(&ctx->d_spec, EC * 2 * sizeof(CarrSpec)));
     CU(cudaMalloc(&ctx->d_info, EC * sizeof(CarrInfo)));
     CU(cudaMalloc(&ctx->d_fallbacks, sizeof(int)));
@@ -589,7 +608,7 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_desc); cudaFree(ctx->d_lut); cudaFree(ctx->d_code_ck); cudaFree(ctx->d_wrap_ck);
-    cudaFree(ctx->d_carr_ck); cudaFree(ctx->d_spec); cudaFree(ctx->d_info); cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_carr_trace); cudaFree(ctx->d_ca);
+    cudaFree(ctx->d_carr_ck); cudaFree(ctx->d_tab); cudaFree(ctx->d_spec); cudaFree(ctx->d_info); cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_carr_trace); cudaFree(ctx->d_ca);
     cudaFree(ctx->d_iq); cudaFree(ctx->d_sums); cudaFree(ctx->d_err);
     for (int i = 0; i < TIMING_RING; i++)
         for (int j = 0; j < 3; j++) cudaEventDestroy(ctx->ev[i][j]);
@@ -602,17 +621,17 @@ static int enqueue_scan(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_e
     const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
     const int EC = n_epochs * C;
     if (ctx->ev_count < TIMING_RING) CU(cudaEventRecord(ctx->ev[ctx->ev_count][0], st));
-    k_prepare<<<EC, 128, 0, st>>>(desc_dev, ctx->d_lut, ctx->d_err);
-    k_scan_code<<<(EC + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_code_ck, ctx->d_wrap_ck, EC, C, N, T, ntiles);
+    k_prepare<<<EC, 128, 0, st>>>(desc_dev, ctx->d_lut, ctx->d_tab, ctx->cfg.carrier_mode, ctx->d_err);
+    k_scan_code<<<(EC + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_code_ck, ctx->d_wrap_ck, EC, C, N, T, ntiles);
     if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && ctx->cfg.reserved[0] == 0) {
         const int chains = EC * 2;
-        k_carr_speculate<<<(chains + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_carr_state, ctx->d_carr_ck, ctx->ck_plane,
+        k_carr_speculate<<<(chains + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_carr_state, ctx->d_carr_ck, ctx->ck_plane,
                                                          ctx->d_spec, n_epochs, C, N, T, ntiles);
-        k_carr_chain<<<C, 32, 0, st>>>(desc_dev, ctx->d_spec, ctx->d_carr_ck, ctx->d_carr_state, ctx->d_carr_trace,
+        k_carr_chain<<<C, 32, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_spec, ctx->d_carr_ck, ctx->d_carr_state, ctx->d_carr_trace,
                                        ctx->d_info, ctx->d_fallbacks, n_epochs, C, N, T, ntiles);
         ctx->launches += 4;
     } else {  // INT32 carrier (closed form) or the serial float scan (cfg.reserved[0] = 1, cross-check)
-        k_scan_carrier<<<C, 32, 0, st>>>(desc_dev, ctx->d_carr_ck, ctx->d_carr_state, ctx->d_carr_trace, ctx->d_info,
+        k_scan_carrier<<<C, 32, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_carr_ck, ctx->d_carr_state, ctx->d_carr_trace, ctx->d_info,
                                          n_epochs, C, N, T, ntiles, ctx->cfg.carrier_mode);
         ctx->launches += 3;
     }

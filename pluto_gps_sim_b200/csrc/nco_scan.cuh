@@ -12,19 +12,25 @@
 // Lemma.  Let x be a binary64 in the binade [2^b, 2^(b+1)),
 // ulp g = 2^(b-52).  If RN(x+d) stays in the same binade, then
 // RN(x+d) = x + D*g with D = RN(d/g) an integer that does not depend on x
-// (x is a multiple of g); on an exact tie RN picks the even mantissa, after
-// which the increment is constant as well.  Within a binade the raw IEEE bit
-// pattern of a positive double is an affine function of its value, so k such
-// steps are ONE integer multiply-add on the bit pattern:
+// (x is a multiple of g); on an exact tie RN picks the even mantissa, so from
+// an even mantissa the increment is constant as well.  Within a binade the raw
+// IEEE bit pattern of a positive double is an affine function of its value, so
+// k such steps are ONE integer multiply-add on the bit pattern:
 //     bits(x_k) = bits(x_0) + k*D.
 // In other words: inside a binade the reference's floating-point NCO *is* a
 // fixed-point NCO.  Binade crossings and wraps are done with true additions.
 // The subtractions x-1023.0 (x in [1023,1024.4)) and x-1.0 (x in [1,2)) are
 // exact; x+1.0 for a small negative x rounds to the 2^-53 grid.
 //
-// This header is shared by the CUDA kernels (device) and by the host-side unit
-// test build (tests/ compile it with g++ and compare against the literal
-// per-sample recurrence).
+// The per-binade increments D_b depend only on the step d, so they are
+// tabulated once per (epoch, channel, NCO) (BinadeTab) and every scan --
+// the per-epoch scan kernels and the per-tile prologue of the synthesis
+// kernel -- steps segment by segment: [k in-binade steps by one multiply-add]
+// [one true step].
+//
+// This header is shared by the CUDA kernels (device) and by the host-side
+// entry points gpsiq_nco_advance / gpsiq_carrier_chain_host, which the tests
+// compare against the literal per-sample recurrence.
 #pragma once
 #include <stdint.h>
 
@@ -58,12 +64,50 @@ GPSIQ_HD double add_rn(double a, double b) {
     volatile double r = a + b; return r;
 #endif
 }
+GPSIQ_HD double pow2_of(int64_t biased_exp) { return bits_f64(biased_exp << 52); }
 
 constexpr int NCO_CODE = 0;     // wrap at 1023, step > 0, counts wraps
 constexpr int NCO_CARRIER = 1;  // wrap at 1 / 0, step of either sign
 
 constexpr int64_t BITS_1023 = 0x408FF80000000000LL;  // bits(1023.0)
 constexpr int64_t BITS_1 = 0x3FF0000000000000LL;     // bits(1.0)
+constexpr int NBINADE = 16;
+
+template <int MODE> struct NcoTraits;
+template <> struct NcoTraits<NCO_CODE> { static constexpr int64_t ETOP = 1032; static constexpr int64_t LIM = BITS_1023; };
+template <> struct NcoTraits<NCO_CARRIER> { static constexpr int64_t ETOP = 1022; static constexpr int64_t LIM = BITS_1; };
+
+// In-binade increments of the bit pattern for one step value d.
+// Binade index bi = ETOP - biased exponent: 0 is [512,1024) for the code NCO,
+// [0.5,1) for the carrier NCO; states in lower binades than NBINADE-1 take true steps.
+struct BinadeTab {
+    int64_t delta[NBINADE];  // D_b from an even mantissa (any mantissa if the binade has no tie)
+    float rcp[NBINADE];      // ~1/|D_b|
+    uint32_t valid;          // bit bi: delta[bi] is usable
+    uint32_t tie;            // bit bi: d/ulp_b is an exact half-integer: an odd mantissa steps differently once
+};
+
+template <int MODE>
+GPSIQ_HD void build_binade_tab(double d, BinadeTab& tab) {
+    tab.valid = 0;
+    tab.tie = 0;
+    for (int bi = 0; bi < NBINADE; bi++) {
+        const int64_t e = NcoTraits<MODE>::ETOP - bi;
+        const int64_t b_even = (e << 52) | (1LL << 51);  // 1.5 * 2^b, even mantissa
+        const double y0 = add_rn(bits_f64(b_even), d);
+        const double y1 = add_rn(bits_f64(b_even + 1), d);
+        const int64_t c0 = f64_bits(y0), c1 = f64_bits(y1);
+        tab.delta[bi] = 0;
+        tab.rcp[bi] = 0.f;
+        if ((c0 >> 52) != e || (c1 >> 52) != e || c0 >= NcoTraits<MODE>::LIM) continue;  // probe left the binade
+        const int64_t d0 = c0 - b_even, d1 = c1 - (b_even + 1);
+        tab.delta[bi] = d0;
+        const int64_t a = d0 < 0 ? -d0 : d0;
+        tab.rcp[bi] = a ? 1.0f / (float) a : 0.f;
+        tab.valid |= 1u << bi;
+        if (d1 != d0) tab.tie |= 1u << bi;
+    }
+}
 
 // One literal step of the reference recurrence. Returns true if it wrapped.
 template <int MODE>
@@ -80,55 +124,62 @@ GPSIQ_HD bool nco_step(double& x, double d, int& wraps) {
     return w;
 }
 
-// Floor of a/b for 0 <= a < 2^53, 0 < b < 2^53 without a 64-bit integer
-// division on the device: both are exact doubles, the round-toward-zero
-// quotient is the largest double <= a/b, and every integer below 2^53 is
-// representable, so its floor is the exact integer quotient.
-GPSIQ_HD int64_t floor_div_pos(int64_t a, int64_t b) {
-#if defined(__CUDA_ARCH__)
-    return __double2ll_rz(__ddiv_rz(__ll2double_rn(a), __ll2double_rn(b)));
-#else
-    return a / b;
-#endif
+// Take up to maxk steps that provably stay inside x's binade (and below the
+// wrap limit) with one multiply-add on the bit pattern.  Returns the number of
+// steps taken (possibly 0); none of them wraps.  edge_gap (if not null)
+// receives the distance, in ulps of the binade, between the last iterate and
+// the binade edge / wrap limit it is moving toward (>= 1).
+template <int MODE>
+GPSIQ_HD int run_in_binade(double& x, const BinadeTab& tab, int maxk, int64_t* edge_gap = nullptr) {
+    const int64_t b = f64_bits(x);
+    const int64_t e = b >> 52;
+    const int64_t bi = NcoTraits<MODE>::ETOP - e;
+    if (edge_gap) *edge_gap = 0;
+    if (bi < 0 || bi >= NBINADE || maxk <= 0) return 0;
+    if (!((tab.valid >> bi) & 1u)) return 0;
+    if (((tab.tie >> bi) & 1u) && (b & 1)) return 0;  // odd mantissa in a tie binade: take a true step first
+    const int64_t delta = tab.delta[bi];
+    if (delta == 0) return maxk;  // |d| < ulp/2: the state no longer moves
+    int64_t num, ad;
+    if (delta > 0) {
+        int64_t top = (e + 1) << 52;
+        if (NcoTraits<MODE>::LIM < top) top = NcoTraits<MODE>::LIM;
+        num = top - 1 - b;  // iterates must stay <= top-1
+        ad = delta;
+    } else {
+        num = b - (e << 52) - 1;  // iterates must stay >= first pattern of the binade + 1
+        ad = -delta;
+    }
+    if (num < ad) return 0;
+    // k = min(floor(num/ad), maxk) without an integer or FP64 division
+    int64_t k;
+    const float qf = (float) num * tab.rcp[bi];
+    if (qf >= (float) maxk + 4.0f) {
+        k = maxk;
+    } else {
+        k = (int64_t) qf;
+        int64_t r = num - k * ad;
+        while (r < 0) { k--; r += ad; }
+        while (r >= ad) { k++; r -= ad; }
+        if (k > maxk) k = maxk;
+    }
+    x = bits_f64(b + k * delta);
+    if (edge_gap) *edge_gap = num - k * ad + 1;
+    return (int) k;
 }
 
 // Advance x by `count` steps of the MODE recurrence with step d; `wraps`
 // accumulates code-period wraps (NCO_CODE).  Exactly equivalent to calling
 // nco_step `count` times.
 template <int MODE>
-GPSIQ_HD void nco_advance(double& x, double d, int count, int& wraps) {
+GPSIQ_HD void nco_advance(double& x, double d, const BinadeTab& tab, int count, int& wraps) {
     while (count > 0) {
-        double x0 = x;
-        bool w = nco_step<MODE>(x, d, wraps);
+        count -= run_in_binade<MODE>(x, tab, count);
+        if (count == 0) break;
+        nco_step<MODE>(x, d, wraps);
         count--;
-        if (w || count < 3) continue;
-        int64_t b0 = f64_bits(x0), b1 = f64_bits(x);
-        if ((b0 >> 52) != (b1 >> 52)) continue;  // left the binade
-        // second literal step: after it the increment is tie-free and constant
-        w = nco_step<MODE>(x, d, wraps);
-        count--;
-        if (w) continue;
-        int64_t b2 = f64_bits(x);
-        if ((b2 >> 52) != (b1 >> 52)) continue;
-        int64_t delta = b2 - b1;
-        if (delta == 0) return;  // step below half an ulp: the phase no longer moves
-        int64_t k;
-        if (delta > 0) {
-            int64_t top = ((b2 >> 52) + 1) << 52;  // first pattern of the next binade
-            const int64_t lim = (MODE == NCO_CODE) ? BITS_1023 : BITS_1;
-            if (lim < top) top = lim;
-            k = floor_div_pos(top - 1 - b2, delta);  // results stay <= top-1
-        } else {
-            int64_t bot = (b2 >> 52) << 52;  // first pattern of this binade
-            k = floor_div_pos(b2 - bot - 1, -delta);  // results stay >= bot+1
-        }
-        if (k > count) k = count;
-        x = bits_f64(b2 + k * delta);
-        count -= (int) k;
     }
 }
-
-}  // namespace gpsiq
 
 // ===========================================================================
 // Parallel exact carrier scan: speculate -> translate -> verify
@@ -146,11 +197,11 @@ GPSIQ_HD void nco_advance(double& x, double d, int count, int& wraps) {
 //      exact) or of 2^-53 (step < 0: RN(y+1.0) lands in [0.5,1)).
 //  (2) TRANSLATE.  Let x'_n be the speculative states from that first wrap on
 //      and x_n the true ones, x_n1 = x'_n1 + D with D a multiple of 2^-52.
-//      Every rounding in the recurrence is to a grid 2^-52 or finer, so D is an
-//      EVEN multiple of every grid below 1.0 and RN(x'+D+d) = RN(x'+d)+D, ties
-//      included -- provided every decision (binade of each sum, wrap or not)
-//      comes out the same for both runs.  Then x_n = x'_n + D for the rest of
-//      the epoch, and that sum is exact in binary64 (same binade, D on its grid).
+//      Every rounding below 1.0 is to a grid of 2^-53 or finer, so D is an EVEN
+//      multiple of it and RN(x'+D+d) = RN(x'+d)+D, ties included -- provided
+//      every decision (binade of each sum, wrap or not) comes out the same for
+//      both runs.  Then x_n = x'_n + D for the rest of the epoch, and that sum
+//      is exact in binary64 (same binade, D on its grid).
 //      step > 0 needs one exclusion: sums in [1,2) round to 2^-52, of which D
 //      may be an odd multiple; a tie there needs step == 0 (mod 2^-53), so such
 //      epochs (1 in ~2^9) are not speculated.  step < 0 wraps leave multiples of
@@ -164,9 +215,6 @@ GPSIQ_HD void nco_advance(double& x, double d, int count, int& wraps) {
 //      end state is xend' + D; otherwise (or if not speculated) the epoch is
 //      scanned serially.  Exactness never depends on the estimate's quality,
 //      only the speed does.
-namespace gpsiq {
-
-GPSIQ_HD double pow2_of(int64_t biased_exp) { return bits_f64(biased_exp << 52); }
 
 // distance of |r| to the nearest power of two (the ends of its binade), minus one ulp of slack
 GPSIQ_HD double binade_margin(double r) {
@@ -187,7 +235,7 @@ struct CarrSpec {   // result of one speculative epoch scan
     int pad;
 };
 
-// One step with margin tracking (TRACK) -- same arithmetic as nco_step<NCO_CARRIER>.
+// One carrier step with margin tracking (TRACK) -- same arithmetic as nco_step<NCO_CARRIER>.
 template <bool TRACK>
 GPSIQ_HD bool carr_step(double& x, double d, double& margin) {
     double y = add_rn(x, d);
@@ -205,42 +253,24 @@ GPSIQ_HD bool carr_step(double& x, double d, double& margin) {
 // Advance up to `count` carrier steps; with stop_at_wrap, return right after
 // the first step that wrapped.  Returns the number of steps taken.
 template <bool TRACK>
-GPSIQ_HD int carr_advance(double& x, double d, int count, bool stop_at_wrap, bool& wrapped, double& margin) {
+GPSIQ_HD int carr_advance(double& x, double d, const BinadeTab& tab, int count, bool stop_at_wrap, bool& wrapped,
+                          double& margin) {
     const int count0 = count;
     wrapped = false;
     while (count > 0) {
-        const double x0 = x;
-        bool w = carr_step<TRACK>(x, d, margin);
-        count--;
-        if (w) { wrapped = true; if (stop_at_wrap) break; continue; }
-        if (count < 3) continue;
-        const int64_t b0 = f64_bits(x0), b1 = f64_bits(x);
-        if ((b0 >> 52) != (b1 >> 52)) continue;
-        w = carr_step<TRACK>(x, d, margin);
-        count--;
-        if (w) { wrapped = true; if (stop_at_wrap) break; continue; }
-        const int64_t b2 = f64_bits(x);
-        if ((b2 >> 52) != (b1 >> 52)) continue;
-        const int64_t delta = b2 - b1;
-        if (delta == 0) { count = 0; break; }
-        int64_t k, edge;
-        if (delta > 0) {
-            edge = ((b2 >> 52) + 1) << 52;
-            if (BITS_1 < edge) edge = BITS_1;
-            k = floor_div_pos(edge - 1 - b2, delta);
-        } else {
-            edge = (b2 >> 52) << 52;
-            k = floor_div_pos(b2 - edge - 1, -delta);
-        }
-        if (k > count) k = count;
-        x = bits_f64(b2 + k * delta);
-        count -= (int) k;
-        if (TRACK) {
-            // the last iterate of the run is the one closest to the edge it approaches
-            const double xe = bits_f64(edge);
-            const double m = (delta > 0 ? xe - x : x - xe) - pow2_of(b2 >> 52) * 0x1p-52;
+        int64_t gap;
+        const int k = run_in_binade<NCO_CARRIER>(x, tab, count, TRACK ? &gap : nullptr);
+        count -= k;
+        if (TRACK && k > 0) {
+            // the last iterate of the run is the one closest to the edge it approaches;
+            // one ulp of slack for the rounding of its sum
+            const double m = (double) (gap - 1) * pow2_of((f64_bits(x) >> 52) - 52);
             if (m < margin) margin = m;
         }
+        if (count == 0) break;
+        const bool w = carr_step<TRACK>(x, d, margin);
+        count--;
+        if (w) { wrapped = true; if (stop_at_wrap) break; }
     }
     return count0 - count;
 }
@@ -249,12 +279,13 @@ GPSIQ_HD int carr_advance(double& x, double d, int count, bool stop_at_wrap, boo
 GPSIQ_HD bool carr_step_speculable(double d) {
     const int64_t b = f64_bits(d) & 0x7fffffffffffffffLL;
     const int64_t e = b >> 52;
-    if (e == 0 || e >= 1021) return false;               // zero/denormal, or |d| >= 0.25
+    if (e == 0 || e >= 1021) return false;  // zero/denormal, or |d| >= 0.25
     if (d > 0.0) {
         // exclude d == 0 (mod 2^-53): lowest set bit of |d| at 2^-53 or above
         const int64_t m = (b & 0xfffffffffffffLL) | (1LL << 52);
+        const int64_t low = m & -m;  // lowest set bit of the significand
         int tz = 0;
-        while (!((m >> tz) & 1)) tz++;
+        while ((low >> tz) != 1) tz++;
         if ((int) e - 1075 + tz >= -53) return false;
     }
     return true;
@@ -262,8 +293,8 @@ GPSIQ_HD bool carr_step_speculable(double d) {
 
 // (1) speculative scan of one epoch from x (an estimate of the epoch's start
 // phase).  ck[t*ck_stride] receives the state at the start of tile t.
-GPSIQ_HD void spec_scan_epoch(double x, double d, int N, int T, int variant, double* ck, size_t ck_stride,
-                              CarrSpec& out) {
+GPSIQ_HD void spec_scan_epoch(double x, double d, const BinadeTab& tab, int N, int T, int variant, double* ck,
+                              size_t ck_stride, CarrSpec& out) {
     const int ntiles = (N + T - 1) / T;
     double margin = 1.0;
     bool seen_wrap = false;
@@ -278,7 +309,7 @@ GPSIQ_HD void spec_scan_epoch(double x, double d, int N, int T, int variant, dou
             int steps;
             if (!seen_wrap) {
                 double dummy = 1.0;
-                steps = carr_advance<false>(x, d, remaining, true, w, dummy);
+                steps = carr_advance<false>(x, d, tab, remaining, true, w, dummy);
                 if (w) {
                     seen_wrap = true;
                     if (variant == 1) x = (x + 0x1p-53 < 1.0) ? x + 0x1p-53 : x - 0x1p-53;  // other parity of the 2^-53 grid
@@ -287,7 +318,7 @@ GPSIQ_HD void spec_scan_epoch(double x, double d, int N, int T, int variant, dou
                     out.xw1 = x;
                 }
             } else {
-                steps = carr_advance<true>(x, d, remaining, false, w, margin);
+                steps = carr_advance<true>(x, d, tab, remaining, false, w, margin);
             }
             remaining -= steps;
             n += steps;
@@ -305,8 +336,8 @@ struct CarrInfo {   // per (epoch, channel): how the renderer obtains tile-start
 
 // (3) exact chaining of one epoch from the exact start x; returns the exact end
 // state.  ck0 is plane 0 of the checkpoint array for this (epoch, channel).
-GPSIQ_HD double chain_epoch(double x, double d, int N, int T, const CarrSpec& s0, const CarrSpec& s1, double* ck0,
-                            size_t ck_stride, CarrInfo& info, int& fell_back) {
+GPSIQ_HD double chain_epoch(double x, double d, const BinadeTab& tab, int N, int T, const CarrSpec& s0,
+                            const CarrSpec& s1, double* ck0, size_t ck_stride, CarrInfo& info, int& fell_back) {
     const int ntiles = (N + T - 1) / T;
     int n = 0, t = 0, remaining = 0;
     bool wrapped = false;
@@ -316,7 +347,7 @@ GPSIQ_HD double chain_epoch(double x, double d, int N, int T, const CarrSpec& s0
         ck0[(size_t) t * ck_stride] = x;
         remaining = (T < N - t * T) ? T : N - t * T;
         while (remaining > 0 && !wrapped) {
-            const int steps = carr_advance<false>(x, d, remaining, true, wrapped, dummy);
+            const int steps = carr_advance<false>(x, d, tab, remaining, true, wrapped, dummy);
             remaining -= steps;
             n += steps;
         }
@@ -347,17 +378,11 @@ GPSIQ_HD double chain_epoch(double x, double d, int N, int T, const CarrSpec& s0
     // fallback: finish the epoch serially, exact checkpoints for the remaining tiles
     fell_back++;
     bool w;
-    while (remaining > 0) {
-        const int steps = carr_advance<false>(x, d, remaining, false, w, dummy);
-        remaining -= steps;
-    }
+    while (remaining > 0) remaining -= carr_advance<false>(x, d, tab, remaining, false, w, dummy);
     for (; t < ntiles; t++) {
         ck0[(size_t) t * ck_stride] = x;
         remaining = (T < N - t * T) ? T : N - t * T;
-        while (remaining > 0) {
-            const int steps = carr_advance<false>(x, d, remaining, false, w, dummy);
-            remaining -= steps;
-        }
+        while (remaining > 0) remaining -= carr_advance<false>(x, d, tab, remaining, false, w, dummy);
     }
     return x;
 }
