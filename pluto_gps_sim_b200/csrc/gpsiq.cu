@@ -26,6 +26,7 @@
 
 #include "../../include/gpsiq.h"
 #include "nco_scan.cuh"
+#include "synth_fixed.cuh"
 
 using namespace gpsiq;
 
@@ -75,6 +76,10 @@ struct gpsiq_ctx {
     int ev_count;                    // steps recorded since gpsiq_timing_begin
     gpsiq_chan_desc* d_desc;
     int2* d_lut;          // [E][C][512]
+    int32_t* d_lutp;      // [E][C][512] packed (Q << 16) + I
+    int8_t* d_chips;      // [33][2048] +-1, index = polarity << 10 | chip
+    int* d_flags;         // [2][E]: amplitude sum per epoch, step-contract flag per epoch
+    int use_fixed;        // k_synth_fixed is eligible for this configuration
     double* d_code_ck;    // [E][ntiles][C]
     int* d_wrap_ck;       // [E][ntiles][C]
     double* d_carr_ck;    // [2][E][ntiles][C] two speculation planes (INT32 mode: uint32 phase as double, plane 0)
@@ -115,7 +120,8 @@ static int fail(gpsiq_ctx* ctx, int code, const char* what, cudaError_t ce) {
 // k_prepare: amplitude LUT per (epoch, slot)
 // ---------------------------------------------------------------------------
 __global__ void k_prepare(const gpsiq_chan_desc* __restrict__ desc, int2* __restrict__ lut,
-                          BinadeTab* __restrict__ tab, int carrier_mode, int* __restrict__ err) {
+                          int32_t* __restrict__ lutp, BinadeTab* __restrict__ tab, int* __restrict__ amp_sum,
+                          int* __restrict__ step_flag, int C, int carrier_mode, int* __restrict__ err) {
     const int ec = blockIdx.x;
     const gpsiq_chan_desc d = desc[ec];
     int2* out = lut + (size_t) ec * 512;
@@ -134,6 +140,14 @@ __global__ void k_prepare(const gpsiq_chan_desc* __restrict__ desc, int2* __rest
         int ip = __double2int_rz(__dmul_rn((double) c_cos512[k], d.gain));
         int qp = __double2int_rz(__dmul_rn((double) c_sin512[k], d.gain));
         out[k] = make_int2(ip, qp);
+        lutp[(size_t) ec * 512 + k] = qp * 65536 + ip;  // exact while the per-sample sums fit int16 (amp_sum)
+    }
+    if (threadIdx.x == 64) {
+        // |entry| <= 512*|gain| + 1: bound on this slot's share of |sum I|, |sum Q|
+        const double a = fabs(d.gain) * 512.0 + 1.0;
+        atomicAdd(&amp_sum[ec / C], a < 40000.0 ? (int) a : 40000);
+        // segment-list contract of k_synth_fixed: <= 4 carrier cycles and <= 2 code periods per 1024-sample tile
+        if (!(fabs(d.carr_step) <= 0x1p-8) || !(d.code_step <= 0.5)) atomicOr(&step_flag[ec / C], 1);
     }
 }
 
@@ -284,7 +298,8 @@ __global__ void __launch_bounds__(LANES_WARPS * 32)
 k_synth_lanes(const gpsiq_chan_desc* __restrict__ desc, const int2* __restrict__ lut,
               const double* __restrict__ code_ck, const int* __restrict__ wrap_ck,
               const double* __restrict__ carr_ck, size_t ck_plane, const CarrInfo* __restrict__ info,
-              const uint32_t* __restrict__ ca, int16_t* __restrict__ iq,
+              const uint32_t* __restrict__ ca, const int* __restrict__ amp_sum, const int* __restrict__ step_flag,
+              int only_flagged, int16_t* __restrict__ iq,
               int C, int N, int T, int ntiles, int tile_groups, int carrier_mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int2* s_lut = reinterpret_cast<int2*>(smem_raw);                       // [C][512]
@@ -292,6 +307,7 @@ k_synth_lanes(const gpsiq_chan_desc* __restrict__ desc, const int2* __restrict__
 
     const int e = blockIdx.x / tile_groups;
     const int tg = blockIdx.x - e * tile_groups;
+    if (only_flagged && !(amp_sum[e] > 32767 || step_flag[e])) return;  // rendered by k_synth_fixed
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const gpsiq_chan_desc* de = desc + (size_t) e * C;
 
@@ -559,8 +575,14 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
     ctx->C = cfg->max_chan;
     ctx->N = cfg->samples_per_epoch;
     ctx->E = cfg->max_epochs;
-    ctx->T = cfg->tile_samples ? cfg->tile_samples : 1024;
+    ctx->T = cfg->tile_samples ? cfg->tile_samples : FX_TILE;
     ctx->T = (ctx->T + 31) & ~31;
+    // the fixed-point kernel needs its own tile length, 16-byte aligned epochs, the float carrier and <= FX_MAXC slots
+    ctx->use_fixed = (cfg->kernel != GPSIQ_KERNEL_LANE_PER_CHANNEL) && ctx->T == FX_TILE && (ctx->N % 4 == 0) &&
+                     ctx->C <= FX_MAXC && cfg->carrier_mode == GPSIQ_CARRIER_FLOAT;
+    if (cfg->kernel == GPSIQ_KERNEL_FIXED_POINT && !ctx->use_fixed)
+        return fail(NULL, GPSIQ_ERR_ARG, "gpsiq_create: fixed-point kernel needs tile_samples 0/1024, samples_per_epoch % 4 == 0, "
+                    "max_chan <= 24 and the float carrier", cudaSuccess);
     ctx->ntiles = (ctx->N + ctx->T - 1) / ctx->T;
     CU(cudaSetDevice(cfg->device));
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -570,6 +592,10 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
     const size_t ck = EC * ctx->ntiles;
     CU(cudaMalloc(&ctx->d_desc, EC * sizeof(gpsiq_chan_desc)));
     CU(cudaMalloc(&ctx->d_lut, EC * 512 * sizeof(int2)));
+    CU(cudaMalloc(&ctx->d_lutp, EC * 512 * sizeof(int32_t)));
+    CU(cudaMalloc(&ctx->d_chips, 33 * 2048));
+    CU(cudaMalloc(&ctx->d_flags, 2 * (size_t) ctx->E * sizeof(int)));
+    CU(cudaMemset(ctx->d_flags, 0, 2 * (size_t) ctx->E * sizeof(int)));
     CU(cudaMalloc(&ctx->d_code_ck, ck * sizeof(double)));
     CU(cudaMalloc(&ctx->d_wrap_ck, ck * sizeof(int)));
     ctx->ck_plane = ck;
@@ -597,6 +623,23 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
         for (int i = 0; i < GPSIQ_CA_LEN; i++) h_ca[prn * CA_WORDS + (i >> 5)] |= (uint32_t) chips[i] << (i & 31);
     }
     CU(cudaMemcpy(ctx->d_ca, h_ca, sizeof h_ca, cudaMemcpyHostToDevice));
+    {
+        int8_t* h_chips = (int8_t*) malloc(33 * 2048);
+        if (!h_chips) return GPSIQ_ERR_NOMEM;
+        memset(h_chips, 1, 33 * 2048);
+        for (int prn = 1; prn <= 32; prn++) {
+            uint8_t chips[GPSIQ_CA_LEN];
+            ca_generate(prn, chips);
+            for (int pol = 0; pol < 2; pol++)
+                for (int i = 0; i < GPSIQ_CA_LEN; i++)  // BPSK sign: +1 iff NAV bit == chip (plutogpssim.c:2701, 2732, 2737)
+                    h_chips[prn * 2048 + pol * 1024 + i] = (chips[i] == pol) ? 1 : -1;
+        }
+        cudaError_t ce2 = cudaMemcpy(ctx->d_chips, h_chips, 33 * 2048, cudaMemcpyHostToDevice);
+        free(h_chips);
+        CU(ce2);
+    }
+    if (ctx->use_fixed)
+        CU(cudaFuncSetAttribute(k_synth_fixed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fx_smem_bytes(ctx->C)));
     const size_t smem_lanes = (size_t) ctx->C * 512 * sizeof(int2) + (size_t) ctx->C * 33 * 4;
     CU(cudaFuncSetAttribute(k_synth_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_lanes));
     *out = ctx;
@@ -607,7 +650,7 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_desc); cudaFree(ctx->d_lut); cudaFree(ctx->d_code_ck); cudaFree(ctx->d_wrap_ck);
+    cudaFree(ctx->d_desc); cudaFree(ctx->d_lut); cudaFree(ctx->d_lutp); cudaFree(ctx->d_chips); cudaFree(ctx->d_flags); cudaFree(ctx->d_code_ck); cudaFree(ctx->d_wrap_ck);
     cudaFree(ctx->d_carr_ck); cudaFree(ctx->d_tab); cudaFree(ctx->d_spec); cudaFree(ctx->d_info); cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_carr_trace); cudaFree(ctx->d_ca);
     cudaFree(ctx->d_iq); cudaFree(ctx->d_sums); cudaFree(ctx->d_err);
     for (int i = 0; i < TIMING_RING; i++)
@@ -621,7 +664,9 @@ static int enqueue_scan(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_e
     const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
     const int EC = n_epochs * C;
     if (ctx->ev_count < TIMING_RING) CU(cudaEventRecord(ctx->ev[ctx->ev_count][0], st));
-    k_prepare<<<EC, 128, 0, st>>>(desc_dev, ctx->d_lut, ctx->d_tab, ctx->cfg.carrier_mode, ctx->d_err);
+    CU(cudaMemsetAsync(ctx->d_flags, 0, 2 * (size_t) ctx->E * sizeof(int), st));
+    k_prepare<<<EC, 128, 0, st>>>(desc_dev, ctx->d_lut, ctx->d_lutp, ctx->d_tab, ctx->d_flags, ctx->d_flags + ctx->E, C,
+                                  ctx->cfg.carrier_mode, ctx->d_err);
     k_scan_code<<<(EC + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_code_ck, ctx->d_wrap_ck, EC, C, N, T, ntiles);
     if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && ctx->cfg.reserved[0] == 0) {
         const int chains = EC * 2;
@@ -647,9 +692,18 @@ static int enqueue_render(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n
     if (ctx->ev_count < TIMING_RING) CU(cudaEventRecord(ctx->ev[ctx->ev_count][1], st));
     const int tile_groups = (ntiles + LANES_WARPS - 1) / LANES_WARPS;
     const size_t smem = (size_t) C * 512 * sizeof(int2) + (size_t) C * 33 * 4;
+    if (ctx->use_fixed) {
+        const int groups = (ntiles + FX_TILES_PER_CTA - 1) / FX_TILES_PER_CTA;
+        k_synth_fixed<<<n_epochs * groups, FX_THREADS, fx_smem_bytes(C), st>>>(
+            desc_dev, ctx->d_lutp, ctx->d_tab, ctx->d_code_ck, ctx->d_wrap_ck, ctx->d_carr_ck, ctx->ck_plane,
+            ctx->d_info, ctx->d_chips, ctx->d_flags, ctx->d_flags + ctx->E, iq_dev, ctx->d_err, C, N, ntiles, groups);
+        ctx->launches += 1;
+    }
+    // all epochs (lane kernel selected) or only those outside the fixed-point kernel's contract
     k_synth_lanes<<<n_epochs * tile_groups, LANES_WARPS * 32, smem, st>>>(
         desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, ctx->d_carr_ck, ctx->ck_plane, ctx->d_info, ctx->d_ca,
-        iq_dev, C, N, T, ntiles, tile_groups, ctx->cfg.carrier_mode);
+        ctx->d_flags, ctx->d_flags + ctx->E, ctx->use_fixed, iq_dev, C, N, T, ntiles, tile_groups,
+        ctx->cfg.carrier_mode);
     if (ctx->ev_count < TIMING_RING) {
         CU(cudaEventRecord(ctx->ev[ctx->ev_count][2], st));
         ctx->ev_count++;

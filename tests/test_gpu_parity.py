@@ -10,7 +10,7 @@ from pluto_gps_sim_b200 import Synthesizer, capi, checksum_host
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [capi.KERNEL_LANE_PER_CHANNEL]
+KERNELS = [capi.KERNEL_LANE_PER_CHANNEL, capi.KERNEL_FIXED_POINT]
 
 
 def first_diff(a, b):
@@ -32,7 +32,7 @@ def test_config1_static12_bit_exact_vs_reference_golden(kernel):
     assert np.array_equal(trace, want)
 
 
-@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("kernel", [capi.KERNEL_LANE_PER_CHANNEL, capi.KERNEL_AUTO])
 def test_config3_allsky32_bit_exact_vs_reference_golden(kernel):
     meta = ol.load_golden_meta("allsky32")
     desc = ol.load_golden_desc("allsky32")
@@ -62,7 +62,8 @@ def test_config2_circle_310_epochs_batched_with_carry(kernel):
 def test_tile_size_independence(tile):
     desc = ol.load_golden_desc("static12")[:2]
     want, _ = ol.oracle_synth(desc, 50000)
-    with Synthesizer(max_chan=12, samples_per_epoch=50000, max_epochs=2, tile_samples=tile) as s:
+    with Synthesizer(max_chan=12, samples_per_epoch=50000, max_epochs=2, tile_samples=tile,
+                     kernel=capi.KERNEL_LANE_PER_CHANNEL) as s:
         got = s.synth(desc)
     assert first_diff(got, want) is None
 
@@ -76,15 +77,68 @@ def test_ragged_epoch_lengths(n):
     assert first_diff(got, want) is None
 
 
-def test_inactive_slots_and_empty_epoch():
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_inactive_slots_and_empty_epoch(kernel):
     desc = ol.load_golden_desc("static12")[:2].copy()
     desc[0, 3]["prn"] = 0
     desc[1, :]["prn"] = 0          # an epoch with no satellites: all-zero I/Q
     want, _ = ol.oracle_synth(desc, 20000)
-    with Synthesizer(max_chan=12, samples_per_epoch=20000, max_epochs=2) as s:
+    with Synthesizer(max_chan=12, samples_per_epoch=20000, max_epochs=2, kernel=kernel) as s:
         got = s.synth(desc)
     assert first_diff(got, want) is None
     assert not got[1].any()
+
+
+@pytest.mark.parametrize("n", [8, 1020, 1028, 4100, 30004])
+def test_fixed_point_kernel_ragged_epochs(n):
+    desc = ol.load_golden_desc("circle12")[300:303]
+    want, _ = ol.oracle_synth(desc, n)
+    with Synthesizer(max_chan=12, samples_per_epoch=n, max_epochs=3, kernel=capi.KERNEL_FIXED_POINT) as s:
+        got = s.synth(desc)
+    assert first_diff(got, want) is None
+
+
+def test_fixed_point_kernel_routes_out_of_contract_epochs_to_lane_kernel():
+    """Huge gains (packed int16 accumulation could overflow) and extreme Doppler
+    (segment lists too long) are rendered by the lane-per-channel kernel; the
+    reference's (short) wrap-around is reproduced either way."""
+    desc = ol.load_golden_desc("static12")[:4].copy()
+    desc[1]["gain"] *= 40.0                    # |sum| far beyond int16: the reference wraps, so must we
+    desc[2, 5]["carr_step"] = 0.0123           # ~32 kHz Doppler at 2.6 MS/s
+    desc[3, 7]["carr_step"] = -0.0077
+    want, wt = ol.oracle_synth(desc, 40000)
+    with Synthesizer(max_chan=12, samples_per_epoch=40000, max_epochs=4, kernel=capi.KERNEL_FIXED_POINT) as s:
+        got = s.synth(desc)
+        gt = s.carrier_trace(4)
+    assert first_diff(got, want) is None
+    assert np.array_equal(gt, wt)
+
+
+def test_fixed_point_kernel_random_descriptors():
+    """Synthetic descriptors over the whole contract range (both Doppler signs up to
+    ~9 kHz, code phases near the wrap, NAV edges in the first tile)."""
+    rng = np.random.default_rng(7)
+    E, Cn, n = 6, 12, 66000
+    desc = np.zeros((E, Cn), capi.DESC_DTYPE)
+    for e in range(E):
+        for c in range(Cn):
+            f = rng.uniform(-9000, 9000) if c % 4 else rng.uniform(-40, 40)
+            d = desc[e, c]
+            d["prn"] = int(rng.integers(1, 33))
+            d["ms0"] = int(rng.integers(0, 1000))
+            d["navbits"] = int(rng.integers(0, 2 ** 62))
+            d["code_phase0"] = [rng.uniform(0, 1023), 1022.9999, 0.0, 1e-7][int(rng.integers(0, 4))]
+            d["code_step"] = (1.023e6 + f / 1540.0) / 2.6e6
+            d["carr_step"] = f / 2.6e6
+            d["carr_phase0"] = rng.random()
+            d["gain"] = rng.uniform(0.05, 1.5)
+            d["flags"] = 1 if (e == 0 or rng.random() < 0.1) else 0
+    want, wt = ol.oracle_synth(desc, n)
+    with Synthesizer(max_chan=Cn, samples_per_epoch=n, max_epochs=E, kernel=capi.KERNEL_FIXED_POINT) as s:
+        got = s.synth(desc)
+        gt = s.carrier_trace(E)
+    assert first_diff(got, want) is None
+    assert np.array_equal(gt, wt)
 
 
 def test_integer_carrier_mode_vs_oracle():
