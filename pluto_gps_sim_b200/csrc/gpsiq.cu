@@ -68,6 +68,8 @@ static void ca_generate(int prn, uint8_t* chips) {
 // ---------------------------------------------------------------------------
 #define TIMING_RING 64
 
+#define FX_SUB_EPOCHS 16  // tile records of this many epochs (~56 MB at 12 slots) stay L2 resident between the two kernels
+
 struct gpsiq_ctx {
     gpsiq_config cfg;
     int C, N, T, ntiles, E;
@@ -80,6 +82,8 @@ struct gpsiq_ctx {
     int8_t* d_chips;      // [33][2048] +-1, index = polarity << 10 | chip
     int* d_flags;         // [2][E]: amplitude sum per epoch, step-contract flag per epoch
     int use_fixed;        // k_synth_fixed is eligible for this configuration
+    unsigned char* d_recs; // [FX_SUB_EPOCHS][ntiles] tile records (synth_fixed.cuh)
+    uint32_t* d_fixmasks;  // [FX_SUB_EPOCHS][ntiles][C][4]
     double* d_code_ck;    // [E][ntiles][C]
     int* d_wrap_ck;       // [E][ntiles][C]
     double* d_carr_ck;    // [2][E][ntiles][C] two speculation planes (INT32 mode: uint32 phase as double, plane 0)
@@ -261,28 +265,69 @@ __global__ void k_carr_speculate(const gpsiq_chan_desc* __restrict__ desc, const
     spec[(size_t) ec * 2 + v] = out;
 }
 
-__global__ void k_carr_chain(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
-                             const CarrSpec* __restrict__ spec,
-                             double* __restrict__ carr_ck, double* __restrict__ carr_state,
-                             double* __restrict__ carr_trace, CarrInfo* __restrict__ info, int* __restrict__ fallbacks,
-                             int E, int C, int N, int T, int ntiles) {
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (c >= C || (threadIdx.x & 31)) return;
+// Per-epoch inputs of the chain, staged through shared memory: the chain is one
+// latency-bound thread, so the other 31 lanes of its warp prefetch the next
+// epoch's descriptor, binade table and speculation results while lane 0 works.
+struct ChainStage {
+    gpsiq_chan_desc d;   // 64 B
+    BinadeTab tab;       // 200 B
+    CarrSpec s0, s1;     // 2 x 32 B
+};
+#define CHAIN_WORDS ((int) (sizeof(ChainStage) / 4))
+
+__device__ __forceinline__ uint32_t chain_stage_word(const gpsiq_chan_desc* desc, const BinadeTab* tabs,
+                                                     const CarrSpec* spec, size_t ec, int w) {
+    constexpr int WD = sizeof(gpsiq_chan_desc) / 4, WT = sizeof(BinadeTab) / 4;
+    if (w < WD) return ((const uint32_t*) (desc + ec))[w];
+    if (w < WD + WT) return ((const uint32_t*) (tabs + ec * 2 + 1))[w - WD];
+    return ((const uint32_t*) (spec + ec * 2))[w - WD - WT];
+}
+
+__global__ void __launch_bounds__(32)
+k_carr_chain(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
+             const CarrSpec* __restrict__ spec, double* __restrict__ carr_ck, double* __restrict__ carr_state,
+             double* __restrict__ carr_trace, CarrInfo* __restrict__ info, int* __restrict__ fallbacks, int E, int C,
+             int N, int T, int ntiles) {
+    static_assert(sizeof(ChainStage) % 8 == 0 && sizeof(ChainStage) / 4 <= 96, "stage layout");
+    __shared__ __align__(8) uint32_t stage[2][96];
+    const int c = blockIdx.x, lane = threadIdx.x;
+    if (c >= C) return;
     double x = carr_state[c];
     int fb = 0;
+    uint32_t r0, r1, r2;
+    r0 = chain_stage_word(desc, tabs, spec, (size_t) c, lane);
+    r1 = chain_stage_word(desc, tabs, spec, (size_t) c, lane + 32);
+    r2 = (lane + 64 < CHAIN_WORDS) ? chain_stage_word(desc, tabs, spec, (size_t) c, lane + 64) : 0u;
     for (int e = 0; e < E; e++) {
-        const size_t ec = (size_t) e * C + c;
-        const gpsiq_chan_desc d = desc[ec];
-        if (d.prn <= 0) { carr_trace[ec] = x; continue; }
-        if (d.flags & GPSIQ_FLAG_RESET_CARRIER) x = d.carr_phase0;
-        CarrInfo inf;
-        x = chain_epoch(x, d.carr_step, tabs[ec * 2 + 1], N, T, spec[ec * 2], spec[ec * 2 + 1], carr_ck + (size_t) e * ntiles * C + c,
-                        (size_t) C, inf, fb);
-        info[ec] = inf;
-        carr_trace[ec] = x;
+        uint32_t* sb = stage[e & 1];
+        sb[lane] = r0; sb[lane + 32] = r1; sb[lane + 64] = r2;
+        __syncwarp();
+        if (e + 1 < E) {  // prefetch the next epoch while lane 0 chains this one
+            const size_t en = (size_t) (e + 1) * C + c;
+            r0 = chain_stage_word(desc, tabs, spec, en, lane);
+            r1 = chain_stage_word(desc, tabs, spec, en, lane + 32);
+            r2 = (lane + 64 < CHAIN_WORDS) ? chain_stage_word(desc, tabs, spec, en, lane + 64) : 0u;
+        }
+        if (lane == 0) {
+            const ChainStage& st = *reinterpret_cast<const ChainStage*>(sb);
+            const size_t ec = (size_t) e * C + c;
+            if (st.d.prn <= 0) {
+                carr_trace[ec] = x;
+            } else {
+                if (st.d.flags & GPSIQ_FLAG_RESET_CARRIER) x = st.d.carr_phase0;
+                CarrInfo inf;
+                x = chain_epoch(x, st.d.carr_step, st.tab, N, T, st.s0, st.s1, carr_ck + (size_t) e * ntiles * C + c,
+                                (size_t) C, inf, fb);
+                info[ec] = inf;
+                carr_trace[ec] = x;
+            }
+        }
+        __syncwarp();
     }
-    carr_state[c] = x;
-    if (fb) atomicAdd(fallbacks, fb);
+    if (lane == 0) {
+        carr_state[c] = x;
+        if (fb) atomicAdd(fallbacks, fb);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -638,8 +683,12 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
         free(h_chips);
         CU(ce2);
     }
-    if (ctx->use_fixed)
+    if (ctx->use_fixed) {
         CU(cudaFuncSetAttribute(k_synth_fixed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fx_smem_bytes(ctx->C)));
+        const size_t tiles = (size_t) FX_SUB_EPOCHS * ctx->ntiles;
+        CU(cudaMalloc(&ctx->d_recs, tiles * fx_rec_bytes(ctx->C)));
+        CU(cudaMalloc(&ctx->d_fixmasks, tiles * fx_fixmask_words(ctx->C) * 4));
+    }
     const size_t smem_lanes = (size_t) ctx->C * 512 * sizeof(int2) + (size_t) ctx->C * 33 * 4;
     CU(cudaFuncSetAttribute(k_synth_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_lanes));
     *out = ctx;
@@ -650,7 +699,8 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_desc); cudaFree(ctx->d_lut); cudaFree(ctx->d_lutp); cudaFree(ctx->d_chips); cudaFree(ctx->d_flags); cudaFree(ctx->d_code_ck); cudaFree(ctx->d_wrap_ck);
+    cudaFree(ctx->d_desc); cudaFree(ctx->d_lut); cudaFree(ctx->d_lutp); cudaFree(ctx->d_chips); cudaFree(ctx->d_flags);
+    cudaFree(ctx->d_recs); cudaFree(ctx->d_fixmasks); cudaFree(ctx->d_code_ck); cudaFree(ctx->d_wrap_ck);
     cudaFree(ctx->d_carr_ck); cudaFree(ctx->d_tab); cudaFree(ctx->d_spec); cudaFree(ctx->d_info); cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_carr_trace); cudaFree(ctx->d_ca);
     cudaFree(ctx->d_iq); cudaFree(ctx->d_sums); cudaFree(ctx->d_err);
     for (int i = 0; i < TIMING_RING; i++)
@@ -694,10 +744,20 @@ static int enqueue_render(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n
     const size_t smem = (size_t) C * 512 * sizeof(int2) + (size_t) C * 33 * 4;
     if (ctx->use_fixed) {
         const int groups = (ntiles + FX_TILES_PER_CTA - 1) / FX_TILES_PER_CTA;
-        k_synth_fixed<<<n_epochs * groups, FX_THREADS, fx_smem_bytes(C), st>>>(
-            desc_dev, ctx->d_lutp, ctx->d_tab, ctx->d_code_ck, ctx->d_wrap_ck, ctx->d_carr_ck, ctx->ck_plane,
-            ctx->d_info, ctx->d_chips, ctx->d_flags, ctx->d_flags + ctx->E, iq_dev, ctx->d_err, C, N, ntiles, groups);
-        ctx->launches += 1;
+        const int tgroups = (ntiles + 31) / 32;
+        for (int e0 = 0; e0 < n_epochs; e0 += FX_SUB_EPOCHS) {
+            const int ne = n_epochs - e0 < FX_SUB_EPOCHS ? n_epochs - e0 : FX_SUB_EPOCHS;
+            CU(cudaMemsetAsync(ctx->d_fixmasks, 0, (size_t) ne * ntiles * fx_fixmask_words(C) * 4, st));
+            const int warps = ne * 2 * C * tgroups;
+            k_tile_prologue<<<(warps + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_code_ck, ctx->d_wrap_ck,
+                                                             ctx->d_carr_ck, ctx->ck_plane, ctx->d_info, ctx->d_flags,
+                                                             ctx->d_flags + ctx->E, ctx->d_recs, ctx->d_fixmasks, e0, ne,
+                                                             C, N, ntiles);
+            k_synth_fixed<<<ne * groups, FX_THREADS, fx_smem_bytes(C), st>>>(
+                desc_dev, ctx->d_lutp, ctx->d_tab, ctx->d_recs, ctx->d_fixmasks, ctx->d_chips, ctx->d_flags,
+                ctx->d_flags + ctx->E, iq_dev, e0, C, N, ntiles, groups);
+            ctx->launches += 2;
+        }
     }
     // all epochs (lane kernel selected) or only those outside the fixed-point kernel's contract
     k_synth_lanes<<<n_epochs * tile_groups, LANES_WARPS * 32, smem, st>>>(

@@ -34,7 +34,6 @@
 #define FX_THREADS 128
 #define FX_RUN 8
 #define FX_TILE (FX_THREADS * FX_RUN)
-#define FX_SEGMAX 96
 #define FX_MAXC 24
 #define FX_TILES_PER_CTA 8
 
@@ -70,110 +69,62 @@ __device__ __forceinline__ int64_t fx_scale_delta(int64_t delta, int sh) {
 __device__ __forceinline__ int fx_carr_bi(uint64_t f) { return min(__clzll((long long) f), NBINADE - 1); }
 __device__ __forceinline__ int fx_code_bi(uint64_t g) { return min(__clzll((long long) (g & ~FX_POL)) - 1, NBINADE - 1); }
 
-struct FxSmem {
-    int C;
-    int32_t* lut;      // [C][512]  packed (Q << 16) + I
-    int8_t* chip;      // [C][2048] +-1, index = nav polarity << 10 | chip
-    uint64_t* slotF;   // [C][FX_THREADS]
-    uint64_t* slotG;   // [C][FX_THREADS]
-    int64_t* dF;       // [C][NBINADE]
-    int64_t* dG;       // [C][NBINADE]
-    BinadeTab* tab;    // [C][2]
-    uint64_t* segF;    // [2C][FX_SEGMAX]
-    int16_t* segn;     // [2C][FX_SEGMAX]
-    int* nseg;         // [2C]
-    int32_t* delta;    // [FX_TILE]
-    uint32_t* fixmask; // [C][FX_THREADS/32]
-    uint16_t* work;    // [C * FX_THREADS]
-    int* nwork;
-};
 
-__host__ __device__ inline size_t fx_smem_bytes(int C) {
-    size_t b = 0;
-    b += (size_t) C * 512 * 4;                 // lut
-    b += (size_t) C * 2048;                    // chip
-    b += (size_t) C * FX_THREADS * 8 * 2;      // slotF, slotG
-    b += (size_t) C * NBINADE * 8 * 2;         // dF, dG
-    b += (size_t) C * 2 * sizeof(BinadeTab);   // tab
-    b += (size_t) C * 2 * FX_SEGMAX * 8;       // segF
-    b += (size_t) C * 2 * FX_SEGMAX * 2;       // segn
-    b += (size_t) C * 2 * 4;                   // nseg
-    b += (size_t) FX_TILE * 4;                 // delta
-    b += (size_t) C * (FX_THREADS / 32) * 4;   // fixmask
-    b += (size_t) C * FX_THREADS * 2;          // work
-    b += 16;                                   // nwork + pad
-    return b + 64;
-}
+// ---- per-tile record written by k_tile_prologue, read by k_synth_fixed ------
+// One record per (epoch, tile): the segment lists of the 2C (channel, NCO) tasks,
+// the segment index of every 8-sample run, and which (channel, run) pairs contain
+// a segment boundary.  Layout (bytes), C = channel slots:
+//   segF   [C][FX_SCARR + FX_SCODE] u64   fixed-point state at each segment start
+//   segn   [C][FX_SCARR + FX_SCODE] u16   tile-relative sample index of each start
+//   runseg [2C][FX_THREADS]         u8    segment index of each run's first sample
+//   nseg   [2C]                     u16
+// plus, in a separate array zeroed by the host before the prologue,
+//   fixmask[C][FX_THREADS/32]       u32   bit r: run r of the channel contains a segment boundary
+#define FX_SCARR 48
+#define FX_SCODE 24
+#define FX_SPER (FX_SCARR + FX_SCODE)
 
-__device__ __forceinline__ void fx_carve(FxSmem& s, unsigned char* base, int C) {
-    // 8-byte members first
-    s.C = C;
-    s.slotF = (uint64_t*) base;               base += (size_t) C * FX_THREADS * 8;
-    s.slotG = (uint64_t*) base;               base += (size_t) C * FX_THREADS * 8;
-    s.dF = (int64_t*) base;                   base += (size_t) C * NBINADE * 8;
-    s.dG = (int64_t*) base;                   base += (size_t) C * NBINADE * 8;
-    s.tab = (BinadeTab*) base;                base += (size_t) C * 2 * sizeof(BinadeTab);
-    s.segF = (uint64_t*) base;                base += (size_t) C * 2 * FX_SEGMAX * 8;
-    s.lut = (int32_t*) base;                  base += (size_t) C * 512 * 4;
-    s.delta = (int32_t*) base;                base += (size_t) FX_TILE * 4;
-    s.nseg = (int*) base;                     base += (size_t) C * 2 * 4;
-    s.fixmask = (uint32_t*) base;             base += (size_t) C * (FX_THREADS / 32) * 4;
-    s.nwork = (int*) base;                    base += 16;
-    s.segn = (int16_t*) base;                 base += (size_t) C * 2 * FX_SEGMAX * 2;
-    s.work = (uint16_t*) base;                base += (size_t) C * FX_THREADS * 2;
-    s.chip = (int8_t*) base;
-}
+__host__ __device__ inline size_t fx_rec_segF(int C) { (void) C; return 0; }
+__host__ __device__ inline size_t fx_rec_segn(int C) { return (size_t) C * FX_SPER * 8; }
+__host__ __device__ inline size_t fx_rec_runseg(int C) { return fx_rec_segn(C) + (size_t) C * FX_SPER * 2; }
+__host__ __device__ inline size_t fx_rec_nseg(int C) { return fx_rec_runseg(C) + (size_t) 2 * C * FX_THREADS; }
+__host__ __device__ inline size_t fx_rec_bytes(int C) { return (fx_rec_nseg(C) + (size_t) 2 * C * 2 + 15) & ~(size_t) 15; }
+__host__ __device__ inline size_t fx_fixmask_words(int C) { return (size_t) C * (FX_THREADS / 32); }
+// segment storage of task (c, nco) inside a record: carrier lists first in each channel's block
+__host__ __device__ inline int fx_seg_base(int c, int is_carrier) { return c * FX_SPER + (is_carrier ? 0 : FX_SCARR); }
+__host__ __device__ inline int fx_seg_cap(int is_carrier) { return is_carrier ? FX_SCARR : FX_SCODE; }
 
-// Contribution of channel c to sample j of run r, extrapolating the run's start state:
-// exactly what the main pass adds (shared by the fix-up pass for the "wrong" value).
-__device__ __forceinline__ int32_t fx_extrapolated(const FxSmem& s, int c, int r, int j) {
-    const uint64_t f0 = s.slotF[c * FX_THREADS + r], g0 = s.slotG[c * FX_THREADS + r];
-    const uint64_t f = f0 + (uint64_t) j * (uint64_t) s.dF[c * NBINADE + fx_carr_bi(f0)];
-    const uint64_t g = g0 + (uint64_t) j * (uint64_t) s.dG[c * NBINADE + fx_code_bi(g0)];
-    return s.lut[c * 512 + (int) (f >> 55)] * (int32_t) s.chip[c * 2048 + (int) (g >> 53)];
-}
-
-// Exact fixed-point state of one NCO at tile sample n, from its segment list.
-__device__ __forceinline__ uint64_t fx_exact(const FxSmem& s, int task, int n, const int64_t* dtab, bool code) {
-    const int16_t* sn = s.segn + task * FX_SEGMAX;
-    int lo = 0, hi = s.nseg[task] - 1;
-    while (lo < hi) {  // last segment with start <= n
-        const int mid = (lo + hi + 1) >> 1;
-        if (sn[mid] <= n) lo = mid; else hi = mid - 1;
-    }
-    const uint64_t f0 = s.segF[task * FX_SEGMAX + lo];
-    const int bi = code ? fx_code_bi(f0) : fx_carr_bi(f0);
-    return f0 + (uint64_t) (n - sn[lo]) * (uint64_t) dtab[bi];
-}
-
-// Tile prologue for one (channel, NCO): segment list + per-run start states.
+// Tile prologue for one (epoch, tile, channel, NCO): walk the tile's segments from
+// the exact tile-start state.  One thread per task; a warp holds 32 consecutive
+// tiles of the same (epoch, channel, NCO), so its lanes see the same step and
+// similar segment statistics.
 template <int MODE>
-__device__ void fx_prologue(FxSmem& s, int c, double x, double d, int len, int icode, int kbit, uint64_t navbits,
-                            int* err) {
-    const int task = c * 2 + (MODE == NCO_CARRIER ? 1 : 0);
-    const BinadeTab& tab = s.tab[task];
-    const int64_t* dtab = (MODE == NCO_CARRIER ? s.dF : s.dG) + c * NBINADE;
-    uint64_t* slot = (MODE == NCO_CARRIER ? s.slotF : s.slotG) + c * FX_THREADS;
-    uint64_t* segF = s.segF + task * FX_SEGMAX;
-    int16_t* segn = s.segn + task * FX_SEGMAX;
-    int n = 0, nseg = 0;
+__device__ __forceinline__ void fx_tile_walk(unsigned char* rec, uint32_t* fixmask, int C, int c, const BinadeTab& tab,
+                                             double x, double d, int len, int icode, int kbit, uint64_t navbits,
+                                             int* overflow) {
+    constexpr int IS_CARR = (MODE == NCO_CARRIER) ? 1 : 0;
+    const int task = c * 2 + IS_CARR;
+    uint64_t* segF = (uint64_t*) (rec + fx_rec_segF(C)) + fx_seg_base(c, IS_CARR);
+    uint16_t* segn = (uint16_t*) (rec + fx_rec_segn(C)) + fx_seg_base(c, IS_CARR);
+    uint32_t* runseg = (uint32_t*) (rec + fx_rec_runseg(C) + (size_t) task * FX_THREADS);
+    fixmask += c * (FX_THREADS / 32);
+    int n = 0, nseg = 0, rnext = 0;
+    uint32_t word = 0;
     while (n < len) {
-        if (nseg >= FX_SEGMAX) { atomicExch(err, 0x40000000 | task); break; }  // outside the step contract
+        if (nseg >= fx_seg_cap(IS_CARR)) { *overflow = 1; break; }
         const uint32_t pol = (uint32_t) (navbits >> (kbit & 63)) & 1u;
-        const uint64_t f0 = (MODE == NCO_CARRIER) ? fx_carr_fixed(x) : fx_code_fixed(x, pol);
-        segn[nseg] = (int16_t) n;
-        segF[nseg] = f0;
-        nseg++;
+        segF[nseg] = (MODE == NCO_CARRIER) ? fx_carr_fixed(x) : fx_code_fixed(x, pol);
+        segn[nseg] = (uint16_t) n;
         if (n & (FX_RUN - 1)) {  // a boundary inside a run: that (channel, run) needs a fix-up
             const int r = n >> 3;
-            const uint32_t bit = 1u << (r & 31);
-            const uint32_t old = atomicOr(&s.fixmask[c * (FX_THREADS / 32) + (r >> 5)], bit);
-            if (!(old & bit)) s.work[atomicAdd(s.nwork, 1)] = (uint16_t) (c * FX_THREADS + r);
+            atomicOr(&fixmask[r >> 5], 1u << (r & 31));
         }
         const int k = run_in_binade<MODE>(x, tab, len - 1 - n);  // samples n .. n+k share the segment
-        const int64_t df = dtab[(MODE == NCO_CARRIER) ? fx_carr_bi(f0) : fx_code_bi(f0)];
-        for (int r = (n + FX_RUN - 1) >> 3; (r << 3) <= n + k; r++)
-            slot[r] = f0 + (uint64_t) ((r << 3) - n) * (uint64_t) df;
+        for (; (rnext << 3) <= n + k; rnext++) {                 // runs whose first sample lies in it
+            word |= (uint32_t) nseg << ((rnext & 3) * 8);
+            if ((rnext & 3) == 3) { runseg[rnext >> 2] = word; word = 0; }
+        }
+        nseg++;
         n += k + 1;
         if (n < len) {  // true step into the next segment
             int w = 0;
@@ -183,40 +134,138 @@ __device__ void fx_prologue(FxSmem& s, int c, double x, double d, int len, int i
             }
         }
     }
-    s.nseg[task] = nseg;
+    if (rnext & 3) runseg[rnext >> 2] = word;
+    ((uint16_t*) (rec + fx_rec_nseg(C)))[task] = (uint16_t) nseg;
+}
+
+__global__ void __launch_bounds__(128)
+k_tile_prologue(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
+                const double* __restrict__ code_ck, const int* __restrict__ wrap_ck,
+                const double* __restrict__ carr_ck, size_t ck_plane, const CarrInfo* __restrict__ info,
+                const int* __restrict__ amp_sum, int* __restrict__ step_flag, unsigned char* __restrict__ recs,
+                uint32_t* __restrict__ fixmasks, int e0, int E, int C, int N, int ntiles) {
+    __shared__ BinadeTab s_tab[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tgroups = (ntiles + 31) / 32;
+    int w = blockIdx.x * 4 + warp;  // warp id -> (epoch, task, group of 32 tiles)
+    const int tg = w % tgroups; w /= tgroups;
+    const int task = w % (2 * C);
+    const int e = e0 + w / (2 * C);
+    if (e >= e0 + E) return;
+    const int c = task >> 1;
+    const gpsiq_chan_desc d = desc[(size_t) e * C + c];
+    const int t = tg * 32 + lane;
+    const size_t rec_bytes = fx_rec_bytes(C);
+    const size_t tile_id = (size_t) (e - e0) * ntiles + (t < ntiles ? t : 0);
+    unsigned char* rec = recs + tile_id * rec_bytes;
+    uint32_t* fixmask = fixmasks + tile_id * fx_fixmask_words(C);
+    if (d.prn <= 0 || amp_sum[e] > 32767 || (step_flag[e] & 1)) {
+        if (t < ntiles) ((uint16_t*) (rec + fx_rec_nseg(C)))[task] = 0;
+        return;
+    }
+    for (int i = lane; i < (int) (sizeof(BinadeTab) / 4); i += 32)
+        ((uint32_t*) &s_tab[warp])[i] = ((const uint32_t*) (tabs + ((size_t) e * C + c) * 2 + (task & 1)))[i];
+    __syncwarp();
+    if (t >= ntiles) return;
+    const int n0 = t * FX_TILE;
+    const int len = min(FX_TILE, N - n0);
+    const size_t o = ((size_t) e * ntiles + t) * C + c;
+    int overflow = 0;
+    if (task & 1) {
+        const CarrInfo inf = info[(size_t) e * C + c];
+        double ph;
+        if (n0 < inf.n1 || inf.n1 >= N) ph = carr_ck[o];
+        else ph = __dadd_rn(carr_ck[(size_t) inf.variant * ck_plane + o], inf.delta);
+        fx_tile_walk<NCO_CARRIER>(rec, fixmask, C, c, s_tab[warp], ph, d.carr_step, len, 0, 0, 0, &overflow);
+    } else {
+        const int wr = wrap_ck[o] + d.ms0 % 20;
+        fx_tile_walk<NCO_CODE>(rec, fixmask, C, c, s_tab[warp], code_ck[o], d.code_step, len, wr % 20, wr / 20,
+                               d.navbits, &overflow);
+    }
+    if (overflow) atomicOr(&step_flag[e], 2);  // segment list too long: the epoch goes to k_synth_lanes
+}
+
+struct FxSmem {
+    int C;
+    int32_t* lut;        // [C][512]  packed (Q << 16) + I
+    int8_t* chip;        // [C][2048] +-1, index = nav polarity << 10 | chip
+    int64_t* dF;         // [C][NBINADE]
+    int64_t* dG;         // [C][NBINADE]
+    unsigned char* rec;  // the tile record (fx_rec_bytes)
+    int32_t* delta;      // [FX_TILE]
+    uint16_t* work;      // [C * FX_THREADS]
+    int* nwork;
+};
+
+__host__ __device__ inline size_t fx_smem_bytes(int C) {
+    return (size_t) C * 512 * 4 + (size_t) C * 2048 + (size_t) C * NBINADE * 16 + fx_rec_bytes(C) + (size_t) FX_TILE * 4 +
+           (size_t) C * FX_THREADS * 2 + 16 + 64;
+}
+
+__device__ __forceinline__ void fx_carve(FxSmem& s, unsigned char* base, int C) {
+    s.C = C;
+    s.rec = base;                             base += fx_rec_bytes(C);
+    s.dF = (int64_t*) base;                   base += (size_t) C * NBINADE * 8;
+    s.dG = (int64_t*) base;                   base += (size_t) C * NBINADE * 8;
+    s.lut = (int32_t*) base;                  base += (size_t) C * 512 * 4;
+    s.delta = (int32_t*) base;                base += (size_t) FX_TILE * 4;
+    s.nwork = (int*) base;                    base += 16;
+    s.chip = (int8_t*) base;                  base += (size_t) C * 2048;
+    s.work = (uint16_t*) base;
+}
+
+// Fixed-point state of one NCO of channel c at the first sample of run r, and its
+// in-segment step: the run's segment start extrapolated inside its binade.
+__device__ __forceinline__ void fx_run_state(const FxSmem& s, int c, int is_carrier, int r, uint64_t& f, uint64_t& df) {
+    const int task = c * 2 + is_carrier;
+    const int idx = s.rec[fx_rec_runseg(s.C) + task * FX_THREADS + r];
+    const int slot = fx_seg_base(c, is_carrier) + idx;
+    const uint64_t f0 = ((const uint64_t*) (s.rec + fx_rec_segF(s.C)))[slot];
+    const int ns = ((const uint16_t*) (s.rec + fx_rec_segn(s.C)))[slot];
+    df = is_carrier ? (uint64_t) s.dF[c * NBINADE + fx_carr_bi(f0)] : (uint64_t) s.dG[c * NBINADE + fx_code_bi(f0)];
+    f = f0 + (uint64_t) (r * FX_RUN - ns) * df;
+}
+
+// Exact fixed-point state of one NCO at tile sample n, from its segment list.
+__device__ __forceinline__ uint64_t fx_exact(const FxSmem& s, int c, int is_carrier, int n) {
+    const int base = fx_seg_base(c, is_carrier);
+    const uint16_t* sn = (const uint16_t*) (s.rec + fx_rec_segn(s.C)) + base;
+    int lo = 0, hi = ((const uint16_t*) (s.rec + fx_rec_nseg(s.C)))[c * 2 + is_carrier] - 1;
+    while (lo < hi) {  // last segment with start <= n
+        const int mid = (lo + hi + 1) >> 1;
+        if (sn[mid] <= n) lo = mid; else hi = mid - 1;
+    }
+    const uint64_t f0 = ((const uint64_t*) (s.rec + fx_rec_segF(s.C)))[base + lo];
+    const uint64_t df = is_carrier ? (uint64_t) s.dF[c * NBINADE + fx_carr_bi(f0)] : (uint64_t) s.dG[c * NBINADE + fx_code_bi(f0)];
+    return f0 + (uint64_t) (n - sn[lo]) * df;
 }
 
 __global__ void __launch_bounds__(FX_THREADS)
 k_synth_fixed(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict__ lutp,
-              const BinadeTab* __restrict__ tabs, const double* __restrict__ code_ck,
-              const int* __restrict__ wrap_ck, const double* __restrict__ carr_ck, size_t ck_plane,
-              const CarrInfo* __restrict__ info, const int8_t* __restrict__ chips, const int* __restrict__ amp_sum,
-              const int* __restrict__ step_flag, int16_t* __restrict__ iq, int* __restrict__ err, int C, int N,
-              int ntiles, int groups) {
+              const BinadeTab* __restrict__ tabs, const unsigned char* __restrict__ recs,
+              const uint32_t* __restrict__ fixmasks, const int8_t* __restrict__ chips, const int* __restrict__ amp_sum, const int* __restrict__ step_flag,
+              int16_t* __restrict__ iq, int e0, int C, int N, int ntiles, int groups) {
     extern __shared__ __align__(16) unsigned char fx_raw[];
     FxSmem s;
     fx_carve(s, fx_raw, C);
-    const int e = blockIdx.x / groups;
-    const int grp = blockIdx.x - e * groups;
+    const int e = e0 + blockIdx.x / groups;
+    const int grp = blockIdx.x % groups;
     if (amp_sum[e] > 32767 || step_flag[e]) return;  // this epoch is rendered by k_synth_lanes
     const gpsiq_chan_desc* de = desc + (size_t) e * C;
     const int tid = threadIdx.x;
+    const size_t rec_bytes = fx_rec_bytes(C);
 
     // ---- stage the epoch's tables (reused for FX_TILES_PER_CTA tiles)
     for (int i = tid; i < C * 512; i += FX_THREADS) s.lut[i] = (de[i >> 9].prn > 0) ? lutp[(size_t) e * C * 512 + i] : 0;
     for (int i = tid; i < C * 512; i += FX_THREADS) {  // 2048 bytes per channel, 4 at a time
-        const int c = i >> 9;
-        const int prn = de[c].prn;
+        const int prn = de[i >> 9].prn;
         ((uint32_t*) s.chip)[i] = (prn > 0 && prn <= 32) ? ((const uint32_t*) chips)[prn * 512 + (i & 511)] : 0x01010101u;
     }
-    for (int i = tid; i < C * 2 * (int) (sizeof(BinadeTab) / 4); i += FX_THREADS)
-        ((uint32_t*) s.tab)[i] = ((const uint32_t*) (tabs + (size_t) e * C * 2))[i];
-    __syncthreads();
     for (int i = tid; i < C * NBINADE; i += FX_THREADS) {
         const int c = i / NBINADE, bi = i - c * NBINADE;
-        const BinadeTab& tc = s.tab[c * 2], &tp = s.tab[c * 2 + 1];
-        s.dG[i] = ((tc.valid >> bi) & 1u) ? fx_scale_delta(tc.delta[bi], 10 - bi) : 0;
-        s.dF[i] = ((tp.valid >> bi) & 1u) ? fx_scale_delta(tp.delta[bi], 11 - bi) : 0;
+        const BinadeTab* tc = tabs + ((size_t) e * C + c) * 2;
+        s.dG[i] = ((tc[0].valid >> bi) & 1u) ? fx_scale_delta(tc[0].delta[bi], 10 - bi) : 0;
+        s.dF[i] = ((tc[1].valid >> bi) & 1u) ? fx_scale_delta(tc[1].delta[bi], 11 - bi) : 0;
     }
 
     uint32_t* out_epoch = reinterpret_cast<uint32_t*>(iq) + (size_t) e * N;
@@ -226,49 +275,40 @@ k_synth_fixed(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restric
         const int n0 = t * FX_TILE;
         const int len = min(FX_TILE, N - n0);
 
-        // ---- reset per-tile scratch
+        // ---- load the tile record, reset per-tile scratch
+        {
+            const uint4* src = (const uint4*) (recs + ((size_t) (e - e0) * ntiles + t) * rec_bytes);
+            uint4* dst = (uint4*) s.rec;
+            for (int i = tid; i < (int) (rec_bytes / 16); i += FX_THREADS) dst[i] = src[i];
+        }
         for (int i = tid; i < FX_TILE; i += FX_THREADS) s.delta[i] = 0;
-        for (int i = tid; i < C * (FX_THREADS / 32); i += FX_THREADS) s.fixmask[i] = 0;
         if (tid == 0) *s.nwork = 0;
         __syncthreads();
 
-        // ---- prologue: task = (channel, NCO); tasks are spread over the 4 warps
+        // ---- list the (channel, run) pairs that contain a segment boundary
         {
-            const int warp = tid >> 5, lane = tid & 31;
-            const int task = lane * 4 + warp;
-            if (task < 2 * C) {
-                const int c = task >> 1;
-                const gpsiq_chan_desc d = de[c];
-                if (d.prn > 0) {
-                    const size_t o = ((size_t) e * ntiles + t) * C + c;
-                    if (task & 1) {
-                        const CarrInfo inf = info[(size_t) e * C + c];
-                        double ph;
-                        if (n0 < inf.n1 || inf.n1 >= N) ph = carr_ck[o];
-                        else ph = __dadd_rn(carr_ck[(size_t) inf.variant * ck_plane + o], inf.delta);
-                        fx_prologue<NCO_CARRIER>(s, c, ph, d.carr_step, len, 0, 0, 0, err);
-                    } else {
-                        const int w = wrap_ck[o] + d.ms0 % 20;
-                        fx_prologue<NCO_CODE>(s, c, code_ck[o], d.code_step, len, w % 20, w / 20, d.navbits, err);
-                    }
-                } else {
-                    s.nseg[task] = 0;
-                }
-            }
+            const uint32_t* fixmask = fixmasks + ((size_t) (e - e0) * ntiles + t) * fx_fixmask_words(C);
+            for (int c = 0; c < C; c++)
+                if ((fixmask[c * (FX_THREADS / 32) + (tid >> 5)] >> (tid & 31)) & 1u)
+                    s.work[atomicAdd(s.nwork, 1)] = (uint16_t) (c * FX_THREADS + tid);
         }
         __syncthreads();
 
-        // ---- fix-up pass: runs that contain a segment boundary
+        // ---- fix-up pass: (right - wrong) for the samples of those runs
         for (int i = tid; i < *s.nwork; i += FX_THREADS) {
             const int c = s.work[i] / FX_THREADS, r = s.work[i] % FX_THREADS;
+            uint64_t f, df, g, dg;
+            fx_run_state(s, c, 1, r, f, df);
+            fx_run_state(s, c, 0, r, g, dg);
             for (int j = 0; j < FX_RUN; j++) {
                 const int n = r * FX_RUN + j;
                 if (n >= len) break;
-                const uint64_t f = fx_exact(s, c * 2 + 1, n, s.dF + c * NBINADE, false);
-                const uint64_t g = fx_exact(s, c * 2, n, s.dG + c * NBINADE, true);
-                const int32_t right = s.lut[c * 512 + (int) (f >> 55)] * (int32_t) s.chip[c * 2048 + (int) (g >> 53)];
-                const int32_t wrong = fx_extrapolated(s, c, r, j);
+                const uint64_t fe = fx_exact(s, c, 1, n), ge = fx_exact(s, c, 0, n);
+                const int32_t right = s.lut[c * 512 + (int) (fe >> 55)] * (int32_t) s.chip[c * 2048 + (int) (ge >> 53)];
+                const int32_t wrong = s.lut[c * 512 + (int) (f >> 55)] * (int32_t) s.chip[c * 2048 + (int) (g >> 53)];
                 if (right != wrong) atomicAdd(&s.delta[n], right - wrong);
+                f += df;
+                g += dg;
             }
         }
         __syncthreads();
@@ -282,11 +322,12 @@ k_synth_fixed(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restric
                 acc[0] = a.x; acc[1] = a.y; acc[2] = a.z; acc[3] = a.w;
                 acc[4] = b.x; acc[5] = b.y; acc[6] = b.z; acc[7] = b.w;
             }
+            const uint16_t* nseg = (const uint16_t*) (s.rec + fx_rec_nseg(C));
             for (int c = 0; c < C; c++) {
-                if (s.nseg[c * 2] == 0) continue;  // inactive slot (uniform across the CTA)
-                uint64_t f = s.slotF[c * FX_THREADS + tid], g = s.slotG[c * FX_THREADS + tid];
-                const uint64_t df = (uint64_t) s.dF[c * NBINADE + fx_carr_bi(f)];
-                const uint64_t dg = (uint64_t) s.dG[c * NBINADE + fx_code_bi(g)];
+                if (nseg[c * 2] == 0) continue;  // inactive slot (uniform across the CTA)
+                uint64_t f, df, g, dg;
+                fx_run_state(s, c, 1, tid, f, df);
+                fx_run_state(s, c, 0, tid, g, dg);
                 const int32_t* lut = s.lut + c * 512;
                 const int8_t* chip = s.chip + c * 2048;
 #pragma unroll
