@@ -229,6 +229,7 @@ def ours_arm(args):
     torch.cuda.synchronize()
     launches = synth.launch_count - l0
     nrec, scan_ms, synth_ms = synth.timing_collect()
+    fallbacks = synth.carrier_fallbacks
     t = torch.tensor([ms, float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
         tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -288,7 +289,9 @@ def ours_arm(args):
                        "parallelism": "time-slice x%d, NCCL carrier-phase hand-off" % world if world > 1 else "single GPU",
                        "l2_policy": "output per step %.1f MB > 126 MB L2; inputs are %d B of descriptors"
                                     % (samples_per_step * 4 / 1e6, nbytes_desc),
-                       "kernel": args.kernel, "tile_samples": args.tile},
+                       "kernel": args.kernel, "tile_samples": args.tile,
+                       "carrier_scan_serial_fallbacks": fallbacks,
+                       "carrier_scan_chains": (args.warmup + args.steps) * E * C},
             "e2e": {"value": round(e2e_value, 3), "unit": "Msamples/s", "h2d_bytes_per_step": nbytes_desc,
                     "d2h_bytes_per_step": samples_per_step * 4},
             "gpu_launches": launches,

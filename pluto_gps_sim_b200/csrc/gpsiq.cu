@@ -88,6 +88,7 @@ struct gpsiq_ctx {
     int* d_wrap_ck;       // [E][ntiles][C]
     double* d_carr_ck;    // [2][E][ntiles][C] two speculation planes (INT32 mode: uint32 phase as double, plane 0)
     BinadeTab* d_tab;     // [E][C][2]  (0 = code NCO, 1 = carrier NCO)
+    double* d_drift;      // [E][C] predicted carrier rounding drift per epoch (estimate aid only)
     CarrSpec* d_spec;     // [E][C][2]
     CarrInfo* d_info;     // [E][C]
     int* d_fallbacks;     // epochs that fell back to the serial carrier scan (diagnostic counter)
@@ -124,16 +125,20 @@ static int fail(gpsiq_ctx* ctx, int code, const char* what, cudaError_t ce) {
 // k_prepare: amplitude LUT per (epoch, slot)
 // ---------------------------------------------------------------------------
 __global__ void k_prepare(const gpsiq_chan_desc* __restrict__ desc, int2* __restrict__ lut,
-                          int32_t* __restrict__ lutp, BinadeTab* __restrict__ tab, int* __restrict__ amp_sum,
-                          int* __restrict__ step_flag, int C, int carrier_mode, int* __restrict__ err) {
+                          int32_t* __restrict__ lutp, BinadeTab* __restrict__ tab, double* __restrict__ drift,
+                          int* __restrict__ amp_sum, int* __restrict__ step_flag, int C, int N, int carrier_mode,
+                          int* __restrict__ err) {
     const int ec = blockIdx.x;
     const gpsiq_chan_desc d = desc[ec];
     int2* out = lut + (size_t) ec * 512;
     if (d.prn <= 0) return;
     // per-binade fixed-point increments of the two NCOs for this epoch's steps (nco_scan.cuh)
     if (threadIdx.x == 0) build_binade_tab<NCO_CODE>(d.code_step, tab[(size_t) ec * 2]);
-    if (threadIdx.x == 32 && carrier_mode == GPSIQ_CARRIER_FLOAT)
-        build_binade_tab<NCO_CARRIER>(d.carr_step, tab[(size_t) ec * 2 + 1]);
+    if (threadIdx.x == 32 && carrier_mode == GPSIQ_CARRIER_FLOAT) {
+        BinadeTab& tp = tab[(size_t) ec * 2 + 1];
+        build_binade_tab<NCO_CARRIER>(d.carr_step, tp);
+        drift[ec] = carr_drift_estimate(d.carr_step, tp, N);
+    }
     if (d.prn > 32 || !(d.code_phase0 >= 0.0 && d.code_phase0 < 1023.0) || !(d.code_step > 0.0 && d.code_step < 1023.0)) {
         if (threadIdx.x == 0) atomicExch(err, 1 + ec);
         return;
@@ -238,7 +243,7 @@ __device__ __forceinline__ double est_advance_dev(double x, double d, int N) {
 }
 
 __global__ void k_carr_speculate(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
-                                 const double* __restrict__ carr_state,
+                                 const double* __restrict__ drift, const double* __restrict__ carr_state,
                                  double* __restrict__ carr_ck, size_t ck_plane, CarrSpec* __restrict__ spec, int E,
                                  int C, int N, int T, int ntiles) {
     const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -255,7 +260,7 @@ __global__ void k_carr_speculate(const gpsiq_chan_desc* __restrict__ desc, const
             const gpsiq_chan_desc* dk = desc + (size_t) k * C + c;
             if (dk->prn <= 0) continue;
             if (dk->flags & GPSIQ_FLAG_RESET_CARRIER) x = dk->carr_phase0;
-            x = est_advance_dev(x, dk->carr_step, N);
+            x = est_advance_dev(x + drift[(size_t) k * C + c], dk->carr_step, N);
         }
         if (d.flags & GPSIQ_FLAG_RESET_CARRIER) x = d.carr_phase0;
         const BinadeTab tab = tabs[(size_t) ec * 2 + 1];
@@ -578,7 +583,7 @@ int gpsiq_carrier_chain_host(const double* steps, int n_epochs, int N, int T, do
             const bool exact = (t * T < info.n1) || info.n1 >= N;
             ck_out[(size_t) e * ntiles + t] = exact ? plane[0][t] : plane[info.variant][t] + info.delta;
         }
-        xe = est_advance(xe, d, N);
+        xe = est_advance(xe + carr_drift_estimate(d, tab, N), d, N);
     }
     free(plane[0]);
     if (x_end_out) *x_end_out = x;
@@ -646,6 +651,7 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
     ctx->ck_plane = ck;
     CU(cudaMalloc(&ctx->d_carr_ck, 2 * ck * sizeof(double)));
     CU(cudaMalloc(&ctx->d_tab, EC * 2 * sizeof(BinadeTab)));
+    CU(cudaMalloc(&ctx->d_drift, EC * sizeof(double)));
     CU(cudaMalloc(&ctx->d_spec, EC * 2 * sizeof(CarrSpec)));
     CU(cudaMalloc(&ctx->d_info, EC * sizeof(CarrInfo)));
     CU(cudaMalloc(&ctx->d_fallbacks, sizeof(int)));
@@ -701,7 +707,7 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_desc); cudaFree(ctx->d_lut); cudaFree(ctx->d_lutp); cudaFree(ctx->d_chips); cudaFree(ctx->d_flags);
     cudaFree(ctx->d_recs); cudaFree(ctx->d_fixmasks); cudaFree(ctx->d_code_ck); cudaFree(ctx->d_wrap_ck);
-    cudaFree(ctx->d_carr_ck); cudaFree(ctx->d_tab); cudaFree(ctx->d_spec); cudaFree(ctx->d_info); cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_carr_trace); cudaFree(ctx->d_ca);
+    cudaFree(ctx->d_carr_ck); cudaFree(ctx->d_tab); cudaFree(ctx->d_drift); cudaFree(ctx->d_spec); cudaFree(ctx->d_info); cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_carr_trace); cudaFree(ctx->d_ca);
     cudaFree(ctx->d_iq); cudaFree(ctx->d_sums); cudaFree(ctx->d_err);
     for (int i = 0; i < TIMING_RING; i++)
         for (int j = 0; j < 3; j++) cudaEventDestroy(ctx->ev[i][j]);
@@ -715,12 +721,12 @@ static int enqueue_scan(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_e
     const int EC = n_epochs * C;
     if (ctx->ev_count < TIMING_RING) CU(cudaEventRecord(ctx->ev[ctx->ev_count][0], st));
     CU(cudaMemsetAsync(ctx->d_flags, 0, 2 * (size_t) ctx->E * sizeof(int), st));
-    k_prepare<<<EC, 128, 0, st>>>(desc_dev, ctx->d_lut, ctx->d_lutp, ctx->d_tab, ctx->d_flags, ctx->d_flags + ctx->E, C,
-                                  ctx->cfg.carrier_mode, ctx->d_err);
+    k_prepare<<<EC, 128, 0, st>>>(desc_dev, ctx->d_lut, ctx->d_lutp, ctx->d_tab, ctx->d_drift, ctx->d_flags,
+                                  ctx->d_flags + ctx->E, C, N, ctx->cfg.carrier_mode, ctx->d_err);
     k_scan_code<<<(EC + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_code_ck, ctx->d_wrap_ck, EC, C, N, T, ntiles);
     if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && ctx->cfg.reserved[0] == 0) {
         const int chains = EC * 2;
-        k_carr_speculate<<<(chains + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_carr_state, ctx->d_carr_ck, ctx->ck_plane,
+        k_carr_speculate<<<(chains + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_drift, ctx->d_carr_state, ctx->d_carr_ck, ctx->ck_plane,
                                                          ctx->d_spec, n_epochs, C, N, T, ntiles);
         k_carr_chain<<<C, 32, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_spec, ctx->d_carr_ck, ctx->d_carr_state, ctx->d_carr_trace,
                                        ctx->d_info, ctx->d_fallbacks, n_epochs, C, N, T, ntiles);

@@ -275,6 +275,21 @@ GPSIQ_HD int carr_advance(double& x, double d, const BinadeTab& tab, int count, 
     return count0 - count;
 }
 
+// Predicted systematic rounding drift of the carrier recurrence over n steps of
+// step d: inside binade bi every step errs by (D_b*ulp_b - d), and the phase
+// spends a fraction 2^-(bi+1) of its steps there.  Only used to improve the
+// START-PHASE ESTIMATES of the speculative scans (fewer serial fallbacks);
+// never part of an exact result.
+GPSIQ_HD double carr_drift_estimate(double d, const BinadeTab& tab, int n) {
+    double acc = 0.0;
+    for (int bi = 0; bi < NBINADE; bi++) {
+        if (!((tab.valid >> bi) & 1u)) continue;
+        const double step_b = (double) tab.delta[bi] * pow2_of(1022 - bi - 52);  // exact: D_b * ulp_b
+        acc += (step_b - d) * pow2_of(1022 - bi);                               // width of [2^-(bi+1), 2^-bi)
+    }
+    return acc * (double) n;
+}
+
 // true if an epoch with this step may be speculated
 GPSIQ_HD bool carr_step_speculable(double d) {
     const int64_t b = f64_bits(d) & 0x7fffffffffffffffLL;

@@ -192,19 +192,21 @@ struct FxSmem {
     int64_t* dF;         // [C][NBINADE]
     int64_t* dG;         // [C][NBINADE]
     unsigned char* rec;  // the tile record (fx_rec_bytes)
+    uint64_t* segdF;     // [C][FX_SPER] in-segment fixed-point step of every segment
     int32_t* delta;      // [FX_TILE]
     uint16_t* work;      // [C * FX_THREADS]
     int* nwork;
 };
 
 __host__ __device__ inline size_t fx_smem_bytes(int C) {
-    return (size_t) C * 512 * 4 + (size_t) C * 2048 + (size_t) C * NBINADE * 16 + fx_rec_bytes(C) + (size_t) FX_TILE * 4 +
-           (size_t) C * FX_THREADS * 2 + 16 + 64;
+    return (size_t) C * 512 * 4 + (size_t) C * 2048 + (size_t) C * NBINADE * 16 + fx_rec_bytes(C) + (size_t) C * FX_SPER * 8 +
+           (size_t) FX_TILE * 4 + (size_t) C * FX_THREADS * 2 + 16 + 64;
 }
 
 __device__ __forceinline__ void fx_carve(FxSmem& s, unsigned char* base, int C) {
     s.C = C;
     s.rec = base;                             base += fx_rec_bytes(C);
+    s.segdF = (uint64_t*) base;               base += (size_t) C * FX_SPER * 8;
     s.dF = (int64_t*) base;                   base += (size_t) C * NBINADE * 8;
     s.dG = (int64_t*) base;                   base += (size_t) C * NBINADE * 8;
     s.lut = (int32_t*) base;                  base += (size_t) C * 512 * 4;
@@ -216,28 +218,16 @@ __device__ __forceinline__ void fx_carve(FxSmem& s, unsigned char* base, int C) 
 
 // Fixed-point state of one NCO of channel c at the first sample of run r, and its
 // in-segment step: the run's segment start extrapolated inside its binade.
-__device__ __forceinline__ void fx_run_state(const FxSmem& s, int c, int is_carrier, int r, uint64_t& f, uint64_t& df) {
+// Returns the segment's index within the task's list.
+__device__ __forceinline__ int fx_run_state(const FxSmem& s, int c, int is_carrier, int r, uint64_t& f, uint64_t& df) {
     const int task = c * 2 + is_carrier;
     const int idx = s.rec[fx_rec_runseg(s.C) + task * FX_THREADS + r];
     const int slot = fx_seg_base(c, is_carrier) + idx;
     const uint64_t f0 = ((const uint64_t*) (s.rec + fx_rec_segF(s.C)))[slot];
     const int ns = ((const uint16_t*) (s.rec + fx_rec_segn(s.C)))[slot];
-    df = is_carrier ? (uint64_t) s.dF[c * NBINADE + fx_carr_bi(f0)] : (uint64_t) s.dG[c * NBINADE + fx_code_bi(f0)];
+    df = s.segdF[slot];
     f = f0 + (uint64_t) (r * FX_RUN - ns) * df;
-}
-
-// Exact fixed-point state of one NCO at tile sample n, from its segment list.
-__device__ __forceinline__ uint64_t fx_exact(const FxSmem& s, int c, int is_carrier, int n) {
-    const int base = fx_seg_base(c, is_carrier);
-    const uint16_t* sn = (const uint16_t*) (s.rec + fx_rec_segn(s.C)) + base;
-    int lo = 0, hi = ((const uint16_t*) (s.rec + fx_rec_nseg(s.C)))[c * 2 + is_carrier] - 1;
-    while (lo < hi) {  // last segment with start <= n
-        const int mid = (lo + hi + 1) >> 1;
-        if (sn[mid] <= n) lo = mid; else hi = mid - 1;
-    }
-    const uint64_t f0 = ((const uint64_t*) (s.rec + fx_rec_segF(s.C)))[base + lo];
-    const uint64_t df = is_carrier ? (uint64_t) s.dF[c * NBINADE + fx_carr_bi(f0)] : (uint64_t) s.dG[c * NBINADE + fx_code_bi(f0)];
-    return f0 + (uint64_t) (n - sn[lo]) * df;
+    return idx;
 }
 
 __global__ void __launch_bounds__(FX_THREADS)
@@ -284,6 +274,12 @@ k_synth_fixed(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restric
         for (int i = tid; i < FX_TILE; i += FX_THREADS) s.delta[i] = 0;
         if (tid == 0) *s.nwork = 0;
         __syncthreads();
+        for (int i = tid; i < C * FX_SPER; i += FX_THREADS) {  // in-segment step of every segment, from its binade
+            const int c = i / FX_SPER, k = i - c * FX_SPER;
+            const uint64_t f0 = ((const uint64_t*) (s.rec + fx_rec_segF(C)))[i];
+            s.segdF[i] = (k < FX_SCARR) ? (uint64_t) s.dF[c * NBINADE + fx_carr_bi(f0)]
+                                        : (uint64_t) s.dG[c * NBINADE + fx_code_bi(f0)];
+        }
 
         // ---- list the (channel, run) pairs that contain a segment boundary
         {
@@ -295,20 +291,27 @@ k_synth_fixed(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restric
         __syncthreads();
 
         // ---- fix-up pass: (right - wrong) for the samples of those runs
-        for (int i = tid; i < *s.nwork; i += FX_THREADS) {
-            const int c = s.work[i] / FX_THREADS, r = s.work[i] % FX_THREADS;
-            uint64_t f, df, g, dg;
-            fx_run_state(s, c, 1, r, f, df);
-            fx_run_state(s, c, 0, r, g, dg);
-            for (int j = 0; j < FX_RUN; j++) {
-                const int n = r * FX_RUN + j;
-                if (n >= len) break;
-                const uint64_t fe = fx_exact(s, c, 1, n), ge = fx_exact(s, c, 0, n);
-                const int32_t right = s.lut[c * 512 + (int) (fe >> 55)] * (int32_t) s.chip[c * 2048 + (int) (ge >> 53)];
-                const int32_t wrong = s.lut[c * 512 + (int) (f >> 55)] * (int32_t) s.chip[c * 2048 + (int) (g >> 53)];
-                if (right != wrong) atomicAdd(&s.delta[n], right - wrong);
-                f += df;
-                g += dg;
+        {
+            const uint64_t* segF = (const uint64_t*) (s.rec + fx_rec_segF(C));
+            const uint16_t* segn = (const uint16_t*) (s.rec + fx_rec_segn(C));
+            const uint16_t* nsegs = (const uint16_t*) (s.rec + fx_rec_nseg(C));
+            for (int i = tid; i < *s.nwork; i += FX_THREADS) {
+                const int c = s.work[i] / FX_THREADS, r = s.work[i] % FX_THREADS;
+                uint64_t f, df, g, dg;                 // extrapolated (what the main pass will add)
+                int ic = fx_run_state(s, c, 1, r, f, df) + fx_seg_base(c, 1);
+                int ig = fx_run_state(s, c, 0, r, g, dg) + fx_seg_base(c, 0);
+                const int ec = fx_seg_base(c, 1) + nsegs[c * 2 + 1], eg = fx_seg_base(c, 0) + nsegs[c * 2];
+                uint64_t fe = f, dfe = df, ge = g, dge = dg;  // exact: follows the segment lists
+                for (int j = 0; j < FX_RUN; j++) {
+                    const int n = r * FX_RUN + j;
+                    if (n >= len) break;
+                    if (ic + 1 < ec && segn[ic + 1] == n) { ic++; fe = segF[ic]; dfe = s.segdF[ic]; }
+                    if (ig + 1 < eg && segn[ig + 1] == n) { ig++; ge = segF[ig]; dge = s.segdF[ig]; }
+                    const int32_t right = s.lut[c * 512 + (int) (fe >> 55)] * (int32_t) s.chip[c * 2048 + (int) (ge >> 53)];
+                    const int32_t wrong = s.lut[c * 512 + (int) (f >> 55)] * (int32_t) s.chip[c * 2048 + (int) (g >> 53)];
+                    if (right != wrong) atomicAdd(&s.delta[n], right - wrong);
+                    f += df; g += dg; fe += dfe; ge += dge;
+                }
             }
         }
         __syncthreads();
