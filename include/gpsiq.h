@@ -152,14 +152,32 @@ int gpsiq_carrier_chain_host(const double *steps, int n_epochs, int N, int T, do
 void *gpsiq_host_alloc(size_t bytes);
 void gpsiq_host_free(void *p);
 
-/* The two phases of gpsiq_synth_device, separately, for time-sliced multi-GPU
- * runs: scan = amplitude LUTs + exact NCO state at every tile boundary (this is
- * what advances the carrier state, so the next slice's owner can be handed the
- * phases before the per-sample work starts); render = the per-sample synthesis
- * from the checkpoints of the immediately preceding scan of the same batch. */
+/* The phases of gpsiq_synth_device, separately, for time-sliced multi-GPU runs
+ * (pluto_gps_sim_b200/timeslice.py).  A batch goes through
+ *   prepare   -> LUTs, binade tables, and the batch's closed-form phase advance
+ *                per slot (advance_dev, 2*max_chan doubles: advance or absolute
+ *                phase, then 0/1 "re-seeded" flags), which the owners of LATER
+ *                slices fold into their start-phase estimates;
+ *   speculate -> code-NCO scan + speculative carrier scans from the context's
+ *                start-phase ESTIMATE; needs no exact phase, so all ranks run it
+ *                at the same time;
+ *   chain     -> the only serial part: the exact carrier phase is chained through
+ *                the batch from the context's carrier state (received from the
+ *                previous slice's owner); O(one carrier cycle) per epoch;
+ *   render    -> the per-sample synthesis.
+ * gpsiq_scan_device = prepare + speculate + chain.  Estimates only affect speed:
+ * a bad one makes epochs fall back to the serial scan, never changes a result. */
+int gpsiq_prepare_device(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc_dev, int n_epochs, double *advance_dev,
+                         void *cuda_stream);
+int gpsiq_speculate_device(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc_dev, int n_epochs, void *cuda_stream);
+int gpsiq_chain_device(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc_dev, int n_epochs, void *cuda_stream);
 int gpsiq_scan_device(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc_dev, int n_epochs, void *cuda_stream);
 int gpsiq_render_device(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc_dev, int n_epochs, int16_t *iq_dev,
                         void *cuda_stream);
+/* estimate <- fold(estimate, advance): skip over a slice synthesized elsewhere */
+int gpsiq_estimate_fold_device(gpsiq_ctx *ctx, const double *advance_dev, void *cuda_stream);
+/* estimate <- the context's exact carrier state (e.g. right after gpsiq_carrier_from_device) */
+int gpsiq_estimate_anchor_device(gpsiq_ctx *ctx, void *cuda_stream);
 /* Copy the carrier state (max_chan doubles) to / from DEVICE memory on a stream
  * (e.g. the buffer of an NCCL send / recv). */
 int gpsiq_carrier_to_device(gpsiq_ctx *ctx, double *dst_dev, void *cuda_stream);

@@ -74,6 +74,11 @@ SYMBOLS = {
     "gpsiq_timing_begin": (_i, [_vp]),
     "gpsiq_timing_collect": (_i, [_vp, C.POINTER(_i), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "gpsiq_scan_device": (_i, [_vp, _vp, _i, _vp]),
+    "gpsiq_prepare_device": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "gpsiq_speculate_device": (_i, [_vp, _vp, _i, _vp]),
+    "gpsiq_chain_device": (_i, [_vp, _vp, _i, _vp]),
+    "gpsiq_estimate_fold_device": (_i, [_vp, _vp, _vp]),
+    "gpsiq_estimate_anchor_device": (_i, [_vp, _vp]),
     "gpsiq_render_device": (_i, [_vp, _vp, _i, _vp, _vp]),
     "gpsiq_carrier_to_device": (_i, [_vp, _vp, _vp]),
     "gpsiq_carrier_from_device": (_i, [_vp, _vp, _vp]),

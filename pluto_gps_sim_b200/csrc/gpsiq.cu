@@ -68,7 +68,7 @@ static void ca_generate(int prn, uint8_t* chips) {
 // ---------------------------------------------------------------------------
 #define TIMING_RING 64
 
-#define FX_SUB_EPOCHS 16  // tile records of this many epochs (~56 MB at 12 slots) stay L2 resident between the two kernels
+#define FX_SUB_EPOCHS 12  // 12 epochs x 37 CTAs = 444 = 148 SMs x 3 resident CTAs: one full wave; records (~42 MB) stay in L2
 
 struct gpsiq_ctx {
     gpsiq_config cfg;
@@ -93,13 +93,16 @@ struct gpsiq_ctx {
     CarrInfo* d_info;     // [E][C]
     int* d_fallbacks;     // epochs that fell back to the serial carrier scan (diagnostic counter)
     size_t ck_plane;      // elements per plane
-    double* d_carr_state; // [C]
+    double* d_carr_state; // [C]  exact carrier phase per slot after the last chained epoch
+    double* d_est_state;  // [C]  ESTIMATED phase at the start of the next batch to speculate (never part of a result)
+    double* d_adv;        // [2C] this batch's closed-form phase advance per slot + "re-seeded" flags
     double* d_carr_trace; // [E][C]
     uint32_t* d_ca;       // [33][CA_WORDS]
     int16_t* d_iq;        // [E][N][2]
     unsigned long long* d_sums;
     int* d_err;
     int last_epochs;
+    int phase_done;       // 1 prepare, 2 speculate, 3 chain -- of the batch in flight
     int64_t launches;
     char err[256];
 };
@@ -242,6 +245,35 @@ __device__ __forceinline__ double est_advance_dev(double x, double d, int N) {
     return (t >= 0.0 && t < 1.0) ? t : 0.0;
 }
 
+// Closed-form (estimated) effect of one batch on the carrier phase of every slot:
+// adv[c] = sum over the batch's epochs of N*step + predicted rounding drift, and
+// adv[C+c] = 1 if a descriptor re-seeded the slot (then adv[c] is an absolute phase).
+// Feeds only the start-phase ESTIMATES of later speculative scans, on this GPU or
+// -- for time-sliced multi-GPU runs -- on the ranks that own later slices.
+__global__ void k_slice_advance(const gpsiq_chan_desc* __restrict__ desc, const double* __restrict__ drift,
+                                double* __restrict__ adv, int E, int C, int N) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double x = 0.0, abs_flag = 0.0;
+    for (int e = 0; e < E; e++) {
+        const gpsiq_chan_desc* d = desc + (size_t) e * C + c;
+        if (d->prn <= 0) continue;
+        if (d->flags & GPSIQ_FLAG_RESET_CARRIER) { x = d->carr_phase0; abs_flag = 1.0; }
+        x = est_advance_dev(x + drift[(size_t) e * C + c], d->carr_step, N);
+    }
+    adv[c] = x;
+    adv[C + c] = abs_flag;
+}
+
+// est = fold(est, adv): est <- adv (absolute) or frac(est + adv)
+__global__ void k_est_fold(double* __restrict__ est, const double* __restrict__ adv, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double t = (adv[C + c] != 0.0) ? adv[c] : est[c] + adv[c];
+    t -= floor(t);
+    est[c] = (t >= 0.0 && t < 1.0) ? t : 0.0;
+}
+
 __global__ void k_carr_speculate(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
                                  const double* __restrict__ drift, const double* __restrict__ carr_state,
                                  double* __restrict__ carr_ck, size_t ck_plane, CarrSpec* __restrict__ spec, int E,
@@ -255,7 +287,7 @@ __global__ void k_carr_speculate(const gpsiq_chan_desc* __restrict__ desc, const
     out.margin = -1.0; out.n1 = -1; out.xw1 = 0.0; out.xend = 0.0; out.pad = 0;
     if (d.prn > 0 && !(v == 1 && d.carr_step >= 0.0) && carr_step_speculable(d.carr_step)) {
         // estimated start phase: chain the batch's epochs in closed form (one rounding per epoch)
-        double x = carr_state[c];
+        double x = carr_state[c];  // = the context's ESTIMATE of the batch-start phase
         for (int k = 0; k < e; k++) {
             const gpsiq_chan_desc* dk = desc + (size_t) k * C + c;
             if (dk->prn <= 0) continue;
@@ -657,6 +689,9 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
     CU(cudaMalloc(&ctx->d_fallbacks, sizeof(int)));
     CU(cudaMemset(ctx->d_fallbacks, 0, sizeof(int)));
     CU(cudaMalloc(&ctx->d_carr_state, ctx->C * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_est_state, ctx->C * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_adv, 2 * ctx->C * sizeof(double)));
+    CU(cudaMemset(ctx->d_est_state, 0, ctx->C * sizeof(double)));
     CU(cudaMalloc(&ctx->d_carr_trace, EC * sizeof(double)));
     CU(cudaMalloc(&ctx->d_ca, 33 * CA_WORDS * sizeof(uint32_t)));
     CU(cudaMalloc(&ctx->d_iq, (size_t) ctx->E * ctx->N * 4));
@@ -707,7 +742,7 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_desc); cudaFree(ctx->d_lut); cudaFree(ctx->d_lutp); cudaFree(ctx->d_chips); cudaFree(ctx->d_flags);
     cudaFree(ctx->d_recs); cudaFree(ctx->d_fixmasks); cudaFree(ctx->d_code_ck); cudaFree(ctx->d_wrap_ck);
-    cudaFree(ctx->d_carr_ck); cudaFree(ctx->d_tab); cudaFree(ctx->d_drift); cudaFree(ctx->d_spec); cudaFree(ctx->d_info); cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_carr_trace); cudaFree(ctx->d_ca);
+    cudaFree(ctx->d_carr_ck); cudaFree(ctx->d_tab); cudaFree(ctx->d_drift); cudaFree(ctx->d_spec); cudaFree(ctx->d_info); cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_est_state); cudaFree(ctx->d_adv); cudaFree(ctx->d_carr_trace); cudaFree(ctx->d_ca);
     cudaFree(ctx->d_iq); cudaFree(ctx->d_sums); cudaFree(ctx->d_err);
     for (int i = 0; i < TIMING_RING; i++)
         for (int j = 0; j < 3; j++) cudaEventDestroy(ctx->ev[i][j]);
@@ -715,30 +750,68 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
     free(ctx);
 }
 
-// Phase 1: amplitude LUTs + exact NCO checkpoints for the batch (advances the carrier state).
-static int enqueue_scan(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, cudaStream_t st) {
-    const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
+// Phase 1a: amplitude LUTs, binade tables, contract flags, and the batch's closed-form phase advance.
+static int enqueue_prepare(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, cudaStream_t st) {
+    const int C = ctx->C, N = ctx->N;
     const int EC = n_epochs * C;
     if (ctx->ev_count < TIMING_RING) CU(cudaEventRecord(ctx->ev[ctx->ev_count][0], st));
     CU(cudaMemsetAsync(ctx->d_flags, 0, 2 * (size_t) ctx->E * sizeof(int), st));
     k_prepare<<<EC, 128, 0, st>>>(desc_dev, ctx->d_lut, ctx->d_lutp, ctx->d_tab, ctx->d_drift, ctx->d_flags,
                                   ctx->d_flags + ctx->E, C, N, ctx->cfg.carrier_mode, ctx->d_err);
+    ctx->launches += 1;
+    if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT) {
+        k_slice_advance<<<1, 32, 0, st>>>(desc_dev, ctx->d_drift, ctx->d_adv, n_epochs, C, N);
+        ctx->launches += 1;
+    }
+    ctx->last_epochs = n_epochs;
+    ctx->phase_done = 1;
+    CU(cudaGetLastError());
+    return GPSIQ_OK;
+}
+
+// Phase 1b: everything that does NOT need the exact carrier phase: the code-NCO scan and the
+// speculative carrier scans from the context's start-phase estimate (advanced afterwards).
+static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, cudaStream_t st) {
+    const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
+    const int EC = n_epochs * C;
     k_scan_code<<<(EC + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_code_ck, ctx->d_wrap_ck, EC, C, N, T, ntiles);
+    ctx->launches += 1;
     if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && ctx->cfg.reserved[0] == 0) {
         const int chains = EC * 2;
-        k_carr_speculate<<<(chains + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_drift, ctx->d_carr_state, ctx->d_carr_ck, ctx->ck_plane,
-                                                         ctx->d_spec, n_epochs, C, N, T, ntiles);
+        k_carr_speculate<<<(chains + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_drift, ctx->d_est_state,
+                                                         ctx->d_carr_ck, ctx->ck_plane, ctx->d_spec, n_epochs, C, N, T,
+                                                         ntiles);
+        k_est_fold<<<1, 32, 0, st>>>(ctx->d_est_state, ctx->d_adv, C);
+        ctx->launches += 2;
+    }
+    ctx->phase_done = 2;
+    CU(cudaGetLastError());
+    return GPSIQ_OK;
+}
+
+// Phase 1c: the serial part -- chain the exact carrier phase through the batch (advances the carrier
+// state) and re-anchor the estimate on it.
+static int enqueue_chain(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, cudaStream_t st) {
+    const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
+    if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && ctx->cfg.reserved[0] == 0) {
         k_carr_chain<<<C, 32, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_spec, ctx->d_carr_ck, ctx->d_carr_state, ctx->d_carr_trace,
                                        ctx->d_info, ctx->d_fallbacks, n_epochs, C, N, T, ntiles);
-        ctx->launches += 4;
     } else {  // INT32 carrier (closed form) or the serial float scan (cfg.reserved[0] = 1, cross-check)
         k_scan_carrier<<<C, 32, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_carr_ck, ctx->d_carr_state, ctx->d_carr_trace, ctx->d_info,
                                          n_epochs, C, N, T, ntiles, ctx->cfg.carrier_mode);
-        ctx->launches += 3;
     }
-    ctx->last_epochs = n_epochs;
+    ctx->launches += 1;
+    CU(cudaMemcpyAsync(ctx->d_est_state, ctx->d_carr_state, C * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    ctx->phase_done = 3;
     CU(cudaGetLastError());
     return GPSIQ_OK;
+}
+
+static int enqueue_scan(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, cudaStream_t st) {
+    int rc = enqueue_prepare(ctx, desc_dev, n_epochs, st);
+    if (!rc) rc = enqueue_speculate(ctx, desc_dev, n_epochs, st);
+    if (!rc) rc = enqueue_chain(ctx, desc_dev, n_epochs, st);
+    return rc;
 }
 
 // Phase 2: the per-sample synthesis from the checkpoints of the last scan.
@@ -825,8 +898,51 @@ int gpsiq_scan_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epo
     return enqueue_scan(ctx, desc_dev, n_epochs, (cudaStream_t) stream);
 }
 
+int gpsiq_prepare_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, double* advance_dev, void* stream) {
+    if (!ctx || !desc_dev || n_epochs < 1) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_prepare_device: bad argument", cudaSuccess);
+    if (n_epochs > ctx->E) return fail(ctx, GPSIQ_ERR_CAPACITY, "gpsiq_prepare_device: n_epochs > max_epochs", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    int rc = enqueue_prepare(ctx, desc_dev, n_epochs, (cudaStream_t) stream);
+    if (rc) return rc;
+    if (advance_dev)
+        CU(cudaMemcpyAsync(advance_dev, ctx->d_adv, 2 * ctx->C * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t) stream));
+    return GPSIQ_OK;
+}
+
+int gpsiq_speculate_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, void* stream) {
+    if (!ctx || !desc_dev || n_epochs != ctx->last_epochs || ctx->phase_done != 1)
+        return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_speculate_device: must follow gpsiq_prepare_device of the same batch", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    return enqueue_speculate(ctx, desc_dev, n_epochs, (cudaStream_t) stream);
+}
+
+int gpsiq_chain_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, void* stream) {
+    if (!ctx || !desc_dev || n_epochs != ctx->last_epochs || ctx->phase_done != 2)
+        return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_chain_device: must follow gpsiq_speculate_device of the same batch", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    return enqueue_chain(ctx, desc_dev, n_epochs, (cudaStream_t) stream);
+}
+
+int gpsiq_estimate_fold_device(gpsiq_ctx* ctx, const double* advance_dev, void* stream) {
+    if (!ctx || !advance_dev) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_estimate_fold_device: bad argument", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    k_est_fold<<<1, 32, 0, (cudaStream_t) stream>>>(ctx->d_est_state, advance_dev, ctx->C);
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    return GPSIQ_OK;
+}
+
+int gpsiq_estimate_anchor_device(gpsiq_ctx* ctx, void* stream) {
+    if (!ctx) return GPSIQ_ERR_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaMemcpyAsync(ctx->d_est_state, ctx->d_carr_state, ctx->C * sizeof(double), cudaMemcpyDeviceToDevice,
+                       (cudaStream_t) stream));
+    return GPSIQ_OK;
+}
+
 int gpsiq_render_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, int16_t* iq_dev, void* stream) {
-    if (!ctx || !desc_dev || !iq_dev || n_epochs < 1 || n_epochs != ctx->last_epochs || ((uintptr_t) iq_dev & 15))
+    if (!ctx || !desc_dev || !iq_dev || n_epochs < 1 || n_epochs != ctx->last_epochs || ctx->phase_done != 3 ||
+        ((uintptr_t) iq_dev & 15))
         return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_render_device: bad argument (must follow gpsiq_scan_device of the same batch)",
                     cudaSuccess);
     CU(cudaSetDevice(ctx->cfg.device));
@@ -846,7 +962,7 @@ int gpsiq_carrier_from_device(gpsiq_ctx* ctx, const double* src_dev, void* strea
     CU(cudaSetDevice(ctx->cfg.device));
     CU(cudaMemcpyAsync(ctx->d_carr_state, src_dev, ctx->C * sizeof(double), cudaMemcpyDeviceToDevice,
                        (cudaStream_t) stream));
-    return GPSIQ_OK;
+    return GPSIQ_OK;  // the estimate is NOT touched: a speculation from it may already be in flight
 }
 
 int gpsiq_get_carrier(gpsiq_ctx* ctx, double* p) {
@@ -862,6 +978,7 @@ int gpsiq_set_carrier(gpsiq_ctx* ctx, const double* p) {
     CU(cudaSetDevice(ctx->cfg.device));
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(ctx->d_carr_state, p, ctx->C * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_est_state, p, ctx->C * sizeof(double), cudaMemcpyHostToDevice));
     return GPSIQ_OK;
 }
 

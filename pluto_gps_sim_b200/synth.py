@@ -136,6 +136,21 @@ class Synthesizer:
     def scan_device(self, desc_dev_ptr, n_epochs, stream_ptr=None):
         capi.check(capi.lib.gpsiq_scan_device(self._ctx, desc_dev_ptr, n_epochs, stream_ptr), self._ctx)
 
+    def prepare_device(self, desc_dev_ptr, n_epochs, advance_dev_ptr=None, stream_ptr=None):
+        capi.check(capi.lib.gpsiq_prepare_device(self._ctx, desc_dev_ptr, n_epochs, advance_dev_ptr, stream_ptr), self._ctx)
+
+    def speculate_device(self, desc_dev_ptr, n_epochs, stream_ptr=None):
+        capi.check(capi.lib.gpsiq_speculate_device(self._ctx, desc_dev_ptr, n_epochs, stream_ptr), self._ctx)
+
+    def chain_device(self, desc_dev_ptr, n_epochs, stream_ptr=None):
+        capi.check(capi.lib.gpsiq_chain_device(self._ctx, desc_dev_ptr, n_epochs, stream_ptr), self._ctx)
+
+    def estimate_fold_device(self, advance_dev_ptr, stream_ptr=None):
+        capi.check(capi.lib.gpsiq_estimate_fold_device(self._ctx, advance_dev_ptr, stream_ptr), self._ctx)
+
+    def estimate_anchor_device(self, stream_ptr=None):
+        capi.check(capi.lib.gpsiq_estimate_anchor_device(self._ctx, stream_ptr), self._ctx)
+
     def render_device(self, desc_dev_ptr, n_epochs, iq_dev_ptr, stream_ptr=None):
         capi.check(capi.lib.gpsiq_render_device(self._ctx, desc_dev_ptr, n_epochs, iq_dev_ptr, stream_ptr), self._ctx)
 

@@ -8,18 +8,24 @@ channel: rank r owns slice r of every step (epochs [r*E, (r+1)*E) of the step's
 N*E epochs) and needs the carrier phases at the end of the previous slice.
 
 Per step, rank r:
-    1. receives max_chan doubles from rank r-1 (rank 0: from rank N-1's slice
+    1. prepare: LUTs/tables and the slice's CLOSED-FORM phase advance per channel;
+       one tiny all_gather shares the advances, and every rank folds the advances
+       of the slices between its previous slice and this one into its start-phase
+       ESTIMATE;
+    2. speculate: code-NCO scan + speculative carrier scans from that estimate --
+       no exact phase needed, so all ranks do this at the same time;
+    3. receives max_chan exact phases from rank r-1 (rank 0: from rank N-1's slice
        of the previous step -- the stream is continuous), except at stream start;
-    2. runs the scan phase (exact NCO state at every tile boundary) -- this is
-       what advances the carrier phase;
-    3. sends its end phases to rank r+1 *before* starting the per-sample work;
-    4. renders its slice (the bulk of the work) while later ranks scan.
+    4. chain: the exact phase is chained through the slice (O(one carrier cycle)
+       per epoch: the only serial work of the whole scheme);
+    5. sends its end phases to rank r+1 *before* starting the per-sample work;
+    6. renders its slice (the bulk of the work) while later ranks chain.
 
-The only collective traffic is max_chan doubles per slice boundary (point to
-point, latency bound); there is deliberately no bulk collective (NVLink
-bandwidth is irrelevant to this path).  In FLOAT carrier mode the scan phases of
-the N ranks are therefore serialised (a relay) and the renders overlap; in INT32
-mode the phase advance of a slice is a closed form, so the relay costs nothing.
+The collective traffic is 2*max_chan doubles per rank per step in the all_gather
+plus max_chan doubles per slice boundary point to point (latency bound);
+there is deliberately no bulk collective (NVLink bandwidth is irrelevant to this
+path).  Estimates only affect speed: a poor one makes epochs fall back to the
+serial scan inside `chain`, it never changes a sample.
 
 ``engine`` abstracts the device: ``Synthesizer``-backed on GPUs (GpuSliceEngine),
 an oracle-backed stand-in in the gloo/CPU tests of this logic.
@@ -34,6 +40,7 @@ class GpuSliceEngine:
     def __init__(self, synth):
         self.s = synth
         self.phase = torch.zeros(synth.max_chan, dtype=torch.float64, device="cuda")
+        self.adv = torch.zeros(2 * synth.max_chan, dtype=torch.float64, device="cuda")
 
     def _stream(self):
         return torch.cuda.current_stream().cuda_stream
@@ -44,8 +51,20 @@ class GpuSliceEngine:
     def store_carrier(self):           # engine state -> self.phase
         self.s.carrier_to_device(self.phase.data_ptr(), self._stream())
 
-    def scan(self, desc_dev, n_epochs):
-        self.s.scan_device(desc_dev.data_ptr(), n_epochs, self._stream())
+    def prepare(self, desc_dev, n_epochs):      # -> self.adv
+        self.s.prepare_device(desc_dev.data_ptr(), n_epochs, self.adv.data_ptr(), self._stream())
+
+    def estimate_fold(self, adv):
+        self.s.estimate_fold_device(adv.data_ptr(), self._stream())
+
+    def estimate_anchor(self):         # estimate <- exact carrier state
+        self.s.estimate_anchor_device(self._stream())
+
+    def speculate(self, desc_dev, n_epochs):
+        self.s.speculate_device(desc_dev.data_ptr(), n_epochs, self._stream())
+
+    def chain(self, desc_dev, n_epochs):
+        self.s.chain_device(desc_dev.data_ptr(), n_epochs, self._stream())
 
     def render(self, desc_dev, n_epochs, out_dev):
         self.s.render_device(desc_dev.data_ptr(), n_epochs, out_dev.data_ptr(), self._stream())
@@ -57,16 +76,36 @@ class TimeSliceRunner:
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
         self.step_index = 0
+        self.prev_adv = None
 
     def step(self, desc, n_epochs, out):
-        """Synthesize this rank's slice of the next step."""
+        """Synthesize this rank's slice of the next step.
+
+        Every rank issues its communication in the same global order -- hand-off into
+        rank 0 (closing the previous step's ring), all_gather of this step, then the
+        hand-offs 0->1->...->N-1 -- so in-order streams (NCCL) and blocking calls
+        (gloo) cannot deadlock."""
         eng, r, n = self.engine, self.rank, self.world
+        have_exact = False
+        if n > 1 and r == 0 and self.step_index > 0:            # close the previous step's ring first
+            dist.recv(eng.phase, src=n - 1)
+            eng.load_carrier()
+            eng.estimate_anchor()                               # rank 0 speculates from the exact phase
+            have_exact = True
+        eng.prepare(desc, n_epochs)
         if n > 1:
-            first = self.step_index == 0 and r == 0          # stream start: phases come from RESET descriptors
-            if not first:
-                dist.recv(eng.phase, src=(r - 1) % n)
-                eng.load_carrier()
-        eng.scan(desc, n_epochs)
+            adv_all = [torch.empty_like(eng.adv) for _ in range(n)]
+            dist.all_gather(adv_all, eng.adv)
+            if not have_exact:                                  # slices owned by other ranks since my last one
+                skipped = ([] if self.prev_adv is None else self.prev_adv[r + 1:]) + adv_all[:r]
+                for a in skipped:
+                    eng.estimate_fold(a)
+            self.prev_adv = adv_all
+        eng.speculate(desc, n_epochs)
+        if n > 1 and r > 0:
+            dist.recv(eng.phase, src=r - 1)
+            eng.load_carrier()
+        eng.chain(desc, n_epochs)
         if n > 1:
             eng.store_carrier()
             dist.send(eng.phase, dst=(r + 1) % n)
