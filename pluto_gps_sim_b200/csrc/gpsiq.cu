@@ -68,7 +68,8 @@ static void ca_generate(int prn, uint8_t* chips) {
 // ---------------------------------------------------------------------------
 #define TIMING_RING 64
 
-#define FX_SUB_EPOCHS 12  // 12 epochs x 37 CTAs = 444 = 148 SMs x 3 resident CTAs: one full wave; records (~42 MB) stay in L2
+#define FX_SUB_EPOCHS 8   // 8 epochs x 37 CTAs = 296 = 148 SMs x 2 resident 512-thread CTAs: one full wave; the
+                          // sub-batch's records + corrections (~42 MB at 12 slots) stay in L2 between the kernels
 
 struct gpsiq_ctx {
     gpsiq_config cfg;
@@ -83,7 +84,10 @@ struct gpsiq_ctx {
     int* d_flags;         // [2][E]: amplitude sum per epoch, step-contract flag per epoch
     int use_fixed;        // k_synth_fixed is eligible for this configuration
     unsigned char* d_recs; // [FX_SUB_EPOCHS][ntiles] tile records (synth_fixed.cuh)
-    uint32_t* d_fixmasks;  // [FX_SUB_EPOCHS][ntiles][C][4]
+    uint32_t* d_fixmasks;  // [FX_SUB_EPOCHS][ntiles][C][4] (+ the work-list counter behind it, cleared together)
+    int32_t* d_delta;      // [FX_SUB_EPOCHS][ntiles][FX_TILE] per-sample corrections
+    uint32_t* d_work;      // work list of (tile, channel, run) triples with a segment boundary
+    int work_cap;
     double* d_code_ck;    // [E][ntiles][C]
     int* d_wrap_ck;       // [E][ntiles][C]
     double* d_carr_ck;    // [2][E][ntiles][C] two speculation planes (INT32 mode: uint32 phase as double, plane 0)
@@ -728,7 +732,10 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
         CU(cudaFuncSetAttribute(k_synth_fixed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fx_smem_bytes(ctx->C)));
         const size_t tiles = (size_t) FX_SUB_EPOCHS * ctx->ntiles;
         CU(cudaMalloc(&ctx->d_recs, tiles * fx_rec_bytes(ctx->C)));
-        CU(cudaMalloc(&ctx->d_fixmasks, tiles * fx_fixmask_words(ctx->C) * 4));
+        CU(cudaMalloc(&ctx->d_fixmasks, tiles * fx_fixmask_words(ctx->C) * 4 + 16));
+        CU(cudaMalloc(&ctx->d_delta, tiles * FX_TILE * sizeof(int32_t)));
+        ctx->work_cap = (int) (tiles * ctx->C * 40);  // ~3x the typical count; overflow routes the epoch to the lane kernel
+        CU(cudaMalloc(&ctx->d_work, (size_t) ctx->work_cap * 4));
     }
     const size_t smem_lanes = (size_t) ctx->C * 512 * sizeof(int2) + (size_t) ctx->C * 33 * 4;
     CU(cudaFuncSetAttribute(k_synth_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_lanes));
@@ -741,7 +748,7 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_desc); cudaFree(ctx->d_lut); cudaFree(ctx->d_lutp); cudaFree(ctx->d_chips); cudaFree(ctx->d_flags);
-    cudaFree(ctx->d_recs); cudaFree(ctx->d_fixmasks); cudaFree(ctx->d_code_ck); cudaFree(ctx->d_wrap_ck);
+    cudaFree(ctx->d_recs); cudaFree(ctx->d_fixmasks); cudaFree(ctx->d_delta); cudaFree(ctx->d_work); cudaFree(ctx->d_code_ck); cudaFree(ctx->d_wrap_ck);
     cudaFree(ctx->d_carr_ck); cudaFree(ctx->d_tab); cudaFree(ctx->d_drift); cudaFree(ctx->d_spec); cudaFree(ctx->d_info); cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_est_state); cudaFree(ctx->d_adv); cudaFree(ctx->d_carr_trace); cudaFree(ctx->d_ca);
     cudaFree(ctx->d_iq); cudaFree(ctx->d_sums); cudaFree(ctx->d_err);
     for (int i = 0; i < TIMING_RING; i++)
@@ -826,16 +833,22 @@ static int enqueue_render(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n
         const int tgroups = (ntiles + 31) / 32;
         for (int e0 = 0; e0 < n_epochs; e0 += FX_SUB_EPOCHS) {
             const int ne = n_epochs - e0 < FX_SUB_EPOCHS ? n_epochs - e0 : FX_SUB_EPOCHS;
-            CU(cudaMemsetAsync(ctx->d_fixmasks, 0, (size_t) ne * ntiles * fx_fixmask_words(C) * 4, st));
+            const size_t mask_bytes = (size_t) ne * ntiles * fx_fixmask_words(C) * 4;
+            int* nwork = (int*) ((unsigned char*) ctx->d_fixmasks + (size_t) FX_SUB_EPOCHS * ntiles * fx_fixmask_words(C) * 4);
+            CU(cudaMemsetAsync(ctx->d_fixmasks, 0, mask_bytes, st));
+            CU(cudaMemsetAsync(nwork, 0, 16, st));
+            CU(cudaMemsetAsync(ctx->d_delta, 0, (size_t) ne * ntiles * FX_TILE * sizeof(int32_t), st));
             const int warps = ne * 2 * C * tgroups;
             k_tile_prologue<<<(warps + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_code_ck, ctx->d_wrap_ck,
                                                              ctx->d_carr_ck, ctx->ck_plane, ctx->d_info, ctx->d_flags,
-                                                             ctx->d_flags + ctx->E, ctx->d_recs, ctx->d_fixmasks, e0, ne,
-                                                             C, N, ntiles);
-            k_synth_fixed<<<ne * groups, FX_THREADS, fx_smem_bytes(C), st>>>(
-                desc_dev, ctx->d_lutp, ctx->d_tab, ctx->d_recs, ctx->d_fixmasks, ctx->d_chips, ctx->d_flags,
+                                                             ctx->d_flags + ctx->E, ctx->d_recs, ctx->d_fixmasks,
+                                                             ctx->d_work, nwork, ctx->work_cap, e0, ne, C, N, ntiles);
+            k_tile_fixup<<<148 * 8, 128, 0, st>>>(desc_dev, ctx->d_lutp, ctx->d_tab, ctx->d_recs, ctx->d_chips, ctx->d_work,
+                                                 nwork, ctx->work_cap, ctx->d_delta, e0, C, N, ntiles);
+            k_synth_fixed<<<ne * groups, FX_WORKERS * FX_THREADS, fx_smem_bytes(C), st>>>(
+                desc_dev, ctx->d_lutp, ctx->d_tab, ctx->d_recs, ctx->d_delta, ctx->d_chips, ctx->d_flags,
                 ctx->d_flags + ctx->E, iq_dev, e0, C, N, ntiles, groups);
-            ctx->launches += 2;
+            ctx->launches += 3;
         }
     }
     // all epochs (lane kernel selected) or only those outside the fixed-point kernel's contract

@@ -23,9 +23,14 @@
 // two shared-memory loads and one multiply-add on the packed I/Q word
 // (plutogpssim.c:2701-2706), with no branch.  A run that contains a segment
 // boundary (binade crossing, wrap, NAV bit edge) extrapolates the wrong segment
-// for the rest of the run; those few (channel, run) pairs are listed by the
-// prologue and a fix-up pass adds (right - wrong) to a per-sample correction
-// that the main pass starts its accumulators from.  Packed accumulation is
+// for the rest of the run; those few (tile, channel, run) triples are appended to
+// a work list by the prologue, and k_tile_fixup adds (right - wrong) into a dense
+// per-sample correction array that the main pass starts its accumulators from.
+//
+// Per sub-batch of FX_SUB_EPOCHS epochs (sized so that the records stay in L2):
+//   k_tile_prologue  1 thread per (epoch, tile, channel, NCO): segment lists
+//   k_tile_fixup     1 thread per listed (tile, channel, run): corrections
+//   k_synth_fixed    4 tile-workers of 128 threads per CTA: the sample loop  Packed accumulation is
 // exact while |sum I|, |sum Q| <= 32767; epochs that could exceed that, or
 // whose steps are outside the segment-list contract, are flagged by k_prepare
 // and rendered by k_synth_lanes instead.
@@ -35,7 +40,6 @@
 #define FX_RUN 8
 #define FX_TILE (FX_THREADS * FX_RUN)
 #define FX_MAXC 24
-#define FX_TILES_PER_CTA 8
 
 namespace gpsiq {
 
@@ -99,7 +103,8 @@ __host__ __device__ inline int fx_seg_cap(int is_carrier) { return is_carrier ? 
 // tiles of the same (epoch, channel, NCO), so its lanes see the same step and
 // similar segment statistics.
 template <int MODE>
-__device__ __forceinline__ void fx_tile_walk(unsigned char* rec, uint32_t* fixmask, int C, int c, const BinadeTab& tab,
+__device__ __forceinline__ void fx_tile_walk(unsigned char* rec, uint32_t* fixmask, uint32_t* work, int* nwork,
+                                             int work_cap, uint32_t tile_id, int C, int c, const BinadeTab& tab,
                                              double x, double d, int len, int icode, int kbit, uint64_t navbits,
                                              int* overflow) {
     constexpr int IS_CARR = (MODE == NCO_CARRIER) ? 1 : 0;
@@ -117,7 +122,12 @@ __device__ __forceinline__ void fx_tile_walk(unsigned char* rec, uint32_t* fixma
         segn[nseg] = (uint16_t) n;
         if (n & (FX_RUN - 1)) {  // a boundary inside a run: that (channel, run) needs a fix-up
             const int r = n >> 3;
-            atomicOr(&fixmask[r >> 5], 1u << (r & 31));
+            const uint32_t bit = 1u << (r & 31);
+            if (!(atomicOr(&fixmask[r >> 5], bit) & bit)) {  // first boundary seen in this (channel, run)
+                const int slot = atomicAdd(nwork, 1);
+                if (slot < work_cap) work[slot] = (tile_id << 12) | ((uint32_t) c << 7) | (uint32_t) r;
+                else *overflow = 1;
+            }
         }
         const int k = run_in_binade<MODE>(x, tab, len - 1 - n);  // samples n .. n+k share the segment
         for (; (rnext << 3) <= n + k; rnext++) {                 // runs whose first sample lies in it
@@ -143,7 +153,8 @@ k_tile_prologue(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __res
                 const double* __restrict__ code_ck, const int* __restrict__ wrap_ck,
                 const double* __restrict__ carr_ck, size_t ck_plane, const CarrInfo* __restrict__ info,
                 const int* __restrict__ amp_sum, int* __restrict__ step_flag, unsigned char* __restrict__ recs,
-                uint32_t* __restrict__ fixmasks, int e0, int E, int C, int N, int ntiles) {
+                uint32_t* __restrict__ fixmasks, uint32_t* __restrict__ work, int* __restrict__ nwork, int work_cap,
+                int e0, int E, int C, int N, int ntiles) {
     __shared__ BinadeTab s_tab[4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tgroups = (ntiles + 31) / 32;
@@ -176,163 +187,164 @@ k_tile_prologue(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __res
         double ph;
         if (n0 < inf.n1 || inf.n1 >= N) ph = carr_ck[o];
         else ph = __dadd_rn(carr_ck[(size_t) inf.variant * ck_plane + o], inf.delta);
-        fx_tile_walk<NCO_CARRIER>(rec, fixmask, C, c, s_tab[warp], ph, d.carr_step, len, 0, 0, 0, &overflow);
+        fx_tile_walk<NCO_CARRIER>(rec, fixmask, work, nwork, work_cap, (uint32_t) tile_id, C, c, s_tab[warp], ph,
+                                  d.carr_step, len, 0, 0, 0, &overflow);
     } else {
         const int wr = wrap_ck[o] + d.ms0 % 20;
-        fx_tile_walk<NCO_CODE>(rec, fixmask, C, c, s_tab[warp], code_ck[o], d.code_step, len, wr % 20, wr / 20,
-                               d.navbits, &overflow);
+        fx_tile_walk<NCO_CODE>(rec, fixmask, work, nwork, work_cap, (uint32_t) tile_id, C, c, s_tab[warp], code_ck[o],
+                               d.code_step, len, wr % 20, wr / 20, d.navbits, &overflow);
     }
     if (overflow) atomicOr(&step_flag[e], 2);  // segment list too long: the epoch goes to k_synth_lanes
 }
 
-struct FxSmem {
-    int C;
-    int32_t* lut;        // [C][512]  packed (Q << 16) + I
-    int8_t* chip;        // [C][2048] +-1, index = nav polarity << 10 | chip
-    int64_t* dF;         // [C][NBINADE]
-    int64_t* dG;         // [C][NBINADE]
-    unsigned char* rec;  // the tile record (fx_rec_bytes)
-    uint64_t* segdF;     // [C][FX_SPER] in-segment fixed-point step of every segment
-    int32_t* delta;      // [FX_TILE]
-    uint16_t* work;      // [C * FX_THREADS]
-    int* nwork;
-};
-
-__host__ __device__ inline size_t fx_smem_bytes(int C) {
-    return (size_t) C * 512 * 4 + (size_t) C * 2048 + (size_t) C * NBINADE * 16 + fx_rec_bytes(C) + (size_t) C * FX_SPER * 8 +
-           (size_t) FX_TILE * 4 + (size_t) C * FX_THREADS * 2 + 16 + 64;
+// In-segment fixed-point step of the segment starting at fixed-point state f0.
+__device__ __forceinline__ uint64_t fx_seg_step(const BinadeTab& tab, uint64_t f0, int is_carrier) {
+    const int bi = is_carrier ? fx_carr_bi(f0) : fx_code_bi(f0);
+    if (!((tab.valid >> bi) & 1u)) return 0;
+    return (uint64_t) fx_scale_delta(tab.delta[bi], (is_carrier ? 11 : 10) - bi);
 }
 
-__device__ __forceinline__ void fx_carve(FxSmem& s, unsigned char* base, int C) {
-    s.C = C;
-    s.rec = base;                             base += fx_rec_bytes(C);
-    s.segdF = (uint64_t*) base;               base += (size_t) C * FX_SPER * 8;
-    s.dF = (int64_t*) base;                   base += (size_t) C * NBINADE * 8;
-    s.dG = (int64_t*) base;                   base += (size_t) C * NBINADE * 8;
-    s.lut = (int32_t*) base;                  base += (size_t) C * 512 * 4;
-    s.delta = (int32_t*) base;                base += (size_t) FX_TILE * 4;
-    s.nwork = (int*) base;                    base += 16;
-    s.chip = (int8_t*) base;                  base += (size_t) C * 2048;
-    s.work = (uint16_t*) base;
+// k_tile_fixup: one thread per listed (tile, channel, run).  For each sample of the run it
+// evaluates what the main pass will add for that channel (the run's start state extrapolated)
+// and what is right (following the segment lists), and adds the difference to delta[tile][n].
+__global__ void __launch_bounds__(128)
+k_tile_fixup(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict__ lutp,
+             const BinadeTab* __restrict__ tabs, const unsigned char* __restrict__ recs,
+             const int8_t* __restrict__ chips, const uint32_t* __restrict__ work, const int* __restrict__ nwork,
+             int work_cap, int32_t* __restrict__ delta, int e0, int C, int N, int ntiles) {
+    const int count = min(*nwork, work_cap);
+    const size_t rec_bytes = fx_rec_bytes(C);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const uint32_t item = work[i];
+        const int r = item & 127, c = (item >> 7) & 31;
+        const uint32_t tile_id = item >> 12;
+        const int e = e0 + tile_id / ntiles, t = tile_id % ntiles;
+        const int len = min(FX_TILE, N - t * FX_TILE);
+        const unsigned char* rec = recs + (size_t) tile_id * rec_bytes;
+        const uint64_t* segF = (const uint64_t*) (rec + fx_rec_segF(C));
+        const uint16_t* segn = (const uint16_t*) (rec + fx_rec_segn(C));
+        const uint16_t* nsegs = (const uint16_t*) (rec + fx_rec_nseg(C));
+        const BinadeTab* tab = tabs + ((size_t) e * C + c) * 2;  // [0] code, [1] carrier
+        const int32_t* lut = lutp + ((size_t) e * C + c) * 512;
+        const int8_t* chip = chips + (size_t) desc[(size_t) e * C + c].prn * 2048;
+        // run-start states, extrapolated exactly as the main pass does
+        int ic = fx_seg_base(c, 1) + rec[fx_rec_runseg(C) + (c * 2 + 1) * FX_THREADS + r];
+        int ig = fx_seg_base(c, 0) + rec[fx_rec_runseg(C) + (c * 2) * FX_THREADS + r];
+        const int endc = fx_seg_base(c, 1) + nsegs[c * 2 + 1], endg = fx_seg_base(c, 0) + nsegs[c * 2];
+        uint64_t df = fx_seg_step(tab[1], segF[ic], 1), dg = fx_seg_step(tab[0], segF[ig], 0);
+        uint64_t f = segF[ic] + (uint64_t) (r * FX_RUN - segn[ic]) * df;
+        uint64_t g = segF[ig] + (uint64_t) (r * FX_RUN - segn[ig]) * dg;
+        uint64_t fe = f, dfe = df, ge = g, dge = dg;  // exact: follows the segment lists
+        for (int j = 0; j < FX_RUN; j++) {
+            const int n = r * FX_RUN + j;
+            if (n >= len) break;
+            if (ic + 1 < endc && segn[ic + 1] == n) { ic++; fe = segF[ic]; dfe = fx_seg_step(tab[1], fe, 1); }
+            if (ig + 1 < endg && segn[ig + 1] == n) { ig++; ge = segF[ig]; dge = fx_seg_step(tab[0], ge, 0); }
+            const int ir = (int) (fe >> 55), iw = (int) (f >> 55), cr = (int) (ge >> 53), cw = (int) (g >> 53);
+            if (ir != iw || cr != cw) {
+                const int32_t right = lut[ir] * (int32_t) chip[cr];
+                const int32_t wrong = lut[iw] * (int32_t) chip[cw];
+                if (right != wrong) atomicAdd(&delta[(size_t) tile_id * FX_TILE + n], right - wrong);
+            }
+            f += df; g += dg; fe += dfe; ge += dge;
+        }
+    }
+}
+
+// ---- k_synth_fixed -------------------------------------------------------------
+#define FX_WORKERS 4  // tile-workers (128 threads each) per CTA, sharing the epoch's tables
+#define FX_TILES_PER_WORKER 2
+#define FX_TILES_PER_CTA (FX_WORKERS * FX_TILES_PER_WORKER)
+
+__host__ __device__ inline size_t fx_smem_bytes(int C) {
+    return (size_t) C * 512 * 4 + (size_t) C * 2048 + (size_t) C * NBINADE * 16 + FX_WORKERS * fx_rec_bytes(C) + 64;
+}
+
+__device__ __forceinline__ void fx_worker_sync(int worker) {
+    asm volatile("bar.sync %0, %1;" ::"r"(worker + 1), "n"(FX_THREADS) : "memory");
 }
 
 // Fixed-point state of one NCO of channel c at the first sample of run r, and its
 // in-segment step: the run's segment start extrapolated inside its binade.
-// Returns the segment's index within the task's list.
-__device__ __forceinline__ int fx_run_state(const FxSmem& s, int c, int is_carrier, int r, uint64_t& f, uint64_t& df) {
+__device__ __forceinline__ void fx_run_state(const unsigned char* rec, const int64_t* dtab, int C, int c, int is_carrier,
+                                             int r, uint64_t& f, uint64_t& df) {
     const int task = c * 2 + is_carrier;
-    const int idx = s.rec[fx_rec_runseg(s.C) + task * FX_THREADS + r];
-    const int slot = fx_seg_base(c, is_carrier) + idx;
-    const uint64_t f0 = ((const uint64_t*) (s.rec + fx_rec_segF(s.C)))[slot];
-    const int ns = ((const uint16_t*) (s.rec + fx_rec_segn(s.C)))[slot];
-    df = s.segdF[slot];
+    const int slot = fx_seg_base(c, is_carrier) + rec[fx_rec_runseg(C) + task * FX_THREADS + r];
+    const uint64_t f0 = ((const uint64_t*) (rec + fx_rec_segF(C)))[slot];
+    const int ns = ((const uint16_t*) (rec + fx_rec_segn(C)))[slot];
+    df = (uint64_t) dtab[c * NBINADE + (is_carrier ? fx_carr_bi(f0) : fx_code_bi(f0))];
     f = f0 + (uint64_t) (r * FX_RUN - ns) * df;
-    return idx;
 }
 
-__global__ void __launch_bounds__(FX_THREADS)
+__global__ void __launch_bounds__(FX_WORKERS * FX_THREADS)
 k_synth_fixed(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict__ lutp,
               const BinadeTab* __restrict__ tabs, const unsigned char* __restrict__ recs,
-              const uint32_t* __restrict__ fixmasks, const int8_t* __restrict__ chips, const int* __restrict__ amp_sum, const int* __restrict__ step_flag,
-              int16_t* __restrict__ iq, int e0, int C, int N, int ntiles, int groups) {
+              const int32_t* __restrict__ delta, const int8_t* __restrict__ chips, const int* __restrict__ amp_sum,
+              const int* __restrict__ step_flag, int16_t* __restrict__ iq, int e0, int C, int N, int ntiles,
+              int groups) {
     extern __shared__ __align__(16) unsigned char fx_raw[];
-    FxSmem s;
-    fx_carve(s, fx_raw, C);
+    const size_t rec_bytes = fx_rec_bytes(C);
+    unsigned char* s_rec0 = fx_raw;
+    int64_t* s_dF = (int64_t*) (fx_raw + FX_WORKERS * rec_bytes);
+    int64_t* s_dG = s_dF + C * NBINADE;
+    int32_t* s_lut = (int32_t*) (s_dG + C * NBINADE);
+    int8_t* s_chip = (int8_t*) (s_lut + C * 512);
+
     const int e = e0 + blockIdx.x / groups;
     const int grp = blockIdx.x % groups;
     if (amp_sum[e] > 32767 || step_flag[e]) return;  // this epoch is rendered by k_synth_lanes
     const gpsiq_chan_desc* de = desc + (size_t) e * C;
-    const int tid = threadIdx.x;
-    const size_t rec_bytes = fx_rec_bytes(C);
+    const int tid_cta = threadIdx.x;
+    const int worker = tid_cta >> 7, tid = tid_cta & (FX_THREADS - 1);
 
-    // ---- stage the epoch's tables (reused for FX_TILES_PER_CTA tiles)
-    for (int i = tid; i < C * 512; i += FX_THREADS) s.lut[i] = (de[i >> 9].prn > 0) ? lutp[(size_t) e * C * 512 + i] : 0;
-    for (int i = tid; i < C * 512; i += FX_THREADS) {  // 2048 bytes per channel, 4 at a time
+    // ---- stage the epoch's tables once per CTA
+    for (int i = tid_cta; i < C * 512; i += FX_WORKERS * FX_THREADS) {
         const int prn = de[i >> 9].prn;
-        ((uint32_t*) s.chip)[i] = (prn > 0 && prn <= 32) ? ((const uint32_t*) chips)[prn * 512 + (i & 511)] : 0x01010101u;
+        s_lut[i] = (prn > 0) ? lutp[(size_t) e * C * 512 + i] : 0;
+        ((uint32_t*) s_chip)[i] = (prn > 0 && prn <= 32) ? ((const uint32_t*) chips)[prn * 512 + (i & 511)] : 0x01010101u;
     }
-    for (int i = tid; i < C * NBINADE; i += FX_THREADS) {
+    for (int i = tid_cta; i < C * NBINADE; i += FX_WORKERS * FX_THREADS) {
         const int c = i / NBINADE, bi = i - c * NBINADE;
         const BinadeTab* tc = tabs + ((size_t) e * C + c) * 2;
-        s.dG[i] = ((tc[0].valid >> bi) & 1u) ? fx_scale_delta(tc[0].delta[bi], 10 - bi) : 0;
-        s.dF[i] = ((tc[1].valid >> bi) & 1u) ? fx_scale_delta(tc[1].delta[bi], 11 - bi) : 0;
+        s_dG[i] = ((tc[0].valid >> bi) & 1u) ? fx_scale_delta(tc[0].delta[bi], 10 - bi) : 0;
+        s_dF[i] = ((tc[1].valid >> bi) & 1u) ? fx_scale_delta(tc[1].delta[bi], 11 - bi) : 0;
     }
+    __syncthreads();
 
+    unsigned char* s_rec = s_rec0 + worker * rec_bytes;
     uint32_t* out_epoch = reinterpret_cast<uint32_t*>(iq) + (size_t) e * N;
-    for (int tt = 0; tt < FX_TILES_PER_CTA; tt++) {
-        const int t = grp * FX_TILES_PER_CTA + tt;
+    for (int tt = 0; tt < FX_TILES_PER_WORKER; tt++) {
+        const int t = grp * FX_TILES_PER_CTA + tt * FX_WORKERS + worker;
         if (t >= ntiles) break;
         const int n0 = t * FX_TILE;
         const int len = min(FX_TILE, N - n0);
+        const size_t tile_id = (size_t) (e - e0) * ntiles + t;
 
-        // ---- load the tile record, reset per-tile scratch
+        // ---- this worker's tile record -> shared memory
         {
-            const uint4* src = (const uint4*) (recs + ((size_t) (e - e0) * ntiles + t) * rec_bytes);
-            uint4* dst = (uint4*) s.rec;
+            const uint4* src = (const uint4*) (recs + tile_id * rec_bytes);
+            uint4* dst = (uint4*) s_rec;
             for (int i = tid; i < (int) (rec_bytes / 16); i += FX_THREADS) dst[i] = src[i];
         }
-        for (int i = tid; i < FX_TILE; i += FX_THREADS) s.delta[i] = 0;
-        if (tid == 0) *s.nwork = 0;
-        __syncthreads();
-        for (int i = tid; i < C * FX_SPER; i += FX_THREADS) {  // in-segment step of every segment, from its binade
-            const int c = i / FX_SPER, k = i - c * FX_SPER;
-            const uint64_t f0 = ((const uint64_t*) (s.rec + fx_rec_segF(C)))[i];
-            s.segdF[i] = (k < FX_SCARR) ? (uint64_t) s.dF[c * NBINADE + fx_carr_bi(f0)]
-                                        : (uint64_t) s.dG[c * NBINADE + fx_code_bi(f0)];
-        }
-
-        // ---- list the (channel, run) pairs that contain a segment boundary
-        {
-            const uint32_t* fixmask = fixmasks + ((size_t) (e - e0) * ntiles + t) * fx_fixmask_words(C);
-            for (int c = 0; c < C; c++)
-                if ((fixmask[c * (FX_THREADS / 32) + (tid >> 5)] >> (tid & 31)) & 1u)
-                    s.work[atomicAdd(s.nwork, 1)] = (uint16_t) (c * FX_THREADS + tid);
-        }
-        __syncthreads();
-
-        // ---- fix-up pass: (right - wrong) for the samples of those runs
-        {
-            const uint64_t* segF = (const uint64_t*) (s.rec + fx_rec_segF(C));
-            const uint16_t* segn = (const uint16_t*) (s.rec + fx_rec_segn(C));
-            const uint16_t* nsegs = (const uint16_t*) (s.rec + fx_rec_nseg(C));
-            for (int i = tid; i < *s.nwork; i += FX_THREADS) {
-                const int c = s.work[i] / FX_THREADS, r = s.work[i] % FX_THREADS;
-                uint64_t f, df, g, dg;                 // extrapolated (what the main pass will add)
-                int ic = fx_run_state(s, c, 1, r, f, df) + fx_seg_base(c, 1);
-                int ig = fx_run_state(s, c, 0, r, g, dg) + fx_seg_base(c, 0);
-                const int ec = fx_seg_base(c, 1) + nsegs[c * 2 + 1], eg = fx_seg_base(c, 0) + nsegs[c * 2];
-                uint64_t fe = f, dfe = df, ge = g, dge = dg;  // exact: follows the segment lists
-                for (int j = 0; j < FX_RUN; j++) {
-                    const int n = r * FX_RUN + j;
-                    if (n >= len) break;
-                    if (ic + 1 < ec && segn[ic + 1] == n) { ic++; fe = segF[ic]; dfe = s.segdF[ic]; }
-                    if (ig + 1 < eg && segn[ig + 1] == n) { ig++; ge = segF[ig]; dge = s.segdF[ig]; }
-                    const int32_t right = s.lut[c * 512 + (int) (fe >> 55)] * (int32_t) s.chip[c * 2048 + (int) (ge >> 53)];
-                    const int32_t wrong = s.lut[c * 512 + (int) (f >> 55)] * (int32_t) s.chip[c * 2048 + (int) (g >> 53)];
-                    if (right != wrong) atomicAdd(&s.delta[n], right - wrong);
-                    f += df; g += dg; fe += dfe; ge += dge;
-                }
-            }
-        }
-        __syncthreads();
+        fx_worker_sync(worker);
 
         // ---- main pass: uniform integer inner loop
         if (tid * FX_RUN < len) {
             int32_t acc[FX_RUN];
-            {
-                const int4 a = *reinterpret_cast<const int4*>(s.delta + tid * FX_RUN);
-                const int4 b = *reinterpret_cast<const int4*>(s.delta + tid * FX_RUN + 4);
+            {   // corrections for runs that contain a segment boundary (zero elsewhere)
+                const int4* dp = reinterpret_cast<const int4*>(delta + tile_id * FX_TILE + tid * FX_RUN);
+                const int4 a = dp[0], b = dp[1];
                 acc[0] = a.x; acc[1] = a.y; acc[2] = a.z; acc[3] = a.w;
                 acc[4] = b.x; acc[5] = b.y; acc[6] = b.z; acc[7] = b.w;
             }
-            const uint16_t* nseg = (const uint16_t*) (s.rec + fx_rec_nseg(C));
+            const uint16_t* nseg = (const uint16_t*) (s_rec + fx_rec_nseg(C));
             for (int c = 0; c < C; c++) {
-                if (nseg[c * 2] == 0) continue;  // inactive slot (uniform across the CTA)
+                if (nseg[c * 2] == 0) continue;  // inactive slot (uniform across the worker)
                 uint64_t f, df, g, dg;
-                fx_run_state(s, c, 1, tid, f, df);
-                fx_run_state(s, c, 0, tid, g, dg);
-                const int32_t* lut = s.lut + c * 512;
-                const int8_t* chip = s.chip + c * 2048;
+                fx_run_state(s_rec, s_dF, C, c, 1, tid, f, df);
+                fx_run_state(s_rec, s_dG, C, c, 0, tid, g, dg);
+                const int32_t* lut = s_lut + c * 512;
+                const int8_t* chip = s_chip + c * 2048;
 #pragma unroll
                 for (int j = 0; j < FX_RUN; j++) {
                     acc[j] += lut[(uint32_t) (f >> 55)] * (int32_t) chip[(uint32_t) (g >> 53)];
@@ -352,7 +364,7 @@ k_synth_fixed(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restric
                 for (int j = 0; j < FX_RUN && tid * FX_RUN + j < len; j++) dst[j] = w[j];
             }
         }
-        __syncthreads();
+        fx_worker_sync(worker);  // the record buffer is reused for the next tile
     }
 }
 
