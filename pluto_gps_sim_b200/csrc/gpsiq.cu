@@ -90,10 +90,16 @@ struct gpsiq_ctx {
     int work_cap;
     double* d_code_ck;    // [E][ntiles][C]
     int* d_wrap_ck;       // [E][ntiles][C]
-    double* d_carr_ck;    // [2][E][ntiles][C] two speculation planes (INT32 mode: uint32 phase as double, plane 0)
+    double* d_carr_ck;    // [5][E][ntiles][C] planes: 0,1 chunk speculation (parity variants), 2,3 stitched epoch-level
+                          // trajectory P (variants), 4 exact (chain heads / fallbacks; INT32 mode: uint32 phase as double)
     BinadeTab* d_tab;     // [E][C][2]  (0 = code NCO, 1 = carrier NCO)
-    double* d_drift;      // [E][C] predicted carrier rounding drift per epoch (estimate aid only)
-    CarrSpec* d_spec;     // [E][C][2]
+    double* d_drift;      // [E][C] estimate aids only: closed-form phase advance of each epoch incl. predicted
+                          // rounding drift (eadv), then [E][C] re-seed phase or -1 (ereset), then [E][C] the
+                          // estimated phase at the start of each epoch (est_epoch)
+    CarrSpec* d_spec;     // [E][C][J][2] chunk-level speculation results
+    CarrSpec* d_specE;    // [E][C][2]    epoch-level (stitched) results
+    ChunkInfo* d_cinfo;   // [E][C][2][J]
+    int G, J;             // chunk length in tiles, chunks per epoch
     CarrInfo* d_info;     // [E][C]
     int* d_fallbacks;     // epochs that fell back to the serial carrier scan (diagnostic counter)
     size_t ck_plane;      // elements per plane
@@ -138,13 +144,17 @@ __global__ void k_prepare(const gpsiq_chan_desc* __restrict__ desc, int2* __rest
     const int ec = blockIdx.x;
     const gpsiq_chan_desc d = desc[ec];
     int2* out = lut + (size_t) ec * 512;
-    if (d.prn <= 0) return;
+    if (d.prn <= 0) {
+        if (threadIdx.x == 0) { drift[ec] = 0.0; drift[(size_t) gridDim.x + ec] = -1.0; }
+        return;
+    }
     // per-binade fixed-point increments of the two NCOs for this epoch's steps (nco_scan.cuh)
     if (threadIdx.x == 0) build_binade_tab<NCO_CODE>(d.code_step, tab[(size_t) ec * 2]);
     if (threadIdx.x == 32 && carrier_mode == GPSIQ_CARRIER_FLOAT) {
         BinadeTab& tp = tab[(size_t) ec * 2 + 1];
         build_binade_tab<NCO_CARRIER>(d.carr_step, tp);
-        drift[ec] = carr_drift_estimate(d.carr_step, tp, N);
+        drift[ec] = fma((double) N, d.carr_step, carr_drift_estimate(d.carr_step, tp, N));   // eadv
+        drift[(size_t) gridDim.x + ec] = (d.flags & GPSIQ_FLAG_RESET_CARRIER) ? d.carr_phase0 : -1.0;  // ereset
     }
     if (d.prn > 32 || !(d.code_phase0 >= 0.0 && d.code_phase0 < 1023.0) || !(d.code_step > 0.0 && d.code_step < 1023.0)) {
         if (threadIdx.x == 0) atomicExch(err, 1 + ec);
@@ -221,7 +231,7 @@ __global__ void k_scan_carrier(const gpsiq_chan_desc* __restrict__ desc, const B
         if (carrier_mode == GPSIQ_CARRIER_FLOAT) {
             const BinadeTab tab = tabs[((size_t) e * C + c) * 2 + 1];
             for (int t = 0; t < ntiles; t++) {
-                carr_ck[((size_t) e * ntiles + t) * C + c] = x;
+                carr_ck[((size_t) e * ntiles + t) * C + c] = x;  // (carr_ck = the exact plane)
                 const int len = min(T, N - t * T);
                 nco_advance<NCO_CARRIER>(x, d.carr_step, tab, len, dummy);
             }
@@ -249,21 +259,26 @@ __device__ __forceinline__ double est_advance_dev(double x, double d, int N) {
     return (t >= 0.0 && t < 1.0) ? t : 0.0;
 }
 
+__device__ __forceinline__ double frac01(double t) {
+    t -= floor(t);
+    return (t >= 0.0 && t < 1.0) ? t : 0.0;
+}
+
 // Closed-form (estimated) effect of one batch on the carrier phase of every slot:
 // adv[c] = sum over the batch's epochs of N*step + predicted rounding drift, and
 // adv[C+c] = 1 if a descriptor re-seeded the slot (then adv[c] is an absolute phase).
 // Feeds only the start-phase ESTIMATES of later speculative scans, on this GPU or
 // -- for time-sliced multi-GPU runs -- on the ranks that own later slices.
-__global__ void k_slice_advance(const gpsiq_chan_desc* __restrict__ desc, const double* __restrict__ drift,
-                                double* __restrict__ adv, int E, int C, int N) {
+__global__ void k_slice_advance(const double* __restrict__ eadv, const double* __restrict__ ereset,
+                                double* __restrict__ adv, int E, int C) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double x = 0.0, abs_flag = 0.0;
+#pragma unroll 16
     for (int e = 0; e < E; e++) {
-        const gpsiq_chan_desc* d = desc + (size_t) e * C + c;
-        if (d->prn <= 0) continue;
-        if (d->flags & GPSIQ_FLAG_RESET_CARRIER) { x = d->carr_phase0; abs_flag = 1.0; }
-        x = est_advance_dev(x + drift[(size_t) e * C + c], d->carr_step, N);
+        const double r = ereset[(size_t) e * C + c], a = eadv[(size_t) e * C + c];
+        if (r >= 0.0) { x = r; abs_flag = 1.0; }
+        x = frac01(x + a);
     }
     adv[c] = x;
     adv[C + c] = abs_flag;
@@ -273,37 +288,78 @@ __global__ void k_slice_advance(const gpsiq_chan_desc* __restrict__ desc, const 
 __global__ void k_est_fold(double* __restrict__ est, const double* __restrict__ adv, int C) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    double t = (adv[C + c] != 0.0) ? adv[c] : est[c] + adv[c];
-    t -= floor(t);
-    est[c] = (t >= 0.0 && t < 1.0) ? t : 0.0;
+    est[c] = frac01((adv[C + c] != 0.0) ? adv[c] : est[c] + adv[c]);
 }
 
+// Estimated phase at the start of every epoch of the batch, from the context's batch-start estimate.
+__global__ void k_epoch_estimates(const double* __restrict__ eadv, const double* __restrict__ ereset,
+                                  const double* __restrict__ est_state, double* __restrict__ est_epoch, int E, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double x = est_state[c];
+#pragma unroll 16
+    for (int e = 0; e < E; e++) {
+        const double r = ereset[(size_t) e * C + c], a = eadv[(size_t) e * C + c];
+        if (r >= 0.0) x = r;  // re-seeded: the start phase of this epoch is known exactly
+        est_epoch[(size_t) e * C + c] = x;
+        x = frac01(x + a);
+    }
+}
+
+// One chain per (epoch, slot, chunk, parity variant): speculative scan of the chunk's tiles.
 __global__ void k_carr_speculate(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
-                                 const double* __restrict__ drift, const double* __restrict__ carr_state,
+                                 const double* __restrict__ eadv, const double* __restrict__ est_epoch,
                                  double* __restrict__ carr_ck, size_t ck_plane, CarrSpec* __restrict__ spec, int E,
-                                 int C, int N, int T, int ntiles) {
+                                 int C, int N, int T, int ntiles, int G, int J) {
     const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (chain >= E * C * 2 || (threadIdx.x & 31)) return;
-    const int v = chain & 1, ec = chain >> 1;
+    if (chain >= E * C * J * 2 || (threadIdx.x & 31)) return;
+    const int v = chain & 1;
+    const int j = (chain >> 1) % J, ec = (chain >> 1) / J;
     const int e = ec / C, c = ec - e * C;
     const gpsiq_chan_desc d = desc[ec];
     CarrSpec out;
     out.margin = -1.0; out.n1 = -1; out.xw1 = 0.0; out.xend = 0.0; out.pad = 0;
     if (d.prn > 0 && !(v == 1 && d.carr_step >= 0.0) && carr_step_speculable(d.carr_step)) {
-        // estimated start phase: chain the batch's epochs in closed form (one rounding per epoch)
-        double x = carr_state[c];  // = the context's ESTIMATE of the batch-start phase
-        for (int k = 0; k < e; k++) {
-            const gpsiq_chan_desc* dk = desc + (size_t) k * C + c;
-            if (dk->prn <= 0) continue;
-            if (dk->flags & GPSIQ_FLAG_RESET_CARRIER) x = dk->carr_phase0;
-            x = est_advance_dev(x + drift[(size_t) k * C + c], dk->carr_step, N);
-        }
-        if (d.flags & GPSIQ_FLAG_RESET_CARRIER) x = d.carr_phase0;
+        const int t0 = j * G, t1 = min(t0 + G, ntiles);
+        // estimated phase at the chunk's first sample (chunk 0: the epoch estimate itself)
+        double x = est_epoch[ec];
+        if (j > 0) x = frac01(x + eadv[ec] * ((double) (t0 * T) / (double) N));
         const BinadeTab tab = tabs[(size_t) ec * 2 + 1];
-        spec_scan_epoch(x, d.carr_step, tab, N, T, v, carr_ck + (size_t) v * ck_plane + (size_t) e * ntiles * C + c,
-                        (size_t) C, out);
+        spec_scan_range(x, d.carr_step, tab, N, T, t0, t1, v,
+                        carr_ck + (size_t) v * ck_plane + (size_t) e * ntiles * C + c, (size_t) C, out);
     }
-    spec[(size_t) ec * 2 + v] = out;
+    spec[((size_t) ec * J + j) * 2 + v] = out;
+}
+
+// One chain per (epoch, slot, epoch-level variant): stitch the chunk runs into the epoch-level trajectory P.
+__global__ void k_carr_stitch(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
+                              const double* __restrict__ est_epoch, const CarrSpec* __restrict__ spec,
+                              double* __restrict__ carr_ck, size_t ck_plane, ChunkInfo* __restrict__ cinfo,
+                              CarrSpec* __restrict__ specE, int E, int C, int N, int T, int ntiles, int G, int J) {
+    __shared__ BinadeTab s_tab[4];
+    __shared__ CarrSpec s_cs[4][16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chain = blockIdx.x * 4 + warp;
+    if (chain >= E * C * 2) return;
+    const int V = chain & 1, ec = chain >> 1;
+    const int e = ec / C, c = ec - e * C;
+    const gpsiq_chan_desc d = desc[ec];
+    CarrSpec out;
+    out.margin = -1.0; out.n1 = -1; out.xw1 = 0.0; out.xend = 0.0; out.pad = 0;
+    const bool run = d.prn > 0 && !(V == 1 && d.carr_step >= 0.0) && carr_step_speculable(d.carr_step);
+    if (run) {  // stage this chain's table and chunk results (warp-cooperative, coalesced)
+        for (int i = lane; i < (int) (sizeof(BinadeTab) / 4); i += 32)
+            ((uint32_t*) &s_tab[warp])[i] = ((const uint32_t*) (tabs + (size_t) ec * 2 + 1))[i];
+        for (int i = lane; i < J * 2 * (int) (sizeof(CarrSpec) / 4); i += 32)
+            ((uint32_t*) s_cs[warp])[i] = ((const uint32_t*) (spec + (size_t) ec * J * 2))[i];
+    }
+    __syncwarp();
+    if (lane) return;
+    if (run)
+        stitch_epoch(est_epoch[ec], d.carr_step, s_tab[warp], N, T, G, V, s_cs[warp],
+                     carr_ck + (size_t) (2 + V) * ck_plane + (size_t) e * ntiles * C + c, (size_t) C,
+                     cinfo + ((size_t) ec * 2 + V) * J, out);
+    specE[(size_t) ec * 2 + V] = out;
 }
 
 // Per-epoch inputs of the chain, staged through shared memory: the chain is one
@@ -321,14 +377,14 @@ __device__ __forceinline__ uint32_t chain_stage_word(const gpsiq_chan_desc* desc
     constexpr int WD = sizeof(gpsiq_chan_desc) / 4, WT = sizeof(BinadeTab) / 4;
     if (w < WD) return ((const uint32_t*) (desc + ec))[w];
     if (w < WD + WT) return ((const uint32_t*) (tabs + ec * 2 + 1))[w - WD];
-    return ((const uint32_t*) (spec + ec * 2))[w - WD - WT];
+    return ((const uint32_t*) (spec + ec * 2))[w - WD - WT];  // spec = epoch-level (stitched) results
 }
 
 __global__ void __launch_bounds__(32)
 k_carr_chain(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
-             const CarrSpec* __restrict__ spec, double* __restrict__ carr_ck, double* __restrict__ carr_state,
-             double* __restrict__ carr_trace, CarrInfo* __restrict__ info, int* __restrict__ fallbacks, int E, int C,
-             int N, int T, int ntiles) {
+             const CarrSpec* __restrict__ spec, double* __restrict__ carr_ck, size_t ck_plane,
+             double* __restrict__ carr_state, double* __restrict__ carr_trace, CarrInfo* __restrict__ info,
+             int* __restrict__ fallbacks, int E, int C, int N, int T, int ntiles) {
     static_assert(sizeof(ChainStage) % 8 == 0 && sizeof(ChainStage) / 4 <= 96, "stage layout");
     __shared__ __align__(8) uint32_t stage[2][96];
     const int c = blockIdx.x, lane = threadIdx.x;
@@ -357,8 +413,8 @@ k_carr_chain(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restri
             } else {
                 if (st.d.flags & GPSIQ_FLAG_RESET_CARRIER) x = st.d.carr_phase0;
                 CarrInfo inf;
-                x = chain_epoch(x, st.d.carr_step, st.tab, N, T, st.s0, st.s1, carr_ck + (size_t) e * ntiles * C + c,
-                                (size_t) C, inf, fb);
+                x = chain_epoch(x, st.d.carr_step, st.tab, N, T, st.s0, st.s1,
+                                carr_ck + 4 * ck_plane + (size_t) e * ntiles * C + c, (size_t) C, inf, fb);
                 info[ec] = inf;
                 carr_trace[ec] = x;
             }
@@ -384,6 +440,7 @@ __global__ void __launch_bounds__(LANES_WARPS * 32)
 k_synth_lanes(const gpsiq_chan_desc* __restrict__ desc, const int2* __restrict__ lut,
               const double* __restrict__ code_ck, const int* __restrict__ wrap_ck,
               const double* __restrict__ carr_ck, size_t ck_plane, const CarrInfo* __restrict__ info,
+              const ChunkInfo* __restrict__ cinfo, int G, int J,
               const uint32_t* __restrict__ ca, const int* __restrict__ amp_sum, const int* __restrict__ step_flag,
               int only_flagged, int16_t* __restrict__ iq,
               int C, int N, int T, int ntiles, int tile_groups, int carrier_mode) {
@@ -422,9 +479,8 @@ k_synth_lanes(const gpsiq_chan_desc* __restrict__ desc, const int2* __restrict__
         const int w = wrap_ck[o] + d.ms0 % 20;
         kbit = w / 20;
         icode = w - kbit * 20;
-        const CarrInfo inf = info[(size_t) e * C + lane];
-        if (n0 < inf.n1 || inf.n1 >= N) ph = carr_ck[o];                               // exact plane
-        else ph = __dadd_rn(carr_ck[(size_t) inf.variant * ck_plane + o], inf.delta);  // speculative plane, translated
+        ph = carr_tile_phase(carr_ck + (size_t) e * ntiles * C + lane, ck_plane, (size_t) C, t, T, N, G, J,
+                             info[(size_t) e * C + lane], cinfo + ((size_t) e * C + lane) * 2 * J);
         uph = (uint32_t) ph;
         cstep = d.code_step;
         pstep = d.carr_step;
@@ -597,31 +653,44 @@ int gpsiq_carrier_chain_host(const double* steps, int n_epochs, int N, int T, do
                              double* x_end_out, int* n_fallback) {
     if (!steps || !ck_out || n_epochs < 1 || N < 1 || T < 1) return GPSIQ_ERR_ARG;
     const int ntiles = (N + T - 1) / T;
-    double* plane[2];
-    plane[0] = (double*) malloc(sizeof(double) * ntiles * 2);
-    if (!plane[0]) return GPSIQ_ERR_NOMEM;
-    plane[1] = plane[0] + ntiles;
+    const int G = (ntiles + 7) / 8, J = (ntiles + G - 1) / G;
+    double* planes = (double*) malloc(sizeof(double) * ntiles * 5);
+    if (!planes) return GPSIQ_ERR_NOMEM;
     double x = x0, xe = x0;
     int fb = 0;
     for (int e = 0; e < n_epochs; e++) {
         const double d = steps[e];
-        CarrSpec s0, s1;
-        s1.margin = -1.0; s1.n1 = -1; s1.xw1 = 0; s1.xend = 0;
-        double est = xe + est_err;                       // what the device would guess, plus injected error
-        est -= floor(est);
         BinadeTab tab;
         build_binade_tab<NCO_CARRIER>(d, tab);
-        spec_scan_epoch(est, d, tab, N, T, 0, plane[0], 1, s0);
-        if (d < 0.0) spec_scan_epoch(est, d, tab, N, T, 1, plane[1], 1, s1);
-        CarrInfo info;
-        x = chain_epoch(x, d, tab, N, T, s0, s1, plane[0], 1, info, fb);
-        for (int t = 0; t < ntiles; t++) {
-            const bool exact = (t * T < info.n1) || info.n1 >= N;
-            ck_out[(size_t) e * ntiles + t] = exact ? plane[0][t] : plane[info.variant][t] + info.delta;
+        const double eadv = fma((double) N, d, carr_drift_estimate(d, tab, N));
+        double est = xe + est_err;                       // what the device would guess, plus injected error
+        est -= floor(est);
+        CarrSpec cs[16], sE[2];
+        ChunkInfo ci[2 * 8];
+        for (int j = 0; j < J; j++)
+            for (int v = 0; v < 2; v++) {
+                CarrSpec& o = cs[j * 2 + v];
+                o.margin = -1.0; o.n1 = -1; o.xw1 = 0; o.xend = 0; o.pad = 0;
+                if ((v == 1 && d >= 0.0) || !carr_step_speculable(d)) continue;
+                const int t0 = j * G, t1 = (t0 + G < ntiles) ? t0 + G : ntiles;
+                double xs = est;
+                if (j > 0) { xs = est + eadv * ((double) (t0 * T) / (double) N); xs -= floor(xs); if (!(xs >= 0.0 && xs < 1.0)) xs = 0.0; }
+                spec_scan_range(xs, d, tab, N, T, t0, t1, v, planes + (size_t) v * ntiles, 1, o);
+            }
+        for (int V = 0; V < 2; V++) {
+            sE[V].margin = -1.0; sE[V].n1 = -1; sE[V].xw1 = 0; sE[V].xend = 0; sE[V].pad = 0;
+            if ((V == 1 && d >= 0.0) || !carr_step_speculable(d)) continue;
+            stitch_epoch(est, d, tab, N, T, G, V, cs, planes + (size_t) (2 + V) * ntiles, 1, ci + V * J, sE[V]);
         }
-        xe = est_advance(xe + carr_drift_estimate(d, tab, N), d, N);
+        CarrInfo info;
+        x = chain_epoch(x, d, tab, N, T, sE[0], sE[1], planes + (size_t) 4 * ntiles, 1, info, fb);
+        for (int t = 0; t < ntiles; t++)
+            ck_out[(size_t) e * ntiles + t] = carr_tile_phase(planes, (size_t) ntiles, 1, t, T, N, G, J, info, ci);
+        double t2 = xe + eadv;
+        t2 -= floor(t2);
+        xe = (t2 >= 0.0 && t2 < 1.0) ? t2 : 0.0;
     }
-    free(plane[0]);
+    free(planes);
     if (x_end_out) *x_end_out = x;
     if (n_fallback) *n_fallback = fb;
     return GPSIQ_OK;
@@ -685,10 +754,14 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
     CU(cudaMalloc(&ctx->d_code_ck, ck * sizeof(double)));
     CU(cudaMalloc(&ctx->d_wrap_ck, ck * sizeof(int)));
     ctx->ck_plane = ck;
-    CU(cudaMalloc(&ctx->d_carr_ck, 2 * ck * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_carr_ck, 5 * ck * sizeof(double)));
+    ctx->G = (ctx->ntiles + 7) / 8;
+    ctx->J = (ctx->ntiles + ctx->G - 1) / ctx->G;
+    CU(cudaMalloc(&ctx->d_specE, EC * 2 * sizeof(CarrSpec)));
+    CU(cudaMalloc(&ctx->d_cinfo, EC * 2 * ctx->J * sizeof(ChunkInfo)));
     CU(cudaMalloc(&ctx->d_tab, EC * 2 * sizeof(BinadeTab)));
-    CU(cudaMalloc(&ctx->d_drift, EC * sizeof(double)));
-    CU(cudaMalloc(&ctx->d_spec, EC * 2 * sizeof(CarrSpec)));
+    CU(cudaMalloc(&ctx->d_drift, 3 * EC * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_spec, EC * 2 * 8 * sizeof(CarrSpec)));
     CU(cudaMalloc(&ctx->d_info, EC * sizeof(CarrInfo)));
     CU(cudaMalloc(&ctx->d_fallbacks, sizeof(int)));
     CU(cudaMemset(ctx->d_fallbacks, 0, sizeof(int)));
@@ -749,7 +822,7 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_desc); cudaFree(ctx->d_lut); cudaFree(ctx->d_lutp); cudaFree(ctx->d_chips); cudaFree(ctx->d_flags);
     cudaFree(ctx->d_recs); cudaFree(ctx->d_fixmasks); cudaFree(ctx->d_delta); cudaFree(ctx->d_work); cudaFree(ctx->d_code_ck); cudaFree(ctx->d_wrap_ck);
-    cudaFree(ctx->d_carr_ck); cudaFree(ctx->d_tab); cudaFree(ctx->d_drift); cudaFree(ctx->d_spec); cudaFree(ctx->d_info); cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_est_state); cudaFree(ctx->d_adv); cudaFree(ctx->d_carr_trace); cudaFree(ctx->d_ca);
+    cudaFree(ctx->d_carr_ck); cudaFree(ctx->d_tab); cudaFree(ctx->d_drift); cudaFree(ctx->d_spec); cudaFree(ctx->d_specE); cudaFree(ctx->d_cinfo); cudaFree(ctx->d_info); cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_est_state); cudaFree(ctx->d_adv); cudaFree(ctx->d_carr_trace); cudaFree(ctx->d_ca);
     cudaFree(ctx->d_iq); cudaFree(ctx->d_sums); cudaFree(ctx->d_err);
     for (int i = 0; i < TIMING_RING; i++)
         for (int j = 0; j < 3; j++) cudaEventDestroy(ctx->ev[i][j]);
@@ -767,7 +840,7 @@ static int enqueue_prepare(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int 
                                   ctx->d_flags + ctx->E, C, N, ctx->cfg.carrier_mode, ctx->d_err);
     ctx->launches += 1;
     if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT) {
-        k_slice_advance<<<1, 32, 0, st>>>(desc_dev, ctx->d_drift, ctx->d_adv, n_epochs, C, N);
+        k_slice_advance<<<1, 32, 0, st>>>(ctx->d_drift, ctx->d_drift + (size_t) EC, ctx->d_adv, n_epochs, C);
         ctx->launches += 1;
     }
     ctx->last_epochs = n_epochs;
@@ -784,12 +857,20 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
     k_scan_code<<<(EC + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_code_ck, ctx->d_wrap_ck, EC, C, N, T, ntiles);
     ctx->launches += 1;
     if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && ctx->cfg.reserved[0] == 0) {
-        const int chains = EC * 2;
-        k_carr_speculate<<<(chains + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_drift, ctx->d_est_state,
-                                                         ctx->d_carr_ck, ctx->ck_plane, ctx->d_spec, n_epochs, C, N, T,
-                                                         ntiles);
+        const size_t ECmax = (size_t) ctx->E * C;
+        double* eadv = ctx->d_drift;
+        double* ereset = ctx->d_drift + (size_t) EC;      // k_prepare wrote it at [gridDim.x + ec] with gridDim.x = EC
+        double* est_epoch = ctx->d_drift + 2 * ECmax;
+        k_epoch_estimates<<<1, 32, 0, st>>>(eadv, ereset, ctx->d_est_state, est_epoch, n_epochs, C);
+        const int chains = EC * ctx->J * 2;
+        k_carr_speculate<<<(chains + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, eadv, est_epoch, ctx->d_carr_ck,
+                                                         ctx->ck_plane, ctx->d_spec, n_epochs, C, N, T, ntiles, ctx->G,
+                                                         ctx->J);
+        k_carr_stitch<<<(EC * 2 + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, est_epoch, ctx->d_spec, ctx->d_carr_ck,
+                                                      ctx->ck_plane, ctx->d_cinfo, ctx->d_specE, n_epochs, C, N, T,
+                                                      ntiles, ctx->G, ctx->J);
         k_est_fold<<<1, 32, 0, st>>>(ctx->d_est_state, ctx->d_adv, C);
-        ctx->launches += 2;
+        ctx->launches += 4;
     }
     ctx->phase_done = 2;
     CU(cudaGetLastError());
@@ -801,11 +882,11 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
 static int enqueue_chain(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, cudaStream_t st) {
     const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
     if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && ctx->cfg.reserved[0] == 0) {
-        k_carr_chain<<<C, 32, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_spec, ctx->d_carr_ck, ctx->d_carr_state, ctx->d_carr_trace,
-                                       ctx->d_info, ctx->d_fallbacks, n_epochs, C, N, T, ntiles);
+        k_carr_chain<<<C, 32, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_specE, ctx->d_carr_ck, ctx->ck_plane, ctx->d_carr_state,
+                                       ctx->d_carr_trace, ctx->d_info, ctx->d_fallbacks, n_epochs, C, N, T, ntiles);
     } else {  // INT32 carrier (closed form) or the serial float scan (cfg.reserved[0] = 1, cross-check)
-        k_scan_carrier<<<C, 32, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_carr_ck, ctx->d_carr_state, ctx->d_carr_trace, ctx->d_info,
-                                         n_epochs, C, N, T, ntiles, ctx->cfg.carrier_mode);
+        k_scan_carrier<<<C, 32, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_carr_ck + 4 * ctx->ck_plane, ctx->d_carr_state,
+                                         ctx->d_carr_trace, ctx->d_info, n_epochs, C, N, T, ntiles, ctx->cfg.carrier_mode);
     }
     ctx->launches += 1;
     CU(cudaMemcpyAsync(ctx->d_est_state, ctx->d_carr_state, C * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -840,7 +921,8 @@ static int enqueue_render(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n
             CU(cudaMemsetAsync(ctx->d_delta, 0, (size_t) ne * ntiles * FX_TILE * sizeof(int32_t), st));
             const int warps = ne * 2 * C * tgroups;
             k_tile_prologue<<<(warps + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_code_ck, ctx->d_wrap_ck,
-                                                             ctx->d_carr_ck, ctx->ck_plane, ctx->d_info, ctx->d_flags,
+                                                             ctx->d_carr_ck, ctx->ck_plane, ctx->d_info, ctx->d_cinfo,
+                                                             ctx->G, ctx->J, ctx->d_flags,
                                                              ctx->d_flags + ctx->E, ctx->d_recs, ctx->d_fixmasks,
                                                              ctx->d_work, nwork, ctx->work_cap, e0, ne, C, N, ntiles);
             k_tile_fixup<<<148 * 8, 128, 0, st>>>(desc_dev, ctx->d_lutp, ctx->d_tab, ctx->d_recs, ctx->d_chips, ctx->d_work,
@@ -853,9 +935,9 @@ static int enqueue_render(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n
     }
     // all epochs (lane kernel selected) or only those outside the fixed-point kernel's contract
     k_synth_lanes<<<n_epochs * tile_groups, LANES_WARPS * 32, smem, st>>>(
-        desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, ctx->d_carr_ck, ctx->ck_plane, ctx->d_info, ctx->d_ca,
-        ctx->d_flags, ctx->d_flags + ctx->E, ctx->use_fixed, iq_dev, C, N, T, ntiles, tile_groups,
-        ctx->cfg.carrier_mode);
+        desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, ctx->d_carr_ck, ctx->ck_plane, ctx->d_info, ctx->d_cinfo,
+        ctx->G, ctx->J, ctx->d_ca, ctx->d_flags, ctx->d_flags + ctx->E, ctx->use_fixed, iq_dev, C, N, T, ntiles,
+        tile_groups, ctx->cfg.carrier_mode);
     if (ctx->ev_count < TIMING_RING) {
         CU(cudaEventRecord(ctx->ev[ctx->ev_count][2], st));
         ctx->ev_count++;

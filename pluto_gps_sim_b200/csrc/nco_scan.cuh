@@ -306,17 +306,19 @@ GPSIQ_HD bool carr_step_speculable(double d) {
     return true;
 }
 
-// (1) speculative scan of one epoch from x (an estimate of the epoch's start
-// phase).  ck[t*ck_stride] receives the state at the start of tile t.
-GPSIQ_HD void spec_scan_epoch(double x, double d, const BinadeTab& tab, int N, int T, int variant, double* ck,
-                              size_t ck_stride, CarrSpec& out) {
-    const int ntiles = (N + T - 1) / T;
+// (1) speculative scan of tiles [t0, t1) of an epoch from x, an estimate of the
+// phase at sample t0*T.  ck[t*ck_stride] receives the state at the start of tile
+// t (absolute tile index).  out.n1 is relative to sample t0*T; it equals the
+// range's sample count if the run never wraps.
+GPSIQ_HD void spec_scan_range(double x, double d, const BinadeTab& tab, int N, int T, int t0, int t1, int variant,
+                              double* ck, size_t ck_stride, CarrSpec& out) {
+    const int m_total = ((t1 * T < N) ? t1 * T : N) - t0 * T;
     double margin = 1.0;
     bool seen_wrap = false;
     int n = 0;
-    out.n1 = N;
+    out.n1 = m_total;
     out.xw1 = 0.0;
-    for (int t = 0; t < ntiles; t++) {
+    for (int t = t0; t < t1; t++) {
         ck[(size_t) t * ck_stride] = x;
         int remaining = (T < N - t * T) ? T : N - t * T;
         while (remaining > 0) {
@@ -343,11 +345,146 @@ GPSIQ_HD void spec_scan_epoch(double x, double d, const BinadeTab& tab, int N, i
     out.margin = (seen_wrap && carr_step_speculable(d)) ? margin : -1.0;
 }
 
+GPSIQ_HD void spec_scan_epoch(double x, double d, const BinadeTab& tab, int N, int T, int variant, double* ck,
+                              size_t ck_stride, CarrSpec& out) {
+    spec_scan_range(x, d, tab, N, T, 0, (N + T - 1) / T, variant, ck, ck_stride, out);
+}
+
+// Match an exact post-wrap state x (at range-relative sample n) against the two
+// parity variants of a speculative run; on success returns the variant and the
+// translation.  Shared by the chunk stitcher and the epoch chain.
+GPSIQ_HD bool spec_match(double x, int n, double d, const CarrSpec& s0, const CarrSpec& s1, int& v, double& diff) {
+    if (!(s0.margin > 0.0) || n != s0.n1) return false;
+    const CarrSpec* s = &s0;
+    v = 0;
+    diff = x - s0.xw1;  // exact: both on the 2^-53 grid and close
+    double q = diff * 0x1p52;
+    if (d < 0.0 && q != (double) (long long) q && s1.margin > 0.0 && n == s1.n1) {
+        s = &s1; v = 1;
+        diff = x - s1.xw1;
+        q = diff * 0x1p52;
+    }
+    const double ad = diff < 0.0 ? -diff : diff;
+    return q == (double) (long long) q && ad < s->margin - 0x1p-50;
+}
+
+// ---- two-level speculation: chunks of G tiles ---------------------------------
+// One speculative chain per whole epoch is still ~2000 serial segments.  So the
+// epoch is cut into chunks of G tiles, each speculated independently from its
+// own closed-form start estimate (spec_scan_range, all chunks of all epochs in
+// parallel), and stitch_epoch then builds ONE epoch-level speculative trajectory
+// P out of them with the same translate/verify step, chunk by chunk: it only
+// runs the exact scan over the head of each chunk (up to its first wrap).  P is
+// "the exact recurrence started from the epoch's estimated start phase"; the
+// epoch chain (chain_epoch) treats it exactly like a directly scanned epoch.
+struct ChunkInfo {  // per (epoch, channel, epoch-level variant, chunk)
+    double delta;   // translation of the chunk's speculative run onto P
+    int n1;         // tiles of the chunk starting before this epoch sample read the P plane; others: chunk plane + delta
+    int variant;    // which chunk-level parity plane
+};
+
+// a0: estimated epoch start phase (the chunk-0 runs started from exactly this value).
+// cs: chunk results [J][2]; ckP: this trajectory's P plane for head/fallback tiles.
+GPSIQ_HD void stitch_epoch(double a0, double d, const BinadeTab& tab, int N, int T, int G, int V,
+                           const CarrSpec* cs, double* ckP, size_t ck_stride, ChunkInfo* ci, CarrSpec& outE) {
+    const int ntiles = (N + T - 1) / T;
+    const int J = (ntiles + G - 1) / G;
+    double s = a0, marginE = 1.0;
+    bool seen = false, usable = carr_step_speculable(d);
+    outE.n1 = N;
+    outE.xw1 = 0.0;
+    for (int j = 0; j < J; j++) {
+        const int t0 = j * G, t1 = (t0 + G < ntiles) ? t0 + G : ntiles;
+        const int nstart = t0 * T;
+        const int m_total = ((t1 * T < N) ? t1 * T : N) - nstart;
+        ChunkInfo c;
+        c.delta = 0.0; c.n1 = nstart + m_total; c.variant = 0;
+        if (j == 0) {
+            // the chunk-0 runs started from a0 itself: variant V *is* P (V flips the parity at the first wrap)
+            const bool wrapped0 = cs[0].n1 < m_total;
+            const CarrSpec& sp = cs[(wrapped0 && V == 1) ? 1 : 0];
+            c.n1 = 0;
+            c.variant = (wrapped0 && V == 1) ? 1 : 0;
+            if (wrapped0) {
+                seen = true;
+                outE.n1 = sp.n1;
+                outE.xw1 = sp.xw1;
+                if (!(sp.margin > 0.0)) usable = false; else if (sp.margin < marginE) marginE = sp.margin;
+            }
+            s = sp.xend;
+            ci[0] = c;
+            continue;
+        }
+        // exact-in-P head of chunk j: up to and including its first wrap
+        int n = 0, t = t0, remaining = 0;
+        bool wrapped = false;
+        for (; t < t1 && !wrapped; t++) {
+            ckP[(size_t) t * ck_stride] = s;
+            remaining = (T < N - t * T) ? T : N - t * T;
+            while (remaining > 0 && !wrapped) {
+                int steps;
+                if (seen) steps = carr_advance<true>(s, d, tab, remaining, true, wrapped, marginE);
+                else { double dummy = 1.0; steps = carr_advance<false>(s, d, tab, remaining, true, wrapped, dummy); }
+                remaining -= steps;
+                n += steps;
+            }
+        }
+        if (wrapped) {
+            if (!seen) {  // the epoch's first wrap happens in this head
+                seen = true;
+                if (V == 1) s = (s + 0x1p-53 < 1.0) ? s + 0x1p-53 : s - 0x1p-53;
+                if (!(s >= 0.0 && s < 1.0)) usable = false;
+                outE.n1 = nstart + n;
+                outE.xw1 = s;
+            }
+            int v;
+            double diff;
+            if (spec_match(s, n, d, cs[j * 2], cs[j * 2 + 1], v, diff)) {
+                const CarrSpec& sp = cs[j * 2 + v];
+                c.delta = diff; c.n1 = nstart + n; c.variant = v;
+                const double ad = diff < 0.0 ? -diff : diff;
+                if (sp.margin - ad < marginE) marginE = sp.margin - ad;
+                s = add_rn(sp.xend, diff);
+                ci[j] = c;
+                continue;
+            }
+            // the chunk's speculation does not fit: finish the chunk with the exact scan
+            bool w;
+            while (remaining > 0) remaining -= carr_advance<true>(s, d, tab, remaining, false, w, marginE);
+            for (; t < t1; t++) {
+                ckP[(size_t) t * ck_stride] = s;
+                remaining = (T < N - t * T) ? T : N - t * T;
+                while (remaining > 0) remaining -= carr_advance<true>(s, d, tab, remaining, false, w, marginE);
+            }
+        }
+        ci[j] = c;  // every tile of the chunk reads the P plane
+    }
+    outE.xend = s;
+    outE.margin = (seen && usable) ? marginE : -1.0;
+    outE.pad = 0;
+}
+
+
 struct CarrInfo {   // per (epoch, channel): how the renderer obtains tile-start phases
     double delta;   // translation for tiles starting at or after n1
     int n1;         // tiles starting before n1 read the exact plane 0; N = all exact
     int variant;    // speculative plane (0/1) for the translated tiles
 };
+
+// Exact carrier phase at the start of tile t of one (epoch, channel), composing the
+// three levels: chain result (info) -> stitched trajectory P -> chunk runs.
+// ck points at this (epoch, channel)'s entry of plane 0; `plane` elements per plane,
+// `stride` elements between consecutive tiles.  Planes: 0,1 chunk runs, 2,3 P, 4 exact.
+GPSIQ_HD double carr_tile_phase(const double* ck, size_t plane, size_t stride, int t, int T, int N, int G, int J,
+                                const CarrInfo& inf, const ChunkInfo* ci) {
+    const int n0 = t * T;
+    const size_t o = (size_t) t * stride;
+    if (n0 < inf.n1 || inf.n1 >= N) return ck[4 * plane + o];
+    const int V = inf.variant;
+    const ChunkInfo c = ci[V * J + t / G];
+    const double p = (n0 < c.n1) ? ck[(size_t) (2 + V) * plane + o] : add_rn(ck[(size_t) c.variant * plane + o], c.delta);
+    return add_rn(p, inf.delta);
+}
 
 // (3) exact chaining of one epoch from the exact start x; returns the exact end
 // state.  ck0 is plane 0 of the checkpoint array for this (epoch, channel).
@@ -372,22 +509,14 @@ GPSIQ_HD double chain_epoch(double x, double d, const BinadeTab& tab, int N, int
     info.variant = 0;
     if (!wrapped) return x;  // the whole epoch was the head (low Doppler)
     // try the translation
-    if (s0.margin > 0.0 && n == s0.n1) {
-        const CarrSpec* s = &s0;
-        int v = 0;
-        double diff = x - s0.xw1;  // exact: both on the 2^-53 grid and close
-        double q = diff * 0x1p52;
-        if (d < 0.0 && q != (double) (long long) q && s1.margin > 0.0 && n == s1.n1) {
-            s = &s1; v = 1;
-            diff = x - s1.xw1;
-            q = diff * 0x1p52;
-        }
-        const double ad = diff < 0.0 ? -diff : diff;
-        if (q == (double) (long long) q && ad < s->margin - 0x1p-50) {
+    {
+        int v;
+        double diff;
+        if (spec_match(x, n, d, s0, s1, v, diff)) {
             info.delta = diff;
             info.n1 = n;
             info.variant = v;
-            return add_rn(s->xend, diff);
+            return add_rn(v ? s1.xend : s0.xend, diff);
         }
     }
     // fallback: finish the epoch serially, exact checkpoints for the remaining tiles
