@@ -75,6 +75,8 @@ struct gpsiq_ctx {
     gpsiq_config cfg;
     int C, N, T, ntiles, E;
     cudaStream_t stream;
+    cudaStream_t copy_stream;        // device-to-host copies of finished sub-batches overlap the rendering of the next
+    cudaEvent_t ev_sub[2];
     cudaEvent_t ev[TIMING_RING][3];  // per recorded step: begin, scans done (= synth start), synth done
     int ev_count;                    // steps recorded since gpsiq_timing_begin
     gpsiq_chan_desc* d_desc;
@@ -311,11 +313,15 @@ __global__ void k_carr_speculate(const gpsiq_chan_desc* __restrict__ desc, const
                                  const double* __restrict__ eadv, const double* __restrict__ est_epoch,
                                  double* __restrict__ carr_ck, size_t ck_plane, CarrSpec* __restrict__ spec, int E,
                                  int C, int N, int T, int ntiles, int G, int J) {
-    const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (chain >= E * C * J * 2 || (threadIdx.x & 31)) return;
-    const int v = chain & 1;
-    const int j = (chain >> 1) % J, ec = (chain >> 1) / J;
-    const int e = ec / C, c = ec - e * C;
+    // one chain per THREAD; the lanes of a warp hold the same (slot, chunk, variant) for 32 consecutive
+    // epochs: same satellite, nearly the same Doppler, so their segment walks stay mostly convergent
+    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= E * C * J * 2) return;
+    const int e = chain % E;
+    const int rest = chain / E;
+    const int v = rest & 1;
+    const int j = (rest >> 1) % J, c = (rest >> 1) / J;
+    const int ec = e * C + c;
     const gpsiq_chan_desc d = desc[ec];
     CarrSpec out;
     out.margin = -1.0; out.n1 = -1; out.xw1 = 0.0; out.xend = 0.0; out.pad = 0;
@@ -442,14 +448,14 @@ k_synth_lanes(const gpsiq_chan_desc* __restrict__ desc, const int2* __restrict__
               const double* __restrict__ carr_ck, size_t ck_plane, const CarrInfo* __restrict__ info,
               const ChunkInfo* __restrict__ cinfo, int G, int J,
               const uint32_t* __restrict__ ca, const int* __restrict__ amp_sum, const int* __restrict__ step_flag,
-              int only_flagged, int16_t* __restrict__ iq,
+              int only_flagged, int16_t* __restrict__ iq, int e0,
               int C, int N, int T, int ntiles, int tile_groups, int carrier_mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int2* s_lut = reinterpret_cast<int2*>(smem_raw);                       // [C][512]
     uint32_t* s_ca = reinterpret_cast<uint32_t*>(s_lut + (size_t) C * 512); // [C][33]
 
-    const int e = blockIdx.x / tile_groups;
-    const int tg = blockIdx.x - e * tile_groups;
+    const int e = e0 + blockIdx.x / tile_groups;
+    const int tg = blockIdx.x % tile_groups;
     if (only_flagged && !(amp_sum[e] > 32767 || step_flag[e])) return;  // rendered by k_synth_fixed
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const gpsiq_chan_desc* de = desc + (size_t) e * C;
@@ -741,6 +747,9 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
     ctx->ntiles = (ctx->N + ctx->T - 1) / ctx->T;
     CU(cudaSetDevice(cfg->device));
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ctx->ev_sub[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->ev_sub[1], cudaEventDisableTiming));
     for (int i = 0; i < TIMING_RING; i++)
         for (int j = 0; j < 3; j++) CU(cudaEventCreate(&ctx->ev[i][j]));
     const size_t EC = (size_t) ctx->E * ctx->C;
@@ -827,6 +836,8 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
     for (int i = 0; i < TIMING_RING; i++)
         for (int j = 0; j < 3; j++) cudaEventDestroy(ctx->ev[i][j]);
     cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    cudaEventDestroy(ctx->ev_sub[0]); cudaEventDestroy(ctx->ev_sub[1]);
     free(ctx);
 }
 
@@ -863,7 +874,7 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
         double* est_epoch = ctx->d_drift + 2 * ECmax;
         k_epoch_estimates<<<1, 32, 0, st>>>(eadv, ereset, ctx->d_est_state, est_epoch, n_epochs, C);
         const int chains = EC * ctx->J * 2;
-        k_carr_speculate<<<(chains + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, eadv, est_epoch, ctx->d_carr_ck,
+        k_carr_speculate<<<(chains + 127) / 128, 128, 0, st>>>(desc_dev, ctx->d_tab, eadv, est_epoch, ctx->d_carr_ck,
                                                          ctx->ck_plane, ctx->d_spec, n_epochs, C, N, T, ntiles, ctx->G,
                                                          ctx->J);
         k_carr_stitch<<<(EC * 2 + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, est_epoch, ctx->d_spec, ctx->d_carr_ck,
@@ -904,7 +915,7 @@ static int enqueue_scan(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_e
 
 // Phase 2: the per-sample synthesis from the checkpoints of the last scan.
 static int enqueue_render(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, int16_t* iq_dev,
-                          cudaStream_t st) {
+                          cudaStream_t st, int16_t* iq_host = NULL) {
     const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
     if (ctx->ev_count < TIMING_RING) CU(cudaEventRecord(ctx->ev[ctx->ev_count][1], st));
     const int tile_groups = (ntiles + LANES_WARPS - 1) / LANES_WARPS;
@@ -930,19 +941,33 @@ static int enqueue_render(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n
             k_synth_fixed<<<ne * groups, FX_WORKERS * FX_THREADS, fx_smem_bytes(C), st>>>(
                 desc_dev, ctx->d_lutp, ctx->d_tab, ctx->d_recs, ctx->d_delta, ctx->d_chips, ctx->d_flags,
                 ctx->d_flags + ctx->E, iq_dev, e0, C, N, ntiles, groups);
-            ctx->launches += 3;
+            // epochs of this sub-batch outside the fixed-point kernel's contract
+            k_synth_lanes<<<ne * tile_groups, LANES_WARPS * 32, smem, st>>>(
+                desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, ctx->d_carr_ck, ctx->ck_plane, ctx->d_info,
+                ctx->d_cinfo, ctx->G, ctx->J, ctx->d_ca, ctx->d_flags, ctx->d_flags + ctx->E, 1, iq_dev, e0, C, N, T, ntiles,
+                tile_groups, ctx->cfg.carrier_mode);
+            ctx->launches += 4;
+            if (iq_host) {  // ship the finished sub-batch while the next one renders
+                cudaEvent_t ev = ctx->ev_sub[(e0 / FX_SUB_EPOCHS) & 1];
+                CU(cudaEventRecord(ev, st));
+                CU(cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
+                CU(cudaMemcpyAsync(iq_host + (size_t) e0 * N * 2, iq_dev + (size_t) e0 * N * 2, (size_t) ne * N * 4,
+                                   cudaMemcpyDeviceToHost, ctx->copy_stream));
+            }
         }
+    } else {
+        k_synth_lanes<<<n_epochs * tile_groups, LANES_WARPS * 32, smem, st>>>(
+            desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, ctx->d_carr_ck, ctx->ck_plane, ctx->d_info, ctx->d_cinfo,
+            ctx->G, ctx->J, ctx->d_ca, ctx->d_flags, ctx->d_flags + ctx->E, 0, iq_dev, 0, C, N, T, ntiles, tile_groups,
+            ctx->cfg.carrier_mode);
+        ctx->launches += 1;
+        if (iq_host)
+            CU(cudaMemcpyAsync(iq_host, iq_dev, (size_t) n_epochs * N * 4, cudaMemcpyDeviceToHost, st));
     }
-    // all epochs (lane kernel selected) or only those outside the fixed-point kernel's contract
-    k_synth_lanes<<<n_epochs * tile_groups, LANES_WARPS * 32, smem, st>>>(
-        desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, ctx->d_carr_ck, ctx->ck_plane, ctx->d_info, ctx->d_cinfo,
-        ctx->G, ctx->J, ctx->d_ca, ctx->d_flags, ctx->d_flags + ctx->E, ctx->use_fixed, iq_dev, C, N, T, ntiles,
-        tile_groups, ctx->cfg.carrier_mode);
     if (ctx->ev_count < TIMING_RING) {
         CU(cudaEventRecord(ctx->ev[ctx->ev_count][2], st));
         ctx->ev_count++;
     }
-    ctx->launches += 1;
     CU(cudaGetLastError());
     return GPSIQ_OK;
 }
@@ -971,11 +996,12 @@ int gpsiq_synth(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc, int n_epochs, int16
     CU(cudaSetDevice(ctx->cfg.device));
     CU(cudaMemcpyAsync(ctx->d_desc, desc, (size_t) n_epochs * ctx->C * sizeof(gpsiq_chan_desc), cudaMemcpyHostToDevice,
                        ctx->stream));
-    int rc = enqueue(ctx, ctx->d_desc, n_epochs, ctx->d_iq, ctx->stream);
+    int rc = enqueue_scan(ctx, ctx->d_desc, n_epochs, ctx->stream);
+    if (!rc) rc = enqueue_render(ctx, ctx->d_desc, n_epochs, ctx->d_iq, ctx->stream, iq_out);
     if (rc) return rc;
-    if (iq_out)
-        CU(cudaMemcpyAsync(iq_out, ctx->d_iq, (size_t) n_epochs * ctx->N * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    return check_device_error(ctx);
+    rc = check_device_error(ctx);
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    return rc;
 }
 
 int gpsiq_synth_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, int16_t* iq_dev, void* stream) {
