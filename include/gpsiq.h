@@ -193,6 +193,11 @@ int gpsiq_carrier_fallbacks(gpsiq_ctx *ctx, int64_t *count);
  * returns the number of recorded calls and the summed durations in ms. */
 int gpsiq_timing_begin(gpsiq_ctx *ctx);
 int gpsiq_timing_collect(gpsiq_ctx *ctx, int *n_steps, float *scan_ms, float *synth_ms);
+/* The dominant kernel alone: summed duration of the first k_synth_fixed launch of every
+ * recorded call (CUDA events on the launching stream around that launch only), the
+ * number of such launches and the epochs each one covers (epochs*samples_per_epoch*4
+ * algorithmic bytes per launch). */
+int gpsiq_timing_sample_kernel(gpsiq_ctx *ctx, int *n_launches, float *kernel_ms, int *epochs_per_launch);
 
 const char *gpsiq_strerror(int status);
 const char *gpsiq_last_error(const gpsiq_ctx *ctx);

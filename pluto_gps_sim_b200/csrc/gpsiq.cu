@@ -77,7 +77,11 @@ struct gpsiq_ctx {
     cudaStream_t stream;
     cudaStream_t copy_stream;        // device-to-host copies of finished sub-batches overlap the rendering of the next
     cudaEvent_t ev_sub[2];
-    cudaEvent_t ev[TIMING_RING][3];  // per recorded step: begin, scans done (= synth start), synth done
+    cudaStream_t aux_stream;         // code-NCO scan and tile prologues run beside the carrier chain / the sample kernels
+    cudaEvent_t ev_fork, ev_chain, ev_P[2], ev_F[2];
+    cudaEvent_t ev[TIMING_RING][5];  // per recorded step: begin, scans done (= render start), render done,
+                                     // and around the first k_synth_fixed launch of the step
+    int fixed_epochs;                // epochs covered by that launch
     int ev_count;                    // steps recorded since gpsiq_timing_begin
     gpsiq_chan_desc* d_desc;
     int2* d_lut;          // [E][C][512]
@@ -85,10 +89,11 @@ struct gpsiq_ctx {
     int8_t* d_chips;      // [33][2048] +-1, index = polarity << 10 | chip
     int* d_flags;         // [2][E]: amplitude sum per epoch, step-contract flag per epoch
     int use_fixed;        // k_synth_fixed is eligible for this configuration
-    unsigned char* d_recs; // [FX_SUB_EPOCHS][ntiles] tile records (synth_fixed.cuh)
-    uint32_t* d_fixmasks;  // [FX_SUB_EPOCHS][ntiles][C][4] (+ the work-list counter behind it, cleared together)
-    int32_t* d_delta;      // [FX_SUB_EPOCHS][ntiles][FX_TILE] per-sample corrections
-    uint32_t* d_work;      // work list of (tile, channel, run) triples with a segment boundary
+    // per sub-batch scratch, double buffered: the prologue of sub-batch k+1 overlaps the sample kernels of k
+    unsigned char* d_recs[2]; // [FX_SUB_EPOCHS][ntiles] tile records (synth_fixed.cuh)
+    uint32_t* d_fixmasks[2];  // [FX_SUB_EPOCHS][ntiles][C][4] (+ the work-list counter behind it)
+    int32_t* d_delta[2];      // [FX_SUB_EPOCHS][ntiles][FX_TILE] per-sample corrections
+    uint32_t* d_work[2];      // work list of (tile, channel, run) triples with a segment boundary
     int work_cap;
     double* d_code_ck;    // [E][ntiles][C]
     int* d_wrap_ck;       // [E][ntiles][C]
@@ -750,8 +755,15 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
     CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&ctx->ev_sub[0], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_sub[1], cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) {
+        CU(cudaEventCreateWithFlags(&ctx->ev_P[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_F[i], cudaEventDisableTiming));
+    }
     for (int i = 0; i < TIMING_RING; i++)
-        for (int j = 0; j < 3; j++) CU(cudaEventCreate(&ctx->ev[i][j]));
+        for (int j = 0; j < 5; j++) CU(cudaEventCreate(&ctx->ev[i][j]));
     const size_t EC = (size_t) ctx->E * ctx->C;
     const size_t ck = EC * ctx->ntiles;
     CU(cudaMalloc(&ctx->d_desc, EC * sizeof(gpsiq_chan_desc)));
@@ -813,11 +825,13 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
     if (ctx->use_fixed) {
         CU(cudaFuncSetAttribute(k_synth_fixed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fx_smem_bytes(ctx->C)));
         const size_t tiles = (size_t) FX_SUB_EPOCHS * ctx->ntiles;
-        CU(cudaMalloc(&ctx->d_recs, tiles * fx_rec_bytes(ctx->C)));
-        CU(cudaMalloc(&ctx->d_fixmasks, tiles * fx_fixmask_words(ctx->C) * 4 + 16));
-        CU(cudaMalloc(&ctx->d_delta, tiles * FX_TILE * sizeof(int32_t)));
         ctx->work_cap = (int) (tiles * ctx->C * 40);  // ~3x the typical count; overflow routes the epoch to the lane kernel
-        CU(cudaMalloc(&ctx->d_work, (size_t) ctx->work_cap * 4));
+        for (int i = 0; i < 2; i++) {
+            CU(cudaMalloc(&ctx->d_recs[i], tiles * fx_rec_bytes(ctx->C)));
+            CU(cudaMalloc(&ctx->d_fixmasks[i], tiles * fx_fixmask_words(ctx->C) * 4 + 16));
+            CU(cudaMalloc(&ctx->d_delta[i], tiles * FX_TILE * sizeof(int32_t)));
+            CU(cudaMalloc(&ctx->d_work[i], (size_t) ctx->work_cap * 4));
+        }
     }
     const size_t smem_lanes = (size_t) ctx->C * 512 * sizeof(int2) + (size_t) ctx->C * 33 * 4;
     CU(cudaFuncSetAttribute(k_synth_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_lanes));
@@ -830,13 +844,19 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_desc); cudaFree(ctx->d_lut); cudaFree(ctx->d_lutp); cudaFree(ctx->d_chips); cudaFree(ctx->d_flags);
-    cudaFree(ctx->d_recs); cudaFree(ctx->d_fixmasks); cudaFree(ctx->d_delta); cudaFree(ctx->d_work); cudaFree(ctx->d_code_ck); cudaFree(ctx->d_wrap_ck);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(ctx->d_recs[i]); cudaFree(ctx->d_fixmasks[i]); cudaFree(ctx->d_delta[i]); cudaFree(ctx->d_work[i]);
+    } cudaFree(ctx->d_code_ck); cudaFree(ctx->d_wrap_ck);
     cudaFree(ctx->d_carr_ck); cudaFree(ctx->d_tab); cudaFree(ctx->d_drift); cudaFree(ctx->d_spec); cudaFree(ctx->d_specE); cudaFree(ctx->d_cinfo); cudaFree(ctx->d_info); cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_est_state); cudaFree(ctx->d_adv); cudaFree(ctx->d_carr_trace); cudaFree(ctx->d_ca);
     cudaFree(ctx->d_iq); cudaFree(ctx->d_sums); cudaFree(ctx->d_err);
     for (int i = 0; i < TIMING_RING; i++)
-        for (int j = 0; j < 3; j++) cudaEventDestroy(ctx->ev[i][j]);
+        for (int j = 0; j < 5; j++) cudaEventDestroy(ctx->ev[i][j]);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->aux_stream);
+    cudaStreamDestroy(ctx->aux_stream);
+    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_chain);
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_P[i]); cudaEventDestroy(ctx->ev_F[i]); }
     cudaEventDestroy(ctx->ev_sub[0]); cudaEventDestroy(ctx->ev_sub[1]);
     free(ctx);
 }
@@ -865,7 +885,11 @@ static int enqueue_prepare(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int 
 static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, cudaStream_t st) {
     const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
     const int EC = n_epochs * C;
-    k_scan_code<<<(EC + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_code_ck, ctx->d_wrap_ck, EC, C, N, T, ntiles);
+    // the code-NCO scan does not depend on the carrier chain: it runs beside it on the aux stream
+    CU(cudaEventRecord(ctx->ev_fork, st));
+    CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    k_scan_code<<<(EC + 3) / 4, 128, 0, ctx->aux_stream>>>(desc_dev, ctx->d_tab, ctx->d_code_ck, ctx->d_wrap_ck, EC, C, N, T,
+                                                         ntiles);
     ctx->launches += 1;
     if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && ctx->cfg.reserved[0] == 0) {
         const size_t ECmax = (size_t) ctx->E * C;
@@ -920,42 +944,57 @@ static int enqueue_render(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n
     if (ctx->ev_count < TIMING_RING) CU(cudaEventRecord(ctx->ev[ctx->ev_count][1], st));
     const int tile_groups = (ntiles + LANES_WARPS - 1) / LANES_WARPS;
     const size_t smem = (size_t) C * 512 * sizeof(int2) + (size_t) C * 33 * 4;
+    // everything below needs the chain's result; the aux stream (already holding the code scan) joins here
+    CU(cudaEventRecord(ctx->ev_chain, st));
+    CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_chain, 0));
     if (ctx->use_fixed) {
         const int groups = (ntiles + FX_TILES_PER_CTA - 1) / FX_TILES_PER_CTA;
         const int tgroups = (ntiles + 31) / 32;
-        for (int e0 = 0; e0 < n_epochs; e0 += FX_SUB_EPOCHS) {
+        cudaStream_t ax = ctx->aux_stream;
+        int k = 0;
+        for (int e0 = 0; e0 < n_epochs; e0 += FX_SUB_EPOCHS, k++) {
             const int ne = n_epochs - e0 < FX_SUB_EPOCHS ? n_epochs - e0 : FX_SUB_EPOCHS;
+            const int b = k & 1;
             const size_t mask_bytes = (size_t) ne * ntiles * fx_fixmask_words(C) * 4;
-            int* nwork = (int*) ((unsigned char*) ctx->d_fixmasks + (size_t) FX_SUB_EPOCHS * ntiles * fx_fixmask_words(C) * 4);
-            CU(cudaMemsetAsync(ctx->d_fixmasks, 0, mask_bytes, st));
-            CU(cudaMemsetAsync(nwork, 0, 16, st));
-            CU(cudaMemsetAsync(ctx->d_delta, 0, (size_t) ne * ntiles * FX_TILE * sizeof(int32_t), st));
+            int* nwork = (int*) ((unsigned char*) ctx->d_fixmasks[b] + (size_t) FX_SUB_EPOCHS * ntiles * fx_fixmask_words(C) * 4);
+            // aux stream: prologue of sub-batch k into buffer b (free once the sample kernels of k-2 are done)
+            if (k >= 2) CU(cudaStreamWaitEvent(ax, ctx->ev_F[b], 0));
+            CU(cudaMemsetAsync(ctx->d_fixmasks[b], 0, mask_bytes, ax));
+            CU(cudaMemsetAsync(nwork, 0, 16, ax));
+            CU(cudaMemsetAsync(ctx->d_delta[b], 0, (size_t) ne * ntiles * FX_TILE * sizeof(int32_t), ax));
             const int warps = ne * 2 * C * tgroups;
-            k_tile_prologue<<<(warps + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_code_ck, ctx->d_wrap_ck,
+            k_tile_prologue<<<(warps + 3) / 4, 128, 0, ax>>>(desc_dev, ctx->d_tab, ctx->d_code_ck, ctx->d_wrap_ck,
                                                              ctx->d_carr_ck, ctx->ck_plane, ctx->d_info, ctx->d_cinfo,
-                                                             ctx->G, ctx->J, ctx->d_flags,
-                                                             ctx->d_flags + ctx->E, ctx->d_recs, ctx->d_fixmasks,
-                                                             ctx->d_work, nwork, ctx->work_cap, e0, ne, C, N, ntiles);
-            k_tile_fixup<<<148 * 8, 128, 0, st>>>(desc_dev, ctx->d_lutp, ctx->d_tab, ctx->d_recs, ctx->d_chips, ctx->d_work,
-                                                 nwork, ctx->work_cap, ctx->d_delta, e0, C, N, ntiles);
+                                                             ctx->G, ctx->J, ctx->d_flags, ctx->d_flags + ctx->E,
+                                                             ctx->d_recs[b], ctx->d_fixmasks[b], ctx->d_work[b], nwork,
+                                                             ctx->work_cap, e0, ne, C, N, ntiles);
+            CU(cudaEventRecord(ctx->ev_P[b], ax));
+            // main stream: corrections + sample kernels of sub-batch k
+            CU(cudaStreamWaitEvent(st, ctx->ev_P[b], 0));
+            k_tile_fixup<<<148 * 8, 128, 0, st>>>(desc_dev, ctx->d_lutp, ctx->d_tab, ctx->d_recs[b], ctx->d_chips,
+                                                 ctx->d_work[b], nwork, ctx->work_cap, ctx->d_delta[b], e0, C, N, ntiles);
+            const bool timed = (k == 0 && ctx->ev_count < TIMING_RING);
+            if (timed) { CU(cudaEventRecord(ctx->ev[ctx->ev_count][3], st)); ctx->fixed_epochs = ne; }
             k_synth_fixed<<<ne * groups, FX_WORKERS * FX_THREADS, fx_smem_bytes(C), st>>>(
-                desc_dev, ctx->d_lutp, ctx->d_tab, ctx->d_recs, ctx->d_delta, ctx->d_chips, ctx->d_flags,
+                desc_dev, ctx->d_lutp, ctx->d_tab, ctx->d_recs[b], ctx->d_delta[b], ctx->d_chips, ctx->d_flags,
                 ctx->d_flags + ctx->E, iq_dev, e0, C, N, ntiles, groups);
+            if (timed) CU(cudaEventRecord(ctx->ev[ctx->ev_count][4], st));
             // epochs of this sub-batch outside the fixed-point kernel's contract
             k_synth_lanes<<<ne * tile_groups, LANES_WARPS * 32, smem, st>>>(
                 desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, ctx->d_carr_ck, ctx->ck_plane, ctx->d_info,
                 ctx->d_cinfo, ctx->G, ctx->J, ctx->d_ca, ctx->d_flags, ctx->d_flags + ctx->E, 1, iq_dev, e0, C, N, T, ntiles,
                 tile_groups, ctx->cfg.carrier_mode);
+            CU(cudaEventRecord(ctx->ev_F[b], st));
             ctx->launches += 4;
             if (iq_host) {  // ship the finished sub-batch while the next one renders
-                cudaEvent_t ev = ctx->ev_sub[(e0 / FX_SUB_EPOCHS) & 1];
-                CU(cudaEventRecord(ev, st));
-                CU(cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
+                CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_F[b], 0));
                 CU(cudaMemcpyAsync(iq_host + (size_t) e0 * N * 2, iq_dev + (size_t) e0 * N * 2, (size_t) ne * N * 4,
                                    cudaMemcpyDeviceToHost, ctx->copy_stream));
             }
         }
     } else {
+        CU(cudaEventRecord(ctx->ev_P[0], ctx->aux_stream));   // join: the code scan must be complete
+        CU(cudaStreamWaitEvent(st, ctx->ev_P[0], 0));
         k_synth_lanes<<<n_epochs * tile_groups, LANES_WARPS * 32, smem, st>>>(
             desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, ctx->d_carr_ck, ctx->ck_plane, ctx->d_info, ctx->d_cinfo,
             ctx->G, ctx->J, ctx->d_ca, ctx->d_flags, ctx->d_flags + ctx->E, 0, iq_dev, 0, C, N, T, ntiles, tile_groups,
@@ -1162,6 +1201,25 @@ int gpsiq_timing_collect(gpsiq_ctx* ctx, int* n_steps, float* scan_ms, float* sy
     if (n_steps) *n_steps = ctx->ev_count;
     if (scan_ms) *scan_ms = a;
     if (synth_ms) *synth_ms = b;
+    return GPSIQ_OK;
+}
+
+int gpsiq_timing_sample_kernel(gpsiq_ctx* ctx, int* n_launches, float* kernel_ms, int* epochs_per_launch) {
+    if (!ctx) return GPSIQ_ERR_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    float a = 0.f;
+    int n = 0;
+    if (ctx->use_fixed)
+        for (int i = 0; i < ctx->ev_count; i++) {
+            float t = 0.f;
+            CU(cudaEventSynchronize(ctx->ev[i][4]));
+            CU(cudaEventElapsedTime(&t, ctx->ev[i][3], ctx->ev[i][4]));
+            a += t;
+            n++;
+        }
+    if (n_launches) *n_launches = n;
+    if (kernel_ms) *kernel_ms = a;
+    if (epochs_per_launch) *epochs_per_launch = ctx->fixed_epochs;
     return GPSIQ_OK;
 }
 

@@ -132,6 +132,12 @@ class Synthesizer:
         capi.check(capi.lib.gpsiq_timing_collect(self._ctx, C.byref(n), C.byref(a), C.byref(b)), self._ctx)
         return n.value, a.value, b.value
 
+    def timing_sample_kernel(self):
+        """-> (launches, summed ms, epochs per launch) of the dominant kernel (k_synth_fixed) alone."""
+        n, a, e = C.c_int(0), C.c_float(0), C.c_int(0)
+        capi.check(capi.lib.gpsiq_timing_sample_kernel(self._ctx, C.byref(n), C.byref(a), C.byref(e)), self._ctx)
+        return n.value, a.value, e.value
+
     # -- time-slice phases (multi-GPU) --------------------------------------
     def scan_device(self, desc_dev_ptr, n_epochs, stream_ptr=None):
         capi.check(capi.lib.gpsiq_scan_device(self._ctx, desc_dev_ptr, n_epochs, stream_ptr), self._ctx)
