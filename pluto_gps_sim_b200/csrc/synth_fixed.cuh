@@ -113,7 +113,8 @@ __device__ __forceinline__ void fx_tile_walk(unsigned char* rec, uint32_t* fixma
     uint16_t* segn = (uint16_t*) (rec + fx_rec_segn(C)) + fx_seg_base(c, IS_CARR);
     uint32_t* runseg = (uint32_t*) (rec + fx_rec_runseg(C) + (size_t) task * FX_THREADS);
     fixmask += c * (FX_THREADS / 32);
-    int n = 0, nseg = 0;
+    int n = 0, nseg = 0, rnext = 0;
+    uint32_t word = 0;
     while (n < len) {
         if (nseg >= fx_seg_cap(IS_CARR)) { *overflow = 1; break; }
         const uint32_t pol = (uint32_t) (navbits >> (kbit & 63)) & 1u;
@@ -129,6 +130,10 @@ __device__ __forceinline__ void fx_tile_walk(unsigned char* rec, uint32_t* fixma
             }
         }
         const int k = run_in_binade<MODE>(x, tab, len - 1 - n);  // samples n .. n+k share the segment
+        for (; (rnext << 3) <= n + k; rnext++) {                 // runs whose first sample lies in it
+            word |= (uint32_t) nseg << ((rnext & 3) * 8);
+            if ((rnext & 3) == 3) { runseg[rnext >> 2] = word; word = 0; }
+        }
         nseg++;
         n += k + 1;
         if (n < len) {  // true step into the next segment
@@ -139,17 +144,7 @@ __device__ __forceinline__ void fx_tile_walk(unsigned char* rec, uint32_t* fixma
             }
         }
     }
-    // run -> segment map, as a second, uniform loop (every lane does FX_THREADS iterations; filling it
-    // inside the walk would make the warp wait for its longest segment at every step)
-    {
-        int idx = 0;
-        uint32_t word = 0;
-        for (int r = 0; r < FX_THREADS; r++) {
-            while (idx + 1 < nseg && segn[idx + 1] <= (r << 3)) idx++;
-            word |= (uint32_t) idx << ((r & 3) * 8);
-            if ((r & 3) == 3) { runseg[r >> 2] = word; word = 0; }
-        }
-    }
+    if (rnext & 3) runseg[rnext >> 2] = word;
     ((uint16_t*) (rec + fx_rec_nseg(C)))[task] = (uint16_t) nseg;
 }
 
