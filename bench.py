@@ -211,21 +211,40 @@ def ours_arm(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput (value)
-    for i in range(args.warmup):
-        runner.step(d_first if (i == 0 and rank == 0) else d_desc, E, d_out)
+    # N == 1: the streaming pair submit/fetch with one batch of lookahead (the serial carrier chain of
+    # batch k+1 overlaps the sample kernels of batch k).  N > 1: time slices with the NCCL hand-off.
+    sp = stream.cuda_stream
+
+    def run_batches(count, first_desc=None):
+        """`count` whole batches through the streaming pair, pipeline fill and drain included."""
+        synth.submit_device((first_desc if first_desc is not None else d_desc).data_ptr(), E, sp)
+        for _ in range(count - 1):
+            synth.submit_device(d_desc.data_ptr(), E, sp)    # scan of the next batch ...
+            synth.fetch_device(d_out.data_ptr(), sp)         # ... while this one is rendered
+        synth.fetch_device(d_out.data_ptr(), sp)
+
+    if world == 1:
+        run_batches(max(args.warmup, 1), d_first)
+    else:
+        for i in range(args.warmup):
+            runner.step(d_first if (i == 0 and rank == 0) else d_desc, E, d_out)
     barrier()
     l0 = synth.launch_count
     synth.timing_begin()
     sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for i in range(args.steps):
-        runner.step(d_desc, E, d_out)
+    if world == 1:
+        run_batches(args.steps)                              # exactly `steps` batches scanned AND rendered in here
+    else:
+        for i in range(args.steps):
+            runner.step(d_desc, E, d_out)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if sampler else None
-    runner.finish()
+    if world > 1:
+        runner.finish()
     torch.cuda.synchronize()
     launches = synth.launch_count - l0
     nrec, scan_ms, synth_ms = synth.timing_collect()

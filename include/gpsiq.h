@@ -105,6 +105,16 @@ int gpsiq_synth(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc, int n_epochs, int16
 int gpsiq_synth_device(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc_dev, int n_epochs, int16_t *iq_dev,
                        void *cuda_stream);
 
+/* Streaming pair (the submit/fetch seam of SURVEY.md §8b): gpsiq_submit_device copies the
+ * descriptors (DEVICE pointer; ordered after the work already enqueued on after_stream) and
+ * runs every scan phase for the batch ahead of time on the context's own stream;
+ * gpsiq_fetch_device renders the oldest submitted batch into iq_dev on cuda_stream.  Up to two
+ * batches may be in flight, so the serial carrier chain of batch k+1 overlaps the sample
+ * kernels of batch k.  Results are identical to gpsiq_synth_device called batch by batch.
+ * Do not interleave with the other synthesis calls while batches are in flight. */
+int gpsiq_submit_device(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc_dev, int n_epochs, void *after_stream);
+int gpsiq_fetch_device(gpsiq_ctx *ctx, int16_t *iq_dev, void *cuda_stream);
+
 /* Carrier phase per slot after the last synthesized epoch (max_chan values;
  * INT32 mode: the uint32 phase as a double) — chan[i].carr_phase after
  * plutogpssim.c:2741-2748.  Used for time-slice hand-off between GPUs. */

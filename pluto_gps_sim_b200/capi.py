@@ -74,6 +74,8 @@ SYMBOLS = {
     "gpsiq_timing_begin": (_i, [_vp]),
     "gpsiq_timing_collect": (_i, [_vp, C.POINTER(_i), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "gpsiq_timing_sample_kernel": (_i, [_vp, C.POINTER(_i), C.POINTER(C.c_float), C.POINTER(_i)]),
+    "gpsiq_submit_device": (_i, [_vp, _vp, _i, _vp]),
+    "gpsiq_fetch_device": (_i, [_vp, _vp, _vp]),
     "gpsiq_scan_device": (_i, [_vp, _vp, _i, _vp]),
     "gpsiq_prepare_device": (_i, [_vp, _vp, _i, _vp, _vp]),
     "gpsiq_speculate_device": (_i, [_vp, _vp, _i, _vp]),

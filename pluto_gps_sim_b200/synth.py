@@ -86,6 +86,14 @@ class Synthesizer:
         """All-device, asynchronous on `stream_ptr` (a cudaStream_t as int)."""
         capi.check(capi.lib.gpsiq_synth_device(self._ctx, desc_dev_ptr, n_epochs, iq_dev_ptr, stream_ptr), self._ctx)
 
+    def submit_device(self, desc_dev_ptr, n_epochs, after_stream_ptr=None):
+        """Scan a batch ahead of time (asynchronous, on the context's own stream)."""
+        capi.check(capi.lib.gpsiq_submit_device(self._ctx, desc_dev_ptr, n_epochs, after_stream_ptr), self._ctx)
+
+    def fetch_device(self, iq_dev_ptr, stream_ptr=None):
+        """Render the oldest submitted batch on `stream_ptr` (asynchronous)."""
+        capi.check(capi.lib.gpsiq_fetch_device(self._ctx, iq_dev_ptr, stream_ptr), self._ctx)
+
     def device_iq_ptr(self):
         return capi.lib.gpsiq_device_iq(self._ctx)
 

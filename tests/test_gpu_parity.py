@@ -205,6 +205,33 @@ def test_out_of_contract_descriptor_is_rejected():
         assert ei.value.status == capi.ERR_CAPACITY
 
 
+def test_streaming_submit_fetch_matches_reference():
+    """submit/fetch with one batch of lookahead over the 310-epoch user-motion golden (uneven batches)."""
+    import torch
+
+    meta = ol.load_golden_meta("circle12")
+    desc = ol.load_golden_desc("circle12")
+    sizes = [40, 64, 64, 1, 64, 64, 13]
+    assert sum(sizes) == 310
+    st = torch.cuda.Stream()
+    sums = []
+    with torch.cuda.stream(st), Synthesizer(max_chan=12, max_epochs=64) as s:
+        bufs = [torch.empty(64 * 300000 * 2, dtype=torch.int16, device="cuda") for _ in range(2)]
+        descs, e = [], 0
+        for n in sizes:
+            descs.append(torch.from_numpy(desc[e:e + n].copy().view(np.uint8).reshape(-1)).cuda())
+            e += n
+        torch.cuda.synchronize()
+        s.submit_device(descs[0].data_ptr(), sizes[0], st.cuda_stream)
+        for k in range(len(sizes)):
+            if k + 1 < len(sizes):
+                s.submit_device(descs[k + 1].data_ptr(), sizes[k + 1], st.cuda_stream)
+            s.fetch_device(bufs[k & 1].data_ptr(), st.cuda_stream)
+            st.synchronize()
+            sums += [int(x) for x in s.checksum_device(bufs[k & 1].data_ptr(), sizes[k])]
+    assert sums == meta["epoch_checksums"]
+
+
 def test_device_path_with_torch_buffers():
     import torch
 
