@@ -113,6 +113,12 @@ int gpsiq_synth_device(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc_dev, int n_ep
  * kernels of batch k.  Results are identical to gpsiq_synth_device called batch by batch.
  * Do not interleave with the other synthesis calls while batches are in flight. */
 int gpsiq_submit_device(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc_dev, int n_epochs, void *after_stream);
+/* Host-buffer versions: gpsiq_submit copies the descriptors (the caller may reuse desc at once) and
+ * returns immediately; gpsiq_fetch blocks until the oldest submitted batch is complete in iq_out
+ * (pinned memory from gpsiq_host_alloc keeps the copies asynchronous).  The producer loop of the
+ * reference's main (plutogpssim.c:2655-2806) maps onto: submit(k+1); fetch(k); push(k). */
+int gpsiq_submit(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc, int n_epochs);
+int gpsiq_fetch(gpsiq_ctx *ctx, int16_t *iq_out);
 int gpsiq_fetch_device(gpsiq_ctx *ctx, int16_t *iq_dev, void *cuda_stream);
 
 /* Carrier phase per slot after the last synthesized epoch (max_chan values;
@@ -208,6 +214,11 @@ int gpsiq_timing_collect(gpsiq_ctx *ctx, int *n_steps, float *scan_ms, float *sy
  * number of such launches and the epochs each one covers (epochs*samples_per_epoch*4
  * algorithmic bytes per launch). */
 int gpsiq_timing_sample_kernel(gpsiq_ctx *ctx, int *n_launches, float *kernel_ms, int *epochs_per_launch);
+/* The same kernel ALONE: re-launches the last k_synth_fixed (same inputs, same output range) `reps`
+ * times back to back on an idle device and returns the mean duration.  In the pipelined calls the
+ * kernel shares the SMs with the scan kernels of the next batch, so its in-pipeline duration says
+ * little about the kernel itself. */
+int gpsiq_timing_sample_kernel_isolated(gpsiq_ctx *ctx, int reps, float *kernel_ms, int *epochs_per_launch);
 
 const char *gpsiq_strerror(int status);
 const char *gpsiq_last_error(const gpsiq_ctx *ctx);

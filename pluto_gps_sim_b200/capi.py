@@ -74,8 +74,11 @@ SYMBOLS = {
     "gpsiq_timing_begin": (_i, [_vp]),
     "gpsiq_timing_collect": (_i, [_vp, C.POINTER(_i), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "gpsiq_timing_sample_kernel": (_i, [_vp, C.POINTER(_i), C.POINTER(C.c_float), C.POINTER(_i)]),
+    "gpsiq_submit": (_i, [_vp, _vp, _i]),
+    "gpsiq_fetch": (_i, [_vp, _vp]),
     "gpsiq_submit_device": (_i, [_vp, _vp, _i, _vp]),
     "gpsiq_fetch_device": (_i, [_vp, _vp, _vp]),
+    "gpsiq_timing_sample_kernel_isolated": (_i, [_vp, _i, C.POINTER(C.c_float), C.POINTER(_i)]),
     "gpsiq_scan_device": (_i, [_vp, _vp, _i, _vp]),
     "gpsiq_prepare_device": (_i, [_vp, _vp, _i, _vp, _vp]),
     "gpsiq_speculate_device": (_i, [_vp, _vp, _i, _vp]),

@@ -99,6 +99,7 @@ struct gpsiq_ctx {
     cudaEvent_t ev[TIMING_RING][5];  // per recorded step: begin, scans done (= render start), render done,
                                      // and around the first k_synth_fixed launch of the step
     int fixed_epochs;                // epochs covered by that launch
+    struct { const gpsiq_chan_desc* desc; int16_t* iq; int e0, ne, b, set; } last_fx;  // last k_synth_fixed launch
     int ev_count;                    // steps recorded since gpsiq_timing_begin
     gpsiq_chan_desc* d_desc;
     int2* d_lut;          // [E][C][512]
@@ -133,6 +134,8 @@ struct gpsiq_ctx {
     double* d_carr_trace; // [E][C]
     uint32_t* d_ca;       // [33][CA_WORDS]
     int16_t* d_iq;        // [E][N][2]
+    int16_t* d_iq2;       // second output buffer for the host streaming pair (allocated on first use)
+    gpsiq_chan_desc* h_stage[2];  // pinned staging of submitted host descriptors
     unsigned long long* d_sums;
     int* d_err;
     int last_epochs;
@@ -893,7 +896,9 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
         cudaFree(ctx->d_recs[i]); cudaFree(ctx->d_fixmasks[i]); cudaFree(ctx->d_delta[i]); cudaFree(ctx->d_work[i]);
     }
     cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_est_state); cudaFree(ctx->d_ca);
-    cudaFree(ctx->d_iq); cudaFree(ctx->d_sums); cudaFree(ctx->d_err);
+    cudaFree(ctx->d_iq); cudaFree(ctx->d_iq2); cudaFree(ctx->d_sums); cudaFree(ctx->d_err);
+    if (ctx->h_stage[0]) cudaFreeHost(ctx->h_stage[0]);
+    if (ctx->h_stage[1]) cudaFreeHost(ctx->h_stage[1]);
     cudaStreamDestroy(ctx->scan_stream); cudaStreamDestroy(ctx->aux2_stream); cudaEventDestroy(ctx->ev_fork2);
     for (int i = 0; i < TIMING_RING; i++)
         for (int j = 0; j < 5; j++) cudaEventDestroy(ctx->ev[i][j]);
@@ -1028,6 +1033,8 @@ static int enqueue_render(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n
                 desc_dev, ctx->d_lutp, ctx->d_tab, ctx->d_recs[b], ctx->d_delta[b], ctx->d_chips, ctx->d_flags,
                 ctx->d_flags + ctx->E, iq_dev, e0, C, N, ntiles, groups);
             if (timed) CU(cudaEventRecord(ctx->ev[ctx->ev_count][4], st));
+            ctx->last_fx.desc = desc_dev; ctx->last_fx.iq = iq_dev; ctx->last_fx.e0 = e0; ctx->last_fx.ne = ne;
+            ctx->last_fx.b = b; ctx->last_fx.set = ctx->set_cur;
             // epochs of this sub-batch outside the fixed-point kernel's contract
             k_synth_lanes<<<ne * tile_groups, LANES_WARPS * 32, smem, st>>>(
                 desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, ctx->d_carr_ck, ctx->ck_plane, ctx->d_info,
@@ -1146,6 +1153,43 @@ int gpsiq_fetch_device(gpsiq_ctx* ctx, int16_t* iq_dev, void* stream) {
     ctx->set_rd ^= 1;
     ctx->set_pending--;
     return GPSIQ_OK;
+}
+
+// Host-buffer streaming pair: same pipeline, descriptors from / samples to HOST memory.
+int gpsiq_submit(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc, int n_epochs) {
+    if (!ctx || !desc || n_epochs < 1) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_submit: bad argument", cudaSuccess);
+    if (n_epochs > ctx->E) return fail(ctx, GPSIQ_ERR_CAPACITY, "gpsiq_submit: n_epochs > max_epochs", cudaSuccess);
+    if (ctx->set_pending >= 2) return fail(ctx, GPSIQ_ERR_CAPACITY, "gpsiq_submit: two batches already in flight", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    const size_t bytes = (size_t) n_epochs * ctx->C * sizeof(gpsiq_chan_desc);
+    const int w = ctx->set_wr;
+    if (!ctx->h_stage[w]) CU(cudaHostAlloc(&ctx->h_stage[w], (size_t) ctx->E * ctx->C * sizeof(gpsiq_chan_desc), cudaHostAllocDefault));
+    CU(cudaEventSynchronize(ctx->sets[w].scan_done));  // the staging buffer's previous upload has been consumed
+    memcpy(ctx->h_stage[w], desc, bytes);
+    CU(cudaMemcpyAsync(ctx->d_desc, ctx->h_stage[w], bytes, cudaMemcpyHostToDevice, ctx->scan_stream));
+    return gpsiq_submit_device(ctx, ctx->d_desc, n_epochs, (void*) ctx->scan_stream);
+}
+
+int gpsiq_fetch(gpsiq_ctx* ctx, int16_t* iq_out) {
+    if (!ctx || !iq_out) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_fetch: bad argument", cudaSuccess);
+    if (ctx->set_pending < 1) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_fetch: nothing submitted", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (!ctx->d_iq2) CU(cudaMalloc(&ctx->d_iq2, (size_t) ctx->E * ctx->N * 4));
+    ScanSet& set = ctx->sets[ctx->set_rd];
+    int16_t* dev = ctx->set_rd ? ctx->d_iq2 : ctx->d_iq;
+    cudaStream_t st = ctx->stream;
+    CU(cudaStreamWaitEvent(st, set.scan_done, 0));
+    use_set(ctx, ctx->set_rd);
+    ctx->last_epochs = set.n_epochs;
+    ctx->phase_done = 3;
+    int rc = enqueue_render(ctx, set.d_descbuf, set.n_epochs, dev, st, iq_out);
+    if (rc) return rc;
+    CU(cudaEventRecord(set.render_done, st));
+    ctx->set_rd ^= 1;
+    ctx->set_pending--;
+    rc = check_device_error(ctx);
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    return rc;
 }
 
 int gpsiq_scan_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, void* stream) {
@@ -1299,6 +1343,33 @@ int gpsiq_timing_collect(gpsiq_ctx* ctx, int* n_steps, float* scan_ms, float* sy
     if (n_steps) *n_steps = ctx->ev_count;
     if (scan_ms) *scan_ms = a;
     if (synth_ms) *synth_ms = b;
+    return GPSIQ_OK;
+}
+
+// Re-launch the last k_synth_fixed (same records, same output range -- it rewrites identical samples)
+// `reps` times back to back on an otherwise idle device and return the mean duration: the kernel ALONE.
+int gpsiq_timing_sample_kernel_isolated(gpsiq_ctx* ctx, int reps, float* kernel_ms, int* epochs_per_launch) {
+    if (!ctx || reps < 1 || !kernel_ms) return GPSIQ_ERR_ARG;
+    if (!ctx->use_fixed || !ctx->last_fx.desc) return fail(ctx, GPSIQ_ERR_ARG, "no k_synth_fixed launch to repeat", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaDeviceSynchronize());
+    use_set(ctx, ctx->last_fx.set);
+    const int C = ctx->C, N = ctx->N, ntiles = ctx->ntiles, b = ctx->last_fx.b;
+    const int groups = (ntiles + FX_TILES_PER_CTA - 1) / FX_TILES_PER_CTA;
+    cudaEvent_t e0 = ctx->ev[TIMING_RING - 1][3], e1 = ctx->ev[TIMING_RING - 1][4];
+    for (int i = 0; i < reps + 1; i++) {  // first launch is a warm-up
+        if (i == 1) CU(cudaEventRecord(e0, ctx->stream));
+        k_synth_fixed<<<ctx->last_fx.ne * groups, FX_WORKERS * FX_THREADS, fx_smem_bytes(C), ctx->stream>>>(
+            ctx->last_fx.desc, ctx->d_lutp, ctx->d_tab, ctx->d_recs[b], ctx->d_delta[b], ctx->d_chips, ctx->d_flags,
+            ctx->d_flags + ctx->E, ctx->last_fx.iq, ctx->last_fx.e0, C, N, ntiles, groups);
+    }
+    CU(cudaEventRecord(e1, ctx->stream));
+    CU(cudaEventSynchronize(e1));
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, e0, e1));
+    ctx->launches += reps + 1;
+    *kernel_ms = t / reps;
+    if (epochs_per_launch) *epochs_per_launch = ctx->last_fx.ne;
     return GPSIQ_OK;
 }
 

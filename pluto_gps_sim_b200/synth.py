@@ -86,6 +86,25 @@ class Synthesizer:
         """All-device, asynchronous on `stream_ptr` (a cudaStream_t as int)."""
         capi.check(capi.lib.gpsiq_synth_device(self._ctx, desc_dev_ptr, n_epochs, iq_dev_ptr, stream_ptr), self._ctx)
 
+    def submit(self, desc):
+        """Host descriptors ([n_epochs][max_chan] array or raw pointer via submit_ptr); returns immediately."""
+        d = self._desc_array(desc)
+        capi.check(capi.lib.gpsiq_submit(self._ctx, d.ctypes.data, d.shape[0]), self._ctx)
+        return d.shape[0]
+
+    def submit_ptr(self, desc_ptr, n_epochs):
+        capi.check(capi.lib.gpsiq_submit(self._ctx, desc_ptr, n_epochs), self._ctx)
+
+    def fetch_ptr(self, iq_ptr):
+        """Blocks until the oldest submitted batch is complete in host memory at iq_ptr."""
+        capi.check(capi.lib.gpsiq_fetch(self._ctx, iq_ptr), self._ctx)
+
+    def fetch(self, n_epochs, out=None):
+        if out is None:
+            out = np.empty((n_epochs, self.samples_per_epoch, 2), np.int16)
+        capi.check(capi.lib.gpsiq_fetch(self._ctx, out.ctypes.data), self._ctx)
+        return out
+
     def submit_device(self, desc_dev_ptr, n_epochs, after_stream_ptr=None):
         """Scan a batch ahead of time (asynchronous, on the context's own stream)."""
         capi.check(capi.lib.gpsiq_submit_device(self._ctx, desc_dev_ptr, n_epochs, after_stream_ptr), self._ctx)
@@ -145,6 +164,12 @@ class Synthesizer:
         n, a, e = C.c_int(0), C.c_float(0), C.c_int(0)
         capi.check(capi.lib.gpsiq_timing_sample_kernel(self._ctx, C.byref(n), C.byref(a), C.byref(e)), self._ctx)
         return n.value, a.value, e.value
+
+    def timing_sample_kernel_isolated(self, reps=20):
+        """-> (mean ms, epochs per launch) of k_synth_fixed re-launched alone on an idle device."""
+        a, e = C.c_float(0), C.c_int(0)
+        capi.check(capi.lib.gpsiq_timing_sample_kernel_isolated(self._ctx, reps, C.byref(a), C.byref(e)), self._ctx)
+        return a.value, e.value
 
     # -- time-slice phases (multi-GPU) --------------------------------------
     def scan_device(self, desc_dev_ptr, n_epochs, stream_ptr=None):

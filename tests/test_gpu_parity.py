@@ -232,6 +232,22 @@ def test_streaming_submit_fetch_matches_reference():
     assert sums == meta["epoch_checksums"]
 
 
+def test_host_streaming_submit_fetch_matches_reference():
+    """gpsiq_submit / gpsiq_fetch with host buffers, one batch of lookahead, static golden in 3+3+4 epochs."""
+    meta = ol.load_golden_meta("static12")
+    desc = ol.load_golden_desc("static12")
+    parts = [desc[0:3], desc[3:6], desc[6:10]]
+    outs = []
+    with Synthesizer(max_chan=12, max_epochs=4) as s:
+        s.submit(parts[0])
+        for k in range(3):
+            if k + 1 < 3:
+                s.submit(parts[k + 1])
+            outs.append(s.fetch(len(parts[k])))
+    iq = np.concatenate(outs)
+    assert ol.sha256(iq) == meta["iq_sha256"]
+
+
 def test_device_path_with_torch_buffers():
     import torch
 
