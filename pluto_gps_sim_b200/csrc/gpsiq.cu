@@ -210,11 +210,13 @@ __global__ void k_prepare(const gpsiq_chan_desc* __restrict__ desc, int2* __rest
 __global__ void k_scan_code(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
                             double* __restrict__ code_ck, int* __restrict__ wrap_ck, int EC, int C, int N, int T,
                             int ntiles) {
-    // one chain per warp, lane 0 only: the scan is branchy and data dependent,
-    // chains sharing a warp would serialise each other's paths
-    const int ec = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (ec >= EC || (threadIdx.x & 31)) return;
-    const int e = ec / C, c = ec - e * C;
+    // one chain per thread; the lanes of a warp hold the same slot for 32 consecutive epochs (same
+    // satellite, nearly the same code rate), so their segment walks stay mostly convergent
+    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= EC) return;
+    const int E = EC / C;
+    const int e = chain % E, c = chain / E;
+    const int ec = e * C + c;
     const gpsiq_chan_desc d = desc[ec];
     if (d.prn <= 0) return;
     double x = d.code_phase0;
@@ -942,7 +944,7 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
     // the code-NCO scan does not depend on the carrier chain: it runs beside it on the aux stream
     CU(cudaEventRecord(fork, st));
     CU(cudaStreamWaitEvent(aux, fork, 0));
-    k_scan_code<<<(EC + 3) / 4, 128, 0, aux>>>(desc_dev, ctx->d_tab, ctx->d_code_ck, ctx->d_wrap_ck, EC, C, N, T, ntiles);
+    k_scan_code<<<(EC + 63) / 64, 64, 0, aux>>>(desc_dev, ctx->d_tab, ctx->d_code_ck, ctx->d_wrap_ck, EC, C, N, T, ntiles);
     if (ahead) CU(cudaEventRecord(ctx->ev_code2, aux));
     ctx->launches += 1;
     if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && ctx->cfg.reserved[0] == 0) {
