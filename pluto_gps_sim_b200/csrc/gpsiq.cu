@@ -80,7 +80,9 @@ struct ScanSet {
     BinadeTab* d_tab; double* d_drift; CarrSpec* d_spec; CarrSpec* d_specE; ChunkInfo* d_cinfo; CarrInfo* d_info;
     double* d_adv; double* d_carr_trace;
     cudaEvent_t scan_done, render_done;
+    const gpsiq_chan_desc* desc;  // the batch's descriptors (device)
     int n_epochs;
+    int phase;                    // 0 free, 1 prepared, 2 speculated, 3 chained (waiting to be rendered)
 };
 
 struct gpsiq_ctx {
@@ -139,7 +141,6 @@ struct gpsiq_ctx {
     unsigned long long* d_sums;
     int* d_err;
     int last_epochs;
-    int phase_done;       // 1 prepare, 2 speculate, 3 chain -- of the batch in flight
     int64_t launches;
     char err[256];
 };
@@ -915,9 +916,27 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
 }
 
 // Phase 1a: amplitude LUTs, binade tables, contract flags, and the batch's closed-form phase advance.
-static int enqueue_prepare(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, cudaStream_t st) {
+// Every batch goes through a ring of two scan sets: begin_batch claims the free one (waiting, on
+// the given stream, until its previous batch has been rendered), the scan phases fill it, the
+// render phase consumes the oldest chained one.  A plain gpsiq_synth_device uses the ring with one
+// batch in flight; submit/fetch and the time-slice runner keep two.
+static int begin_batch(gpsiq_ctx* ctx, cudaStream_t st) {
+    if (ctx->set_pending >= 2 || ctx->sets[ctx->set_wr].phase != 0)
+        return fail(ctx, GPSIQ_ERR_CAPACITY, "two batches already in flight (render one first)", cudaSuccess);
+    CU(cudaStreamWaitEvent(st, ctx->sets[ctx->set_wr].render_done, 0));
+    use_set(ctx, ctx->set_wr);
+    return GPSIQ_OK;
+}
+
+static int enqueue_prepare(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, cudaStream_t st,
+                           bool begun = false) {
     const int C = ctx->C, N = ctx->N;
     const int EC = n_epochs * C;
+    if (!begun) { int rc0 = begin_batch(ctx, st); if (rc0) return rc0; }
+    ScanSet& set = ctx->sets[ctx->set_wr];
+    set.desc = desc_dev;
+    set.n_epochs = n_epochs;
+    set.phase = 1;
     if (ctx->ev_count < TIMING_RING && st != ctx->scan_stream) CU(cudaEventRecord(ctx->ev[ctx->ev_count][0], st));
     CU(cudaMemsetAsync(ctx->d_flags, 0, 2 * (size_t) ctx->E * sizeof(int), st));
     k_prepare<<<EC, 128, 0, st>>>(desc_dev, ctx->d_lut, ctx->d_lutp, ctx->d_tab, ctx->d_drift, ctx->d_flags,
@@ -928,24 +947,23 @@ static int enqueue_prepare(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int 
         ctx->launches += 1;
     }
     ctx->last_epochs = n_epochs;
-    ctx->phase_done = 1;
     CU(cudaGetLastError());
     return GPSIQ_OK;
 }
 
 // Phase 1b: everything that does NOT need the exact carrier phase: the code-NCO scan and the
 // speculative carrier scans from the context's start-phase estimate (advanced afterwards).
-static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, cudaStream_t st,
-                             bool ahead = false) {
-    cudaStream_t aux = ahead ? ctx->aux2_stream : ctx->aux_stream;
-    cudaEvent_t fork = ahead ? ctx->ev_fork2 : ctx->ev_fork;
+static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, cudaStream_t st) {
+    cudaStream_t aux = ctx->aux2_stream;  // (aux_stream may be busy with the tile prologues of the batch being rendered)
+    cudaEvent_t fork = ctx->ev_fork;
+    use_set(ctx, ctx->set_wr);
     const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
     const int EC = n_epochs * C;
     // the code-NCO scan does not depend on the carrier chain: it runs beside it on the aux stream
     CU(cudaEventRecord(fork, st));
     CU(cudaStreamWaitEvent(aux, fork, 0));
     k_scan_code<<<(EC + 63) / 64, 64, 0, aux>>>(desc_dev, ctx->d_tab, ctx->d_code_ck, ctx->d_wrap_ck, EC, C, N, T, ntiles);
-    if (ahead) CU(cudaEventRecord(ctx->ev_code2, aux));
+    CU(cudaEventRecord(ctx->ev_code2, aux));
     ctx->launches += 1;
     if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && ctx->cfg.reserved[0] == 0) {
         const size_t ECmax = (size_t) ctx->E * C;
@@ -963,7 +981,7 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
         k_est_fold<<<1, 32, 0, st>>>(ctx->d_est_state, ctx->d_adv, C);
         ctx->launches += 4;
     }
-    ctx->phase_done = 2;
+    ctx->sets[ctx->set_wr].phase = 2;
     CU(cudaGetLastError());
     return GPSIQ_OK;
 }
@@ -972,6 +990,7 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
 // state) and re-anchor the estimate on it.
 static int enqueue_chain(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, cudaStream_t st) {
     const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
+    use_set(ctx, ctx->set_wr);
     if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && ctx->cfg.reserved[0] == 0) {
         k_carr_chain<<<C, 32, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_specE, ctx->d_carr_ck, ctx->ck_plane, ctx->d_carr_state,
                                        ctx->d_carr_trace, ctx->d_info, ctx->d_fallbacks, n_epochs, C, N, T, ntiles);
@@ -981,7 +1000,12 @@ static int enqueue_chain(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_
     }
     ctx->launches += 1;
     CU(cudaMemcpyAsync(ctx->d_est_state, ctx->d_carr_state, C * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    ctx->phase_done = 3;
+    CU(cudaStreamWaitEvent(st, ctx->ev_code2, 0));  // scan_done covers the code scan on the side stream too
+    ScanSet& set = ctx->sets[ctx->set_wr];
+    CU(cudaEventRecord(set.scan_done, st));
+    set.phase = 3;
+    ctx->set_wr ^= 1;
+    ctx->set_pending++;
     CU(cudaGetLastError());
     return GPSIQ_OK;
 }
@@ -994,8 +1018,14 @@ static int enqueue_scan(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_e
 }
 
 // Phase 2: the per-sample synthesis from the checkpoints of the last scan.
-static int enqueue_render(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, int16_t* iq_dev,
-                          cudaStream_t st, int16_t* iq_host = NULL) {
+static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int16_t* iq_host = NULL) {
+    if (ctx->set_pending < 1 || ctx->sets[ctx->set_rd].phase != 3)
+        return fail(ctx, GPSIQ_ERR_ARG, "nothing to render (scan phases of a batch must complete first)", cudaSuccess);
+    ScanSet& set = ctx->sets[ctx->set_rd];
+    CU(cudaStreamWaitEvent(st, set.scan_done, 0));
+    use_set(ctx, ctx->set_rd);
+    const gpsiq_chan_desc* desc_dev = set.desc;
+    const int n_epochs = set.n_epochs;
     const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
     if (ctx->ev_count < TIMING_RING) CU(cudaEventRecord(ctx->ev[ctx->ev_count][1], st));
     const int tile_groups = (ntiles + LANES_WARPS - 1) / LANES_WARPS;
@@ -1065,14 +1095,19 @@ static int enqueue_render(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n
         CU(cudaEventRecord(ctx->ev[ctx->ev_count][2], st));
         ctx->ev_count++;
     }
+    CU(cudaEventRecord(set.render_done, st));
+    set.phase = 0;
+    ctx->set_rd ^= 1;
+    ctx->set_pending--;
     CU(cudaGetLastError());
     return GPSIQ_OK;
 }
 
 static int enqueue(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, int16_t* iq_dev, cudaStream_t st) {
+    if (ctx->set_pending) return fail(ctx, GPSIQ_ERR_ARG, "batches submitted ahead are still in flight: fetch them first", cudaSuccess);
     int rc = enqueue_scan(ctx, desc_dev, n_epochs, st);
     if (rc) return rc;
-    return enqueue_render(ctx, desc_dev, n_epochs, iq_dev, st);
+    return enqueue_render(ctx, iq_dev, st);
 }
 
 static int check_device_error(gpsiq_ctx* ctx) {
@@ -1093,8 +1128,9 @@ int gpsiq_synth(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc, int n_epochs, int16
     CU(cudaSetDevice(ctx->cfg.device));
     CU(cudaMemcpyAsync(ctx->d_desc, desc, (size_t) n_epochs * ctx->C * sizeof(gpsiq_chan_desc), cudaMemcpyHostToDevice,
                        ctx->stream));
+    if (ctx->set_pending) return fail(ctx, GPSIQ_ERR_ARG, "batches submitted ahead are still in flight: fetch them first", cudaSuccess);
     int rc = enqueue_scan(ctx, ctx->d_desc, n_epochs, ctx->stream);
-    if (!rc) rc = enqueue_render(ctx, ctx->d_desc, n_epochs, ctx->d_iq, ctx->stream, iq_out);
+    if (!rc) rc = enqueue_render(ctx, ctx->d_iq, ctx->stream, iq_out);
     if (rc) return rc;
     rc = check_device_error(ctx);
     CU(cudaStreamSynchronize(ctx->copy_stream));
@@ -1115,46 +1151,27 @@ int gpsiq_synth_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_ep
 int gpsiq_submit_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, void* after_stream) {
     if (!ctx || !desc_dev || n_epochs < 1) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_submit_device: bad argument", cudaSuccess);
     if (n_epochs > ctx->E) return fail(ctx, GPSIQ_ERR_CAPACITY, "gpsiq_submit_device: n_epochs > max_epochs", cudaSuccess);
-    if (ctx->set_pending >= 2) return fail(ctx, GPSIQ_ERR_CAPACITY, "gpsiq_submit_device: two batches already in flight", cudaSuccess);
     CU(cudaSetDevice(ctx->cfg.device));
     cudaStream_t ss = ctx->scan_stream;
-    ScanSet& set = ctx->sets[ctx->set_wr];
     if (after_stream != (void*) ss) {  // the descriptors are produced on the caller's stream
         CU(cudaEventRecord(ctx->ev_fork2, (cudaStream_t) after_stream));
         CU(cudaStreamWaitEvent(ss, ctx->ev_fork2, 0));
     }
-    CU(cudaStreamWaitEvent(ss, set.render_done, 0));  // the set's previous batch must have been rendered
+    int rc = begin_batch(ctx, ss);
+    if (rc) return rc;
+    ScanSet& set = ctx->sets[ctx->set_wr];
     CU(cudaMemcpyAsync(set.d_descbuf, desc_dev, (size_t) n_epochs * ctx->C * sizeof(gpsiq_chan_desc),
                        cudaMemcpyDeviceToDevice, ss));
-    use_set(ctx, ctx->set_wr);
-    int rc = enqueue_prepare(ctx, set.d_descbuf, n_epochs, ss);
-    if (!rc) rc = enqueue_speculate(ctx, set.d_descbuf, n_epochs, ss, true);
+    rc = enqueue_prepare(ctx, set.d_descbuf, n_epochs, ss, true);
+    if (!rc) rc = enqueue_speculate(ctx, set.d_descbuf, n_epochs, ss);
     if (!rc) rc = enqueue_chain(ctx, set.d_descbuf, n_epochs, ss);
-    if (rc) return rc;
-    CU(cudaStreamWaitEvent(ss, ctx->ev_code2, 0));  // scan_done covers the code scan on the side stream too
-    CU(cudaEventRecord(set.scan_done, ss));
-    set.n_epochs = n_epochs;
-    ctx->set_wr ^= 1;
-    ctx->set_pending++;
-    return GPSIQ_OK;
+    return rc;
 }
 
 int gpsiq_fetch_device(gpsiq_ctx* ctx, int16_t* iq_dev, void* stream) {
     if (!ctx || !iq_dev || ((uintptr_t) iq_dev & 15)) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_fetch_device: bad argument", cudaSuccess);
-    if (ctx->set_pending < 1) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_fetch_device: nothing submitted", cudaSuccess);
     CU(cudaSetDevice(ctx->cfg.device));
-    cudaStream_t st = (cudaStream_t) stream;
-    ScanSet& set = ctx->sets[ctx->set_rd];
-    CU(cudaStreamWaitEvent(st, set.scan_done, 0));
-    use_set(ctx, ctx->set_rd);
-    ctx->last_epochs = set.n_epochs;
-    ctx->phase_done = 3;
-    int rc = enqueue_render(ctx, set.d_descbuf, set.n_epochs, iq_dev, st);
-    if (rc) return rc;
-    CU(cudaEventRecord(set.render_done, st));
-    ctx->set_rd ^= 1;
-    ctx->set_pending--;
-    return GPSIQ_OK;
+    return enqueue_render(ctx, iq_dev, (cudaStream_t) stream);
 }
 
 // Host-buffer streaming pair: same pipeline, descriptors from / samples to HOST memory.
@@ -1174,21 +1191,11 @@ int gpsiq_submit(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc, int n_epochs) {
 
 int gpsiq_fetch(gpsiq_ctx* ctx, int16_t* iq_out) {
     if (!ctx || !iq_out) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_fetch: bad argument", cudaSuccess);
-    if (ctx->set_pending < 1) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_fetch: nothing submitted", cudaSuccess);
     CU(cudaSetDevice(ctx->cfg.device));
     if (!ctx->d_iq2) CU(cudaMalloc(&ctx->d_iq2, (size_t) ctx->E * ctx->N * 4));
-    ScanSet& set = ctx->sets[ctx->set_rd];
     int16_t* dev = ctx->set_rd ? ctx->d_iq2 : ctx->d_iq;
-    cudaStream_t st = ctx->stream;
-    CU(cudaStreamWaitEvent(st, set.scan_done, 0));
-    use_set(ctx, ctx->set_rd);
-    ctx->last_epochs = set.n_epochs;
-    ctx->phase_done = 3;
-    int rc = enqueue_render(ctx, set.d_descbuf, set.n_epochs, dev, st, iq_out);
+    int rc = enqueue_render(ctx, dev, ctx->stream, iq_out);
     if (rc) return rc;
-    CU(cudaEventRecord(set.render_done, st));
-    ctx->set_rd ^= 1;
-    ctx->set_pending--;
     rc = check_device_error(ctx);
     CU(cudaStreamSynchronize(ctx->copy_stream));
     return rc;
@@ -1213,14 +1220,14 @@ int gpsiq_prepare_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_
 }
 
 int gpsiq_speculate_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, void* stream) {
-    if (!ctx || !desc_dev || n_epochs != ctx->last_epochs || ctx->phase_done != 1)
+    if (!ctx || !desc_dev || n_epochs != ctx->sets[ctx->set_wr].n_epochs || ctx->sets[ctx->set_wr].phase != 1)
         return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_speculate_device: must follow gpsiq_prepare_device of the same batch", cudaSuccess);
     CU(cudaSetDevice(ctx->cfg.device));
     return enqueue_speculate(ctx, desc_dev, n_epochs, (cudaStream_t) stream);
 }
 
 int gpsiq_chain_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, void* stream) {
-    if (!ctx || !desc_dev || n_epochs != ctx->last_epochs || ctx->phase_done != 2)
+    if (!ctx || !desc_dev || n_epochs != ctx->sets[ctx->set_wr].n_epochs || ctx->sets[ctx->set_wr].phase != 2)
         return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_chain_device: must follow gpsiq_speculate_device of the same batch", cudaSuccess);
     CU(cudaSetDevice(ctx->cfg.device));
     return enqueue_chain(ctx, desc_dev, n_epochs, (cudaStream_t) stream);
@@ -1244,12 +1251,13 @@ int gpsiq_estimate_anchor_device(gpsiq_ctx* ctx, void* stream) {
 }
 
 int gpsiq_render_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, int16_t* iq_dev, void* stream) {
-    if (!ctx || !desc_dev || !iq_dev || n_epochs < 1 || n_epochs != ctx->last_epochs || ctx->phase_done != 3 ||
-        ((uintptr_t) iq_dev & 15))
-        return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_render_device: bad argument (must follow gpsiq_scan_device of the same batch)",
+    (void) desc_dev;
+    if (!ctx || !iq_dev || n_epochs < 1 || ((uintptr_t) iq_dev & 15) || ctx->set_pending < 1 ||
+        n_epochs != ctx->sets[ctx->set_rd].n_epochs)
+        return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_render_device: bad argument (renders the oldest batch whose scan phases are complete)",
                     cudaSuccess);
     CU(cudaSetDevice(ctx->cfg.device));
-    return enqueue_render(ctx, desc_dev, n_epochs, iq_dev, (cudaStream_t) stream);
+    return enqueue_render(ctx, iq_dev, (cudaStream_t) stream);
 }
 
 int gpsiq_carrier_to_device(gpsiq_ctx* ctx, double* dst_dev, void* stream) {

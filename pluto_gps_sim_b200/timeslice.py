@@ -30,6 +30,8 @@ serial scan inside `chain`, it never changes a sample.
 ``engine`` abstracts the device: ``Synthesizer``-backed on GPUs (GpuSliceEngine),
 an oracle-backed stand-in in the gloo/CPU tests of this logic.
 """
+import contextlib
+
 import torch
 import torch.distributed as dist
 
@@ -41,6 +43,17 @@ class GpuSliceEngine:
         self.s = synth
         self.phase = torch.zeros(synth.max_chan, dtype=torch.float64, device="cuda")
         self.adv = torch.zeros(2 * synth.max_chan, dtype=torch.float64, device="cuda")
+        # scan phases and the hand-offs run on their own stream, ahead of the render stream: with the
+        # context's two scan sets the next slice is prepared / speculated / chained while this one renders
+        self.scan_stream = torch.cuda.Stream()
+
+    def scan_context(self, order_after_caller=False):
+        # The scan stream must not be ordered after the caller's stream in steady state (that would
+        # serialise it behind the previous slice's render); descriptors uploaded on the caller's
+        # stream right before a step need order_after_caller=True (the runner does it for step 0).
+        if order_after_caller:
+            self.scan_stream.wait_stream(torch.cuda.current_stream())
+        return torch.cuda.stream(self.scan_stream)
 
     def _stream(self):
         return torch.cuda.current_stream().cuda_stream
@@ -86,6 +99,14 @@ class TimeSliceRunner:
         hand-offs 0->1->...->N-1 -- so in-order streams (NCCL) and blocking calls
         (gloo) cannot deadlock."""
         eng, r, n = self.engine, self.rank, self.world
+        ctx = eng.scan_context(self.step_index == 0) if hasattr(eng, "scan_context") else contextlib.nullcontext()
+        with ctx:
+            self._scan_phases(desc, n_epochs)
+        eng.render(desc, n_epochs, out)
+        self.step_index += 1
+
+    def _scan_phases(self, desc, n_epochs):
+        eng, r, n = self.engine, self.rank, self.world
         have_exact = False
         if n > 1 and r == 0 and self.step_index > 0:            # close the previous step's ring first
             dist.recv(eng.phase, src=n - 1)
@@ -109,11 +130,12 @@ class TimeSliceRunner:
         if n > 1:
             eng.store_carrier()
             dist.send(eng.phase, dst=(r + 1) % n)
-        eng.render(desc, n_epochs, out)
-        self.step_index += 1
 
     def finish(self):
         """Drain the last hand-off (rank 0 receives the phases after the final slice)."""
         if self.world > 1 and self.rank == 0 and self.step_index > 0:
-            dist.recv(self.engine.phase, src=self.world - 1)
-            self.engine.load_carrier()
+            eng = self.engine
+            ctx = eng.scan_context() if hasattr(eng, "scan_context") else contextlib.nullcontext()
+            with ctx:
+                dist.recv(eng.phase, src=self.world - 1)
+                eng.load_carrier()
