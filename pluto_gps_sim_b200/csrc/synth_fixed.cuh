@@ -130,9 +130,24 @@ __device__ __forceinline__ void fx_tile_walk(unsigned char* rec, uint32_t* fixma
             }
         }
         const int k = run_in_binade<MODE>(x, tab, len - 1 - n);  // samples n .. n+k share the segment
-        for (; (rnext << 3) <= n + k; rnext++) {                 // runs whose first sample lies in it
-            word |= (uint32_t) nseg << ((rnext & 3) * 8);
-            if ((rnext & 3) == 3) { runseg[rnext >> 2] = word; word = 0; }
+        {   // runs rnext .. rlast have their first sample in this segment: word-wise fill of the byte map
+            const int rlast = (n + k) >> 3;
+            if (rlast >= rnext) {
+                const uint32_t rep = (uint32_t) nseg * 0x01010101u;
+                int r = rnext;
+                if (r & 3) {  // finish the partially filled word
+                    const int stop = min(rlast + 1, (r | 3) + 1);
+                    word |= rep & (((stop & 3) ? ((1u << ((stop & 3) * 8)) - 1u) : 0xffffffffu) & ~((1u << ((r & 3) * 8)) - 1u));
+                    r = stop;
+                    if (!(r & 3)) { runseg[(r >> 2) - 1] = word; word = 0; }
+                }
+                for (; r + 4 <= rlast + 1; r += 4) runseg[r >> 2] = rep;  // whole words
+                if (r <= rlast) {  // start a new partial word
+                    word = rep & ((1u << (((rlast + 1) & 3) * 8)) - 1u);
+                    r = rlast + 1;
+                }
+                rnext = r;
+            }
         }
         nseg++;
         n += k + 1;
