@@ -191,9 +191,13 @@ def ours_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     E = args.epochs
-    C = 12
-    base = np.load(GOLDEN_DESC)                               # [10][12], reference-derived
-    desc = np.concatenate([base] * ((E + 9) // 10))[:E].copy()
+    if args.workload == "config3":
+        base = np.load(os.path.join(REPO, "tests", "golden", "allsky32_desc.npy"))   # [20][32]
+        args.no_cpu_baseline = True
+    else:
+        base = np.load(GOLDEN_DESC)                           # [10][12], reference-derived
+    C = base.shape[1]
+    desc = np.concatenate([base] * ((E + len(base) - 1) // len(base)))[:E].copy()
     desc["flags"] = 0                                         # carrier chains through the whole run ...
     first = desc.copy()
     first[0]["flags"] = capi.FLAG_RESET_CARRIER               # ... from the allocation phases of epoch 0
@@ -335,12 +339,14 @@ def ours_arm(args):
                 cpu = {"value": round(v, 3), "unit": "Msamples/s", "cores": 1, "kind": "port",
                        "sample": "100 epochs (3e7 samples), oracle C restatement"}
         line = {
-            "metric": "Msamples/sec (complex I/Q) at 12 channels; bit-exact vs CPU ref",
+            "metric": "Msamples/sec (complex I/Q) at %d channels; bit-exact vs CPU ref" % C,
             "value": round(value, 3), "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 NCO / int32 accumulate / int16 out",
             "data": "synthetic (reference-derived golden descriptors of config[1], tiled in time)",
-            "config": {"workload": WORKLOAD, "epochs_per_step_per_gpu": E, "samples_per_step_per_gpu": samples_per_step,
+            "config": {"workload": WORKLOAD if args.workload == "config1" else
+                       "config[3]: static location, 10.0 MS/s, 32 channels (synthetic all-visible constellation), 300000 samples/epoch",
+                       "epochs_per_step_per_gpu": E, "samples_per_step_per_gpu": samples_per_step,
                        "parallelism": "time-slice x%d, NCCL carrier-phase hand-off" % world if world > 1 else "single GPU",
                        "l2_policy": "output per step %.1f MB > 126 MB L2; inputs are %d B of descriptors"
                                     % (samples_per_step * 4 / 1e6, nbytes_desc),
@@ -377,6 +383,9 @@ def main():
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", choices=["config1", "config3"], default="config1",
+                    help="config1 (default, the metric's configuration): 12 channels, 2.6 MS/s; config3: 32 channels, "
+                         "10 MS/s, synthetic all-visible constellation (informative; no CPU baseline / reference arm)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

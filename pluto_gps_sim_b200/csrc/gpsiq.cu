@@ -780,7 +780,7 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
                      ctx->C <= FX_MAXC && cfg->carrier_mode == GPSIQ_CARRIER_FLOAT;
     if (cfg->kernel == GPSIQ_KERNEL_FIXED_POINT && !ctx->use_fixed)
         return fail(NULL, GPSIQ_ERR_ARG, "gpsiq_create: fixed-point kernel needs tile_samples 0/1024, samples_per_epoch % 4 == 0, "
-                    "max_chan <= 24 and the float carrier", cudaSuccess);
+                    "max_chan <= 32 and the float carrier", cudaSuccess);
     ctx->ntiles = (ctx->N + ctx->T - 1) / ctx->T;
     CU(cudaSetDevice(cfg->device));
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));

@@ -39,7 +39,8 @@
 #define FX_THREADS 128
 #define FX_RUN 8
 #define FX_TILE (FX_THREADS * FX_RUN)
-#define FX_MAXC 24
+#define FX_MAXC 32
+#define FX_CGROUP 16  // channels whose tables are resident in shared memory at a time
 
 namespace gpsiq {
 
@@ -271,7 +272,8 @@ k_tile_fixup(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
 #define FX_TILES_PER_CTA (FX_WORKERS * FX_TILES_PER_WORKER)
 
 __host__ __device__ inline size_t fx_smem_bytes(int C) {
-    return (size_t) C * 512 * 4 + (size_t) C * 2048 + (size_t) C * NBINADE * 16 + FX_WORKERS * fx_rec_bytes(C) + 64;
+    const int CG = C < FX_CGROUP ? C : FX_CGROUP;
+    return (size_t) CG * 512 * 4 + (size_t) CG * 2048 + (size_t) CG * NBINADE * 16 + FX_WORKERS * fx_rec_bytes(C) + 64;
 }
 
 __device__ __forceinline__ void fx_worker_sync(int worker) {
@@ -298,11 +300,13 @@ k_synth_fixed(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restric
               int groups) {
     extern __shared__ __align__(16) unsigned char fx_raw[];
     const size_t rec_bytes = fx_rec_bytes(C);
+    const int CG = C < FX_CGROUP ? C : FX_CGROUP;          // channels per table group
+    const int ngroups = (C + CG - 1) / CG;
     unsigned char* s_rec0 = fx_raw;
     int64_t* s_dF = (int64_t*) (fx_raw + FX_WORKERS * rec_bytes);
-    int64_t* s_dG = s_dF + C * NBINADE;
-    int32_t* s_lut = (int32_t*) (s_dG + C * NBINADE);
-    int8_t* s_chip = (int8_t*) (s_lut + C * 512);
+    int64_t* s_dG = s_dF + CG * NBINADE;
+    int32_t* s_lut = (int32_t*) (s_dG + CG * NBINADE);
+    int8_t* s_chip = (int8_t*) (s_lut + CG * 512);
 
     const int e = e0 + blockIdx.x / groups;
     const int grp = blockIdx.x % groups;
@@ -311,61 +315,81 @@ k_synth_fixed(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restric
     const int tid_cta = threadIdx.x;
     const int worker = tid_cta >> 7, tid = tid_cta & (FX_THREADS - 1);
 
-    // ---- stage the epoch's tables once per CTA
-    for (int i = tid_cta; i < C * 512; i += FX_WORKERS * FX_THREADS) {
-        const int prn = de[i >> 9].prn;
-        s_lut[i] = (prn > 0) ? lutp[(size_t) e * C * 512 + i] : 0;
-        ((uint32_t*) s_chip)[i] = (prn > 0 && prn <= 32) ? ((const uint32_t*) chips)[prn * 512 + (i & 511)] : 0x01010101u;
+    // stage the tables of channel group g (amplitude LUTs, chip signs, fixed-point steps)
+    auto stage_tables = [&](int g) {
+        const int c0 = g * CG, nc = min(CG, C - c0);
+        for (int i = tid_cta; i < nc * 512; i += FX_WORKERS * FX_THREADS) {
+            const int prn = de[c0 + (i >> 9)].prn;
+            s_lut[i] = (prn > 0) ? lutp[((size_t) e * C + c0) * 512 + i] : 0;
+            ((uint32_t*) s_chip)[i] = (prn > 0 && prn <= 32) ? ((const uint32_t*) chips)[prn * 512 + (i & 511)] : 0x01010101u;
+        }
+        for (int i = tid_cta; i < nc * NBINADE; i += FX_WORKERS * FX_THREADS) {
+            const int c = i / NBINADE, bi = i - c * NBINADE;
+            const BinadeTab* tc = tabs + ((size_t) e * C + c0 + c) * 2;
+            s_dG[i] = ((tc[0].valid >> bi) & 1u) ? fx_scale_delta(tc[0].delta[bi], 10 - bi) : 0;
+            s_dF[i] = ((tc[1].valid >> bi) & 1u) ? fx_scale_delta(tc[1].delta[bi], 11 - bi) : 0;
+        }
+    };
+    if (ngroups == 1) {  // the usual case: everything resident for the CTA's whole life
+        stage_tables(0);
+        __syncthreads();
     }
-    for (int i = tid_cta; i < C * NBINADE; i += FX_WORKERS * FX_THREADS) {
-        const int c = i / NBINADE, bi = i - c * NBINADE;
-        const BinadeTab* tc = tabs + ((size_t) e * C + c) * 2;
-        s_dG[i] = ((tc[0].valid >> bi) & 1u) ? fx_scale_delta(tc[0].delta[bi], 10 - bi) : 0;
-        s_dF[i] = ((tc[1].valid >> bi) & 1u) ? fx_scale_delta(tc[1].delta[bi], 11 - bi) : 0;
-    }
-    __syncthreads();
 
     unsigned char* s_rec = s_rec0 + worker * rec_bytes;
     uint32_t* out_epoch = reinterpret_cast<uint32_t*>(iq) + (size_t) e * N;
     for (int tt = 0; tt < FX_TILES_PER_WORKER; tt++) {
         const int t = grp * FX_TILES_PER_CTA + tt * FX_WORKERS + worker;
-        if (t >= ntiles) break;
+        const bool active = t < ntiles;                  // (with several groups every worker keeps hitting the CTA barriers)
+        if (!active && ngroups == 1) break;
         const int n0 = t * FX_TILE;
-        const int len = min(FX_TILE, N - n0);
-        const size_t tile_id = (size_t) (e - e0) * ntiles + t;
+        const int len = active ? min(FX_TILE, N - n0) : 0;
+        const size_t tile_id = (size_t) (e - e0) * ntiles + (active ? t : 0);
+        const bool mine = active && tid * FX_RUN < len;
 
         // ---- this worker's tile record -> shared memory
-        {
+        if (active) {
             const uint4* src = (const uint4*) (recs + tile_id * rec_bytes);
             uint4* dst = (uint4*) s_rec;
             for (int i = tid; i < (int) (rec_bytes / 16); i += FX_THREADS) dst[i] = src[i];
         }
         fx_worker_sync(worker);
 
-        // ---- main pass: uniform integer inner loop
-        if (tid * FX_RUN < len) {
-            int32_t acc[FX_RUN];
-            {   // corrections for runs that contain a segment boundary (zero elsewhere)
-                const int4* dp = reinterpret_cast<const int4*>(delta + tile_id * FX_TILE + tid * FX_RUN);
-                const int4 a = dp[0], b = dp[1];
-                acc[0] = a.x; acc[1] = a.y; acc[2] = a.z; acc[3] = a.w;
-                acc[4] = b.x; acc[5] = b.y; acc[6] = b.z; acc[7] = b.w;
+        int32_t acc[FX_RUN];
+#pragma unroll
+        for (int j = 0; j < FX_RUN; j++) acc[j] = 0;
+        if (mine) {  // corrections for runs that contain a segment boundary (zero elsewhere)
+            const int4* dp = reinterpret_cast<const int4*>(delta + tile_id * FX_TILE + tid * FX_RUN);
+            const int4 a = dp[0], b = dp[1];
+            acc[0] = a.x; acc[1] = a.y; acc[2] = a.z; acc[3] = a.w;
+            acc[4] = b.x; acc[5] = b.y; acc[6] = b.z; acc[7] = b.w;
+        }
+        const uint16_t* nseg = (const uint16_t*) (s_rec + fx_rec_nseg(C));
+        for (int g = 0; g < ngroups; g++) {
+            if (ngroups > 1) {
+                __syncthreads();   // everyone is done with the previous group's tables
+                stage_tables(g);
+                __syncthreads();
             }
-            const uint16_t* nseg = (const uint16_t*) (s_rec + fx_rec_nseg(C));
-            for (int c = 0; c < C; c++) {
+            if (!mine) continue;
+            const int c0 = g * CG, nc = min(CG, C - c0);
+            // ---- main pass: uniform integer inner loop
+            for (int cl = 0; cl < nc; cl++) {
+                const int c = c0 + cl;
                 if (nseg[c * 2] == 0) continue;  // inactive slot (uniform across the worker)
-                uint64_t f, df, g, dg;
-                fx_run_state(s_rec, s_dF, C, c, 1, tid, f, df);
-                fx_run_state(s_rec, s_dG, C, c, 0, tid, g, dg);
-                const int32_t* lut = s_lut + c * 512;
-                const int8_t* chip = s_chip + c * 2048;
+                uint64_t f, df, g2, dg;
+                fx_run_state(s_rec, s_dF - (size_t) c0 * NBINADE, C, c, 1, tid, f, df);
+                fx_run_state(s_rec, s_dG - (size_t) c0 * NBINADE, C, c, 0, tid, g2, dg);
+                const int32_t* lut = s_lut + cl * 512;
+                const int8_t* chip = s_chip + cl * 2048;
 #pragma unroll
                 for (int j = 0; j < FX_RUN; j++) {
-                    acc[j] += lut[(uint32_t) (f >> 55)] * (int32_t) chip[(uint32_t) (g >> 53)];
+                    acc[j] += lut[(uint32_t) (f >> 55)] * (int32_t) chip[(uint32_t) (g2 >> 53)];
                     f += df;
-                    g += dg;
+                    g2 += dg;
                 }
             }
+        }
+        if (mine) {
             // packed (Q<<16)+I with signed I  ->  int16 pair (plutogpssim.c:2754-2755)
             uint32_t w[FX_RUN];
 #pragma unroll

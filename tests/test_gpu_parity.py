@@ -32,7 +32,7 @@ def test_config1_static12_bit_exact_vs_reference_golden(kernel):
     assert np.array_equal(trace, want)
 
 
-@pytest.mark.parametrize("kernel", [capi.KERNEL_LANE_PER_CHANNEL, capi.KERNEL_AUTO])
+@pytest.mark.parametrize("kernel", KERNELS)
 def test_config3_allsky32_bit_exact_vs_reference_golden(kernel):
     meta = ol.load_golden_meta("allsky32")
     desc = ol.load_golden_desc("allsky32")
@@ -94,6 +94,16 @@ def test_fixed_point_kernel_ragged_epochs(n):
     desc = ol.load_golden_desc("circle12")[300:303]
     want, _ = ol.oracle_synth(desc, n)
     with Synthesizer(max_chan=12, samples_per_epoch=n, max_epochs=3, kernel=capi.KERNEL_FIXED_POINT) as s:
+        got = s.synth(desc)
+    assert first_diff(got, want) is None
+
+
+@pytest.mark.parametrize("nchan", [17, 24, 32])
+def test_fixed_point_kernel_channel_groups(nchan):
+    """More than 16 slots: the kernel walks the channels in groups of 16 resident tables."""
+    desc = ol.load_golden_desc("allsky32")[:3, :nchan].copy()
+    want, _ = ol.oracle_synth(desc, 20000)
+    with Synthesizer(max_chan=nchan, samples_per_epoch=20000, max_epochs=3, kernel=capi.KERNEL_FIXED_POINT) as s:
         got = s.synth(desc)
     assert first_diff(got, want) is None
 
