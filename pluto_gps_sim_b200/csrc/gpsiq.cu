@@ -78,6 +78,7 @@ struct ScanSet {
     gpsiq_chan_desc* d_descbuf;
     int2* d_lut; int32_t* d_lutp; int* d_flags; double* d_code_ck; int* d_wrap_ck; double* d_carr_ck;
     BinadeTab* d_tab; double* d_drift; CarrSpec* d_spec; CarrSpec* d_specE; ChunkInfo* d_cinfo; CarrInfo* d_info;
+    CarrSpec* d_specG; GroupInfo* d_ginfo; double* d_traceG;
     double* d_adv; double* d_carr_trace;
     cudaEvent_t scan_done, render_done;
     const gpsiq_chan_desc* desc;  // the batch's descriptors (device)
@@ -127,7 +128,10 @@ struct gpsiq_ctx {
     CarrSpec* d_specE;    // [E][C][2]    epoch-level (stitched) results
     ChunkInfo* d_cinfo;   // [E][C][2][J]
     int G, J;             // chunk length in tiles, chunks per epoch
-    CarrInfo* d_info;     // [E][C]
+    CarrInfo* d_info;     // [3][E][C]: epoch results of the group-chain variants 0, 1 and of the exact fallback chain
+    CarrSpec* d_specG;    // [groups][C][2] group-level speculation results
+    GroupInfo* d_ginfo;   // [groups][C]    final chain results
+    double* d_traceG;     // [2][E][C]      post-epoch phases of the group chains
     int* d_fallbacks;     // epochs that fell back to the serial carrier scan (diagnostic counter)
     size_t ck_plane;      // elements per plane
     double* d_carr_state; // [C]  exact carrier phase per slot after the last chained epoch
@@ -238,14 +242,23 @@ __global__ void k_scan_code(const gpsiq_chan_desc* __restrict__ desc, const Bina
 __global__ void k_scan_carrier(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
                                double* __restrict__ carr_ck,
                                double* __restrict__ carr_state, double* __restrict__ carr_trace,
-                               CarrInfo* __restrict__ info, int E, int C, int N, int T, int ntiles, int carrier_mode) {
+                               CarrInfo* __restrict__ info, GroupInfo* __restrict__ ginfo, int GP, int E, int C, int N,
+                               int T, int ntiles, int carrier_mode) {
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one chain per warp, lane 0
     if (c >= C || (threadIdx.x & 31)) return;
+    for (int g = 0; g * GP < E; g++) {  // every group: "chained exactly", all tiles in the exact plane
+        GroupInfo gi; gi.delta = 0.0; gi.pos = 0x7fffffff; gi.variant = 0;
+        ginfo[(size_t) g * C + c] = gi;
+    }
     double x = carr_state[c];
     uint32_t u = (uint32_t) x;
     int dummy = 0;
     for (int e = 0; e < E; e++) {
         const gpsiq_chan_desc d = desc[(size_t) e * C + c];
+        {
+            CarrInfo inf; inf.delta = 0.0; inf.n1 = N; inf.variant = 0;  // every tile reads the exact plane
+            info[(size_t) e * C + c] = inf;
+        }
         if (d.prn <= 0) {
             carr_trace[(size_t) e * C + c] = (carrier_mode == GPSIQ_CARRIER_FLOAT) ? x : (double) u;
             continue;
@@ -253,10 +266,6 @@ __global__ void k_scan_carrier(const gpsiq_chan_desc* __restrict__ desc, const B
         if (d.flags & GPSIQ_FLAG_RESET_CARRIER) {
             x = d.carr_phase0;
             u = (uint32_t) d.carr_phase0;
-        }
-        {
-            CarrInfo inf; inf.delta = 0.0; inf.n1 = N; inf.variant = 0;  // every tile reads the exact plane 0
-            info[(size_t) e * C + c] = inf;
         }
         if (carrier_mode == GPSIQ_CARRIER_FLOAT) {
             const BinadeTab tab = tabs[((size_t) e * C + c) * 2 + 1];
@@ -396,62 +405,82 @@ __global__ void k_carr_stitch(const gpsiq_chan_desc* __restrict__ desc, const Bi
     specE[(size_t) ec * 2 + V] = out;
 }
 
-// Per-epoch inputs of the chain, staged through shared memory: the chain is one
-// latency-bound thread, so the other 31 lanes of its warp prefetch the next
-// epoch's descriptor, binade table and speculation results while lane 0 works.
-struct ChainStage {
-    gpsiq_chan_desc d;   // 64 B
-    BinadeTab tab;       // 200 B
-    CarrSpec s0, s1;     // 2 x 32 B
-};
-#define CHAIN_WORDS ((int) (sizeof(ChainStage) / 4))
-
-__device__ __forceinline__ uint32_t chain_stage_word(const gpsiq_chan_desc* desc, const BinadeTab* tabs,
-                                                     const CarrSpec* spec, size_t ec, int w) {
-    constexpr int WD = sizeof(gpsiq_chan_desc) / 4, WT = sizeof(BinadeTab) / 4;
-    if (w < WD) return ((const uint32_t*) (desc + ec))[w];
-    if (w < WD + WT) return ((const uint32_t*) (tabs + ec * 2 + 1))[w - WD];
-    return ((const uint32_t*) (spec + ec * 2))[w - WD - WT];  // spec = epoch-level (stitched) results
+// Stage the per-epoch inputs of one group for one slot into shared memory (one lane per epoch).
+__device__ __forceinline__ void stage_group(GroupEpoch* ge, const gpsiq_chan_desc* __restrict__ desc,
+                                            const BinadeTab* __restrict__ tabs, const CarrSpec* __restrict__ specE,
+                                            int first, int count, int c, int C, int lane) {
+    if (lane < count) {
+        const size_t ec = (size_t) (first + lane) * C + c;
+        const gpsiq_chan_desc d = desc[ec];
+        GroupEpoch& g = ge[lane];
+        g.d = d.carr_step;
+        g.phase0 = d.carr_phase0;
+        g.active = d.prn > 0;
+        g.reset = (d.flags & GPSIQ_FLAG_RESET_CARRIER) != 0;
+        g.tab = tabs[ec * 2 + 1];
+        g.s0 = specE[ec * 2];
+        g.s1 = specE[ec * 2 + 1];
+    }
+    __syncwarp();
 }
 
+#define GROUP_EPOCHS 16  // epochs per group (level 3)
+
+// Level 3: one chain per (group, slot, variant): the group's epochs chained from the ESTIMATED group start.
+__global__ void __launch_bounds__(128)
+k_carr_group(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
+             const CarrSpec* __restrict__ specE, const double* __restrict__ est_epoch, double* __restrict__ carr_ck,
+             size_t ck_plane, CarrInfo* __restrict__ infoG, size_t info_plane, double* __restrict__ traceG,
+             CarrSpec* __restrict__ specG, int* __restrict__ fallbacks, int E, int C, int N, int T, int ntiles) {
+    __shared__ GroupEpoch s_ge[4][GROUP_EPOCHS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ngroups = (E + GROUP_EPOCHS - 1) / GROUP_EPOCHS;
+    const int chain = blockIdx.x * 4 + warp;
+    if (chain >= ngroups * C * 2) return;
+    const int V = chain & 1, gc = chain >> 1;
+    const int g = gc / C, c = gc - g * C;
+    const int first = g * GROUP_EPOCHS, count = min(GROUP_EPOCHS, E - first);
+    stage_group(s_ge[warp], desc, tabs, specE, first, count, c, C, lane);
+    if (lane) return;
+    CarrSpec out;
+    out.margin = -1.0; out.n1 = -1; out.xw1 = 0.0; out.xend = 0.0; out.pad = 0;
+    bool any_neg = false;
+    for (int k = 0; k < count; k++) any_neg |= s_ge[warp][k].active && s_ge[warp][k].d < 0.0;
+    if (V == 0 || any_neg) {
+        int fb = 0;
+        group_chain(est_epoch[(size_t) first * C + c], s_ge[warp], count, N, T, V,
+                    carr_ck + (size_t) (4 + V) * ck_plane + (size_t) first * ntiles * C + c, (size_t) C, (size_t) ntiles * C,
+                    infoG + (size_t) V * info_plane + (size_t) first * C + c, (size_t) C,
+                    traceG + (size_t) V * info_plane + (size_t) first * C + c, (size_t) C, out, fb);
+        if (fb && V == 0) atomicAdd(fallbacks, fb);
+    }
+    specG[(size_t) gc * 2 + V] = out;
+}
+
+// Level 4: the exact chain, one chain per slot, serial over the groups: one head scan per group.
 __global__ void __launch_bounds__(32)
-k_carr_chain(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
-             const CarrSpec* __restrict__ spec, double* __restrict__ carr_ck, size_t ck_plane,
-             double* __restrict__ carr_state, double* __restrict__ carr_trace, CarrInfo* __restrict__ info,
+k_carr_final(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
+             const CarrSpec* __restrict__ specE, const CarrSpec* __restrict__ specG, double* __restrict__ carr_ck,
+             size_t ck_plane, CarrInfo* __restrict__ infoG, size_t info_plane, const double* __restrict__ traceG,
+             double* __restrict__ carr_state, double* __restrict__ carr_trace, GroupInfo* __restrict__ ginfo,
              int* __restrict__ fallbacks, int E, int C, int N, int T, int ntiles) {
-    static_assert(sizeof(ChainStage) % 8 == 0 && sizeof(ChainStage) / 4 <= 96, "stage layout");
-    __shared__ __align__(8) uint32_t stage[2][96];
+    __shared__ GroupEpoch s_ge[GROUP_EPOCHS];
     const int c = blockIdx.x, lane = threadIdx.x;
     if (c >= C) return;
+    const int ngroups = (E + GROUP_EPOCHS - 1) / GROUP_EPOCHS;
     double x = carr_state[c];
     int fb = 0;
-    uint32_t r0, r1, r2;
-    r0 = chain_stage_word(desc, tabs, spec, (size_t) c, lane);
-    r1 = chain_stage_word(desc, tabs, spec, (size_t) c, lane + 32);
-    r2 = (lane + 64 < CHAIN_WORDS) ? chain_stage_word(desc, tabs, spec, (size_t) c, lane + 64) : 0u;
-    for (int e = 0; e < E; e++) {
-        uint32_t* sb = stage[e & 1];
-        sb[lane] = r0; sb[lane + 32] = r1; sb[lane + 64] = r2;
-        __syncwarp();
-        if (e + 1 < E) {  // prefetch the next epoch while lane 0 chains this one
-            const size_t en = (size_t) (e + 1) * C + c;
-            r0 = chain_stage_word(desc, tabs, spec, en, lane);
-            r1 = chain_stage_word(desc, tabs, spec, en, lane + 32);
-            r2 = (lane + 64 < CHAIN_WORDS) ? chain_stage_word(desc, tabs, spec, en, lane + 64) : 0u;
-        }
+    for (int g = 0; g < ngroups; g++) {
+        const int first = g * GROUP_EPOCHS, count = min(GROUP_EPOCHS, E - first);
+        stage_group(s_ge, desc, tabs, specE, first, count, c, C, lane);
         if (lane == 0) {
-            const ChainStage& st = *reinterpret_cast<const ChainStage*>(sb);
-            const size_t ec = (size_t) e * C + c;
-            if (st.d.prn <= 0) {
-                carr_trace[ec] = x;
-            } else {
-                if (st.d.flags & GPSIQ_FLAG_RESET_CARRIER) x = st.d.carr_phase0;
-                CarrInfo inf;
-                x = chain_epoch(x, st.d.carr_step, st.tab, N, T, st.s0, st.s1,
-                                carr_ck + 4 * ck_plane + (size_t) e * ntiles * C + c, (size_t) C, inf, fb);
-                info[ec] = inf;
-                carr_trace[ec] = x;
-            }
+            GroupInfo gi;
+            const size_t o = (size_t) first * C + c;
+            x = group_final(x, s_ge, count, N, T, specG[((size_t) g * C + c) * 2], specG[((size_t) g * C + c) * 2 + 1],
+                            carr_ck + 6 * ck_plane + (size_t) first * ntiles * C + c, (size_t) C, (size_t) ntiles * C,
+                            infoG + 2 * info_plane + o, (size_t) C, traceG + o, traceG + info_plane + o, carr_trace + o,
+                            (size_t) C, gi, fb);
+            ginfo[(size_t) g * C + c] = gi;
         }
         __syncwarp();
     }
@@ -473,8 +502,7 @@ k_carr_chain(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restri
 __global__ void __launch_bounds__(LANES_WARPS * 32)
 k_synth_lanes(const gpsiq_chan_desc* __restrict__ desc, const int2* __restrict__ lut,
               const double* __restrict__ code_ck, const int* __restrict__ wrap_ck,
-              const double* __restrict__ carr_ck, size_t ck_plane, const CarrInfo* __restrict__ info,
-              const ChunkInfo* __restrict__ cinfo, int G, int J,
+              const CarrLookup carr,
               const uint32_t* __restrict__ ca, const int* __restrict__ amp_sum, const int* __restrict__ step_flag,
               int only_flagged, int16_t* __restrict__ iq, int e0,
               int C, int N, int T, int ntiles, int tile_groups, int carrier_mode) {
@@ -513,8 +541,7 @@ k_synth_lanes(const gpsiq_chan_desc* __restrict__ desc, const int2* __restrict__
         const int w = wrap_ck[o] + d.ms0 % 20;
         kbit = w / 20;
         icode = w - kbit * 20;
-        ph = carr_tile_phase(carr_ck + (size_t) e * ntiles * C + lane, ck_plane, (size_t) C, t, T, N, G, J,
-                             info[(size_t) e * C + lane], cinfo + ((size_t) e * C + lane) * 2 * J);
+        ph = carr_lookup(carr, e, lane, t, T, N, C, ntiles);
         uph = (uint32_t) ph;
         cstep = d.code_step;
         pstep = d.carr_step;
@@ -596,6 +623,7 @@ static void use_set(gpsiq_ctx* ctx, int i) {
     ctx->d_lut = ss.d_lut; ctx->d_lutp = ss.d_lutp; ctx->d_flags = ss.d_flags; ctx->d_code_ck = ss.d_code_ck;
     ctx->d_wrap_ck = ss.d_wrap_ck; ctx->d_carr_ck = ss.d_carr_ck; ctx->d_tab = ss.d_tab; ctx->d_drift = ss.d_drift;
     ctx->d_spec = ss.d_spec; ctx->d_specE = ss.d_specE; ctx->d_cinfo = ss.d_cinfo; ctx->d_info = ss.d_info;
+    ctx->d_specG = ss.d_specG; ctx->d_ginfo = ss.d_ginfo; ctx->d_traceG = ss.d_traceG;
     ctx->d_adv = ss.d_adv; ctx->d_carr_trace = ss.d_carr_trace;
     ctx->set_cur = i;
 }
@@ -697,43 +725,76 @@ int gpsiq_carrier_chain_host(const double* steps, int n_epochs, int N, int T, do
     if (!steps || !ck_out || n_epochs < 1 || N < 1 || T < 1) return GPSIQ_ERR_ARG;
     const int ntiles = (N + T - 1) / T;
     const int G = (ntiles + 7) / 8, J = (ntiles + G - 1) / G;
-    double* planes = (double*) malloc(sizeof(double) * ntiles * 5);
-    if (!planes) return GPSIQ_ERR_NOMEM;
-    double x = x0, xe = x0;
+    const int GP = 4;                                   // epochs per group (the device uses 16)
+    const int E = n_epochs;
+    const size_t ep = (size_t) 7 * ntiles;              // planes of one epoch: [7][ntiles]
+    double* planes = (double*) malloc(sizeof(double) * ep * E);
+    GroupEpoch* ge = (GroupEpoch*) malloc(sizeof(GroupEpoch) * E);
+    ChunkInfo* ci = (ChunkInfo*) malloc(sizeof(ChunkInfo) * 2 * J * E);
+    CarrInfo* infG = (CarrInfo*) malloc(sizeof(CarrInfo) * 3 * E);   // [0],[1] group variants, [2] exact
+    double* trace = (double*) malloc(sizeof(double) * 3 * E);
+    double* est = (double*) malloc(sizeof(double) * E);
+    if (!planes || !ge || !ci || !infG || !trace || !est) return GPSIQ_ERR_NOMEM;
     int fb = 0;
-    for (int e = 0; e < n_epochs; e++) {
+    double xe = x0;
+    // levels 1 + 2 per epoch: chunk speculation, stitch
+    for (int e = 0; e < E; e++) {
         const double d = steps[e];
-        BinadeTab tab;
-        build_binade_tab<NCO_CARRIER>(d, tab);
-        const double eadv = fma((double) N, d, carr_drift_estimate(d, tab, N));
-        double est = xe + est_err;                       // what the device would guess, plus injected error
-        est -= floor(est);
-        CarrSpec cs[16], sE[2];
-        ChunkInfo ci[2 * 8];
+        GroupEpoch& g = ge[e];
+        g.d = d; g.phase0 = 0.0; g.active = 1; g.reset = 0;
+        build_binade_tab<NCO_CARRIER>(d, g.tab);
+        const double eadv = fma((double) N, d, carr_drift_estimate(d, g.tab, N));
+        double a0 = xe + est_err;                        // what the device would guess, plus injected error
+        a0 -= floor(a0);
+        est[e] = a0;
+        double* pl = planes + ep * e;
+        CarrSpec cs[16];
         for (int j = 0; j < J; j++)
             for (int v = 0; v < 2; v++) {
                 CarrSpec& o = cs[j * 2 + v];
                 o.margin = -1.0; o.n1 = -1; o.xw1 = 0; o.xend = 0; o.pad = 0;
                 if ((v == 1 && d >= 0.0) || !carr_step_speculable(d)) continue;
                 const int t0 = j * G, t1 = (t0 + G < ntiles) ? t0 + G : ntiles;
-                double xs = est;
-                if (j > 0) { xs = est + eadv * ((double) (t0 * T) / (double) N); xs -= floor(xs); if (!(xs >= 0.0 && xs < 1.0)) xs = 0.0; }
-                spec_scan_range(xs, d, tab, N, T, t0, t1, v, planes + (size_t) v * ntiles, 1, o);
+                double xs = a0;
+                if (j > 0) { xs = a0 + eadv * ((double) (t0 * T) / (double) N); xs -= floor(xs); if (!(xs >= 0.0 && xs < 1.0)) xs = 0.0; }
+                spec_scan_range(xs, d, g.tab, N, T, t0, t1, v, pl + (size_t) v * ntiles, 1, o);
             }
+        CarrSpec* sE[2] = {&g.s0, &g.s1};
         for (int V = 0; V < 2; V++) {
-            sE[V].margin = -1.0; sE[V].n1 = -1; sE[V].xw1 = 0; sE[V].xend = 0; sE[V].pad = 0;
+            sE[V]->margin = -1.0; sE[V]->n1 = -1; sE[V]->xw1 = 0; sE[V]->xend = 0; sE[V]->pad = 0;
             if ((V == 1 && d >= 0.0) || !carr_step_speculable(d)) continue;
-            stitch_epoch(est, d, tab, N, T, G, V, cs, planes + (size_t) (2 + V) * ntiles, 1, ci + V * J, sE[V]);
+            stitch_epoch(a0, d, g.tab, N, T, G, V, cs, pl + (size_t) (2 + V) * ntiles, 1, ci + ((size_t) e * 2 + V) * J, *sE[V]);
         }
-        CarrInfo info;
-        x = chain_epoch(x, d, tab, N, T, sE[0], sE[1], planes + (size_t) 4 * ntiles, 1, info, fb);
-        for (int t = 0; t < ntiles; t++)
-            ck_out[(size_t) e * ntiles + t] = carr_tile_phase(planes, (size_t) ntiles, 1, t, T, N, G, J, info, ci);
         double t2 = xe + eadv;
         t2 -= floor(t2);
         xe = (t2 >= 0.0 && t2 < 1.0) ? t2 : 0.0;
     }
-    free(planes);
+    // levels 3 + 4 per group
+    double x = x0;
+    for (int first = 0; first < E; first += GP) {
+        const int count = (E - first < GP) ? E - first : GP;
+        CarrSpec sG[2];
+        bool any_neg = false;
+        for (int k = 0; k < count; k++) any_neg |= ge[first + k].d < 0.0;
+        for (int V = 0; V < 2; V++) {
+            sG[V].margin = -1.0; sG[V].n1 = -1; sG[V].xw1 = 0; sG[V].xend = 0; sG[V].pad = 0;
+            if (V == 1 && !any_neg) continue;
+            group_chain(est[first], ge + first, count, N, T, V, planes + ep * first + (size_t) (4 + V) * ntiles, 1, ep,
+                        infG + (size_t) V * E + first, 1, trace + (size_t) V * E + first, 1, sG[V], fb);
+        }
+        GroupInfo gi;
+        x = group_final(x, ge + first, count, N, T, sG[0], sG[1], planes + ep * first + (size_t) 6 * ntiles, 1, ep,
+                        infG + (size_t) 2 * E + first, 1, trace + first, trace + (size_t) E + first,
+                        trace + (size_t) 2 * E + first, 1, gi, fb);
+        for (int k = 0; k < count; k++) {
+            const int e = first + k;
+            for (int t = 0; t < ntiles; t++)
+                ck_out[(size_t) e * ntiles + t] = carr_tile_phase(planes + ep * e, (size_t) ntiles, 1, t, T, N, G, J, k, gi,
+                                                                  infG[e], infG[(size_t) E + e], infG[(size_t) 2 * E + e],
+                                                                  ci + (size_t) e * 2 * J);
+        }
+    }
+    free(planes); free(ge); free(ci); free(infG); free(trace); free(est);
     if (x_end_out) *x_end_out = x;
     if (n_fallback) *n_fallback = fb;
     return GPSIQ_OK;
@@ -814,13 +875,19 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
         CU(cudaMemset(ss.d_flags, 0, 2 * (size_t) ctx->E * sizeof(int)));
         CU(cudaMalloc(&ss.d_code_ck, ck * sizeof(double)));
         CU(cudaMalloc(&ss.d_wrap_ck, ck * sizeof(int)));
-        CU(cudaMalloc(&ss.d_carr_ck, 5 * ck * sizeof(double)));
+        CU(cudaMalloc(&ss.d_carr_ck, 7 * ck * sizeof(double)));
         CU(cudaMalloc(&ss.d_specE, EC * 2 * sizeof(CarrSpec)));
         CU(cudaMalloc(&ss.d_cinfo, EC * 2 * ctx->J * sizeof(ChunkInfo)));
         CU(cudaMalloc(&ss.d_tab, EC * 2 * sizeof(BinadeTab)));
         CU(cudaMalloc(&ss.d_drift, 3 * EC * sizeof(double)));
         CU(cudaMalloc(&ss.d_spec, EC * 2 * 8 * sizeof(CarrSpec)));
-        CU(cudaMalloc(&ss.d_info, EC * sizeof(CarrInfo)));
+        CU(cudaMalloc(&ss.d_info, 3 * EC * sizeof(CarrInfo)));
+        {
+            const size_t ng = ((size_t) ctx->E + GROUP_EPOCHS - 1) / GROUP_EPOCHS;
+            CU(cudaMalloc(&ss.d_specG, ng * ctx->C * 2 * sizeof(CarrSpec)));
+            CU(cudaMalloc(&ss.d_ginfo, ng * ctx->C * sizeof(GroupInfo)));
+            CU(cudaMalloc(&ss.d_traceG, 2 * EC * sizeof(double)));
+        }
         CU(cudaMalloc(&ss.d_adv, 2 * ctx->C * sizeof(double)));
         CU(cudaMalloc(&ss.d_carr_trace, EC * sizeof(double)));
         CU(cudaEventCreateWithFlags(&ss.scan_done, cudaEventDisableTiming));
@@ -895,6 +962,7 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
         cudaFree(ss.d_descbuf); cudaFree(ss.d_lut); cudaFree(ss.d_lutp); cudaFree(ss.d_flags); cudaFree(ss.d_code_ck);
         cudaFree(ss.d_wrap_ck); cudaFree(ss.d_carr_ck); cudaFree(ss.d_tab); cudaFree(ss.d_drift); cudaFree(ss.d_spec);
         cudaFree(ss.d_specE); cudaFree(ss.d_cinfo); cudaFree(ss.d_info); cudaFree(ss.d_adv); cudaFree(ss.d_carr_trace);
+        cudaFree(ss.d_specG); cudaFree(ss.d_ginfo); cudaFree(ss.d_traceG);
         cudaEventDestroy(ss.scan_done); cudaEventDestroy(ss.render_done);
         cudaFree(ctx->d_recs[i]); cudaFree(ctx->d_fixmasks[i]); cudaFree(ctx->d_delta[i]); cudaFree(ctx->d_work[i]);
     }
@@ -978,8 +1046,15 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
         k_carr_stitch<<<(EC * 2 + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, est_epoch, ctx->d_spec, ctx->d_carr_ck,
                                                       ctx->ck_plane, ctx->d_cinfo, ctx->d_specE, n_epochs, C, N, T,
                                                       ntiles, ctx->G, ctx->J);
+        {
+            const int ngroups = (n_epochs + GROUP_EPOCHS - 1) / GROUP_EPOCHS;
+            k_carr_group<<<(ngroups * C * 2 + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_specE, est_epoch,
+                                                                   ctx->d_carr_ck, ctx->ck_plane, ctx->d_info, ECmax,
+                                                                   ctx->d_traceG, ctx->d_specG, ctx->d_fallbacks, n_epochs,
+                                                                   C, N, T, ntiles);
+        }
         k_est_fold<<<1, 32, 0, st>>>(ctx->d_est_state, ctx->d_adv, C);
-        ctx->launches += 4;
+        ctx->launches += 5;
     }
     ctx->sets[ctx->set_wr].phase = 2;
     CU(cudaGetLastError());
@@ -992,11 +1067,13 @@ static int enqueue_chain(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_
     const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
     use_set(ctx, ctx->set_wr);
     if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && ctx->cfg.reserved[0] == 0) {
-        k_carr_chain<<<C, 32, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_specE, ctx->d_carr_ck, ctx->ck_plane, ctx->d_carr_state,
-                                       ctx->d_carr_trace, ctx->d_info, ctx->d_fallbacks, n_epochs, C, N, T, ntiles);
+        k_carr_final<<<C, 32, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_specE, ctx->d_specG, ctx->d_carr_ck, ctx->ck_plane,
+                                       ctx->d_info, (size_t) ctx->E * C, ctx->d_traceG, ctx->d_carr_state, ctx->d_carr_trace,
+                                       ctx->d_ginfo, ctx->d_fallbacks, n_epochs, C, N, T, ntiles);
     } else {  // INT32 carrier (closed form) or the serial float scan (cfg.reserved[0] = 1, cross-check)
-        k_scan_carrier<<<C, 32, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_carr_ck + 4 * ctx->ck_plane, ctx->d_carr_state,
-                                         ctx->d_carr_trace, ctx->d_info, n_epochs, C, N, T, ntiles, ctx->cfg.carrier_mode);
+        k_scan_carrier<<<C, 32, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_carr_ck + 6 * ctx->ck_plane, ctx->d_carr_state,
+                                         ctx->d_carr_trace, ctx->d_info + 2 * (size_t) ctx->E * C, ctx->d_ginfo, GROUP_EPOCHS,
+                                         n_epochs, C, N, T, ntiles, ctx->cfg.carrier_mode);
     }
     ctx->launches += 1;
     CU(cudaMemcpyAsync(ctx->d_est_state, ctx->d_carr_state, C * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -1018,6 +1095,13 @@ static int enqueue_scan(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_e
 }
 
 // Phase 2: the per-sample synthesis from the checkpoints of the last scan.
+static CarrLookup make_lookup(const gpsiq_ctx* ctx) {
+    CarrLookup L;
+    L.ck = ctx->d_carr_ck; L.plane = ctx->ck_plane; L.ginfo = ctx->d_ginfo; L.infoG = ctx->d_info;
+    L.info_plane = (size_t) ctx->E * ctx->C; L.cinfo = ctx->d_cinfo; L.G = ctx->G; L.J = ctx->J; L.GP = GROUP_EPOCHS;
+    return L;
+}
+
 static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int16_t* iq_host = NULL) {
     if (ctx->set_pending < 1 || ctx->sets[ctx->set_rd].phase != 3)
         return fail(ctx, GPSIQ_ERR_ARG, "nothing to render (scan phases of a batch must complete first)", cudaSuccess);
@@ -1050,8 +1134,7 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
             CU(cudaMemsetAsync(ctx->d_delta[b], 0, (size_t) ne * ntiles * FX_TILE * sizeof(int32_t), ax));
             const int warps = ne * 2 * C * tgroups;
             k_tile_prologue<<<(warps + 3) / 4, 128, 0, ax>>>(desc_dev, ctx->d_tab, ctx->d_code_ck, ctx->d_wrap_ck,
-                                                             ctx->d_carr_ck, ctx->ck_plane, ctx->d_info, ctx->d_cinfo,
-                                                             ctx->G, ctx->J, ctx->d_flags, ctx->d_flags + ctx->E,
+                                                             make_lookup(ctx), ctx->d_flags, ctx->d_flags + ctx->E,
                                                              ctx->d_recs[b], ctx->d_fixmasks[b], ctx->d_work[b], nwork,
                                                              ctx->work_cap, e0, ne, C, N, ntiles);
             CU(cudaEventRecord(ctx->ev_P[b], ax));
@@ -1069,9 +1152,8 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
             ctx->last_fx.b = b; ctx->last_fx.set = ctx->set_cur;
             // epochs of this sub-batch outside the fixed-point kernel's contract
             k_synth_lanes<<<ne * tile_groups, LANES_WARPS * 32, smem, st>>>(
-                desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, ctx->d_carr_ck, ctx->ck_plane, ctx->d_info,
-                ctx->d_cinfo, ctx->G, ctx->J, ctx->d_ca, ctx->d_flags, ctx->d_flags + ctx->E, 1, iq_dev, e0, C, N, T, ntiles,
-                tile_groups, ctx->cfg.carrier_mode);
+                desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx), ctx->d_ca, ctx->d_flags,
+                ctx->d_flags + ctx->E, 1, iq_dev, e0, C, N, T, ntiles, tile_groups, ctx->cfg.carrier_mode);
             CU(cudaEventRecord(ctx->ev_F[b], st));
             ctx->launches += 4;
             if (iq_host) {  // ship the finished sub-batch while the next one renders
@@ -1084,9 +1166,8 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
         CU(cudaEventRecord(ctx->ev_P[0], ctx->aux_stream));   // join: the code scan must be complete
         CU(cudaStreamWaitEvent(st, ctx->ev_P[0], 0));
         k_synth_lanes<<<n_epochs * tile_groups, LANES_WARPS * 32, smem, st>>>(
-            desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, ctx->d_carr_ck, ctx->ck_plane, ctx->d_info, ctx->d_cinfo,
-            ctx->G, ctx->J, ctx->d_ca, ctx->d_flags, ctx->d_flags + ctx->E, 0, iq_dev, 0, C, N, T, ntiles, tile_groups,
-            ctx->cfg.carrier_mode);
+            desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx), ctx->d_ca, ctx->d_flags,
+            ctx->d_flags + ctx->E, 0, iq_dev, 0, C, N, T, ntiles, tile_groups, ctx->cfg.carrier_mode);
         ctx->launches += 1;
         if (iq_host)
             CU(cudaMemcpyAsync(iq_host, iq_dev, (size_t) n_epochs * N * 4, cudaMemcpyDeviceToHost, st));

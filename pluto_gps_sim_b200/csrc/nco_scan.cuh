@@ -471,44 +471,73 @@ struct CarrInfo {   // per (epoch, channel): how the renderer obtains tile-start
     int variant;    // speculative plane (0/1) for the translated tiles
 };
 
-// Exact carrier phase at the start of tile t of one (epoch, channel), composing the
-// three levels: chain result (info) -> stitched trajectory P -> chunk runs.
-// ck points at this (epoch, channel)'s entry of plane 0; `plane` elements per plane,
-// `stride` elements between consecutive tiles.  Planes: 0,1 chunk runs, 2,3 P, 4 exact.
-GPSIQ_HD double carr_tile_phase(const double* ck, size_t plane, size_t stride, int t, int T, int N, int G, int J,
-                                const CarrInfo& inf, const ChunkInfo* ci) {
-    const int n0 = t * T;
-    const size_t o = (size_t) t * stride;
-    if (n0 < inf.n1 || inf.n1 >= N) return ck[4 * plane + o];
-    const int V = inf.variant;
-    const ChunkInfo c = ci[V * J + t / G];
-    const double p = (n0 < c.n1) ? ck[(size_t) (2 + V) * plane + o] : add_rn(ck[(size_t) c.variant * plane + o], c.delta);
-    return add_rn(p, inf.delta);
+// ---- third level: groups of epochs ---------------------------------------------
+// After stitching, the only serial work is one head scan per epoch (chain_epoch).  For
+// long batches and for time-sliced multi-GPU runs even that is too much on the critical
+// path, so the same step is applied once more: the epochs of a GROUP are chained from an
+// ESTIMATED group start phase (all groups in parallel, group_chain_epoch with SPEC), which
+// yields a group-level speculative trajectory with its own first-wrap state and margin;
+// the final, truly serial chain then needs one head scan per GROUP.
+struct GroupTrack {   // running state of a group-level speculative chain
+    double margin;    // decision margin since the chain's first wrap
+    double xw1;       // state right after that wrap
+    int pos;          // its position: (epoch index within the group) * N + sample; -1: none yet
+    int usable;
+};
+
+struct GroupInfo {    // per (group, channel): result of the final chain
+    double delta;     // translation of the group trajectory onto the exact one
+    int pos;          // tiles at or after this (epoch-in-group * N + sample) are translated; earlier ones
+                      // read the exact plane.  0x7fffffff: the whole group was chained exactly (fallback)
+    int variant;
+};
+
+// Scan from x over the tiles of one epoch starting at tile t (remaining = samples left of a partially
+// scanned tile, or 0), writing the state at every tile start passed, until the first wrap or the epoch's
+// end.  TRACK: margin-track every decision.
+template <bool TRACK>
+GPSIQ_HD void scan_epoch_head(double& x, double d, const BinadeTab& tab, int N, int T, double* ck, size_t ck_stride,
+                              int& t, int& n, int& remaining, bool& wrapped, bool stop_at_wrap, double& margin) {
+    const int ntiles = (N + T - 1) / T;
+    wrapped = false;
+    for (;;) {
+        while (remaining > 0 && !(wrapped && stop_at_wrap)) {
+            bool w;
+            const int steps = carr_advance<TRACK>(x, d, tab, remaining, stop_at_wrap, w, margin);
+            remaining -= steps;
+            n += steps;
+            if (w) wrapped = true;
+        }
+        if ((wrapped && stop_at_wrap) || t >= ntiles) return;
+        ck[(size_t) t * ck_stride] = x;
+        remaining = (T < N - t * T) ? T : N - t * T;
+        t++;
+    }
 }
 
-// (3) exact chaining of one epoch from the exact start x; returns the exact end
-// state.  ck0 is plane 0 of the checkpoint array for this (epoch, channel).
-GPSIQ_HD double chain_epoch(double x, double d, const BinadeTab& tab, int N, int T, const CarrSpec& s0,
-                            const CarrSpec& s1, double* ck0, size_t ck_stride, CarrInfo& info, int& fell_back) {
-    const int ntiles = (N + T - 1) / T;
+// One epoch of a chain.  SPEC = false: the exact chain (this is chain_epoch).  SPEC = true: the chain is
+// itself speculative (started from an estimate): once it has wrapped, every decision is margin-tracked
+// into g, each epoch's own translation costs margin, and variant V flips the parity at the chain's
+// first wrap.  eg = index of the epoch within its group.
+template <bool SPEC>
+GPSIQ_HD double group_chain_epoch(double x, double d, const BinadeTab& tab, int N, int T, const CarrSpec& s0,
+                                  const CarrSpec& s1, double* ck0, size_t ck_stride, CarrInfo& info, int& fell_back,
+                                  GroupTrack* g, int V, int eg) {
     int n = 0, t = 0, remaining = 0;
     bool wrapped = false;
     double dummy = 1.0;
-    // exact head: up to and including the first wrap
-    for (; t < ntiles && !wrapped; t++) {
-        ck0[(size_t) t * ck_stride] = x;
-        remaining = (T < N - t * T) ? T : N - t * T;
-        while (remaining > 0 && !wrapped) {
-            const int steps = carr_advance<false>(x, d, tab, remaining, true, wrapped, dummy);
-            remaining -= steps;
-            n += steps;
-        }
-    }
+    if (SPEC && g->pos >= 0) scan_epoch_head<true>(x, d, tab, N, T, ck0, ck_stride, t, n, remaining, wrapped, true, g->margin);
+    else scan_epoch_head<false>(x, d, tab, N, T, ck0, ck_stride, t, n, remaining, wrapped, true, dummy);
     info.delta = 0.0;
     info.n1 = N;
     info.variant = 0;
     if (!wrapped) return x;  // the whole epoch was the head (low Doppler)
-    // try the translation
+    if (SPEC && g->pos < 0) {  // the chain's first wrap
+        if (V == 1) x = (x + 0x1p-53 < 1.0) ? x + 0x1p-53 : x - 0x1p-53;
+        if (!(x >= 0.0 && x < 1.0)) g->usable = 0;
+        g->pos = eg * N + n;
+        g->xw1 = x;
+    }
     {
         int v;
         double diff;
@@ -516,19 +545,152 @@ GPSIQ_HD double chain_epoch(double x, double d, const BinadeTab& tab, int N, int
             info.delta = diff;
             info.n1 = n;
             info.variant = v;
+            if (SPEC) {
+                const double m = (v ? s1.margin : s0.margin) - (diff < 0.0 ? -diff : diff);
+                if (m < g->margin) g->margin = m;
+            }
             return add_rn(v ? s1.xend : s0.xend, diff);
         }
     }
-    // fallback: finish the epoch serially, exact checkpoints for the remaining tiles
+    // the epoch's speculation does not fit: finish the epoch with the exact scan
     fell_back++;
-    bool w;
-    while (remaining > 0) remaining -= carr_advance<false>(x, d, tab, remaining, false, w, dummy);
-    for (; t < ntiles; t++) {
-        ck0[(size_t) t * ck_stride] = x;
-        remaining = (T < N - t * T) ? T : N - t * T;
-        while (remaining > 0) remaining -= carr_advance<false>(x, d, tab, remaining, false, w, dummy);
-    }
+    if (SPEC) scan_epoch_head<true>(x, d, tab, N, T, ck0, ck_stride, t, n, remaining, wrapped, false, g->margin);
+    else scan_epoch_head<false>(x, d, tab, N, T, ck0, ck_stride, t, n, remaining, wrapped, false, dummy);
     return x;
+}
+
+// Per-epoch inputs of the group-level chains, staged by the caller (shared memory on the device).
+struct GroupEpoch {
+    double d, phase0;
+    BinadeTab tab;
+    CarrSpec s0, s1;   // the epoch's stitched (epoch-level) speculation results, both variants
+    int active, reset;
+};
+
+// Level 3: speculative chain of one group of `count` epochs from x, an ESTIMATE of the phase at the
+// group's first sample.  Head tiles go to ckHead (plane 4+V), per-epoch results to info/trace.
+// outG.n1 holds the first-wrap position as (epoch-in-group * N + sample), count*N if the chain never wraps.
+GPSIQ_HD void group_chain(double x, const GroupEpoch* ge, int count, int N, int T, int V, double* ckHead,
+                          size_t tile_stride, size_t epoch_stride, CarrInfo* info, size_t info_stride, double* trace,
+                          size_t trace_stride, CarrSpec& outG, int& fb) {
+    GroupTrack g;
+    g.margin = 1.0; g.xw1 = 0.0; g.pos = -1; g.usable = 1;
+    for (int eg = 0; eg < count; eg++) {
+        CarrInfo inf;
+        inf.delta = 0.0; inf.n1 = N; inf.variant = 0;
+        if (ge[eg].active) {
+            if (ge[eg].reset) { g.usable = 0; x = ge[eg].phase0; }       // re-seeded inside the group: not translatable
+            if (!carr_step_speculable(ge[eg].d)) g.usable = 0;
+            x = group_chain_epoch<true>(x, ge[eg].d, ge[eg].tab, N, T, ge[eg].s0, ge[eg].s1,
+                                        ckHead + (size_t) eg * epoch_stride, tile_stride, inf, fb, &g, V, eg);
+        }
+        info[(size_t) eg * info_stride] = inf;
+        trace[(size_t) eg * trace_stride] = x;
+    }
+    outG.xw1 = g.xw1;
+    outG.xend = x;
+    outG.margin = (g.pos >= 0 && g.usable) ? g.margin : -1.0;
+    outG.n1 = g.pos < 0 ? count * N : g.pos;
+    outG.pad = 0;
+}
+
+// Level 4: the final, exact chain over one group from the exact phase x: one head scan up to the group's
+// first wrap, then the group trajectory translated -- or, if that does not fit, the rest chained exactly.
+// Exact head / fallback tiles go to ckX (plane 6).  Returns the exact phase after the group.
+GPSIQ_HD double group_final(double x, const GroupEpoch* ge, int count, int N, int T, const CarrSpec& sG0,
+                            const CarrSpec& sG1, double* ckX, size_t tile_stride, size_t epoch_stride, CarrInfo* infoX,
+                            size_t info_stride, const double* traceG0, const double* traceG1, double* trace,
+                            size_t trace_stride, GroupInfo& gi, int& fb) {
+    double dummy = 1.0;
+    CarrInfo all_exact;
+    all_exact.delta = 0.0; all_exact.n1 = N; all_exact.variant = 0;
+    for (int eg = 0; eg < count; eg++) {
+        infoX[(size_t) eg * info_stride] = all_exact;
+        if (!ge[eg].active) { trace[(size_t) eg * trace_stride] = x; continue; }
+        if (ge[eg].reset) x = ge[eg].phase0;
+        int t = 0, n = 0, remaining = 0;
+        bool wrapped = false;
+        double* ck = ckX + (size_t) eg * epoch_stride;
+        scan_epoch_head<false>(x, ge[eg].d, ge[eg].tab, N, T, ck, tile_stride, t, n, remaining, wrapped, true, dummy);
+        if (!wrapped) { trace[(size_t) eg * trace_stride] = x; continue; }
+        const int pos = eg * N + n;
+        int v;
+        double diff;
+        if (spec_match(x, pos, ge[eg].d, sG0, sG1, v, diff)) {
+            gi.delta = diff; gi.pos = pos; gi.variant = v;
+            const double* tg = v ? traceG1 : traceG0;
+            for (int e2 = eg; e2 < count; e2++) trace[(size_t) e2 * trace_stride] = add_rn(tg[(size_t) e2 * trace_stride], diff);
+            return add_rn(v ? sG1.xend : sG0.xend, diff);
+        }
+        // the group's speculation does not fit: chain the rest of the group exactly
+        fb++;
+        scan_epoch_head<false>(x, ge[eg].d, ge[eg].tab, N, T, ck, tile_stride, t, n, remaining, wrapped, false, dummy);
+        trace[(size_t) eg * trace_stride] = x;
+        for (int e2 = eg + 1; e2 < count; e2++) {
+            CarrInfo inf = all_exact;
+            if (ge[e2].active) {
+                if (ge[e2].reset) x = ge[e2].phase0;
+                x = group_chain_epoch<false>(x, ge[e2].d, ge[e2].tab, N, T, ge[e2].s0, ge[e2].s1,
+                                             ckX + (size_t) e2 * epoch_stride, tile_stride, inf, fb, nullptr, 0, 0);
+            }
+            infoX[(size_t) e2 * info_stride] = inf;
+            trace[(size_t) e2 * trace_stride] = x;
+        }
+        gi.delta = 0.0; gi.pos = 0x7fffffff; gi.variant = 0;
+        return x;
+    }
+    gi.delta = 0.0; gi.pos = count * N; gi.variant = 0;  // the group never wraps: every tile is in the exact plane
+    return x;
+}
+
+// Exact carrier phase at the start of tile t of epoch e (eg = its index within its group), composing the
+// four levels: final chain (gi) -> group chain (inf) -> stitched trajectory P -> chunk runs.
+// ck points at this (epoch, channel)'s entry of plane 0; `plane` elements per plane, `stride` elements
+// between consecutive tiles.  Planes: 0,1 chunk runs; 2,3 P; 4,5 group-chain heads (variants); 6 exact.
+// infG[0], infG[1]: the epoch's CarrInfo from the two group-chain variants; infX: from the exact fallback chain.
+GPSIQ_HD double carr_tile_phase(const double* ck, size_t plane, size_t stride, int t, int T, int N, int G, int J, int eg,
+                                const GroupInfo& gi, const CarrInfo& infG0, const CarrInfo& infG1, const CarrInfo& infX,
+                                const ChunkInfo* ci) {
+    const int n0 = t * T;
+    const size_t o = (size_t) t * stride;
+    const bool all_exact = gi.pos == 0x7fffffff;
+    if (!all_exact && eg * N + n0 < gi.pos) return ck[6 * plane + o];  // before the group's first wrap
+    const CarrInfo& inf = all_exact ? infX : (gi.variant ? infG1 : infG0);
+    const size_t headp = all_exact ? 6 : (size_t) (4 + gi.variant);
+    double p;
+    if (n0 < inf.n1 || inf.n1 >= N) {
+        p = ck[headp * plane + o];
+    } else {
+        const int V = inf.variant;
+        const ChunkInfo c = ci[V * J + t / G];
+        p = (n0 < c.n1) ? ck[(size_t) (2 + V) * plane + o] : add_rn(ck[(size_t) c.variant * plane + o], c.delta);
+        p = add_rn(p, inf.delta);
+    }
+    return all_exact ? p : add_rn(p, gi.delta);
+}
+
+// Everything a renderer needs to compose exact tile-start carrier phases (device pointers, one batch).
+struct CarrLookup {
+    const double* ck;        // [7][E][ntiles][C]
+    size_t plane;            // elements per plane
+    const GroupInfo* ginfo;  // [groups][C]
+    const CarrInfo* infoG;   // [3][Ecap][C]: group-chain variants 0, 1 and the exact fallback chain
+    size_t info_plane;       // Ecap * C
+    const ChunkInfo* cinfo;  // [E][C][2][J]
+    int G, J, GP;            // chunk length (tiles), chunks per epoch, epochs per group
+};
+
+GPSIQ_HD double carr_lookup(const CarrLookup& L, int e, int c, int t, int T, int N, int C, int ntiles) {
+    const size_t ec = (size_t) e * C + c;
+    return carr_tile_phase(L.ck + (size_t) e * ntiles * C + c, L.plane, (size_t) C, t, T, N, L.G, L.J, e % L.GP,
+                           L.ginfo[(size_t) (e / L.GP) * C + c], L.infoG[ec], L.infoG[L.info_plane + ec],
+                           L.infoG[2 * L.info_plane + ec], L.cinfo + ec * 2 * L.J);
+}
+
+// (3) exact chaining of one epoch from the exact start x; returns the exact end state.
+GPSIQ_HD double chain_epoch(double x, double d, const BinadeTab& tab, int N, int T, const CarrSpec& s0,
+                            const CarrSpec& s1, double* ck0, size_t ck_stride, CarrInfo& info, int& fell_back) {
+    return group_chain_epoch<false>(x, d, tab, N, T, s0, s1, ck0, ck_stride, info, fell_back, nullptr, 0, 0);
 }
 
 }  // namespace gpsiq

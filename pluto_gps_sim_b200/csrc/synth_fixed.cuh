@@ -167,8 +167,7 @@ __device__ __forceinline__ void fx_tile_walk(unsigned char* rec, uint32_t* fixma
 __global__ void __launch_bounds__(128)
 k_tile_prologue(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
                 const double* __restrict__ code_ck, const int* __restrict__ wrap_ck,
-                const double* __restrict__ carr_ck, size_t ck_plane, const CarrInfo* __restrict__ info,
-                const ChunkInfo* __restrict__ cinfo, int G, int J,
+                const CarrLookup carr,
                 const int* __restrict__ amp_sum, int* __restrict__ step_flag, unsigned char* __restrict__ recs,
                 uint32_t* __restrict__ fixmasks, uint32_t* __restrict__ work, int* __restrict__ nwork, int work_cap,
                 int e0, int E, int C, int N, int ntiles) {
@@ -200,8 +199,7 @@ k_tile_prologue(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __res
     const size_t o = ((size_t) e * ntiles + t) * C + c;
     int overflow = 0;
     if (task & 1) {
-        const double ph = carr_tile_phase(carr_ck + (size_t) e * ntiles * C + c, ck_plane, (size_t) C, t, FX_TILE, N, G, J,
-                                          info[(size_t) e * C + c], cinfo + ((size_t) e * C + c) * 2 * J);
+        const double ph = carr_lookup(carr, e, c, t, FX_TILE, N, C, ntiles);
         fx_tile_walk<NCO_CARRIER>(rec, fixmask, work, nwork, work_cap, (uint32_t) tile_id, C, c, s_tab[warp], ph,
                                   d.carr_step, len, 0, 0, 0, &overflow);
     } else {
