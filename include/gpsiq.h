@@ -50,6 +50,7 @@ extern "C" {
 #define GPSIQ_KERNEL_AUTO 0
 #define GPSIQ_KERNEL_LANE_PER_CHANNEL 1 /* warp = sample tile, lane = channel, true FP64 steps */
 #define GPSIQ_KERNEL_FIXED_POINT 2      /* thread = sample run, integer NCO segments */
+#define GPSIQ_KERNEL_LINE 3             /* one fixed-point line per 1024-sample tile + exact safety check (AUTO picks it) */
 
 #define GPSIQ_MAX_CHAN 32
 #define GPSIQ_CA_LEN 1023
@@ -81,7 +82,9 @@ typedef struct gpsiq_config {
     int32_t max_epochs;        /* capacity of one gpsiq_synth call */
     int32_t tile_samples;      /* 0 = default; checkpoint / CTA tile length */
     int32_t kernel;            /* GPSIQ_KERNEL_* */
-    int32_t reserved[9];       /* reserved[0]: 1 = serial carrier scan (cross-check of the parallel one); rest 0 */
+    int32_t reserved[9];       /* reserved[0]: 1 = serial carrier scan (cross-check of the parallel one);
+                                  reserved[1]: test hooks of the line kernel (1 force chunk re-check, 2 force every
+                                  tile through the literal-recurrence patch path, 4 perturb the anchors); rest 0 */
 } gpsiq_config;
 
 typedef struct gpsiq_ctx gpsiq_ctx;
@@ -219,6 +222,17 @@ int gpsiq_timing_sample_kernel(gpsiq_ctx *ctx, int *n_launches, float *kernel_ms
  * kernel shares the SMs with the scan kernels of the next batch, so its in-pipeline duration says
  * little about the kernel itself. */
 int gpsiq_timing_sample_kernel_isolated(gpsiq_ctx *ctx, int reps, float *kernel_ms, int *epochs_per_launch);
+
+/* Line kernel diagnostics, accumulated over the context's life: (tile, slot) pairs that had to be
+ * re-checked with the literal recurrence, samples patched, 32-tile chunks flagged by the first-level check. */
+int gpsiq_line_stats(gpsiq_ctx *ctx, int64_t *hazard_tiles, int64_t *patches, int64_t *flagged_chunks);
+/* Host execution of the safety check's arithmetic (tests):
+ * gpsiq_minmod_host: min over x in [0,n) of (b + a*x) mod m (may return any attained value < stop early).
+ * gpsiq_line_probe_host: run the literal NCO recurrence (plutogpssim.c:2709-2713 / 2741-2746) for n samples
+ * from x0 next to the straight fixed-point line the line kernel would use; reports the largest deviation
+ * (line units), the number of samples whose table/chip index differs, and whether the check flags the run. */
+uint64_t gpsiq_minmod_host(uint64_t b, uint64_t a, uint64_t m, uint64_t n, uint64_t stop);
+int gpsiq_line_probe_host(int mode, double x0, double step, int n, int64_t *max_dev, int *mismatches, int *hazard);
 
 const char *gpsiq_strerror(int status);
 const char *gpsiq_last_error(const gpsiq_ctx *ctx);

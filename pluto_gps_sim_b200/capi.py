@@ -16,7 +16,8 @@ OK = 0
 ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_CAPACITY = -1, -2, -3, -4
 CARRIER_FLOAT, CARRIER_INT32 = 0, 1
 FLAG_RESET_CARRIER = 1
-KERNEL_AUTO, KERNEL_LANE_PER_CHANNEL, KERNEL_FIXED_POINT = 0, 1, 2
+KERNEL_AUTO, KERNEL_LANE_PER_CHANNEL, KERNEL_FIXED_POINT, KERNEL_LINE = 0, 1, 2, 3
+LINE_DBG_FORCE_CHUNK, LINE_DBG_FORCE_TILE, LINE_DBG_PERTURB = 1, 2, 4
 MAX_CHAN = 32
 NCO_CODE, NCO_CARRIER = 0, 1
 
@@ -88,6 +89,9 @@ SYMBOLS = {
     "gpsiq_render_device": (_i, [_vp, _vp, _i, _vp, _vp]),
     "gpsiq_carrier_to_device": (_i, [_vp, _vp, _vp]),
     "gpsiq_carrier_from_device": (_i, [_vp, _vp, _vp]),
+    "gpsiq_line_stats": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "gpsiq_minmod_host": (C.c_uint64, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "gpsiq_line_probe_host": (_i, [_i, _d, _d, _i, C.POINTER(_i64), C.POINTER(_i), C.POINTER(_i)]),
     "gpsiq_strerror": (C.c_char_p, [_i]),
     "gpsiq_last_error": (C.c_char_p, [_vp]),
     "gpsiq_version": (C.c_char_p, []),
@@ -148,6 +152,18 @@ def nco_advance(mode, phase, step, count):
     w = _i64(0)
     check(lib.gpsiq_nco_advance(int(mode), C.byref(x), float(step), int(count), C.byref(w)))
     return x.value, w.value
+
+
+def minmod(b, a, m, n, stop=0):
+    """min over x in [0, n) of (b + a*x) mod m, as the safety check of the line kernel computes it (host run)."""
+    return int(lib.gpsiq_minmod_host(int(b), int(a), int(m), int(n), int(stop)))
+
+
+def line_probe(mode, x0, step, n):
+    """Literal recurrence vs the line kernel's straight line -> (max deviation, index mismatches, hazard flagged)."""
+    dev, mm, hz = _i64(0), _i(0), _i(0)
+    check(lib.gpsiq_line_probe_host(int(mode), float(x0), float(step), int(n), C.byref(dev), C.byref(mm), C.byref(hz)))
+    return dev.value, mm.value, bool(hz.value)
 
 
 def carrier_chain_host(steps, N, T, x0, est_err=0.0):

@@ -27,6 +27,7 @@
 #include "../../include/gpsiq.h"
 #include "nco_scan.cuh"
 #include "synth_fixed.cuh"
+#include "synth_line.cuh"
 
 using namespace gpsiq;
 
@@ -94,6 +95,7 @@ struct gpsiq_ctx {
     cudaStream_t scan_stream;         // gpsiq_submit_device scans here, ahead of the caller's render stream
     cudaStream_t aux2_stream;         // its code-NCO scan (aux_stream is busy with the tile prologues of the batch being rendered)
     int C, N, T, ntiles, E;
+    int sm_count;
     cudaStream_t stream;
     cudaStream_t copy_stream;        // device-to-host copies of finished sub-batches overlap the rendering of the next
     cudaEvent_t ev_sub[2];
@@ -110,6 +112,15 @@ struct gpsiq_ctx {
     int8_t* d_chips;      // [33][2048] +-1, index = polarity << 10 | chip
     int* d_flags;         // [2][E]: amplitude sum per epoch, step-contract flag per epoch
     int use_fixed;        // k_synth_fixed is eligible for this configuration
+    int use_line;         // k_synth_line (the production kernel) is eligible for this configuration
+    int8_t* d_chips4;     // [33][4][LN_VS] +-1: chip/NAV sign tables in 4 polarity variants, extended past chip 1022
+    ulonglong2* d_anch[2];   // [E][ntiles][C] tile anchors {F, G} (one buffer per scan set)
+    uint32_t* d_hazlist;  // (tile, slot) pairs k_line_anchor could not clear
+    int haz_cap, patch_cap;
+    int* d_line_counters; // [0] listed hazards, [1] patches, [2] flagged chunks (per batch)
+    unsigned long long* d_line_totals;  // the same, accumulated over the context's life
+    LinePatch* d_patches;
+    struct { const gpsiq_chan_desc* desc; int16_t* iq; int ne, set, e0; } last_ln;  // last k_synth_line launch
     // per sub-batch scratch, double buffered: the prologue of sub-batch k+1 overlaps the sample kernels of k
     unsigned char* d_recs[2]; // [FX_SUB_EPOCHS][ntiles] tile records (synth_fixed.cuh)
     uint32_t* d_fixmasks[2];  // [FX_SUB_EPOCHS][ntiles][C][4] (+ the work-list counter behind it)
@@ -831,6 +842,7 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
     ctx = (gpsiq_ctx*) calloc(1, sizeof *ctx);
     if (!ctx) return GPSIQ_ERR_NOMEM;
     ctx->cfg = *cfg;
+    ctx->sm_count = prop.multiProcessorCount;
     ctx->C = cfg->max_chan;
     ctx->N = cfg->samples_per_epoch;
     ctx->E = cfg->max_epochs;
@@ -839,6 +851,12 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
     // the fixed-point kernel needs its own tile length, 16-byte aligned epochs, the float carrier and <= FX_MAXC slots
     ctx->use_fixed = (cfg->kernel != GPSIQ_KERNEL_LANE_PER_CHANNEL) && ctx->T == FX_TILE && (ctx->N % 4 == 0) &&
                      ctx->C <= FX_MAXC && cfg->carrier_mode == GPSIQ_CARRIER_FLOAT;
+    ctx->use_line = (cfg->kernel == GPSIQ_KERNEL_AUTO || cfg->kernel == GPSIQ_KERNEL_LINE) && ctx->T == LN_TILE &&
+                    ctx->C <= 32 && cfg->carrier_mode == GPSIQ_CARRIER_FLOAT;
+    if (cfg->kernel == GPSIQ_KERNEL_LINE && !ctx->use_line)
+        return fail(NULL, GPSIQ_ERR_ARG, "gpsiq_create: the line kernel needs tile_samples 0/1024, max_chan <= 32 and the float carrier",
+                    cudaSuccess);
+    if (ctx->use_line) ctx->use_fixed = 0;
     if (cfg->kernel == GPSIQ_KERNEL_FIXED_POINT && !ctx->use_fixed)
         return fail(NULL, GPSIQ_ERR_ARG, "gpsiq_create: fixed-point kernel needs tile_samples 0/1024, samples_per_epoch % 4 == 0, "
                     "max_chan <= 32 and the float carrier", cudaSuccess);
@@ -944,6 +962,38 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
             CU(cudaMalloc(&ctx->d_work[i], (size_t) ctx->work_cap * 4));
         }
     }
+    if (ctx->use_line) {
+        CU(cudaFuncSetAttribute(k_synth_line, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ln_smem_bytes(ctx->C)));
+        const size_t tiles = (size_t) ctx->E * ctx->ntiles;
+        for (int i = 0; i < 2; i++) CU(cudaMalloc(&ctx->d_anch[i], tiles * ctx->C * sizeof(ulonglong2)));
+        const int dbg = cfg->reserved[1];
+        ctx->haz_cap = (dbg & LN_DBG_FORCE_TILE) ? (int) (tiles * ctx->C) : (int) (tiles * ctx->C / 64 + 1024);
+        ctx->patch_cap = 1 << 20;
+        CU(cudaMalloc(&ctx->d_hazlist, (size_t) ctx->haz_cap * 4));
+        CU(cudaMalloc(&ctx->d_patches, (size_t) ctx->patch_cap * sizeof(LinePatch)));
+        CU(cudaMalloc(&ctx->d_line_counters, 4 * sizeof(int)));
+        CU(cudaMalloc(&ctx->d_line_totals, 4 * sizeof(unsigned long long)));
+        CU(cudaMemset(ctx->d_line_totals, 0, 4 * sizeof(unsigned long long)));
+        // chip/NAV sign tables: variant v = pol0*2 + pol1; entry k < 1023: chip k under NAV bit pol0,
+        // k >= 1023: chip k-1023 of the NEXT code period under NAV bit pol1.  +1 iff NAV bit == chip
+        // (plutogpssim.c:2701, 2732, 2737)
+        int8_t* h4 = (int8_t*) malloc((size_t) 33 * 4 * LN_VS);
+        if (!h4) return GPSIQ_ERR_NOMEM;
+        memset(h4, 1, (size_t) 33 * 4 * LN_VS);
+        for (int prn = 1; prn <= 32; prn++) {
+            uint8_t chips[GPSIQ_CA_LEN];
+            ca_generate(prn, chips);
+            for (int v = 0; v < 4; v++)
+                for (int k = 0; k < LN_VS; k++) {
+                    const int pol = (k < GPSIQ_CA_LEN) ? (v >> 1) : (v & 1);
+                    h4[((size_t) prn * 4 + v) * LN_VS + k] = (chips[k % GPSIQ_CA_LEN] == pol) ? 1 : -1;
+                }
+        }
+        CU(cudaMalloc(&ctx->d_chips4, (size_t) 33 * 4 * LN_VS));
+        cudaError_t ce3 = cudaMemcpy(ctx->d_chips4, h4, (size_t) 33 * 4 * LN_VS, cudaMemcpyHostToDevice);
+        free(h4);
+        CU(ce3);
+    }
     const size_t smem_lanes = (size_t) ctx->C * 512 * sizeof(int2) + (size_t) ctx->C * 33 * 4;
     CU(cudaFuncSetAttribute(k_synth_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_lanes));
     *out = ctx;
@@ -966,6 +1016,8 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
         cudaEventDestroy(ss.scan_done); cudaEventDestroy(ss.render_done);
         cudaFree(ctx->d_recs[i]); cudaFree(ctx->d_fixmasks[i]); cudaFree(ctx->d_delta[i]); cudaFree(ctx->d_work[i]);
     }
+    cudaFree(ctx->d_chips4); cudaFree(ctx->d_anch[0]); cudaFree(ctx->d_anch[1]); cudaFree(ctx->d_hazlist);
+    cudaFree(ctx->d_patches); cudaFree(ctx->d_line_counters); cudaFree(ctx->d_line_totals);
     cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_est_state); cudaFree(ctx->d_ca);
     cudaFree(ctx->d_iq); cudaFree(ctx->d_iq2); cudaFree(ctx->d_sums); cudaFree(ctx->d_err);
     if (ctx->h_stage[0]) cudaFreeHost(ctx->h_stage[0]);
@@ -1117,7 +1169,53 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
     // everything below needs the chain's result; the aux stream (already holding the code scan) joins here
     CU(cudaEventRecord(ctx->ev_chain, st));
     CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_chain, 0));
-    if (ctx->use_fixed) {
+    if (ctx->use_line) {
+        const int dbg = ctx->cfg.reserved[1];
+        ulonglong2* anch = ctx->d_anch[ctx->set_cur];
+        CU(cudaMemsetAsync(ctx->d_line_counters, 0, 4 * sizeof(int), st));
+        const int chunks = (ntiles + LN_CHUNK - 1) / LN_CHUNK;
+        const int warps = n_epochs * C * chunks;
+        k_line_anchor<<<(warps + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx),
+                                                       ctx->d_flags, ctx->d_flags + ctx->E, anch, ctx->d_hazlist,
+                                                       ctx->d_line_counters, ctx->haz_cap, n_epochs, C, N, ntiles, dbg);
+        // the (tile, slot) pairs the check could not clear: literal recurrence, compared with the anchors' lines
+        k_line_patch<<<(dbg & LN_DBG_FORCE_TILE) ? 1024 : 8, 128, 0, st>>>(
+            desc_dev, ctx->d_lutp, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx), anch, ctx->d_chips4, ctx->d_hazlist,
+            ctx->d_line_counters, ctx->haz_cap, ctx->d_patches, ctx->patch_cap, ctx->d_flags + ctx->E, C, N, ntiles);
+        ctx->launches += 2;
+        // device-resident output: one launch; host output: sub-batches so that the copies overlap the rendering
+        const int sub = iq_host ? 32 : n_epochs;
+        int k = 0;
+        for (int e0 = 0; e0 < n_epochs; e0 += sub, k++) {
+            const int ne = n_epochs - e0 < sub ? n_epochs - e0 : sub;
+            const long long tiles = (long long) ne * ntiles;
+            const int grid = (int) (tiles < 2LL * ctx->sm_count ? tiles : 2LL * ctx->sm_count);
+            const bool timed = (k == 0 && ctx->ev_count < TIMING_RING);
+            if (timed) { CU(cudaEventRecord(ctx->ev[ctx->ev_count][3], st)); ctx->fixed_epochs = ne; }
+            k_synth_line<<<grid, LN_THREADS, ln_smem_bytes(C), st>>>(
+                desc_dev + (size_t) e0 * C, ctx->d_lutp + (size_t) e0 * C * 512, ctx->d_chips4,
+                anch + (size_t) e0 * ntiles * C, ctx->d_flags + e0, ctx->d_flags + ctx->E + e0,
+                iq_dev + (size_t) e0 * N * 2, ne, C, N, ntiles, ctx->d_err);
+            if (timed) CU(cudaEventRecord(ctx->ev[ctx->ev_count][4], st));
+            ctx->last_ln.desc = desc_dev + (size_t) e0 * C; ctx->last_ln.iq = iq_dev + (size_t) e0 * N * 2;
+            ctx->last_ln.ne = ne; ctx->last_ln.set = ctx->set_cur;
+            ctx->last_ln.e0 = e0;
+            k_line_apply<<<4, 128, 0, st>>>(ctx->d_patches, ctx->d_line_counters, ctx->patch_cap,
+                                            reinterpret_cast<uint32_t*>(iq_dev), (unsigned long long) e0 * N,
+                                            (unsigned long long) (e0 + ne) * N, e0 == 0 ? ctx->d_line_totals : NULL);
+            // epochs outside the line kernel's contract (or whose hazard / patch lists overflowed)
+            k_synth_lanes<<<ne * tile_groups, LANES_WARPS * 32, smem, st>>>(
+                desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx), ctx->d_ca, ctx->d_flags,
+                ctx->d_flags + ctx->E, 1, iq_dev, e0, C, N, T, ntiles, tile_groups, ctx->cfg.carrier_mode);
+            ctx->launches += 3;
+            if (iq_host) {
+                CU(cudaEventRecord(ctx->ev_F[k & 1], st));
+                CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_F[k & 1], 0));
+                CU(cudaMemcpyAsync(iq_host + (size_t) e0 * N * 2, iq_dev + (size_t) e0 * N * 2, (size_t) ne * N * 4,
+                                   cudaMemcpyDeviceToHost, ctx->copy_stream));
+            }
+        }
+    } else if (ctx->use_fixed) {
         const int groups = (ntiles + FX_TILES_PER_CTA - 1) / FX_TILES_PER_CTA;
         const int tgroups = (ntiles + 31) / 32;
         cudaStream_t ax = ctx->aux_stream;
@@ -1441,18 +1539,30 @@ int gpsiq_timing_collect(gpsiq_ctx* ctx, int* n_steps, float* scan_ms, float* sy
 // `reps` times back to back on an otherwise idle device and return the mean duration: the kernel ALONE.
 int gpsiq_timing_sample_kernel_isolated(gpsiq_ctx* ctx, int reps, float* kernel_ms, int* epochs_per_launch) {
     if (!ctx || reps < 1 || !kernel_ms) return GPSIQ_ERR_ARG;
-    if (!ctx->use_fixed || !ctx->last_fx.desc) return fail(ctx, GPSIQ_ERR_ARG, "no k_synth_fixed launch to repeat", cudaSuccess);
+    const bool line = ctx->use_line && ctx->last_ln.desc;
+    if (!line && (!ctx->use_fixed || !ctx->last_fx.desc))
+        return fail(ctx, GPSIQ_ERR_ARG, "no k_synth_line / k_synth_fixed launch to repeat", cudaSuccess);
     CU(cudaSetDevice(ctx->cfg.device));
     CU(cudaDeviceSynchronize());
-    use_set(ctx, ctx->last_fx.set);
+    use_set(ctx, line ? ctx->last_ln.set : ctx->last_fx.set);
     const int C = ctx->C, N = ctx->N, ntiles = ctx->ntiles, b = ctx->last_fx.b;
     const int groups = (ntiles + FX_TILES_PER_CTA - 1) / FX_TILES_PER_CTA;
     cudaEvent_t e0 = ctx->ev[TIMING_RING - 1][3], e1 = ctx->ev[TIMING_RING - 1][4];
     for (int i = 0; i < reps + 1; i++) {  // first launch is a warm-up
         if (i == 1) CU(cudaEventRecord(e0, ctx->stream));
-        k_synth_fixed<<<ctx->last_fx.ne * groups, FX_WORKERS * FX_THREADS, fx_smem_bytes(C), ctx->stream>>>(
-            ctx->last_fx.desc, ctx->d_lutp, ctx->d_tab, ctx->d_recs[b], ctx->d_delta[b], ctx->d_chips, ctx->d_flags,
-            ctx->d_flags + ctx->E, ctx->last_fx.iq, ctx->last_fx.e0, C, N, ntiles, groups);
+        if (line) {
+            const int ne = ctx->last_ln.ne, le0 = ctx->last_ln.e0;
+            const long long tiles = (long long) ne * ntiles;
+            const int grid = (int) (tiles < 2LL * ctx->sm_count ? tiles : 2LL * ctx->sm_count);
+            k_synth_line<<<grid, LN_THREADS, ln_smem_bytes(C), ctx->stream>>>(
+                ctx->last_ln.desc, ctx->d_lutp + (size_t) le0 * C * 512, ctx->d_chips4,
+                ctx->d_anch[ctx->last_ln.set] + (size_t) le0 * ntiles * C, ctx->d_flags + le0, ctx->d_flags + ctx->E + le0,
+                ctx->last_ln.iq, ne, C, N, ntiles, ctx->d_err);
+        } else {
+            k_synth_fixed<<<ctx->last_fx.ne * groups, FX_WORKERS * FX_THREADS, fx_smem_bytes(C), ctx->stream>>>(
+                ctx->last_fx.desc, ctx->d_lutp, ctx->d_tab, ctx->d_recs[b], ctx->d_delta[b], ctx->d_chips, ctx->d_flags,
+                ctx->d_flags + ctx->E, ctx->last_fx.iq, ctx->last_fx.e0, C, N, ntiles, groups);
+        }
     }
     CU(cudaEventRecord(e1, ctx->stream));
     CU(cudaEventSynchronize(e1));
@@ -1460,7 +1570,7 @@ int gpsiq_timing_sample_kernel_isolated(gpsiq_ctx* ctx, int reps, float* kernel_
     CU(cudaEventElapsedTime(&t, e0, e1));
     ctx->launches += reps + 1;
     *kernel_ms = t / reps;
-    if (epochs_per_launch) *epochs_per_launch = ctx->last_fx.ne;
+    if (epochs_per_launch) *epochs_per_launch = line ? ctx->last_ln.ne : ctx->last_fx.ne;
     return GPSIQ_OK;
 }
 
@@ -1469,7 +1579,7 @@ int gpsiq_timing_sample_kernel(gpsiq_ctx* ctx, int* n_launches, float* kernel_ms
     CU(cudaSetDevice(ctx->cfg.device));
     float a = 0.f;
     int n = 0;
-    if (ctx->use_fixed)
+    if (ctx->use_fixed || ctx->use_line)
         for (int i = 0; i < ctx->ev_count; i++) {
             float t = 0.f;
             CU(cudaEventSynchronize(ctx->ev[i][4]));
@@ -1480,6 +1590,51 @@ int gpsiq_timing_sample_kernel(gpsiq_ctx* ctx, int* n_launches, float* kernel_ms
     if (n_launches) *n_launches = n;
     if (kernel_ms) *kernel_ms = a;
     if (epochs_per_launch) *epochs_per_launch = ctx->fixed_epochs;
+    return GPSIQ_OK;
+}
+
+int gpsiq_line_stats(gpsiq_ctx* ctx, int64_t* hazard_tiles, int64_t* patches, int64_t* flagged_chunks) {
+    if (!ctx) return GPSIQ_ERR_ARG;
+    unsigned long long h[4] = {0, 0, 0, 0};
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaDeviceSynchronize());
+    if (ctx->use_line) CU(cudaMemcpy(h, ctx->d_line_totals, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (hazard_tiles) *hazard_tiles = (int64_t) h[0];
+    if (patches) *patches = (int64_t) h[1];
+    if (flagged_chunks) *flagged_chunks = (int64_t) h[2];
+    return GPSIQ_OK;
+}
+
+uint64_t gpsiq_minmod_host(uint64_t b, uint64_t a, uint64_t m, uint64_t n, uint64_t stop) {
+    return minmod(b, a, m, n, stop);
+}
+
+int gpsiq_line_probe_host(int mode, double x0, double step, int n, int64_t* max_dev, int* mismatches, int* hazard) {
+    if ((mode != NCO_CODE && mode != NCO_CARRIER) || n < 1 || n > (1 << 20)) return GPSIQ_ERR_ARG;
+    const int B = (mode == NCO_CARRIER) ? LN_FBITS : LN_GBITS;
+    const uint64_t A = (mode == NCO_CARRIER) ? ln_carr_fixed(x0) : ln_code_fixed(x0);
+    const uint64_t d = (mode == NCO_CARRIER) ? ln_carr_slope(step) : ln_code_slope(step);
+    double x = x0;
+    uint64_t L = A;
+    int wraps = 0, mism = 0;
+    int64_t dev = 0;
+    for (int i = 0; i < n; i++) {
+        // truth in the line's coordinates: carrier mod 2^64, code unwrapped by 1023 chips per wrap
+        const uint64_t T = (mode == NCO_CARRIER) ? ln_carr_fixed(x)
+                                                 : ln_code_fixed(x) + (((uint64_t) wraps * 1023u) << LN_GBITS);
+        int64_t dv = (int64_t) (T - L);
+        if (mode == NCO_CARRIER && x == 1.0) dv = (int64_t) (0 - L);  // 1.0 saturates to 2^64 - 1: compare with 2^64
+        if (dv < 0) dv = -dv;
+        if (dv > dev) dev = dv;
+        if ((T >> B) != (L >> B)) mism++;
+        L += d;
+        if (mode == NCO_CARRIER) nco_step<NCO_CARRIER>(x, step, wraps);
+        else nco_step<NCO_CODE>(x, step, wraps);
+    }
+    const int64_t eps = ln_eps(mode == NCO_CARRIER, n);
+    if (max_dev) *max_dev = dev;
+    if (mismatches) *mismatches = mism;
+    if (hazard) *hazard = line_hazard(A, d, B, (uint64_t) n, -eps, eps) ? 1 : 0;
     return GPSIQ_OK;
 }
 

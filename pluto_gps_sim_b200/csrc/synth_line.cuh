@@ -1,0 +1,323 @@
+// synth_line.cuh — k_synth_line: the production synthesis kernel (plutogpssim.c:2689-2756),
+// with k_line_anchor (tile anchors + safety check) before and k_line_patch / k_line_apply after it.
+//
+// Per channel and sample the main kernel does exactly: two 64-bit adds (the two NCO lines), two
+// shifts (carrier table index, plutogpssim.c:2697; chip index, plutogpssim.c:2737), two shared-memory
+// loads (amplitude LUT entry = (int)(cos|sin * gain) of plutogpssim.c:2701-2702 packed as Q<<16 + I;
+// chip/NAV sign as a +-1 byte) and one multiply-add into the packed accumulator
+// (plutogpssim.c:2705-2706).  No branch, no per-run state, no correction array: see line_check.cuh
+// for why a straight line per 1024-sample tile is exact once k_line_anchor has cleared the tile.
+//
+//   tile        1024 samples; anchor = exact NCO states at its first sample (from the scan phases)
+//   warp-block  256 samples: lane l renders samples l, l+32, ..., l+224 of the block, so the 32 lanes
+//               of one shared-memory request touch <= 32 consecutive LUT entries (no bank conflict)
+//               and <= 16 consecutive chip bytes (broadcast), and every store instruction of a warp
+//               writes 128 contiguous bytes
+//   CTA         512 threads, persistent: a contiguous range of the batch's tiles; tables of the
+//               current epoch resident in shared memory: per slot the 512-entry amplitude LUT and the
+//               chip-sign table in 4 variants (NAV polarity before / after the one code-period wrap a
+//               tile can contain, plutogpssim.c:2710-2733), extended past chip 1022 so that the code
+//               line never has to wrap inside a tile
+//   chip index  the high bits of G hold the shared-memory byte address of the slot's table + variant
+//               offset + chip, so the load needs no address arithmetic
+// More than LN_CG slots: the CTA makes one pass per channel group over its range and keeps the raw
+// packed sums in the output buffer between passes.
+#pragma once
+
+#include "line_check.cuh"
+
+#define LN_RUN 8
+#define LN_WB (32 * LN_RUN)       // samples per warp-block
+#define LN_TILE 1024
+#define LN_THREADS 512
+#define LN_WARPS (LN_THREADS / 32)
+#define LN_CG 12                  // slots resident at a time
+#define LN_VS 1536                // chip-sign entries per variant: 1023 + 512 (code_step <= 0.5) + 1
+#define LN_CHUNK 32               // tiles per hazard chunk (= lanes)
+
+#define LN_DBG_FORCE_CHUNK 1      // cfg.reserved[1] bits (tests): treat every chunk as flagged,
+#define LN_DBG_FORCE_TILE 2       //   every tile as a hazard (all samples re-checked by k_line_patch),
+#define LN_DBG_PERTURB 4          //   and shift the anchors the main kernel uses (patches must repair it)
+
+namespace gpsiq {
+
+struct LinePatch { uint32_t sample; int32_t delta; };  // batch-relative sample index, packed (right - wrong)
+
+__host__ __device__ inline int ln_groups(int C) { return (C + LN_CG - 1) / LN_CG; }
+__host__ __device__ inline int ln_group_slots(int C) { const int g = ln_groups(C); return (C + g - 1) / g; }
+__host__ __device__ inline size_t ln_smem_bytes(int C) {
+    const int CG = ln_group_slots(C);
+    return (size_t) CG * 4 * LN_VS + (size_t) CG * 2048 + 16 * 16 /* steps */ + LN_WARPS * 16 * 16 /* anchors */ + 64;
+}
+
+// ---- k_line_anchor ---------------------------------------------------------------
+// One warp per (epoch, slot, chunk of 32 tiles), lane = tile.  Writes the tile anchors
+//   anch[(e*ntiles + t)*C + c] = { F (carrier), G (code) + variant offset }
+// and appends every (tile, slot) that the line model cannot be proven exact for to hazlist.
+__global__ void __launch_bounds__(128)
+k_line_anchor(const gpsiq_chan_desc* __restrict__ desc, const double* __restrict__ code_ck,
+              const int* __restrict__ wrap_ck, const CarrLookup carr, const int* __restrict__ amp_sum,
+              int* __restrict__ step_flag, ulonglong2* __restrict__ anch, uint32_t* __restrict__ hazlist,
+              int* __restrict__ counters, int haz_cap, int E, int C, int N, int ntiles, int dbg) {
+    const int lane = threadIdx.x & 31;
+    const int chunks = (ntiles + LN_CHUNK - 1) / LN_CHUNK;
+    int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int ch = w % chunks; w /= chunks;
+    const int c = w % C;
+    const int e = w / C;
+    if (e >= E) return;
+    const gpsiq_chan_desc d = desc[(size_t) e * C + c];
+    const int t = ch * LN_CHUNK + lane;
+    const bool valid = t < ntiles;
+    const size_t o = ((size_t) e * ntiles + (valid ? t : 0)) * C + c;
+    if (d.prn <= 0 || amp_sum[e] > 32767 || step_flag[e]) {  // inactive slot / epoch rendered by k_synth_lanes
+        if (valid) anch[o] = make_ulonglong2(0, 0);
+        return;
+    }
+    const uint64_t dF = ln_carr_slope(d.carr_step), dG = ln_code_slope(d.code_step);
+    uint64_t FA = 0, GA = 0;
+    if (valid) {
+        FA = ln_carr_fixed(carr_lookup(carr, e, c, t, LN_TILE, N, C, ntiles));
+        GA = ln_code_fixed(code_ck[o]);
+        // NAV polarity at the tile start and after the next code-period wrap (plutogpssim.c:2714-2733)
+        const int wr = wrap_ck[o] + d.ms0 % 20;
+        const uint32_t pol0 = (uint32_t) (d.navbits >> ((wr / 20) & 63)) & 1u;
+        const uint32_t pol1 = (uint32_t) (d.navbits >> (((wr + 1) / 20) & 63)) & 1u;
+        uint64_t Fs = FA, Gs = GA + ((uint64_t) ((pol0 * 2 + pol1) * LN_VS) << LN_GBITS);
+        if (dbg & LN_DBG_PERTURB) { Fs += (uint64_t) (1 + t % 3) << 49; Gs += (uint64_t) (t % 5) << 42; }
+        anch[o] = make_ulonglong2(Fs, Gs);
+    }
+    // ---- chunk-level check: all tiles of the chunk against ONE line from the chunk's first anchor
+    const uint64_t F0 = __shfl_sync(0xffffffffu, FA, 0), G0 = __shfl_sync(0xffffffffu, GA, 0);
+    const uint64_t gmask = (1ULL << LN_GBITS) - 1;
+    const uint64_t off = (uint64_t) lane * LN_TILE;
+    int64_t dlF = valid ? (int64_t) (FA - (F0 + off * dF)) : 0;
+    // code: only G mod 2^47 matters (wraps and variant offsets are multiples of 2^47)
+    int64_t dlG = valid ? (int64_t) (((GA - G0 - off * dG) & gmask) << (64 - LN_GBITS)) >> (64 - LN_GBITS) : 0;
+    int64_t loF = dlF, hiF = dlF, loG = dlG, hiG = dlG;
+#pragma unroll
+    for (int s = 16; s; s >>= 1) {
+        loF = min(loF, (int64_t) __shfl_xor_sync(0xffffffffu, loF, s));
+        hiF = max(hiF, (int64_t) __shfl_xor_sync(0xffffffffu, hiF, s));
+        loG = min(loG, (int64_t) __shfl_xor_sync(0xffffffffu, loG, s));
+        hiG = max(hiG, (int64_t) __shfl_xor_sync(0xffffffffu, hiG, s));
+    }
+    const int n_chunk = min(LN_CHUNK * LN_TILE, N - ch * LN_CHUNK * LN_TILE);
+    const int64_t eF = ln_eps(1, LN_TILE), eG = ln_eps(0, LN_TILE);
+    bool flagged = (dbg & (LN_DBG_FORCE_CHUNK | LN_DBG_FORCE_TILE)) != 0;
+    if (!flagged) {
+        bool hz = false;
+        if (lane == 0) hz = line_hazard(F0, dF, LN_FBITS, (uint64_t) n_chunk, loF - eF, hiF + eF);
+        if (lane == 1) hz = line_hazard(G0, dG, LN_GBITS, (uint64_t) n_chunk, loG - eG, hiG + eG);
+        flagged = __any_sync(0xffffffffu, hz);
+    }
+    if (!flagged) return;
+    if (lane == 0) atomicAdd(&counters[2], 1);  // diagnostic: flagged chunks
+    // ---- tile-level check from the tile's own exact anchor
+    if (!valid) return;
+    const int len = min(LN_TILE, N - t * LN_TILE);
+    const bool hz = (dbg & LN_DBG_FORCE_TILE) || line_hazard(FA, dF, LN_FBITS, (uint64_t) len, -eF, eF) ||
+                    line_hazard(GA, dG, LN_GBITS, (uint64_t) len, -eG, eG);
+    if (hz) {
+        const int slot = atomicAdd(&counters[0], 1);
+        if (slot < haz_cap) hazlist[slot] = (uint32_t) (e * ntiles + t) * 32u + (uint32_t) c;
+        else atomicOr(&step_flag[e], 4);  // list full: the epoch is re-rendered by k_synth_lanes
+    }
+}
+
+// ---- k_line_patch ------------------------------------------------------------------
+// One thread per listed (tile, slot): the literal recurrences of plutogpssim.c:2697-2746 from the exact
+// tile-start state, compared sample by sample with what k_synth_line computes from the anchors.
+__global__ void __launch_bounds__(128)
+k_line_patch(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict__ lutp,
+             const double* __restrict__ code_ck, const int* __restrict__ wrap_ck, const CarrLookup carr,
+             const ulonglong2* __restrict__ anch, const int8_t* __restrict__ chips4,
+             const uint32_t* __restrict__ hazlist, int* __restrict__ counters, int haz_cap,
+             LinePatch* __restrict__ patches, int patch_cap, int* __restrict__ step_flag, int C, int N, int ntiles) {
+    const int count = min(counters[0], haz_cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const uint32_t item = hazlist[i];
+        const int c = item & 31;
+        const int tg = item >> 5;
+        const int e = tg / ntiles, t = tg - e * ntiles;
+        const size_t ec = (size_t) e * C + c;
+        const gpsiq_chan_desc d = desc[ec];
+        const size_t o = ((size_t) e * ntiles + t) * C + c;
+        const int len = min(LN_TILE, N - t * LN_TILE);
+        double cp = code_ck[o];
+        double ph = carr_lookup(carr, e, c, t, LN_TILE, N, C, ntiles);
+        const int wr = wrap_ck[o] + d.ms0 % 20;
+        int kbit = wr / 20, icode = wr - kbit * 20;
+        const ulonglong2 a = anch[o];
+        const uint64_t dF = ln_carr_slope(d.carr_step), dG = ln_code_slope(d.code_step);
+        uint64_t F = a.x, G = a.y;
+        const int32_t* lut = lutp + ec * 512;
+        const int8_t* chipv = chips4 + (size_t) d.prn * 4 * LN_VS;  // variants of this PRN
+        const int8_t* chip0 = chips4 + (size_t) d.prn * 4 * LN_VS;  // variant 0 = polarity (0,0): +1 iff chip == 0
+        for (int n = 0; n < len; n++) {
+            // exact (plutogpssim.c:2697, 2701-2702, 2732, 2737)
+            const int it = min(__double2int_rd(__dmul_rn(ph, 512.0)), 511);
+            const int chipi = __double2int_rz(cp);
+            const int chipbit = chip0[chipi] > 0 ? 0 : 1;
+            const int nav = (int) (d.navbits >> (kbit & 63)) & 1;
+            const int32_t right = (chipbit == nav) ? lut[it] : -lut[it];
+            // what k_synth_line adds for this slot
+            const int32_t wrong = lut[(uint32_t) (F >> LN_FBITS)] * (int32_t) chipv[(uint32_t) (G >> LN_GBITS)];
+            if (right != wrong) {
+                const int slot = atomicAdd(&counters[1], 1);
+                if (slot < patch_cap) {
+                    LinePatch p; p.sample = (uint32_t) ((size_t) e * N + (size_t) t * LN_TILE + n); p.delta = right - wrong;
+                    patches[slot] = p;
+                } else {
+                    atomicOr(&step_flag[e], 4);
+                }
+            }
+            F += dF; G += dG;
+            int wdummy = 0;
+            if (nco_step<NCO_CODE>(cp, d.code_step, wdummy)) { if (++icode >= 20) { icode = 0; kbit++; } }
+            nco_step<NCO_CARRIER>(ph, d.carr_step, wdummy);
+        }
+    }
+}
+
+// packed sum (Q << 16) + I with signed I  <->  int16 pair as stored (plutogpssim.c:2754-2755)
+__device__ __forceinline__ uint32_t ln_pack(uint32_t acc) { return acc + ((acc & 0x8000u) << 1); }
+__device__ __forceinline__ uint32_t ln_unpack(uint32_t w) { return w - ((w & 0x8000u) << 1); }
+
+__global__ void __launch_bounds__(128)
+k_line_apply(const LinePatch* __restrict__ patches, const int* __restrict__ counters, int patch_cap,
+             uint32_t* __restrict__ iq, unsigned long long s_lo, unsigned long long s_hi,
+             unsigned long long* __restrict__ totals) {
+    const int count = min(counters[1], patch_cap);
+    if (totals && blockIdx.x == 0 && threadIdx.x < 3) totals[threadIdx.x] += (unsigned long long) counters[threadIdx.x];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const LinePatch p = patches[i];
+        if (p.sample < s_lo || p.sample >= s_hi) continue;  // samples of this sub-batch only
+        uint32_t* w = iq + p.sample;
+        uint32_t old = *w, seen;
+        do {
+            seen = old;
+            old = atomicCAS(w, seen, ln_pack(ln_unpack(seen) + (uint32_t) p.delta));
+        } while (old != seen);
+    }
+}
+
+// ---- k_synth_line --------------------------------------------------------------------
+__device__ __forceinline__ int32_t ln_lds_s8(uint32_t saddr) {
+    int32_t v;
+    asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+// LUT entry idx of the table at shared address base: one multiply-add for the address (kept as one
+// instruction: the compiler would otherwise split (x >> 23) << 2 into shift + mask + add)
+__device__ __forceinline__ int32_t ln_lds_lut(uint32_t base, uint32_t idx) {
+    int32_t v;
+    uint32_t addr;
+    asm volatile("mad.lo.u32 %0, %1, 4, %2;" : "=r"(addr) : "r"(idx), "r"(base));
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+__global__ void __launch_bounds__(LN_THREADS, 2)
+k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict__ lutp,
+             const int8_t* __restrict__ chips4, const ulonglong2* __restrict__ anch,
+             const int* __restrict__ amp_sum, const int* __restrict__ step_flag, int16_t* __restrict__ iq,
+             int E, int C, int N, int ntiles, int* __restrict__ err) {
+    extern __shared__ __align__(16) unsigned char ln_raw[];
+    const int CG = ln_group_slots(C), ngroups = ln_groups(C);
+    int8_t* s_chip = (int8_t*) ln_raw;                                   // [CG][4][LN_VS]
+    int32_t* s_lut = (int32_t*) (ln_raw + (size_t) CG * 4 * LN_VS);      // [CG][512]
+    ulonglong2* s_step = (ulonglong2*) (s_lut + (size_t) CG * 512);      // [16] {dF, dG}; dF == dG == 0: inactive
+    ulonglong2* s_anch = s_step + 16;                                    // [LN_WARPS][16]
+    const uint32_t chip_saddr = (uint32_t) __cvta_generic_to_shared(s_chip);
+    const uint32_t lut_saddr = (uint32_t) __cvta_generic_to_shared(s_lut);
+    if (chip_saddr + (uint32_t) CG * 4 * LN_VS > (1u << (64 - LN_GBITS))) {  // the chip address must fit G's index field
+        if (threadIdx.x == 0) atomicExch(err, 0x40000000);
+        return;
+    }
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ulonglong2* my_anch = s_anch + warp * 16;
+    const long long tiles_total = (long long) E * ntiles;
+    const long long tg_begin = tiles_total * blockIdx.x / gridDim.x, tg_end = tiles_total * (blockIdx.x + 1) / gridDim.x;
+    const int wb_epoch = (N + LN_WB - 1) / LN_WB;
+
+    for (long long tg = tg_begin; tg < tg_end;) {
+        const int e = (int) (tg / ntiles);
+        const int t0 = (int) (tg - (long long) e * ntiles);
+        const int t1 = (int) min((long long) ntiles, t0 + (tg_end - tg));
+        tg += t1 - t0;
+        if (amp_sum[e] > 32767 || step_flag[e]) continue;  // rendered by k_synth_lanes (uniform per CTA)
+        const gpsiq_chan_desc* de = desc + (size_t) e * C;
+        uint32_t* out_epoch = reinterpret_cast<uint32_t*>(iq) + (size_t) e * N;
+        const int wb0 = t0 * (LN_TILE / LN_WB), wb1 = min(t1 * (LN_TILE / LN_WB), wb_epoch);
+        for (int g = 0; g < ngroups; g++) {
+            const int c0 = g * CG, nc = min(CG, C - c0);
+            __syncthreads();  // everyone is done with the previous tables
+            for (int i = threadIdx.x; i < nc * (4 * LN_VS / 16); i += LN_THREADS) {
+                const int cl = i / (4 * LN_VS / 16), k = i - cl * (4 * LN_VS / 16);
+                const int prn = de[c0 + cl].prn;
+                if (prn > 0 && prn <= 32)
+                    ((uint4*) s_chip)[i] = ((const uint4*) (chips4 + (size_t) prn * 4 * LN_VS))[k];
+            }
+            for (int i = threadIdx.x; i < nc * 128; i += LN_THREADS) {
+                const int cl = i >> 7;
+                if (de[c0 + cl].prn > 0)
+                    ((uint4*) s_lut)[i] = ((const uint4*) (lutp + ((size_t) e * C + c0 + cl) * 512))[i & 127];
+            }
+            if (threadIdx.x < 16) {
+                ulonglong2 s = make_ulonglong2(0, 0);
+                if (threadIdx.x < nc && de[c0 + threadIdx.x].prn > 0) {
+                    s.x = ln_carr_slope(de[c0 + threadIdx.x].carr_step);
+                    s.y = ln_code_slope(de[c0 + threadIdx.x].code_step);  // > 0 for every active slot
+                }
+                s_step[threadIdx.x] = s;
+            }
+            __syncthreads();
+
+            for (int wb = wb0 + warp; wb < wb1; wb += LN_WARPS) {
+                const int tile = wb >> 2;
+                const uint32_t m0 = (uint32_t) ((wb & 3) * LN_WB + lane);  // sample offset inside the tile
+                __syncwarp();
+                if (lane < nc) my_anch[lane] = anch[((size_t) e * ntiles + tile) * C + c0 + lane];
+                __syncwarp();
+                uint32_t* dst = out_epoch + (size_t) wb * LN_WB + lane;
+                const int nleft = N - (wb * LN_WB + lane);  // this lane's sample j exists iff 32*j < nleft
+                int32_t acc[LN_RUN];
+#pragma unroll
+                for (int j = 0; j < LN_RUN; j++) acc[j] = 0;
+                if (g > 0) {
+#pragma unroll
+                    for (int j = 0; j < LN_RUN; j++)
+                        if (32 * j < nleft) acc[j] = (int32_t) dst[32 * j];  // raw packed sums of the earlier groups
+                }
+                for (int cl = 0; cl < nc; cl++) {
+                    const ulonglong2 st = s_step[cl];
+                    if (st.y == 0) continue;  // inactive slot (uniform)
+                    const ulonglong2 a = my_anch[cl];
+                    uint64_t F = a.x + (uint64_t) m0 * st.x;
+                    uint64_t G = a.y + (uint64_t) m0 * st.y + ((uint64_t) (chip_saddr + (uint32_t) cl * 4 * LN_VS) << LN_GBITS);
+                    const uint64_t dF = st.x << 5, dG = st.y << 5;
+                    const uint32_t lut = lut_saddr + (uint32_t) cl * 2048;
+#pragma unroll
+                    for (int j = 0; j < LN_RUN; j++) {
+                        acc[j] += ln_lds_lut(lut, (uint32_t) (F >> LN_FBITS)) * ln_lds_s8((uint32_t) (G >> LN_GBITS));
+                        F += dF;
+                        G += dG;
+                    }
+                }
+                if (g == ngroups - 1) {
+#pragma unroll
+                    for (int j = 0; j < LN_RUN; j++)
+                        if (32 * j < nleft) dst[32 * j] = ln_pack((uint32_t) acc[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < LN_RUN; j++)
+                        if (32 * j < nleft) dst[32 * j] = (uint32_t) acc[j];
+                }
+            }
+        }
+    }
+}
+
+}  // namespace gpsiq

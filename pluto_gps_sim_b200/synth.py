@@ -17,7 +17,7 @@ NUM_SAMPLES = 300000  # plutogpssim.c:43-44: TX_SAMPLE_FREQ/10, independent of -
 
 class Synthesizer:
     def __init__(self, max_chan=12, samples_per_epoch=NUM_SAMPLES, max_epochs=100, carrier_mode=capi.CARRIER_FLOAT,
-                 device=0, tile_samples=0, kernel=capi.KERNEL_AUTO, serial_carrier_scan=False):
+                 device=0, tile_samples=0, kernel=capi.KERNEL_AUTO, serial_carrier_scan=False, line_debug=0):
         cfg = capi.Config()
         cfg.device = device
         cfg.max_chan = max_chan
@@ -27,6 +27,7 @@ class Synthesizer:
         cfg.tile_samples = tile_samples
         cfg.kernel = kernel
         cfg.reserved[0] = 1 if serial_carrier_scan else 0
+        cfg.reserved[1] = int(line_debug)   # test hooks of the line kernel (capi.LINE_DBG_*)
         self._ctx = C.c_void_p()
         capi.check(capi.lib.gpsiq_create(C.byref(self._ctx), C.byref(cfg)))
         self.max_chan = max_chan
@@ -150,6 +151,13 @@ class Synthesizer:
         capi.check(capi.lib.gpsiq_carrier_fallbacks(self._ctx, C.byref(n)), self._ctx)
         return n.value
 
+    @property
+    def line_stats(self):
+        """-> (tile-slot pairs re-checked with the literal recurrence, samples patched, chunks flagged)."""
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        capi.check(capi.lib.gpsiq_line_stats(self._ctx, C.byref(a), C.byref(b), C.byref(c)), self._ctx)
+        return a.value, b.value, c.value
+
     def timing_begin(self):
         capi.check(capi.lib.gpsiq_timing_begin(self._ctx), self._ctx)
 
@@ -160,13 +168,13 @@ class Synthesizer:
         return n.value, a.value, b.value
 
     def timing_sample_kernel(self):
-        """-> (launches, summed ms, epochs per launch) of the dominant kernel (k_synth_fixed) alone."""
+        """-> (launches, summed ms, epochs per launch) of the dominant kernel (k_synth_line / k_synth_fixed) alone."""
         n, a, e = C.c_int(0), C.c_float(0), C.c_int(0)
         capi.check(capi.lib.gpsiq_timing_sample_kernel(self._ctx, C.byref(n), C.byref(a), C.byref(e)), self._ctx)
         return n.value, a.value, e.value
 
     def timing_sample_kernel_isolated(self, reps=20):
-        """-> (mean ms, epochs per launch) of k_synth_fixed re-launched alone on an idle device."""
+        """-> (mean ms, epochs per launch) of the dominant kernel re-launched alone on an idle device."""
         a, e = C.c_float(0), C.c_int(0)
         capi.check(capi.lib.gpsiq_timing_sample_kernel_isolated(self._ctx, reps, C.byref(a), C.byref(e)), self._ctx)
         return a.value, e.value

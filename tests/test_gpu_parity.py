@@ -10,7 +10,8 @@ from pluto_gps_sim_b200 import Synthesizer, capi, checksum_host
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [capi.KERNEL_LANE_PER_CHANNEL, capi.KERNEL_FIXED_POINT]
+KERNELS = [capi.KERNEL_LANE_PER_CHANNEL, capi.KERNEL_FIXED_POINT, capi.KERNEL_LINE]
+FAST_KERNELS = [capi.KERNEL_FIXED_POINT, capi.KERNEL_LINE]
 
 
 def first_diff(a, b):
@@ -89,26 +90,29 @@ def test_inactive_slots_and_empty_epoch(kernel):
     assert not got[1].any()
 
 
+@pytest.mark.parametrize("kernel", FAST_KERNELS)
 @pytest.mark.parametrize("n", [8, 1020, 1028, 4100, 30004])
-def test_fixed_point_kernel_ragged_epochs(n):
+def test_fixed_point_kernel_ragged_epochs(n, kernel):
     desc = ol.load_golden_desc("circle12")[300:303]
     want, _ = ol.oracle_synth(desc, n)
-    with Synthesizer(max_chan=12, samples_per_epoch=n, max_epochs=3, kernel=capi.KERNEL_FIXED_POINT) as s:
+    with Synthesizer(max_chan=12, samples_per_epoch=n, max_epochs=3, kernel=kernel) as s:
         got = s.synth(desc)
     assert first_diff(got, want) is None
 
 
-@pytest.mark.parametrize("nchan", [17, 24, 32])
-def test_fixed_point_kernel_channel_groups(nchan):
+@pytest.mark.parametrize("kernel", FAST_KERNELS)
+@pytest.mark.parametrize("nchan", [13, 17, 24, 32])
+def test_fixed_point_kernel_channel_groups(nchan, kernel):
     """More than 16 slots: the kernel walks the channels in groups of 16 resident tables."""
     desc = ol.load_golden_desc("allsky32")[:3, :nchan].copy()
     want, _ = ol.oracle_synth(desc, 20000)
-    with Synthesizer(max_chan=nchan, samples_per_epoch=20000, max_epochs=3, kernel=capi.KERNEL_FIXED_POINT) as s:
+    with Synthesizer(max_chan=nchan, samples_per_epoch=20000, max_epochs=3, kernel=kernel) as s:
         got = s.synth(desc)
     assert first_diff(got, want) is None
 
 
-def test_fixed_point_kernel_routes_out_of_contract_epochs_to_lane_kernel():
+@pytest.mark.parametrize("kernel", FAST_KERNELS)
+def test_fixed_point_kernel_routes_out_of_contract_epochs_to_lane_kernel(kernel):
     """Huge gains (packed int16 accumulation could overflow) and extreme Doppler
     (segment lists too long) are rendered by the lane-per-channel kernel; the
     reference's (short) wrap-around is reproduced either way."""
@@ -117,14 +121,15 @@ def test_fixed_point_kernel_routes_out_of_contract_epochs_to_lane_kernel():
     desc[2, 5]["carr_step"] = 0.0123           # ~32 kHz Doppler at 2.6 MS/s
     desc[3, 7]["carr_step"] = -0.0077
     want, wt = ol.oracle_synth(desc, 40000)
-    with Synthesizer(max_chan=12, samples_per_epoch=40000, max_epochs=4, kernel=capi.KERNEL_FIXED_POINT) as s:
+    with Synthesizer(max_chan=12, samples_per_epoch=40000, max_epochs=4, kernel=kernel) as s:
         got = s.synth(desc)
         gt = s.carrier_trace(4)
     assert first_diff(got, want) is None
     assert np.array_equal(gt, wt)
 
 
-def test_fixed_point_kernel_random_descriptors():
+@pytest.mark.parametrize("kernel", FAST_KERNELS)
+def test_fixed_point_kernel_random_descriptors(kernel):
     """Synthetic descriptors over the whole contract range (both Doppler signs up to
     ~9 kHz, code phases near the wrap, NAV edges in the first tile)."""
     rng = np.random.default_rng(7)
@@ -144,11 +149,68 @@ def test_fixed_point_kernel_random_descriptors():
             d["gain"] = rng.uniform(0.05, 1.5)
             d["flags"] = 1 if (e == 0 or rng.random() < 0.1) else 0
     want, wt = ol.oracle_synth(desc, n)
-    with Synthesizer(max_chan=Cn, samples_per_epoch=n, max_epochs=E, kernel=capi.KERNEL_FIXED_POINT) as s:
+    with Synthesizer(max_chan=Cn, samples_per_epoch=n, max_epochs=E, kernel=kernel) as s:
         got = s.synth(desc)
         gt = s.carrier_trace(E)
     assert first_diff(got, want) is None
     assert np.array_equal(gt, wt)
+
+
+@pytest.mark.parametrize("dbg", [capi.LINE_DBG_FORCE_CHUNK, capi.LINE_DBG_FORCE_TILE,
+                                 capi.LINE_DBG_FORCE_TILE | capi.LINE_DBG_PERTURB])
+def test_line_kernel_check_and_patch_paths(dbg):
+    """The line kernel's second-level check, its literal-recurrence patch path, and -- with the anchors the
+    main kernel uses deliberately shifted -- the patch application: all must still give the reference's bytes."""
+    desc = ol.load_golden_desc("circle12")[298:302]       # crosses the 30 s refresh (re-allocation, NAV rebuild)
+    n = 70000
+    want, wt = ol.oracle_synth(desc, n)
+    with Synthesizer(max_chan=12, samples_per_epoch=n, max_epochs=4, kernel=capi.KERNEL_LINE, line_debug=dbg) as s:
+        got = s.synth(desc)
+        gt = s.carrier_trace(4)
+        hz, patches, chunks = s.line_stats
+    assert first_diff(got, want) is None
+    assert np.array_equal(gt, wt)
+    n_active = int((desc["prn"] > 0).sum())
+    assert chunks == n_active * 3                          # 69 tiles = 3 chunks per active (epoch, slot)
+    if dbg & capi.LINE_DBG_FORCE_TILE:
+        assert hz == n_active * 69
+    if dbg & capi.LINE_DBG_PERTURB:
+        assert patches > 1000                              # the shifted anchors really were wrong
+    else:
+        assert patches == 0                                # the line alone already matches the recurrence
+
+
+def test_line_kernel_clears_almost_every_tile():
+    """On the reference scenario the check must clear (nearly) all tiles: the patch path is a safety net."""
+    desc = ol.load_golden_desc("static12")
+    with Synthesizer(max_chan=12, max_epochs=10, kernel=capi.KERNEL_LINE) as s:
+        s.synth(desc, keep_on_device=True)
+        hz, patches, chunks = s.line_stats
+    assert chunks <= 8 and hz <= 2 and patches == 0, (hz, patches, chunks)
+
+
+def test_line_kernel_nav_edges_in_every_position():
+    """NAV bit edges and code-period wraps at every offset inside a tile (the 4-variant chip tables)."""
+    rng = np.random.default_rng(21)
+    E, Cn, n = 3, 12, 9000
+    desc = np.zeros((E, Cn), capi.DESC_DTYPE)
+    for e in range(E):
+        for c in range(Cn):
+            d = desc[e, c]
+            f = rng.uniform(-5000, 5000)
+            d["prn"] = int(rng.integers(1, 33))
+            d["ms0"] = 19 + 20 * int(rng.integers(0, 40))            # icode = 19: the first wrap is a bit edge
+            d["navbits"] = int(rng.integers(0, 2 ** 63))
+            d["code_step"] = (1.023e6 + f / 1540.0) / 2.6e6
+            d["code_phase0"] = 1023.0 - d["code_step"] * (1 + 97 * c + 13 * e) - 1e-9   # wrap after 1 + 97c + 13e samples
+            d["carr_step"] = f / 2.6e6
+            d["carr_phase0"] = rng.random()
+            d["gain"] = rng.uniform(0.2, 1.0)
+            d["flags"] = 1
+    want, _ = ol.oracle_synth(desc, n)
+    with Synthesizer(max_chan=Cn, samples_per_epoch=n, max_epochs=E, kernel=capi.KERNEL_LINE) as s:
+        got = s.synth(desc)
+    assert first_diff(got, want) is None
 
 
 def test_integer_carrier_mode_vs_oracle():
