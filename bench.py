@@ -49,7 +49,7 @@ REF_ARGS = ["-e", NAV_FIXTURE, "-l", "30.286502,120.032669,100", "-s", "2600000"
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_synth_fixed launch (8 epochs, 12 slots) from the
 # ncu --set full capture summarised in profiles/r01_c_render_kernels_ncu_full.txt (the output itself is
 # still in L2 when the kernel ends; the reads are the tile records and corrections)
-TRAFFIC_PER_LAUNCH = 37450240
+TRAFFIC_PER_LAUNCH = {"k_synth_fixed": 37450240, "k_synth_line": None}
 WORKLOAD = "config[1]: static -l 30.286502,120.032669,100, synthetic brdc3540.14n, 2.6 MS/s, 12 channels, 300000 samples/epoch"
 
 
@@ -307,18 +307,19 @@ def ours_arm(args):
 
     if rank == 0:
         peak, peak_src = peaks()
-        # dominant kernel = k_synth_fixed; one launch covers `kep` epochs (a sub-batch)
+        # dominant kernel = k_synth_line (k_synth_fixed with --kernel 2); one launch covers `kep` epochs
+        dom = "k_synth_fixed" if args.kernel == capi.KERNEL_FIXED_POINT else "k_synth_line"
         if kiso_ms > 0:
             # the dominant kernel timed ALONE (20 back-to-back re-launches of the last k_synth_fixed on an idle
             # device, CUDA events on its stream); inside the pipelined region it shares the SMs with the scan
             # kernels of the next batch, so its in-pipeline duration (kernel_ms_in_pipeline) is not the kernel's own
             kern_ms = kiso_ms
             kern_bytes = kiso_ep * N_SAMPLES * 4
-            kern_name = "k_synth_fixed (one launch = %d epochs), timed alone" % kiso_ep
+            kern_name = "%s (one launch = %d epochs), timed alone" % (dom, kiso_ep)
         elif kn > 0:
             kern_ms = kms / kn
             kern_bytes = kep * N_SAMPLES * 4
-            kern_name = "k_synth_fixed (one launch = %d epochs)" % kep
+            kern_name = "%s (one launch = %d epochs)" % (dom, kep)
         else:
             kern_ms = synth_ms / max(nrec, 1)
             kern_bytes = samples_per_step * 4
@@ -357,7 +358,7 @@ def ours_arm(args):
                     "d2h_bytes_per_step": samples_per_step * 4},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 5), "traffic": TRAFFIC_PER_LAUNCH, "peak_source": peak_src,
+                         "frac": round(achieved / peak, 5), "traffic": TRAFFIC_PER_LAUNCH.get(dom), "peak_source": peak_src,
                          "kernel": kern_name, "kernel_ms_per_launch": round(kern_ms, 4),
                          "algorithmic_bytes_per_launch": kern_bytes,
                          "kernel_ms_in_pipeline": round(kms / kn, 4) if kn else None,

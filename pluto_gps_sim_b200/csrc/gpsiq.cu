@@ -117,6 +117,7 @@ struct gpsiq_ctx {
     ulonglong2* d_anch[2];   // [E][ntiles][C] tile anchors {F, G} (one buffer per scan set)
     uint32_t* d_hazlist;  // (tile, slot) pairs k_line_anchor could not clear
     int haz_cap, patch_cap;
+    unsigned int* d_sched;   // [33][2] tile schedulers of k_synth_line (self-resetting)
     int* d_line_counters; // [0] listed hazards, [1] patches, [2] flagged chunks (per batch)
     unsigned long long* d_line_totals;  // the same, accumulated over the context's life
     LinePatch* d_patches;
@@ -319,19 +320,36 @@ __device__ __forceinline__ double frac01(double t) {
 // adv[C+c] = 1 if a descriptor re-seeded the slot (then adv[c] is an absolute phase).
 // Feeds only the start-phase ESTIMATES of later speculative scans, on this GPU or
 // -- for time-sliced multi-GPU runs -- on the ranks that own later slices.
-__global__ void k_slice_advance(const double* __restrict__ eadv, const double* __restrict__ ereset,
-                                double* __restrict__ adv, int E, int C) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per slot: the lanes stage the slot's column of the two [E][C] arrays in shared memory
+// (a lane-strided, latency-overlapped load), then lane 0 runs the short serial recurrence from there.
+#define EST_MAX_E 2048
+__device__ __forceinline__ void stage_column(double* s_a, double* s_r, const double* __restrict__ eadv,
+                                             const double* __restrict__ ereset, int e0, int n, int c, int C, int lane) {
+    for (int i = lane; i < n; i += 32) {
+        s_a[i] = eadv[(size_t) (e0 + i) * C + c];
+        s_r[i] = ereset[(size_t) (e0 + i) * C + c];
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32)
+k_slice_advance(const double* __restrict__ eadv, const double* __restrict__ ereset, double* __restrict__ adv, int E, int C) {
+    __shared__ double s_a[EST_MAX_E], s_r[EST_MAX_E];
+    const int c = blockIdx.x, lane = threadIdx.x;
     if (c >= C) return;
     double x = 0.0, abs_flag = 0.0;
-#pragma unroll 16
-    for (int e = 0; e < E; e++) {
-        const double r = ereset[(size_t) e * C + c], a = eadv[(size_t) e * C + c];
-        if (r >= 0.0) { x = r; abs_flag = 1.0; }
-        x = frac01(x + a);
+    for (int e0 = 0; e0 < E; e0 += EST_MAX_E) {
+        const int n = min(EST_MAX_E, E - e0);
+        stage_column(s_a, s_r, eadv, ereset, e0, n, c, C, lane);
+        if (lane == 0)
+            for (int i = 0; i < n; i++) {
+                const double r = s_r[i];
+                if (r >= 0.0) { x = r; abs_flag = 1.0; }
+                x = frac01(x + s_a[i]);
+            }
+        __syncwarp();
     }
-    adv[c] = x;
-    adv[C + c] = abs_flag;
+    if (lane == 0) { adv[c] = x; adv[C + c] = abs_flag; }
 }
 
 // est = fold(est, adv): est <- adv (absolute) or frac(est + adv)
@@ -342,17 +360,27 @@ __global__ void k_est_fold(double* __restrict__ est, const double* __restrict__ 
 }
 
 // Estimated phase at the start of every epoch of the batch, from the context's batch-start estimate.
-__global__ void k_epoch_estimates(const double* __restrict__ eadv, const double* __restrict__ ereset,
-                                  const double* __restrict__ est_state, double* __restrict__ est_epoch, int E, int C) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32)
+k_epoch_estimates(const double* __restrict__ eadv, const double* __restrict__ ereset,
+                  const double* __restrict__ est_state, double* __restrict__ est_epoch, int E, int C) {
+    __shared__ double s_a[EST_MAX_E], s_r[EST_MAX_E];
+    const int c = blockIdx.x, lane = threadIdx.x;
     if (c >= C) return;
     double x = est_state[c];
-#pragma unroll 16
-    for (int e = 0; e < E; e++) {
-        const double r = ereset[(size_t) e * C + c], a = eadv[(size_t) e * C + c];
-        if (r >= 0.0) x = r;  // re-seeded: the start phase of this epoch is known exactly
-        est_epoch[(size_t) e * C + c] = x;
-        x = frac01(x + a);
+    for (int e0 = 0; e0 < E; e0 += EST_MAX_E) {
+        const int n = min(EST_MAX_E, E - e0);
+        stage_column(s_a, s_r, eadv, ereset, e0, n, c, C, lane);
+        if (lane == 0)
+            for (int i = 0; i < n; i++) {
+                const double r = s_r[i];
+                if (r >= 0.0) x = r;  // re-seeded: the start phase of this epoch is known exactly
+                const double a = s_a[i];
+                s_a[i] = x;           // (becomes the output column)
+                x = frac01(x + a);
+            }
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) est_epoch[(size_t) (e0 + i) * C + c] = s_a[i];
+        __syncwarp();
     }
 }
 
@@ -972,6 +1000,8 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
         CU(cudaMalloc(&ctx->d_hazlist, (size_t) ctx->haz_cap * 4));
         CU(cudaMalloc(&ctx->d_patches, (size_t) ctx->patch_cap * sizeof(LinePatch)));
         CU(cudaMalloc(&ctx->d_line_counters, 4 * sizeof(int)));
+        CU(cudaMalloc(&ctx->d_sched, 33 * 2 * sizeof(unsigned int)));
+        CU(cudaMemset(ctx->d_sched, 0, 33 * 2 * sizeof(unsigned int)));
         CU(cudaMalloc(&ctx->d_line_totals, 4 * sizeof(unsigned long long)));
         CU(cudaMemset(ctx->d_line_totals, 0, 4 * sizeof(unsigned long long)));
         // chip/NAV sign tables: variant v = pol0*2 + pol1; entry k < 1023: chip k under NAV bit pol0,
@@ -1017,7 +1047,7 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
         cudaFree(ctx->d_recs[i]); cudaFree(ctx->d_fixmasks[i]); cudaFree(ctx->d_delta[i]); cudaFree(ctx->d_work[i]);
     }
     cudaFree(ctx->d_chips4); cudaFree(ctx->d_anch[0]); cudaFree(ctx->d_anch[1]); cudaFree(ctx->d_hazlist);
-    cudaFree(ctx->d_patches); cudaFree(ctx->d_line_counters); cudaFree(ctx->d_line_totals);
+    cudaFree(ctx->d_patches); cudaFree(ctx->d_line_counters); cudaFree(ctx->d_sched); cudaFree(ctx->d_line_totals);
     cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_est_state); cudaFree(ctx->d_ca);
     cudaFree(ctx->d_iq); cudaFree(ctx->d_iq2); cudaFree(ctx->d_sums); cudaFree(ctx->d_err);
     if (ctx->h_stage[0]) cudaFreeHost(ctx->h_stage[0]);
@@ -1063,7 +1093,7 @@ static int enqueue_prepare(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int 
                                   ctx->d_flags + ctx->E, C, N, ctx->cfg.carrier_mode, ctx->d_err);
     ctx->launches += 1;
     if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT) {
-        k_slice_advance<<<1, 32, 0, st>>>(ctx->d_drift, ctx->d_drift + (size_t) EC, ctx->d_adv, n_epochs, C);
+        k_slice_advance<<<C, 32, 0, st>>>(ctx->d_drift, ctx->d_drift + (size_t) EC, ctx->d_adv, n_epochs, C);
         ctx->launches += 1;
     }
     ctx->last_epochs = n_epochs;
@@ -1090,7 +1120,7 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
         double* eadv = ctx->d_drift;
         double* ereset = ctx->d_drift + (size_t) EC;      // k_prepare wrote it at [gridDim.x + ec] with gridDim.x = EC
         double* est_epoch = ctx->d_drift + 2 * ECmax;
-        k_epoch_estimates<<<1, 32, 0, st>>>(eadv, ereset, ctx->d_est_state, est_epoch, n_epochs, C);
+        k_epoch_estimates<<<C, 32, 0, st>>>(eadv, ereset, ctx->d_est_state, est_epoch, n_epochs, C);
         const int chains = EC * ctx->J * 2;
         k_carr_speculate<<<(chains + 127) / 128, 128, 0, st>>>(desc_dev, ctx->d_tab, eadv, est_epoch, ctx->d_carr_ck,
                                                          ctx->ck_plane, ctx->d_spec, n_epochs, C, N, T, ntiles, ctx->G,
@@ -1173,8 +1203,7 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
         const int dbg = ctx->cfg.reserved[1];
         ulonglong2* anch = ctx->d_anch[ctx->set_cur];
         CU(cudaMemsetAsync(ctx->d_line_counters, 0, 4 * sizeof(int), st));
-        const int chunks = (ntiles + LN_CHUNK - 1) / LN_CHUNK;
-        const int warps = n_epochs * C * chunks;
+        const int warps = n_epochs * C;
         k_line_anchor<<<(warps + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx),
                                                        ctx->d_flags, ctx->d_flags + ctx->E, anch, ctx->d_hazlist,
                                                        ctx->d_line_counters, ctx->haz_cap, n_epochs, C, N, ntiles, dbg);
@@ -1195,7 +1224,7 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
             k_synth_line<<<grid, LN_THREADS, ln_smem_bytes(C), st>>>(
                 desc_dev + (size_t) e0 * C, ctx->d_lutp + (size_t) e0 * C * 512, ctx->d_chips4,
                 anch + (size_t) e0 * ntiles * C, ctx->d_flags + e0, ctx->d_flags + ctx->E + e0,
-                iq_dev + (size_t) e0 * N * 2, ne, C, N, ntiles, ctx->d_err);
+                iq_dev + (size_t) e0 * N * 2, ne, C, N, ntiles, ctx->d_sched + 2 * (k & 31), ctx->d_err);
             if (timed) CU(cudaEventRecord(ctx->ev[ctx->ev_count][4], st));
             ctx->last_ln.desc = desc_dev + (size_t) e0 * C; ctx->last_ln.iq = iq_dev + (size_t) e0 * N * 2;
             ctx->last_ln.ne = ne; ctx->last_ln.set = ctx->set_cur;
@@ -1557,7 +1586,7 @@ int gpsiq_timing_sample_kernel_isolated(gpsiq_ctx* ctx, int reps, float* kernel_
             k_synth_line<<<grid, LN_THREADS, ln_smem_bytes(C), ctx->stream>>>(
                 ctx->last_ln.desc, ctx->d_lutp + (size_t) le0 * C * 512, ctx->d_chips4,
                 ctx->d_anch[ctx->last_ln.set] + (size_t) le0 * ntiles * C, ctx->d_flags + le0, ctx->d_flags + ctx->E + le0,
-                ctx->last_ln.iq, ne, C, N, ntiles, ctx->d_err);
+                ctx->last_ln.iq, ne, C, N, ntiles, ctx->d_sched + 2 * 32, ctx->d_err);
         } else {
             k_synth_fixed<<<ctx->last_fx.ne * groups, FX_WORKERS * FX_THREADS, fx_smem_bytes(C), ctx->stream>>>(
                 ctx->last_fx.desc, ctx->d_lutp, ctx->d_tab, ctx->d_recs[b], ctx->d_delta[b], ctx->d_chips, ctx->d_flags,

@@ -58,6 +58,14 @@ GPSIQ_HD uint64_t ln_carr_slope(double d) {
 }
 GPSIQ_HD uint64_t ln_code_slope(double d) { return ln_fixed_abs(d, LN_GBITS); }
 
+GPSIQ_HD int ln_ctz64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long) v) - 1;
+#else
+    return __builtin_ctzll(v);
+#endif
+}
+
 // ---- min over x in [0, n) of (b + a*x) mod m --------------------------------------
 // 0 <= b < m, 0 <= a < m, n >= 1.  Returns the exact minimum, except that it may return early
 // with ANY attained value < stop (callers only ask "is the minimum below stop?").
@@ -72,10 +80,13 @@ GPSIQ_HD uint64_t minmod(uint64_t b, uint64_t a, uint64_t m, uint64_t n, uint64_
     for (int guard = 0; guard < 200; guard++) {
         if (b < best) best = b;
         if (best < stop || a == 0 || n <= 1) return best;
-        if (2 * (u128) a <= m) {
-            // ascending: values b + a*x - k*m
+        if (a <= m - a) {
+            // ascending: values b + a*x - k*m; K = floor((b + (n-1)*a) / m) wraps
+            uint64_t K;
             const u128 tot = (u128) (n - 1) * a + b;
-            const uint64_t K = (uint64_t) (tot / m);
+            if ((uint64_t) (tot >> 64) == 0) K = (uint64_t) tot / m;   // the usual case after the first round
+            else if ((m & (m - 1)) == 0) K = (uint64_t) (tot >> ln_ctz64(m));  // first round: m = 2^B
+            else K = (uint64_t) (tot / m);
             if (K == 0) return best;
             const uint64_t r = m % a;
             const uint64_t nb = (a - ((m - b) % a)) % a;  // (b - m) mod a
@@ -89,11 +100,15 @@ GPSIQ_HD uint64_t minmod(uint64_t b, uint64_t a, uint64_t m, uint64_t n, uint64_
                 const uint64_t v = b - (uint64_t) tot;
                 return v < best ? v : best;
             }
-            const u128 need = tot - b;                         // > 0
-            const uint64_t K = (uint64_t) ((need + m - 1) / m);  // wraps
+            const u128 need = tot - b;                           // > 0
+            uint64_t K;                                          // wraps = ceil(need / m)
+            const u128 num = need + (m - 1);
+            if ((uint64_t) (num >> 64) == 0) K = (uint64_t) num / m;
+            else if ((m & (m - 1)) == 0) K = (uint64_t) (num >> ln_ctz64(m));
+            else K = (uint64_t) (num / m);
             const uint64_t fin = (uint64_t) ((u128) K * m - need);  // last value, in [0, m)
             if (fin < best) best = fin;
-            b = b % c; a = m % c; m = c; n = K;                // troughs (b + k*m) mod c, k = 0..K-1
+            b = b % c; a = m % c; m = c; n = K;                  // troughs (b + k*m) mod c, k = 0..K-1
         }
     }
     return 0;  // not reachable (the modulus halves every two rounds); "hazard" is the safe answer

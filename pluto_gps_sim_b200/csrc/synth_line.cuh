@@ -9,7 +9,7 @@
 // for why a straight line per 1024-sample tile is exact once k_line_anchor has cleared the tile.
 //
 //   tile        1024 samples; anchor = exact NCO states at its first sample (from the scan phases)
-//   warp-block  256 samples: lane l renders samples l, l+32, ..., l+224 of the block, so the 32 lanes
+//   warp-block  512 samples: lane l renders samples l, l+32, ..., l+480 of the block, so the 32 lanes
 //               of one shared-memory request touch <= 32 consecutive LUT entries (no bank conflict)
 //               and <= 16 consecutive chip bytes (broadcast), and every store instruction of a warp
 //               writes 128 contiguous bytes
@@ -26,7 +26,7 @@
 
 #include "line_check.cuh"
 
-#define LN_RUN 8
+#define LN_RUN 16
 #define LN_WB (32 * LN_RUN)       // samples per warp-block
 #define LN_TILE 1024
 #define LN_THREADS 512
@@ -47,81 +47,111 @@ __host__ __device__ inline int ln_groups(int C) { return (C + LN_CG - 1) / LN_CG
 __host__ __device__ inline int ln_group_slots(int C) { const int g = ln_groups(C); return (C + g - 1) / g; }
 __host__ __device__ inline size_t ln_smem_bytes(int C) {
     const int CG = ln_group_slots(C);
-    return (size_t) CG * 4 * LN_VS + (size_t) CG * 2048 + 16 * 16 /* steps */ + LN_WARPS * 16 * 16 /* anchors */ + 64;
+    return (size_t) CG * 4 * LN_VS + (size_t) CG * 2048 + 16 * 16 /* steps */ + LN_WARPS * 16 * 16 /* anchors */ + 128;
 }
 
 // ---- k_line_anchor ---------------------------------------------------------------
-// One warp per (epoch, slot, chunk of 32 tiles), lane = tile.  Writes the tile anchors
+// One warp per (epoch, slot).  Pass 1, chunk by chunk (32 tiles, lane = tile): the tile anchors
 //   anch[(e*ntiles + t)*C + c] = { F (carrier), G (code) + variant offset }
-// and appends every (tile, slot) that the line model cannot be proven exact for to hazlist.
+// and, per chunk, the spread of the anchors around ONE line from the chunk's first anchor.  Pass 2:
+// lane j checks the carrier line of chunk j, lane 16+j the code line of chunk j (line_hazard), all
+// chunks of the epoch at once.  Pass 3, only for flagged chunks: every tile against its own anchor;
+// the (tile, slot) pairs that still cannot be cleared go to hazlist.
+struct LineTile { uint64_t FA, GA, Fs, Gs; };
+
+__device__ __forceinline__ LineTile ln_tile_anchor(const gpsiq_chan_desc& d, const double* __restrict__ code_ck,
+                                                   const int* __restrict__ wrap_ck, const CarrLookup& carr, int e, int c,
+                                                   int t, int C, int N, int ntiles, int dbg) {
+    LineTile r;
+    const size_t o = ((size_t) e * ntiles + t) * C + c;
+    r.FA = ln_carr_fixed(carr_lookup(carr, e, c, t, LN_TILE, N, C, ntiles));
+    r.GA = ln_code_fixed(code_ck[o]);
+    // NAV polarity at the tile start and after the next code-period wrap (plutogpssim.c:2714-2733)
+    const int wr = wrap_ck[o] + d.ms0 % 20;
+    const uint32_t pol0 = (uint32_t) (d.navbits >> ((wr / 20) & 63)) & 1u;
+    const uint32_t pol1 = (uint32_t) (d.navbits >> (((wr + 1) / 20) & 63)) & 1u;
+    r.Fs = r.FA;
+    r.Gs = r.GA + ((uint64_t) ((pol0 * 2 + pol1) * LN_VS) << LN_GBITS);
+    if (dbg & LN_DBG_PERTURB) { r.Fs += (uint64_t) (1 + t % 3) << 49; r.Gs += (uint64_t) (t % 5) << 42; }
+    return r;
+}
+
 __global__ void __launch_bounds__(128)
 k_line_anchor(const gpsiq_chan_desc* __restrict__ desc, const double* __restrict__ code_ck,
               const int* __restrict__ wrap_ck, const CarrLookup carr, const int* __restrict__ amp_sum,
               int* __restrict__ step_flag, ulonglong2* __restrict__ anch, uint32_t* __restrict__ hazlist,
               int* __restrict__ counters, int haz_cap, int E, int C, int N, int ntiles, int dbg) {
     const int lane = threadIdx.x & 31;
-    const int chunks = (ntiles + LN_CHUNK - 1) / LN_CHUNK;
-    int w = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const int ch = w % chunks; w /= chunks;
-    const int c = w % C;
-    const int e = w / C;
+    const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int c = w % C, e = w / C;
     if (e >= E) return;
     const gpsiq_chan_desc d = desc[(size_t) e * C + c];
-    const int t = ch * LN_CHUNK + lane;
-    const bool valid = t < ntiles;
-    const size_t o = ((size_t) e * ntiles + (valid ? t : 0)) * C + c;
+    const int chunks = (ntiles + LN_CHUNK - 1) / LN_CHUNK;
     if (d.prn <= 0 || amp_sum[e] > 32767 || step_flag[e]) {  // inactive slot / epoch rendered by k_synth_lanes
-        if (valid) anch[o] = make_ulonglong2(0, 0);
+        for (int t = lane; t < ntiles; t += 32) anch[((size_t) e * ntiles + t) * C + c] = make_ulonglong2(0, 0);
         return;
     }
     const uint64_t dF = ln_carr_slope(d.carr_step), dG = ln_code_slope(d.code_step);
-    uint64_t FA = 0, GA = 0;
-    if (valid) {
-        FA = ln_carr_fixed(carr_lookup(carr, e, c, t, LN_TILE, N, C, ntiles));
-        GA = ln_code_fixed(code_ck[o]);
-        // NAV polarity at the tile start and after the next code-period wrap (plutogpssim.c:2714-2733)
-        const int wr = wrap_ck[o] + d.ms0 % 20;
-        const uint32_t pol0 = (uint32_t) (d.navbits >> ((wr / 20) & 63)) & 1u;
-        const uint32_t pol1 = (uint32_t) (d.navbits >> (((wr + 1) / 20) & 63)) & 1u;
-        uint64_t Fs = FA, Gs = GA + ((uint64_t) ((pol0 * 2 + pol1) * LN_VS) << LN_GBITS);
-        if (dbg & LN_DBG_PERTURB) { Fs += (uint64_t) (1 + t % 3) << 49; Gs += (uint64_t) (t % 5) << 42; }
-        anch[o] = make_ulonglong2(Fs, Gs);
-    }
-    // ---- chunk-level check: all tiles of the chunk against ONE line from the chunk's first anchor
-    const uint64_t F0 = __shfl_sync(0xffffffffu, FA, 0), G0 = __shfl_sync(0xffffffffu, GA, 0);
     const uint64_t gmask = (1ULL << LN_GBITS) - 1;
-    const uint64_t off = (uint64_t) lane * LN_TILE;
-    int64_t dlF = valid ? (int64_t) (FA - (F0 + off * dF)) : 0;
-    // code: only G mod 2^47 matters (wraps and variant offsets are multiples of 2^47)
-    int64_t dlG = valid ? (int64_t) (((GA - G0 - off * dG) & gmask) << (64 - LN_GBITS)) >> (64 - LN_GBITS) : 0;
-    int64_t loF = dlF, hiF = dlF, loG = dlG, hiG = dlG;
-#pragma unroll
-    for (int s = 16; s; s >>= 1) {
-        loF = min(loF, (int64_t) __shfl_xor_sync(0xffffffffu, loF, s));
-        hiF = max(hiF, (int64_t) __shfl_xor_sync(0xffffffffu, hiF, s));
-        loG = min(loG, (int64_t) __shfl_xor_sync(0xffffffffu, loG, s));
-        hiG = max(hiG, (int64_t) __shfl_xor_sync(0xffffffffu, hiG, s));
-    }
-    const int n_chunk = min(LN_CHUNK * LN_TILE, N - ch * LN_CHUNK * LN_TILE);
     const int64_t eF = ln_eps(1, LN_TILE), eG = ln_eps(0, LN_TILE);
-    bool flagged = (dbg & (LN_DBG_FORCE_CHUNK | LN_DBG_FORCE_TILE)) != 0;
-    if (!flagged) {
+    const bool force = (dbg & (LN_DBG_FORCE_CHUNK | LN_DBG_FORCE_TILE)) != 0;
+    for (int ch0 = 0; ch0 < chunks; ch0 += 16) {  // rounds of 16 chunks (one round up to 524288 samples per epoch)
+        const int nch = min(16, chunks - ch0);
+        uint64_t my_A = 0;       // lane j: F0 of chunk j; lane 16+j: G0 of chunk j
+        int64_t my_lo = 0, my_hi = 0;
+        for (int j = 0; j < nch; j++) {
+            const int t = (ch0 + j) * LN_CHUNK + lane;
+            const bool valid = t < ntiles;
+            LineTile a;
+            a.FA = a.GA = a.Fs = a.Gs = 0;
+            if (valid) {
+                a = ln_tile_anchor(d, code_ck, wrap_ck, carr, e, c, t, C, N, ntiles, dbg);
+                anch[((size_t) e * ntiles + t) * C + c] = make_ulonglong2(a.Fs, a.Gs);
+            }
+            const uint64_t F0 = __shfl_sync(0xffffffffu, a.FA, 0), G0 = __shfl_sync(0xffffffffu, a.GA, 0);
+            const uint64_t off = (uint64_t) lane * LN_TILE;
+            const int64_t dlF = valid ? (int64_t) (a.FA - (F0 + off * dF)) : 0;
+            // code: only G mod 2^47 matters (wraps and variant offsets are multiples of 2^47)
+            const int64_t dlG = valid ? (int64_t) (((a.GA - G0 - off * dG) & gmask) << (64 - LN_GBITS)) >> (64 - LN_GBITS) : 0;
+            int64_t loF = dlF, hiF = dlF, loG = dlG, hiG = dlG;
+#pragma unroll
+            for (int s = 16; s; s >>= 1) {
+                loF = min(loF, (int64_t) __shfl_xor_sync(0xffffffffu, loF, s));
+                hiF = max(hiF, (int64_t) __shfl_xor_sync(0xffffffffu, hiF, s));
+                loG = min(loG, (int64_t) __shfl_xor_sync(0xffffffffu, loG, s));
+                hiG = max(hiG, (int64_t) __shfl_xor_sync(0xffffffffu, hiG, s));
+            }
+            if (lane == j) { my_A = F0; my_lo = loF - eF; my_hi = hiF + eF; }
+            if (lane == 16 + j) { my_A = G0; my_lo = loG - eG; my_hi = hiG + eG; }
+        }
+        // ---- chunk-level check, all chunks of the round at once
         bool hz = false;
-        if (lane == 0) hz = line_hazard(F0, dF, LN_FBITS, (uint64_t) n_chunk, loF - eF, hiF + eF);
-        if (lane == 1) hz = line_hazard(G0, dG, LN_GBITS, (uint64_t) n_chunk, loG - eG, hiG + eG);
-        flagged = __any_sync(0xffffffffu, hz);
-    }
-    if (!flagged) return;
-    if (lane == 0) atomicAdd(&counters[2], 1);  // diagnostic: flagged chunks
-    // ---- tile-level check from the tile's own exact anchor
-    if (!valid) return;
-    const int len = min(LN_TILE, N - t * LN_TILE);
-    const bool hz = (dbg & LN_DBG_FORCE_TILE) || line_hazard(FA, dF, LN_FBITS, (uint64_t) len, -eF, eF) ||
-                    line_hazard(GA, dG, LN_GBITS, (uint64_t) len, -eG, eG);
-    if (hz) {
-        const int slot = atomicAdd(&counters[0], 1);
-        if (slot < haz_cap) hazlist[slot] = (uint32_t) (e * ntiles + t) * 32u + (uint32_t) c;
-        else atomicOr(&step_flag[e], 4);  // list full: the epoch is re-rendered by k_synth_lanes
+        const int j = lane & 15;
+        if (j < nch && !force) {
+            const int n_chunk = min(LN_CHUNK * LN_TILE, N - (ch0 + j) * LN_CHUNK * LN_TILE);
+            hz = (lane < 16) ? line_hazard(my_A, dF, LN_FBITS, (uint64_t) n_chunk, my_lo, my_hi)
+                             : line_hazard(my_A, dG, LN_GBITS, (uint64_t) n_chunk, my_lo, my_hi);
+        }
+        uint32_t flagged = __ballot_sync(0xffffffffu, hz);
+        flagged = (flagged | (flagged >> 16)) & 0xffffu;
+        if (force) flagged = (1u << nch) - 1u;
+        if (lane == 0 && flagged) atomicAdd(&counters[2], __popc(flagged));  // diagnostic: flagged chunks
+        // ---- tile-level check of the flagged chunks, each tile from its own exact anchor
+        while (flagged) {
+            const int jj = __ffs(flagged) - 1;
+            flagged &= flagged - 1;
+            const int t = (ch0 + jj) * LN_CHUNK + lane;
+            if (t >= ntiles) continue;
+            const LineTile a = ln_tile_anchor(d, code_ck, wrap_ck, carr, e, c, t, C, N, ntiles, dbg);
+            const int len = min(LN_TILE, N - t * LN_TILE);
+            const bool hzt = (dbg & LN_DBG_FORCE_TILE) || line_hazard(a.FA, dF, LN_FBITS, (uint64_t) len, -eF, eF) ||
+                             line_hazard(a.GA, dG, LN_GBITS, (uint64_t) len, -eG, eG);
+            if (hzt) {
+                const int slot = atomicAdd(&counters[0], 1);
+                if (slot < haz_cap) hazlist[slot] = (uint32_t) (e * ntiles + t) * 32u + (uint32_t) c;
+                else atomicOr(&step_flag[e], 4);  // list full: the epoch is re-rendered by k_synth_lanes
+            }
+        }
     }
 }
 
@@ -218,66 +248,92 @@ __device__ __forceinline__ int32_t ln_lds_lut(uint32_t base, uint32_t idx) {
     return v;
 }
 
+// Work is handed out in units of LN_UNIT consecutive tiles of one epoch through an atomic counter
+// (sched[0]; sched[1] counts finished CTAs and the last one resets both, so the pair is reusable
+// without a memset).  Dynamic hand-out keeps every resident CTA busy to the end when the kernel
+// shares the GPU with the scan kernels of the next batch and fewer CTAs than launched fit at once.
+// A CTA re-stages the amplitude LUTs when the epoch of its unit changes, and a slot's chip tables
+// only when its PRN changes.
+#define LN_UNIT 8
+
 __global__ void __launch_bounds__(LN_THREADS, 2)
 k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict__ lutp,
              const int8_t* __restrict__ chips4, const ulonglong2* __restrict__ anch,
              const int* __restrict__ amp_sum, const int* __restrict__ step_flag, int16_t* __restrict__ iq,
-             int E, int C, int N, int ntiles, int* __restrict__ err) {
+             int E, int C, int N, int ntiles, unsigned int* __restrict__ sched, int* __restrict__ err) {
     extern __shared__ __align__(16) unsigned char ln_raw[];
     const int CG = ln_group_slots(C), ngroups = ln_groups(C);
     int8_t* s_chip = (int8_t*) ln_raw;                                   // [CG][4][LN_VS]
     int32_t* s_lut = (int32_t*) (ln_raw + (size_t) CG * 4 * LN_VS);      // [CG][512]
-    ulonglong2* s_step = (ulonglong2*) (s_lut + (size_t) CG * 512);      // [16] {dF, dG}; dF == dG == 0: inactive
+    ulonglong2* s_step = (ulonglong2*) (s_lut + (size_t) CG * 512);      // [16] {dF, dG}; dG == 0: inactive
     ulonglong2* s_anch = s_step + 16;                                    // [LN_WARPS][16]
+    int* s_prn = (int*) (s_anch + LN_WARPS * 16);                        // [16] PRN whose chip tables are resident
+    int* s_unit = s_prn + 16;
     const uint32_t chip_saddr = (uint32_t) __cvta_generic_to_shared(s_chip);
     const uint32_t lut_saddr = (uint32_t) __cvta_generic_to_shared(s_lut);
     if (chip_saddr + (uint32_t) CG * 4 * LN_VS > (1u << (64 - LN_GBITS))) {  // the chip address must fit G's index field
         if (threadIdx.x == 0) atomicExch(err, 0x40000000);
         return;
     }
-
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     ulonglong2* my_anch = s_anch + warp * 16;
-    const long long tiles_total = (long long) E * ntiles;
-    const long long tg_begin = tiles_total * blockIdx.x / gridDim.x, tg_end = tiles_total * (blockIdx.x + 1) / gridDim.x;
     const int wb_epoch = (N + LN_WB - 1) / LN_WB;
+    const int upe = (ntiles + LN_UNIT - 1) / LN_UNIT;  // units per epoch
+    const unsigned int nunits = (unsigned int) E * upe;
+    constexpr int WPT = LN_TILE / LN_WB;               // warp-blocks per tile
+    if (threadIdx.x < 16) s_prn[threadIdx.x] = -1;
+    int cur_e = -1;
 
-    for (long long tg = tg_begin; tg < tg_end;) {
-        const int e = (int) (tg / ntiles);
-        const int t0 = (int) (tg - (long long) e * ntiles);
-        const int t1 = (int) min((long long) ntiles, t0 + (tg_end - tg));
-        tg += t1 - t0;
+    for (;;) {
+        __syncthreads();  // everyone is done with the previous unit (tables, s_unit)
+        if (threadIdx.x == 0) *s_unit = (int) atomicAdd(&sched[0], 1u);
+        __syncthreads();
+        const unsigned int unit = (unsigned int) *s_unit;
+        if (unit >= nunits) break;
+        const int e = (int) (unit / upe);
+        const int t0 = (int) (unit - (unsigned int) e * upe) * LN_UNIT;
+        const int t1 = min(ntiles, t0 + LN_UNIT);
         if (amp_sum[e] > 32767 || step_flag[e]) continue;  // rendered by k_synth_lanes (uniform per CTA)
         const gpsiq_chan_desc* de = desc + (size_t) e * C;
         uint32_t* out_epoch = reinterpret_cast<uint32_t*>(iq) + (size_t) e * N;
-        const int wb0 = t0 * (LN_TILE / LN_WB), wb1 = min(t1 * (LN_TILE / LN_WB), wb_epoch);
+        const int wb0 = t0 * WPT, wb1 = min(t1 * WPT, wb_epoch);
         for (int g = 0; g < ngroups; g++) {
             const int c0 = g * CG, nc = min(CG, C - c0);
-            __syncthreads();  // everyone is done with the previous tables
-            for (int i = threadIdx.x; i < nc * (4 * LN_VS / 16); i += LN_THREADS) {
-                const int cl = i / (4 * LN_VS / 16), k = i - cl * (4 * LN_VS / 16);
-                const int prn = de[c0 + cl].prn;
-                if (prn > 0 && prn <= 32)
-                    ((uint4*) s_chip)[i] = ((const uint4*) (chips4 + (size_t) prn * 4 * LN_VS))[k];
-            }
-            for (int i = threadIdx.x; i < nc * 128; i += LN_THREADS) {
-                const int cl = i >> 7;
-                if (de[c0 + cl].prn > 0)
-                    ((uint4*) s_lut)[i] = ((const uint4*) (lutp + ((size_t) e * C + c0 + cl) * 512))[i & 127];
-            }
-            if (threadIdx.x < 16) {
-                ulonglong2 s = make_ulonglong2(0, 0);
-                if (threadIdx.x < nc && de[c0 + threadIdx.x].prn > 0) {
-                    s.x = ln_carr_slope(de[c0 + threadIdx.x].carr_step);
-                    s.y = ln_code_slope(de[c0 + threadIdx.x].code_step);  // > 0 for every active slot
+            if (ngroups > 1 || e != cur_e) {
+                if (g > 0) __syncthreads();  // everyone is done with the previous group's tables
+                // chip tables: only the slots whose PRN differs from what is resident
+                for (int cl = 0; cl < nc; cl++) {
+                    const int prn = de[c0 + cl].prn;
+                    if (prn > 0 && prn <= 32 && prn != s_prn[cl]) {
+                        const uint4* src = (const uint4*) (chips4 + (size_t) prn * 4 * LN_VS);
+                        uint4* dst = (uint4*) (s_chip + (size_t) cl * 4 * LN_VS);
+                        for (int i = threadIdx.x; i < 4 * LN_VS / 16; i += LN_THREADS) dst[i] = src[i];
+                    }
                 }
-                s_step[threadIdx.x] = s;
+                for (int i = threadIdx.x; i < nc * 128; i += LN_THREADS) {
+                    const int cl = i >> 7;
+                    if (de[c0 + cl].prn > 0)
+                        ((uint4*) s_lut)[i] = ((const uint4*) (lutp + ((size_t) e * C + c0 + cl) * 512))[i & 127];
+                }
+                __syncthreads();  // all reads of s_prn above are done
+                if (threadIdx.x < 16) {
+                    ulonglong2 st = make_ulonglong2(0, 0);
+                    if (threadIdx.x < nc) {
+                        const int prn = de[c0 + threadIdx.x].prn;
+                        if (prn > 0 && prn <= 32) {
+                            s_prn[threadIdx.x] = prn;
+                            st.x = ln_carr_slope(de[c0 + threadIdx.x].carr_step);
+                            st.y = ln_code_slope(de[c0 + threadIdx.x].code_step);  // > 0 for every active slot
+                        }
+                    }
+                    s_step[threadIdx.x] = st;
+                }
+                __syncthreads();
             }
-            __syncthreads();
 
             for (int wb = wb0 + warp; wb < wb1; wb += LN_WARPS) {
-                const int tile = wb >> 2;
-                const uint32_t m0 = (uint32_t) ((wb & 3) * LN_WB + lane);  // sample offset inside the tile
+                const int tile = wb / WPT;
+                const uint32_t m0 = (uint32_t) ((wb % WPT) * LN_WB + lane);  // sample offset inside the tile
                 __syncwarp();
                 if (lane < nc) my_anch[lane] = anch[((size_t) e * ntiles + tile) * C + c0 + lane];
                 __syncwarp();
@@ -317,6 +373,12 @@ k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
                 }
             }
         }
+        cur_e = e;
+    }
+    // the last CTA to leave resets the scheduler for the next launch
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) { sched[0] = 0; sched[1] = 0; __threadfence(); }
     }
 }
 
