@@ -234,6 +234,11 @@ int gpsiq_line_stats(gpsiq_ctx *ctx, int64_t *hazard_tiles, int64_t *patches, in
 uint64_t gpsiq_minmod_host(uint64_t b, uint64_t a, uint64_t m, uint64_t n, uint64_t stop);
 int gpsiq_line_probe_host(int mode, double x0, double step, int n, int64_t *max_dev, int *mismatches, int *hazard);
 
+/* Diagnostics: with GPSIQ_TRACE set in the environment the context records a CUDA event after every kernel it
+ * launches; this prints them to stderr as milliseconds since the first one (stream 0 = caller / render stream,
+ * 1 = scan stream, 2 = code-scan side stream).  reset != 0 clears the record. */
+int gpsiq_trace_dump(gpsiq_ctx *ctx, int reset);
+
 const char *gpsiq_strerror(int status);
 const char *gpsiq_last_error(const gpsiq_ctx *ctx);
 const char *gpsiq_version(void);

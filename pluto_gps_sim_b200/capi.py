@@ -89,6 +89,7 @@ SYMBOLS = {
     "gpsiq_render_device": (_i, [_vp, _vp, _i, _vp, _vp]),
     "gpsiq_carrier_to_device": (_i, [_vp, _vp, _vp]),
     "gpsiq_carrier_from_device": (_i, [_vp, _vp, _vp]),
+    "gpsiq_trace_dump": (_i, [_vp, _i]),
     "gpsiq_line_stats": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "gpsiq_minmod_host": (C.c_uint64, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
     "gpsiq_line_probe_host": (_i, [_i, _d, _d, _i, C.POINTER(_i64), C.POINTER(_i), C.POINTER(_i)]),

@@ -69,6 +69,11 @@ static void ca_generate(int prn, uint8_t* chips) {
 // ---------------------------------------------------------------------------
 #define TIMING_RING 64
 
+// Optional timeline trace (GPSIQ_TRACE=1 in the environment): an event after every kernel launch,
+// dumped by gpsiq_trace_dump as milliseconds since the first one.  Diagnostics only.
+#define TRACE_MAX 4096
+struct TraceRec { cudaEvent_t ev; const char* label; int stream_id; };
+
 #define FX_SUB_EPOCHS 8   // 8 epochs x 37 CTAs = 296 = 148 SMs x 2 resident 512-thread CTAs: one full wave; the
                           // sub-batch's records + corrections (~42 MB at 12 slots) stay in L2 between the kernels
 
@@ -81,7 +86,7 @@ struct ScanSet {
     BinadeTab* d_tab; double* d_drift; CarrSpec* d_spec; CarrSpec* d_specE; ChunkInfo* d_cinfo; CarrInfo* d_info;
     CarrSpec* d_specG; GroupInfo* d_ginfo; double* d_traceG;
     double* d_adv; double* d_carr_trace;
-    cudaEvent_t scan_done, render_done;
+    cudaEvent_t scan_done, render_done, spec_done;
     const gpsiq_chan_desc* desc;  // the batch's descriptors (device)
     int n_epochs;
     int phase;                    // 0 free, 1 prepared, 2 speculated, 3 chained (waiting to be rendered)
@@ -158,10 +163,23 @@ struct gpsiq_ctx {
     int* d_err;
     int last_epochs;
     int64_t launches;
+    int trace_on, trace_n;
+    TraceRec* trace;
     char err[256];
 };
 
+static void trace_mark(gpsiq_ctx* ctx, cudaStream_t st, const char* label) {
+    if (!ctx->trace_on || ctx->trace_n >= TRACE_MAX) return;
+    TraceRec& r = ctx->trace[ctx->trace_n];
+    if (!r.ev) cudaEventCreate(&r.ev);
+    r.label = label;
+    r.stream_id = (st == ctx->scan_stream) ? 1 : (st == ctx->aux2_stream) ? 2 : (st == ctx->aux_stream) ? 3 : (st == ctx->copy_stream) ? 4 : 0;
+    cudaEventRecord(r.ev, st);
+    ctx->trace_n++;
+}
+
 static char g_err[256];
+
 
 static int fail(gpsiq_ctx* ctx, int code, const char* what, cudaError_t ce) {
     char* dst = ctx ? ctx->err : g_err;
@@ -870,6 +888,8 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
     ctx = (gpsiq_ctx*) calloc(1, sizeof *ctx);
     if (!ctx) return GPSIQ_ERR_NOMEM;
     ctx->cfg = *cfg;
+    ctx->trace_on = getenv("GPSIQ_TRACE") != NULL;
+    if (ctx->trace_on) ctx->trace = (TraceRec*) calloc(TRACE_MAX, sizeof(TraceRec));
     ctx->sm_count = prop.multiProcessorCount;
     ctx->C = cfg->max_chan;
     ctx->N = cfg->samples_per_epoch;
@@ -938,6 +958,7 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
         CU(cudaMalloc(&ss.d_carr_trace, EC * sizeof(double)));
         CU(cudaEventCreateWithFlags(&ss.scan_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ss.render_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ss.spec_done, cudaEventDisableTiming));
         ss.n_epochs = 0;
     }
     use_set(ctx, 0);
@@ -1043,7 +1064,7 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
         cudaFree(ss.d_wrap_ck); cudaFree(ss.d_carr_ck); cudaFree(ss.d_tab); cudaFree(ss.d_drift); cudaFree(ss.d_spec);
         cudaFree(ss.d_specE); cudaFree(ss.d_cinfo); cudaFree(ss.d_info); cudaFree(ss.d_adv); cudaFree(ss.d_carr_trace);
         cudaFree(ss.d_specG); cudaFree(ss.d_ginfo); cudaFree(ss.d_traceG);
-        cudaEventDestroy(ss.scan_done); cudaEventDestroy(ss.render_done);
+        cudaEventDestroy(ss.scan_done); cudaEventDestroy(ss.render_done); cudaEventDestroy(ss.spec_done);
         cudaFree(ctx->d_recs[i]); cudaFree(ctx->d_fixmasks[i]); cudaFree(ctx->d_delta[i]); cudaFree(ctx->d_work[i]);
     }
     cudaFree(ctx->d_chips4); cudaFree(ctx->d_anch[0]); cudaFree(ctx->d_anch[1]); cudaFree(ctx->d_hazlist);
@@ -1092,9 +1113,11 @@ static int enqueue_prepare(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int 
     k_prepare<<<EC, 128, 0, st>>>(desc_dev, ctx->d_lut, ctx->d_lutp, ctx->d_tab, ctx->d_drift, ctx->d_flags,
                                   ctx->d_flags + ctx->E, C, N, ctx->cfg.carrier_mode, ctx->d_err);
     ctx->launches += 1;
+    trace_mark(ctx, st, "k_prepare");
     if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT) {
         k_slice_advance<<<C, 32, 0, st>>>(ctx->d_drift, ctx->d_drift + (size_t) EC, ctx->d_adv, n_epochs, C);
         ctx->launches += 1;
+        trace_mark(ctx, st, "k_slice_advance");
     }
     ctx->last_epochs = n_epochs;
     CU(cudaGetLastError());
@@ -1114,20 +1137,26 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
     CU(cudaStreamWaitEvent(aux, fork, 0));
     k_scan_code<<<(EC + 63) / 64, 64, 0, aux>>>(desc_dev, ctx->d_tab, ctx->d_code_ck, ctx->d_wrap_ck, EC, C, N, T, ntiles);
     CU(cudaEventRecord(ctx->ev_code2, aux));
+    trace_mark(ctx, aux, "k_scan_code");
     ctx->launches += 1;
     if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && ctx->cfg.reserved[0] == 0) {
         const size_t ECmax = (size_t) ctx->E * C;
         double* eadv = ctx->d_drift;
         double* ereset = ctx->d_drift + (size_t) EC;      // k_prepare wrote it at [gridDim.x + ec] with gridDim.x = EC
         double* est_epoch = ctx->d_drift + 2 * ECmax;
+        trace_mark(ctx, st, "(speculate begin)");
         k_epoch_estimates<<<C, 32, 0, st>>>(eadv, ereset, ctx->d_est_state, est_epoch, n_epochs, C);
+        trace_mark(ctx, st, "k_epoch_estimates");
         const int chains = EC * ctx->J * 2;
         k_carr_speculate<<<(chains + 127) / 128, 128, 0, st>>>(desc_dev, ctx->d_tab, eadv, est_epoch, ctx->d_carr_ck,
                                                          ctx->ck_plane, ctx->d_spec, n_epochs, C, N, T, ntiles, ctx->G,
                                                          ctx->J);
+        trace_mark(ctx, st, "k_carr_speculate");
+        CU(cudaEventRecord(ctx->sets[ctx->set_wr].spec_done, st));
         k_carr_stitch<<<(EC * 2 + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, est_epoch, ctx->d_spec, ctx->d_carr_ck,
                                                       ctx->ck_plane, ctx->d_cinfo, ctx->d_specE, n_epochs, C, N, T,
                                                       ntiles, ctx->G, ctx->J);
+        trace_mark(ctx, st, "k_carr_stitch");
         {
             const int ngroups = (n_epochs + GROUP_EPOCHS - 1) / GROUP_EPOCHS;
             k_carr_group<<<(ngroups * C * 2 + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_specE, est_epoch,
@@ -1135,6 +1164,7 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
                                                                    ctx->d_traceG, ctx->d_specG, ctx->d_fallbacks, n_epochs,
                                                                    C, N, T, ntiles);
         }
+        trace_mark(ctx, st, "k_carr_group");
         k_est_fold<<<1, 32, 0, st>>>(ctx->d_est_state, ctx->d_adv, C);
         ctx->launches += 5;
     }
@@ -1158,6 +1188,7 @@ static int enqueue_chain(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_
                                          n_epochs, C, N, T, ntiles, ctx->cfg.carrier_mode);
     }
     ctx->launches += 1;
+    trace_mark(ctx, st, "k_carr_final");
     CU(cudaMemcpyAsync(ctx->d_est_state, ctx->d_carr_state, C * sizeof(double), cudaMemcpyDeviceToDevice, st));
     CU(cudaStreamWaitEvent(st, ctx->ev_code2, 0));  // scan_done covers the code scan on the side stream too
     ScanSet& set = ctx->sets[ctx->set_wr];
@@ -1189,11 +1220,20 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
         return fail(ctx, GPSIQ_ERR_ARG, "nothing to render (scan phases of a batch must complete first)", cudaSuccess);
     ScanSet& set = ctx->sets[ctx->set_rd];
     CU(cudaStreamWaitEvent(st, set.scan_done, 0));
+    if (ctx->set_pending >= 2 && ctx->sets[ctx->set_rd ^ 1].phase >= 2 && ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT &&
+        ctx->cfg.reserved[0] == 0) {
+        // Another batch has been submitted ahead.  Its chunk speculation wants the whole GPU (one chain per
+        // thread, as many resident as possible) while the sample kernel below is issue-bound and holds on to
+        // the SMs it gets: let the speculation finish first; the rest of that batch's carrier chain (few,
+        // latency-bound threads) then runs beside the sample kernel.
+        CU(cudaStreamWaitEvent(st, ctx->sets[ctx->set_rd ^ 1].spec_done, 0));
+    }
     use_set(ctx, ctx->set_rd);
     const gpsiq_chan_desc* desc_dev = set.desc;
     const int n_epochs = set.n_epochs;
     const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
     if (ctx->ev_count < TIMING_RING) CU(cudaEventRecord(ctx->ev[ctx->ev_count][1], st));
+    trace_mark(ctx, st, "(render begin)");
     const int tile_groups = (ntiles + LANES_WARPS - 1) / LANES_WARPS;
     const size_t smem = (size_t) C * 512 * sizeof(int2) + (size_t) C * 33 * 4;
     // everything below needs the chain's result; the aux stream (already holding the code scan) joins here
@@ -1207,6 +1247,7 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
         k_line_anchor<<<(warps + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx),
                                                        ctx->d_flags, ctx->d_flags + ctx->E, anch, ctx->d_hazlist,
                                                        ctx->d_line_counters, ctx->haz_cap, n_epochs, C, N, ntiles, dbg);
+        trace_mark(ctx, st, "k_line_anchor");
         // the (tile, slot) pairs the check could not clear: literal recurrence, compared with the anchors' lines
         k_line_patch<<<(dbg & LN_DBG_FORCE_TILE) ? 1024 : 8, 128, 0, st>>>(
             desc_dev, ctx->d_lutp, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx), anch, ctx->d_chips4, ctx->d_hazlist,
@@ -1226,6 +1267,7 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
                 anch + (size_t) e0 * ntiles * C, ctx->d_flags + e0, ctx->d_flags + ctx->E + e0,
                 iq_dev + (size_t) e0 * N * 2, ne, C, N, ntiles, ctx->d_sched + 2 * (k & 31), ctx->d_err);
             if (timed) CU(cudaEventRecord(ctx->ev[ctx->ev_count][4], st));
+            trace_mark(ctx, st, "k_synth_line");
             ctx->last_ln.desc = desc_dev + (size_t) e0 * C; ctx->last_ln.iq = iq_dev + (size_t) e0 * N * 2;
             ctx->last_ln.ne = ne; ctx->last_ln.set = ctx->set_cur;
             ctx->last_ln.e0 = e0;
@@ -1303,6 +1345,7 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
         CU(cudaEventRecord(ctx->ev[ctx->ev_count][2], st));
         ctx->ev_count++;
     }
+    trace_mark(ctx, st, "(render end)");
     CU(cudaEventRecord(set.render_done, st));
     set.phase = 0;
     ctx->set_rd ^= 1;
@@ -1619,6 +1662,19 @@ int gpsiq_timing_sample_kernel(gpsiq_ctx* ctx, int* n_launches, float* kernel_ms
     if (n_launches) *n_launches = n;
     if (kernel_ms) *kernel_ms = a;
     if (epochs_per_launch) *epochs_per_launch = ctx->fixed_epochs;
+    return GPSIQ_OK;
+}
+
+int gpsiq_trace_dump(gpsiq_ctx* ctx, int reset) {
+    if (!ctx) return GPSIQ_ERR_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaDeviceSynchronize());
+    for (int i = 0; i < ctx->trace_n; i++) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, ctx->trace[0].ev, ctx->trace[i].ev);
+        fprintf(stderr, "trace %9.3f ms  stream %d  %s\n", t, ctx->trace[i].stream_id, ctx->trace[i].label);
+    }
+    if (reset) ctx->trace_n = 0;
     return GPSIQ_OK;
 }
 

@@ -256,7 +256,9 @@ __device__ __forceinline__ int32_t ln_lds_lut(uint32_t base, uint32_t idx) {
 // only when its PRN changes.
 #define LN_UNIT 8
 
-__global__ void __launch_bounds__(LN_THREADS, 2)
+// 48 registers: two CTAs use 3/4 of an SM's register file, so that the small latency-bound kernels of the
+// next batch's carrier chain (stitch / group / final, code scan) can run beside it
+__global__ void __maxnreg__(48)
 k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict__ lutp,
              const int8_t* __restrict__ chips4, const ulonglong2* __restrict__ anch,
              const int* __restrict__ amp_sum, const int* __restrict__ step_flag, int16_t* __restrict__ iq,

@@ -75,6 +75,10 @@ def run_batches(count):
 
 run_batches(3)
 torch.cuda.synchronize()
+if os.environ.get("GPSIQ_TRACE"):
+    capi.lib.gpsiq_trace_dump(s._ctx, 1)
+    run_batches(4)
+    capi.lib.gpsiq_trace_dump(s._ctx, 1)
 a, b = ev(), ev()
 a.record()
 run_batches(20)
