@@ -254,7 +254,7 @@ __device__ __forceinline__ int32_t ln_lds_lut(uint32_t base, uint32_t idx) {
 // shares the GPU with the scan kernels of the next batch and fewer CTAs than launched fit at once.
 // A CTA re-stages the amplitude LUTs when the epoch of its unit changes, and a slot's chip tables
 // only when its PRN changes.
-#define LN_UNIT 8
+#define LN_UNIT 32
 
 // 48 registers: two CTAs use 3/4 of an SM's register file, so that the small latency-bound kernels of the
 // next batch's carrier chain (stitch / group / final, code scan) can run beside it
