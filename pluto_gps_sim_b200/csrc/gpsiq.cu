@@ -122,7 +122,6 @@ struct gpsiq_ctx {
     ulonglong2* d_anch[2];   // [E][ntiles][C] tile anchors {F, G} (one buffer per scan set)
     uint32_t* d_hazlist;  // (tile, slot) pairs k_line_anchor could not clear
     int haz_cap, patch_cap;
-    unsigned int* d_sched;   // [33][2] tile schedulers of k_synth_line (self-resetting)
     int* d_line_counters; // [0] listed hazards, [1] patches, [2] flagged chunks (per batch)
     unsigned long long* d_line_totals;  // the same, accumulated over the context's life
     LinePatch* d_patches;
@@ -484,28 +483,29 @@ __device__ __forceinline__ void stage_group(GroupEpoch* ge, const gpsiq_chan_des
 #define GROUP_EPOCHS 16  // epochs per group (level 3)
 
 // Level 3: one chain per (group, slot, variant): the group's epochs chained from the ESTIMATED group start.
-__global__ void __launch_bounds__(128)
+// One warp per block: 4.6 KB of shared memory, so that the blocks fit beside two resident k_synth_line CTAs.
+__global__ void __launch_bounds__(32)
 k_carr_group(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
              const CarrSpec* __restrict__ specE, const double* __restrict__ est_epoch, double* __restrict__ carr_ck,
              size_t ck_plane, CarrInfo* __restrict__ infoG, size_t info_plane, double* __restrict__ traceG,
              CarrSpec* __restrict__ specG, int* __restrict__ fallbacks, int E, int C, int N, int T, int ntiles) {
-    __shared__ GroupEpoch s_ge[4][GROUP_EPOCHS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ GroupEpoch s_ge[GROUP_EPOCHS];
+    const int lane = threadIdx.x;
     const int ngroups = (E + GROUP_EPOCHS - 1) / GROUP_EPOCHS;
-    const int chain = blockIdx.x * 4 + warp;
+    const int chain = blockIdx.x;
     if (chain >= ngroups * C * 2) return;
     const int V = chain & 1, gc = chain >> 1;
     const int g = gc / C, c = gc - g * C;
     const int first = g * GROUP_EPOCHS, count = min(GROUP_EPOCHS, E - first);
-    stage_group(s_ge[warp], desc, tabs, specE, first, count, c, C, lane);
+    stage_group(s_ge, desc, tabs, specE, first, count, c, C, lane);
     if (lane) return;
     CarrSpec out;
     out.margin = -1.0; out.n1 = -1; out.xw1 = 0.0; out.xend = 0.0; out.pad = 0;
     bool any_neg = false;
-    for (int k = 0; k < count; k++) any_neg |= s_ge[warp][k].active && s_ge[warp][k].d < 0.0;
+    for (int k = 0; k < count; k++) any_neg |= s_ge[k].active && s_ge[k].d < 0.0;
     if (V == 0 || any_neg) {
         int fb = 0;
-        group_chain(est_epoch[(size_t) first * C + c], s_ge[warp], count, N, T, V,
+        group_chain(est_epoch[(size_t) first * C + c], s_ge, count, N, T, V,
                     carr_ck + (size_t) (4 + V) * ck_plane + (size_t) first * ntiles * C + c, (size_t) C, (size_t) ntiles * C,
                     infoG + (size_t) V * info_plane + (size_t) first * C + c, (size_t) C,
                     traceG + (size_t) V * info_plane + (size_t) first * C + c, (size_t) C, out, fb);
@@ -962,8 +962,14 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
         ss.n_epochs = 0;
     }
     use_set(ctx, 0);
-    CU(cudaStreamCreateWithFlags(&ctx->scan_stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&ctx->aux2_stream, cudaStreamNonBlocking));
+    {
+        // the scan streams carry small latency-bound kernels that must get onto the SMs beside the sample
+        // kernel of the previous batch: highest priority
+        int prio_lo = 0, prio_hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CU(cudaStreamCreateWithPriority(&ctx->scan_stream, cudaStreamNonBlocking, prio_hi));
+        CU(cudaStreamCreateWithPriority(&ctx->aux2_stream, cudaStreamNonBlocking, prio_hi));
+    }
     CU(cudaMalloc(&ctx->d_fallbacks, sizeof(int)));
     CU(cudaMemset(ctx->d_fallbacks, 0, sizeof(int)));
     CU(cudaMalloc(&ctx->d_carr_state, ctx->C * sizeof(double)));
@@ -1012,6 +1018,14 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
         }
     }
     if (ctx->use_line) {
+        // The kernels meant to run beside k_synth_line (the rest of the next batch's carrier chain) ask for the
+        // same (maximum) shared-memory carve-out: an SM cannot change its L1/shared split while blocks are
+        // resident, so a kernel preferring another split would wait for the sample kernel's persistent CTAs
+        // to leave.  The chunk speculation keeps the default split: it lives on L1 (per-thread tables).
+#define CARVE(k) CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared))
+        CARVE(k_synth_line); CARVE(k_carr_stitch); CARVE(k_carr_group); CARVE(k_carr_final); CARVE(k_line_apply);
+        CARVE(k_synth_lanes);
+#undef CARVE
         CU(cudaFuncSetAttribute(k_synth_line, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ln_smem_bytes(ctx->C)));
         const size_t tiles = (size_t) ctx->E * ctx->ntiles;
         for (int i = 0; i < 2; i++) CU(cudaMalloc(&ctx->d_anch[i], tiles * ctx->C * sizeof(ulonglong2)));
@@ -1021,8 +1035,6 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
         CU(cudaMalloc(&ctx->d_hazlist, (size_t) ctx->haz_cap * 4));
         CU(cudaMalloc(&ctx->d_patches, (size_t) ctx->patch_cap * sizeof(LinePatch)));
         CU(cudaMalloc(&ctx->d_line_counters, 4 * sizeof(int)));
-        CU(cudaMalloc(&ctx->d_sched, 33 * 2 * sizeof(unsigned int)));
-        CU(cudaMemset(ctx->d_sched, 0, 33 * 2 * sizeof(unsigned int)));
         CU(cudaMalloc(&ctx->d_line_totals, 4 * sizeof(unsigned long long)));
         CU(cudaMemset(ctx->d_line_totals, 0, 4 * sizeof(unsigned long long)));
         // chip/NAV sign tables: variant v = pol0*2 + pol1; entry k < 1023: chip k under NAV bit pol0,
@@ -1068,7 +1080,7 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
         cudaFree(ctx->d_recs[i]); cudaFree(ctx->d_fixmasks[i]); cudaFree(ctx->d_delta[i]); cudaFree(ctx->d_work[i]);
     }
     cudaFree(ctx->d_chips4); cudaFree(ctx->d_anch[0]); cudaFree(ctx->d_anch[1]); cudaFree(ctx->d_hazlist);
-    cudaFree(ctx->d_patches); cudaFree(ctx->d_line_counters); cudaFree(ctx->d_sched); cudaFree(ctx->d_line_totals);
+    cudaFree(ctx->d_patches); cudaFree(ctx->d_line_counters); cudaFree(ctx->d_line_totals);
     cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_est_state); cudaFree(ctx->d_ca);
     cudaFree(ctx->d_iq); cudaFree(ctx->d_iq2); cudaFree(ctx->d_sums); cudaFree(ctx->d_err);
     if (ctx->h_stage[0]) cudaFreeHost(ctx->h_stage[0]);
@@ -1159,7 +1171,7 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
         trace_mark(ctx, st, "k_carr_stitch");
         {
             const int ngroups = (n_epochs + GROUP_EPOCHS - 1) / GROUP_EPOCHS;
-            k_carr_group<<<(ngroups * C * 2 + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_specE, est_epoch,
+            k_carr_group<<<ngroups * C * 2, 32, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_specE, est_epoch,
                                                                    ctx->d_carr_ck, ctx->ck_plane, ctx->d_info, ECmax,
                                                                    ctx->d_traceG, ctx->d_specG, ctx->d_fallbacks, n_epochs,
                                                                    C, N, T, ntiles);
@@ -1220,14 +1232,6 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
         return fail(ctx, GPSIQ_ERR_ARG, "nothing to render (scan phases of a batch must complete first)", cudaSuccess);
     ScanSet& set = ctx->sets[ctx->set_rd];
     CU(cudaStreamWaitEvent(st, set.scan_done, 0));
-    if (ctx->set_pending >= 2 && ctx->sets[ctx->set_rd ^ 1].phase >= 2 && ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT &&
-        ctx->cfg.reserved[0] == 0) {
-        // Another batch has been submitted ahead.  Its chunk speculation wants the whole GPU (one chain per
-        // thread, as many resident as possible) while the sample kernel below is issue-bound and holds on to
-        // the SMs it gets: let the speculation finish first; the rest of that batch's carrier chain (few,
-        // latency-bound threads) then runs beside the sample kernel.
-        CU(cudaStreamWaitEvent(st, ctx->sets[ctx->set_rd ^ 1].spec_done, 0));
-    }
     use_set(ctx, ctx->set_rd);
     const gpsiq_chan_desc* desc_dev = set.desc;
     const int n_epochs = set.n_epochs;
@@ -1253,19 +1257,25 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
             desc_dev, ctx->d_lutp, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx), anch, ctx->d_chips4, ctx->d_hazlist,
             ctx->d_line_counters, ctx->haz_cap, ctx->d_patches, ctx->patch_cap, ctx->d_flags + ctx->E, C, N, ntiles);
         ctx->launches += 2;
+        if (ctx->set_pending >= 2 && ctx->sets[ctx->set_rd ^ 1].phase >= 2 && ctx->cfg.reserved[0] == 0) {
+            // Another batch has been submitted ahead.  Its chunk speculation wants the whole GPU (one chain per
+            // thread, as many resident as possible) while the sample kernel below is issue-bound and holds on to
+            // the SMs it gets: let the speculation finish first (the anchor kernel above ran beside it); the rest
+            // of that batch's carrier chain (few, latency-bound threads) then runs beside the sample kernel.
+            CU(cudaStreamWaitEvent(st, ctx->sets[ctx->set_rd ^ 1].spec_done, 0));
+        }
         // device-resident output: one launch; host output: sub-batches so that the copies overlap the rendering
         const int sub = iq_host ? 32 : n_epochs;
         int k = 0;
         for (int e0 = 0; e0 < n_epochs; e0 += sub, k++) {
             const int ne = n_epochs - e0 < sub ? n_epochs - e0 : sub;
-            const long long tiles = (long long) ne * ntiles;
-            const int grid = (int) (tiles < 2LL * ctx->sm_count ? tiles : 2LL * ctx->sm_count);
+            const int grid = ne * ((ntiles + LN_UNIT - 1) / LN_UNIT);
             const bool timed = (k == 0 && ctx->ev_count < TIMING_RING);
             if (timed) { CU(cudaEventRecord(ctx->ev[ctx->ev_count][3], st)); ctx->fixed_epochs = ne; }
             k_synth_line<<<grid, LN_THREADS, ln_smem_bytes(C), st>>>(
                 desc_dev + (size_t) e0 * C, ctx->d_lutp + (size_t) e0 * C * 512, ctx->d_chips4,
                 anch + (size_t) e0 * ntiles * C, ctx->d_flags + e0, ctx->d_flags + ctx->E + e0,
-                iq_dev + (size_t) e0 * N * 2, ne, C, N, ntiles, ctx->d_sched + 2 * (k & 31), ctx->d_err);
+                iq_dev + (size_t) e0 * N * 2, ne, C, N, ntiles, ctx->d_err);
             if (timed) CU(cudaEventRecord(ctx->ev[ctx->ev_count][4], st));
             trace_mark(ctx, st, "k_synth_line");
             ctx->last_ln.desc = desc_dev + (size_t) e0 * C; ctx->last_ln.iq = iq_dev + (size_t) e0 * N * 2;
@@ -1624,12 +1634,11 @@ int gpsiq_timing_sample_kernel_isolated(gpsiq_ctx* ctx, int reps, float* kernel_
         if (i == 1) CU(cudaEventRecord(e0, ctx->stream));
         if (line) {
             const int ne = ctx->last_ln.ne, le0 = ctx->last_ln.e0;
-            const long long tiles = (long long) ne * ntiles;
-            const int grid = (int) (tiles < 2LL * ctx->sm_count ? tiles : 2LL * ctx->sm_count);
+            const int grid = ne * ((ntiles + LN_UNIT - 1) / LN_UNIT);
             k_synth_line<<<grid, LN_THREADS, ln_smem_bytes(C), ctx->stream>>>(
                 ctx->last_ln.desc, ctx->d_lutp + (size_t) le0 * C * 512, ctx->d_chips4,
                 ctx->d_anch[ctx->last_ln.set] + (size_t) le0 * ntiles * C, ctx->d_flags + le0, ctx->d_flags + ctx->E + le0,
-                ctx->last_ln.iq, ne, C, N, ntiles, ctx->d_sched + 2 * 32, ctx->d_err);
+                ctx->last_ln.iq, ne, C, N, ntiles, ctx->d_err);
         } else {
             k_synth_fixed<<<ctx->last_fx.ne * groups, FX_WORKERS * FX_THREADS, fx_smem_bytes(C), ctx->stream>>>(
                 ctx->last_fx.desc, ctx->d_lutp, ctx->d_tab, ctx->d_recs[b], ctx->d_delta[b], ctx->d_chips, ctx->d_flags,

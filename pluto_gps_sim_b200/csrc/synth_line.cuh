@@ -248,12 +248,10 @@ __device__ __forceinline__ int32_t ln_lds_lut(uint32_t base, uint32_t idx) {
     return v;
 }
 
-// Work is handed out in units of LN_UNIT consecutive tiles of one epoch through an atomic counter
-// (sched[0]; sched[1] counts finished CTAs and the last one resets both, so the pair is reusable
-// without a memset).  Dynamic hand-out keeps every resident CTA busy to the end when the kernel
-// shares the GPU with the scan kernels of the next batch and fewer CTAs than launched fit at once.
-// A CTA re-stages the amplitude LUTs when the epoch of its unit changes, and a slot's chip tables
-// only when its PRN changes.
+// One CTA per unit of LN_UNIT consecutive tiles of one epoch.  The CTAs are deliberately NOT persistent:
+// they retire every ~100 us, so the hardware block scheduler can place the small latency-bound kernels of
+// the next batch's carrier chain (launched on higher-priority streams) beside this kernel as slots free up.
+// A persistent variant with its own tile scheduler was ~3 % faster alone but starved those kernels.
 #define LN_UNIT 32
 
 // 48 registers: two CTAs use 3/4 of an SM's register file, so that the small latency-bound kernels of the
@@ -262,7 +260,7 @@ __global__ void __maxnreg__(48)
 k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict__ lutp,
              const int8_t* __restrict__ chips4, const ulonglong2* __restrict__ anch,
              const int* __restrict__ amp_sum, const int* __restrict__ step_flag, int16_t* __restrict__ iq,
-             int E, int C, int N, int ntiles, unsigned int* __restrict__ sched, int* __restrict__ err) {
+             int E, int C, int N, int ntiles, int* __restrict__ err) {
     extern __shared__ __align__(16) unsigned char ln_raw[];
     const int CG = ln_group_slots(C), ngroups = ln_groups(C);
     int8_t* s_chip = (int8_t*) ln_raw;                                   // [CG][4][LN_VS]
@@ -270,7 +268,6 @@ k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
     ulonglong2* s_step = (ulonglong2*) (s_lut + (size_t) CG * 512);      // [16] {dF, dG}; dG == 0: inactive
     ulonglong2* s_anch = s_step + 16;                                    // [LN_WARPS][16]
     int* s_prn = (int*) (s_anch + LN_WARPS * 16);                        // [16] PRN whose chip tables are resident
-    int* s_unit = s_prn + 16;
     const uint32_t chip_saddr = (uint32_t) __cvta_generic_to_shared(s_chip);
     const uint32_t lut_saddr = (uint32_t) __cvta_generic_to_shared(s_lut);
     if (chip_saddr + (uint32_t) CG * 4 * LN_VS > (1u << (64 - LN_GBITS))) {  // the chip address must fit G's index field
@@ -285,13 +282,10 @@ k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
     constexpr int WPT = LN_TILE / LN_WB;               // warp-blocks per tile
     if (threadIdx.x < 16) s_prn[threadIdx.x] = -1;
     int cur_e = -1;
+    (void) E;
 
-    for (;;) {
-        __syncthreads();  // everyone is done with the previous unit (tables, s_unit)
-        if (threadIdx.x == 0) *s_unit = (int) atomicAdd(&sched[0], 1u);
-        __syncthreads();
-        const unsigned int unit = (unsigned int) *s_unit;
-        if (unit >= nunits) break;
+    for (unsigned int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+        __syncthreads();  // everyone is done with the previous unit's tables
         const int e = (int) (unit / upe);
         const int t0 = (int) (unit - (unsigned int) e * upe) * LN_UNIT;
         const int t1 = min(ntiles, t0 + LN_UNIT);
@@ -376,11 +370,6 @@ k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
             }
         }
         cur_e = e;
-    }
-    // the last CTA to leave resets the scheduler for the next launch
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) { sched[0] = 0; sched[1] = 0; __threadfence(); }
     }
 }
 
