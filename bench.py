@@ -46,10 +46,12 @@ NAV_FIXTURE = os.path.join(REPO, "tests", "golden", "brdc3540_synth.14n.gz")
 REF_BIN = os.path.join(REPO, "oracle", "_ref", "ref_harness_O2")
 REF_BIN_O0 = os.path.join(REPO, "oracle", "_ref", "ref_harness_O0")
 REF_ARGS = ["-e", NAV_FIXTURE, "-l", "30.286502,120.032669,100", "-s", "2600000"]
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_synth_fixed launch (8 epochs, 12 slots) from the
-# ncu --set full capture summarised in profiles/r01_c_render_kernels_ncu_full.txt (the output itself is
-# still in L2 when the kernel ends; the reads are the tile records and corrections)
-TRAFFIC_PER_LAUNCH = {"k_synth_fixed": 37450240, "k_synth_line": None}
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from ncu --set full captures, per EPOCH
+# (300000 samples x 12 slots) so that it scales to the launch the roofline is quoted on:
+#   k_synth_line   600381440 B for a 512-epoch launch (profiles/r01_i_synth_line_ncu_full.txt): 42.5 MB read
+#                  (tables, anchors) + 557.9 MB written of the 614.4 MB of output (the rest is still in L2)
+#   k_synth_fixed  37450240 B for an 8-epoch launch (profiles/r01_c_render_kernels_ncu_full.txt)
+TRAFFIC_PER_EPOCH = {"k_synth_line": 600381440 / 512, "k_synth_fixed": 37450240 / 8}
 WORKLOAD = "config[1]: static -l 30.286502,120.032669,100, synthetic brdc3540.14n, 2.6 MS/s, 12 channels, 300000 samples/epoch"
 
 
@@ -210,7 +212,7 @@ def ours_arm(args):
     stream = torch.cuda.Stream()                 # everything below is enqueued on this stream
     torch.cuda.set_stream(stream)
     engine = GpuSliceEngine(synth)
-    runner = TimeSliceRunner(engine, rank, world)
+    runner = TimeSliceRunner(engine, rank, world, deferred_render=True)
 
     def barrier():
         torch.cuda.synchronize()
@@ -358,7 +360,7 @@ def ours_arm(args):
                     "d2h_bytes_per_step": samples_per_step * 4},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 5), "traffic": TRAFFIC_PER_LAUNCH.get(dom), "peak_source": peak_src,
+                         "frac": round(achieved / peak, 5), "traffic": int(TRAFFIC_PER_EPOCH[dom] * (kern_bytes // (N_SAMPLES * 4))) if C == 12 else None, "peak_source": peak_src,
                          "kernel": kern_name, "kernel_ms_per_launch": round(kern_ms, 4),
                          "algorithmic_bytes_per_launch": kern_bytes,
                          "kernel_ms_in_pipeline": round(kms / kn, 4) if kn else None,

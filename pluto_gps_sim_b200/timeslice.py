@@ -45,7 +45,7 @@ class GpuSliceEngine:
         self.adv = torch.zeros(2 * synth.max_chan, dtype=torch.float64, device="cuda")
         # scan phases and the hand-offs run on their own stream, ahead of the render stream: with the
         # context's two scan sets the next slice is prepared / speculated / chained while this one renders
-        self.scan_stream = torch.cuda.Stream()
+        self.scan_stream = torch.cuda.Stream(priority=-1)   # small latency-bound kernels: ahead of the sample kernel
 
     def scan_context(self, order_after_caller=False):
         # The scan stream must not be ordered after the caller's stream in steady state (that would
@@ -84,12 +84,19 @@ class GpuSliceEngine:
 
 
 class TimeSliceRunner:
-    def __init__(self, engine, rank=None, world=None):
+    def __init__(self, engine, rank=None, world=None, deferred_render=False):
+        """deferred_render: step k enqueues the scan phases of slice k and then the rendering of slice k-1
+        (the last slice is rendered by finish()).  The device then sees the next slice's chunk speculation
+        before this slice's sample kernel, which is the order gpsiq_submit/gpsiq_fetch produce on one GPU:
+        the speculation runs first at full occupancy and the rest of the chain beside the sample kernel.
+        An `out` buffer passed to step k is complete only after step k+1 (or finish) has been enqueued."""
         self.engine = engine
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
         self.step_index = 0
         self.prev_adv = None
+        self.deferred = deferred_render
+        self.pending = None
 
     def step(self, desc, n_epochs, out):
         """Synthesize this rank's slice of the next step.
@@ -102,7 +109,12 @@ class TimeSliceRunner:
         ctx = eng.scan_context(self.step_index == 0) if hasattr(eng, "scan_context") else contextlib.nullcontext()
         with ctx:
             self._scan_phases(desc, n_epochs)
-        eng.render(desc, n_epochs, out)
+        if self.deferred:
+            if self.pending is not None:
+                eng.render(*self.pending)
+            self.pending = (desc, n_epochs, out)
+        else:
+            eng.render(desc, n_epochs, out)
         self.step_index += 1
 
     def _scan_phases(self, desc, n_epochs):
@@ -132,7 +144,11 @@ class TimeSliceRunner:
             dist.send(eng.phase, dst=(r + 1) % n)
 
     def finish(self):
-        """Drain the last hand-off (rank 0 receives the phases after the final slice)."""
+        """Render the slice still pending (deferred_render) and drain the last hand-off (rank 0 receives
+        the phases after the final slice)."""
+        if self.pending is not None:
+            self.engine.render(*self.pending)
+            self.pending = None
         if self.world > 1 and self.rank == 0 and self.step_index > 0:
             eng = self.engine
             ctx = eng.scan_context() if hasattr(eng, "scan_context") else contextlib.nullcontext()

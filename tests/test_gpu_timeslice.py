@@ -18,7 +18,7 @@ E = 16
 STEPS = 9
 
 
-def _worker(rank, world, port, outdir):
+def _worker(rank, world, port, outdir, deferred=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -27,29 +27,35 @@ def _worker(rank, world, port, outdir):
 
     desc = ol.load_golden_desc("circle12")
     synth = Synthesizer(max_chan=12, max_epochs=E, device=rank)
-    runner = TimeSliceRunner(GpuSliceEngine(synth), rank, world)
-    out = torch.empty(E * 300000 * 2, dtype=torch.int16, device="cuda")
+    runner = TimeSliceRunner(GpuSliceEngine(synth), rank, world, deferred_render=deferred)
+    outs = [torch.empty(E * 300000 * 2, dtype=torch.int16, device="cuda") for _ in range(2)]
     sums = []
     for s in range(STEPS):
         first = (s * world + rank) * E
         d = torch.from_numpy(desc[first:first + E].copy().view(np.uint8).reshape(-1)).cuda()
-        runner.step(d, E, out)
+        runner.step(d, E, outs[s & 1])
         torch.cuda.synchronize()
-        sums.append(synth.checksum_device(out.data_ptr(), E))
+        if not deferred:
+            sums.append(synth.checksum_device(outs[s & 1].data_ptr(), E))
+        elif s > 0:                              # slice s-1 was rendered by this step
+            sums.append(synth.checksum_device(outs[(s - 1) & 1].data_ptr(), E))
     runner.finish()
     torch.cuda.synchronize()
+    if deferred:
+        sums.append(synth.checksum_device(outs[(STEPS - 1) & 1].data_ptr(), E))
     np.save(os.path.join(outdir, "sums%d.npy" % rank), np.stack(sums))
     np.save(os.path.join(outdir, "fb%d.npy" % rank), np.array([synth.carrier_fallbacks]))
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_time_slices_match_reference(tmp_path):
+@pytest.mark.parametrize("deferred", [False, True])
+def test_two_gpu_time_slices_match_reference(tmp_path, deferred):
     world = 2
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), deferred), nprocs=world, join=True)
     meta = ol.load_golden_meta("circle12")
     parts = [np.load(tmp_path / ("sums%d.npy" % r)) for r in range(world)]
     got = np.concatenate([parts[r][s] for s in range(STEPS) for r in range(world)])
