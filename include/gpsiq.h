@@ -199,6 +199,16 @@ int gpsiq_estimate_fold_device(gpsiq_ctx *ctx, const double *advance_dev, void *
 int gpsiq_estimate_anchor_device(gpsiq_ctx *ctx, void *cuda_stream);
 /* Copy the carrier state (max_chan doubles) to / from DEVICE memory on a stream
  * (e.g. the buffer of an NCCL send / recv). */
+/* Time-sliced runs keep the start-phase ESTIMATE on its own (speculation) stream, decoupled from the exact
+ * chain: with GPSIQ_OPT_CHAIN_KEEPS_ESTIMATE set, gpsiq_chain_device no longer re-anchors the estimate on the
+ * exact phase; gpsiq_estimate_to_device saves it, and gpsiq_estimate_correct_device feeds back
+ * gain * (an older saved estimate - the exact phase later found for the same instant).  Estimates only ever
+ * affect speed (how often the serial fallback runs), never a sample. */
+#define GPSIQ_OPT_CHAIN_KEEPS_ESTIMATE 1
+int gpsiq_set_option(gpsiq_ctx *ctx, int option, int value);
+int gpsiq_estimate_to_device(gpsiq_ctx *ctx, double *dst_dev, void *cuda_stream);
+int gpsiq_estimate_correct_device(gpsiq_ctx *ctx, const double *exact_old_dev, const double *est_old_dev, double gain,
+                                  void *cuda_stream);
 int gpsiq_carrier_to_device(gpsiq_ctx *ctx, double *dst_dev, void *cuda_stream);
 int gpsiq_carrier_from_device(gpsiq_ctx *ctx, const double *src_dev, void *cuda_stream);
 

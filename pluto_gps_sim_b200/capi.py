@@ -20,6 +20,7 @@ KERNEL_AUTO, KERNEL_LANE_PER_CHANNEL, KERNEL_FIXED_POINT, KERNEL_LINE = 0, 1, 2,
 LINE_DBG_FORCE_CHUNK, LINE_DBG_FORCE_TILE, LINE_DBG_PERTURB = 1, 2, 4
 MAX_CHAN = 32
 NCO_CODE, NCO_CARRIER = 0, 1
+OPT_CHAIN_KEEPS_ESTIMATE = 1
 
 # numpy view of gpsiq_chan_desc (64 bytes, include/gpsiq.h)
 DESC_DTYPE = np.dtype(
@@ -87,6 +88,9 @@ SYMBOLS = {
     "gpsiq_estimate_fold_device": (_i, [_vp, _vp, _vp]),
     "gpsiq_estimate_anchor_device": (_i, [_vp, _vp]),
     "gpsiq_render_device": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "gpsiq_set_option": (_i, [_vp, _i, _i]),
+    "gpsiq_estimate_to_device": (_i, [_vp, _vp, _vp]),
+    "gpsiq_estimate_correct_device": (_i, [_vp, _vp, _vp, _d, _vp]),
     "gpsiq_carrier_to_device": (_i, [_vp, _vp, _vp]),
     "gpsiq_carrier_from_device": (_i, [_vp, _vp, _vp]),
     "gpsiq_trace_dump": (_i, [_vp, _i]),

@@ -116,6 +116,7 @@ struct gpsiq_ctx {
     int32_t* d_lutp;      // [E][C][512] packed (Q << 16) + I
     int8_t* d_chips;      // [33][2048] +-1, index = polarity << 10 | chip
     int* d_flags;         // [2][E]: amplitude sum per epoch, step-contract flag per epoch
+    int chain_keeps_estimate;  // GPSIQ_OPT_CHAIN_KEEPS_ESTIMATE
     int use_fixed;        // k_synth_fixed is eligible for this configuration
     int use_line;         // k_synth_line (the production kernel) is eligible for this configuration
     int8_t* d_chips4;     // [33][4][LN_VS] +-1: chip/NAV sign tables in 4 polarity variants, extended past chip 1022
@@ -168,7 +169,8 @@ struct gpsiq_ctx {
 };
 
 static void trace_mark(gpsiq_ctx* ctx, cudaStream_t st, const char* label) {
-    if (!ctx->trace_on || ctx->trace_n >= TRACE_MAX) return;
+    if (!ctx->trace_on) return;
+    if (ctx->trace_n >= TRACE_MAX) ctx->trace_n = 0;  // ring
     TraceRec& r = ctx->trace[ctx->trace_n];
     if (!r.ev) cudaEventCreate(&r.ev);
     r.label = label;
@@ -376,6 +378,17 @@ __global__ void k_est_fold(double* __restrict__ est, const double* __restrict__ 
     est[c] = frac01((adv[C + c] != 0.0) ? adv[c] : est[c] + adv[c]);
 }
 
+// est <- est - gain * (est_old - exact_old): feeds a measured estimate error of an earlier slice back
+// (time-sliced runs, where the estimate is never re-anchored on the exact phase directly)
+__global__ void k_est_correct(double* __restrict__ est, const double* __restrict__ exact_old,
+                              const double* __restrict__ est_old, double gain, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double diff = est_old[c] - exact_old[c];
+    diff -= rint(diff);
+    est[c] = frac01(est[c] - gain * diff);
+}
+
 // Estimated phase at the start of every epoch of the batch, from the context's batch-start estimate.
 __global__ void __launch_bounds__(32)
 k_epoch_estimates(const double* __restrict__ eadv, const double* __restrict__ ereset,
@@ -465,10 +478,10 @@ __global__ void k_carr_stitch(const gpsiq_chan_desc* __restrict__ desc, const Bi
 __device__ __forceinline__ void stage_group(GroupEpoch* ge, const gpsiq_chan_desc* __restrict__ desc,
                                             const BinadeTab* __restrict__ tabs, const CarrSpec* __restrict__ specE,
                                             int first, int count, int c, int C, int lane) {
-    if (lane < count) {
-        const size_t ec = (size_t) (first + lane) * C + c;
+    for (int i = lane; i < count; i += 32) {
+        const size_t ec = (size_t) (first + i) * C + c;
         const gpsiq_chan_desc d = desc[ec];
-        GroupEpoch& g = ge[lane];
+        GroupEpoch& g = ge[i];
         g.d = d.carr_step;
         g.phase0 = d.carr_phase0;
         g.active = d.prn > 0;
@@ -480,7 +493,7 @@ __device__ __forceinline__ void stage_group(GroupEpoch* ge, const gpsiq_chan_des
     __syncwarp();
 }
 
-#define GROUP_EPOCHS 16  // epochs per group (level 3)
+#define GROUP_EPOCHS 64  // epochs per group (level 3): the final, serial chain does one head scan per group
 
 // Level 3: one chain per (group, slot, variant): the group's epochs chained from the ESTIMATED group start.
 // One warp per block: 4.6 KB of shared memory, so that the blocks fit beside two resident k_synth_line CTAs.
@@ -529,16 +542,34 @@ k_carr_final(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restri
     int fb = 0;
     for (int g = 0; g < ngroups; g++) {
         const int first = g * GROUP_EPOCHS, count = min(GROUP_EPOCHS, E - first);
-        stage_group(s_ge, desc, tabs, specE, first, count, c, C, lane);
-        if (lane == 0) {
-            GroupInfo gi;
-            const size_t o = (size_t) first * C + c;
-            x = group_final(x, s_ge, count, N, T, specG[((size_t) g * C + c) * 2], specG[((size_t) g * C + c) * 2 + 1],
-                            carr_ck + 6 * ck_plane + (size_t) first * ntiles * C + c, (size_t) C, (size_t) ntiles * C,
-                            infoG + 2 * info_plane + o, (size_t) C, traceG + o, traceG + info_plane + o, carr_trace + o,
-                            (size_t) C, gi, fb);
-            ginfo[(size_t) g * C + c] = gi;
+        const size_t o = (size_t) first * C + c;
+        const CarrSpec sG0 = specG[((size_t) g * C + c) * 2], sG1 = specG[((size_t) g * C + c) * 2 + 1];
+        double* ckX = carr_ck + 6 * ck_plane + (size_t) first * ntiles * C + c;
+        // Fast path (almost always taken): the group's first epoch is active, wraps, and the group trajectory
+        // fits from there.  Only that epoch's inputs are staged; the serial work is its head scan, and the
+        // lanes translate the post-epoch phases of the other epochs in parallel.
+        stage_group(s_ge, desc, tabs, specE, first, 1, c, C, lane);
+        const double x_start = x;
+        GroupInfo gi;
+        gi.delta = 0.0; gi.pos = 0x7fffffff; gi.variant = 0;
+        int fb_try = 0;
+        if (lane == 0)
+            x = group_final(x_start, s_ge, 1, N, T, sG0, sG1, ckX, (size_t) C, (size_t) ntiles * C, infoG + 2 * info_plane + o,
+                            (size_t) C, traceG + o, traceG + info_plane + o, carr_trace + o, (size_t) C, gi, fb_try);
+        const int pos = __shfl_sync(0xffffffffu, gi.pos, 0);
+        if (pos < N) {  // translated inside the first epoch
+            const double diff = __shfl_sync(0xffffffffu, gi.delta, 0);
+            const int v = __shfl_sync(0xffffffffu, gi.variant, 0);
+            const double* tg = traceG + (v ? info_plane : 0) + o;
+            for (int e2 = 1 + lane; e2 < count; e2 += 32) carr_trace[o + (size_t) e2 * C] = add_rn(tg[(size_t) e2 * C], diff);
+        } else {        // anything else: the general chain over the whole group, from the group's start state
+            stage_group(s_ge, desc, tabs, specE, first, count, c, C, lane);
+            if (lane == 0)
+                x = group_final(x_start, s_ge, count, N, T, sG0, sG1, ckX, (size_t) C, (size_t) ntiles * C,
+                                infoG + 2 * info_plane + o, (size_t) C, traceG + o, traceG + info_plane + o, carr_trace + o,
+                                (size_t) C, gi, fb);
         }
+        if (lane == 0) ginfo[(size_t) g * C + c] = gi;
         __syncwarp();
     }
     if (lane == 0) {
@@ -1025,6 +1056,14 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
 #define CARVE(k) CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared))
         CARVE(k_synth_line); CARVE(k_carr_stitch); CARVE(k_carr_group); CARVE(k_carr_final); CARVE(k_line_apply);
         CARVE(k_synth_lanes);
+        // ... and the big latency-bound kernels ask for a split that still leaves ~32 KB of shared memory, so that
+        // the chain kernels of ANOTHER slice (k_carr_final: 19 KB per block; the ring of a time-sliced run must
+        // not wait for a speculation kernel to drain) fit beside them
+#define CARVE_PCT(k, pct) CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct))
+        CARVE_PCT(k_carr_speculate, 15); CARVE_PCT(k_scan_code, 15); CARVE_PCT(k_prepare, 15); CARVE_PCT(k_line_anchor, 15);
+        CARVE_PCT(k_line_patch, 15); CARVE_PCT(k_epoch_estimates, 15); CARVE_PCT(k_slice_advance, 15); CARVE_PCT(k_est_fold, 15);
+        CARVE_PCT(k_est_correct, 15);
+#undef CARVE_PCT
 #undef CARVE
         CU(cudaFuncSetAttribute(k_synth_line, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ln_smem_bytes(ctx->C)));
         const size_t tiles = (size_t) ctx->E * ctx->ntiles;
@@ -1063,9 +1102,18 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
     return GPSIQ_OK;
 }
 
+int gpsiq_trace_dump(gpsiq_ctx* ctx, int reset);
+
 void gpsiq_destroy(gpsiq_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
+    if (ctx->trace_on && getenv("GPSIQ_TRACE")[0] == '2') {  // GPSIQ_TRACE=2: dump the last records at destruction
+        if (ctx->trace_n > 120) {  // keep the tail
+            for (int i = 0; i < 120; i++) { TraceRec t = ctx->trace[i]; ctx->trace[i] = ctx->trace[ctx->trace_n - 120 + i]; ctx->trace[ctx->trace_n - 120 + i] = t; }
+            ctx->trace_n = 120;
+        }
+        gpsiq_trace_dump(ctx, 1);
+    }
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->scan_stream);
     cudaStreamSynchronize(ctx->aux2_stream);
@@ -1201,7 +1249,8 @@ static int enqueue_chain(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_
     }
     ctx->launches += 1;
     trace_mark(ctx, st, "k_carr_final");
-    CU(cudaMemcpyAsync(ctx->d_est_state, ctx->d_carr_state, C * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (!ctx->chain_keeps_estimate)  // re-anchor the estimate on the exact phase (single-stream use)
+        CU(cudaMemcpyAsync(ctx->d_est_state, ctx->d_carr_state, C * sizeof(double), cudaMemcpyDeviceToDevice, st));
     CU(cudaStreamWaitEvent(st, ctx->ev_code2, 0));  // scan_done covers the code scan on the side stream too
     ScanSet& set = ctx->sets[ctx->set_wr];
     CU(cudaEventRecord(set.scan_done, st));
@@ -1511,6 +1560,29 @@ int gpsiq_estimate_anchor_device(gpsiq_ctx* ctx, void* stream) {
     return GPSIQ_OK;
 }
 
+int gpsiq_set_option(gpsiq_ctx* ctx, int option, int value) {
+    if (!ctx) return GPSIQ_ERR_ARG;
+    if (option == GPSIQ_OPT_CHAIN_KEEPS_ESTIMATE) { ctx->chain_keeps_estimate = value != 0; return GPSIQ_OK; }
+    return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_set_option: unknown option", cudaSuccess);
+}
+
+int gpsiq_estimate_to_device(gpsiq_ctx* ctx, double* dst_dev, void* stream) {
+    if (!ctx || !dst_dev) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_estimate_to_device: bad argument", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaMemcpyAsync(dst_dev, ctx->d_est_state, ctx->C * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t) stream));
+    return GPSIQ_OK;
+}
+
+int gpsiq_estimate_correct_device(gpsiq_ctx* ctx, const double* exact_old_dev, const double* est_old_dev, double gain,
+                                  void* stream) {
+    if (!ctx || !exact_old_dev || !est_old_dev) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_estimate_correct_device: bad argument", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    k_est_correct<<<1, 32, 0, (cudaStream_t) stream>>>(ctx->d_est_state, exact_old_dev, est_old_dev, gain, ctx->C);
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    return GPSIQ_OK;
+}
+
 int gpsiq_render_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, int16_t* iq_dev, void* stream) {
     (void) desc_dev;
     if (!ctx || !iq_dev || n_epochs < 1 || ((uintptr_t) iq_dev & 15) || ctx->set_pending < 1 ||
@@ -1681,7 +1753,7 @@ int gpsiq_trace_dump(gpsiq_ctx* ctx, int reset) {
     for (int i = 0; i < ctx->trace_n; i++) {
         float t = 0.f;
         cudaEventElapsedTime(&t, ctx->trace[0].ev, ctx->trace[i].ev);
-        fprintf(stderr, "trace %9.3f ms  stream %d  %s\n", t, ctx->trace[i].stream_id, ctx->trace[i].label);
+        fprintf(stderr, "trace dev %d %9.3f ms  stream %d  %s\n", ctx->cfg.device, t, ctx->trace[i].stream_id, ctx->trace[i].label);
     }
     if (reset) ctx->trace_n = 0;
     return GPSIQ_OK;

@@ -201,6 +201,16 @@ class Synthesizer:
     def render_device(self, desc_dev_ptr, n_epochs, iq_dev_ptr, stream_ptr=None):
         capi.check(capi.lib.gpsiq_render_device(self._ctx, desc_dev_ptr, n_epochs, iq_dev_ptr, stream_ptr), self._ctx)
 
+    def set_option(self, option, value):
+        capi.check(capi.lib.gpsiq_set_option(self._ctx, int(option), int(value)), self._ctx)
+
+    def estimate_to_device(self, dst_dev_ptr, stream_ptr=None):
+        capi.check(capi.lib.gpsiq_estimate_to_device(self._ctx, dst_dev_ptr, stream_ptr), self._ctx)
+
+    def estimate_correct_device(self, exact_old_ptr, est_old_ptr, gain, stream_ptr=None):
+        capi.check(capi.lib.gpsiq_estimate_correct_device(self._ctx, exact_old_ptr, est_old_ptr, float(gain), stream_ptr),
+                   self._ctx)
+
     def carrier_to_device(self, dst_dev_ptr, stream_ptr=None):
         capi.check(capi.lib.gpsiq_carrier_to_device(self._ctx, dst_dev_ptr, stream_ptr), self._ctx)
 
