@@ -382,7 +382,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--epochs", type=int, default=512, help="epochs per step per GPU (512 -> 614.4 MB of output)")
+    ap.add_argument("--epochs", type=int, default=1024, help="epochs per step per GPU (1024 -> 1228.8 MB of output)")
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
