@@ -1301,10 +1301,16 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
                                                        ctx->d_flags, ctx->d_flags + ctx->E, anch, ctx->d_hazlist,
                                                        ctx->d_line_counters, ctx->haz_cap, n_epochs, C, N, ntiles, dbg);
         trace_mark(ctx, st, "k_line_anchor");
-        // the (tile, slot) pairs the check could not clear: literal recurrence, compared with the anchors' lines
-        k_line_patch<<<(dbg & LN_DBG_FORCE_TILE) ? 1024 : 8, 128, 0, st>>>(
+        // The (tile, slot) pairs the check could not clear (one or two per thousand epochs): literal recurrence,
+        // compared with the anchors' lines.  A serial 1024-sample walk per pair (~150 us): on the side stream,
+        // beside the sample kernel; k_line_apply joins it.  (If its patch list overflowed it flags the epoch and
+        // k_synth_lanes, which runs last, re-renders it.)
+        CU(cudaEventRecord(ctx->ev_P[0], st));
+        CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_P[0], 0));
+        k_line_patch<<<(dbg & LN_DBG_FORCE_TILE) ? 1024 : 8, 128, 0, ctx->aux_stream>>>(
             desc_dev, ctx->d_lutp, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx), anch, ctx->d_chips4, ctx->d_hazlist,
             ctx->d_line_counters, ctx->haz_cap, ctx->d_patches, ctx->patch_cap, ctx->d_flags + ctx->E, C, N, ntiles);
+        CU(cudaEventRecord(ctx->ev_P[1], ctx->aux_stream));
         ctx->launches += 2;
         if (ctx->set_pending >= 2 && ctx->sets[ctx->set_rd ^ 1].phase >= 2 && ctx->cfg.reserved[0] == 0) {
             // Another batch has been submitted ahead.  Its chunk speculation wants the whole GPU (one chain per
@@ -1330,6 +1336,7 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
             ctx->last_ln.desc = desc_dev + (size_t) e0 * C; ctx->last_ln.iq = iq_dev + (size_t) e0 * N * 2;
             ctx->last_ln.ne = ne; ctx->last_ln.set = ctx->set_cur;
             ctx->last_ln.e0 = e0;
+            if (k == 0) CU(cudaStreamWaitEvent(st, ctx->ev_P[1], 0));  // the patch list is complete
             k_line_apply<<<4, 128, 0, st>>>(ctx->d_patches, ctx->d_line_counters, ctx->patch_cap,
                                             reinterpret_cast<uint32_t*>(iq_dev), (unsigned long long) e0 * N,
                                             (unsigned long long) (e0 + ne) * N, e0 == 0 ? ctx->d_line_totals : NULL);
