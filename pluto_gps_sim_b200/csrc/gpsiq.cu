@@ -25,6 +25,7 @@
 #include <string.h>
 
 #include "../../include/gpsiq.h"
+#include "../../include/gpsiq_desc.h"
 #include "nco_scan.cuh"
 #include "synth_fixed.cuh"
 #include "synth_line.cuh"
@@ -746,37 +747,8 @@ int gpsiq_get_ca_code(int prn, uint8_t* chips) {
 int gpsiq_make_desc(gpsiq_chan_desc* out, int carrier_mode, int prn, double f_carr, double f_code, double delt,
                     double carr_phase, double code_phase, const uint64_t* dwrd60, int iword, int ibit, int icode,
                     double gain, int carr_phase_is_new) {
-    if (!out) return GPSIQ_ERR_ARG;
-    memset(out, 0, sizeof *out);
-    if (prn <= 0) return GPSIQ_OK;
-    if (prn > 32 || !dwrd60 || iword < 0 || ibit < 0 || ibit >= 30 || icode < 0 || icode >= 20) return GPSIQ_ERR_ARG;
-    out->prn = prn;
-    out->ms0 = iword * 600 + ibit * 20 + icode;
-    // NAV bit window: bit k = data bit number (iword*30 + ibit + k); words past the
-    // reference's 60-word buffer read as 0 (the reference would over-read, App. A)
-    uint64_t nb = 0;
-    const int b0 = iword * 30 + ibit;
-    for (int k = 0; k < 64; k++) {
-        const int b = b0 + k, w = b / 30;
-        if (w >= 60) break;
-        nb |= ((dwrd60[w] >> (29 - b % 30)) & 1ULL) << k;
-    }
-    out->navbits = nb;
-    out->code_phase0 = code_phase;
-    volatile double cs = f_code * delt;  // the very product of plutogpssim.c:2709, one rounding
-    volatile double ps = f_carr * delt;  // plutogpssim.c:2741
-    out->code_step = cs;
-    if (carrier_mode == GPSIQ_CARRIER_FLOAT) {
-        out->carr_step = ps;
-    } else {
-        volatile double q = 512.0 * 65536.0 * f_carr;
-        q = q * delt;                                  // left-to-right, plutogpssim.c:2675
-        out->carr_step = (double) (int) round(q);
-    }
-    out->carr_phase0 = carr_phase;
-    out->gain = gain;
-    out->flags = carr_phase_is_new ? GPSIQ_FLAG_RESET_CARRIER : 0u;
-    return GPSIQ_OK;
+    return gpsiq_make_desc_inline(out, carrier_mode, prn, f_carr, f_code, delt, carr_phase, code_phase, dwrd60, iword, ibit,
+                                  icode, gain, carr_phase_is_new);
 }
 
 int gpsiq_nco_advance(int mode, double* phase, double step, int64_t count, int64_t* wraps) {

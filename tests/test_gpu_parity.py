@@ -332,3 +332,37 @@ def test_device_path_with_torch_buffers():
         s.synth_device(d.data_ptr(), 10, out.data_ptr(), st)
         torch.cuda.synchronize()
     assert ol.sha256(out.cpu().numpy()) == meta["iq_sha256"]
+
+
+# ---- host orchestrator + command-line front end ------------------------------
+def test_host_orchestrator_descriptors_drive_the_kernels():
+    """navigation file -> libgpshost descriptors -> kernels == the reference's stream (no reference-made input)."""
+    from pluto_gps_sim_b200 import hostapi
+
+    meta = ol.load_golden_meta("static12")
+    nav = os.path.join(ol.GOLDEN, "brdc3540_synth.14n.gz")
+    with hostapi.Scenario(nav, llh=(30.286502, 120.032669, 100), sample_rate=2600000) as sc, \
+            Synthesizer(max_chan=12, max_epochs=10) as s:
+        iq = s.synth(sc.next(10))
+    assert ol.sha256(iq) == meta["iq_sha256"]
+
+
+@pytest.mark.parametrize("scenario,args,epochs", [
+    ("static12", ["-l", "30.286502,120.032669,100", "-s", "2600000", "-d", "1.0"], 10),
+    ("static12", ["-l", "30.286502,120.032669,100", "-s", "2600000", "-d", "1.0", "-b", "3"], 10),
+    ("allsky32", ["-l", "30.286502,120.032669,100", "-s", "10000000", "-d", "2.0", "-n", "32", "-b", "8"], 20),
+])
+def test_command_line_front_end_reproduces_the_reference_stream(tmp_path, scenario, args, epochs):
+    """gpsiq_sim with the reference's options writes byte for byte what the reference pushes to the SDR."""
+    import hashlib
+    import subprocess
+    from pluto_gps_sim_b200 import hostapi
+
+    meta = ol.load_golden_meta(scenario)
+    nav = os.path.join(ol.GOLDEN, "brdc3540_synth.14n.gz" if scenario == "static12" else "allsky32_synth.14n.gz")
+    out = tmp_path / "iq.bin"
+    r = subprocess.run([hostapi.SIM_PATH, "-e", nav, "-o", str(out)] + args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    data = out.read_bytes()
+    assert len(data) == epochs * 300000 * 4
+    assert hashlib.sha256(data).hexdigest() == meta["iq_sha256"], r.stderr

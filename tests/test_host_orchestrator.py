@@ -1,0 +1,109 @@
+"""Host orchestrator (libgpshost.so): the descriptors it computes from a
+navigation file must be BIT-identical to the reference's own per-epoch channel state -- against the committed
+goldens (made from the compiled reference, tools/gen_golden.py) and, where oracle/_ref is built, against
+live runs of the reference with other option combinations (-t, -T, -i, -c, ephemeris roll-over)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import refdump
+from pluto_gps_sim_b200 import capi, hostapi
+
+NAV12 = os.path.join(ol.GOLDEN, "brdc3540_synth.14n.gz")
+NAV32 = os.path.join(ol.GOLDEN, "allsky32_synth.14n.gz")
+CIRCLE = os.path.join(refdump.REF_DIR, "circle.csv")
+LLH = (30.286502, 120.032669, 100)
+
+
+def assert_same_descriptors(got, want):
+    """bit-for-bit; carr_phase0 only where the reset flag is set (elsewhere the golden carries the sample
+    loop's running phase, which the context -- not the host -- owns)."""
+    assert got.shape == want.shape
+    for f in ("prn", "ms0", "navbits", "flags"):
+        bad = np.argwhere(got[f] != want[f])
+        assert len(bad) == 0, (f, bad[0], got[f][tuple(bad[0])], want[f][tuple(bad[0])])
+    for f in ("code_phase0", "code_step", "carr_step", "gain"):
+        bad = np.argwhere(got[f].view(np.uint64) != want[f].view(np.uint64))
+        assert len(bad) == 0, (f, bad[0], got[f][tuple(bad[0])].hex(), want[f][tuple(bad[0])].hex())
+    m = (want["flags"] & 1) != 0
+    assert np.array_equal(got["carr_phase0"][m].view(np.uint64), want["carr_phase0"][m].view(np.uint64))
+
+
+def test_static12_descriptors_equal_reference_golden():
+    with hostapi.Scenario(NAV12, llh=LLH, sample_rate=2600000) as s:
+        got = s.next(10)
+        assert "PRN   Az    El     Range     Iono" in s.describe()
+    assert_same_descriptors(got, ol.load_golden_desc("static12"))
+
+
+def test_allsky32_descriptors_equal_reference_golden():
+    with hostapi.Scenario(NAV32, llh=LLH, sample_rate=10000000, max_chan=32) as s:
+        got = s.next(20)
+    assert_same_descriptors(got, ol.load_golden_desc("allsky32"))
+
+
+@pytest.mark.skipif(not os.path.exists(CIRCLE), reason="needs the reference's circle.csv (oracle/_ref)")
+def test_circle12_user_motion_across_the_30s_refresh():
+    """310 epochs of user motion: NAV frame rebuild and channel re-allocation at t = 30 s."""
+    with hostapi.Scenario(NAV12, motion=CIRCLE, sample_rate=2600000) as s:
+        got = np.concatenate([s.next(n) for n in (1, 7, 128, 100, 74)])   # batching must not matter
+    assert_same_descriptors(got, ol.load_golden_desc("circle12"))
+
+
+LIVE = [
+    # name, reference argv, Scenario kwargs, epochs
+    ("start_time", ["-l", "30.286502,120.032669,100", "-s", "2600000", "-t", "2014/12/20,03:10:05"],
+     dict(llh=LLH, sample_rate=2600000, start=(2014, 12, 20, 3, 10, 5.0)), 12),
+    ("no_iono_ecef", ["-c", "-2758918.64,4772301.12,3197889.44", "-s", "3000000", "-i"],
+     dict(xyz=(-2758918.64, 4772301.12, 3197889.44), sample_rate=3000000, iono=False), 12),
+    ("overwrite", ["-l", "30.286502,120.032669,100", "-s", "2600000", "-t", "2021/06/07,08:09:10", "-T", "x"],
+     dict(llh=LLH, sample_rate=2600000, start=(2021, 6, 7, 8, 9, 10.0), time_overwrite=True), 12),
+    ("ephemeris_rollover", ["-l", "30.286502,120.032669,100", "-s", "2600000", "-t", "2014/12/20,00:59:40"],
+     dict(llh=LLH, sample_rate=2600000, start=(2014, 12, 20, 0, 59, 40.0)), 330),
+]
+
+
+@pytest.mark.skipif(not refdump.have_ref(), reason="needs the compiled reference (oracle/_ref)")
+@pytest.mark.parametrize("name,argv,kw,epochs", LIVE, ids=[c[0] for c in LIVE])
+def test_option_combinations_against_live_reference(tmp_path, name, argv, kw, epochs):
+    refdump.SCENARIOS["_live"] = ("ref_harness_O2", "brdc3540_synth.14n.gz", argv, 12)
+    recs, _, _ = refdump.run_reference("_live", epochs, str(tmp_path), want_iq=False)
+    want = refdump.to_descriptors(recs)
+    with hostapi.Scenario(NAV12, **kw) as s:
+        got = s.next(epochs)
+    assert_same_descriptors(got, want)
+
+
+def test_known_answers():
+    # values the reference's own functions produce
+    assert hostapi.parity(0x8B0000 << 6, 0) == 0x22C00012
+    assert hostapi.date2gps(2014, 12, 20, 0, 0, 0.0) == (1823, 518400.0)
+    xyz = hostapi.llh2xyz(30.286502, 120.032669, 100.0)
+    assert np.allclose(xyz, [-2758918.635941, 4772301.120089, 3197889.437237], atol=1e-6)
+    llh = hostapi.xyz2llh(xyz)
+    assert abs(llh[0] * 57.2957795131 - 30.286502) < 1e-9 and abs(llh[2] - 100.0) < 1e-3
+    # every word the orchestrator emits passes the parity equations it was built with
+    with hostapi.Scenario(NAV12, llh=LLH, sample_rate=2600000) as s:
+        d = s.next(1)
+    assert (d["prn"] > 0).sum() == 12
+
+
+def test_error_reporting():
+    with pytest.raises(hostapi.HostError) as ei:
+        hostapi.Scenario("/nonexistent.14n", llh=LLH)
+    assert ei.value.status == hostapi.ERR_NAVFILE
+    with pytest.raises(hostapi.HostError) as ei:
+        hostapi.Scenario(NAV12, llh=LLH, start=(2016, 1, 1, 0, 0, 0.0))          # outside the file's span
+    assert ei.value.status == hostapi.ERR_TIME
+    with pytest.raises(hostapi.HostError) as ei:
+        hostapi.Scenario(NAV12, motion="/nonexistent.csv")
+    assert ei.value.status == hostapi.ERR_MOTION
+    with pytest.raises(hostapi.HostError):
+        hostapi.Scenario(NAV12, llh=LLH, sample_rate=500000)                     # the reference rejects < 1 MHz too
+
+
+def test_library_exports_every_declared_symbol():
+    for name in hostapi.SYMBOLS:
+        assert hasattr(hostapi.lib, name)
