@@ -366,3 +366,34 @@ def test_command_line_front_end_reproduces_the_reference_stream(tmp_path, scenar
     data = out.read_bytes()
     assert len(data) == epochs * 300000 * 4
     assert hashlib.sha256(data).hexdigest() == meta["iq_sha256"], r.stderr
+
+
+def test_config2_full_300s_user_motion_stream_through_the_front_end():
+    """BASELINE config[2] in full: 3000 epochs (300 s, 3.6 GB) of circle.csv user motion, navigation file in,
+    bytes out, SHA-256 against the reference's own 300 s run (tools/gen_golden_long.py).  Crosses ten 30 s
+    refreshes (NAV frame rebuild, re-allocation) and exercises ~3 of the line kernel's patch-path tiles."""
+    import hashlib
+    import json
+    import subprocess
+    import refdump
+    from pluto_gps_sim_b200 import hostapi
+
+    circle = os.path.join(refdump.REF_DIR, "circle.csv")
+    if not os.path.exists(circle):
+        pytest.skip("needs the reference's circle.csv (oracle/_ref)")
+    with open(os.path.join(ol.GOLDEN, "circle12_300s_meta.json")) as f:
+        meta = json.load(f)
+    nav = os.path.join(ol.GOLDEN, "brdc3540_synth.14n.gz")
+    p = subprocess.Popen([hostapi.SIM_PATH, "-e", nav, "-u", circle, "-s", "2600000", "-d", "300", "-b", "250", "-o", "-"],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    sha, total = hashlib.sha256(), 0
+    while True:
+        buf = p.stdout.read(1 << 24)
+        if not buf:
+            break
+        sha.update(buf)
+        total += len(buf)
+    err = p.stderr.read().decode()
+    assert p.wait() == 0, err
+    assert total == 3000 * 300000 * 4
+    assert sha.hexdigest() == meta["iq_sha256"], err
