@@ -611,6 +611,7 @@ GPSIQ_HD double group_final(double x, const GroupEpoch* ge, int count, int N, in
         int t = 0, n = 0, remaining = 0;
         bool wrapped = false;
         double* ck = ckX + (size_t) eg * epoch_stride;
+        const double x_epoch = x;  // exact phase at the first sample of this epoch
         scan_epoch_head<false>(x, ge[eg].d, ge[eg].tab, N, T, ck, tile_stride, t, n, remaining, wrapped, true, dummy);
         if (!wrapped) { trace[(size_t) eg * trace_stride] = x; continue; }
         const int pos = eg * N + n;
@@ -622,14 +623,15 @@ GPSIQ_HD double group_final(double x, const GroupEpoch* ge, int count, int N, in
             for (int e2 = eg; e2 < count; e2++) trace[(size_t) e2 * trace_stride] = add_rn(tg[(size_t) e2 * trace_stride], diff);
             return add_rn(v ? sG1.xend : sG0.xend, diff);
         }
-        // the group's speculation does not fit: chain the rest of the group exactly
+        // The group's speculation does not fit: chain this and the remaining epochs exactly, each through its
+        // own epoch-level speculation (one head scan + translation per epoch; an epoch scans serially only if
+        // that does not fit either).
         fb++;
-        scan_epoch_head<false>(x, ge[eg].d, ge[eg].tab, N, T, ck, tile_stride, t, n, remaining, wrapped, false, dummy);
-        trace[(size_t) eg * trace_stride] = x;
-        for (int e2 = eg + 1; e2 < count; e2++) {
+        x = x_epoch;
+        for (int e2 = eg; e2 < count; e2++) {
             CarrInfo inf = all_exact;
             if (ge[e2].active) {
-                if (ge[e2].reset) x = ge[e2].phase0;
+                if (e2 > eg && ge[e2].reset) x = ge[e2].phase0;
                 x = group_chain_epoch<false>(x, ge[e2].d, ge[e2].tab, N, T, ge[e2].s0, ge[e2].s1,
                                              ckX + (size_t) e2 * epoch_stride, tile_stride, inf, fb, nullptr, 0, 0);
             }
