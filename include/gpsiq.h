@@ -205,6 +205,10 @@ int gpsiq_estimate_anchor_device(gpsiq_ctx *ctx, void *cuda_stream);
  * gain * (an older saved estimate - the exact phase later found for the same instant).  Estimates only ever
  * affect speed (how often the serial fallback runs), never a sample. */
 #define GPSIQ_OPT_CHAIN_KEEPS_ESTIMATE 1
+/* Rendering a batch while another one has been scanned ahead normally waits only for that batch's chunk
+ * speculation; with this option it waits for its exact chain as well (time-sliced multi-GPU runs: the chain is a
+ * hop of the inter-GPU ring and must not compete with the sample kernel for the SMs). */
+#define GPSIQ_OPT_RENDER_AFTER_NEXT_CHAIN 2
 int gpsiq_set_option(gpsiq_ctx *ctx, int option, int value);
 int gpsiq_estimate_to_device(gpsiq_ctx *ctx, double *dst_dev, void *cuda_stream);
 int gpsiq_estimate_correct_device(gpsiq_ctx *ctx, const double *exact_old_dev, const double *est_old_dev, double gain,

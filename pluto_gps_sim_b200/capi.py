@@ -20,7 +20,7 @@ KERNEL_AUTO, KERNEL_LANE_PER_CHANNEL, KERNEL_FIXED_POINT, KERNEL_LINE = 0, 1, 2,
 LINE_DBG_FORCE_CHUNK, LINE_DBG_FORCE_TILE, LINE_DBG_PERTURB = 1, 2, 4
 MAX_CHAN = 32
 NCO_CODE, NCO_CARRIER = 0, 1
-OPT_CHAIN_KEEPS_ESTIMATE = 1
+OPT_CHAIN_KEEPS_ESTIMATE, OPT_RENDER_AFTER_NEXT_CHAIN = 1, 2
 
 # numpy view of gpsiq_chan_desc (64 bytes, include/gpsiq.h)
 DESC_DTYPE = np.dtype(

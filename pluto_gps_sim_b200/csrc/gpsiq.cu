@@ -118,6 +118,7 @@ struct gpsiq_ctx {
     int8_t* d_chips;      // [33][2048] +-1, index = polarity << 10 | chip
     int* d_flags;         // [2][E]: amplitude sum per epoch, step-contract flag per epoch
     int chain_keeps_estimate;  // GPSIQ_OPT_CHAIN_KEEPS_ESTIMATE
+    int render_after_next_chain;  // GPSIQ_OPT_RENDER_AFTER_NEXT_CHAIN
     int use_fixed;        // k_synth_fixed is eligible for this configuration
     int use_line;         // k_synth_line (the production kernel) is eligible for this configuration
     int8_t* d_chips4;     // [33][4][LN_VS] +-1: chip/NAV sign tables in 4 polarity variants, extended past chip 1022
@@ -1289,7 +1290,12 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
             // thread, as many resident as possible) while the sample kernel below is issue-bound and holds on to
             // the SMs it gets: let the speculation finish first (the anchor kernel above ran beside it); the rest
             // of that batch's carrier chain (few, latency-bound threads) then runs beside the sample kernel.
-            CU(cudaStreamWaitEvent(st, ctx->sets[ctx->set_rd ^ 1].spec_done, 0));
+            // Time-sliced runs (GPSIQ_OPT_RENDER_AFTER_NEXT_CHAIN) wait for that batch's whole chain instead: its
+            // exact step is a hop of the inter-GPU ring, and a hop beside the sample kernel is several times slower
+            // (the chain kernel and the NCCL hand-off wait for SM resources) -- that delay multiplies by the ring
+            // length, while waiting here costs this rank at most the ring's quiet length once.
+            ScanSet& nxt = ctx->sets[ctx->set_rd ^ 1];
+            CU(cudaStreamWaitEvent(st, (ctx->render_after_next_chain && nxt.phase >= 3) ? nxt.scan_done : nxt.spec_done, 0));
         }
         // device-resident output: one launch; host output: sub-batches so that the copies overlap the rendering
         const int sub = iq_host ? 32 : n_epochs;
@@ -1542,6 +1548,7 @@ int gpsiq_estimate_anchor_device(gpsiq_ctx* ctx, void* stream) {
 int gpsiq_set_option(gpsiq_ctx* ctx, int option, int value) {
     if (!ctx) return GPSIQ_ERR_ARG;
     if (option == GPSIQ_OPT_CHAIN_KEEPS_ESTIMATE) { ctx->chain_keeps_estimate = value != 0; return GPSIQ_OK; }
+    if (option == GPSIQ_OPT_RENDER_AFTER_NEXT_CHAIN) { ctx->render_after_next_chain = value != 0; return GPSIQ_OK; }
     return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_set_option: unknown option", cudaSuccess);
 }
 

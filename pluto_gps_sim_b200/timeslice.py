@@ -46,6 +46,9 @@ class GpuSliceEngine:
         # scan phases and the hand-offs run on their own stream, ahead of the render stream: with the
         # context's two scan sets the next slice is prepared / speculated / chained while this one renders
         self.scan_stream = torch.cuda.Stream(priority=-1)   # small latency-bound kernels: ahead of the sample kernel
+        # (GPSIQ_OPT_RENDER_AFTER_NEXT_CHAIN was measured and is NOT enabled: with two scan sets the next prepare
+        # waits for this render, so delaying the render behind the ring serialises speculation, ring and rendering:
+        # 6.6 ms instead of 4.3 ms per step at 2 GPUs)
         # estimate feedback: the closed-form advance of the slices a rank does not own carries a small systematic
         # error (predicted vs actual rounding drift, ~1e-14 cycles per epoch); `bias` integrates, per slot, the
         # difference between the start-phase estimate a slice was speculated from and the exact phase received
