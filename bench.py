@@ -48,10 +48,10 @@ REF_BIN_O0 = os.path.join(REPO, "oracle", "_ref", "ref_harness_O0")
 REF_ARGS = ["-e", NAV_FIXTURE, "-l", "30.286502,120.032669,100", "-s", "2600000"]
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from ncu --set full captures, per EPOCH
 # (300000 samples x 12 slots) so that it scales to the launch the roofline is quoted on:
-#   k_synth_line   600381440 B for a 512-epoch launch (profiles/r01_i_synth_line_ncu_full.txt): 42.5 MB read
-#                  (tables, anchors) + 557.9 MB written of the 614.4 MB of output (the rest is still in L2)
+#   k_synth_line   1255370192 B for a 1024-epoch launch (profiles/r01_m_synth_line_ncu_full.txt): 83.8 MB read
+#                  (tables, anchors) + 1171.6 MB written of the 1228.8 MB of output (the rest is still in L2)
 #   k_synth_fixed  37450240 B for an 8-epoch launch (profiles/r01_c_render_kernels_ncu_full.txt)
-TRAFFIC_PER_EPOCH = {"k_synth_line": 600381440 / 512, "k_synth_fixed": 37450240 / 8}
+TRAFFIC_PER_EPOCH = {"k_synth_line": 1255370192 / 1024, "k_synth_fixed": 37450240 / 8}
 WORKLOAD = "config[1]: static -l 30.286502,120.032669,100, synthetic brdc3540.14n, 2.6 MS/s, 12 channels, 300000 samples/epoch"
 
 
