@@ -117,6 +117,8 @@ struct gpsiq_ctx {
     int32_t* d_lutp;      // [E][C][512] packed (Q << 16) + I
     int8_t* d_chips;      // [33][2048] +-1, index = polarity << 10 | chip
     int* d_flags;         // [2][E]: amplitude sum per epoch, step-contract flag per epoch
+    double* d_bias_rate;  // [C] measured residual of the closed-form epoch advance (cycles per epoch), see k_bias_update
+    double* d_carr_start; // [C] exact phases at the start of the batch being chained
     int chain_keeps_estimate;  // GPSIQ_OPT_CHAIN_KEEPS_ESTIMATE
     int render_after_next_chain;  // GPSIQ_OPT_RENDER_AFTER_NEXT_CHAIN
     int use_fixed;        // k_synth_fixed is eligible for this configuration
@@ -205,12 +207,12 @@ static int fail(gpsiq_ctx* ctx, int code, const char* what, cudaError_t ce) {
 __global__ void k_prepare(const gpsiq_chan_desc* __restrict__ desc, int2* __restrict__ lut,
                           int32_t* __restrict__ lutp, BinadeTab* __restrict__ tab, double* __restrict__ drift,
                           int* __restrict__ amp_sum, int* __restrict__ step_flag, int C, int N, int carrier_mode,
-                          int* __restrict__ err) {
+                          const double* __restrict__ bias_rate, double* __restrict__ eadv_frac, int* __restrict__ err) {
     const int ec = blockIdx.x;
     const gpsiq_chan_desc d = desc[ec];
     int2* out = lut + (size_t) ec * 512;
     if (d.prn <= 0) {
-        if (threadIdx.x == 0) { drift[ec] = 0.0; drift[(size_t) gridDim.x + ec] = -1.0; }
+        if (threadIdx.x == 0) { drift[ec] = 0.0; drift[(size_t) gridDim.x + ec] = -1.0; eadv_frac[ec] = 0.0; }
         return;
     }
     // per-binade fixed-point increments of the two NCOs for this epoch's steps (nco_scan.cuh)
@@ -218,7 +220,15 @@ __global__ void k_prepare(const gpsiq_chan_desc* __restrict__ desc, int2* __rest
     if (threadIdx.x == 32 && carrier_mode == GPSIQ_CARRIER_FLOAT) {
         BinadeTab& tp = tab[(size_t) ec * 2 + 1];
         build_binade_tab<NCO_CARRIER>(d.carr_step, tp);
-        drift[ec] = fma((double) N, d.carr_step, carr_drift_estimate(d.carr_step, tp, N));   // eadv
+        const double dest = carr_drift_estimate(d.carr_step, tp, N);
+        drift[ec] = fma((double) N, d.carr_step, dest);   // eadv: whole-epoch advance in cycles (chunk interpolation)
+        // The same advance modulo one cycle, to full precision: N*step is ~300 cycles, so its double carries only
+        // ~5e-14 of absolute precision -- more than the per-epoch corrections that matter here.  Split the product
+        // exactly (fma), take the fraction of the big part, and add the small terms: the predicted rounding drift
+        // and the slot's measured residual per epoch (k_bias_update).
+        const double p = __dmul_rn((double) N, d.carr_step);
+        const double pe = fma((double) N, d.carr_step, -p);
+        eadv_frac[ec] = (p - floor(p)) + ((pe + dest) - bias_rate[ec % C]);
         drift[(size_t) gridDim.x + ec] = (d.flags & GPSIQ_FLAG_RESET_CARRIER) ? d.carr_phase0 : -1.0;  // ereset
     }
     if (d.prn > 32 || !(d.code_phase0 >= 0.0 && d.code_phase0 < 1023.0) || !(d.code_step > 0.0 && d.code_step < 1023.0)) {
@@ -371,6 +381,20 @@ k_slice_advance(const double* __restrict__ eadv, const double* __restrict__ eres
         __syncwarp();
     }
     if (lane == 0) { adv[c] = x; adv[C + c] = abs_flag; }
+}
+
+// After the exact chain of a batch: how far was the closed-form advance off?  adv[c] is the predicted advance of the
+// slot over the batch (k_slice_advance), start/end its exact phases before/after the chain.  The per-epoch residual
+// is integrated into rate[c], which k_prepare subtracts from later predictions: the predictor's systematic error
+// (~1e-14 cycles per epoch) otherwise grows along a batch until group-level speculations stop fitting.
+// Estimates only: never part of a result.
+__global__ void k_bias_update(const double* __restrict__ adv, const double* __restrict__ start,
+                              const double* __restrict__ end, double* __restrict__ rate, int n_epochs, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C || adv[C + c] != 0.0) return;  // re-seeded inside the batch: adv is an absolute phase
+    double err = adv[c] - (end[c] - start[c]);
+    err -= rint(err);
+    if (fabs(err) < 1e-8) rate[c] += 0.7 * err / (double) n_epochs;
 }
 
 // est = fold(est, adv): est <- adv (absolute) or frac(est + adv)
@@ -949,7 +973,7 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
         CU(cudaMalloc(&ss.d_specE, EC * 2 * sizeof(CarrSpec)));
         CU(cudaMalloc(&ss.d_cinfo, EC * 2 * ctx->J * sizeof(ChunkInfo)));
         CU(cudaMalloc(&ss.d_tab, EC * 2 * sizeof(BinadeTab)));
-        CU(cudaMalloc(&ss.d_drift, 3 * EC * sizeof(double)));
+        CU(cudaMalloc(&ss.d_drift, 4 * EC * sizeof(double)));
         CU(cudaMalloc(&ss.d_spec, EC * 2 * 8 * sizeof(CarrSpec)));
         CU(cudaMalloc(&ss.d_info, 3 * EC * sizeof(CarrInfo)));
         {
@@ -979,6 +1003,9 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
     CU(cudaMalloc(&ctx->d_carr_state, ctx->C * sizeof(double)));
     CU(cudaMalloc(&ctx->d_est_state, ctx->C * sizeof(double)));
     CU(cudaMemset(ctx->d_est_state, 0, ctx->C * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_bias_rate, ctx->C * sizeof(double)));
+    CU(cudaMemset(ctx->d_bias_rate, 0, ctx->C * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_carr_start, ctx->C * sizeof(double)));
     CU(cudaMalloc(&ctx->d_ca, 33 * CA_WORDS * sizeof(uint32_t)));
     CU(cudaMalloc(&ctx->d_iq, (size_t) ctx->E * ctx->N * 4));
     CU(cudaMalloc(&ctx->d_sums, (size_t) ctx->E * sizeof(unsigned long long)));
@@ -1102,6 +1129,7 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
     }
     cudaFree(ctx->d_chips4); cudaFree(ctx->d_anch[0]); cudaFree(ctx->d_anch[1]); cudaFree(ctx->d_hazlist);
     cudaFree(ctx->d_patches); cudaFree(ctx->d_line_counters); cudaFree(ctx->d_line_totals);
+    cudaFree(ctx->d_bias_rate); cudaFree(ctx->d_carr_start);
     cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_est_state); cudaFree(ctx->d_ca);
     cudaFree(ctx->d_iq); cudaFree(ctx->d_iq2); cudaFree(ctx->d_sums); cudaFree(ctx->d_err);
     if (ctx->h_stage[0]) cudaFreeHost(ctx->h_stage[0]);
@@ -1144,11 +1172,12 @@ static int enqueue_prepare(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int 
     if (ctx->ev_count < TIMING_RING && st != ctx->scan_stream) CU(cudaEventRecord(ctx->ev[ctx->ev_count][0], st));
     CU(cudaMemsetAsync(ctx->d_flags, 0, 2 * (size_t) ctx->E * sizeof(int), st));
     k_prepare<<<EC, 128, 0, st>>>(desc_dev, ctx->d_lut, ctx->d_lutp, ctx->d_tab, ctx->d_drift, ctx->d_flags,
-                                  ctx->d_flags + ctx->E, C, N, ctx->cfg.carrier_mode, ctx->d_err);
+                                  ctx->d_flags + ctx->E, C, N, ctx->cfg.carrier_mode, ctx->d_bias_rate,
+                                  ctx->d_drift + 3 * (size_t) ctx->E * C, ctx->d_err);
     ctx->launches += 1;
     trace_mark(ctx, st, "k_prepare");
     if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT) {
-        k_slice_advance<<<C, 32, 0, st>>>(ctx->d_drift, ctx->d_drift + (size_t) EC, ctx->d_adv, n_epochs, C);
+        k_slice_advance<<<C, 32, 0, st>>>(ctx->d_drift + 3 * (size_t) ctx->E * C, ctx->d_drift + (size_t) EC, ctx->d_adv, n_epochs, C);
         ctx->launches += 1;
         trace_mark(ctx, st, "k_slice_advance");
     }
@@ -1178,7 +1207,7 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
         double* ereset = ctx->d_drift + (size_t) EC;      // k_prepare wrote it at [gridDim.x + ec] with gridDim.x = EC
         double* est_epoch = ctx->d_drift + 2 * ECmax;
         trace_mark(ctx, st, "(speculate begin)");
-        k_epoch_estimates<<<C, 32, 0, st>>>(eadv, ereset, ctx->d_est_state, est_epoch, n_epochs, C);
+        k_epoch_estimates<<<C, 32, 0, st>>>(ctx->d_drift + 3 * ECmax, ereset, ctx->d_est_state, est_epoch, n_epochs, C);
         trace_mark(ctx, st, "k_epoch_estimates");
         const int chains = EC * ctx->J * 2;
         k_carr_speculate<<<(chains + 127) / 128, 128, 0, st>>>(desc_dev, ctx->d_tab, eadv, est_epoch, ctx->d_carr_ck,
@@ -1212,9 +1241,12 @@ static int enqueue_chain(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_
     const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
     use_set(ctx, ctx->set_wr);
     if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && ctx->cfg.reserved[0] == 0) {
+        CU(cudaMemcpyAsync(ctx->d_carr_start, ctx->d_carr_state, C * sizeof(double), cudaMemcpyDeviceToDevice, st));
         k_carr_final<<<C, 32, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_specE, ctx->d_specG, ctx->d_carr_ck, ctx->ck_plane,
                                        ctx->d_info, (size_t) ctx->E * C, ctx->d_traceG, ctx->d_carr_state, ctx->d_carr_trace,
                                        ctx->d_ginfo, ctx->d_fallbacks, n_epochs, C, N, T, ntiles);
+        k_bias_update<<<1, 32, 0, st>>>(ctx->d_adv, ctx->d_carr_start, ctx->d_carr_state, ctx->d_bias_rate, n_epochs, C);
+        ctx->launches += 1;
     } else {  // INT32 carrier (closed form) or the serial float scan (cfg.reserved[0] = 1, cross-check)
         k_scan_carrier<<<C, 32, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_carr_ck + 6 * ctx->ck_plane, ctx->d_carr_state,
                                          ctx->d_carr_trace, ctx->d_info + 2 * (size_t) ctx->E * C, ctx->d_ginfo, GROUP_EPOCHS,
