@@ -1,12 +1,15 @@
 // synth_line.cuh — k_synth_line: the production synthesis kernel (plutogpssim.c:2689-2756),
 // with k_line_anchor (tile anchors + safety check) before and k_line_patch / k_line_apply after it.
 //
-// Per channel and sample the main kernel does exactly: two 64-bit adds (the two NCO lines), two
-// shifts (carrier table index, plutogpssim.c:2697; chip index, plutogpssim.c:2737), two shared-memory
+// Per channel and sample the main kernel does exactly: two 64-bit adds (the two NCO lines, kept in
+// "split-word" form: the HIGH 32-bit word of each accumulator is the shared-memory address material,
+// the low word the fraction), one AND/OR (carrier table index, plutogpssim.c:2697 -> LUT address; the
+// chip index of plutogpssim.c:2737 needs none: the high word IS the byte address), two shared-memory
 // loads (amplitude LUT entry = (int)(cos|sin * gain) of plutogpssim.c:2701-2702 packed as Q<<16 + I;
 // chip/NAV sign as a +-1 byte) and one multiply-add into the packed accumulator
-// (plutogpssim.c:2705-2706).  No branch, no per-run state, no correction array: see line_check.cuh
-// for why a straight line per 1024-sample tile is exact once k_line_anchor has cleared the tile.
+// (plutogpssim.c:2705-2706): 8 instructions.  No branch, no per-run state, no correction array: see
+// line_check.cuh for why a straight line per 1024-sample tile is exact once k_line_anchor has cleared
+// the tile; the split-word form truncates the line by < LN_KF / LN_KG units, which the check covers.
 //
 //   tile        1024 samples; anchor = exact NCO states at its first sample (from the scan phases)
 //   warp-block  512 samples: lane l renders samples l, l+32, ..., l+480 of the block, so the 32 lanes
@@ -34,6 +37,15 @@
 #define LN_CG 12                  // slots resident at a time
 #define LN_VS 1536                // chip-sign entries per variant: 1023 + 512 (code_step <= 0.5) + 1
 #define LN_CHUNK 32               // tiles per hazard chunk (= lanes)
+// Split-word lines: a lane's LN_RUN samples of a warp-block are evaluated as
+//     X_j = (F0 >> LN_XSH) + j * DX,  DX = (32 dF) >> LN_XSH (arithmetic)   carrier: index = bits [10:2] of X's high word
+//     Y_j = (G0 >> LN_YSH) + j * DY,  DY = (32 dG) >> LN_YSH                code: byte address = Y's high word
+// from the lane's exact 64-bit start F0 = anchor + m0 dF.  Both truncations round down, so the value the
+// kernel floors lies in (line - LN_K*, line]: k_line_anchor widens the lower side of its hazard window by LN_K*.
+#define LN_XSH 21
+#define LN_YSH 15
+#define LN_KF ((int64_t) LN_RUN << LN_XSH)
+#define LN_KG ((int64_t) LN_RUN << LN_YSH)
 
 #define LN_DBG_FORCE_CHUNK 1      // cfg.reserved[1] bits (tests): treat every chunk as flagged,
 #define LN_DBG_FORCE_TILE 2       //   every tile as a hazard (all samples re-checked by k_line_patch),
@@ -47,7 +59,21 @@ __host__ __device__ inline int ln_groups(int C) { return (C + LN_CG - 1) / LN_CG
 __host__ __device__ inline int ln_group_slots(int C) { const int g = ln_groups(C); return (C + g - 1) / g; }
 __host__ __device__ inline size_t ln_smem_bytes(int C) {
     const int CG = ln_group_slots(C);
-    return (size_t) CG * 4 * LN_VS + (size_t) CG * 2048 + 16 * 16 /* steps */ + LN_WARPS * 16 * 16 /* anchors */ + 128;
+    return (size_t) CG * 4 * LN_VS + 2048 /* LUT alignment */ + (size_t) CG * 2048 + 16 * 32 /* steps */ +
+           LN_WARPS * 16 * 16 /* anchors */ + 128;
+}
+
+// what k_synth_line evaluates for tile-relative sample n of a tile anchored at (aF, aG): carrier table index and
+// chip-table index (k_line_patch compares exactly this with the literal recurrence)
+GPSIQ_HD uint64_t ln_split_dx(uint64_t dF) { return (uint64_t) ((int64_t) dF >> (LN_XSH - 5)); }
+GPSIQ_HD uint64_t ln_split_dy(uint64_t dG) { return dG >> (LN_YSH - 5); }
+GPSIQ_HD void ln_kernel_index(uint64_t aF, uint64_t aG, uint64_t dF, uint64_t dG, uint32_t n, uint32_t& ci, uint32_t& gi) {
+    const uint32_t m0 = (n & ~(uint32_t) (LN_WB - 1)) | (n & 31u);  // the lane's first sample of the warp-block
+    const uint32_t j = (n >> 5) & (uint32_t) (LN_RUN - 1);
+    const uint64_t X = ((aF + (uint64_t) m0 * dF) >> LN_XSH) + (uint64_t) j * ln_split_dx(dF);
+    const uint64_t Y = ((aG + (uint64_t) m0 * dG) >> LN_YSH) + (uint64_t) j * ln_split_dy(dG);
+    ci = (uint32_t) (X >> (LN_FBITS - LN_XSH)) & 511u;
+    gi = (uint32_t) (Y >> (LN_GBITS - LN_YSH));
 }
 
 // ---- k_line_anchor ---------------------------------------------------------------
@@ -121,8 +147,8 @@ k_line_anchor(const gpsiq_chan_desc* __restrict__ desc, const double* __restrict
                 loG = min(loG, (int64_t) __shfl_xor_sync(0xffffffffu, loG, s));
                 hiG = max(hiG, (int64_t) __shfl_xor_sync(0xffffffffu, hiG, s));
             }
-            if (lane == j) { my_A = F0; my_lo = loF - eF; my_hi = hiF + eF; }
-            if (lane == 16 + j) { my_A = G0; my_lo = loG - eG; my_hi = hiG + eG; }
+            if (lane == j) { my_A = F0; my_lo = loF - eF - LN_KF; my_hi = hiF + eF; }
+            if (lane == 16 + j) { my_A = G0; my_lo = loG - eG - LN_KG; my_hi = hiG + eG; }
         }
         // ---- chunk-level check, all chunks of the round at once
         bool hz = false;
@@ -144,8 +170,8 @@ k_line_anchor(const gpsiq_chan_desc* __restrict__ desc, const double* __restrict
             if (t >= ntiles) continue;
             const LineTile a = ln_tile_anchor(d, code_ck, wrap_ck, carr, e, c, t, C, N, ntiles, dbg);
             const int len = min(LN_TILE, N - t * LN_TILE);
-            const bool hzt = (dbg & LN_DBG_FORCE_TILE) || line_hazard(a.FA, dF, LN_FBITS, (uint64_t) len, -eF, eF) ||
-                             line_hazard(a.GA, dG, LN_GBITS, (uint64_t) len, -eG, eG);
+            const bool hzt = (dbg & LN_DBG_FORCE_TILE) || line_hazard(a.FA, dF, LN_FBITS, (uint64_t) len, -eF - LN_KF, eF) ||
+                             line_hazard(a.GA, dG, LN_GBITS, (uint64_t) len, -eG - LN_KG, eG);
             if (hzt) {
                 const int slot = atomicAdd(&counters[0], 1);
                 if (slot < haz_cap) hazlist[slot] = (uint32_t) (e * ntiles + t) * 32u + (uint32_t) c;
@@ -180,7 +206,6 @@ k_line_patch(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
         int kbit = wr / 20, icode = wr - kbit * 20;
         const ulonglong2 a = anch[o];
         const uint64_t dF = ln_carr_slope(d.carr_step), dG = ln_code_slope(d.code_step);
-        uint64_t F = a.x, G = a.y;
         const int32_t* lut = lutp + ec * 512;
         const int8_t* chipv = chips4 + (size_t) d.prn * 4 * LN_VS;  // variants of this PRN
         const int8_t* chip0 = chips4 + (size_t) d.prn * 4 * LN_VS;  // variant 0 = polarity (0,0): +1 iff chip == 0
@@ -192,7 +217,9 @@ k_line_patch(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
             const int nav = (int) (d.navbits >> (kbit & 63)) & 1;
             const int32_t right = (chipbit == nav) ? lut[it] : -lut[it];
             // what k_synth_line adds for this slot
-            const int32_t wrong = lut[(uint32_t) (F >> LN_FBITS)] * (int32_t) chipv[(uint32_t) (G >> LN_GBITS)];
+            uint32_t ci, gi;
+            ln_kernel_index(a.x, a.y, dF, dG, (uint32_t) n, ci, gi);
+            const int32_t wrong = lut[ci] * (int32_t) chipv[gi];
             if (right != wrong) {
                 const int slot = atomicAdd(&counters[1], 1);
                 if (slot < patch_cap) {
@@ -202,7 +229,6 @@ k_line_patch(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
                     atomicOr(&step_flag[e], 4);
                 }
             }
-            F += dF; G += dG;
             int wdummy = 0;
             if (nco_step<NCO_CODE>(cp, d.code_step, wdummy)) { if (++icode >= 20) { icode = 0; kbit++; } }
             nco_step<NCO_CARRIER>(ph, d.carr_step, wdummy);
@@ -238,12 +264,12 @@ __device__ __forceinline__ int32_t ln_lds_s8(uint32_t saddr) {
     asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
-// LUT entry idx of the table at shared address base: one multiply-add for the address (kept as one
-// instruction: the compiler would otherwise split (x >> 23) << 2 into shift + mask + add)
-__device__ __forceinline__ int32_t ln_lds_lut(uint32_t base, uint32_t idx) {
+// LUT entry of the 2 KB-aligned table at shared address base, index taken from bits [10:2] of the carrier
+// accumulator's high word: one LOP3 for the address
+__device__ __forceinline__ int32_t ln_lds_lut(uint32_t base, uint32_t xh) {
     int32_t v;
     uint32_t addr;
-    asm volatile("mad.lo.u32 %0, %1, 4, %2;" : "=r"(addr) : "r"(idx), "r"(base));
+    asm volatile("lop3.b32 %0, %1, 0x7fc, %2, 0xea;" : "=r"(addr) : "r"(xh), "r"(base));  // (xh & 0x7fc) | base
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
@@ -264,12 +290,13 @@ k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
     extern __shared__ __align__(16) unsigned char ln_raw[];
     const int CG = ln_group_slots(C), ngroups = ln_groups(C);
     int8_t* s_chip = (int8_t*) ln_raw;                                   // [CG][4][LN_VS]
-    int32_t* s_lut = (int32_t*) (ln_raw + (size_t) CG * 4 * LN_VS);      // [CG][512]
-    ulonglong2* s_step = (ulonglong2*) (s_lut + (size_t) CG * 512);      // [16] {dF, dG}; dG == 0: inactive
-    ulonglong2* s_anch = s_step + 16;                                    // [LN_WARPS][16]
-    int* s_prn = (int*) (s_anch + LN_WARPS * 16);                        // [16] PRN whose chip tables are resident
     const uint32_t chip_saddr = (uint32_t) __cvta_generic_to_shared(s_chip);
-    const uint32_t lut_saddr = (uint32_t) __cvta_generic_to_shared(s_lut);
+    // the LUTs start on a 2 KB boundary of the shared window, so that (index bits) | base is the entry address
+    const uint32_t lut_saddr = (chip_saddr + (uint32_t) CG * 4 * LN_VS + 2047u) & ~2047u;
+    int32_t* s_lut = (int32_t*) (ln_raw + (lut_saddr - chip_saddr));     // [CG][512]
+    ulonglong2* s_step = (ulonglong2*) (s_lut + (size_t) CG * 512);      // [16][2] {dF, dG}, {DX, DY}; dG == 0: inactive
+    ulonglong2* s_anch = s_step + 32;                                    // [LN_WARPS][16]
+    int* s_prn = (int*) (s_anch + LN_WARPS * 16);                        // [16] PRN whose chip tables are resident
     if (chip_saddr + (uint32_t) CG * 4 * LN_VS > (1u << (64 - LN_GBITS))) {  // the chip address must fit G's index field
         if (threadIdx.x == 0) atomicExch(err, 0x40000000);
         return;
@@ -322,7 +349,8 @@ k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
                             st.y = ln_code_slope(de[c0 + threadIdx.x].code_step);  // > 0 for every active slot
                         }
                     }
-                    s_step[threadIdx.x] = st;
+                    s_step[2 * threadIdx.x] = st;
+                    s_step[2 * threadIdx.x + 1] = make_ulonglong2(ln_split_dx(st.x), ln_split_dy(st.y));
                 }
                 __syncthreads();
             }
@@ -344,18 +372,19 @@ k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
                         if (32 * j < nleft) acc[j] = (int32_t) dst[32 * j];  // raw packed sums of the earlier groups
                 }
                 for (int cl = 0; cl < nc; cl++) {
-                    const ulonglong2 st = s_step[cl];
+                    const ulonglong2 st = s_step[2 * cl];
                     if (st.y == 0) continue;  // inactive slot (uniform)
+                    const ulonglong2 sd = s_step[2 * cl + 1];
                     const ulonglong2 a = my_anch[cl];
-                    uint64_t F = a.x + (uint64_t) m0 * st.x;
-                    uint64_t G = a.y + (uint64_t) m0 * st.y + ((uint64_t) (chip_saddr + (uint32_t) cl * 4 * LN_VS) << LN_GBITS);
-                    const uint64_t dF = st.x << 5, dG = st.y << 5;
+                    // the lane's exact start, then the split-word lines (ln_kernel_index is the same arithmetic)
+                    uint64_t X = (a.x + (uint64_t) m0 * st.x) >> LN_XSH;
+                    uint64_t Y = ((a.y + (uint64_t) m0 * st.y) >> LN_YSH) + ((uint64_t) (chip_saddr + (uint32_t) cl * 4 * LN_VS) << 32);
                     const uint32_t lut = lut_saddr + (uint32_t) cl * 2048;
 #pragma unroll
                     for (int j = 0; j < LN_RUN; j++) {
-                        acc[j] += ln_lds_lut(lut, (uint32_t) (F >> LN_FBITS)) * ln_lds_s8((uint32_t) (G >> LN_GBITS));
-                        F += dF;
-                        G += dG;
+                        acc[j] += ln_lds_lut(lut, (uint32_t) (X >> 32)) * ln_lds_s8((uint32_t) (Y >> 32));
+                        X += sd.x;
+                        Y += sd.y;
                     }
                 }
                 if (g == ngroups - 1) {
