@@ -274,6 +274,12 @@ __device__ __forceinline__ int32_t ln_lds_lut(uint32_t base, uint32_t xh) {
     return v;
 }
 
+__device__ __forceinline__ ulonglong2 ln_lds_v2(uint32_t saddr) {
+    ulonglong2 v;
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(saddr));
+    return v;
+}
+
 // One CTA per unit of LN_UNIT consecutive tiles of one epoch.  The CTAs are deliberately NOT persistent:
 // they retire every ~100 us, so the hardware block scheduler can place the small latency-bound kernels of
 // the next batch's carrier chain (launched on higher-priority streams) beside this kernel as slots free up.
@@ -303,6 +309,8 @@ k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     ulonglong2* my_anch = s_anch + warp * 16;
+    const uint32_t step_saddr = (uint32_t) __cvta_generic_to_shared(s_step);
+    const uint32_t anch_saddr = (uint32_t) __cvta_generic_to_shared(my_anch);
     const int wb_epoch = (N + LN_WB - 1) / LN_WB;
     const int upe = (ntiles + LN_UNIT - 1) / LN_UNIT;  // units per epoch
     const unsigned int nunits = (unsigned int) E * upe;
@@ -357,9 +365,16 @@ k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
 
             for (int wb = wb0 + warp; wb < wb1; wb += LN_WARPS) {
                 const int tile = wb / WPT;
-                const uint32_t m0 = (uint32_t) ((wb % WPT) * LN_WB + lane);  // sample offset inside the tile
+                const uint32_t mb = (uint32_t) ((wb % WPT) * LN_WB);  // the warp-block's offset inside the tile
                 __syncwarp();
-                if (lane < nc) my_anch[lane] = anch[((size_t) e * ntiles + tile) * C + c0 + lane];
+                if (lane < nc) {
+                    // anchor of the warp-block: tile anchor + mb steps; the chip table's shared address goes into G
+                    ulonglong2 a = anch[((size_t) e * ntiles + tile) * C + c0 + lane];
+                    const ulonglong2 st = s_step[2 * lane];
+                    a.x += (uint64_t) mb * st.x;
+                    a.y += (uint64_t) mb * st.y + ((uint64_t) (chip_saddr + (uint32_t) lane * 4 * LN_VS) << LN_GBITS);
+                    my_anch[lane] = a;
+                }
                 __syncwarp();
                 uint32_t* dst = out_epoch + (size_t) wb * LN_WB + lane;
                 const int nleft = N - (wb * LN_WB + lane);  // this lane's sample j exists iff 32*j < nleft
@@ -371,15 +386,17 @@ k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
                     for (int j = 0; j < LN_RUN; j++)
                         if (32 * j < nleft) acc[j] = (int32_t) dst[32 * j];  // raw packed sums of the earlier groups
                 }
-                for (int cl = 0; cl < nc; cl++) {
-                    const ulonglong2 st = s_step[2 * cl];
+                // carried shared addresses: step record, warp-block anchor, LUT of the slot
+                uint32_t rp = step_saddr, ap = anch_saddr, lut = lut_saddr;
+                const uint32_t rp_end = step_saddr + (uint32_t) nc * 32u;
+                for (; rp != rp_end; rp += 32u, ap += 16u, lut += 2048u) {
+                    const ulonglong2 st = ln_lds_v2(rp);
                     if (st.y == 0) continue;  // inactive slot (uniform)
-                    const ulonglong2 sd = s_step[2 * cl + 1];
-                    const ulonglong2 a = my_anch[cl];
+                    const ulonglong2 sd = ln_lds_v2(rp + 16u);
+                    const ulonglong2 a = ln_lds_v2(ap);
                     // the lane's exact start, then the split-word lines (ln_kernel_index is the same arithmetic)
-                    uint64_t X = (a.x + (uint64_t) m0 * st.x) >> LN_XSH;
-                    uint64_t Y = ((a.y + (uint64_t) m0 * st.y) >> LN_YSH) + ((uint64_t) (chip_saddr + (uint32_t) cl * 4 * LN_VS) << 32);
-                    const uint32_t lut = lut_saddr + (uint32_t) cl * 2048;
+                    uint64_t X = (a.x + (uint64_t) lane * st.x) >> LN_XSH;
+                    uint64_t Y = (a.y + (uint64_t) lane * st.y) >> LN_YSH;
 #pragma unroll
                     for (int j = 0; j < LN_RUN; j++) {
                         acc[j] += ln_lds_lut(lut, (uint32_t) (X >> 32)) * ln_lds_s8((uint32_t) (Y >> 32));
