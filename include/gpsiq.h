@@ -209,6 +209,10 @@ int gpsiq_estimate_anchor_device(gpsiq_ctx *ctx, void *cuda_stream);
  * speculation; with this option it waits for its exact chain as well (time-sliced multi-GPU runs: the chain is a
  * hop of the inter-GPU ring and must not compete with the sample kernel for the SMs). */
 #define GPSIQ_OPT_RENDER_AFTER_NEXT_CHAIN 2
+/* Most CTAs of one k_synth_line launch; the CTAs then stride over the launch's work units (persistent form).
+ * 0 (default): one CTA per unit.  A cap just below 2 x the SM count leaves a few half-empty SMs to the small
+ * latency-bound kernels that run beside the sample kernel (the next batch's chain, a ring hop). */
+#define GPSIQ_OPT_LINE_GRID_CAP 3
 int gpsiq_set_option(gpsiq_ctx *ctx, int option, int value);
 int gpsiq_estimate_to_device(gpsiq_ctx *ctx, double *dst_dev, void *cuda_stream);
 int gpsiq_estimate_correct_device(gpsiq_ctx *ctx, const double *exact_old_dev, const double *est_old_dev, double gain,
@@ -243,8 +247,9 @@ int gpsiq_line_stats(gpsiq_ctx *ctx, int64_t *hazard_tiles, int64_t *patches, in
 /* Host execution of the safety check's arithmetic (tests):
  * gpsiq_minmod_host: min over x in [0,n) of (b + a*x) mod m (may return any attained value < stop early).
  * gpsiq_line_probe_host: run the literal NCO recurrence (plutogpssim.c:2709-2713 / 2741-2746) for n samples
- * from x0 next to the straight fixed-point line the line kernel would use; reports the largest deviation
- * (line units), the number of samples whose table/chip index differs, and whether the check flags the run. */
+ * from x0 next to the straight fixed-point line of the line kernel; reports the largest deviation of the
+ * recurrence from that line (line units), the number of samples whose table/chip index differs from the index
+ * the kernel evaluates (its split-word form of the line, truncation included), and whether the check flags the run. */
 uint64_t gpsiq_minmod_host(uint64_t b, uint64_t a, uint64_t m, uint64_t n, uint64_t stop);
 int gpsiq_line_probe_host(int mode, double x0, double step, int n, int64_t *max_dev, int *mismatches, int *hazard);
 

@@ -121,6 +121,7 @@ struct gpsiq_ctx {
     double* d_carr_start; // [C] exact phases at the start of the batch being chained
     int chain_keeps_estimate;  // GPSIQ_OPT_CHAIN_KEEPS_ESTIMATE
     int render_after_next_chain;  // GPSIQ_OPT_RENDER_AFTER_NEXT_CHAIN
+    int line_grid_cap;    // GPSIQ_OPT_LINE_GRID_CAP: most CTAs of one k_synth_line launch (0: one CTA per unit)
     int use_fixed;        // k_synth_fixed is eligible for this configuration
     int use_line;         // k_synth_line (the production kernel) is eligible for this configuration
     int8_t* d_chips4;     // [33][4][LN_VS] +-1: chip/NAV sign tables in 4 polarity variants, extended past chip 1022
@@ -917,6 +918,7 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
     if (!ctx) return GPSIQ_ERR_NOMEM;
     ctx->cfg = *cfg;
     ctx->trace_on = getenv("GPSIQ_TRACE") != NULL;
+    if (getenv("GPSIQ_LINE_GRID_CAP")) ctx->line_grid_cap = atoi(getenv("GPSIQ_LINE_GRID_CAP"));  // experiments
     if (ctx->trace_on) ctx->trace = (TraceRec*) calloc(TRACE_MAX, sizeof(TraceRec));
     ctx->sm_count = prop.multiProcessorCount;
     ctx->C = cfg->max_chan;
@@ -1334,7 +1336,8 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
         int k = 0;
         for (int e0 = 0; e0 < n_epochs; e0 += sub, k++) {
             const int ne = n_epochs - e0 < sub ? n_epochs - e0 : sub;
-            const int grid = ne * ((ntiles + LN_UNIT - 1) / LN_UNIT);
+            int grid = ne * ((ntiles + LN_UNIT - 1) / LN_UNIT);
+            if (ctx->line_grid_cap > 0 && grid > ctx->line_grid_cap) grid = ctx->line_grid_cap;  // CTAs stride over the units
             const bool timed = (k == 0 && ctx->ev_count < TIMING_RING);
             if (timed) { CU(cudaEventRecord(ctx->ev[ctx->ev_count][3], st)); ctx->fixed_epochs = ne; }
             k_synth_line<<<grid, LN_THREADS, ln_smem_bytes(C), st>>>(
@@ -1581,6 +1584,7 @@ int gpsiq_set_option(gpsiq_ctx* ctx, int option, int value) {
     if (!ctx) return GPSIQ_ERR_ARG;
     if (option == GPSIQ_OPT_CHAIN_KEEPS_ESTIMATE) { ctx->chain_keeps_estimate = value != 0; return GPSIQ_OK; }
     if (option == GPSIQ_OPT_RENDER_AFTER_NEXT_CHAIN) { ctx->render_after_next_chain = value != 0; return GPSIQ_OK; }
+    if (option == GPSIQ_OPT_LINE_GRID_CAP) { ctx->line_grid_cap = value > 0 ? value : 0; return GPSIQ_OK; }
     return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_set_option: unknown option", cudaSuccess);
 }
 
@@ -1724,7 +1728,8 @@ int gpsiq_timing_sample_kernel_isolated(gpsiq_ctx* ctx, int reps, float* kernel_
         if (i == 1) CU(cudaEventRecord(e0, ctx->stream));
         if (line) {
             const int ne = ctx->last_ln.ne, le0 = ctx->last_ln.e0;
-            const int grid = ne * ((ntiles + LN_UNIT - 1) / LN_UNIT);
+            int grid = ne * ((ntiles + LN_UNIT - 1) / LN_UNIT);
+            if (ctx->line_grid_cap > 0 && grid > ctx->line_grid_cap) grid = ctx->line_grid_cap;
             k_synth_line<<<grid, LN_THREADS, ln_smem_bytes(C), ctx->stream>>>(
                 ctx->last_ln.desc, ctx->d_lutp + (size_t) le0 * C * 512, ctx->d_chips4,
                 ctx->d_anch[ctx->last_ln.set] + (size_t) le0 * ntiles * C, ctx->d_flags + le0, ctx->d_flags + ctx->E + le0,
@@ -1810,15 +1815,22 @@ int gpsiq_line_probe_host(int mode, double x0, double step, int n, int64_t* max_
         if (mode == NCO_CARRIER && x == 1.0) dv = (int64_t) (0 - L);  // 1.0 saturates to 2^64 - 1: compare with 2^64
         if (dv < 0) dv = -dv;
         if (dv > dev) dev = dv;
-        if ((T >> B) != (L >> B)) mism++;
+        // the index k_synth_line evaluates for this sample (split-word line from the lane's exact start)
+        uint32_t ci, gi;
+        ln_kernel_index(A, A, d, d, (uint32_t) i, ci, gi);
+        const uint32_t ki = (mode == NCO_CARRIER) ? ci : gi;
+        const uint32_t ti = (mode == NCO_CARRIER) ? (uint32_t) (T >> B) & 511u : (uint32_t) (T >> B);
+        if (ti != ki) mism++;
         L += d;
         if (mode == NCO_CARRIER) nco_step<NCO_CARRIER>(x, step, wraps);
         else nco_step<NCO_CODE>(x, step, wraps);
     }
+    // the window k_line_anchor uses: truth within +-eps of the line, the kernel's value up to LN_K* below it
     const int64_t eps = ln_eps(mode == NCO_CARRIER, n);
+    const int64_t K = (mode == NCO_CARRIER) ? LN_KF : LN_KG;
     if (max_dev) *max_dev = dev;
     if (mismatches) *mismatches = mism;
-    if (hazard) *hazard = line_hazard(A, d, B, (uint64_t) n, -eps, eps) ? 1 : 0;
+    if (hazard) *hazard = line_hazard(A, d, B, (uint64_t) n, -eps - K, eps) ? 1 : 0;
     return GPSIQ_OK;
 }
 

@@ -319,7 +319,11 @@ k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
     int cur_e = -1;
     (void) E;
 
-    for (unsigned int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+    // a CTA takes a contiguous range of units (one unit each unless the launch caps the grid): consecutive units
+    // of one epoch reuse the resident tables
+    const unsigned int unit_lo = (unsigned int) ((unsigned long long) nunits * blockIdx.x / gridDim.x);
+    const unsigned int unit_hi = (unsigned int) ((unsigned long long) nunits * (blockIdx.x + 1) / gridDim.x);
+    for (unsigned int unit = unit_lo; unit < unit_hi; unit++) {
         __syncthreads();  // everyone is done with the previous unit's tables
         const int e = (int) (unit / upe);
         const int t0 = (int) (unit - (unsigned int) e * upe) * LN_UNIT;

@@ -99,6 +99,34 @@ def test_near_boundary_lines_are_flagged():
     assert seen_mismatch > 0   # the probe really produces index disagreements (so `mism == 0 or hz` is not vacuous)
 
 
+def test_split_word_truncation_is_covered():
+    """k_synth_line evaluates the line in split-word form (high word = address bits), which truncates it by
+    up to 2^25 (carrier) / 2^19 (code) units: a line that passes just ABOVE a boundary makes the kernel's index
+    lag the true one.  Such runs must be flagged, and the lag must really occur in the probe."""
+    rng = random.Random(14)
+    n = 1024
+    lag_seen = 0
+    for trial in range(400):
+        fs = rng.choice(FS)
+        f = rng.uniform(200, 9000) * rng.choice([-1, 1])
+        d = f / fs
+        k = rng.randrange(17, n)           # past the lane's first sample, where the truncation has built up
+        target = rng.randrange(0, 512) / 512.0
+        off = rng.randrange(1 << 12, 1 << 21) * 2.0 ** -64   # above the boundary, inside the truncation band
+        x0 = (target - k * d + off) % 1.0
+        dev, mism, hz = capi.line_probe(capi.NCO_CARRIER, x0, d, n)
+        assert mism == 0 or hz, ("carrier", x0, d, k)
+        lag_seen += mism
+        step = (1.023e6 + f / 1540.0) / fs
+        chip = rng.randrange(1, 1023)
+        c0 = chip - k * step + rng.randrange(1 << 6, 1 << 15) * 2.0 ** -47
+        if 0.0 <= c0 < 1023.0:
+            dev, mism, hz = capi.line_probe(capi.NCO_CODE, c0, step, n)
+            assert mism == 0 or hz, ("code", c0, step, k)
+            lag_seen += mism
+    assert lag_seen > 0
+
+
 def test_generic_lines_are_not_flagged():
     """The check must clear ordinary tiles, or the patch path would carry the load."""
     rng = random.Random(13)
