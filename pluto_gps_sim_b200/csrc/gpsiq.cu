@@ -470,13 +470,14 @@ __global__ void k_carr_speculate(const gpsiq_chan_desc* __restrict__ desc, const
     spec[((size_t) ec * J + j) * 2 + v] = out;
 }
 
+#define SPEC_MAX_CHUNKS 16  // most chunks per epoch (level 1)
 // One chain per (epoch, slot, epoch-level variant): stitch the chunk runs into the epoch-level trajectory P.
 __global__ void k_carr_stitch(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
                               const double* __restrict__ est_epoch, const CarrSpec* __restrict__ spec,
                               double* __restrict__ carr_ck, size_t ck_plane, ChunkInfo* __restrict__ cinfo,
                               CarrSpec* __restrict__ specE, int E, int C, int N, int T, int ntiles, int G, int J) {
     __shared__ BinadeTab s_tab[4];
-    __shared__ CarrSpec s_cs[4][16];
+    __shared__ CarrSpec s_cs[4][2 * SPEC_MAX_CHUNKS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chain = blockIdx.x * 4 + warp;
     if (chain >= E * C * 2) return;
@@ -834,7 +835,7 @@ int gpsiq_carrier_chain_host(const double* steps, int n_epochs, int N, int T, do
         a0 -= floor(a0);
         est[e] = a0;
         double* pl = planes + ep * e;
-        CarrSpec cs[16];
+        CarrSpec cs[2 * SPEC_MAX_CHUNKS];
         for (int j = 0; j < J; j++)
             for (int v = 0; v < 2; v++) {
                 CarrSpec& o = cs[j * 2 + v];
@@ -960,7 +961,13 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
     CU(cudaMalloc(&ctx->d_desc, EC * sizeof(gpsiq_chan_desc)));
     CU(cudaMalloc(&ctx->d_chips, 33 * 2048));
     ctx->ck_plane = ck;
-    ctx->G = (ctx->ntiles + 7) / 8;
+    {   // chunks per epoch of the first speculation level (default 8; GPSIQ_SPEC_CHUNKS: experiments)
+        int chunks = 8;
+        if (getenv("GPSIQ_SPEC_CHUNKS")) chunks = atoi(getenv("GPSIQ_SPEC_CHUNKS"));
+        if (chunks < 1) chunks = 1;
+        if (chunks > SPEC_MAX_CHUNKS) chunks = SPEC_MAX_CHUNKS;
+        ctx->G = (ctx->ntiles + chunks - 1) / chunks;
+    }
     ctx->J = (ctx->ntiles + ctx->G - 1) / ctx->G;
     for (int i = 0; i < 2; i++) {
         ScanSet& ss = ctx->sets[i];
@@ -976,7 +983,7 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
         CU(cudaMalloc(&ss.d_cinfo, EC * 2 * ctx->J * sizeof(ChunkInfo)));
         CU(cudaMalloc(&ss.d_tab, EC * 2 * sizeof(BinadeTab)));
         CU(cudaMalloc(&ss.d_drift, 4 * EC * sizeof(double)));
-        CU(cudaMalloc(&ss.d_spec, EC * 2 * 8 * sizeof(CarrSpec)));
+        CU(cudaMalloc(&ss.d_spec, EC * 2 * ctx->J * sizeof(CarrSpec)));
         CU(cudaMalloc(&ss.d_info, 3 * EC * sizeof(CarrInfo)));
         {
             const size_t ng = ((size_t) ctx->E + GROUP_EPOCHS - 1) / GROUP_EPOCHS;
