@@ -190,7 +190,10 @@ def ours_arm(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        opts = None
+        if os.environ.get("GPSIQ_NCCL_HIPRI"):               # experiment: NCCL kernels on a high-priority stream
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
 
     E = args.epochs
     if args.workload == "config3":
@@ -212,7 +215,10 @@ def ours_arm(args):
     stream = torch.cuda.Stream()                 # everything below is enqueued on this stream
     torch.cuda.set_stream(stream)
     engine = GpuSliceEngine(synth)
-    runner = TimeSliceRunner(engine, rank, world, deferred_render=True)
+    handoff = args.handoff if world > 1 else "nccl"
+    if handoff == "mailbox":
+        engine.mailbox_setup(rank, world)
+    runner = TimeSliceRunner(engine, rank, world, deferred_render=True, handoff=handoff)
 
     def barrier():
         torch.cuda.synchronize()
@@ -350,7 +356,8 @@ def ours_arm(args):
             "config": {"workload": WORKLOAD if args.workload == "config1" else
                        "config[3]: static location, 10.0 MS/s, 32 channels (synthetic all-visible constellation), 300000 samples/epoch",
                        "epochs_per_step_per_gpu": E, "samples_per_step_per_gpu": samples_per_step,
-                       "parallelism": "time-slice x%d, NCCL carrier-phase hand-off" % world if world > 1 else "single GPU",
+                       "parallelism": ("time-slice x%d, %s carrier-phase hand-off" % (world, "NCCL" if handoff == "nccl" else
+                                        "peer-memory mailbox (NCCL only for the advance all_gather)")) if world > 1 else "single GPU",
                        "l2_policy": "output per step %.1f MB > 126 MB L2; inputs are %d B of descriptors"
                                     % (samples_per_step * 4 / 1e6, nbytes_desc),
                        "kernel": args.kernel, "tile_samples": args.tile,
@@ -386,6 +393,9 @@ def main():
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--handoff", choices=["nccl", "mailbox"], default=os.environ.get("GPSIQ_HANDOFF", "nccl"),
+                    help="carrier-phase hand-off between time slices (N > 1): NCCL send/recv, or the SM-free "
+                         "peer-memory mailbox (copy engine + stream memory operations)")
     ap.add_argument("--workload", choices=["config1", "config3"], default="config1",
                     help="config1 (default, the metric's configuration): 12 channels, 2.6 MS/s; config3: 32 channels, "
                          "10 MS/s, synthetic all-visible constellation (informative; no CPU baseline / reference arm)")

@@ -215,6 +215,18 @@ int gpsiq_estimate_anchor_device(gpsiq_ctx *ctx, void *cuda_stream);
 #define GPSIQ_OPT_LINE_GRID_CAP 3
 int gpsiq_set_option(gpsiq_ctx *ctx, int option, int value);
 int gpsiq_estimate_to_device(gpsiq_ctx *ctx, double *dst_dev, void *cuda_stream);
+/* SM-free hand-off of the carrier state between the GPUs of one node (time-sliced runs; replaces the NCCL
+ * send/recv of max_chan doubles at a slice boundary -- chan[i].carr_phase, plutogpssim.c:2741-2746, is the only
+ * state that crosses it).  A mailbox is a small device buffer (two state slots + a 64-bit sequence flag) exported
+ * as a 64-byte CUDA IPC handle.  The sender opens the NEXT rank's mailbox once; gpsiq_mailbox_send copies the
+ * context's carrier state into slot (seq & 1) with the copy engine and then writes seq to the flag with a stream
+ * memory operation; gpsiq_mailbox_recv makes the stream wait until the own flag >= seq and then loads slot
+ * (seq & 1) into the carrier state.  No kernel runs on either GPU.  seq must increase by one per message on an
+ * edge; a slot is reused two messages later (in a ring the receiver has consumed it by then). */
+int gpsiq_mailbox_create(gpsiq_ctx *ctx, void *ipc_handle_out_64_bytes);
+int gpsiq_mailbox_open(gpsiq_ctx *ctx, const void *ipc_handle_64_bytes, int peer_device);
+int gpsiq_mailbox_send(gpsiq_ctx *ctx, uint64_t seq, void *cuda_stream);
+int gpsiq_mailbox_recv(gpsiq_ctx *ctx, uint64_t seq, void *cuda_stream);
 int gpsiq_estimate_correct_device(gpsiq_ctx *ctx, const double *exact_old_dev, const double *est_old_dev, double gain,
                                   void *cuda_stream);
 int gpsiq_carrier_to_device(gpsiq_ctx *ctx, double *dst_dev, void *cuda_stream);

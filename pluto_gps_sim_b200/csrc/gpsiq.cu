@@ -18,6 +18,7 @@
 //                                carrier LUT, across-channel accumulate, int16 pack
 //
 // See DESIGN.md for the data layout and the roofline of each kernel.
+#include <cuda.h>          // driver API types only: entry points come from cudaGetDriverEntryPoint (no libcuda link)
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -121,6 +122,12 @@ struct gpsiq_ctx {
     double* d_carr_start; // [C] exact phases at the start of the batch being chained
     int chain_keeps_estimate;  // GPSIQ_OPT_CHAIN_KEEPS_ESTIMATE
     int render_after_next_chain;  // GPSIQ_OPT_RENDER_AFTER_NEXT_CHAIN
+    // SM-free carrier hand-off between the GPUs of one node (gpsiq_mailbox_*)
+    unsigned char* d_mbox;      // own mailbox: [2][MBOX_SLOT] state slots, sequence flag at MBOX_FLAG
+    unsigned char* d_mbox_peer; // the next rank's mailbox (CUDA IPC mapping)
+    void* fn_write64;           // cuStreamWriteValue64 / cuStreamWaitValue64
+    void* fn_wait64;
+    int mbox_flush;             // the device can flush remote writes after a wait
     int line_grid_cap;    // GPSIQ_OPT_LINE_GRID_CAP: most CTAs of one k_synth_line launch (0: one CTA per unit)
     int use_fixed;        // k_synth_fixed is eligible for this configuration
     int use_line;         // k_synth_line (the production kernel) is eligible for this configuration
@@ -1139,6 +1146,8 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
     cudaFree(ctx->d_chips4); cudaFree(ctx->d_anch[0]); cudaFree(ctx->d_anch[1]); cudaFree(ctx->d_hazlist);
     cudaFree(ctx->d_patches); cudaFree(ctx->d_line_counters); cudaFree(ctx->d_line_totals);
     cudaFree(ctx->d_bias_rate); cudaFree(ctx->d_carr_start);
+    if (ctx->d_mbox_peer) cudaIpcCloseMemHandle(ctx->d_mbox_peer);
+    cudaFree(ctx->d_mbox);
     cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_est_state); cudaFree(ctx->d_ca);
     cudaFree(ctx->d_iq); cudaFree(ctx->d_iq2); cudaFree(ctx->d_sums); cudaFree(ctx->d_err);
     if (ctx->h_stage[0]) cudaFreeHost(ctx->h_stage[0]);
@@ -1636,6 +1645,82 @@ int gpsiq_carrier_from_device(gpsiq_ctx* ctx, const double* src_dev, void* strea
     CU(cudaMemcpyAsync(ctx->d_carr_state, src_dev, ctx->C * sizeof(double), cudaMemcpyDeviceToDevice,
                        (cudaStream_t) stream));
     return GPSIQ_OK;  // the estimate is NOT touched: a speculation from it may already be in flight
+}
+
+// ---- mailbox hand-off ------------------------------------------------------------------
+// The carrier phases at a slice boundary (plutogpssim.c:2741-2746 chains them across the whole stream) are the only
+// data a time-sliced run moves between GPUs: max_chan doubles per hop, latency-bound.  A hop through NCCL needs a
+// kernel on both GPUs, which on a GPU saturated by the sample kernel waits for SM resources (measured: 23 us idle,
+// ~0.36 ms busy).  The mailbox path uses none: the sender's copy engine writes the state into the receiver's
+// mailbox (peer memory over NVLink) and a stream memory operation then writes a sequence number; the receiver's
+// stream waits on that number with a stream memory operation.
+#define MBOX_SLOT 1024
+#define MBOX_FLAG 2048
+#define MBOX_BYTES 4096
+typedef CUresult (*mbox_fn64)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);
+
+int gpsiq_mailbox_create(gpsiq_ctx* ctx, void* handle_out) {
+    if (!ctx || !handle_out) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_mailbox_create: bad argument", cudaSuccess);
+    if ((size_t) ctx->C * sizeof(double) > MBOX_SLOT) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_mailbox_create: too many channels", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (!ctx->d_mbox) {
+        CU(cudaMalloc(&ctx->d_mbox, MBOX_BYTES));
+        CU(cudaMemset(ctx->d_mbox, 0, MBOX_BYTES));
+        cudaDriverEntryPointQueryResult q;
+        CU(cudaGetDriverEntryPoint("cuStreamWriteValue64", &ctx->fn_write64, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess) ctx->fn_write64 = NULL;
+        CU(cudaGetDriverEntryPoint("cuStreamWaitValue64", &ctx->fn_wait64, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess) ctx->fn_wait64 = NULL;
+        if (!ctx->fn_write64 || !ctx->fn_wait64)
+            return fail(ctx, GPSIQ_ERR_CUDA, "gpsiq_mailbox_create: no 64-bit stream memory operations in this driver", cudaSuccess);
+        int can = 0;
+        cudaDeviceGetAttribute(&can, cudaDevAttrCanFlushRemoteWrites, ctx->cfg.device);
+        ctx->mbox_flush = can;
+        CU(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ctx->d_mbox));
+    memcpy(handle_out, &h, sizeof h);  // 64 bytes
+    return GPSIQ_OK;
+}
+
+int gpsiq_mailbox_open(gpsiq_ctx* ctx, const void* handle, int peer_device) {
+    if (!ctx || !handle || !ctx->d_mbox) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_mailbox_open: bad argument / no own mailbox", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (peer_device != ctx->cfg.device) {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, ctx->cfg.device, peer_device));
+        if (!can) return fail(ctx, GPSIQ_ERR_CUDA, "gpsiq_mailbox_open: no peer access to that device", cudaSuccess);
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void* p = NULL;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->d_mbox_peer = (unsigned char*) p;
+    return GPSIQ_OK;
+}
+
+// carrier state -> slot (seq & 1) of the next rank's mailbox, then its flag <- seq (both in stream order)
+int gpsiq_mailbox_send(gpsiq_ctx* ctx, uint64_t seq, void* stream) {
+    if (!ctx || !ctx->d_mbox_peer) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_mailbox_send: no peer mailbox open", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaMemcpyAsync(ctx->d_mbox_peer + (seq & 1) * MBOX_SLOT, ctx->d_carr_state, ctx->C * sizeof(double),
+                       cudaMemcpyDefault, (cudaStream_t) stream));
+    const CUresult r = ((mbox_fn64) ctx->fn_write64)((CUstream) stream, (CUdeviceptr) (ctx->d_mbox_peer + MBOX_FLAG), seq, 0);
+    if (r != CUDA_SUCCESS) return fail(ctx, GPSIQ_ERR_CUDA, "gpsiq_mailbox_send: cuStreamWriteValue64 failed", cudaSuccess);
+    return GPSIQ_OK;
+}
+
+// wait until the own mailbox's flag >= seq, then slot (seq & 1) -> carrier state (the estimate is not touched)
+int gpsiq_mailbox_recv(gpsiq_ctx* ctx, uint64_t seq, void* stream) {
+    if (!ctx || !ctx->d_mbox) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_mailbox_recv: no mailbox", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    const unsigned int flags = CU_STREAM_WAIT_VALUE_GEQ | (ctx->mbox_flush ? CU_STREAM_WAIT_VALUE_FLUSH : 0);
+    const CUresult r = ((mbox_fn64) ctx->fn_wait64)((CUstream) stream, (CUdeviceptr) (ctx->d_mbox + MBOX_FLAG), seq, flags);
+    if (r != CUDA_SUCCESS) return fail(ctx, GPSIQ_ERR_CUDA, "gpsiq_mailbox_recv: cuStreamWaitValue64 failed", cudaSuccess);
+    CU(cudaMemcpyAsync(ctx->d_carr_state, ctx->d_mbox + (seq & 1) * MBOX_SLOT, ctx->C * sizeof(double),
+                       cudaMemcpyDeviceToDevice, (cudaStream_t) stream));
+    return GPSIQ_OK;
 }
 
 int gpsiq_get_carrier(gpsiq_ctx* ctx, double* p) {

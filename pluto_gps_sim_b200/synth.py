@@ -217,6 +217,25 @@ class Synthesizer:
     def carrier_from_device(self, src_dev_ptr, stream_ptr=None):
         capi.check(capi.lib.gpsiq_carrier_from_device(self._ctx, src_dev_ptr, stream_ptr), self._ctx)
 
+    # SM-free carrier hand-off between the GPUs of one node (include/gpsiq.h: gpsiq_mailbox_*)
+    def mailbox_create(self):
+        """-> the 64-byte CUDA IPC handle of this context's mailbox."""
+        import ctypes
+        h = ctypes.create_string_buffer(64)
+        capi.check(capi.lib.gpsiq_mailbox_create(self._ctx, h), self._ctx)
+        return h.raw
+
+    def mailbox_open(self, handle, peer_device):
+        import ctypes
+        capi.check(capi.lib.gpsiq_mailbox_open(self._ctx, ctypes.create_string_buffer(bytes(handle), 64), int(peer_device)),
+                   self._ctx)
+
+    def mailbox_send(self, seq, stream_ptr=None):
+        capi.check(capi.lib.gpsiq_mailbox_send(self._ctx, int(seq), stream_ptr), self._ctx)
+
+    def mailbox_recv(self, seq, stream_ptr=None):
+        capi.check(capi.lib.gpsiq_mailbox_recv(self._ctx, int(seq), stream_ptr), self._ctx)
+
 
 def checksum_host(iq):
     """numpy mirror of gpsiq_checksum_device for one epoch (int16 [N,2] or [2N])."""

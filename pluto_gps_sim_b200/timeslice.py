@@ -101,10 +101,34 @@ class GpuSliceEngine:
     def render(self, desc_dev, n_epochs, out_dev):
         self.s.render_device(desc_dev.data_ptr(), n_epochs, out_dev.data_ptr(), self._stream())
 
+    # ---- SM-free hand-off (gpsiq_mailbox_*): the sender's copy engine writes the carrier state into the next
+    # rank's mailbox over NVLink peer memory and a stream memory operation publishes a sequence number; the
+    # receiver's stream waits on it.  No kernel on either GPU, so a hop does not queue for an SM behind the
+    # sample kernel the way an NCCL send/recv pair does.
+    def mailbox_setup(self, rank, world, device_of_rank=None):
+        """Collective (torch.distributed, any backend): every rank exports its mailbox and opens the next rank's."""
+        mine = self.s.mailbox_create()
+        handles = [None] * world
+        dist.all_gather_object(handles, (mine, torch.cuda.current_device()))
+        nxt = (rank + 1) % world
+        handle, dev = handles[nxt]
+        self.s.mailbox_open(handle, dev if device_of_rank is None else device_of_rank(nxt))
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    def handoff_send(self, seq):       # engine state -> next rank's mailbox
+        self.s.mailbox_send(seq, self._stream())
+
+    def handoff_recv(self, seq):       # own mailbox -> engine state (and self.phase, for the estimate feedback)
+        self.s.mailbox_recv(seq, self._stream())
+        self.s.carrier_to_device(self.phase.data_ptr(), self._stream())
+
 
 class TimeSliceRunner:
-    def __init__(self, engine, rank=None, world=None, deferred_render=False):
-        """deferred_render: step k enqueues the scan phases of slice k and then the rendering of slice k-1
+    def __init__(self, engine, rank=None, world=None, deferred_render=False, handoff="nccl"):
+        """handoff: "nccl" (dist.send / dist.recv of the phases) or "mailbox" (the engine's SM-free peer-memory
+        hand-off, GpuSliceEngine.mailbox_setup must have run; same node only).
+        deferred_render: step k enqueues the scan phases of slice k and then the rendering of slice k-1
         (the last slice is rendered by finish()).  The device then sees the next slice's chunk speculation
         before this slice's sample kernel, which is the order gpsiq_submit/gpsiq_fetch produce on one GPU:
         the speculation runs first at full occupancy and the rest of the chain beside the sample kernel.
@@ -116,6 +140,9 @@ class TimeSliceRunner:
         self.prev_adv = None
         self.deferred = deferred_render
         self.pending = None
+        if handoff not in ("nccl", "mailbox"):
+            raise ValueError("handoff must be 'nccl' or 'mailbox'")
+        self.mailbox = handoff == "mailbox" and self.world > 1
 
     def step(self, desc, n_epochs, out):
         """Synthesize this rank's slice of the next step.
@@ -140,8 +167,11 @@ class TimeSliceRunner:
         eng, r, n = self.engine, self.rank, self.world
         have_exact = False
         if n > 1 and r == 0 and self.step_index > 0:            # close the previous step's ring first
-            dist.recv(eng.phase, src=n - 1)
-            eng.load_carrier()
+            if self.mailbox:
+                eng.handoff_recv(self.step_index)               # message number = sender's step index + 1
+            else:
+                dist.recv(eng.phase, src=n - 1)
+                eng.load_carrier()
             eng.estimate_anchor()                               # rank 0 speculates from the exact phase
             have_exact = True
         eng.prepare(desc, n_epochs)
@@ -157,14 +187,22 @@ class TimeSliceRunner:
             self.prev_adv = adv_all
         eng.speculate(desc, n_epochs)
         if n > 1 and r > 0:
-            dist.recv(eng.phase, src=r - 1)
-            eng.load_carrier()
-            if hasattr(eng, "update_bias"):
-                eng.update_bias()
+            if self.mailbox:
+                eng.handoff_recv(self.step_index + 1)
+            else:
+                dist.recv(eng.phase, src=r - 1)
+                eng.load_carrier()
+                if hasattr(eng, "update_bias"):
+                    eng.update_bias()
         eng.chain(desc, n_epochs)
         if n > 1:
-            eng.store_carrier()
-            dist.send(eng.phase, dst=(r + 1) % n)
+            if self.mailbox:
+                eng.handoff_send(self.step_index + 1)
+                if r > 0 and hasattr(eng, "update_bias"):       # estimate feedback: off the ring's critical path
+                    eng.update_bias()
+            else:
+                eng.store_carrier()
+                dist.send(eng.phase, dst=(r + 1) % n)
 
     def finish(self):
         """Render the slice still pending (deferred_render) and drain the last hand-off (rank 0 receives
@@ -176,5 +214,8 @@ class TimeSliceRunner:
             eng = self.engine
             ctx = eng.scan_context() if hasattr(eng, "scan_context") else contextlib.nullcontext()
             with ctx:
-                dist.recv(eng.phase, src=self.world - 1)
-                eng.load_carrier()
+                if self.mailbox:
+                    eng.handoff_recv(self.step_index)
+                else:
+                    dist.recv(eng.phase, src=self.world - 1)
+                    eng.load_carrier()

@@ -18,7 +18,7 @@ E = 16
 STEPS = 9
 
 
-def _worker(rank, world, port, outdir, deferred=False):
+def _worker(rank, world, port, outdir, deferred=False, handoff="nccl"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -27,7 +27,10 @@ def _worker(rank, world, port, outdir, deferred=False):
 
     desc = ol.load_golden_desc("circle12")
     synth = Synthesizer(max_chan=12, max_epochs=E, device=rank)
-    runner = TimeSliceRunner(GpuSliceEngine(synth), rank, world, deferred_render=deferred)
+    engine = GpuSliceEngine(synth)
+    if handoff == "mailbox":
+        engine.mailbox_setup(rank, world)
+    runner = TimeSliceRunner(engine, rank, world, deferred_render=deferred, handoff=handoff)
     outs = [torch.empty(E * 300000 * 2, dtype=torch.int16, device="cuda") for _ in range(2)]
     sums = []
     for s in range(STEPS):
@@ -49,13 +52,13 @@ def _worker(rank, world, port, outdir, deferred=False):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("deferred", [False, True])
-def test_two_gpu_time_slices_match_reference(tmp_path, deferred):
+@pytest.mark.parametrize("deferred,handoff", [(False, "nccl"), (True, "nccl"), (False, "mailbox"), (True, "mailbox")])
+def test_two_gpu_time_slices_match_reference(tmp_path, deferred, handoff):
     world = 2
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_worker, args=(world, port, str(tmp_path), deferred), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), deferred, handoff), nprocs=world, join=True)
     meta = ol.load_golden_meta("circle12")
     parts = [np.load(tmp_path / ("sums%d.npy" % r)) for r in range(world)]
     got = np.concatenate([parts[r][s] for s in range(STEPS) for r in range(world)])
