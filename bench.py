@@ -48,10 +48,10 @@ REF_BIN_O0 = os.path.join(REPO, "oracle", "_ref", "ref_harness_O0")
 REF_ARGS = ["-e", NAV_FIXTURE, "-l", "30.286502,120.032669,100", "-s", "2600000"]
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from ncu --set full captures, per EPOCH
 # (300000 samples x 12 slots) so that it scales to the launch the roofline is quoted on:
-#   k_synth_line   1255370192 B for a 1024-epoch launch (profiles/r01_m_synth_line_ncu_full.txt): 83.8 MB read
-#                  (tables, anchors) + 1171.6 MB written of the 1228.8 MB of output (the rest is still in L2)
+#   k_synth_line   1255168128 B for a 1024-epoch launch (profiles/r01_w_synth_line_ncu_full.txt): 83.7 MB read
+#                  (tables, anchors) + 1171.5 MB written of the 1228.8 MB of output (the rest is still in L2)
 #   k_synth_fixed  37450240 B for an 8-epoch launch (profiles/r01_c_render_kernels_ncu_full.txt)
-TRAFFIC_PER_EPOCH = {"k_synth_line": 1255370192 / 1024, "k_synth_fixed": 37450240 / 8}
+TRAFFIC_PER_EPOCH = {"k_synth_line": 1255168128 / 1024, "k_synth_fixed": 37450240 / 8}
 WORKLOAD = "config[1]: static -l 30.286502,120.032669,100, synthetic brdc3540.14n, 2.6 MS/s, 12 channels, 300000 samples/epoch"
 
 
@@ -216,8 +216,8 @@ def ours_arm(args):
     torch.cuda.set_stream(stream)
     engine = GpuSliceEngine(synth)
     handoff = args.handoff if world > 1 else "nccl"
-    if handoff == "mailbox":
-        engine.mailbox_setup(rank, world)
+    if handoff == "mailbox" and not engine.mailbox_setup(rank, world):
+        handoff = "nccl"                                     # decided collectively: every rank falls back alike
     runner = TimeSliceRunner(engine, rank, world, deferred_render=True, handoff=handoff)
 
     def barrier():
@@ -393,9 +393,9 @@ def main():
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--handoff", choices=["nccl", "mailbox"], default=os.environ.get("GPSIQ_HANDOFF", "nccl"),
-                    help="carrier-phase hand-off between time slices (N > 1): NCCL send/recv, or the SM-free "
-                         "peer-memory mailbox (copy engine + stream memory operations)")
+    ap.add_argument("--handoff", choices=["nccl", "mailbox"], default=os.environ.get("GPSIQ_HANDOFF", "mailbox"),
+                    help="carrier-phase hand-off between time slices (N > 1): the SM-free peer-memory mailbox "
+                         "(copy engine + stream memory operations; falls back to NCCL if unavailable), or NCCL send/recv")
     ap.add_argument("--workload", choices=["config1", "config3"], default="config1",
                     help="config1 (default, the metric's configuration): 12 channels, 2.6 MS/s; config3: 32 channels, "
                          "10 MS/s, synthetic all-visible constellation (informative; no CPU baseline / reference arm)")

@@ -106,15 +106,32 @@ class GpuSliceEngine:
     # receiver's stream waits on it.  No kernel on either GPU, so a hop does not queue for an SM behind the
     # sample kernel the way an NCCL send/recv pair does.
     def mailbox_setup(self, rank, world, device_of_rank=None):
-        """Collective (torch.distributed, any backend): every rank exports its mailbox and opens the next rank's."""
-        mine = self.s.mailbox_create()
+        """Collective (torch.distributed, any backend): every rank exports its mailbox and opens the next rank's.
+        -> True if every rank succeeded; False (on all ranks alike) if any could not (no peer access, no CUDA IPC,
+        no stream memory operations): the caller then keeps the NCCL hand-off."""
+        mine, err = None, None
+        try:
+            mine = self.s.mailbox_create()
+        except Exception as e:                                   # reported below, decided collectively
+            err = e
         handles = [None] * world
         dist.all_gather_object(handles, (mine, torch.cuda.current_device()))
-        nxt = (rank + 1) % world
-        handle, dev = handles[nxt]
-        self.s.mailbox_open(handle, dev if device_of_rank is None else device_of_rank(nxt))
+        ok = all(h[0] is not None for h in handles)
+        if ok:
+            nxt = (rank + 1) % world
+            handle, dev = handles[nxt]
+            try:
+                self.s.mailbox_open(handle, dev if device_of_rank is None else device_of_rank(nxt))
+            except Exception as e:
+                err, ok = e, False
+        oks = [None] * world
+        dist.all_gather_object(oks, ok)
         torch.cuda.synchronize()
-        dist.barrier()
+        if not all(oks):
+            if err is not None:
+                print("mailbox hand-off unavailable on rank %d: %s" % (rank, err), flush=True)
+            return False
+        return True
 
     def handoff_send(self, seq):       # engine state -> next rank's mailbox
         self.s.mailbox_send(seq, self._stream())

@@ -29,7 +29,7 @@ def _worker(rank, world, port, outdir, deferred=False, handoff="nccl"):
     synth = Synthesizer(max_chan=12, max_epochs=E, device=rank)
     engine = GpuSliceEngine(synth)
     if handoff == "mailbox":
-        engine.mailbox_setup(rank, world)
+        assert engine.mailbox_setup(rank, world)
     runner = TimeSliceRunner(engine, rank, world, deferred_render=deferred, handoff=handoff)
     outs = [torch.empty(E * 300000 * 2, dtype=torch.int16, device="cuda") for _ in range(2)]
     sums = []
