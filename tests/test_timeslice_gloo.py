@@ -1,5 +1,6 @@
 """Host logic of the multi-GPU time slicing (pluto_gps_sim_b200/timeslice.py) on
-CPU: world_size-2 gloo processes, the device replaced by an oracle-backed engine.
+CPU: world_size-2 and -3 gloo processes, the device replaced by an oracle-backed engine;
+both hand-off modes (the mailbox one emulated over gloo, sequence numbers checked).
 The concatenated slices must equal one sequential run of the whole stream --
 i.e. the carrier phases are handed from slice to slice (and from the last rank
 back to rank 0 for the next step) exactly like chan[i].carr_phase."""
@@ -7,6 +8,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -16,13 +18,13 @@ import oracle_lib as ol
 N = 2500          # samples per epoch (short: the oracle is a plain per-sample loop)
 E = 2             # epochs per slice
 STEPS = 3
-WORLD = 2
 
 
 class OracleEngine:
     """Same interface as timeslice.GpuSliceEngine, arithmetic by the oracle."""
 
-    def __init__(self, max_chan):
+    def __init__(self, max_chan, rank=0, world=1):
+        self.rank, self.world = rank, world
         self.phase = torch.zeros(max_chan, dtype=torch.float64)
         self.adv = torch.zeros(2 * max_chan, dtype=torch.float64)
         self.state = np.zeros(max_chan)
@@ -49,6 +51,18 @@ class OracleEngine:
     def store_carrier(self):
         self.phase.copy_(torch.from_numpy(self.state.copy()))
 
+    # the mailbox hand-off (gpsiq_mailbox_send / _recv), emulated: the message carries its sequence number,
+    # which must be exactly what the receiver waits for (on the GPU a wrong number would hang or read a stale slot)
+    def handoff_send(self, seq):
+        dist.send(torch.cat([torch.tensor([float(seq)], dtype=torch.float64), torch.from_numpy(self.state.copy())]),
+                  dst=(self.rank + 1) % self.world)
+
+    def handoff_recv(self, seq):
+        buf = torch.zeros(1 + self.state.size, dtype=torch.float64)
+        dist.recv(buf, src=(self.rank - 1) % self.world)
+        assert int(buf[0]) == seq, (self.rank, int(buf[0]), seq)
+        self.state[:] = buf[1:].numpy()
+
     def chain(self, desc, n_epochs):          # advances the carrier state (and keeps the samples for render)
         self.pending, _ = ol.oracle_synth(desc[:n_epochs], N, carr_state=self.state)
 
@@ -56,22 +70,22 @@ class OracleEngine:
         out[...] = self.pending
 
 
-def _stream_desc():
+def _stream_desc(world):
     d = ol.load_golden_desc("static12")
-    d = np.concatenate([d, d])[: WORLD * STEPS * E].copy()
+    d = np.concatenate([d, d])[: world * STEPS * E].copy()
     d["flags"] = 0
     d[0]["flags"] = 1
     return d
 
 
-def _worker(rank, port, outdir):
+def _worker(rank, WORLD, port, outdir, handoff):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=WORLD)
     from pluto_gps_sim_b200.timeslice import TimeSliceRunner
 
-    desc = _stream_desc()
-    eng = OracleEngine(desc.shape[1])
-    runner = TimeSliceRunner(eng, rank, WORLD)
+    desc = _stream_desc(WORLD)
+    eng = OracleEngine(desc.shape[1], rank, WORLD)
+    runner = TimeSliceRunner(eng, rank, WORLD, handoff=handoff)
     outs = []
     for s in range(STEPS):
         first = (s * WORLD + rank) * E
@@ -87,12 +101,13 @@ def _worker(rank, port, outdir):
     dist.destroy_process_group()
 
 
-def test_time_slices_equal_sequential_stream(tmp_path):
+@pytest.mark.parametrize("WORLD,handoff", [(2, "nccl"), (2, "mailbox"), (3, "nccl"), (3, "mailbox")])
+def test_time_slices_equal_sequential_stream(tmp_path, WORLD, handoff):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_worker, args=(port, str(tmp_path)), nprocs=WORLD, join=True)
-    desc = _stream_desc()
+    mp.spawn(_worker, args=(WORLD, port, str(tmp_path), handoff), nprocs=WORLD, join=True)
+    desc = _stream_desc(WORLD)
     st = np.zeros(desc.shape[1])
     want, _ = ol.oracle_synth(desc, N, carr_state=st)
     parts = [np.load(tmp_path / ("rank%d.npy" % r)) for r in range(WORLD)]
