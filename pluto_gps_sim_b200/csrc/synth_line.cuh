@@ -280,6 +280,35 @@ __device__ __forceinline__ ulonglong2 ln_lds_v2(uint32_t saddr) {
     return v;
 }
 
+// ---- TMA bulk copies (cp.async.bulk, global -> shared, completion on an mbarrier): the per-epoch tables are
+// staged by a handful of copy instructions instead of ~340 load/store instructions per warp
+__device__ __forceinline__ void ln_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void ln_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ln_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// -> false if the phase did not complete within a (very long) bounded spin: the caller flags an error
+__device__ __forceinline__ bool ln_mbar_wait(uint32_t bar, uint32_t parity) {
+    for (int spin = 0; spin < (1 << 22); spin++) {
+        uint32_t ok;
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+
 // One CTA per unit of LN_UNIT consecutive tiles of one epoch.  The CTAs are deliberately NOT persistent:
 // they retire every ~100 us, so the hardware block scheduler can place the small latency-bound kernels of
 // the next batch's carrier chain (launched on higher-priority streams) beside this kernel as slots free up.
@@ -303,6 +332,10 @@ k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
     ulonglong2* s_step = (ulonglong2*) (s_lut + (size_t) CG * 512);      // [16][2] {dF, dG}, {DX, DY}; dG == 0: inactive
     ulonglong2* s_anch = s_step + 32;                                    // [LN_WARPS][16]
     int* s_prn = (int*) (s_anch + LN_WARPS * 16);                        // [16] PRN whose chip tables are resident
+    uint64_t* s_bar = (uint64_t*) (s_prn + 16);                          // mbarrier of the table copies
+    uint32_t* s_tx = (uint32_t*) (s_bar + 1);                            // bytes in flight for the current fill
+    const uint32_t bar_saddr = (uint32_t) __cvta_generic_to_shared(s_bar);
+    uint32_t bar_phase = 0;
     if (chip_saddr + (uint32_t) CG * 4 * LN_VS > (1u << (64 - LN_GBITS))) {  // the chip address must fit G's index field
         if (threadIdx.x == 0) atomicExch(err, 0x40000000);
         return;
@@ -316,6 +349,7 @@ k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
     const unsigned int nunits = (unsigned int) E * upe;
     constexpr int WPT = LN_TILE / LN_WB;               // warp-blocks per tile
     if (threadIdx.x < 16) s_prn[threadIdx.x] = -1;
+    if (threadIdx.x == 0) ln_mbar_init(bar_saddr, 1);
     int cur_e = -1;
     (void) E;
 
@@ -336,19 +370,25 @@ k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
             const int c0 = g * CG, nc = min(CG, C - c0);
             if (ngroups > 1 || e != cur_e) {
                 if (g > 0) __syncthreads();  // everyone is done with the previous group's tables
-                // chip tables: only the slots whose PRN differs from what is resident
-                for (int cl = 0; cl < nc; cl++) {
-                    const int prn = de[c0 + cl].prn;
-                    if (prn > 0 && prn <= 32 && prn != s_prn[cl]) {
-                        const uint4* src = (const uint4*) (chips4 + (size_t) prn * 4 * LN_VS);
-                        uint4* dst = (uint4*) (s_chip + (size_t) cl * 4 * LN_VS);
-                        for (int i = threadIdx.x; i < 4 * LN_VS / 16; i += LN_THREADS) dst[i] = src[i];
+                // Tables of the epoch by TMA bulk copies, one lane of warp 0 per slot: the amplitude LUT, and the chip
+                // tables of the slots whose PRN differs from what is resident.  (The top-of-unit barrier ordered all
+                // reads of the previous tables before these writes.)
+                if (warp == 0) {
+                    int prn = 0;
+                    if (lane < nc) prn = de[c0 + lane].prn;
+                    const bool need_lut = prn > 0;
+                    const bool need_chip = prn > 0 && prn <= 32 && prn != s_prn[lane];
+                    const uint32_t mc = __ballot_sync(0xffffffffu, need_chip), ml = __ballot_sync(0xffffffffu, need_lut);
+                    const uint32_t total = (uint32_t) __popc(mc) * (4u * LN_VS) + (uint32_t) __popc(ml) * 2048u;
+                    if (lane == 0) {
+                        *s_tx = total;
+                        if (total) ln_mbar_expect_tx(bar_saddr, total);
                     }
-                }
-                for (int i = threadIdx.x; i < nc * 128; i += LN_THREADS) {
-                    const int cl = i >> 7;
-                    if (de[c0 + cl].prn > 0)
-                        ((uint4*) s_lut)[i] = ((const uint4*) (lutp + ((size_t) e * C + c0 + cl) * 512))[i & 127];
+                    __syncwarp();
+                    if (need_chip)
+                        ln_bulk_g2s(chip_saddr + (uint32_t) lane * 4 * LN_VS, chips4 + (size_t) prn * 4 * LN_VS, 4 * LN_VS, bar_saddr);
+                    if (need_lut)
+                        ln_bulk_g2s(lut_saddr + (uint32_t) lane * 2048, lutp + ((size_t) e * C + c0 + lane) * 512, 2048, bar_saddr);
                 }
                 __syncthreads();  // all reads of s_prn above are done
                 if (threadIdx.x < 16) {
@@ -364,7 +404,12 @@ k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
                     s_step[2 * threadIdx.x] = st;
                     s_step[2 * threadIdx.x + 1] = make_ulonglong2(ln_split_dx(st.x), ln_split_dy(st.y));
                 }
+                const uint32_t in_flight = *s_tx;
                 __syncthreads();
+                if (in_flight) {  // every thread observes the phase: the copied tables are visible to it afterwards
+                    if (!ln_mbar_wait(bar_saddr, bar_phase) && threadIdx.x == 0) atomicExch(err, 0x20000000);
+                    bar_phase ^= 1u;
+                }
             }
 
             for (int wb = wb0 + warp; wb < wb1; wb += LN_WARPS) {
@@ -384,7 +429,7 @@ k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
                 const int nleft = N - (wb * LN_WB + lane);  // this lane's sample j exists iff 32*j < nleft
                 int32_t acc[LN_RUN];
 #pragma unroll
-                for (int j = 0; j < LN_RUN; j++) acc[j] = 0;
+                for (int j = 0; j < LN_RUN; j++) acc[j] = 0x8000;  // I half biased: it never borrows from the Q half
                 if (g > 0) {
 #pragma unroll
                     for (int j = 0; j < LN_RUN; j++)
@@ -411,7 +456,7 @@ k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
                 if (g == ngroups - 1) {
 #pragma unroll
                     for (int j = 0; j < LN_RUN; j++)
-                        if (32 * j < nleft) dst[32 * j] = ln_pack((uint32_t) acc[j]);
+                        if (32 * j < nleft) dst[32 * j] = (uint32_t) acc[j] ^ 0x8000u;  // un-bias: the int16 pair as stored
                 } else {
 #pragma unroll
                     for (int j = 0; j < LN_RUN; j++)
