@@ -157,7 +157,7 @@ def reference_arm(args):
     samples_per_step = epochs * N_SAMPLES * used
     line = {
         "impl": "reference",
-        "metric": "Msamples/sec (complex I/Q) at 12 channels; reference CPU loop",
+        "metric": "Msamples/sec (complex I/Q) at 12 channels; bit-exact vs CPU ref",   # the same metric string as our arm
         "value": round(value, 3), "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(1e3 * samples_per_step / (value * 1e6), 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64 NCO / int accumulate", "data": "synthetic (generated RINEX fixture)",
