@@ -190,6 +190,9 @@ def ours_arm(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own "NCCL version ..." banner (printed when the environment
+        # sets NCCL_DEBUG) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         opts = None
         if os.environ.get("GPSIQ_NCCL_HIPRI"):               # experiment: NCCL kernels on a high-priority stream
             opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
