@@ -264,6 +264,13 @@ int gpsiq_line_stats(gpsiq_ctx *ctx, int64_t *hazard_tiles, int64_t *patches, in
  * the kernel evaluates (its split-word form of the line, truncation included), and whether the check flags the run. */
 uint64_t gpsiq_minmod_host(uint64_t b, uint64_t a, uint64_t m, uint64_t n, uint64_t stop);
 int gpsiq_line_probe_host(int mode, double x0, double step, int n, int64_t *max_dev, int *mismatches, int *hazard);
+/* The same over whole epochs of real descriptors: literal recurrences give the exact state at every 1024-sample
+ * tile start, every tile is checked as the device checks it, every sample's table / chip index as the line kernel
+ * evaluates it is compared with the recurrence's.  bad = differing samples in tiles the check cleared (must be 0);
+ * lag_flagged = differing samples in flagged tiles (the patch path repairs those).  carr0: phases before the first
+ * epoch (NULL: zeros). */
+int gpsiq_line_verify_host(const gpsiq_chan_desc *desc, int n_epochs, int max_chan, int samples_per_epoch,
+                           const double *carr0, int64_t *tiles, int64_t *flagged, int64_t *bad, int64_t *lag_flagged);
 
 /* Diagnostics: with GPSIQ_TRACE set in the environment the context records a CUDA event after every kernel it
  * launches; this prints them to stderr as milliseconds since the first one (stream 0 = caller / render stream,

@@ -101,6 +101,8 @@ SYMBOLS = {
     "gpsiq_line_stats": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "gpsiq_minmod_host": (C.c_uint64, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
     "gpsiq_line_probe_host": (_i, [_i, _d, _d, _i, C.POINTER(_i64), C.POINTER(_i), C.POINTER(_i)]),
+    "gpsiq_line_verify_host": (_i, [_vp, _i, _i, _i, _vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),
+                                    C.POINTER(_i64)]),
     "gpsiq_strerror": (C.c_char_p, [_i]),
     "gpsiq_last_error": (C.c_char_p, [_vp]),
     "gpsiq_version": (C.c_char_p, []),
@@ -173,6 +175,15 @@ def line_probe(mode, x0, step, n):
     dev, mm, hz = _i64(0), _i(0), _i(0)
     check(lib.gpsiq_line_probe_host(int(mode), float(x0), float(step), int(n), C.byref(dev), C.byref(mm), C.byref(hz)))
     return dev.value, mm.value, bool(hz.value)
+
+
+def line_verify(desc, samples_per_epoch):
+    """Host run of the line kernel's index arithmetic + tile check over desc [E][C] -> (tiles, flagged, bad, lag_flagged)."""
+    d = np.ascontiguousarray(desc)
+    t, f, b, l = _i64(0), _i64(0), _i64(0), _i64(0)
+    check(lib.gpsiq_line_verify_host(d.ctypes.data, d.shape[0], d.shape[1], int(samples_per_epoch), None, C.byref(t),
+                                     C.byref(f), C.byref(b), C.byref(l)))
+    return t.value, f.value, b.value, l.value
 
 
 def carrier_chain_host(steps, N, T, x0, est_err=0.0):

@@ -1926,4 +1926,54 @@ int gpsiq_line_probe_host(int mode, double x0, double step, int n, int64_t* max_
     return GPSIQ_OK;
 }
 
+// Host run of the line kernel's index arithmetic over whole epochs of real descriptors (tests): for every
+// (epoch, slot, 1024-sample tile) the exact tile-start state comes from the literal recurrences
+// (plutogpssim.c:2709-2713, 2741-2746), the tile is checked exactly as k_line_anchor checks it at tile level, and
+// every sample's carrier-table / chip index as k_synth_line evaluates it (ln_kernel_index) is compared with the
+// recurrence's.  bad counts differing samples in tiles the check CLEARED: it must stay 0 (samples of flagged tiles
+// are repaired by k_line_patch).  carr0: the slots' phases before the first epoch (NULL: zeros).
+int gpsiq_line_verify_host(const gpsiq_chan_desc* desc, int n_epochs, int C, int N, const double* carr0, int64_t* tiles_out,
+                           int64_t* flagged_out, int64_t* bad_out, int64_t* lag_flagged_out) {
+    if (!desc || n_epochs < 0 || C < 1 || C > GPSIQ_MAX_CHAN || N < 1) return GPSIQ_ERR_ARG;
+    int64_t tiles = 0, flagged = 0, bad = 0, lag = 0;
+    for (int c = 0; c < C; c++) {
+        double ph = carr0 ? carr0[c] : 0.0;
+        for (int e = 0; e < n_epochs; e++) {
+            const gpsiq_chan_desc& d = desc[(size_t) e * C + c];
+            if (d.prn <= 0) continue;
+            if (d.flags & GPSIQ_FLAG_RESET_CARRIER) ph = d.carr_phase0;
+            if (!(d.code_step > 0.0 && d.code_step <= 0.5) || !(fabs(d.carr_step) <= 0x1p-8)) return GPSIQ_ERR_ARG;  // line kernel's contract
+            double cp = d.code_phase0;
+            const uint64_t dF = ln_carr_slope(d.carr_step), dG = ln_code_slope(d.code_step);
+            for (int t0 = 0; t0 < N; t0 += LN_TILE) {
+                const int len = (N - t0 < LN_TILE) ? N - t0 : LN_TILE;
+                const uint64_t FA = ln_carr_fixed(ph), GA = ln_code_fixed(cp);
+                const int64_t eF = ln_eps(1, LN_TILE), eG = ln_eps(0, LN_TILE);
+                const bool hz = line_hazard(FA, dF, LN_FBITS, (uint64_t) len, -eF - LN_KF, eF) ||
+                                line_hazard(GA, dG, LN_GBITS, (uint64_t) len, -eG - LN_KG, eG);
+                int wraps = 0, differ = 0;
+                for (int n = 0; n < len; n++) {
+                    int it = (int) floor(ph * 512.0);
+                    if (it > 511) it = 511;
+                    const uint32_t chip_true = (uint32_t) ((int) cp + 1023 * wraps);  // unwrapped inside the tile, like G
+                    uint32_t ci, gi;
+                    ln_kernel_index(FA, GA, dF, dG, (uint32_t) n, ci, gi);
+                    if (ci != (uint32_t) it || gi != chip_true) differ++;
+                    nco_step<NCO_CODE>(cp, d.code_step, wraps);
+                    int w2 = 0;
+                    nco_step<NCO_CARRIER>(ph, d.carr_step, w2);
+                }
+                tiles++;
+                if (hz) { flagged++; lag += differ; }
+                else bad += differ;
+            }
+        }
+    }
+    if (tiles_out) *tiles_out = tiles;
+    if (flagged_out) *flagged_out = flagged;
+    if (bad_out) *bad_out = bad;
+    if (lag_flagged_out) *lag_flagged_out = lag;
+    return GPSIQ_OK;
+}
+
 }  // extern "C"
