@@ -29,7 +29,7 @@ extern "C" {
 
 #define GPSHOST_OK 0
 #define GPSHOST_ERR_ARG (-1)
-#define GPSHOST_ERR_NAVFILE (-2)   /* cannot open / not a RINEX-2 navigation file */
+#define GPSHOST_ERR_NAVFILE (-2)   /* cannot open / not a RINEX navigation file of the selected version */
 #define GPSHOST_ERR_NOEPH (-3)     /* no ephemeris (set) usable for the start time */
 #define GPSHOST_ERR_MOTION (-4)    /* user motion file missing or empty */
 #define GPSHOST_ERR_TIME (-5)      /* start time outside the ephemeris span */
@@ -39,7 +39,7 @@ extern "C" {
 #define GPSHOST_POS_MOTION 2 /* -u file: t,x,y,z rows at 10 Hz  plutogpssim.c:2301-2304 */
 
 typedef struct gpshost_config {
-    const char *nav_path;      /* -e: RINEX-2 navigation file, plain or gz */
+    const char *nav_path;      /* -e: RINEX-2 (or, with rinex3, RINEX-3) navigation file, plain or gz */
     int32_t pos_mode;          /* GPSHOST_POS_* */
     double pos[3];             /* llh (degrees, metres) or ECEF metres */
     const char *motion_path;   /* GPSHOST_POS_MOTION */
@@ -51,7 +51,8 @@ typedef struct gpshost_config {
     int64_t sample_rate;       /* -s, Hz (reference default 3000000: TX_SAMPLE_FREQ) */
     int32_t max_chan;          /* 12 = MAX_CHAN, plutogpssim.h:21; up to 32 */
     int32_t carrier_mode;      /* GPSIQ_CARRIER_* */
-    int32_t reserved[8];
+    int32_t rinex3;            /* -3: nav_path is a RINEX-3 navigation file (plutogpssim.c:1241-1610) */
+    int32_t reserved[7];
 } gpshost_config;
 
 typedef struct gpshost_scenario gpshost_scenario;

@@ -455,6 +455,33 @@ struct NavReader {
     }
 };
 
+// BROADCAST ORBIT 1-7 of one record (four 19-column fields per line from column `base`: 3 in RINEX 2,
+// 4 in RINEX 3) and the derived constants (plutogpssim.c:1098-1222 / 1451-1602).  false: the file ended inside.
+static bool read_orbit_lines(NavReader& r, Eph& e, int base) {
+    const int c0 = base, c1 = base + 19, c2 = base + 38, c3 = base + 57;
+    if (!r.next()) return false;
+    e.iode = (int) r.num(c0, 19); e.crs = r.num(c1, 19); e.dn = r.num(c2, 19); e.m0 = r.num(c3, 19);
+    if (!r.next()) return false;
+    e.cuc = r.num(c0, 19); e.ecc = r.num(c1, 19); e.cus = r.num(c2, 19); e.sqrta = r.num(c3, 19);
+    if (!r.next()) return false;
+    e.toe.sec = r.num(c0, 19); e.cic = r.num(c1, 19); e.omg0 = r.num(c2, 19); e.cis = r.num(c3, 19);
+    if (!r.next()) return false;
+    e.inc0 = r.num(c0, 19); e.crc = r.num(c1, 19); e.aop = r.num(c2, 19); e.omgdot = r.num(c3, 19);
+    if (!r.next()) return false;
+    e.idot = r.num(c0, 19); e.code_l2 = (int) r.num(c1, 19); e.toe.week = (int) r.num(c2, 19);
+    if (!r.next()) return false;
+    e.health = (int) r.num(c1, 19);
+    if (e.health > 0 && e.health < 32) e.health += 32;  // summary bit
+    e.tgd = r.num(c2, 19); e.iodc = (int) r.num(c3, 19);
+    if (!r.next()) return false;  // transmission time / fit interval: not used
+    e.valid = true;
+    e.A = e.sqrta * e.sqrta;
+    e.n = sqrt(kGM / (e.A * e.A * e.A)) + e.dn;
+    e.sq1e2 = sqrt(1.0 - e.ecc * e.ecc);
+    e.omgkdot = e.omgdot - kOmegaE;
+    return true;
+}
+
 // returns the number of ephemeris sets (a new set starts when TOC advances by more than one hour)
 int load_rinex2(const char* path, std::vector<std::vector<Eph>>& sets, Klob& k, std::string& date) {
     NavReader r;
@@ -511,26 +538,75 @@ int load_rinex2(const char* path, std::vector<std::vector<Eph>>& sets, Klob& k, 
         e.t = t;
         e.toc = g;
         e.af0 = r.num(22, 19); e.af1 = r.num(41, 19); e.af2 = r.num(60, 19);
-        if (!r.next()) break;
-        e.iode = (int) r.num(3, 19); e.crs = r.num(22, 19); e.dn = r.num(41, 19); e.m0 = r.num(60, 19);
-        if (!r.next()) break;
-        e.cuc = r.num(3, 19); e.ecc = r.num(22, 19); e.cus = r.num(41, 19); e.sqrta = r.num(60, 19);
-        if (!r.next()) break;
-        e.toe.sec = r.num(3, 19); e.cic = r.num(22, 19); e.omg0 = r.num(41, 19); e.cis = r.num(60, 19);
-        if (!r.next()) break;
-        e.inc0 = r.num(3, 19); e.crc = r.num(22, 19); e.aop = r.num(41, 19); e.omgdot = r.num(60, 19);
-        if (!r.next()) break;
-        e.idot = r.num(3, 19); e.code_l2 = (int) r.num(22, 19); e.toe.week = (int) r.num(41, 19);
-        if (!r.next()) break;
-        e.health = (int) r.num(22, 19);
-        if (e.health > 0 && e.health < 32) e.health += 32;  // summary bit
-        e.tgd = r.num(41, 19); e.iodc = (int) r.num(60, 19);
-        if (!r.next()) break;  // transmission time / fit interval: not used
-        e.valid = true;
-        e.A = e.sqrta * e.sqrta;
-        e.n = sqrt(kGM / (e.A * e.A * e.A)) + e.dn;
-        e.sq1e2 = sqrt(1.0 - e.ecc * e.ecc);
-        e.omgkdot = e.omgdot - kOmegaE;
+        if (!read_orbit_lines(r, e, 3)) break;
+    }
+    if (first.week >= 0) set += 1;
+    return set;
+}
+
+// RINEX-3 navigation file (plutogpssim.c:1241-1610; the reference's -3 option): same record content, other
+// columns -- a record starts "Gnn yyyy mm dd hh mm ss", fields sit one column further right, the header carries
+// IONOSPHERIC CORR (GPSA / GPSB), TIME SYSTEM CORR (GPUT) and LEAP SECONDS; records of other constellations
+// (first character not 'G') and their continuation lines are skipped.
+int load_rinex3(const char* path, std::vector<std::vector<Eph>>& sets, Klob& k, std::string& date) {
+    NavReader r;
+    r.fp = gzopen(path, "rt");
+    if (!r.fp) return -1;
+    sets.assign(kSets + 1, std::vector<Eph>(kMaxSv));
+    int seen = 0;
+    while (r.next()) {
+        if (r.label("COMMENT")) continue;
+        if (r.label("END OF HEADER")) break;
+        if (r.label("RINEX VERSION / TYPE")) {
+            if (r.num(0, 9) < 3.0) return -2;
+            if (r.line[20] != 'N' && r.line[40] != 'G') return -3;
+        } else if (r.label("PGM / RUN BY / DATE")) {
+            date.assign(r.line + 40, strnlen(r.line + 40, 20));
+        } else if (r.label("IONOSPHERIC CORR")) {
+            if (strncmp(r.line, "GPSA", 4) == 0) {
+                for (int i = 0; i < 4; i++) k.a[i] = r.num(5 + 12 * i, 12);
+                seen |= 1;
+            } else if (strncmp(r.line, "GPSB", 4) == 0) {
+                for (int i = 0; i < 4; i++) k.b[i] = r.num(5 + 12 * i, 12);
+                seen |= 2;
+            }
+        } else if (r.label("TIME SYSTEM CORR") && strncmp(r.line, "GPUT", 4) == 0) {
+            k.A0 = r.num(5, 17);
+            k.A1 = r.num(22, 16);
+            k.tot = (int) r.num(38, 7);   // (the reference converts a 'D' here too before atoi: same digits)
+            k.wnt = r.integer(45, 6);
+            if (k.tot % 4096 == 0) seen |= 4;
+        } else if (r.label("LEAP SECONDS")) {
+            k.dtls = r.integer(0, 6);
+            seen |= 8;
+        }
+    }
+    k.valid = (seen == 0xF);
+
+    Tow first;
+    int set = 0;
+    while (r.next()) {
+        if (r.line[0] != 'G') continue;
+        const int sv = r.integer(1, 2) - 1;
+        Cal t;
+        t.y = r.integer(4, 4);
+        t.m = r.integer(9, 2);
+        t.d = r.integer(12, 2);
+        t.hh = r.integer(15, 2);
+        t.mm = r.integer(18, 2);
+        t.sec = (double) r.integer(21, 2);
+        const Tow g = cal_to_tow(t);
+        if (first.week == -1) first = g;
+        if (tow_diff(g, first) > kHour) {
+            first = g;
+            if (++set >= kSets) break;
+        }
+        if (sv < 0 || sv >= kMaxSv) break;  // not a GPS PRN (the reference would index out of bounds here)
+        Eph& e = sets[set][sv];
+        e.t = t;
+        e.toc = g;
+        e.af0 = r.num(23, 19); e.af1 = r.num(42, 19); e.af2 = r.num(61, 19);
+        if (!read_orbit_lines(r, e, 4)) break;
     }
     if (first.week >= 0) set += 1;
     return set;
@@ -643,8 +719,9 @@ struct gpshost_scenario {
         } else {
             memcpy(xyz0, cfg.pos, sizeof xyz0);
         }
-        nsets = load_rinex2(cfg.nav_path, sets, iono, rinex_date);
-        if (nsets < 0) { g_error = "cannot read RINEX-2 navigation file"; return GPSHOST_ERR_NAVFILE; }
+        nsets = cfg.rinex3 ? load_rinex3(cfg.nav_path, sets, iono, rinex_date)
+                                : load_rinex2(cfg.nav_path, sets, iono, rinex_date);
+        if (nsets < 0) { g_error = cfg.rinex3 ? "cannot read RINEX-3 navigation file" : "cannot read RINEX-2 navigation file"; return GPSHOST_ERR_NAVFILE; }
         if (nsets == 0) { g_error = "no ephemeris available"; return GPSHOST_ERR_NOEPH; }
 
         // span of the file, start time, optional TOC/TOE overwrite (plutogpssim.c:2497-2574)

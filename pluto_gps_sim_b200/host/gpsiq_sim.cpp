@@ -88,7 +88,7 @@ int main(int argc, char** argv) {
         switch (opt) {
             case 'e': nav = optarg; break;
             case 'u': motion = optarg; hc.pos_mode = GPSHOST_POS_MOTION; have_pos = true; break;
-            case '3': fprintf(stderr, "ERROR: RINEX-3 input is not supported by this build (use a RINEX-2 file).\n"); return 1;
+            case '3': hc.rinex3 = 1; break;  // (takes and ignores an argument, like the reference's "3:" option string)
             case 'f': fprintf(stderr, "ERROR: FTP download is not available (no network code in this build).\n"); return 1;
             case 'c':
                 if (sscanf(optarg, "%lf,%lf,%lf", &hc.pos[0], &hc.pos[1], &hc.pos[2]) != 3) { usage(); return 1; }

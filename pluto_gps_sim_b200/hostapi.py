@@ -23,7 +23,7 @@ class HostConfig(C.Structure):
         ("nav_path", C.c_char_p), ("pos_mode", C.c_int32), ("pos", C.c_double * 3), ("motion_path", C.c_char_p),
         ("have_start", C.c_int32), ("start", C.c_int32 * 5), ("start_sec", C.c_double), ("time_overwrite", C.c_int32),
         ("iono_disable", C.c_int32), ("sample_rate", C.c_int64), ("max_chan", C.c_int32), ("carrier_mode", C.c_int32),
-        ("reserved", C.c_int32 * 8),
+        ("rinex3", C.c_int32), ("reserved", C.c_int32 * 7),
     ]
 
 
@@ -62,11 +62,11 @@ class HostError(RuntimeError):
 
 
 class Scenario:
-    """nav: RINEX-2 navigation file (plain or gz).  Exactly one of llh (deg, deg, m), xyz (ECEF m), motion (csv path).
+    """nav: RINEX-2 navigation file (plain or gz); rinex3=True: a RINEX-3 one (the reference's -3).  Exactly one of llh (deg, deg, m), xyz (ECEF m), motion (csv path).
     start: (y, m, d, hh, mm, sec) or None (first TOC of the file, the reference's default)."""
 
     def __init__(self, nav, llh=None, xyz=None, motion=None, start=None, time_overwrite=False, iono=True,
-                 sample_rate=3000000, max_chan=12, carrier_mode=capi.CARRIER_FLOAT):
+                 sample_rate=3000000, max_chan=12, carrier_mode=capi.CARRIER_FLOAT, rinex3=False):
         cfg = HostConfig()
         self._keep = [os.fsencode(nav), os.fsencode(motion) if motion else None]
         cfg.nav_path = self._keep[0]
@@ -87,6 +87,7 @@ class Scenario:
         cfg.sample_rate = int(sample_rate)
         cfg.max_chan = int(max_chan)
         cfg.carrier_mode = int(carrier_mode)
+        cfg.rinex3 = int(bool(rinex3))
         self.max_chan = int(max_chan)
         self._h = C.c_void_p()
         rc = lib.gpshost_open(C.byref(self._h), C.byref(cfg))

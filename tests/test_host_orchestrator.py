@@ -1,7 +1,8 @@
 """Host orchestrator (libgpshost.so): the descriptors it computes from a
 navigation file must be BIT-identical to the reference's own per-epoch channel state -- against the committed
 goldens (made from the compiled reference, tools/gen_golden.py) and, where oracle/_ref is built, against
-live runs of the reference with other option combinations (-t, -T, -i, -c, ephemeris roll-over)."""
+live runs of the reference with other option combinations (-t, -T, -i, -c, ephemeris roll-over, and -3: a
+RINEX-3 file of the same constellation with records of other constellations interleaved)."""
 import os
 
 import numpy as np
@@ -13,6 +14,7 @@ from pluto_gps_sim_b200 import capi, hostapi
 
 NAV12 = os.path.join(ol.GOLDEN, "brdc3540_synth.14n.gz")
 NAV32 = os.path.join(ol.GOLDEN, "allsky32_synth.14n.gz")
+NAV12_V3 = os.path.join(ol.GOLDEN, "brdc3540_synth.14p.gz")      # RINEX 3.02 (tools/gen_rinex_fixture.py --rinex3)
 CIRCLE = os.path.join(refdump.REF_DIR, "circle.csv")
 LLH = (30.286502, 120.032669, 100)
 
@@ -63,6 +65,33 @@ LIVE = [
     ("ephemeris_rollover", ["-l", "30.286502,120.032669,100", "-s", "2600000", "-t", "2014/12/20,00:59:40"],
      dict(llh=LLH, sample_rate=2600000, start=(2014, 12, 20, 0, 59, 40.0)), 330),
 ]
+
+
+@pytest.mark.skipif(not refdump.have_ref(), reason="needs the compiled reference (oracle/_ref)")
+@pytest.mark.parametrize("start,epochs", [(None, 12), ((2014, 12, 20, 0, 59, 40.0), 330)])
+def test_rinex3_against_live_reference(tmp_path, start, epochs):
+    """The reference's -3 path (readRinex3, plutogpssim.c:1241-1610) on a RINEX-3 file, incl. an ephemeris roll-over."""
+    argv = ["-3", "x", "-l", "30.286502,120.032669,100", "-s", "2600000"]
+    if start:
+        argv += ["-t", "%04d/%02d/%02d,%02d:%02d:%02d" % tuple(int(v) for v in start)]
+    refdump.SCENARIOS["_live3"] = ("ref_harness_O2", "brdc3540_synth.14p.gz", argv, 12)
+    recs, _, _ = refdump.run_reference("_live3", epochs, str(tmp_path), want_iq=False)
+    want = refdump.to_descriptors(recs)
+    with hostapi.Scenario(NAV12_V3, llh=LLH, sample_rate=2600000, start=start, rinex3=True) as s:
+        got = s.next(epochs)
+    assert_same_descriptors(got, want)
+    # the same constellation as the RINEX-2 fixture: the two readers agree with each other as well
+    with hostapi.Scenario(NAV12, llh=LLH, sample_rate=2600000, start=start) as s2:
+        assert_same_descriptors(got, s2.next(epochs))
+
+
+def test_rinex_version_mismatch_is_reported():
+    with pytest.raises(hostapi.HostError) as e:
+        hostapi.Scenario(NAV12, llh=LLH, rinex3=True)            # a RINEX-2 file read as RINEX 3
+    assert e.value.status == hostapi.ERR_NAVFILE
+    with pytest.raises(hostapi.HostError) as e:
+        hostapi.Scenario(NAV12_V3, llh=LLH)                      # and the other way round
+    assert e.value.status == hostapi.ERR_NAVFILE
 
 
 @pytest.mark.skipif(not refdump.have_ref(), reason="needs the compiled reference (oracle/_ref)")

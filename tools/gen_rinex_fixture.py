@@ -98,9 +98,28 @@ def sv_elements_allsky(sv):
     return dict(ecc=ecc, inc0=inc, omg0=wrap_pi(omg0), m0=wrap_pi(m0), aop=wrap_pi(aop))
 
 
-def build(kind):
+def header3():
+    """RINEX 3.02 header as readRinex3 reads it (plutogpssim.c:1263-1368)."""
+    def line(body, label):
+        return body.ljust(60)[:60] + label.ljust(20) + "\n"
+    d17 = lambda x: ("% .10E" % x).replace("E", "D")
+    d16 = lambda x: ("% .9E" % x).replace("E", "D")
+    h = ""
+    h += line("     3.02           N: GNSS NAV DATA    G: GPS", "RINEX VERSION / TYPE")
+    h += line("b200-gps-iq synth   graft               20141221 000000 UTC", "PGM / RUN BY / DATE")
+    h += line("synthetic constellation, see tools/gen_rinex_fixture.py", "COMMENT")
+    h += line("GPSA " + d12(1.1180e-08) + d12(2.2350e-08) + d12(-5.9600e-08) + d12(-1.1920e-07), "IONOSPHERIC CORR")
+    h += line("GPSB " + d12(9.0110e+04) + d12(1.1470e+05) + d12(-6.5540e+04) + d12(-5.2430e+05), "IONOSPHERIC CORR")
+    h += line("GAUT " + d17(1.0e-9) + d16(2.0e-15) + "%7d%5d" % (345600, 1824), "TIME SYSTEM CORR")   # not GPS: skipped
+    h += line("GPUT " + d17(0.0) + d16(0.0) + "%7d%5d" % (503808, 1824), "TIME SYSTEM CORR")
+    h += line("%6d" % 16, "LEAP SECONDS")
+    h += line("", "END OF HEADER")
+    return h
+
+
+def build(kind, rinex3=False):
     out = io.StringIO()
-    out.write(header())
+    out.write(header3() if rinex3 else header())
     n0 = math.sqrt(GM / A_SMA ** 3)
     omgdot = -8.0e-9
     for k in range(12):                       # two-hourly sets
@@ -124,6 +143,19 @@ def build(kind):
                 (2.0, 0.0, -1.0e-8 + 5.0e-10 * (sv % 8), float(iode)),                     # acc health TGD IODC
                 (float(toe - 7200 + 18), 4.0, 0.0, 0.0),                                   # transmission time, fit
             ]
+            if rinex3:
+                if sv % 8 == 1:   # records of other constellations in between (3 resp. 7 continuation lines): skipped
+                    out.write("R%02d %04d %02d %02d %02d %02d %02d" % (sv, 2014, 12, 20, hh, 15, 0) + d19(1e-5) + d19(0.0) + d19(518400.0) + "\n")
+                    for _ in range(3):
+                        out.write("    " + "".join(d19(v) for v in (1.0e4, -2.0, 0.0, 0.0)) + "\n")
+                    out.write("E%02d %04d %02d %02d %02d %02d %02d" % (sv, 2014, 12, 20, hh, 10, 0) + d19(2e-5) + d19(0.0) + d19(0.0) + "\n")
+                    for _ in range(7):
+                        out.write("    " + "".join(d19(v) for v in (5.0, 6.0, 7.0, 8.0)) + "\n")
+                l0 = "G%02d %04d %02d %02d %02d %02d %02d" % (sv, 2014, 12, 20, hh, 0, 0) + d19(af0) + d19(af1) + d19(0.0)
+                out.write(l0 + "\n")
+                for r in rows:
+                    out.write("    " + "".join(d19(v) for v in r) + "\n")
+                continue
             out.write(l0 + "\n")
             for r in rows:
                 out.write("   " + "".join(d19(v) for v in r) + "\n")
@@ -134,8 +166,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--kind", choices=["gps", "allsky"], default="gps")
     ap.add_argument("-o", "--out", required=True)
+    ap.add_argument("--rinex3", action="store_true", help="RINEX 3.02 layout (the reference's -3 / readRinex3), with "
+                    "records of other constellations interleaved")
     a = ap.parse_args()
-    text = build(a.kind).encode("ascii")
+    text = build(a.kind, a.rinex3).encode("ascii")
     raw = io.BytesIO()
     with gzip.GzipFile(fileobj=raw, mode="wb", mtime=0, filename="") as g:
         g.write(text)
