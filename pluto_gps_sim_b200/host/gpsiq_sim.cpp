@@ -3,13 +3,15 @@
 //
 //   host orchestration  libgpshost.so  (descriptors, bit-identical to the reference's per-epoch state)
 //   sample synthesis     libgpsiq.so    (sm_100a kernels behind the C-ABI; no CPU fallback)
-//   sink                 file / stdout / none.  The reference pushes 300000-sample buffers to an ADALM-Pluto
-//                        through libiio (plutogpssim.c:2146-2158); libiio is not available in this build, so
-//                        the SDR options are accepted and reported as ignored, and the stream is delivered to
-//                        a Sink in the same 300000-sample units.
+//   sink                 libgpshost.so  (include/gpssink.h): none / file / stdout / ADALM-Pluto.  The reference pushes
+//                        300000-sample buffers to the SDR through libiio (plutogpssim.c:2146-2158); -r selects
+//                        the same transport here (libiio is dlopen()ed at that point; without it the open
+//                        fails loudly).  Every sink gets the stream in the same 300000-sample units, from
+//                        its own writer thread: batch k is drained while batch k+1 is fetched from the GPU.
 //
 // Differences from the reference, all deliberate: it stops after -d seconds (the reference runs until
-// a signal arrives); -o/-b/-n are new; -f (FTP download) is refused (no network code here).
+// a signal arrives); -o/-b/-n/-r are new (the radio is one sink among others, not the only one); -f (FTP
+// download) is refused (no network code here).
 #include <getopt.h>
 #include <unistd.h>
 
@@ -25,25 +27,11 @@
 
 #include "../../include/gpshost.h"
 #include "../../include/gpsiq.h"
+#include "../../include/gpssink.h"
 
 namespace {
 
 constexpr int kSamplesPerEpoch = 300000;  // NUM_SAMPLES = TX_SAMPLE_FREQ/10, independent of -s (plutogpssim.c:43-44)
-
-struct Sink {  // receives the stream in the reference's push units (one 0.1 s buffer = 300000 I/Q pairs)
-    virtual ~Sink() {}
-    virtual bool push(const int16_t* iq, size_t pairs) = 0;
-};
-struct NullSink : Sink {
-    bool push(const int16_t*, size_t) override { return true; }
-};
-struct FileSink : Sink {
-    FILE* fp;
-    bool own;
-    FileSink(FILE* f, bool o) : fp(f), own(o) {}
-    ~FileSink() override { if (own && fp) fclose(fp); }
-    bool push(const int16_t* iq, size_t pairs) override { return fwrite(iq, 4, pairs, fp) == pairs; }
-};
 
 void usage() {
     fprintf(stderr,
@@ -58,10 +46,14 @@ void usage() {
             "  -s <frequency>   Sampling frequency [Hz] (default: 3000000)\n"
             "  -i               Disable ionospheric delay for spacecraft scenario\n"
             "  -v               Show details about the simulated channels\n"
-            "  -A/-B/-U/-N/-g   SDR options of the reference: accepted, ignored (no libiio in this build)\n"
+            "  -A <attenuation> Set TX attenuation [dB] (default -20.0)          (used with -r)\n"
+            "  -B <bw>          Set RF bandwidth [MHz] (default 5.0)             (used with -r)\n"
+            "  -U <uri>         ADALM-Pluto URI                                  (used with -r)\n"
+            "  -N <network>     ADALM-Pluto network IP or hostname (default pluto.local)\n"
             "Options of this build:\n"
             "  -d <seconds>     Duration [s] (default 1.0; the reference runs until interrupted)\n"
             "  -o <file>        Write the int16 I/Q stream to <file> (\"-\" = stdout; default: discard)\n"
+            "  -r               Transmit through an ADALM-Pluto (libiio), as the reference does\n"
             "  -b <epochs>      0.1 s epochs per GPU batch (default 128)\n"
             "  -n <channels>    Channel slots (default 12 = MAX_CHAN; up to 32)\n");
 }
@@ -78,13 +70,15 @@ int main(int argc, char** argv) {
     hc.carrier_mode = GPSIQ_CARRIER_FLOAT;
     double duration = 1.0;
     int batch = 128;
-    bool verbose = false, have_pos = false;
+    bool verbose = false, have_pos = false, use_radio = false;
+    gpssink_radio_config radio;
+    gpssink_radio_defaults(&radio);
     const char* out_path = nullptr;
     std::string nav, motion;
 
     if (argc < 3) { usage(); return 1; }
     int opt;
-    while ((opt = getopt(argc, argv, "e:3:u:g:c:l:s:T:t:A:B:U:N:vfi?d:o:b:n:")) != -1) {
+    while ((opt = getopt(argc, argv, "e:3:u:g:c:l:s:T:t:A:B:U:N:vfi?d:o:b:n:r")) != -1) {
         switch (opt) {
             case 'e': nav = optarg; break;
             case 'u': motion = optarg; hc.pos_mode = GPSHOST_POS_MOTION; have_pos = true; break;
@@ -101,6 +95,7 @@ int main(int argc, char** argv) {
             case 's':
                 hc.sample_rate = (long long) atoi(optarg);
                 if (hc.sample_rate < 1000000) { fprintf(stderr, "ERROR: Invalid sampling frequency.\n"); return 1; }
+                gpssink_radio_option(&radio, 's', optarg);
                 break;
             case 'T':
                 hc.time_overwrite = 1;
@@ -123,9 +118,9 @@ int main(int argc, char** argv) {
                 break;
             case 'i': hc.iono_disable = 1; break;
             case 'v': verbose = true; break;
-            case 'A': case 'B': case 'U': case 'N': case 'g':
-                fprintf(stderr, "note: -%c %s ignored (SDR transport is not part of this build)\n", opt, optarg);
-                break;
+            case 'A': case 'B': case 'U': case 'N': gpssink_radio_option(&radio, opt, optarg); break;
+            case 'g': break;  // in the reference's option string, handled nowhere (plutogpssim.c:2296)
+            case 'r': use_radio = true; break;
             case 'd': duration = atof(optarg); break;
             case 'o': out_path = optarg; break;
             case 'b': batch = atoi(optarg); break;
@@ -148,14 +143,10 @@ int main(int argc, char** argv) {
         fputs(buf, stderr);
     }
 
-    std::unique_ptr<Sink> sink;
-    if (!out_path) sink.reset(new NullSink());
-    else if (strcmp(out_path, "-") == 0) sink.reset(new FileSink(stdout, false));
-    else {
-        FILE* fp = fopen(out_path, "wb");
-        if (!fp) { fprintf(stderr, "ERROR: cannot open %s\n", out_path); return 1; }
-        sink.reset(new FileSink(fp, true));
-    }
+    gpssink* sink = nullptr;
+    int src = use_radio ? gpssink_open_radio(&sink, &radio) : out_path ? gpssink_open_file(&sink, out_path) : gpssink_open_null(&sink);
+    if (src != GPSSINK_OK) { fprintf(stderr, "ERROR: %s\n", gpssink_last_error()); return 1; }
+    if (use_radio) fprintf(stderr, "Gain: %.1fdB\n", radio.gain_db);  // plutogpssim.c:2571
 
     const long total_epochs = (long) (duration * 10.0 + 0.5);
     if (batch > total_epochs) batch = (int) total_epochs;
@@ -188,24 +179,27 @@ int main(int argc, char** argv) {
     submit_next();
     size_t k = 0;
     bool ok = true;
+    int64_t ticket[2] = {0, 0};                // the sink's claim on each pinned buffer
     while (k < sizes.size() && ok) {
         submit_next();                         // (no-op at the end of the stream)
         int16_t* buf = iq[k & 1];
+        if (ticket[k & 1] > 0 && gpssink_wait(sink, ticket[k & 1]) != GPSSINK_OK) { ok = false; break; }   // batch k-2 drained
         if (gpsiq_fetch(gq, buf) != GPSIQ_OK) { fprintf(stderr, "ERROR: %s\n", gpsiq_last_error(gq)); return 1; }
-        for (int e = 0; e < sizes[k] && ok; e++)   // the reference's unit: one 300000-sample buffer per push
-            ok = sink->push(buf + (size_t) e * kSamplesPerEpoch * 2, kSamplesPerEpoch);
-        if (verbose) {
-            int week; double sec;
-            gpshost_time(sc, &week, &sec);
-            fprintf(stderr, "\rTime into run = %4.1f", (double) (k + 1) * batch / 10.0);
-        }
+        // sizes[k] push units (one 300000-sample buffer each, plutogpssim.c:2146-2158), written while batch k+1 is fetched
+        ticket[k & 1] = gpssink_submit(sink, buf, (size_t) sizes[k] * kSamplesPerEpoch);
+        if (ticket[k & 1] < 0) ok = false;
+        if (verbose) fprintf(stderr, "\rTime into run = %4.1f", (double) std::min<long>((long) (k + 1) * batch, produced) / 10.0);
         k++;
     }
+    int64_t sunk_pairs = 0, pushes = 0;
+    gpssink_stats(sink, &sunk_pairs, &pushes);   // waits for the writer
+    std::string sink_err = ok ? "" : gpssink_last_error();
+    if (gpssink_close(sink) != GPSSINK_OK) { if (ok) sink_err = gpssink_last_error(); ok = false; }
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
-    if (!ok) fprintf(stderr, "\nERROR: sink refused data\n");
-    fprintf(stderr, "%s%ld epochs (%.1f s of signal, %.0f samples) in %.3f s: %.1f Msamples/s, %lld kernel launches\n",
+    if (!ok) fprintf(stderr, "\nERROR: sink refused data: %s\n", sink_err.c_str());
+    fprintf(stderr, "%s%ld epochs (%.1f s of signal, %.0f samples) in %.3f s: %.1f Msamples/s, %lld kernel launches, %lld buffers to the sink\n",
             verbose ? "\n" : "", produced, produced / 10.0, (double) produced * kSamplesPerEpoch, secs,
-            (double) produced * kSamplesPerEpoch / secs / 1e6, (long long) gpsiq_launch_count(gq));
+            (double) produced * kSamplesPerEpoch / secs / 1e6, (long long) gpsiq_launch_count(gq), (long long) (sunk_pairs / kSamplesPerEpoch));
     gpsiq_host_free(desc); gpsiq_host_free(iq[0]); gpsiq_host_free(iq[1]);
     gpsiq_destroy(gq);
     gpshost_close(sc);

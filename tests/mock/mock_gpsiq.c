@@ -1,0 +1,60 @@
+/* TEST INFRASTRUCTURE -- NOT a CPU fallback and never shipped or loaded by the product.
+ *
+ * A stand-in for libgpsiq.so that lets the CPU test suite (no GPU in the build container) exercise the control
+ * flow of the command-line front end gpsiq_sim -- option parsing, host orchestration, batching, the two pinned
+ * buffers in flight, the hand-off to the sink's writer thread -- end to end against the reference's stream.
+ * It implements only the seven entry points gpsiq_sim calls, on top of the parity oracle (oracle/gpsiq_oracle.c,
+ * compiled into this mock by tests/test_front_end_cpu.py), and lives in a scratch directory next to a COPY of the
+ * gpsiq_sim binary (whose rpath is $ORIGIN); the real libgpsiq.so refuses to work without a GPU
+ * (tests/test_capi_load.py::test_no_cpu_fallback_without_gpu) and stays the only library in the package directory. */
+#include <stdlib.h>
+#include <string.h>
+
+#include "gpsiq.h"
+
+int oracle_synth(const gpsiq_chan_desc *desc, int n_epochs, int nslots, int samples_per_epoch, int carrier_mode,
+                 double *carr_state, int16_t *iq_out, double *carr_trace);
+
+struct pending { gpsiq_chan_desc *desc; int n; struct pending *next; };
+struct gpsiq_ctx {
+    gpsiq_config cfg;
+    double carr[GPSIQ_MAX_CHAN];
+    struct pending *head, *tail;
+    int64_t calls;
+};
+
+int gpsiq_create(gpsiq_ctx **ctx, const gpsiq_config *cfg) {
+    gpsiq_ctx *c = calloc(1, sizeof *c);
+    c->cfg = *cfg;
+    *ctx = c;
+    return GPSIQ_OK;
+}
+void gpsiq_destroy(gpsiq_ctx *c) { free(c); }
+void *gpsiq_host_alloc(size_t bytes) { return malloc(bytes); }
+void gpsiq_host_free(void *p) { free(p); }
+const char *gpsiq_last_error(const gpsiq_ctx *c) { (void) c; return "mock_gpsiq (test infrastructure)"; }
+int64_t gpsiq_launch_count(const gpsiq_ctx *c) { (void) c; return 0; }   /* no kernels: says so in the summary line */
+
+int gpsiq_submit(gpsiq_ctx *c, const gpsiq_chan_desc *desc, int n_epochs) {
+    if (n_epochs < 1 || n_epochs > c->cfg.max_epochs) return GPSIQ_ERR_ARG;
+    struct pending *p = calloc(1, sizeof *p);
+    const size_t bytes = (size_t) n_epochs * c->cfg.max_chan * sizeof *desc;
+    p->desc = malloc(bytes);
+    memcpy(p->desc, desc, bytes);        /* the real submit copies the descriptors too: the caller reuses its buffer */
+    p->n = n_epochs;
+    if (c->tail) c->tail->next = p; else c->head = p;
+    c->tail = p;
+    return GPSIQ_OK;
+}
+
+int gpsiq_fetch(gpsiq_ctx *c, int16_t *iq_out) {
+    struct pending *p = c->head;
+    if (!p) return GPSIQ_ERR_ARG;
+    c->head = p->next;
+    if (!c->head) c->tail = NULL;
+    const int rc = oracle_synth(p->desc, p->n, c->cfg.max_chan, c->cfg.samples_per_epoch, c->cfg.carrier_mode, c->carr,
+                                iq_out, NULL);
+    free(p->desc);
+    free(p);
+    return rc == 0 ? GPSIQ_OK : GPSIQ_ERR_ARG;
+}

@@ -1,0 +1,136 @@
+"""Control flow of the command-line front end (gpsiq_sim) on the CPU.
+
+The GPU tests (tests/test_gpu_parity.py) run the real thing.  Here a COPY of the gpsiq_sim binary is placed in a
+scratch directory next to libgpshost.so (the product's) and tests/mock/mock_gpsiq.c (TEST INFRASTRUCTURE: the seven
+libgpsiq entry points gpsiq_sim calls, computed by the parity oracle), so that option parsing, host orchestration,
+batching with two buffers in flight and the hand-off to the sink's writer thread are checked end to end against
+the reference's streams without a GPU.  What is NOT covered here is the CUDA library -- nothing in this file is a
+statement about it, and the product package never contains or loads the mock."""
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+from pluto_gps_sim_b200 import checksum_host, hostapi
+
+N = 300000
+FAKE_IIO = os.path.join(ol.ORACLE_DIR, "libfakeiio.so")
+NAV12 = os.path.join(ol.GOLDEN, "brdc3540_synth.14n.gz")
+NAV32 = os.path.join(ol.GOLDEN, "allsky32_synth.14n.gz")
+STATIC = ["-l", "30.286502,120.032669,100", "-s", "2600000"]
+
+
+@pytest.fixture(scope="module")
+def sim(tmp_path_factory):
+    d = tmp_path_factory.mktemp("front_end")
+    shutil.copy(hostapi.SIM_PATH, d / "gpsiq_sim")
+    shutil.copy(hostapi.LIB_PATH, d / "libgpshost.so")
+    subprocess.run(["gcc", "-std=c11", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(ol.REPO, "include"),
+                    "-o", str(d / "libgpsiq.so"), os.path.join(ol.REPO, "tests", "mock", "mock_gpsiq.c"),
+                    os.path.join(ol.ORACLE_DIR, "gpsiq_oracle.c"), "-lm"], check=True)
+    if not os.path.exists(FAKE_IIO):
+        subprocess.run(["make", "-C", ol.ORACLE_DIR, "libfakeiio.so"], check=True, stdout=subprocess.DEVNULL)
+
+    def run(args, env=None, check=True, binary=False):
+        r = subprocess.run([str(d / "gpsiq_sim")] + args, capture_output=True, env=dict(os.environ, **(env or {})))
+        r.stderr = r.stderr.decode(errors="replace")
+        if not binary:
+            r.stdout = r.stdout.decode(errors="replace")
+        if check:
+            assert r.returncode == 0, r.stderr
+        return r
+    return run
+
+
+@pytest.mark.parametrize("batch", ["4", "3", "128"])      # even, ragged last batch, one batch
+def test_static12_stream_byte_identical_to_the_reference(sim, tmp_path, batch):
+    out = tmp_path / "iq.bin"
+    r = sim(["-e", NAV12, "-o", str(out), "-d", "1.0", "-b", batch] + STATIC)
+    data = out.read_bytes()
+    assert len(data) == 10 * N * 4
+    assert hashlib.sha256(data).hexdigest() == ol.load_golden_meta("static12")["iq_sha256"], r.stderr
+    assert "10 buffers to the sink" in r.stderr and "Using static location mode." in r.stderr
+
+
+def test_32_channels_10MSps_first_epochs(sim, tmp_path):
+    out = tmp_path / "iq.bin"
+    sim(["-e", NAV32, "-o", str(out), "-l", "30.286502,120.032669,100", "-s", "10000000", "-d", "0.3", "-n", "32", "-b", "2"])
+    iq = np.fromfile(out, np.int16).reshape(3, N, 2)
+    want = ol.load_golden_meta("allsky32")["epoch_checksums"]
+    assert [int(checksum_host(iq[e])) for e in range(3)] == want[:3]
+
+
+def test_user_motion_file_first_epochs(sim, tmp_path):
+    circle = os.path.join(ol.ORACLE_DIR, "_ref", "circle.csv")
+    if not os.path.exists(circle):
+        pytest.skip("oracle/_ref/circle.csv (the reference's motion fixture) not present")
+    out = tmp_path / "iq.bin"
+    r = sim(["-e", NAV12, "-o", str(out), "-u", circle, "-s", "2600000", "-d", "0.5", "-b", "2"])
+    iq = np.fromfile(out, np.int16).reshape(5, N, 2)
+    assert [int(checksum_host(iq[e])) for e in range(5)] == ol.load_golden_meta("circle12")["epoch_checksums"][:5]
+    assert "Using user motion mode." in r.stderr
+
+
+def test_user_motion_across_the_30s_refresh_full_golden(sim, tmp_path):
+    """31 s of circle.csv: NAV frame rebuild and channel re-allocation at 30 s (plutogpssim.c:2764-2806) happen inside
+    the front end's batch loop; SHA-256 of the 372 MB stream against the reference's own run."""
+    circle = os.path.join(ol.ORACLE_DIR, "_ref", "circle.csv")
+    if not os.path.exists(circle):
+        pytest.skip("oracle/_ref/circle.csv (the reference's motion fixture) not present")
+    h = hashlib.sha256()
+    r = sim(["-e", NAV12, "-o", "-", "-u", circle, "-s", "2600000", "-d", "31.0", "-b", "64"], binary=True)
+    h.update(r.stdout)
+    assert len(r.stdout) == 310 * N * 4
+    assert h.hexdigest() == ol.load_golden_meta("circle12")["iq_sha256"]
+
+
+def test_stdout_sink_and_null_sink(sim):
+    res = sim(["-e", NAV12, "-d", "0.2", "-b", "1"] + STATIC)                 # discard
+    assert "2 buffers to the sink" in res.stderr and "600000 samples" in res.stderr
+    res = sim(["-e", NAV12, "-d", "0.2", "-o", "-"] + STATIC, binary=True)    # "-" = stdout: bytes only, messages on stderr
+    iq = np.frombuffer(res.stdout, np.int16).reshape(2, N, 2)
+    assert [int(checksum_host(iq[e])) for e in range(2)] == ol.load_golden_meta("static12")["epoch_checksums"][:2]
+
+
+def test_radio_sink_through_the_front_end(sim, tmp_path):
+    """-r: the stream goes out through libiio in 300000-pair buffers, each exactly once (the reference's own
+    hand-off can drop or repeat one), after the reference's radio set-up with its options."""
+    import json
+    log, out = tmp_path / "calls.log", tmp_path / "pushed.bin"
+    env = {"GPSSINK_IIO_LIB": FAKE_IIO, "FAKE_IIO_LOG": str(log), "FAKE_IIO_OUT": str(out), "FAKE_IIO_EPOCHS": "1000",
+           "FAKE_IIO_NO_DEFAULT": "1"}
+    r = sim(["-e", NAV12, "-r", "-d", "1.0", "-b", "3", "-A", "-35.5", "-B", "3.0", "-U", "usb:1.2.5"] + STATIC, env=env)
+    golden = json.load(open(os.path.join(ol.GOLDEN, "iio_calls.json")))["uri_gain_bandwidth"]
+    assert log.read_text().splitlines() == golden["calls"]
+    assert hashlib.sha256(out.read_bytes()).hexdigest() == ol.load_golden_meta("static12")["iq_sha256"]
+    assert "Gain: -35.5dB" in r.stderr and "10 buffers to the sink" in r.stderr
+
+
+def test_radio_sink_failures_end_the_run_with_an_error(sim, tmp_path):
+    env = {"GPSSINK_IIO_LIB": str(tmp_path / "absent-libiio.so")}
+    r = sim(["-e", NAV12, "-r", "-d", "0.2"] + STATIC, env=env, check=False)
+    assert r.returncode == 1 and "libiio is not available" in r.stderr
+    # the device refuses the third buffer: the run stops, exit status 1, tear-down still happens
+    log = tmp_path / "calls.log"
+    env = {"GPSSINK_IIO_LIB": FAKE_IIO, "FAKE_IIO_LOG": str(log), "FAKE_IIO_EPOCHS": "3", "FAKE_IIO_OUT": str(tmp_path / "p.bin")}
+    r = sim(["-e", NAV12, "-r", "-d", "1.0", "-b", "2"] + STATIC, env=env, check=False)
+    assert r.returncode == 1 and "Error pushing buf -1" in r.stderr
+    assert log.read_text().splitlines()[-1] == "context_destroy"
+    assert os.path.getsize(tmp_path / "p.bin") == 3 * N * 4
+
+
+def test_option_errors_match_the_reference_s_messages(sim, tmp_path):
+    assert "ERROR: GPS ephemeris file is not specified." in sim(["-l", "1,2,3", "-d", "1"], check=False).stderr
+    assert "ERROR: Invalid sampling frequency." in sim(["-e", NAV12, "-s", "999999"], check=False).stderr
+    assert "ERROR: Invalid date and time." in sim(["-e", NAV12, "-t", "2014-12-20"], check=False).stderr
+    r = sim(["-e", str(tmp_path / "nope.14n"), "-l", "1,2,3"], check=False)
+    assert r.returncode == 1 and "ERROR" in r.stderr
+    r = sim(["-e", NAV12, "-o", str(tmp_path / "no" / "dir" / "x.bin")] + STATIC, check=False)
+    assert r.returncode == 1 and "cannot open" in r.stderr
+    assert sim(["-e", NAV12, "-f"] + STATIC, check=False).returncode == 1

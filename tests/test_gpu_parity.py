@@ -368,6 +368,30 @@ def test_command_line_front_end_reproduces_the_reference_stream(tmp_path, scenar
     assert hashlib.sha256(data).hexdigest() == meta["iq_sha256"], r.stderr
 
 
+def test_front_end_radio_sink_pushes_the_reference_stream_once_each(tmp_path):
+    """gpsiq_sim -r on the GPU: the reference's libiio set-up calls (tests/golden/iio_calls.json, recorded from the
+    unmodified reference) and then the golden stream, one 300000-pair buffer per push, none lost or repeated.
+    libiio is the capture backend oracle/libfakeiio.so, dlopen()ed by the sink."""
+    import hashlib
+    import json
+    import subprocess
+    from pluto_gps_sim_b200 import hostapi
+
+    fake = os.path.join(ol.ORACLE_DIR, "libfakeiio.so")
+    if not os.path.exists(fake):
+        subprocess.run(["make", "-C", ol.ORACLE_DIR, "libfakeiio.so"], check=True, stdout=subprocess.DEVNULL)
+    log, out = tmp_path / "calls.log", tmp_path / "pushed.bin"
+    env = dict(os.environ, GPSSINK_IIO_LIB=fake, FAKE_IIO_LOG=str(log), FAKE_IIO_OUT=str(out), FAKE_IIO_EPOCHS="1000",
+               FAKE_IIO_NO_DEFAULT="1")
+    nav = os.path.join(ol.GOLDEN, "brdc3540_synth.14n.gz")
+    r = subprocess.run([hostapi.SIM_PATH, "-e", nav, "-r", "-l", "30.286502,120.032669,100", "-s", "2600000", "-d", "1.0",
+                        "-b", "4", "-A", "-35.5", "-B", "3.0", "-U", "usb:1.2.5"], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    golden = json.load(open(os.path.join(ol.GOLDEN, "iio_calls.json")))["uri_gain_bandwidth"]
+    assert log.read_text().splitlines() == golden["calls"]
+    assert hashlib.sha256(out.read_bytes()).hexdigest() == ol.load_golden_meta("static12")["iq_sha256"], r.stderr
+
+
 def test_config2_full_300s_user_motion_stream_through_the_front_end():
     """BASELINE config[2] in full: 3000 epochs (300 s, 3.6 GB) of circle.csv user motion, navigation file in,
     bytes out, SHA-256 against the reference's own 300 s run (tools/gen_golden_long.py).  Crosses ten 30 s
