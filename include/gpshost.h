@@ -52,7 +52,9 @@ typedef struct gpshost_config {
     int32_t max_chan;          /* 12 = MAX_CHAN, plutogpssim.h:21; up to 32 */
     int32_t carrier_mode;      /* GPSIQ_CARRIER_* */
     int32_t rinex3;            /* -3: nav_path is a RINEX-3 navigation file (plutogpssim.c:1241-1610) */
-    int32_t reserved[7];
+    int32_t threads;           /* worker threads of gpshost_next over the epochs of a batch: 0 = $GPSHOST_THREADS, else
+                                  min(8, cores); 1 = serial.  The descriptors do not depend on it. */
+    int32_t reserved[6];
 } gpshost_config;
 
 typedef struct gpshost_scenario gpshost_scenario;

@@ -12,11 +12,13 @@
 
 #include <zlib.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -782,8 +784,9 @@ struct gpshost_scenario {
         return GPSHOST_OK;
     }
 
-    // one pass of the reference's epoch loop minus the sample loop (plutogpssim.c:2655-2687, 2761-2805)
-    int epoch(gpsiq_chan_desc* out) {
+    // one pass of the reference's epoch loop minus the sample loop (plutogpssim.c:2655-2687, 2761-2805).
+    // `sights`, if given, holds this epoch's pseudoranges per slot, computed ahead by run()'s worker threads.
+    int epoch(gpsiq_chan_desc* out, const Sight* sights = nullptr) {
         const std::vector<Eph>& eph = sets[(size_t) iset];
         for (size_t i = 0; i < chan.size(); i++) {
             Slot& ch = chan[i];
@@ -791,7 +794,7 @@ struct gpshost_scenario {
                 memset(&out[i], 0, sizeof out[i]);
                 continue;
             }
-            const Sight rho = line_of_sight(eph[(size_t) ch.prn - 1], iono, grx, position());
+            const Sight rho = sights ? sights[i] : line_of_sight(eph[(size_t) ch.prn - 1], iono, grx, position());
             ch.az = rho.az;
             ch.el = rho.el;
             code_setup(ch, rho, 0.1);
@@ -824,6 +827,68 @@ struct gpshost_scenario {
         if (++imotion >= nmotion) imotion = 0;
         return GPSHOST_OK;
     }
+
+    // n_epochs epochs, multi-threaded over epochs.  The pseudorange of a channel at an epoch
+    // (satellite state, light time, Earth rotation, ionosphere: ~95 % of the host work) depends only on the epoch's time,
+    // the receiver position and the ephemeris -- not on the previous epoch.  Everything that IS sequential stays
+    // sequential: the millisecond-rounded time steps, the range differences (code_setup), the NAV word counters and the
+    // 30 s refresh.  So the stream is cut at the refresh epochs (the channel table and the ephemeris set are constant in
+    // between), the times and positions of a segment are stepped through serially, worker threads fill the segment's
+    // pseudoranges with the very same function calls, and one thread finishes the descriptors: bit-identical to the
+    // serial path by construction (tests/test_host_orchestrator.py compares them anyway).
+    int run(gpsiq_chan_desc* out, int n_epochs) {
+        const size_t nch = chan.size();
+        int workers = cfg.threads > 0 ? cfg.threads : 0;
+        if (workers == 0) {
+            const char* env = getenv("GPSHOST_THREADS");
+            workers = env ? atoi(env) : (int) std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+        }
+        std::vector<Tow> when;
+        std::vector<int> where;
+        std::vector<Sight> sights;
+        int done = 0;
+        while (done < n_epochs) {
+            // the segment: up to and including the next refresh epoch
+            when.clear();
+            where.clear();
+            Tow g = grx;
+            int im = imotion;
+            while (done + (int) when.size() < n_epochs) {
+                when.push_back(g);
+                where.push_back(im);
+                const bool refresh = ((int) (g.sec * 10.0 + 0.5)) % 300 == 0;
+                g = tow_add(g, 0.1);
+                if (++im >= nmotion) im = 0;
+                if (refresh) break;
+            }
+            const int seg = (int) when.size();
+            const int use = std::min(workers, seg / 16);   // below ~16 epochs per thread the spawn costs more than it saves
+            if (use <= 1) {
+                for (int j = 0; j < seg; j++)
+                    if (int rc = epoch(out + (size_t) (done + j) * nch)) return rc;
+                done += seg;
+                continue;
+            }
+            sights.resize((size_t) seg * nch);
+            const std::vector<Eph>& eph = sets[(size_t) iset];
+            auto fill = [&](int j0, int j1) {
+                for (int j = j0; j < j1; j++) {
+                    const double* pos = cfg.pos_mode == GPSHOST_POS_MOTION ? &motion[(size_t) where[(size_t) j] * 3] : xyz0;
+                    for (size_t i = 0; i < nch; i++)
+                        if (chan[i].prn > 0)
+                            sights[(size_t) j * nch + i] = line_of_sight(eph[(size_t) chan[i].prn - 1], iono, when[(size_t) j], pos);
+                }
+            };
+            std::vector<std::thread> pool;
+            for (int t = 1; t < use; t++) pool.emplace_back(fill, (int) ((long) seg * t / use), (int) ((long) seg * (t + 1) / use));
+            fill(0, seg / use);
+            for (std::thread& t : pool) t.join();
+            for (int j = 0; j < seg; j++)
+                if (int rc = epoch(out + (size_t) (done + j) * nch, &sights[(size_t) j * nch])) return rc;
+            done += seg;
+        }
+        return GPSHOST_OK;
+    }
 };
 
 extern "C" {
@@ -845,11 +910,7 @@ void gpshost_close(gpshost_scenario* s) { delete s; }
 
 int gpshost_next(gpshost_scenario* s, gpsiq_chan_desc* desc, int n_epochs) {
     if (!s || !desc || n_epochs < 0) return GPSHOST_ERR_ARG;
-    for (int e = 0; e < n_epochs; e++) {
-        const int rc = s->epoch(desc + (size_t) e * s->chan.size());
-        if (rc != GPSHOST_OK) return rc;
-    }
-    return GPSHOST_OK;
+    return s->run(desc, n_epochs);
 }
 
 int gpshost_time(gpshost_scenario* s, int* week, double* sec) {

@@ -10,7 +10,7 @@
 //                        its own writer thread: batch k is drained while batch k+1 is fetched from the GPU.
 //
 // Differences from the reference, all deliberate: it stops after -d seconds (the reference runs until
-// a signal arrives); -o/-b/-n/-r are new (the radio is one sink among others, not the only one); -f (FTP
+// a signal arrives); -o/-b/-n/-j/-r are new (the radio is one sink among others, not the only one); -f (FTP
 // download) is refused (no network code here).
 #include <getopt.h>
 #include <unistd.h>
@@ -55,7 +55,8 @@ void usage() {
             "  -o <file>        Write the int16 I/Q stream to <file> (\"-\" = stdout; default: discard)\n"
             "  -r               Transmit through an ADALM-Pluto (libiio), as the reference does\n"
             "  -b <epochs>      0.1 s epochs per GPU batch (default 128)\n"
-            "  -n <channels>    Channel slots (default 12 = MAX_CHAN; up to 32)\n");
+            "  -n <channels>    Channel slots (default 12 = MAX_CHAN; up to 32)\n"
+            "  -j <threads>     Host threads for the per-epoch orbit/range work (default min(8, cores); 1 = serial)\n");
 }
 
 }  // namespace
@@ -78,7 +79,7 @@ int main(int argc, char** argv) {
 
     if (argc < 3) { usage(); return 1; }
     int opt;
-    while ((opt = getopt(argc, argv, "e:3:u:g:c:l:s:T:t:A:B:U:N:vfi?d:o:b:n:r")) != -1) {
+    while ((opt = getopt(argc, argv, "e:3:u:g:c:l:s:T:t:A:B:U:N:vfi?d:o:b:n:rj:")) != -1) {
         switch (opt) {
             case 'e': nav = optarg; break;
             case 'u': motion = optarg; hc.pos_mode = GPSHOST_POS_MOTION; have_pos = true; break;
@@ -125,6 +126,7 @@ int main(int argc, char** argv) {
             case 'o': out_path = optarg; break;
             case 'b': batch = atoi(optarg); break;
             case 'n': hc.max_chan = atoi(optarg); break;
+            case 'j': hc.threads = atoi(optarg); break;
             default: usage(); return 1;
         }
     }

@@ -23,7 +23,7 @@ class HostConfig(C.Structure):
         ("nav_path", C.c_char_p), ("pos_mode", C.c_int32), ("pos", C.c_double * 3), ("motion_path", C.c_char_p),
         ("have_start", C.c_int32), ("start", C.c_int32 * 5), ("start_sec", C.c_double), ("time_overwrite", C.c_int32),
         ("iono_disable", C.c_int32), ("sample_rate", C.c_int64), ("max_chan", C.c_int32), ("carrier_mode", C.c_int32),
-        ("rinex3", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("rinex3", C.c_int32), ("threads", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -66,7 +66,7 @@ class Scenario:
     start: (y, m, d, hh, mm, sec) or None (first TOC of the file, the reference's default)."""
 
     def __init__(self, nav, llh=None, xyz=None, motion=None, start=None, time_overwrite=False, iono=True,
-                 sample_rate=3000000, max_chan=12, carrier_mode=capi.CARRIER_FLOAT, rinex3=False):
+                 sample_rate=3000000, max_chan=12, carrier_mode=capi.CARRIER_FLOAT, rinex3=False, threads=0):
         cfg = HostConfig()
         self._keep = [os.fsencode(nav), os.fsencode(motion) if motion else None]
         cfg.nav_path = self._keep[0]
@@ -88,6 +88,7 @@ class Scenario:
         cfg.max_chan = int(max_chan)
         cfg.carrier_mode = int(carrier_mode)
         cfg.rinex3 = int(bool(rinex3))
+        cfg.threads = int(threads)       # 0 = default (min(8, cores)), 1 = serial; same descriptors either way
         self.max_chan = int(max_chan)
         self._h = C.c_void_p()
         rc = lib.gpshost_open(C.byref(self._h), C.byref(cfg))

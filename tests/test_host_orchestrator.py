@@ -136,3 +136,30 @@ def test_error_reporting():
 def test_library_exports_every_declared_symbol():
     for name in hostapi.SYMBOLS:
         assert hasattr(hostapi.lib, name)
+
+
+@pytest.mark.parametrize("name,kw,batches", [
+    ("static12", dict(nav=NAV12, llh=LLH, sample_rate=2600000), [700]),
+    ("static12-ragged", dict(nav=NAV12, llh=LLH, sample_rate=2600000), [1, 298, 2, 17, 300, 95]),   # batches that end on / straddle the refresh
+    ("circle12", dict(nav=NAV12, motion=CIRCLE, sample_rate=2600000), [650]),
+    ("allsky32", dict(nav=NAV32, llh=LLH, sample_rate=10000000, max_chan=32), [400]),
+    ("rinex3-int-carrier", dict(nav=NAV12_V3, rinex3=True, llh=LLH, sample_rate=2600000, carrier_mode=capi.CARRIER_INT32), [330]),
+])
+def test_worker_threads_do_not_change_a_bit(name, kw, batches, monkeypatch):
+    """gpshost_next spreads the pseudorange computations of a batch over worker threads (SURVEY section 8 row f1);
+    the serial pass (threads=1) is the reference's order of evaluation.  Every byte of every descriptor must agree,
+    across the 30 s refresh (NAV frame, re-allocation) and whatever the batch boundaries are."""
+    if "motion" in kw and not os.path.exists(CIRCLE):
+        pytest.skip("oracle/_ref/circle.csv not present")
+    monkeypatch.delenv("GPSHOST_THREADS", raising=False)
+    with hostapi.Scenario(threads=1, **kw) as s:
+        want = s.next(sum(batches))
+    for threads in (3, 8, 0):
+        with hostapi.Scenario(threads=threads, **kw) as s:
+            got = np.concatenate([s.next(n) for n in batches])
+            t_end = s.time
+        assert got.tobytes() == want.tobytes(), (name, threads)
+    monkeypatch.setenv("GPSHOST_THREADS", "5")
+    with hostapi.Scenario(threads=0, **kw) as s:
+        assert s.next(sum(batches)).tobytes() == want.tobytes()
+        assert s.time == t_end
