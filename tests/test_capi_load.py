@@ -53,3 +53,24 @@ def test_product_does_not_reference_oracle():
                 for needle in ("liboracle", "oracle_lib", "gpsiq_oracle", "import oracle", "from oracle", "oracle/_ref",
                                "/oracle/", "oracle_synth"):
                     assert needle not in text, (needle, os.path.join(root, f))
+
+
+def test_every_header_under_include_is_fully_exported():
+    """include/*.h is the drop-in boundary: every function any of the headers declares must be an exported
+    symbol of the library that header documents (no compute is called here)."""
+    from pluto_gps_sim_b200 import hostapi, sinkapi
+
+    libs = {"gpsiq": C.CDLL(capi.LIB_PATH), "gpshost": C.CDLL(hostapi.LIB_PATH), "gpssink": C.CDLL(hostapi.LIB_PATH)}
+    bound = {"gpsiq": set(capi.SYMBOLS), "gpshost": set(hostapi.SYMBOLS), "gpssink": set(sinkapi.SYMBOLS)}
+    seen = set()
+    inc = os.path.join(REPO, "include")
+    for h in sorted(os.listdir(inc)):
+        text = re.sub(r"/\*.*?\*/", "", open(os.path.join(inc, h)).read(), flags=re.S)
+        for name in re.findall(r"\b((gpsiq|gpshost|gpssink)_[a-z0-9_]+)\s*\(", text):
+            fn, prefix = name
+            if fn == "gpsiq_make_desc_inline":          # header-only body (gpsiq_desc.h)
+                continue
+            assert hasattr(libs[prefix], fn), "%s declares %s, which its library does not export" % (h, fn)
+            assert fn in bound[prefix], "%s has no ctypes binding" % fn
+            seen.add(prefix)
+    assert seen == {"gpsiq", "gpshost", "gpssink"}
