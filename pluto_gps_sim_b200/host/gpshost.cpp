@@ -75,6 +75,11 @@ struct Slot {  // one channel (the part of channel_t the host owns)
 std::string g_error;
 
 // ---- time (plutogpssim.c:250-290, 838-866) ------------------------------------------------
+bool cal_ok(const Cal& t) {  // what cal_to_tow can take (a malformed record line must not index the month table)
+    return t.m >= 1 && t.m <= 12 && t.d >= 0 && t.d <= 31 && t.hh >= 0 && t.hh < 25 && t.mm >= 0 && t.mm < 61 && t.sec >= 0.0 &&
+           t.sec < 62.0 && t.y >= 1980 && t.y < 2200;
+}
+
 Tow cal_to_tow(const Cal& t) {
     static const int doy[12] = {0, 31, 59, 90, 120, 151, 181, 212, 243, 273, 304, 334};
     const int ye = t.y - 1980;
@@ -183,7 +188,9 @@ SvState sv_state(const Eph& eph, const Tow& g) {
 
     const double mk = eph.m0 + eph.n * tk;
     double ek = mk, ekold = ek + 1.0, one_m_ecosE = 0;
-    while (fabs(ek - ekold) > 1.0E-14) {  // Kepler's equation, Newton steps
+    // Kepler's equation, Newton steps to the reference's tolerance (plutogpssim.c:470-476).  GPS orbits (e < 0.03) are
+    // there after <= 5 steps; the cap only ends the loop for a corrupted eccentricity, where the reference spins forever.
+    for (int it = 0; it < 64 && fabs(ek - ekold) > 1.0E-14; it++) {
         ekold = ek;
         one_m_ecosE = 1.0 - eph.ecc * cos(ekold);
         ek = ek + (mk - ekold + eph.ecc * sin(ekold)) / one_m_ecosE;
@@ -439,7 +446,12 @@ struct NavReader {
     char line[100];
     NavReader() { memset(line, 0, sizeof line); }
     ~NavReader() { if (fp) gzclose(fp); }
-    bool next() { return gzgets(fp, line, (int) sizeof line) != nullptr; }
+    bool next() {
+        if (!gzgets(fp, line, (int) sizeof line)) return false;
+        const size_t n = strlen(line);
+        memset(line + n, 0, sizeof line - n);  // fixed-column reads past a short line see blanks, not the previous line
+        return true;
+    }
     bool label(const char* s) const { return strncmp(line + 60, s, strlen(s)) == 0; }
     double num(int col, int width) const {
         char tmp[24];
@@ -529,6 +541,7 @@ int load_rinex2(const char* path, std::vector<std::vector<Eph>>& sets, Klob& k, 
         t.hh = r.integer(12, 2);
         t.mm = r.integer(15, 2);
         t.sec = r.num(18, 2);
+        if (!cal_ok(t)) break;  // not a record line
         const Tow g = cal_to_tow(t);
         if (first.week == -1) first = g;
         if (tow_diff(g, first) > kHour) {
@@ -597,6 +610,7 @@ int load_rinex3(const char* path, std::vector<std::vector<Eph>>& sets, Klob& k, 
         t.hh = r.integer(15, 2);
         t.mm = r.integer(18, 2);
         t.sec = (double) r.integer(21, 2);
+        if (!cal_ok(t)) break;  // not a record line
         const Tow g = cal_to_tow(t);
         if (first.week == -1) first = g;
         if (tow_diff(g, first) > kHour) {
@@ -800,6 +814,10 @@ struct gpshost_scenario {
             code_setup(ch, rho, 0.1);
             const double path_loss = 20200000.0 / rho.dist;
             const int ibs = (int) ((90.0 - rho.el * kRad2Deg) / 5.0);  // elevation -> boresight angle index
+            if (ibs < 0 || ibs >= 37) {  // NaN / absurd geometry from a corrupted ephemeris (the reference reads out of bounds)
+                g_error = "satellite geometry not finite (corrupted ephemeris?)";
+                return GPSHOST_ERR_NOEPH;
+            }
             const double gain = path_loss * ant[ibs];
             const int rc = gpsiq_make_desc_inline(&out[i], cfg.carrier_mode, ch.prn, ch.f_carr, ch.f_code, delt, ch.carr_phase0,
                                                   ch.code_phase, ch.words, ch.iword, ch.ibit, ch.icode, gain, ch.fresh);

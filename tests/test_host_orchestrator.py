@@ -163,3 +163,61 @@ def test_worker_threads_do_not_change_a_bit(name, kw, batches, monkeypatch):
     with hostapi.Scenario(threads=0, **kw) as s:
         assert s.next(sum(batches)).tobytes() == want.tobytes()
         assert s.time == t_end
+
+
+def _mutated_nav(tmp_path, src, edits, name="bad.nav"):
+    import gzip
+    lines = gzip.open(src, "rt").read().split("\n")
+    for edit in edits:
+        edit(lines)
+    p = tmp_path / name
+    p.write_text("\n".join(lines))
+    return str(p)
+
+
+def _first_record(lines):
+    return next(i for i, l in enumerate(lines) if "END OF HEADER" in l) + 1
+
+
+def test_corrupted_navigation_files_fail_with_an_error_not_a_crash(tmp_path):
+    """Malformed input the reference answers with out-of-bounds reads or an endless loop (found by mutating the
+    fixtures under ASan/UBSan): month 0 in a record line (doy[] index -1, plutogpssim.c:844), an eccentricity the
+    Kepler iteration cannot converge for (plutogpssim.c:483), geometry that turns NaN (ant_pat[] index,
+    plutogpssim.c:2678), a file cut inside a record, an empty file.  A valid file is untouched by the guards:
+    every golden above still matches bit for bit."""
+    def month0(lines):
+        i = _first_record(lines)
+        lines[i] = lines[i][:6] + " 0" + lines[i][8:]
+
+    def ecc4(lines):                       # BROADCAST ORBIT 2, second field: e
+        for r in range(0, 8 * 12, 8):
+            i = _first_record(lines) + r + 2
+            lines[i] = lines[i][:22] + " 4.000000000000D+00" + lines[i][41:]
+
+    def nan_sqrta(lines):                  # sqrt(A) = 0 -> n = inf -> NaN ranges
+        for r in range(0, 8 * 40, 8):
+            i = _first_record(lines) + r + 2
+            lines[i] = lines[i][:60] + " 0.000000000000D+00"
+
+    def cut(lines):
+        del lines[_first_record(lines) + 3:]
+
+    for edits, status in (([month0], (hostapi.ERR_NOEPH, hostapi.ERR_NAVFILE)), ([cut], (hostapi.ERR_NOEPH, hostapi.ERR_NAVFILE))):
+        with pytest.raises(hostapi.HostError) as ei:
+            hostapi.Scenario(_mutated_nav(tmp_path, NAV12, edits), llh=LLH, sample_rate=2600000)
+        assert ei.value.status in status
+    for edits in ([ecc4], [nan_sqrta]):   # opens or not -- but it returns, with an error at the latest from next()
+        try:
+            with hostapi.Scenario(_mutated_nav(tmp_path, NAV12, edits), llh=LLH, sample_rate=2600000) as s:
+                s.next(320)
+        except hostapi.HostError as e:
+            assert e.status in (hostapi.ERR_NOEPH, hostapi.ERR_ARG, hostapi.ERR_NAVFILE)
+    empty = tmp_path / "empty.nav"
+    empty.write_text("")
+    with pytest.raises(hostapi.HostError):
+        hostapi.Scenario(str(empty), llh=LLH, sample_rate=2600000)
+    with pytest.raises(hostapi.HostError):
+        def month0_v3(lines):              # "Gnn yyyy mm dd ...": month in columns 9-10
+            i = next(k for k in range(_first_record(lines), len(lines)) if lines[k].startswith("G"))   # first GPS record
+            lines[i] = lines[i][:9] + " 0" + lines[i][11:]
+        hostapi.Scenario(_mutated_nav(tmp_path, NAV12_V3, [month0_v3], "bad3.nav"), llh=LLH, sample_rate=2600000, rinex3=True)
