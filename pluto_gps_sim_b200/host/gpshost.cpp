@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -628,20 +629,22 @@ int load_rinex3(const char* path, std::vector<std::vector<Eph>>& sets, Klob& k, 
     return set;
 }
 
-int load_motion(const char* path, std::vector<double>& xyz) {  // plutogpssim.c:1794-1818
-    FILE* fp = fopen(path, "rt");
+// User motion file: "t,x,y,z" rows at 10 Hz, ECEF metres; at most kMotionMax rows; the time column is ignored
+// (readUserMotion, plutogpssim.c:1794-1818).  A row with fewer than four fields keeps the previous row's values for
+// the missing ones (the reference's scratch variables live across rows); a blank line ends the file.
+int load_motion(const char* path, std::vector<double>& xyz) {
+    std::unique_ptr<FILE, int (*)(FILE*)> fp(fopen(path, "rt"), fclose);
     if (!fp) return -1;
-    char str[100];
-    int n = 0;
     xyz.assign((size_t) kMotionMax * 3, 0.0);
-    for (; n < kMotionMax; n++) {
-        if (!fgets(str, sizeof str, fp)) break;
-        double t, x, y, z;
-        if (EOF == sscanf(str, "%lf,%lf,%lf,%lf", &t, &x, &y, &z)) break;
-        xyz[(size_t) n * 3] = x; xyz[(size_t) n * 3 + 1] = y; xyz[(size_t) n * 3 + 2] = z;
+    double row[4] = {0.0, 0.0, 0.0, 0.0};
+    char text[100];
+    int rows = 0;
+    while (rows < kMotionMax && fgets(text, sizeof text, fp.get()) &&
+           sscanf(text, "%lf,%lf,%lf,%lf", &row[0], &row[1], &row[2], &row[3]) != EOF) {
+        std::copy(row + 1, row + 4, xyz.begin() + (size_t) rows * 3);
+        rows++;
     }
-    fclose(fp);
-    return n;
+    return rows;
 }
 
 }  // namespace
