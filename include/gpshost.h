@@ -66,6 +66,9 @@ void gpshost_close(gpshost_scenario *s);
 int gpshost_next(gpshost_scenario *s, gpsiq_chan_desc *desc, int n_epochs);
 /* What the reference prints at start-up (plutogpssim.c:2571-2574, 2634-2639): start time and channel table. */
 int gpshost_describe(gpshost_scenario *s, char *buf, int buflen);
+/* What the reference's -v adds (plutogpssim.c:2487-2495): the ionosphere / UTC parameters of the file header, four
+ * lines; empty when the header is incomplete (the reference prints nothing then). */
+int gpshost_describe_iono(gpshost_scenario *s, char *buf, int buflen);
 /* Receiver time of the next epoch to be produced (GPS week, seconds of week). */
 int gpshost_time(gpshost_scenario *s, int *week, double *sec);
 const char *gpshost_last_error(void);

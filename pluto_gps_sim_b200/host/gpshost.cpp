@@ -959,6 +959,16 @@ int gpshost_describe(gpshost_scenario* s, char* buf, int buflen) {
     return GPSHOST_OK;
 }
 
+int gpshost_describe_iono(gpshost_scenario* s, char* buf, int buflen) {
+    if (!s || !buf || buflen < 1) return GPSHOST_ERR_ARG;
+    buf[0] = 0;
+    const Klob& k = s->iono;
+    if (k.valid)  // the reference prints the block only for a complete header (plutogpssim.c:2487-2495)
+        snprintf(buf, (size_t) buflen, "  %12.3e %12.3e %12.3e %12.3e\n  %12.3e %12.3e %12.3e %12.3e\n   %19.11e %19.11e  %9d %9d\n%6d\n",
+                 k.a[0], k.a[1], k.a[2], k.a[3], k.b[0], k.b[1], k.b[2], k.b[3], k.A0, k.A1, k.tot, k.wnt, k.dtls);
+    return GPSHOST_OK;
+}
+
 uint32_t gpshost_parity(uint32_t source, int nib) { return parity_word(source, nib); }
 
 void gpshost_date2gps(int y, int m, int d, int hh, int mm, double sec, int* week, double* sow) {

@@ -139,16 +139,18 @@ int main(int argc, char** argv) {
 
     gpshost_scenario* sc = nullptr;
     if (gpshost_open(&sc, &hc) != GPSHOST_OK) { fprintf(stderr, "ERROR: %s\n", gpshost_last_error()); return 1; }
-    {
-        char buf[4096];
-        gpshost_describe(sc, buf, sizeof buf);
-        fputs(buf, stderr);
+    char text[4096];
+    if (verbose) {  // ionosphere / UTC parameters of the header (plutogpssim.c:2487-2495)
+        gpshost_describe_iono(sc, text, sizeof text);
+        fputs(text, stderr);
     }
+    if (use_radio) fprintf(stderr, "Gain: %.1fdB\n", radio.gain_db);  // plutogpssim.c:2571
+    gpshost_describe(sc, text, sizeof text);   // RINEX date, start time, channel table (plutogpssim.c:2572-2574, 2634-2639)
+    fputs(text, stderr);
 
     gpssink* sink = nullptr;
     int src = use_radio ? gpssink_open_radio(&sink, &radio) : out_path ? gpssink_open_file(&sink, out_path) : gpssink_open_null(&sink);
     if (src != GPSSINK_OK) { fprintf(stderr, "ERROR: %s\n", gpssink_last_error()); return 1; }
-    if (use_radio) fprintf(stderr, "Gain: %.1fdB\n", radio.gain_db);  // plutogpssim.c:2571
 
     const long total_epochs = (long) (duration * 10.0 + 0.5);
     if (batch > total_epochs) batch = (int) total_epochs;

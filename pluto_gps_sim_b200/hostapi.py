@@ -32,6 +32,7 @@ SYMBOLS = {
     "gpshost_close": (None, [C.c_void_p]),
     "gpshost_next": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "gpshost_describe": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "gpshost_describe_iono": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "gpshost_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "gpshost_last_error": (C.c_char_p, []),
     "gpshost_parity": (C.c_uint32, [C.c_uint32, C.c_int]),
@@ -119,6 +120,12 @@ class Scenario:
     def describe(self):
         buf = C.create_string_buffer(8192)
         lib.gpshost_describe(self._h, buf, len(buf))
+        return buf.value.decode()
+
+    def describe_iono(self):
+        """The reference's -v block: ionosphere / UTC header parameters ('' for an incomplete header)."""
+        buf = C.create_string_buffer(1024)
+        lib.gpshost_describe_iono(self._h, buf, len(buf))
         return buf.value.decode()
 
     @property

@@ -112,6 +112,17 @@ def test_radio_sink_through_the_front_end(sim, tmp_path):
     assert "Gain: -35.5dB" in r.stderr and "10 buffers to the sink" in r.stderr
 
 
+def test_start_up_text_is_the_reference_s(sim, tmp_path):
+    """-v -r: mode, ionosphere/UTC block, gain, RINEX date, start time and channel table, line for line what the
+    unmodified reference prints (recorded by tools/gen_iio_golden.py)."""
+    import json
+    want = json.load(open(os.path.join(ol.GOLDEN, "iio_calls.json")))["_banner_v"]["stderr"]
+    env = {"GPSSINK_IIO_LIB": FAKE_IIO, "FAKE_IIO_EPOCHS": "1000"}
+    r = sim(["-e", NAV12, "-v", "-r", "-d", "0.1"] + STATIC, env=env)
+    got = r.stderr.splitlines()
+    assert got[:len(want)] == want, "\n".join(got)
+
+
 def test_radio_sink_failures_end_the_run_with_an_error(sim, tmp_path):
     env = {"GPSSINK_IIO_LIB": str(tmp_path / "absent-libiio.so")}
     r = sim(["-e", NAV12, "-r", "-d", "0.2"] + STATIC, env=env, check=False)

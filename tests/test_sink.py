@@ -129,7 +129,8 @@ def test_radio_sink_without_libiio_fails_loudly(tmp_path, monkeypatch):
     assert ei.value.status == sinkapi.ERR_BACKEND and "lacks iio_" in str(ei.value)
 
 
-GOLDEN_CALLS = json.load(open(os.path.join(ol.GOLDEN, "iio_calls.json")))
+_GOLDEN_FILE = json.load(open(os.path.join(ol.GOLDEN, "iio_calls.json")))
+GOLDEN_CALLS = {k: v for k, v in _GOLDEN_FILE.items() if not k.startswith("_")}
 
 
 def _run_sink_in_subprocess(tmp_path, options, default_ctx, units, limit=None, mode="submit"):
@@ -197,3 +198,4 @@ def test_call_log_golden_is_what_the_reference_does_now():
     import gen_iio_golden as gg
     for name, (opts, dflt) in gg.CASES.items():
         assert gg.reference_log(opts, dflt) == GOLDEN_CALLS[name]["calls"], name
+    assert gg.reference_banner() == _GOLDEN_FILE["_banner_v"]["stderr"]

@@ -28,6 +28,16 @@ CASES = {
 }
 
 
+def reference_banner(extra=("-v",)):
+    """What the unmodified reference prints at start-up (mode, -v ionosphere/UTC block, gain, RINEX date, start time,
+    channel table: plutogpssim.c:2415-2418, 2487-2495, 2571-2574, 2634-2639), up to its first push."""
+    with tempfile.TemporaryDirectory() as wd:
+        env = dict(os.environ, FAKE_IIO_EPOCHS="1")
+        r = subprocess.run([REF, "-e", NAV, "-l", "30.286502,120.032669,100", "-s", "2600000"] + list(extra), env=env,
+                           check=True, capture_output=True, text=True, cwd=wd)
+        return r.stderr.split("Error pushing buf")[0].splitlines()
+
+
 def reference_log(options, default_ctx):
     with tempfile.TemporaryDirectory() as wd:
         log = os.path.join(wd, "calls.log")
@@ -44,9 +54,10 @@ def main():
         sys.exit("oracle/_ref/ref_verbatim missing: make -C oracle (needs the reference tree)")
     golden = {name: {"options": opts, "default_context": dflt, "calls": reference_log(opts, dflt)}
               for name, (opts, dflt) in CASES.items()}
+    golden["_banner_v"] = {"options": [["s", "2600000"]], "default_context": True, "calls": [], "stderr": reference_banner()}
     with open(OUT, "w") as f:
         json.dump(golden, f, indent=1)
-    print("wrote %s: %s" % (OUT, {k: len(v["calls"]) for k, v in golden.items()}))
+    print("wrote %s: %s" % (OUT, {k: len(v["calls"]) for k, v in golden.items() if not k.startswith("_")}))
 
 
 if __name__ == "__main__":
