@@ -9,18 +9,21 @@
 //                        fails loudly).  Every sink gets the stream in the same 300000-sample units, from
 //                        its own writer thread: batch k is drained while batch k+1 is fetched from the GPU.
 //
-// Differences from the reference, all deliberate: it stops after -d seconds (the reference runs until
-// a signal arrives); -o/-b/-n/-j/-r are new (the radio is one sink among others, not the only one); -f (FTP
+// Differences from the reference, all deliberate: it stops after -d seconds by default (-d 0 runs until
+// a signal arrives, as the reference does); -o/-b/-n/-j/-r are new (the radio is one sink among others, not the only one); -f (FTP
 // download) is refused (no network code here).
 #include <getopt.h>
+#include <signal.h>
 #include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <climits>
 #include <cstring>
 #include <ctime>
+#include <deque>
 #include <memory>
 #include <string>
 #include <vector>
@@ -32,6 +35,11 @@
 namespace {
 
 constexpr int kSamplesPerEpoch = 300000;  // NUM_SAMPLES = TX_SAMPLE_FREQ/10, independent of -s (plutogpssim.c:43-44)
+
+// SIGINT / SIGTERM end the run after the batch in flight; the sink is then closed in order, which for the radio means
+// TX LO off before the context goes away (the reference's handle_sig + exit path, plutogpssim.c:2014-2022, 2160-2178).
+volatile sig_atomic_t g_stop = 0;
+void on_signal(int) { g_stop = 1; }
 
 void usage() {
     fprintf(stderr,
@@ -51,7 +59,7 @@ void usage() {
             "  -U <uri>         ADALM-Pluto URI                                  (used with -r)\n"
             "  -N <network>     ADALM-Pluto network IP or hostname (default pluto.local)\n"
             "Options of this build:\n"
-            "  -d <seconds>     Duration [s] (default 1.0; the reference runs until interrupted)\n"
+            "  -d <seconds>     Duration [s] (default 1.0); 0 = until SIGINT/SIGTERM, as the reference runs\n"
             "  -o <file>        Write the int16 I/Q stream to <file> (\"-\" = stdout; default: discard)\n"
             "  -r               Transmit through an ADALM-Pluto (libiio), as the reference does\n"
             "  -b <epochs>      0.1 s epochs per GPU batch (default 128)\n"
@@ -132,7 +140,7 @@ int main(int argc, char** argv) {
     }
     if (nav.empty()) { fprintf(stderr, "ERROR: GPS ephemeris file is not specified.\n"); return 1; }
     if (!have_pos) fprintf(stderr, "note: no -l/-c/-u given; using the default location (the reference leaves it uninitialised)\n");
-    if (batch < 1 || duration <= 0.0) { usage(); return 1; }
+    if (batch < 1 || duration < 0.0) { usage(); return 1; }
     hc.nav_path = nav.c_str();
     hc.motion_path = motion.empty() ? nullptr : motion.c_str();
     fprintf(stderr, hc.pos_mode == GPSHOST_POS_MOTION ? "Using user motion mode.\n" : "Using static location mode.\n");
@@ -152,7 +160,12 @@ int main(int argc, char** argv) {
     int src = use_radio ? gpssink_open_radio(&sink, &radio) : out_path ? gpssink_open_file(&sink, out_path) : gpssink_open_null(&sink);
     if (src != GPSSINK_OK) { fprintf(stderr, "ERROR: %s\n", gpssink_last_error()); return 1; }
 
-    const long total_epochs = (long) (duration * 10.0 + 0.5);
+    const long total_epochs = duration == 0.0 ? LONG_MAX : (long) (duration * 10.0 + 0.5);
+    struct sigaction sa;
+    memset(&sa, 0, sizeof sa);
+    sa.sa_handler = on_signal;
+    sigaction(SIGINT, &sa, nullptr);
+    sigaction(SIGTERM, &sa, nullptr);
     if (batch > total_epochs) batch = (int) total_epochs;
     gpsiq_config gc;
     memset(&gc, 0, sizeof gc);
@@ -169,11 +182,11 @@ int main(int argc, char** argv) {
     if (!desc || !iq[0] || !iq[1]) { fprintf(stderr, "ERROR: pinned host allocation failed\n"); return 1; }
 
     const auto t_begin = std::chrono::steady_clock::now();
-    std::vector<int> sizes;
+    std::deque<int> sizes;   // epochs of the batches submitted to the GPU and not yet fetched
     long produced = 0;
     auto submit_next = [&]() -> bool {
         const int n = (int) std::min<long>(batch, total_epochs - produced);
-        if (n <= 0) return false;
+        if (n <= 0 || g_stop) return false;
         if (gpshost_next(sc, desc, n) != GPSHOST_OK) { fprintf(stderr, "ERROR: %s\n", gpshost_last_error()); exit(1); }
         if (gpsiq_submit(gq, desc, n) != GPSIQ_OK) { fprintf(stderr, "ERROR: %s\n", gpsiq_last_error(gq)); exit(1); }
         sizes.push_back(n);
@@ -184,13 +197,15 @@ int main(int argc, char** argv) {
     size_t k = 0;
     bool ok = true;
     int64_t ticket[2] = {0, 0};                // the sink's claim on each pinned buffer
-    while (k < sizes.size() && ok) {
+    while (!sizes.empty() && ok) {
         submit_next();                         // (no-op at the end of the stream)
+        const int n_now = sizes.front();
+        sizes.pop_front();
         int16_t* buf = iq[k & 1];
         if (ticket[k & 1] > 0 && gpssink_wait(sink, ticket[k & 1]) != GPSSINK_OK) { ok = false; break; }   // batch k-2 drained
         if (gpsiq_fetch(gq, buf) != GPSIQ_OK) { fprintf(stderr, "ERROR: %s\n", gpsiq_last_error(gq)); return 1; }
-        // sizes[k] push units (one 300000-sample buffer each, plutogpssim.c:2146-2158), written while batch k+1 is fetched
-        ticket[k & 1] = gpssink_submit(sink, buf, (size_t) sizes[k] * kSamplesPerEpoch);
+        // n_now push units (one 300000-sample buffer each, plutogpssim.c:2146-2158), written while batch k+1 is fetched
+        ticket[k & 1] = gpssink_submit(sink, buf, (size_t) n_now * kSamplesPerEpoch);
         if (ticket[k & 1] < 0) ok = false;
         if (verbose) fprintf(stderr, "\rTime into run = %4.1f", (double) std::min<long>((long) (k + 1) * batch, produced) / 10.0);
         k++;

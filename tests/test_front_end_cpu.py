@@ -37,6 +37,9 @@ def sim(tmp_path_factory):
     if not os.path.exists(FAKE_IIO):
         subprocess.run(["make", "-C", ol.ORACLE_DIR, "libfakeiio.so"], check=True, stdout=subprocess.DEVNULL)
 
+    def popen(args, env=None):
+        return subprocess.Popen([str(d / "gpsiq_sim")] + args, stderr=subprocess.PIPE, env=dict(os.environ, **(env or {})))
+
     def run(args, env=None, check=True, binary=False):
         r = subprocess.run([str(d / "gpsiq_sim")] + args, capture_output=True, env=dict(os.environ, **(env or {})))
         r.stderr = r.stderr.decode(errors="replace")
@@ -45,6 +48,7 @@ def sim(tmp_path_factory):
         if check:
             assert r.returncode == 0, r.stderr
         return r
+    run.popen = popen
     return run
 
 
@@ -134,6 +138,32 @@ def test_radio_sink_failures_end_the_run_with_an_error(sim, tmp_path):
     assert r.returncode == 1 and "Error pushing buf -1" in r.stderr
     assert log.read_text().splitlines()[-1] == "context_destroy"
     assert os.path.getsize(tmp_path / "p.bin") == 3 * N * 4
+
+
+def test_runs_until_interrupted_and_shuts_the_radio_down(sim, tmp_path):
+    """-d 0: like the reference, run until SIGINT/SIGTERM; then the batches in flight are delivered, the TX LO is
+    powered down and the context destroyed (plutogpssim.c:2014-2022, 2160-2178), exit status 0."""
+    import signal
+    import time
+    log, out = tmp_path / "calls.log", tmp_path / "pushed.bin"
+    env = {"GPSSINK_IIO_LIB": FAKE_IIO, "FAKE_IIO_LOG": str(log), "FAKE_IIO_OUT": str(out), "FAKE_IIO_EPOCHS": "1000000"}
+    p = sim.popen(["-e", NAV12, "-r", "-d", "0", "-b", "2"] + STATIC, env=env)
+    deadline = time.time() + 60
+    while time.time() < deadline and (not out.exists() or out.stat().st_size < 4 * N * 4):
+        time.sleep(0.05)
+    p.send_signal(signal.SIGINT)
+    err = p.communicate(timeout=60)[1].decode()
+    assert p.returncode == 0, err
+    calls = log.read_text().splitlines()
+    assert calls[-5:] == ["attr ad9361-phy/altvoltage1 powerdown = true", "buffer_destroy", "disable cf-ad9361-dds-core-lpc/voltage0",
+                          "disable cf-ad9361-dds-core-lpc/voltage1", "context_destroy"]
+    iq = np.fromfile(out, np.int16)
+    assert iq.size % (2 * N) == 0 and iq.size >= 4 * 2 * N
+    iq = iq.reshape(-1, N, 2)
+    want = ol.load_golden_meta("static12")["epoch_checksums"]
+    k = min(len(want), len(iq))
+    assert [int(checksum_host(iq[e])) for e in range(k)] == want[:k]
+    assert "%d buffers to the sink" % len(iq) in err
 
 
 def test_option_errors_match_the_reference_s_messages(sim, tmp_path):
