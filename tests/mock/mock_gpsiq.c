@@ -3,7 +3,7 @@
  * A stand-in for libgpsiq.so that lets the CPU test suite (no GPU in the build container) exercise the control
  * flow of the command-line front end gpsiq_sim -- option parsing, host orchestration, batching, the two pinned
  * buffers in flight, the hand-off to the sink's writer thread -- end to end against the reference's stream.
- * It implements only the seven entry points gpsiq_sim calls, on top of the parity oracle (oracle/gpsiq_oracle.c,
+ * It implements only the entry points gpsiq_sim and the literal drop-in build of the reference (oracle/dropin/) call, on top of the parity oracle (oracle/gpsiq_oracle.c,
  * compiled into this mock by tests/test_front_end_cpu.py), and lives in a scratch directory next to a COPY of the
  * gpsiq_sim binary (whose rpath is $ORIGIN); the real libgpsiq.so refuses to work without a GPU
  * (tests/test_capi_load.py::test_no_cpu_fallback_without_gpu) and stays the only library in the package directory. */
@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include "gpsiq.h"
+#include "gpsiq_desc.h"   /* the shipped header-only body of gpsiq_make_desc */
 
 int oracle_synth(const gpsiq_chan_desc *desc, int n_epochs, int nslots, int samples_per_epoch, int carrier_mode,
                  double *carr_state, int16_t *iq_out, double *carr_trace);
@@ -57,4 +58,18 @@ int gpsiq_fetch(gpsiq_ctx *c, int16_t *iq_out) {
     free(p->desc);
     free(p);
     return rc == 0 ? GPSIQ_OK : GPSIQ_ERR_ARG;
+}
+
+/* the two calls of the literal drop-in (oracle/dropin/dropin_loop.inc) */
+int gpsiq_make_desc(gpsiq_chan_desc *out, int carrier_mode, int prn, double f_carr, double f_code, double delt,
+                    double carr_phase, double code_phase, const uint64_t *dwrd60, int iword, int ibit, int icode,
+                    double gain, int carr_phase_is_new) {
+    return gpsiq_make_desc_inline(out, carrier_mode, prn, f_carr, f_code, delt, carr_phase, code_phase, dwrd60, iword, ibit,
+                                  icode, gain, carr_phase_is_new);
+}
+
+int gpsiq_synth(gpsiq_ctx *c, const gpsiq_chan_desc *desc, int n_epochs, int16_t *iq_out) {
+    if (n_epochs < 1 || n_epochs > c->cfg.max_epochs || !iq_out) return GPSIQ_ERR_ARG;
+    return oracle_synth(desc, n_epochs, c->cfg.max_chan, c->cfg.samples_per_epoch, c->cfg.carrier_mode, c->carr, iq_out, NULL) == 0
+               ? GPSIQ_OK : GPSIQ_ERR_ARG;
 }
