@@ -221,3 +221,60 @@ def test_corrupted_navigation_files_fail_with_an_error_not_a_crash(tmp_path):
             i = next(k for k in range(_first_record(lines), len(lines)) if lines[k].startswith("G"))   # first GPS record
             lines[i] = lines[i][:9] + " 0" + lines[i][11:]
         hostapi.Scenario(_mutated_nav(tmp_path, NAV12_V3, [month0_v3], "bad3.nav"), llh=LLH, sample_rate=2600000, rinex3=True)
+
+
+# ---- independent restatement of the IS-GPS-200 parity equations (20.3.5.2, table 20-XIV) -------------------
+_PARITY_TERMS = {          # D25..D30: (which previous-word bit, data bits d1..d24 that enter)
+    25: (29, [1, 2, 3, 5, 6, 10, 11, 12, 13, 14, 17, 18, 20, 23]),
+    26: (30, [2, 3, 4, 6, 7, 11, 12, 13, 14, 15, 18, 19, 21, 24]),
+    27: (29, [1, 3, 4, 5, 7, 8, 12, 13, 14, 15, 16, 19, 20, 22]),
+    28: (30, [2, 4, 5, 6, 8, 9, 13, 14, 15, 16, 17, 20, 21, 23]),
+    29: (30, [1, 3, 5, 6, 7, 9, 10, 14, 15, 16, 17, 18, 21, 22, 24]),
+    30: (29, [3, 5, 6, 8, 9, 10, 11, 13, 15, 19, 22, 23, 24]),
+}
+
+
+def _spec_word(d, p29, p30):
+    """d: list of 24 source data bits d1..d24; p29/p30: D29*, D30* of the previous word -> the 30 transmitted bits."""
+    out = [b ^ p30 for b in d]
+    for k in range(25, 31):
+        prev, terms = _PARITY_TERMS[k]
+        v = p29 if prev == 29 else p30
+        for t in terms:
+            v ^= d[t - 1]
+        out.append(v)
+    return out
+
+
+def test_parity_words_satisfy_the_is_gps_200_equations():
+    """gpshost_parity (the reference's computeChecksum, plutogpssim.c:291-372) against the parity equations written
+    out from the interface specification: 2000 random words, both with plain data (nib = 0) and with the two
+    non-information bits solved so that D29 = D30 = 0 (nib = 1: words 2 and 10 of every subframe)."""
+    rng = np.random.default_rng(2024)
+    for _ in range(2000):
+        src = int(rng.integers(0, 1 << 32)) & 0xFFFFFFC0
+        p29, p30 = (src >> 31) & 1, (src >> 30) & 1
+        d = [(src >> (29 - i)) & 1 for i in range(24)]
+        got = hostapi.parity(src, 0)
+        bits = [(got >> (29 - i)) & 1 for i in range(30)]
+        assert bits == _spec_word(d, p29, p30), hex(src)
+        got = hostapi.parity(src, 1)
+        bits = [(got >> (29 - i)) & 1 for i in range(30)]
+        assert bits[28] == 0 and bits[29] == 0                      # D29 = D30 = 0
+        d_solved = [b ^ p30 for b in bits[:24]]                      # the source bits the word now carries
+        assert d_solved[:22] == d[:22]                               # only d23, d24 were touched
+        assert bits == _spec_word(d_solved, p29, p30), hex(src)
+
+
+def test_time_and_position_round_trips():
+    rng = np.random.default_rng(7)
+    for _ in range(300):
+        y, m, d = int(rng.integers(1981, 2099)), int(rng.integers(1, 13)), int(rng.integers(1, 29))
+        hh, mm, ss = int(rng.integers(0, 24)), int(rng.integers(0, 60)), float(rng.integers(0, 60))
+        import datetime
+        week, sow = hostapi.date2gps(y, m, d, hh, mm, ss)
+        delta = datetime.datetime(y, m, d, hh, mm, int(ss)) - datetime.datetime(1980, 1, 6)
+        assert week * 604800 + sow == delta.total_seconds()          # no leap seconds in GPS time
+        lat, lon, h = float(rng.uniform(-89, 89)), float(rng.uniform(-179, 179)), float(rng.uniform(-100, 20000))
+        back = hostapi.xyz2llh(hostapi.llh2xyz(lat, lon, h))
+        assert abs(back[0] * 57.2957795131 - lat) < 1e-7 and abs(back[1] * 57.2957795131 - lon) < 1e-7 and abs(back[2] - h) < 1e-2
