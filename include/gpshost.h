@@ -64,6 +64,12 @@ void gpshost_close(gpshost_scenario *s);
 /* Descriptors of the next n_epochs 0.1 s epochs: desc[n_epochs][max_chan].  A slot whose satellite was
  * (re)allocated carries GPSIQ_FLAG_RESET_CARRIER and the initial carrier phase of plutogpssim.c:1964. */
 int gpshost_next(gpshost_scenario *s, gpsiq_chan_desc *desc, int n_epochs);
+/* Move n_epochs ahead without producing descriptors: gpshost_skip(n) + gpshost_next(m) yields the same descriptors as
+ * the last m of gpshost_next(n + m), at the cost of one epoch per 30 s refresh interval instead of every epoch -- how
+ * the owner of a later time slice reaches its first epoch.  One difference, deliberate: a
+ * channel allocated inside the skipped span does not carry GPSIQ_FLAG_RESET_CARRIER afterwards (its carrier has been
+ * running; the phase at a slice boundary is handed over by the previous slice's owner, gpsiq_set_carrier). */
+int gpshost_skip(gpshost_scenario *s, int n_epochs);
 /* What the reference prints at start-up (plutogpssim.c:2571-2574, 2634-2639): start time and channel table. */
 int gpshost_describe(gpshost_scenario *s, char *buf, int buflen);
 /* What the reference's -v adds (plutogpssim.c:2487-2495): the ionosphere / UTC parameters of the file header, four

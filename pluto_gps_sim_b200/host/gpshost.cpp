@@ -827,6 +827,12 @@ struct gpshost_scenario {
             if (rc != GPSIQ_OK) { g_error = "descriptor out of range"; return GPSHOST_ERR_ARG; }
             ch.fresh = false;
         }
+        end_of_epoch();
+        return GPSHOST_OK;
+    }
+
+    // what follows the sample loop: the 30 s refresh when due, then time and motion index move on (plutogpssim.c:2761-2805)
+    void end_of_epoch() {
         // every 30 s: next frame of NAV words, ephemeris roll-over, re-allocation
         const int igrx = (int) (grx.sec * 10.0 + 0.5);
         if (igrx % 300 == 0) {
@@ -846,11 +852,50 @@ struct gpshost_scenario {
         }
         grx = tow_add(grx, 0.1);
         if (++imotion >= nmotion) imotion = 0;
+    }
+
+    // Move n_epochs ahead without producing descriptors (the owner of a later time slice reaches its
+    // first epoch without doing the earlier slices' work).  Between two refreshes the only state an epoch leaves behind
+    // is each channel's previous pseudorange (code_setup's rho0), so only the LAST epoch of every refresh-to-refresh
+    // segment is evaluated; the refresh passes themselves (NAV frame, ephemeris roll-over, re-allocation) are replayed.
+    // A channel allocated inside the skipped span loses its RESET_CARRIER flag: its phase has been running since, and
+    // the carrier state at a slice boundary comes from the previous slice's owner, not from the host.
+    int skip(int n_epochs) {
+        int left = n_epochs;
+        while (left > 0) {
+            // epochs up to and including the next refresh epoch (or all that is left)
+            int seg = 0;
+            Tow g = grx;
+            Tow last = grx;
+            int im = imotion, im_last = imotion;
+            while (seg < left) {
+                last = g;
+                im_last = im;
+                seg++;
+                const bool refresh = ((int) (g.sec * 10.0 + 0.5)) % 300 == 0;
+                g = tow_add(g, 0.1);
+                if (++im >= nmotion) im = 0;
+                if (refresh) break;
+            }
+            grx = last;          // stand on the segment's last epoch: its ranges become rho0, its refresh (if due) runs
+            imotion = im_last;
+            const std::vector<Eph>& eph = sets[(size_t) iset];
+            for (Slot& ch : chan) {
+                if (ch.prn <= 0) continue;
+                const Sight rho = line_of_sight(eph[(size_t) ch.prn - 1], iono, grx, position());
+                ch.az = rho.az;
+                ch.el = rho.el;
+                code_setup(ch, rho, 0.1);
+                ch.fresh = false;
+            }
+            end_of_epoch();
+            left -= seg;
+        }
         return GPSHOST_OK;
     }
 
     // n_epochs epochs, multi-threaded over epochs.  The pseudorange of a channel at an epoch
-    // (satellite state, light time, Earth rotation, ionosphere: ~95 % of the host work) depends only on the epoch's time,
+    // (satellite state, light time, Earth rotation, ionosphere: most of the host work) depends only on the epoch's time,
     // the receiver position and the ephemeris -- not on the previous epoch.  Everything that IS sequential stays
     // sequential: the millisecond-rounded time steps, the range differences (code_setup), the NAV word counters and the
     // 30 s refresh.  So the stream is cut at the refresh epochs (the channel table and the ephemeris set are constant in
@@ -932,6 +977,11 @@ void gpshost_close(gpshost_scenario* s) { delete s; }
 int gpshost_next(gpshost_scenario* s, gpsiq_chan_desc* desc, int n_epochs) {
     if (!s || !desc || n_epochs < 0) return GPSHOST_ERR_ARG;
     return s->run(desc, n_epochs);
+}
+
+int gpshost_skip(gpshost_scenario* s, int n_epochs) {
+    if (!s || n_epochs < 0) return GPSHOST_ERR_ARG;
+    return s->skip(n_epochs);
 }
 
 int gpshost_time(gpshost_scenario* s, int* week, double* sec) {

@@ -31,6 +31,7 @@ SYMBOLS = {
     "gpshost_open": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(HostConfig)]),
     "gpshost_close": (None, [C.c_void_p]),
     "gpshost_next": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "gpshost_skip": (C.c_int, [C.c_void_p, C.c_int]),
     "gpshost_describe": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "gpshost_describe_iono": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "gpshost_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
@@ -116,6 +117,12 @@ class Scenario:
         if rc != 0:
             raise HostError(rc)
         return d
+
+    def skip(self, n_epochs):
+        """Advance n_epochs without producing descriptors (one evaluated epoch per 30 s refresh interval)."""
+        rc = lib.gpshost_skip(self._h, int(n_epochs))
+        if rc != 0:
+            raise HostError(rc)
 
     def describe(self):
         buf = C.create_string_buffer(8192)

@@ -278,3 +278,47 @@ def test_time_and_position_round_trips():
         lat, lon, h = float(rng.uniform(-89, 89)), float(rng.uniform(-179, 179)), float(rng.uniform(-100, 20000))
         back = hostapi.xyz2llh(hostapi.llh2xyz(lat, lon, h))
         assert abs(back[0] * 57.2957795131 - lat) < 1e-7 and abs(back[1] * 57.2957795131 - lon) < 1e-7 and abs(back[2] - h) < 1e-2
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("static12", dict(nav=NAV12, llh=LLH, sample_rate=2600000)),
+    ("circle12", dict(nav=NAV12, motion=CIRCLE, sample_rate=2600000)),
+    ("allsky32", dict(nav=NAV32, llh=LLH, sample_rate=10000000, max_chan=32)),
+    ("ephemeris-rollover", dict(nav=NAV12, llh=LLH, sample_rate=2600000, start=(2014, 12, 20, 0, 59, 40.0))),   # next set at 01:00:00
+])
+def test_skip_then_next_equals_the_tail_of_one_long_run(name, kw):
+    """gpshost_skip (how the owner of a later time slice reaches its first epoch) evaluates one epoch
+    per 30 s refresh interval; what follows must be bit-identical to generating everything -- at every kind of cut:
+    inside an interval, on the refresh epoch, right after it, several intervals on, and in two hops."""
+    if "motion" in kw and not os.path.exists(CIRCLE):
+        pytest.skip("oracle/_ref/circle.csv not present")
+    with hostapi.Scenario(**kw) as s:
+        full = s.next(1300)
+    for n in (0, 1, 7, 298, 299, 300, 301, 599, 600, 911, 1200):
+        with hostapi.Scenario(**kw) as s:
+            s.skip(n)
+            t_skip = s.time
+            got = s.next(70)
+        assert got.tobytes() == full[n:n + 70].tobytes(), (name, n)
+        with hostapi.Scenario(**kw) as s:
+            s.next(n)
+            assert s.time == t_skip
+    with hostapi.Scenario(**kw) as s:     # hops and interleaved generation
+        s.skip(250)
+        a = s.next(100)
+        s.skip(333)
+        b = s.next(50)
+    assert a.tobytes() == full[250:350].tobytes() and b.tobytes() == full[683:733].tobytes()
+
+
+def test_skip_is_cheap():
+    import time
+    with hostapi.Scenario(NAV12, llh=LLH, sample_rate=2600000, threads=1) as s:
+        t = time.perf_counter()
+        s.skip(30000)                      # 50 minutes of signal: 100 evaluated epochs + 100 refresh passes
+        dt_skip = time.perf_counter() - t
+    with hostapi.Scenario(NAV12, llh=LLH, sample_rate=2600000, threads=1) as s:
+        t = time.perf_counter()
+        s.next(30000)
+        dt_full = time.perf_counter() - t
+    assert dt_skip * 10 < dt_full, (dt_skip, dt_full)
