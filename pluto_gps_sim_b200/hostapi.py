@@ -164,3 +164,32 @@ def xyz2llh(xyz):
     o = np.zeros(3)
     lib.gpshost_xyz2llh(a.ctypes.data, o.ctypes.data)
     return o
+
+
+class SliceFeeder:
+    """Host side of multi-GPU time slicing (timeslice.py): the descriptors of rank `rank`'s
+    slices of ONE scenario.  Step k of a `world`-rank job covers epochs [k*world*E, (k+1)*world*E); this rank owns
+    [(k*world + rank)*E, +E).  The other ranks' epochs are skipped (gpshost_skip: one evaluated epoch per 30 s refresh
+    interval), so every rank pays for its own slices only and the slices of all ranks, put back in stream order, are
+    byte for byte the descriptors of a single run."""
+
+    def __init__(self, rank, world, epochs_per_slice, **scenario_kw):
+        if not (0 <= rank < world) or epochs_per_slice < 1:
+            raise ValueError("rank/world/epochs_per_slice")
+        self.rank, self.world, self.E = int(rank), int(world), int(epochs_per_slice)
+        self.scenario = Scenario(**scenario_kw)
+        self.scenario.skip(self.rank * self.E)
+
+    def next_slice(self):
+        d = self.scenario.next(self.E)
+        self.scenario.skip((self.world - 1) * self.E)
+        return d
+
+    def close(self):
+        self.scenario.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

@@ -322,3 +322,22 @@ def test_skip_is_cheap():
         s.next(30000)
         dt_full = time.perf_counter() - t
     assert dt_skip * 10 < dt_full, (dt_skip, dt_full)
+
+
+@pytest.mark.parametrize("world,E", [(2, 128), (3, 100), (8, 37)])
+def test_slice_feeders_of_all_ranks_reassemble_the_single_stream(world, E):
+    """Every rank generates only its own time slices (the others are skipped): put back in stream order they are the
+    descriptors of one uninterrupted run, RESET_CARRIER flags included -- each (re)allocation is announced exactly
+    once, by the rank whose slice holds the first epoch after it."""
+    # static scenario started at 00:17:10: PRN rises and is allocated by the refresh at 00:18:00 -> RESET flag on epoch 500,
+    # which is inside a slice for (2, 128) and (8, 37) and the FIRST epoch of a slice -- right after a skipped span -- for (3, 100)
+    kw = dict(nav=NAV12, llh=LLH, sample_rate=2600000, start=(2014, 12, 20, 0, 17, 10.0))
+    steps = 1300 // (world * E)
+    with hostapi.Scenario(**kw) as s:
+        full = s.next(steps * world * E)
+    assert sorted(set(np.nonzero(full["flags"] & 1)[0].tolist())) == [0, 500]
+    feeders = [hostapi.SliceFeeder(r, world, E, **kw) for r in range(world)]
+    got = np.concatenate([feeders[r].next_slice() for _ in range(steps) for r in range(world)])
+    assert got.tobytes() == full.tobytes()
+    for f in feeders:
+        f.close()
