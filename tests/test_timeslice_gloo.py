@@ -23,8 +23,8 @@ STEPS = 3
 class OracleEngine:
     """Same interface as timeslice.GpuSliceEngine, arithmetic by the oracle."""
 
-    def __init__(self, max_chan, rank=0, world=1):
-        self.rank, self.world = rank, world
+    def __init__(self, max_chan, rank=0, world=1, n=N):
+        self.rank, self.world, self.n = rank, world, n
         self.phase = torch.zeros(max_chan, dtype=torch.float64)
         self.adv = torch.zeros(2 * max_chan, dtype=torch.float64)
         self.state = np.zeros(max_chan)
@@ -33,7 +33,7 @@ class OracleEngine:
 
     def prepare(self, desc, n_epochs):        # closed-form advance of the slice (estimates only)
         d = desc[:n_epochs]
-        self.adv[: d.shape[1]] = torch.from_numpy(np.mod((d["carr_step"] * N).sum(axis=0), 1.0))
+        self.adv[: d.shape[1]] = torch.from_numpy(np.mod((d["carr_step"] * self.n).sum(axis=0), 1.0))
         self.adv[d.shape[1]:] = torch.from_numpy(((d["flags"] & 1) != 0).any(axis=0).astype(np.float64))
 
     def estimate_fold(self, adv):
@@ -64,7 +64,7 @@ class OracleEngine:
         self.state[:] = buf[1:].numpy()
 
     def chain(self, desc, n_epochs):          # advances the carrier state (and keeps the samples for render)
-        self.pending, _ = ol.oracle_synth(desc[:n_epochs], N, carr_state=self.state)
+        self.pending, _ = ol.oracle_synth(desc[:n_epochs], self.n, carr_state=self.state)
 
     def render(self, desc, n_epochs, out):
         out[...] = self.pending
@@ -115,3 +115,40 @@ def test_time_slices_equal_sequential_stream(tmp_path, WORLD, handoff):
     assert np.array_equal(got, want)
     # rank 0 ends up holding the phases after the very last slice (ready for the next step)
     assert np.array_equal(np.load(tmp_path / "final_phase.npy"), st)
+
+
+# ---- the whole host side, per rank, from the navigation file ---------------------------------------------------
+def _nav_worker(rank, WORLD, port, outdir, slice_epochs, steps):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    from pluto_gps_sim_b200 import hostapi
+    from pluto_gps_sim_b200.timeslice import TimeSliceRunner
+
+    nav = os.path.join(ol.GOLDEN, "brdc3540_synth.14n.gz")
+    feeder = hostapi.SliceFeeder(rank, WORLD, slice_epochs, nav=nav, llh=(30.286502, 120.032669, 100), sample_rate=2600000)
+    eng = OracleEngine(12, rank, WORLD, n=300000)
+    runner = TimeSliceRunner(eng, rank, WORLD, handoff="mailbox")
+    outs = []
+    for _ in range(steps):
+        out = np.zeros((slice_epochs, 300000, 2), np.int16)
+        runner.step(feeder.next_slice(), slice_epochs, out)      # this rank's own epochs only; the others' are skipped
+        outs.append(out)
+    runner.finish()
+    np.save(os.path.join(outdir, "rank%d.npy" % rank), np.stack(outs))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("WORLD,slice_epochs,steps", [(2, 5, 1), (2, 1, 5), (5, 2, 1)])
+def test_ranks_fed_from_the_navigation_file_reproduce_the_reference_stream(tmp_path, WORLD, slice_epochs, steps):
+    """Navigation file in, every rank computing ONLY its own slices' descriptors (hostapi.SliceFeeder), carrier
+    phases handed from slice to slice: the reassembled 10 epochs are the reference's own bytes (golden SHA-256 of
+    BASELINE config[0]).  The device is the oracle here; tests/test_gpu_timeslice.py runs the same runner on GPUs."""
+    import hashlib
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_nav_worker, args=(WORLD, port, str(tmp_path), slice_epochs, steps), nprocs=WORLD, join=True)
+    parts = [np.load(tmp_path / ("rank%d.npy" % r)) for r in range(WORLD)]
+    got = np.concatenate([parts[r][s] for s in range(steps) for r in range(WORLD)])
+    assert got.shape[0] == 10
+    assert hashlib.sha256(got.tobytes()).hexdigest() == ol.load_golden_meta("static12")["iq_sha256"]
