@@ -191,12 +191,16 @@ struct RadioBackend : Backend {
         if (!phy) return fail(GPSSINK_ERR_DEVICE, "ad9361-phy not found in the IIO context");
         // transmit chain of the AD9361 (plutogpssim.c:2105-2110), then RX LO off and TX LO frequency (2112-2118)
         void* chain = phy_channel("voltage0");
+        void* rx_lo = phy_channel("altvoltage0");
+        void* tx_lo = phy_channel("altvoltage1");
+        if (!chain || !rx_lo || !tx_lo)  // (the reference would hand libiio a null channel here)
+            return fail(GPSSINK_ERR_DEVICE, "ad9361-phy lacks the %s channel", !chain ? "voltage0" : !rx_lo ? "altvoltage0" : "altvoltage1");
         api.channel_attr_write(chain, "rf_port_select", cfg.rfport);
         api.channel_attr_write_longlong(chain, "rf_bandwidth", cfg.bw_hz);
         api.channel_attr_write_longlong(chain, "sampling_frequency", cfg.fs_hz);
         api.channel_attr_write_double(chain, "hardwaregain", cfg.gain_db);
-        api.channel_attr_write_bool(phy_channel("altvoltage0"), "powerdown", true);
-        api.channel_attr_write_longlong(phy_channel("altvoltage1"), "frequency", cfg.lo_hz);
+        api.channel_attr_write_bool(rx_lo, "powerdown", true);
+        api.channel_attr_write_longlong(tx_lo, "frequency", cfg.lo_hz);
 
         // streaming channels of the DAC core: I then Q, with the altvoltage names as fall-back (plutogpssim.c:2120-2129)
         static const char* const names[2][2] = {{"voltage0", "altvoltage0"}, {"voltage1", "altvoltage1"}};
@@ -216,8 +220,7 @@ struct RadioBackend : Backend {
 
         buffer = api.device_create_buffer(tx, (size_t) cfg.pairs_per_push, false);
         if (!buffer) return fail(GPSSINK_ERR_DEVICE, "Could not create TX buffer.");
-        api.channel_attr_write_bool(api.device_find_channel(api.context_find_device(ctx, "ad9361-phy"), "altvoltage1", true),
-                                    "powerdown", false);  // TX LO on (plutogpssim.c:2139-2141)
+        api.channel_attr_write_bool(tx_lo, "powerdown", false);  // TX LO on (plutogpssim.c:2139-2141)
         buffer_mem = (char*) api.buffer_start(buffer);
         return GPSSINK_OK;
     }
@@ -237,9 +240,11 @@ struct RadioBackend : Backend {
     int finish() override {  // plutogpssim.c:2160-2178
         if (closed) return GPSSINK_OK;
         closed = true;
-        if (ctx)
-            api.channel_attr_write_bool(api.device_find_channel(api.context_find_device(ctx, "ad9361-phy"), "altvoltage1", true),
-                                        "powerdown", true);  // TX LO off
+        if (ctx) {  // TX LO off -- also after a failed start, like the reference, but never through a null handle
+            void* dev = api.context_find_device(ctx, "ad9361-phy");
+            void* lo = dev ? api.device_find_channel(dev, "altvoltage1", true) : nullptr;
+            if (lo) api.channel_attr_write_bool(lo, "powerdown", true);
+        }
         if (buffer) api.buffer_destroy(buffer);
         if (tx_i) api.channel_disable(tx_i);
         if (tx_q) api.channel_disable(tx_q);
