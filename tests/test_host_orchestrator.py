@@ -341,3 +341,23 @@ def test_slice_feeders_of_all_ranks_reassemble_the_single_stream(world, E):
     assert got.tobytes() == full.tobytes()
     for f in feeders:
         f.close()
+
+
+@pytest.mark.parametrize("args,fixture", [
+    (["--kind", "gps"], "brdc3540_synth.14n.gz"),
+    (["--kind", "allsky"], "allsky32_synth.14n.gz"),
+    (["--kind", "gps", "--rinex3"], "brdc3540_synth.14p.gz"),
+])
+def test_fixture_generator_reproduces_the_committed_navigation_files(tmp_path, args, fixture):
+    """tools/gen_rinex_fixture.py (the synthetic-constellation generator) is deterministic:
+    it rewrites the committed fixtures byte for byte, so every golden's `nav_fixture_sha256` can be re-derived."""
+    import hashlib
+    import subprocess
+    import sys
+    out = tmp_path / fixture
+    subprocess.run([sys.executable, os.path.join(ol.REPO, "tools", "gen_rinex_fixture.py")] + args + ["-o", str(out)],
+                   check=True, capture_output=True)
+    want = open(os.path.join(ol.GOLDEN, fixture), "rb").read()
+    assert out.read_bytes() == want
+    if fixture == "brdc3540_synth.14n.gz":
+        assert hashlib.sha256(want).hexdigest() == ol.load_golden_meta("static12")["nav_fixture_sha256"]
