@@ -73,7 +73,7 @@ struct Slot {  // one channel (the part of channel_t the host owns)
     bool fresh = false;  // (re)allocated since the last emitted epoch
 };
 
-std::string g_error;
+thread_local std::string g_error;  // per calling thread: scenarios may be driven from different threads
 
 // ---- time (plutogpssim.c:250-290, 838-866) ------------------------------------------------
 bool cal_ok(const Cal& t) {  // what cal_to_tow can take (a malformed record line must not index the month table)
