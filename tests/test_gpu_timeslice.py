@@ -18,7 +18,10 @@ E = 16
 STEPS = 9
 
 
-def _worker(rank, world, port, outdir, deferred=False, handoff="nccl"):
+CIRCLE = os.path.join(ol.ORACLE_DIR, "_ref", "circle.csv")
+
+
+def _worker(rank, world, port, outdir, deferred=False, handoff="nccl", feed="golden"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -26,6 +29,11 @@ def _worker(rank, world, port, outdir, deferred=False, handoff="nccl"):
     from pluto_gps_sim_b200.timeslice import GpuSliceEngine, TimeSliceRunner
 
     desc = ol.load_golden_desc("circle12")
+    feeder = None
+    if feed == "navfile":   # every rank computes ONLY its own slices' descriptors from the navigation file (gpshost_skip)
+        from pluto_gps_sim_b200 import hostapi
+        feeder = hostapi.SliceFeeder(rank, world, E, nav=os.path.join(ol.GOLDEN, "brdc3540_synth.14n.gz"), motion=CIRCLE,
+                                     sample_rate=2600000)
     synth = Synthesizer(max_chan=12, max_epochs=E, device=rank)
     engine = GpuSliceEngine(synth)
     if handoff == "mailbox":
@@ -35,7 +43,8 @@ def _worker(rank, world, port, outdir, deferred=False, handoff="nccl"):
     sums = []
     for s in range(STEPS):
         first = (s * world + rank) * E
-        d = torch.from_numpy(desc[first:first + E].copy().view(np.uint8).reshape(-1)).cuda()
+        mine = feeder.next_slice() if feeder else desc[first:first + E].copy()
+        d = torch.from_numpy(mine.view(np.uint8).reshape(-1)).cuda()
         runner.step(d, E, outs[s & 1])
         torch.cuda.synchronize()
         if not deferred:
@@ -66,3 +75,18 @@ def test_two_gpu_time_slices_match_reference(tmp_path, deferred, handoff):
     # the estimates handed around the ring are good enough that the serial fallback stays rare
     fb = sum(int(np.load(tmp_path / ("fb%d.npy" % r))[0]) for r in range(world))
     assert fb < world * STEPS * E * 12 // 10, fb
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2 or not os.path.exists(CIRCLE), reason="needs 2 GPUs and oracle/_ref/circle.csv")
+def test_two_gpu_time_slices_fed_from_the_navigation_file(tmp_path):
+    """As above, but nothing is precomputed: each rank runs the host orchestrator for its own slices only
+    (hostapi.SliceFeeder), renders them, and the stream is the reference's (per-epoch checksums of its 310-epoch run)."""
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(world, port, str(tmp_path), False, "mailbox", "navfile"), nprocs=world, join=True)
+    meta = ol.load_golden_meta("circle12")
+    parts = [np.load(tmp_path / ("sums%d.npy" % r)) for r in range(world)]
+    got = np.concatenate([parts[r][s] for s in range(STEPS) for r in range(world)])
+    assert [int(x) for x in got] == meta["epoch_checksums"][: world * STEPS * E]
