@@ -175,3 +175,21 @@ def test_option_errors_match_the_reference_s_messages(sim, tmp_path):
     r = sim(["-e", NAV12, "-o", str(tmp_path / "no" / "dir" / "x.bin")] + STATIC, check=False)
     assert r.returncode == 1 and "cannot open" in r.stderr
     assert sim(["-e", NAV12, "-f"] + STATIC, check=False).returncode == 1
+
+
+def test_plain_c_pipeline_example_compiles_and_reproduces_the_stream(tmp_path):
+    """tests/native/pipeline_example.c = the C usage INTEGRATION.md documents, as a complete C11 program: the three
+    headers are plain C, the three-library pipeline with two buffers in flight gives the reference's bytes."""
+    d = tmp_path
+    subprocess.run(["gcc", "-std=c11", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(ol.REPO, "include"),
+                    "-o", str(d / "libgpsiq.so"), os.path.join(ol.REPO, "tests", "mock", "mock_gpsiq.c"),
+                    os.path.join(ol.ORACLE_DIR, "gpsiq_oracle.c"), "-lm"], check=True)
+    shutil.copy(hostapi.LIB_PATH, d / "libgpshost.so")
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-pedantic", "-O2", "-I", os.path.join(ol.REPO, "include"), "-o", str(d / "pipeline_example"),
+                    os.path.join(ol.REPO, "tests", "native", "pipeline_example.c"), "-L" + str(d), "-lgpshost", "-lgpsiq",
+                    "-Wl,-rpath,$ORIGIN"], check=True)
+    for batch in ("3", "4", "16"):
+        out = d / ("iq%s.bin" % batch)
+        r = subprocess.run([str(d / "pipeline_example"), NAV12, str(out), "10", batch], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert hashlib.sha256(out.read_bytes()).hexdigest() == ol.load_golden_meta("static12")["iq_sha256"]
