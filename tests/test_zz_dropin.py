@@ -84,3 +84,21 @@ def test_reference_host_side_drives_the_b200_kernels_gpu(tmp_path):
     assert hashlib.sha256(iq.tobytes()).hexdigest() == ol.load_golden_meta("static12")["iq_sha256"], err
     iq, err = run_dropin(tmp_path, ["-u", CIRCLE, "-s", "2600000"], 50)
     assert [int(checksum_host(iq[e])) for e in range(50)] == ol.load_golden_meta("circle12")["epoch_checksums"][:50], err
+
+
+@pytest.mark.gpu
+def test_plain_c_pipeline_example_on_the_gpu(tmp_path):
+    """tests/native/pipeline_example.c (the C usage INTEGRATION.md documents) linked against the real libraries:
+    navigation file in, the reference's bytes out, at three batch sizes."""
+    from pluto_gps_sim_b200 import capi, hostapi
+    exe = tmp_path / "pipeline_example"
+    libdir = os.path.dirname(capi.LIB_PATH)
+    subprocess.run(["gcc", "-std=c11", "-O2", "-I", os.path.join(ol.REPO, "include"), "-o", str(exe),
+                    os.path.join(ol.REPO, "tests", "native", "pipeline_example.c"), "-L" + libdir, "-lgpshost", "-lgpsiq",
+                    "-Wl,-rpath," + libdir], check=True)
+    assert os.path.dirname(hostapi.LIB_PATH) == libdir
+    for batch in ("3", "4", "16"):
+        out = tmp_path / ("iq%s.bin" % batch)
+        r = subprocess.run([str(exe), NAV12, str(out), "10", batch], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        assert hashlib.sha256(out.read_bytes()).hexdigest() == ol.load_golden_meta("static12")["iq_sha256"]
