@@ -655,6 +655,7 @@ struct gpshost_scenario {
     std::vector<std::vector<Eph>> sets;
     int nsets = 0, iset = -1;
     Klob iono;
+    Klob iono_as_read;  // header values before a -T overwrite touches tot / wnt: what the reference's -v block shows
     std::string rinex_date;
     std::vector<double> motion;
     int nmotion = 0, imotion = 0;
@@ -742,6 +743,7 @@ struct gpshost_scenario {
                                 : load_rinex2(cfg.nav_path, sets, iono, rinex_date);
         if (nsets < 0) { g_error = cfg.rinex3 ? "cannot read RINEX-3 navigation file" : "cannot read RINEX-2 navigation file"; return GPSHOST_ERR_NAVFILE; }
         if (nsets == 0) { g_error = "no ephemeris available"; return GPSHOST_ERR_NOEPH; }
+        iono_as_read = iono;
 
         // span of the file, start time, optional TOC/TOE overwrite (plutogpssim.c:2497-2574)
         Tow gmin, gmax;
@@ -1012,7 +1014,7 @@ int gpshost_describe(gpshost_scenario* s, char* buf, int buflen) {
 int gpshost_describe_iono(gpshost_scenario* s, char* buf, int buflen) {
     if (!s || !buf || buflen < 1) return GPSHOST_ERR_ARG;
     buf[0] = 0;
-    const Klob& k = s->iono;
+    const Klob& k = s->iono_as_read;
     if (k.valid)  // the reference prints the block only for a complete header (plutogpssim.c:2487-2495)
         snprintf(buf, (size_t) buflen, "  %12.3e %12.3e %12.3e %12.3e\n  %12.3e %12.3e %12.3e %12.3e\n   %19.11e %19.11e  %9d %9d\n%6d\n",
                  k.a[0], k.a[1], k.a[2], k.a[3], k.b[0], k.b[1], k.b[2], k.b[3], k.A0, k.A1, k.tot, k.wnt, k.dtls);

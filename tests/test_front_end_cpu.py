@@ -127,6 +127,24 @@ def test_start_up_text_is_the_reference_s(sim, tmp_path):
     assert got[:len(want)] == want, "\n".join(got)
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(ol.ORACLE_DIR, "_ref", "ref_verbatim")), reason="needs the compiled reference (oracle/_ref)")
+@pytest.mark.parametrize("extra", [
+    ["-u", "@circle", "-s", "2600000", "-t", "2014/12/20,00:30:00"],
+    ["-c", "-2758918.64,4772301.12,3197889.44", "-s", "3000000", "-i", "-A", "-12.5"],
+    ["-l", "30.286502,120.032669,100", "-s", "2600000", "-T", "x", "-t", "2021/06/07,08:09:10"],
+])
+def test_start_up_text_equals_a_live_run_of_the_reference(sim, tmp_path, extra):
+    """Other option combinations, against the reference binary run here: mode line, -v block, gain, RINEX date, start
+    time (incl. -T overwrite) and the channel table (azimuth, elevation, range, ionospheric delay per PRN)."""
+    extra = [os.path.join(ol.ORACLE_DIR, "_ref", "circle.csv") if a == "@circle" else a for a in extra]
+    ref = subprocess.run([os.path.join(ol.ORACLE_DIR, "_ref", "ref_verbatim"), "-e", NAV12, "-v"] + extra, capture_output=True, text=True,
+                         env=dict(os.environ, FAKE_IIO_EPOCHS="1"), cwd=str(tmp_path))
+    want = ref.stderr.split("Error pushing buf")[0].splitlines()
+    assert len(want) > 12
+    got = sim(["-e", NAV12, "-v", "-r", "-d", "0.1"] + extra, env={"GPSSINK_IIO_LIB": FAKE_IIO, "FAKE_IIO_EPOCHS": "1000"}).stderr.splitlines()
+    assert got[:len(want)] == want, "\n".join(got[:len(want)]) + "\n--- reference ---\n" + "\n".join(want)
+
+
 def test_radio_sink_failures_end_the_run_with_an_error(sim, tmp_path):
     env = {"GPSSINK_IIO_LIB": str(tmp_path / "absent-libiio.so")}
     r = sim(["-e", NAV12, "-r", "-d", "0.2"] + STATIC, env=env, check=False)
