@@ -732,7 +732,10 @@ struct gpshost_scenario {
         iono.enable = !cfg.iono_disable;
         if (cfg.pos_mode == GPSHOST_POS_MOTION) {
             nmotion = cfg.motion_path ? load_motion(cfg.motion_path, motion) : -1;
-            if (nmotion <= 0) { g_error = "cannot read user motion file"; return GPSHOST_ERR_MOTION; }
+            if (nmotion <= 0) {  // plutogpssim.c:2407-2413
+                g_error = nmotion < 0 ? "Failed to open user motion file." : "Failed to read user motion data.";
+                return GPSHOST_ERR_MOTION;
+            }
         } else if (cfg.pos_mode == GPSHOST_POS_LLH) {
             double llh[3] = {cfg.pos[0] / kRad2Deg, cfg.pos[1] / kRad2Deg, cfg.pos[2]};
             geodetic_to_ecef(llh, xyz0);
@@ -742,7 +745,7 @@ struct gpshost_scenario {
         nsets = cfg.rinex3 ? load_rinex3(cfg.nav_path, sets, iono, rinex_date)
                                 : load_rinex2(cfg.nav_path, sets, iono, rinex_date);
         if (nsets < 0) { g_error = cfg.rinex3 ? "cannot read RINEX-3 navigation file" : "cannot read RINEX-2 navigation file"; return GPSHOST_ERR_NAVFILE; }
-        if (nsets == 0) { g_error = "no ephemeris available"; return GPSHOST_ERR_NOEPH; }
+        if (nsets == 0) { g_error = "No ephemeris available."; return GPSHOST_ERR_NOEPH; }
         iono_as_read = iono;
 
         // span of the file, start time, optional TOC/TOE overwrite (plutogpssim.c:2497-2574)
@@ -758,7 +761,7 @@ struct gpshost_scenario {
             t0.sec = floor(cfg.start_sec);
             if (t0.y <= 1980 || t0.m < 1 || t0.m > 12 || t0.d < 1 || t0.d > 31 || t0.hh < 0 || t0.hh > 23 || t0.mm < 0 ||
                 t0.mm > 59 || cfg.start_sec < 0.0 || cfg.start_sec >= 60.0) {
-                g_error = "invalid date and time";
+                g_error = "Invalid date and time.";
                 return GPSHOST_ERR_TIME;
             }
             g0 = cal_to_tow(t0);
@@ -778,7 +781,15 @@ struct gpshost_scenario {
                         e.toe = tow_add(e.toe, dsec);
                     }
             } else if (tow_diff(g0, gmin) < 0.0 || tow_diff(gmax, g0) < 0.0) {
-                g_error = "start time outside the ephemeris span";
+                char msg[256];  // plutogpssim.c:2556-2563
+                Cal tmax;
+                for (int sv = 0; sv < kMaxSv; sv++)
+                    if (sets[(size_t) nsets - 1][sv].valid) { tmax = sets[(size_t) nsets - 1][sv].t; break; }
+                snprintf(msg, sizeof msg,
+                         "Invalid start time.\ntmin = %4d/%02d/%02d,%02d:%02d:%02.0f (%d:%.0f)\ntmax = %4d/%02d/%02d,%02d:%02d:%02.0f (%d:%.0f)",
+                         tmin.y, tmin.m, tmin.d, tmin.hh, tmin.mm, tmin.sec, gmin.week, gmin.sec, tmax.y, tmax.m, tmax.d, tmax.hh,
+                         tmax.mm, tmax.sec, gmax.week, gmax.sec);
+                g_error = msg;
                 return GPSHOST_ERR_TIME;
             }
         } else {
@@ -791,7 +802,7 @@ struct gpshost_scenario {
                 const double dt = tow_diff(g0, sets[(size_t) i][sv].toc);
                 if (dt >= -kHour && dt < kHour) { iset = i; break; }
             }
-        if (iset < 0) { g_error = "no current set of ephemerides"; return GPSHOST_ERR_NOEPH; }
+        if (iset < 0) { g_error = "No current set of ephemerides has been found."; return GPSHOST_ERR_NOEPH; }
 
         chan.assign((size_t) cfg.max_chan, Slot());
         for (int sv = 0; sv < kMaxSv; sv++) owner[sv] = -1;

@@ -119,7 +119,10 @@ int main(int argc, char** argv) {
                 break;
             case 't':
                 if (sscanf(optarg, "%d/%d/%d,%d:%d:%lf", &hc.start[0], &hc.start[1], &hc.start[2], &hc.start[3], &hc.start[4],
-                           &hc.start_sec) != 6) {
+                           &hc.start_sec) != 6 ||
+                    hc.start[0] <= 1980 || hc.start[1] < 1 || hc.start[1] > 12 || hc.start[2] < 1 || hc.start[2] > 31 ||
+                    hc.start[3] < 0 || hc.start[3] > 23 || hc.start[4] < 0 || hc.start[4] > 59 || hc.start_sec < 0.0 ||
+                    hc.start_sec >= 60.0) {  // refused while the options are read, like the reference (plutogpssim.c:2352-2357)
                     fprintf(stderr, "ERROR: Invalid date and time.\n");
                     return 1;
                 }
@@ -143,10 +146,14 @@ int main(int argc, char** argv) {
     if (batch < 1 || duration < 0.0) { usage(); return 1; }
     hc.nav_path = nav.c_str();
     hc.motion_path = motion.empty() ? nullptr : motion.c_str();
-    fprintf(stderr, hc.pos_mode == GPSHOST_POS_MOTION ? "Using user motion mode.\n" : "Using static location mode.\n");
 
+    // the mode line comes after the motion file has been read and before the navigation file is (plutogpssim.c:2402-2420)
+    const bool moving = hc.pos_mode == GPSHOST_POS_MOTION;
+    if (!moving) fprintf(stderr, "Using static location mode.\n");
     gpshost_scenario* sc = nullptr;
-    if (gpshost_open(&sc, &hc) != GPSHOST_OK) { fprintf(stderr, "ERROR: %s\n", gpshost_last_error()); return 1; }
+    const int opened = gpshost_open(&sc, &hc);
+    if (moving && opened != GPSHOST_ERR_MOTION) fprintf(stderr, "Using user motion mode.\n");
+    if (opened != GPSHOST_OK) { fprintf(stderr, "ERROR: %s\n", gpshost_last_error()); return 1; }
     char text[4096];
     if (verbose) {  // ionosphere / UTC parameters of the header (plutogpssim.c:2487-2495)
         gpshost_describe_iono(sc, text, sizeof text);

@@ -211,3 +211,20 @@ def test_plain_c_pipeline_example_compiles_and_reproduces_the_stream(tmp_path):
         r = subprocess.run([str(d / "pipeline_example"), NAV12, str(out), "10", batch], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         assert hashlib.sha256(out.read_bytes()).hexdigest() == ol.load_golden_meta("static12")["iq_sha256"]
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ol.ORACLE_DIR, "_ref", "ref_verbatim")), reason="needs the compiled reference (oracle/_ref)")
+@pytest.mark.parametrize("args", [
+    ["-e", NAV12, "-l", "30.286502,120.032669,100", "-t", "2015/01/01,00:00:00"],          # start time outside the file
+    ["-e", NAV12, "-l", "30.286502,120.032669,100", "-t", "2014/13/20,00:00:00"],          # invalid date
+    ["-e", NAV12, "-u", "/nonexistent/motion.csv"],                                         # motion file cannot be opened
+    ["-e", NAV12, "-l", "30.286502,120.032669,100", "-s", "500000"],                        # sampling frequency
+    ["-l", "30.286502,120.032669,100"],                                                     # no navigation file
+])
+def test_fatal_errors_are_worded_and_ordered_like_the_reference_s(sim, tmp_path, args):
+    """Exit status 1 and the same stderr as the reference binary run here, line for line."""
+    ref = subprocess.run([os.path.join(ol.ORACLE_DIR, "_ref", "ref_verbatim")] + args, capture_output=True, text=True,
+                         env=dict(os.environ, FAKE_IIO_EPOCHS="1"), cwd=str(tmp_path))
+    got = sim(args, check=False)
+    assert ref.returncode == 1 and got.returncode == 1
+    assert got.stderr.splitlines() == ref.stderr.splitlines()
