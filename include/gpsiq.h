@@ -49,7 +49,7 @@ extern "C" {
 /* synthesis kernel selection (gpsiq_config.kernel) */
 #define GPSIQ_KERNEL_AUTO 0
 #define GPSIQ_KERNEL_LANE_PER_CHANNEL 1 /* warp = sample tile, lane = channel, true FP64 steps */
-#define GPSIQ_KERNEL_FIXED_POINT 2      /* thread = sample run, integer NCO segments */
+/* (2 was the segment-list kernel of the first design; retired -- gpsiq_create rejects it) */
 #define GPSIQ_KERNEL_LINE 3             /* one fixed-point line per 1024-sample tile + exact safety check (AUTO picks it) */
 
 #define GPSIQ_MAX_CHAN 32
@@ -242,12 +242,12 @@ int gpsiq_carrier_fallbacks(gpsiq_ctx *ctx, int64_t *count);
  * returns the number of recorded calls and the summed durations in ms. */
 int gpsiq_timing_begin(gpsiq_ctx *ctx);
 int gpsiq_timing_collect(gpsiq_ctx *ctx, int *n_steps, float *scan_ms, float *synth_ms);
-/* The dominant kernel alone: summed duration of the first k_synth_fixed launch of every
+/* The dominant kernel alone: summed duration of the first k_synth_line launch of every
  * recorded call (CUDA events on the launching stream around that launch only), the
  * number of such launches and the epochs each one covers (epochs*samples_per_epoch*4
  * algorithmic bytes per launch). */
 int gpsiq_timing_sample_kernel(gpsiq_ctx *ctx, int *n_launches, float *kernel_ms, int *epochs_per_launch);
-/* The same kernel ALONE: re-launches the last k_synth_fixed (same inputs, same output range) `reps`
+/* The same kernel ALONE: re-launches the last k_synth_line (same inputs, same output range) `reps`
  * times back to back on an idle device and returns the mean duration.  In the pipelined calls the
  * kernel shares the SMs with the scan kernels of the next batch, so its in-pipeline duration says
  * little about the kernel itself. */

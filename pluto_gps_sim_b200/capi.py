@@ -16,7 +16,7 @@ OK = 0
 ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_CAPACITY = -1, -2, -3, -4
 CARRIER_FLOAT, CARRIER_INT32 = 0, 1
 FLAG_RESET_CARRIER = 1
-KERNEL_AUTO, KERNEL_LANE_PER_CHANNEL, KERNEL_FIXED_POINT, KERNEL_LINE = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_LANE_PER_CHANNEL, KERNEL_LINE = 0, 1, 3   # (2 was the retired segment-list kernel)
 LINE_DBG_FORCE_CHUNK, LINE_DBG_FORCE_TILE, LINE_DBG_PERTURB = 1, 2, 4
 MAX_CHAN = 32
 NCO_CODE, NCO_CARRIER = 0, 1

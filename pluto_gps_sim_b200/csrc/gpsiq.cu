@@ -28,7 +28,6 @@
 #include "../../include/gpsiq.h"
 #include "../../include/gpsiq_desc.h"
 #include "nco_scan.cuh"
-#include "synth_fixed.cuh"
 #include "synth_line.cuh"
 
 using namespace gpsiq;
@@ -76,8 +75,6 @@ static void ca_generate(int prn, uint8_t* chips) {
 #define TRACE_MAX 4096
 struct TraceRec { cudaEvent_t ev; const char* label; int stream_id; };
 
-#define FX_SUB_EPOCHS 8   // 8 epochs x 37 CTAs = 296 = 148 SMs x 2 resident 512-thread CTAs: one full wave; the
-                          // sub-batch's records + corrections (~42 MB at 12 slots) stay in L2 between the kernels
 
 // Everything the scan phases produce for one batch and the render phase consumes.  There are two
 // sets so that gpsiq_submit_device can scan batch k+1 while gpsiq_fetch_device renders batch k;
@@ -109,14 +106,12 @@ struct gpsiq_ctx {
     cudaStream_t aux_stream;         // code-NCO scan and tile prologues run beside the carrier chain / the sample kernels
     cudaEvent_t ev_fork, ev_fork2, ev_code2, ev_chain, ev_P[2], ev_F[2];
     cudaEvent_t ev[TIMING_RING][5];  // per recorded step: begin, scans done (= render start), render done,
-                                     // and around the first k_synth_fixed launch of the step
+                                     // and around the first k_synth_line launch of the step
     int fixed_epochs;                // epochs covered by that launch
-    struct { const gpsiq_chan_desc* desc; int16_t* iq; int e0, ne, b, set; } last_fx;  // last k_synth_fixed launch
     int ev_count;                    // steps recorded since gpsiq_timing_begin
     gpsiq_chan_desc* d_desc;
     int2* d_lut;          // [E][C][512]
     int32_t* d_lutp;      // [E][C][512] packed (Q << 16) + I
-    int8_t* d_chips;      // [33][2048] +-1, index = polarity << 10 | chip
     int* d_flags;         // [2][E]: amplitude sum per epoch, step-contract flag per epoch
     double* d_bias_rate;  // [C] measured residual of the closed-form epoch advance (cycles per epoch), see k_bias_update
     double* d_carr_start; // [C] exact phases at the start of the batch being chained
@@ -129,7 +124,6 @@ struct gpsiq_ctx {
     void* fn_wait64;
     int mbox_flush;             // the device can flush remote writes after a wait
     int line_grid_cap;    // GPSIQ_OPT_LINE_GRID_CAP: most CTAs of one k_synth_line launch (0: one CTA per unit)
-    int use_fixed;        // k_synth_fixed is eligible for this configuration
     int use_line;         // k_synth_line (the production kernel) is eligible for this configuration
     int8_t* d_chips4;     // [33][4][LN_VS] +-1: chip/NAV sign tables in 4 polarity variants, extended past chip 1022
     ulonglong2* d_anch[2];   // [E][ntiles][C] tile anchors {F, G} (one buffer per scan set)
@@ -139,12 +133,6 @@ struct gpsiq_ctx {
     unsigned long long* d_line_totals;  // the same, accumulated over the context's life
     LinePatch* d_patches;
     struct { const gpsiq_chan_desc* desc; int16_t* iq; int ne, set, e0; } last_ln;  // last k_synth_line launch
-    // per sub-batch scratch, double buffered: the prologue of sub-batch k+1 overlaps the sample kernels of k
-    unsigned char* d_recs[2]; // [FX_SUB_EPOCHS][ntiles] tile records (synth_fixed.cuh)
-    uint32_t* d_fixmasks[2];  // [FX_SUB_EPOCHS][ntiles][C][4] (+ the work-list counter behind it)
-    int32_t* d_delta[2];      // [FX_SUB_EPOCHS][ntiles][FX_TILE] per-sample corrections
-    uint32_t* d_work[2];      // work list of (tile, channel, run) triples with a segment boundary
-    int work_cap;
     double* d_code_ck;    // [E][ntiles][C]
     int* d_wrap_ck;       // [E][ntiles][C]
     double* d_carr_ck;    // [5][E][ntiles][C] planes: 0,1 chunk speculation (parity variants), 2,3 stitched epoch-level
@@ -255,7 +243,7 @@ __global__ void k_prepare(const gpsiq_chan_desc* __restrict__ desc, int2* __rest
         // |entry| <= 512*|gain| + 1: bound on this slot's share of |sum I|, |sum Q|
         const double a = fabs(d.gain) * 512.0 + 1.0;
         atomicAdd(&amp_sum[ec / C], a < 40000.0 ? (int) a : 40000);
-        // segment-list contract of k_synth_fixed: <= 4 carrier cycles and <= 2 code periods per 1024-sample tile
+        // contract of k_synth_line: <= 4 carrier cycles and <= 1 code-period wrap per 1024-sample tile
         if (!(fabs(d.carr_step) <= 0x1p-8) || !(d.code_step <= 0.5)) atomicOr(&step_flag[ec / C], 1);
     }
 }
@@ -618,7 +606,7 @@ k_carr_final(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restri
 // Executes the very IEEE additions the reference executes, starting from the
 // exact tile-start state; the across-satellite accumulate (plutogpssim.c:2705-2706)
 // is a warp reduction.  Simple and exact by construction; kept as the
-// cross-check for the fixed-point kernel.
+// cross-check for k_synth_line and as the path for epochs outside its contract.
 // ---------------------------------------------------------------------------
 #define LANES_WARPS 4
 
@@ -635,7 +623,7 @@ k_synth_lanes(const gpsiq_chan_desc* __restrict__ desc, const int2* __restrict__
 
     const int e = e0 + blockIdx.x / tile_groups;
     const int tg = blockIdx.x % tile_groups;
-    if (only_flagged && !(amp_sum[e] > 32767 || step_flag[e])) return;  // rendered by k_synth_fixed
+    if (only_flagged && !(amp_sum[e] > 32767 || step_flag[e])) return;  // rendered by k_synth_line
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const gpsiq_chan_desc* de = desc + (size_t) e * C;
 
@@ -806,14 +794,6 @@ int gpsiq_nco_advance(int mode, double* phase, double step, int64_t count, int64
     return GPSIQ_OK;
 }
 
-// Estimated start phase of epoch e for the speculative scan: the previous
-// state advanced by N*step in one rounding (no per-sample drift).
-static inline double est_advance(double x, double d, int N) {
-    double t = fma((double) N, d, x);
-    t -= floor(t);
-    return (t >= 0.0 && t < 1.0) ? t : 0.0;
-}
-
 int gpsiq_carrier_chain_host(const double* steps, int n_epochs, int N, int T, double x0, double est_err, double* ck_out,
                              double* x_end_out, int* n_fallback) {
     if (!steps || !ck_out || n_epochs < 1 || N < 1 || T < 1) return GPSIQ_ERR_ARG;
@@ -903,27 +883,9 @@ void gpsiq_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
-int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
-    gpsiq_ctx* ctx = NULL;
-    if (!out || !cfg) return fail(NULL, GPSIQ_ERR_ARG, "gpsiq_create: null argument", cudaSuccess);
-    *out = NULL;
-    if (cfg->max_chan < 1 || cfg->max_chan > GPSIQ_MAX_CHAN || cfg->samples_per_epoch < 1 || cfg->max_epochs < 1 ||
-        (cfg->carrier_mode != GPSIQ_CARRIER_FLOAT && cfg->carrier_mode != GPSIQ_CARRIER_INT32) || cfg->tile_samples < 0)
-        return fail(NULL, GPSIQ_ERR_ARG, "gpsiq_create: bad config", cudaSuccess);
-    int ndev = 0;
-    cudaError_t ce = cudaGetDeviceCount(&ndev);
-    if (ce != cudaSuccess || ndev < 1)
-        return fail(NULL, GPSIQ_ERR_CUDA, "gpsiq_create: no CUDA device (there is no CPU fallback)", ce);
-    if (cfg->device < 0 || cfg->device >= ndev) return fail(NULL, GPSIQ_ERR_ARG, "gpsiq_create: bad device", cudaSuccess);
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, cfg->device));
-    if (prop.major != 10) {
-        snprintf(g_err, sizeof g_err, "gpsiq_create: device %d is sm_%d%d; this build is sm_100a only", cfg->device,
-                 prop.major, prop.minor);
-        return GPSIQ_ERR_CUDA;
-    }
-    ctx = (gpsiq_ctx*) calloc(1, sizeof *ctx);
-    if (!ctx) return GPSIQ_ERR_NOMEM;
+// Everything of gpsiq_create that can fail after the context exists: on failure the caller copies the message to
+// the global error text (gpsiq_last_error(NULL)) and destroys the partly built context.
+static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDeviceProp& prop) {
     ctx->cfg = *cfg;
     ctx->trace_on = getenv("GPSIQ_TRACE") != NULL;
     if (getenv("GPSIQ_LINE_GRID_CAP")) ctx->line_grid_cap = atoi(getenv("GPSIQ_LINE_GRID_CAP"));  // experiments
@@ -932,20 +894,13 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
     ctx->C = cfg->max_chan;
     ctx->N = cfg->samples_per_epoch;
     ctx->E = cfg->max_epochs;
-    ctx->T = cfg->tile_samples ? cfg->tile_samples : FX_TILE;
+    ctx->T = cfg->tile_samples ? cfg->tile_samples : LN_TILE;
     ctx->T = (ctx->T + 31) & ~31;
-    // the fixed-point kernel needs its own tile length, 16-byte aligned epochs, the float carrier and <= FX_MAXC slots
-    ctx->use_fixed = (cfg->kernel != GPSIQ_KERNEL_LANE_PER_CHANNEL) && ctx->T == FX_TILE && (ctx->N % 4 == 0) &&
-                     ctx->C <= FX_MAXC && cfg->carrier_mode == GPSIQ_CARRIER_FLOAT;
     ctx->use_line = (cfg->kernel == GPSIQ_KERNEL_AUTO || cfg->kernel == GPSIQ_KERNEL_LINE) && ctx->T == LN_TILE &&
                     ctx->C <= 32 && cfg->carrier_mode == GPSIQ_CARRIER_FLOAT;
     if (cfg->kernel == GPSIQ_KERNEL_LINE && !ctx->use_line)
-        return fail(NULL, GPSIQ_ERR_ARG, "gpsiq_create: the line kernel needs tile_samples 0/1024, max_chan <= 32 and the float carrier",
+        return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_create: the line kernel needs tile_samples 0/1024, max_chan <= 32 and the float carrier",
                     cudaSuccess);
-    if (ctx->use_line) ctx->use_fixed = 0;
-    if (cfg->kernel == GPSIQ_KERNEL_FIXED_POINT && !ctx->use_fixed)
-        return fail(NULL, GPSIQ_ERR_ARG, "gpsiq_create: fixed-point kernel needs tile_samples 0/1024, samples_per_epoch % 4 == 0, "
-                    "max_chan <= 32 and the float carrier", cudaSuccess);
     ctx->ntiles = (ctx->N + ctx->T - 1) / ctx->T;
     CU(cudaSetDevice(cfg->device));
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -966,7 +921,6 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
     const size_t EC = (size_t) ctx->E * ctx->C;
     const size_t ck = EC * ctx->ntiles;
     CU(cudaMalloc(&ctx->d_desc, EC * sizeof(gpsiq_chan_desc)));
-    CU(cudaMalloc(&ctx->d_chips, 33 * 2048));
     ctx->ck_plane = ck;
     {   // chunks per epoch of the first speculation level (default 8; GPSIQ_SPEC_CHUNKS: experiments)
         int chunks = 8;
@@ -1038,32 +992,6 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
         for (int i = 0; i < GPSIQ_CA_LEN; i++) h_ca[prn * CA_WORDS + (i >> 5)] |= (uint32_t) chips[i] << (i & 31);
     }
     CU(cudaMemcpy(ctx->d_ca, h_ca, sizeof h_ca, cudaMemcpyHostToDevice));
-    {
-        int8_t* h_chips = (int8_t*) malloc(33 * 2048);
-        if (!h_chips) return GPSIQ_ERR_NOMEM;
-        memset(h_chips, 1, 33 * 2048);
-        for (int prn = 1; prn <= 32; prn++) {
-            uint8_t chips[GPSIQ_CA_LEN];
-            ca_generate(prn, chips);
-            for (int pol = 0; pol < 2; pol++)
-                for (int i = 0; i < GPSIQ_CA_LEN; i++)  // BPSK sign: +1 iff NAV bit == chip (plutogpssim.c:2701, 2732, 2737)
-                    h_chips[prn * 2048 + pol * 1024 + i] = (chips[i] == pol) ? 1 : -1;
-        }
-        cudaError_t ce2 = cudaMemcpy(ctx->d_chips, h_chips, 33 * 2048, cudaMemcpyHostToDevice);
-        free(h_chips);
-        CU(ce2);
-    }
-    if (ctx->use_fixed) {
-        CU(cudaFuncSetAttribute(k_synth_fixed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fx_smem_bytes(ctx->C)));
-        const size_t tiles = (size_t) FX_SUB_EPOCHS * ctx->ntiles;
-        ctx->work_cap = (int) (tiles * ctx->C * 40);  // ~3x the typical count; overflow routes the epoch to the lane kernel
-        for (int i = 0; i < 2; i++) {
-            CU(cudaMalloc(&ctx->d_recs[i], tiles * fx_rec_bytes(ctx->C)));
-            CU(cudaMalloc(&ctx->d_fixmasks[i], tiles * fx_fixmask_words(ctx->C) * 4 + 16));
-            CU(cudaMalloc(&ctx->d_delta[i], tiles * FX_TILE * sizeof(int32_t)));
-            CU(cudaMalloc(&ctx->d_work[i], (size_t) ctx->work_cap * 4));
-        }
-    }
     if (ctx->use_line) {
         // The kernels meant to run beside k_synth_line (the rest of the next batch's carrier chain) ask for the
         // same (maximum) shared-memory carve-out: an SM cannot change its L1/shared split while blocks are
@@ -1096,7 +1024,7 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
         // k >= 1023: chip k-1023 of the NEXT code period under NAV bit pol1.  +1 iff NAV bit == chip
         // (plutogpssim.c:2701, 2732, 2737)
         int8_t* h4 = (int8_t*) malloc((size_t) 33 * 4 * LN_VS);
-        if (!h4) return GPSIQ_ERR_NOMEM;
+        if (!h4) return fail(ctx, GPSIQ_ERR_NOMEM, "gpsiq_create: out of host memory", cudaSuccess);
         memset(h4, 1, (size_t) 33 * 4 * LN_VS);
         for (int prn = 1; prn <= 32; prn++) {
             uint8_t chips[GPSIQ_CA_LEN];
@@ -1114,6 +1042,40 @@ int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
     }
     const size_t smem_lanes = (size_t) ctx->C * 512 * sizeof(int2) + (size_t) ctx->C * 33 * 4;
     CU(cudaFuncSetAttribute(k_synth_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_lanes));
+    return GPSIQ_OK;
+}
+
+void gpsiq_destroy(gpsiq_ctx* ctx);
+
+int gpsiq_create(gpsiq_ctx** out, const gpsiq_config* cfg) {
+    gpsiq_ctx* ctx = NULL;
+    if (!out || !cfg) return fail(NULL, GPSIQ_ERR_ARG, "gpsiq_create: null argument", cudaSuccess);
+    *out = NULL;
+    if (cfg->max_chan < 1 || cfg->max_chan > GPSIQ_MAX_CHAN || cfg->samples_per_epoch < 1 || cfg->max_epochs < 1 ||
+        (cfg->carrier_mode != GPSIQ_CARRIER_FLOAT && cfg->carrier_mode != GPSIQ_CARRIER_INT32) || cfg->tile_samples < 0 ||
+        (cfg->kernel != GPSIQ_KERNEL_AUTO && cfg->kernel != GPSIQ_KERNEL_LANE_PER_CHANNEL && cfg->kernel != GPSIQ_KERNEL_LINE))
+        return fail(NULL, GPSIQ_ERR_ARG, "gpsiq_create: bad config", cudaSuccess);
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev < 1)
+        return fail(NULL, GPSIQ_ERR_CUDA, "gpsiq_create: no CUDA device (there is no CPU fallback)", ce);
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(NULL, GPSIQ_ERR_ARG, "gpsiq_create: bad device", cudaSuccess);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) {
+        snprintf(g_err, sizeof g_err, "gpsiq_create: device %d is sm_%d%d; this build is sm_100a only", cfg->device,
+                 prop.major, prop.minor);
+        return GPSIQ_ERR_CUDA;
+    }
+    ctx = (gpsiq_ctx*) calloc(1, sizeof *ctx);
+    if (!ctx) return fail(NULL, GPSIQ_ERR_NOMEM, "gpsiq_create: out of host memory", cudaSuccess);
+    const int rc = create_body(ctx, cfg, prop);
+    if (rc != GPSIQ_OK) {
+        snprintf(g_err, sizeof g_err, "%.255s", ctx->err);
+        gpsiq_destroy(ctx);
+        cudaGetLastError();
+        return rc;
+    }
     *out = ctx;
     return GPSIQ_OK;
 }
@@ -1130,18 +1092,18 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
         }
         gpsiq_trace_dump(ctx, 1);
     }
-    cudaStreamSynchronize(ctx->stream);
-    cudaStreamSynchronize(ctx->scan_stream);
-    cudaStreamSynchronize(ctx->aux2_stream);
-    cudaFree(ctx->d_desc); cudaFree(ctx->d_chips);
+    // (also called on a partly built context by gpsiq_create: every handle may still be NULL)
+    cudaDeviceSynchronize();
+    cudaFree(ctx->d_desc);
     for (int i = 0; i < 2; i++) {
         ScanSet& ss = ctx->sets[i];
         cudaFree(ss.d_descbuf); cudaFree(ss.d_lut); cudaFree(ss.d_lutp); cudaFree(ss.d_flags); cudaFree(ss.d_code_ck);
         cudaFree(ss.d_wrap_ck); cudaFree(ss.d_carr_ck); cudaFree(ss.d_tab); cudaFree(ss.d_drift); cudaFree(ss.d_spec);
         cudaFree(ss.d_specE); cudaFree(ss.d_cinfo); cudaFree(ss.d_info); cudaFree(ss.d_adv); cudaFree(ss.d_carr_trace);
         cudaFree(ss.d_specG); cudaFree(ss.d_ginfo); cudaFree(ss.d_traceG);
-        cudaEventDestroy(ss.scan_done); cudaEventDestroy(ss.render_done); cudaEventDestroy(ss.spec_done);
-        cudaFree(ctx->d_recs[i]); cudaFree(ctx->d_fixmasks[i]); cudaFree(ctx->d_delta[i]); cudaFree(ctx->d_work[i]);
+        if (ss.scan_done) cudaEventDestroy(ss.scan_done);
+        if (ss.render_done) cudaEventDestroy(ss.render_done);
+        if (ss.spec_done) cudaEventDestroy(ss.spec_done);
     }
     cudaFree(ctx->d_chips4); cudaFree(ctx->d_anch[0]); cudaFree(ctx->d_anch[1]); cudaFree(ctx->d_hazlist);
     cudaFree(ctx->d_patches); cudaFree(ctx->d_line_counters); cudaFree(ctx->d_line_totals);
@@ -1152,16 +1114,22 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
     cudaFree(ctx->d_iq); cudaFree(ctx->d_iq2); cudaFree(ctx->d_sums); cudaFree(ctx->d_err);
     if (ctx->h_stage[0]) cudaFreeHost(ctx->h_stage[0]);
     if (ctx->h_stage[1]) cudaFreeHost(ctx->h_stage[1]);
-    cudaStreamDestroy(ctx->scan_stream); cudaStreamDestroy(ctx->aux2_stream); cudaEventDestroy(ctx->ev_fork2);
+#define DROP_STREAM(s) do { if (s) cudaStreamDestroy(s); } while (0)
+#define DROP_EVENT(e) do { if (e) cudaEventDestroy(e); } while (0)
+    DROP_STREAM(ctx->scan_stream); DROP_STREAM(ctx->aux2_stream); DROP_EVENT(ctx->ev_fork2); DROP_EVENT(ctx->ev_code2);
     for (int i = 0; i < TIMING_RING; i++)
-        for (int j = 0; j < 5; j++) cudaEventDestroy(ctx->ev[i][j]);
-    cudaStreamDestroy(ctx->stream);
-    cudaStreamDestroy(ctx->copy_stream);
-    cudaStreamSynchronize(ctx->aux_stream);
-    cudaStreamDestroy(ctx->aux_stream);
-    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_chain);
-    for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_P[i]); cudaEventDestroy(ctx->ev_F[i]); }
-    cudaEventDestroy(ctx->ev_sub[0]); cudaEventDestroy(ctx->ev_sub[1]);
+        for (int j = 0; j < 5; j++) DROP_EVENT(ctx->ev[i][j]);
+    DROP_STREAM(ctx->stream); DROP_STREAM(ctx->copy_stream); DROP_STREAM(ctx->aux_stream);
+    DROP_EVENT(ctx->ev_fork); DROP_EVENT(ctx->ev_chain);
+    for (int i = 0; i < 2; i++) { DROP_EVENT(ctx->ev_P[i]); DROP_EVENT(ctx->ev_F[i]); }
+    DROP_EVENT(ctx->ev_sub[0]); DROP_EVENT(ctx->ev_sub[1]);
+    if (ctx->trace) {
+        for (int i = 0; i < TRACE_MAX; i++) DROP_EVENT(ctx->trace[i].ev);
+        free(ctx->trace);
+    }
+#undef DROP_STREAM
+#undef DROP_EVENT
+    cudaGetLastError();
     free(ctx);
 }
 
@@ -1377,51 +1345,6 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
             if (iq_host) {
                 CU(cudaEventRecord(ctx->ev_F[k & 1], st));
                 CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_F[k & 1], 0));
-                CU(cudaMemcpyAsync(iq_host + (size_t) e0 * N * 2, iq_dev + (size_t) e0 * N * 2, (size_t) ne * N * 4,
-                                   cudaMemcpyDeviceToHost, ctx->copy_stream));
-            }
-        }
-    } else if (ctx->use_fixed) {
-        const int groups = (ntiles + FX_TILES_PER_CTA - 1) / FX_TILES_PER_CTA;
-        const int tgroups = (ntiles + 31) / 32;
-        cudaStream_t ax = ctx->aux_stream;
-        int k = 0;
-        for (int e0 = 0; e0 < n_epochs; e0 += FX_SUB_EPOCHS, k++) {
-            const int ne = n_epochs - e0 < FX_SUB_EPOCHS ? n_epochs - e0 : FX_SUB_EPOCHS;
-            const int b = k & 1;
-            const size_t mask_bytes = (size_t) ne * ntiles * fx_fixmask_words(C) * 4;
-            int* nwork = (int*) ((unsigned char*) ctx->d_fixmasks[b] + (size_t) FX_SUB_EPOCHS * ntiles * fx_fixmask_words(C) * 4);
-            // aux stream: prologue of sub-batch k into buffer b (free once the sample kernels of k-2 are done)
-            if (k >= 2) CU(cudaStreamWaitEvent(ax, ctx->ev_F[b], 0));
-            CU(cudaMemsetAsync(ctx->d_fixmasks[b], 0, mask_bytes, ax));
-            CU(cudaMemsetAsync(nwork, 0, 16, ax));
-            CU(cudaMemsetAsync(ctx->d_delta[b], 0, (size_t) ne * ntiles * FX_TILE * sizeof(int32_t), ax));
-            const int warps = ne * 2 * C * tgroups;
-            k_tile_prologue<<<(warps + 3) / 4, 128, 0, ax>>>(desc_dev, ctx->d_tab, ctx->d_code_ck, ctx->d_wrap_ck,
-                                                             make_lookup(ctx), ctx->d_flags, ctx->d_flags + ctx->E,
-                                                             ctx->d_recs[b], ctx->d_fixmasks[b], ctx->d_work[b], nwork,
-                                                             ctx->work_cap, e0, ne, C, N, ntiles);
-            CU(cudaEventRecord(ctx->ev_P[b], ax));
-            // main stream: corrections + sample kernels of sub-batch k
-            CU(cudaStreamWaitEvent(st, ctx->ev_P[b], 0));
-            k_tile_fixup<<<148 * 8, 128, 0, st>>>(desc_dev, ctx->d_lutp, ctx->d_tab, ctx->d_recs[b], ctx->d_chips,
-                                                 ctx->d_work[b], nwork, ctx->work_cap, ctx->d_delta[b], e0, C, N, ntiles);
-            const bool timed = (k == 0 && ctx->ev_count < TIMING_RING);
-            if (timed) { CU(cudaEventRecord(ctx->ev[ctx->ev_count][3], st)); ctx->fixed_epochs = ne; }
-            k_synth_fixed<<<ne * groups, FX_WORKERS * FX_THREADS, fx_smem_bytes(C), st>>>(
-                desc_dev, ctx->d_lutp, ctx->d_tab, ctx->d_recs[b], ctx->d_delta[b], ctx->d_chips, ctx->d_flags,
-                ctx->d_flags + ctx->E, iq_dev, e0, C, N, ntiles, groups);
-            if (timed) CU(cudaEventRecord(ctx->ev[ctx->ev_count][4], st));
-            ctx->last_fx.desc = desc_dev; ctx->last_fx.iq = iq_dev; ctx->last_fx.e0 = e0; ctx->last_fx.ne = ne;
-            ctx->last_fx.b = b; ctx->last_fx.set = ctx->set_cur;
-            // epochs of this sub-batch outside the fixed-point kernel's contract
-            k_synth_lanes<<<ne * tile_groups, LANES_WARPS * 32, smem, st>>>(
-                desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx), ctx->d_ca, ctx->d_flags,
-                ctx->d_flags + ctx->E, 1, iq_dev, e0, C, N, T, ntiles, tile_groups, ctx->cfg.carrier_mode);
-            CU(cudaEventRecord(ctx->ev_F[b], st));
-            ctx->launches += 4;
-            if (iq_host) {  // ship the finished sub-batch while the next one renders
-                CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_F[b], 0));
                 CU(cudaMemcpyAsync(iq_host + (size_t) e0 * N * 2, iq_dev + (size_t) e0 * N * 2, (size_t) ne * N * 4,
                                    cudaMemcpyDeviceToHost, ctx->copy_stream));
             }
@@ -1803,34 +1726,25 @@ int gpsiq_timing_collect(gpsiq_ctx* ctx, int* n_steps, float* scan_ms, float* sy
     return GPSIQ_OK;
 }
 
-// Re-launch the last k_synth_fixed (same records, same output range -- it rewrites identical samples)
+// Re-launch the last k_synth_line (same anchors, same output range -- it rewrites identical samples)
 // `reps` times back to back on an otherwise idle device and return the mean duration: the kernel ALONE.
 int gpsiq_timing_sample_kernel_isolated(gpsiq_ctx* ctx, int reps, float* kernel_ms, int* epochs_per_launch) {
     if (!ctx || reps < 1 || !kernel_ms) return GPSIQ_ERR_ARG;
-    const bool line = ctx->use_line && ctx->last_ln.desc;
-    if (!line && (!ctx->use_fixed || !ctx->last_fx.desc))
-        return fail(ctx, GPSIQ_ERR_ARG, "no k_synth_line / k_synth_fixed launch to repeat", cudaSuccess);
+    if (!ctx->use_line || !ctx->last_ln.desc) return fail(ctx, GPSIQ_ERR_ARG, "no k_synth_line launch to repeat", cudaSuccess);
     CU(cudaSetDevice(ctx->cfg.device));
     CU(cudaDeviceSynchronize());
-    use_set(ctx, line ? ctx->last_ln.set : ctx->last_fx.set);
-    const int C = ctx->C, N = ctx->N, ntiles = ctx->ntiles, b = ctx->last_fx.b;
-    const int groups = (ntiles + FX_TILES_PER_CTA - 1) / FX_TILES_PER_CTA;
+    use_set(ctx, ctx->last_ln.set);
+    const int C = ctx->C, N = ctx->N, ntiles = ctx->ntiles;
     cudaEvent_t e0 = ctx->ev[TIMING_RING - 1][3], e1 = ctx->ev[TIMING_RING - 1][4];
     for (int i = 0; i < reps + 1; i++) {  // first launch is a warm-up
         if (i == 1) CU(cudaEventRecord(e0, ctx->stream));
-        if (line) {
-            const int ne = ctx->last_ln.ne, le0 = ctx->last_ln.e0;
-            int grid = ne * ((ntiles + LN_UNIT - 1) / LN_UNIT);
-            if (ctx->line_grid_cap > 0 && grid > ctx->line_grid_cap) grid = ctx->line_grid_cap;
-            k_synth_line<<<grid, LN_THREADS, ln_smem_bytes(C), ctx->stream>>>(
-                ctx->last_ln.desc, ctx->d_lutp + (size_t) le0 * C * 512, ctx->d_chips4,
-                ctx->d_anch[ctx->last_ln.set] + (size_t) le0 * ntiles * C, ctx->d_flags + le0, ctx->d_flags + ctx->E + le0,
-                ctx->last_ln.iq, ne, C, N, ntiles, ctx->d_err);
-        } else {
-            k_synth_fixed<<<ctx->last_fx.ne * groups, FX_WORKERS * FX_THREADS, fx_smem_bytes(C), ctx->stream>>>(
-                ctx->last_fx.desc, ctx->d_lutp, ctx->d_tab, ctx->d_recs[b], ctx->d_delta[b], ctx->d_chips, ctx->d_flags,
-                ctx->d_flags + ctx->E, ctx->last_fx.iq, ctx->last_fx.e0, C, N, ntiles, groups);
-        }
+        const int ne = ctx->last_ln.ne, le0 = ctx->last_ln.e0;
+        int grid = ne * ((ntiles + LN_UNIT - 1) / LN_UNIT);
+        if (ctx->line_grid_cap > 0 && grid > ctx->line_grid_cap) grid = ctx->line_grid_cap;
+        k_synth_line<<<grid, LN_THREADS, ln_smem_bytes(C), ctx->stream>>>(
+            ctx->last_ln.desc, ctx->d_lutp + (size_t) le0 * C * 512, ctx->d_chips4,
+            ctx->d_anch[ctx->last_ln.set] + (size_t) le0 * ntiles * C, ctx->d_flags + le0, ctx->d_flags + ctx->E + le0,
+            ctx->last_ln.iq, ne, C, N, ntiles, ctx->d_err);
     }
     CU(cudaEventRecord(e1, ctx->stream));
     CU(cudaEventSynchronize(e1));
@@ -1838,7 +1752,7 @@ int gpsiq_timing_sample_kernel_isolated(gpsiq_ctx* ctx, int reps, float* kernel_
     CU(cudaEventElapsedTime(&t, e0, e1));
     ctx->launches += reps + 1;
     *kernel_ms = t / reps;
-    if (epochs_per_launch) *epochs_per_launch = line ? ctx->last_ln.ne : ctx->last_fx.ne;
+    if (epochs_per_launch) *epochs_per_launch = ctx->last_ln.ne;
     return GPSIQ_OK;
 }
 
@@ -1847,7 +1761,7 @@ int gpsiq_timing_sample_kernel(gpsiq_ctx* ctx, int* n_launches, float* kernel_ms
     CU(cudaSetDevice(ctx->cfg.device));
     float a = 0.f;
     int n = 0;
-    if (ctx->use_fixed || ctx->use_line)
+    if (ctx->use_line)
         for (int i = 0; i < ctx->ev_count; i++) {
             float t = 0.f;
             CU(cudaEventSynchronize(ctx->ev[i][4]));

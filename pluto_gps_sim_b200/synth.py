@@ -168,7 +168,7 @@ class Synthesizer:
         return n.value, a.value, b.value
 
     def timing_sample_kernel(self):
-        """-> (launches, summed ms, epochs per launch) of the dominant kernel (k_synth_line / k_synth_fixed) alone."""
+        """-> (launches, summed ms, epochs per launch) of the dominant kernel (k_synth_line) alone."""
         n, a, e = C.c_int(0), C.c_float(0), C.c_int(0)
         capi.check(capi.lib.gpsiq_timing_sample_kernel(self._ctx, C.byref(n), C.byref(a), C.byref(e)), self._ctx)
         return n.value, a.value, e.value

@@ -10,8 +10,8 @@ from pluto_gps_sim_b200 import Synthesizer, capi, checksum_host
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [capi.KERNEL_LANE_PER_CHANNEL, capi.KERNEL_FIXED_POINT, capi.KERNEL_LINE]
-FAST_KERNELS = [capi.KERNEL_FIXED_POINT, capi.KERNEL_LINE]
+KERNELS = [capi.KERNEL_LANE_PER_CHANNEL, capi.KERNEL_LINE]
+FAST_KERNELS = [capi.KERNEL_LINE]
 
 
 def first_diff(a, b):
@@ -230,6 +230,34 @@ def test_integer_carrier_mode_vs_oracle():
         gt = s.carrier_trace(3)
     assert first_diff(got, want) is None
     assert np.array_equal(gt, wt)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_integer_carrier_static12_bit_exact_vs_reference_golden(kernel):
+    """Integer carrier NCO against the reference compiled without FLOAT_CARR_PHASE (tests/golden/static12int_*)."""
+    meta = ol.load_golden_meta("static12int")
+    desc = ol.load_golden_desc("static12int")
+    with Synthesizer(max_chan=12, max_epochs=10, carrier_mode=capi.CARRIER_INT32, kernel=kernel) as s:
+        iq = s.synth(desc)
+        trace = s.carrier_trace(10)
+    assert ol.sha256(iq) == meta["iq_sha256"], first_diff(iq, ol.oracle_synth(desc, 300000, carrier_mode=1)[0])
+    want = np.array([[float.fromhex(h) for h in row] for row in meta["carr_phase_end_hex"]])
+    assert np.array_equal(trace, want)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_integer_carrier_circle_310_epochs_batched_with_carry(kernel):
+    """Integer carrier across the 30 s refresh (slots re-seeded), uneven batches, submit/fetch carry."""
+    meta = ol.load_golden_meta("circle12int")
+    desc = ol.load_golden_desc("circle12int")
+    sums = []
+    with Synthesizer(max_chan=12, max_epochs=128, carrier_mode=capi.CARRIER_INT32, kernel=kernel) as s:
+        e = 0
+        for n in (1, 7, 128, 100, 74):
+            s.synth(desc[e:e + n], keep_on_device=True)
+            sums += [int(x) for x in s.checksum_device(s.device_iq_ptr(), n)]
+            e += n
+    assert sums == meta["epoch_checksums"]
 
 
 def test_parallel_and_serial_carrier_scan_agree():

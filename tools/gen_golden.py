@@ -26,7 +26,7 @@ import refdump  # noqa: E402
 from pluto_gps_sim_b200.synth import checksum_host  # noqa: E402
 
 HEAD = 8192
-PLAN = [("static12", 10, 0), ("circle12", 310, 0), ("allsky32", 20, 0)]
+PLAN = [("static12", 10, 0), ("circle12", 310, 0), ("allsky32", 20, 0), ("static12int", 10, 1), ("circle12int", 310, 1)]
 
 
 def file_sha(path):
@@ -35,7 +35,10 @@ def file_sha(path):
 
 def main():
     out = refdump.GOLDEN
+    only = sys.argv[1:]          # optional: regenerate just these scenarios
     for name, epochs, mode in PLAN:
+        if only and name not in only:
+            continue
         with tempfile.TemporaryDirectory() as wd:
             recs, iq, js = refdump.run_reference(name, epochs, wd)
         desc = refdump.to_descriptors(recs, mode)

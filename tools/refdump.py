@@ -28,6 +28,9 @@ SCENARIOS = {
     # name: (harness, nav fixture, extra args, max_chan)
     "static12": ("ref_harness_O2", "brdc3540_synth.14n.gz", ["-l", "30.286502,120.032669,100", "-s", "2600000"], 12),
     "circle12": ("ref_harness_O2", "brdc3540_synth.14n.gz", ["-u", "@circle", "-s", "2600000"], 12),
+    # the reference built WITHOUT FLOAT_CARR_PHASE (plutogpssim.h:12 removed): its integer carrier NCO
+    "static12int": ("ref_harness_int_O2", "brdc3540_synth.14n.gz", ["-l", "30.286502,120.032669,100", "-s", "2600000"], 12),
+    "circle12int": ("ref_harness_int_O2", "brdc3540_synth.14n.gz", ["-u", "@circle", "-s", "2600000"], 12),
     "allsky32": ("ref_harness32_O2", "allsky32_synth.14n.gz", ["-l", "30.286502,120.032669,100", "-s", "10000000"], 32),
 }
 
