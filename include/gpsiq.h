@@ -195,6 +195,11 @@ int gpsiq_render_device(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc_dev, int n_e
                         void *cuda_stream);
 /* estimate <- fold(estimate, advance): skip over a slice synthesized elsewhere */
 int gpsiq_estimate_fold_device(gpsiq_ctx *ctx, const double *advance_dev, void *cuda_stream);
+/* Integer carrier only: carrier state <- fold(state, advance), EXACT (uint32 arithmetic, plutogpssim.c:2748): skips
+ * over a slice synthesized elsewhere, where advance is what gpsiq_prepare_device returned for that slice (phase
+ * advance modulo 2^32, or an absolute phase when the slice re-seeded the slot).  With it the time slices of the
+ * integer-carrier mode need no ring: every rank folds the advances of the slices before its own. */
+int gpsiq_carrier_fold_device(gpsiq_ctx *ctx, const double *advance_dev, void *cuda_stream);
 /* estimate <- the context's exact carrier state (e.g. right after gpsiq_carrier_from_device) */
 int gpsiq_estimate_anchor_device(gpsiq_ctx *ctx, void *cuda_stream);
 /* Copy the carrier state (max_chan doubles) to / from DEVICE memory on a stream

@@ -86,6 +86,7 @@ SYMBOLS = {
     "gpsiq_speculate_device": (_i, [_vp, _vp, _i, _vp]),
     "gpsiq_chain_device": (_i, [_vp, _vp, _i, _vp]),
     "gpsiq_estimate_fold_device": (_i, [_vp, _vp, _vp]),
+    "gpsiq_carrier_fold_device": (_i, [_vp, _vp, _vp]),
     "gpsiq_estimate_anchor_device": (_i, [_vp, _vp]),
     "gpsiq_render_device": (_i, [_vp, _vp, _i, _vp, _vp]),
     "gpsiq_set_option": (_i, [_vp, _i, _i]),

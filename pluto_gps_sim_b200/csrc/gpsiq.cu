@@ -84,7 +84,7 @@ struct ScanSet {
     int2* d_lut; int32_t* d_lutp; int* d_flags; double* d_code_ck; int* d_wrap_ck; double* d_carr_ck;
     BinadeTab* d_tab; double* d_drift; CarrSpec* d_spec; CarrSpec* d_specE; ChunkInfo* d_cinfo; CarrInfo* d_info;
     CarrSpec* d_specG; GroupInfo* d_ginfo; double* d_traceG;
-    double* d_adv; double* d_carr_trace;
+    double* d_adv; double* d_carr_trace; uint32_t* d_ustart;
     cudaEvent_t scan_done, render_done, spec_done;
     const gpsiq_chan_desc* desc;  // the batch's descriptors (device)
     int n_epochs;
@@ -155,6 +155,7 @@ struct gpsiq_ctx {
     double* d_est_state;  // [C]  ESTIMATED phase at the start of the next batch to speculate (never part of a result)
     double* d_adv;        // [2C] this batch's closed-form phase advance per slot + "re-seeded" flags
     double* d_carr_trace; // [E][C]
+    uint32_t* d_ustart;   // [E][C] integer-carrier mode: the uint32 phase at the first sample of every epoch
     uint32_t* d_ca;       // [33][CA_WORDS]
     int16_t* d_iq;        // [E][N][2]
     int16_t* d_iq2;       // second output buffer for the host streaming pair (allocated on first use)
@@ -244,7 +245,9 @@ __global__ void k_prepare(const gpsiq_chan_desc* __restrict__ desc, int2* __rest
         const double a = fabs(d.gain) * 512.0 + 1.0;
         atomicAdd(&amp_sum[ec / C], a < 40000.0 ? (int) a : 40000);
         // contract of k_synth_line: <= 4 carrier cycles and <= 1 code-period wrap per 1024-sample tile
-        if (!(fabs(d.carr_step) <= 0x1p-8) || !(d.code_step <= 0.5)) atomicOr(&step_flag[ec / C], 1);
+        // (integer carrier: the step is in counts of 2^-25 cycle)
+        const double cmax = (carrier_mode == GPSIQ_CARRIER_FLOAT) ? 0x1p-8 : 0x1p17;
+        if (!(fabs(d.carr_step) <= cmax) || !(d.code_step <= 0.5)) atomicOr(&step_flag[ec / C], 1);
     }
 }
 
@@ -290,7 +293,6 @@ __global__ void k_scan_carrier(const gpsiq_chan_desc* __restrict__ desc, const B
         ginfo[(size_t) g * C + c] = gi;
     }
     double x = carr_state[c];
-    uint32_t u = (uint32_t) x;
     int dummy = 0;
     for (int e = 0; e < E; e++) {
         const gpsiq_chan_desc d = desc[(size_t) e * C + c];
@@ -299,30 +301,79 @@ __global__ void k_scan_carrier(const gpsiq_chan_desc* __restrict__ desc, const B
             info[(size_t) e * C + c] = inf;
         }
         if (d.prn <= 0) {
-            carr_trace[(size_t) e * C + c] = (carrier_mode == GPSIQ_CARRIER_FLOAT) ? x : (double) u;
+            carr_trace[(size_t) e * C + c] = x;
             continue;
         }
-        if (d.flags & GPSIQ_FLAG_RESET_CARRIER) {
-            x = d.carr_phase0;
-            u = (uint32_t) d.carr_phase0;
+        if (d.flags & GPSIQ_FLAG_RESET_CARRIER) x = d.carr_phase0;
+        const BinadeTab tab = tabs[((size_t) e * C + c) * 2 + 1];
+        for (int t = 0; t < ntiles; t++) {
+            carr_ck[((size_t) e * ntiles + t) * C + c] = x;  // (carr_ck = the exact plane)
+            const int len = min(T, N - t * T);
+            nco_advance<NCO_CARRIER>(x, d.carr_step, tab, len, dummy);
         }
-        if (carrier_mode == GPSIQ_CARRIER_FLOAT) {
-            const BinadeTab tab = tabs[((size_t) e * C + c) * 2 + 1];
-            for (int t = 0; t < ntiles; t++) {
-                carr_ck[((size_t) e * ntiles + t) * C + c] = x;  // (carr_ck = the exact plane)
-                const int len = min(T, N - t * T);
-                nco_advance<NCO_CARRIER>(x, d.carr_step, tab, len, dummy);
-            }
-            carr_trace[(size_t) e * C + c] = x;
-        } else {
-            const uint32_t step = (uint32_t) (int32_t) d.carr_step;  // closed form mod 2^32 (plutogpssim.c:2748)
-            for (int t = 0; t < ntiles; t++)
-                carr_ck[((size_t) e * ntiles + t) * C + c] = (double) (u + step * (uint32_t) (t * T));
-            u += step * (uint32_t) N;
-            carr_trace[(size_t) e * C + c] = (double) u;
-        }
+        carr_trace[(size_t) e * C + c] = x;
     }
-    carr_state[c] = (carrier_mode == GPSIQ_CARRIER_FLOAT) ? x : (double) u;
+    carr_state[c] = x;
+}
+
+// ---------------------------------------------------------------------------
+// k_int_carrier: the integer carrier NCO (GPSIQ_CARRIER_INT32; plutogpssim.c:1966-1967, 2675, 2699, 2748).
+// phase += step per sample modulo 2^32 is a closed form, so the whole "chain" is one prefix sum over the
+// batch's epochs per slot: ustart[e][c] = phase at the first sample of epoch e (tile starts follow as
+// ustart + step * n, evaluated where they are needed), trace = phase after every epoch.
+// One warp per slot: the lanes stage the slot's column of steps / re-seeds in shared memory, lane 0 runs
+// the short recurrence.  mode 0 (chain): from carr_state, which it advances.  mode 1 (advance, used by the
+// prepare phase of time-sliced runs): from zero, result to adv[c] with adv[C + c] = 1 if a descriptor re-seeded
+// the slot (adv[c] is then an absolute phase) -- the closed-form hand-off of SURVEY 8e: no ring, a prefix.
+// ---------------------------------------------------------------------------
+#define INTC_MAX_E 2048
+__global__ void __launch_bounds__(32)
+k_int_carrier(const gpsiq_chan_desc* __restrict__ desc, uint32_t* __restrict__ ustart, double* __restrict__ carr_state,
+              double* __restrict__ carr_trace, double* __restrict__ adv, int mode, int E, int C, int N) {
+    __shared__ uint32_t s_step[INTC_MAX_E], s_seed[INTC_MAX_E];
+    __shared__ uint8_t s_kind[INTC_MAX_E];   // 0 inactive, 1 active, 2 active + re-seeded
+    const int c = blockIdx.x, lane = threadIdx.x;
+    if (c >= C) return;
+    uint32_t u = (mode == 0) ? (uint32_t) carr_state[c] : 0u;
+    bool seeded = false;
+    for (int e0 = 0; e0 < E; e0 += INTC_MAX_E) {
+        const int n = min(INTC_MAX_E, E - e0);
+        for (int i = lane; i < n; i += 32) {
+            const gpsiq_chan_desc& d = desc[(size_t) (e0 + i) * C + c];
+            const int prn = d.prn;
+            s_kind[i] = prn <= 0 ? 0 : ((d.flags & GPSIQ_FLAG_RESET_CARRIER) ? 2 : 1);
+            s_step[i] = prn > 0 ? (uint32_t) (int32_t) d.carr_step * (uint32_t) N : 0u;
+            s_seed[i] = prn > 0 ? (uint32_t) d.carr_phase0 : 0u;
+        }
+        __syncwarp();
+        if (lane == 0)
+            for (int i = 0; i < n; i++) {
+                if (s_kind[i] == 2) { u = s_seed[i]; seeded = true; }
+                s_seed[i] = u;                       // (becomes the ustart column)
+                u += s_step[i];
+                s_step[i] = u;                       // (becomes the trace column)
+            }
+        __syncwarp();
+        if (mode == 0)
+            for (int i = lane; i < n; i += 32) {
+                ustart[(size_t) (e0 + i) * C + c] = s_seed[i];
+                carr_trace[(size_t) (e0 + i) * C + c] = (double) s_step[i];
+            }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        if (mode == 0) carr_state[c] = (double) u;
+        else { adv[c] = (double) u; adv[C + c] = seeded ? 1.0 : 0.0; }
+    }
+}
+
+// carr_state <- fold(carr_state, adv) in the integer carrier's arithmetic (exact): skip over a slice synthesized
+// elsewhere.  adv as written by k_int_carrier mode 1.
+__global__ void k_int_fold(double* __restrict__ state, const double* __restrict__ adv, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const uint32_t a = (uint32_t) adv[c];
+    state[c] = (double) ((adv[C + c] != 0.0) ? a : (uint32_t) state[c] + a);
 }
 
 
@@ -613,7 +664,7 @@ k_carr_final(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restri
 __global__ void __launch_bounds__(LANES_WARPS * 32)
 k_synth_lanes(const gpsiq_chan_desc* __restrict__ desc, const int2* __restrict__ lut,
               const double* __restrict__ code_ck, const int* __restrict__ wrap_ck,
-              const CarrLookup carr,
+              const CarrLookup carr, const uint32_t* __restrict__ ustart,
               const uint32_t* __restrict__ ca, const int* __restrict__ amp_sum, const int* __restrict__ step_flag,
               int only_flagged, int16_t* __restrict__ iq, int e0,
               int C, int N, int T, int ntiles, int tile_groups, int carrier_mode) {
@@ -652,11 +703,11 @@ k_synth_lanes(const gpsiq_chan_desc* __restrict__ desc, const int2* __restrict__
         const int w = wrap_ck[o] + d.ms0 % 20;
         kbit = w / 20;
         icode = w - kbit * 20;
-        ph = carr_lookup(carr, e, lane, t, T, N, C, ntiles);
-        uph = (uint32_t) ph;
         cstep = d.code_step;
         pstep = d.carr_step;
         ustep = (uint32_t) (int32_t) d.carr_step;
+        if (carrier_mode == GPSIQ_CARRIER_FLOAT) ph = carr_lookup(carr, e, lane, t, T, N, C, ntiles);
+        else uph = ustart[(size_t) e * C + lane] + ustep * (uint32_t) n0;   // closed form (plutogpssim.c:2748)
         navbits = d.navbits;
     }
     const int2* my_lut = s_lut + (size_t) (active ? lane : 0) * 512;
@@ -735,7 +786,7 @@ static void use_set(gpsiq_ctx* ctx, int i) {
     ctx->d_wrap_ck = ss.d_wrap_ck; ctx->d_carr_ck = ss.d_carr_ck; ctx->d_tab = ss.d_tab; ctx->d_drift = ss.d_drift;
     ctx->d_spec = ss.d_spec; ctx->d_specE = ss.d_specE; ctx->d_cinfo = ss.d_cinfo; ctx->d_info = ss.d_info;
     ctx->d_specG = ss.d_specG; ctx->d_ginfo = ss.d_ginfo; ctx->d_traceG = ss.d_traceG;
-    ctx->d_adv = ss.d_adv; ctx->d_carr_trace = ss.d_carr_trace;
+    ctx->d_adv = ss.d_adv; ctx->d_carr_trace = ss.d_carr_trace; ctx->d_ustart = ss.d_ustart;
     ctx->set_cur = i;
 }
 
@@ -897,9 +948,9 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
     ctx->T = cfg->tile_samples ? cfg->tile_samples : LN_TILE;
     ctx->T = (ctx->T + 31) & ~31;
     ctx->use_line = (cfg->kernel == GPSIQ_KERNEL_AUTO || cfg->kernel == GPSIQ_KERNEL_LINE) && ctx->T == LN_TILE &&
-                    ctx->C <= 32 && cfg->carrier_mode == GPSIQ_CARRIER_FLOAT;
+                    ctx->C <= 32;
     if (cfg->kernel == GPSIQ_KERNEL_LINE && !ctx->use_line)
-        return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_create: the line kernel needs tile_samples 0/1024, max_chan <= 32 and the float carrier",
+        return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_create: the line kernel needs tile_samples 0/1024 and max_chan <= 32",
                     cudaSuccess);
     ctx->ntiles = (ctx->N + ctx->T - 1) / ctx->T;
     CU(cudaSetDevice(cfg->device));
@@ -954,6 +1005,7 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
         }
         CU(cudaMalloc(&ss.d_adv, 2 * ctx->C * sizeof(double)));
         CU(cudaMalloc(&ss.d_carr_trace, EC * sizeof(double)));
+        CU(cudaMalloc(&ss.d_ustart, EC * sizeof(uint32_t)));
         CU(cudaEventCreateWithFlags(&ss.scan_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ss.render_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ss.spec_done, cudaEventDisableTiming));
@@ -1100,7 +1152,7 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
         cudaFree(ss.d_descbuf); cudaFree(ss.d_lut); cudaFree(ss.d_lutp); cudaFree(ss.d_flags); cudaFree(ss.d_code_ck);
         cudaFree(ss.d_wrap_ck); cudaFree(ss.d_carr_ck); cudaFree(ss.d_tab); cudaFree(ss.d_drift); cudaFree(ss.d_spec);
         cudaFree(ss.d_specE); cudaFree(ss.d_cinfo); cudaFree(ss.d_info); cudaFree(ss.d_adv); cudaFree(ss.d_carr_trace);
-        cudaFree(ss.d_specG); cudaFree(ss.d_ginfo); cudaFree(ss.d_traceG);
+        cudaFree(ss.d_specG); cudaFree(ss.d_ginfo); cudaFree(ss.d_traceG); cudaFree(ss.d_ustart);
         if (ss.scan_done) cudaEventDestroy(ss.scan_done);
         if (ss.render_done) cudaEventDestroy(ss.render_done);
         if (ss.spec_done) cudaEventDestroy(ss.spec_done);
@@ -1166,6 +1218,10 @@ static int enqueue_prepare(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int 
         k_slice_advance<<<C, 32, 0, st>>>(ctx->d_drift + 3 * (size_t) ctx->E * C, ctx->d_drift + (size_t) EC, ctx->d_adv, n_epochs, C);
         ctx->launches += 1;
         trace_mark(ctx, st, "k_slice_advance");
+    } else {  // integer carrier: the batch's exact advance per slot (what another slice's owner folds into its state)
+        k_int_carrier<<<C, 32, 0, st>>>(desc_dev, NULL, NULL, NULL, ctx->d_adv, 1, n_epochs, C, N);
+        ctx->launches += 1;
+        trace_mark(ctx, st, "k_int_carrier(adv)");
     }
     ctx->last_epochs = n_epochs;
     CU(cudaGetLastError());
@@ -1233,7 +1289,9 @@ static int enqueue_chain(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_
                                        ctx->d_ginfo, ctx->d_fallbacks, n_epochs, C, N, T, ntiles);
         k_bias_update<<<1, 32, 0, st>>>(ctx->d_adv, ctx->d_carr_start, ctx->d_carr_state, ctx->d_bias_rate, n_epochs, C);
         ctx->launches += 1;
-    } else {  // INT32 carrier (closed form) or the serial float scan (cfg.reserved[0] = 1, cross-check)
+    } else if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_INT32) {  // closed form: one prefix sum over the epochs
+        k_int_carrier<<<C, 32, 0, st>>>(desc_dev, ctx->d_ustart, ctx->d_carr_state, ctx->d_carr_trace, NULL, 0, n_epochs, C, N);
+    } else {  // the serial float scan (cfg.reserved[0] = 1, cross-check)
         k_scan_carrier<<<C, 32, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_carr_ck + 6 * ctx->ck_plane, ctx->d_carr_state,
                                          ctx->d_carr_trace, ctx->d_info + 2 * (size_t) ctx->E * C, ctx->d_ginfo, GROUP_EPOCHS,
                                          n_epochs, C, N, T, ntiles, ctx->cfg.carrier_mode);
@@ -1288,7 +1346,9 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
         ulonglong2* anch = ctx->d_anch[ctx->set_cur];
         CU(cudaMemsetAsync(ctx->d_line_counters, 0, 4 * sizeof(int), st));
         const int warps = n_epochs * C;
-        k_line_anchor<<<(warps + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx),
+        const int intc = ctx->cfg.carrier_mode == GPSIQ_CARRIER_INT32;
+        const uint32_t* ustart = intc ? ctx->d_ustart : NULL;
+        k_line_anchor<<<(warps + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx), ustart,
                                                        ctx->d_flags, ctx->d_flags + ctx->E, anch, ctx->d_hazlist,
                                                        ctx->d_line_counters, ctx->haz_cap, n_epochs, C, N, ntiles, dbg);
         trace_mark(ctx, st, "k_line_anchor");
@@ -1299,11 +1359,11 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
         CU(cudaEventRecord(ctx->ev_P[0], st));
         CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_P[0], 0));
         k_line_patch<<<(dbg & LN_DBG_FORCE_TILE) ? 1024 : 8, 128, 0, ctx->aux_stream>>>(
-            desc_dev, ctx->d_lutp, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx), anch, ctx->d_chips4, ctx->d_hazlist,
+            desc_dev, ctx->d_lutp, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx), ustart, anch, ctx->d_chips4, ctx->d_hazlist,
             ctx->d_line_counters, ctx->haz_cap, ctx->d_patches, ctx->patch_cap, ctx->d_flags + ctx->E, C, N, ntiles);
         CU(cudaEventRecord(ctx->ev_P[1], ctx->aux_stream));
         ctx->launches += 2;
-        if (ctx->set_pending >= 2 && ctx->sets[ctx->set_rd ^ 1].phase >= 2 && ctx->cfg.reserved[0] == 0) {
+        if (ctx->set_pending >= 2 && ctx->sets[ctx->set_rd ^ 1].phase >= 2 && ctx->cfg.reserved[0] == 0 && !intc) {
             // Another batch has been submitted ahead.  Its chunk speculation wants the whole GPU (one chain per
             // thread, as many resident as possible) while the sample kernel below is issue-bound and holds on to
             // the SMs it gets: let the speculation finish first (the anchor kernel above ran beside it); the rest
@@ -1327,7 +1387,7 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
             k_synth_line<<<grid, LN_THREADS, ln_smem_bytes(C), st>>>(
                 desc_dev + (size_t) e0 * C, ctx->d_lutp + (size_t) e0 * C * 512, ctx->d_chips4,
                 anch + (size_t) e0 * ntiles * C, ctx->d_flags + e0, ctx->d_flags + ctx->E + e0,
-                iq_dev + (size_t) e0 * N * 2, ne, C, N, ntiles, ctx->d_err);
+                iq_dev + (size_t) e0 * N * 2, ne, C, N, ntiles, intc, ctx->d_err);
             if (timed) CU(cudaEventRecord(ctx->ev[ctx->ev_count][4], st));
             trace_mark(ctx, st, "k_synth_line");
             ctx->last_ln.desc = desc_dev + (size_t) e0 * C; ctx->last_ln.iq = iq_dev + (size_t) e0 * N * 2;
@@ -1339,7 +1399,7 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
                                             (unsigned long long) (e0 + ne) * N, e0 == 0 ? ctx->d_line_totals : NULL);
             // epochs outside the line kernel's contract (or whose hazard / patch lists overflowed)
             k_synth_lanes<<<ne * tile_groups, LANES_WARPS * 32, smem, st>>>(
-                desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx), ctx->d_ca, ctx->d_flags,
+                desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx), ctx->d_ustart, ctx->d_ca, ctx->d_flags,
                 ctx->d_flags + ctx->E, 1, iq_dev, e0, C, N, T, ntiles, tile_groups, ctx->cfg.carrier_mode);
             ctx->launches += 3;
             if (iq_host) {
@@ -1353,7 +1413,7 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
         CU(cudaEventRecord(ctx->ev_P[0], ctx->aux_stream));   // join: the code scan must be complete
         CU(cudaStreamWaitEvent(st, ctx->ev_P[0], 0));
         k_synth_lanes<<<n_epochs * tile_groups, LANES_WARPS * 32, smem, st>>>(
-            desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx), ctx->d_ca, ctx->d_flags,
+            desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx), ctx->d_ustart, ctx->d_ca, ctx->d_flags,
             ctx->d_flags + ctx->E, 0, iq_dev, 0, C, N, T, ntiles, tile_groups, ctx->cfg.carrier_mode);
         ctx->launches += 1;
         if (iq_host)
@@ -1506,6 +1566,17 @@ int gpsiq_estimate_fold_device(gpsiq_ctx* ctx, const double* advance_dev, void* 
     if (!ctx || !advance_dev) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_estimate_fold_device: bad argument", cudaSuccess);
     CU(cudaSetDevice(ctx->cfg.device));
     k_est_fold<<<1, 32, 0, (cudaStream_t) stream>>>(ctx->d_est_state, advance_dev, ctx->C);
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    return GPSIQ_OK;
+}
+
+int gpsiq_carrier_fold_device(gpsiq_ctx* ctx, const double* advance_dev, void* stream) {
+    if (!ctx || !advance_dev) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_carrier_fold_device: bad argument", cudaSuccess);
+    if (ctx->cfg.carrier_mode != GPSIQ_CARRIER_INT32)
+        return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_carrier_fold_device: only the integer carrier has a closed-form advance", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    k_int_fold<<<1, 32, 0, (cudaStream_t) stream>>>(ctx->d_carr_state, advance_dev, ctx->C);
     ctx->launches += 1;
     CU(cudaGetLastError());
     return GPSIQ_OK;
@@ -1744,7 +1815,7 @@ int gpsiq_timing_sample_kernel_isolated(gpsiq_ctx* ctx, int reps, float* kernel_
         k_synth_line<<<grid, LN_THREADS, ln_smem_bytes(C), ctx->stream>>>(
             ctx->last_ln.desc, ctx->d_lutp + (size_t) le0 * C * 512, ctx->d_chips4,
             ctx->d_anch[ctx->last_ln.set] + (size_t) le0 * ntiles * C, ctx->d_flags + le0, ctx->d_flags + ctx->E + le0,
-            ctx->last_ln.iq, ne, C, N, ntiles, ctx->d_err);
+            ctx->last_ln.iq, ne, C, N, ntiles, ctx->cfg.carrier_mode == GPSIQ_CARRIER_INT32, ctx->d_err);
     }
     CU(cudaEventRecord(e1, ctx->stream));
     CU(cudaEventSynchronize(e1));

@@ -76,6 +76,16 @@ GPSIQ_HD void ln_kernel_index(uint64_t aF, uint64_t aG, uint64_t dF, uint64_t dG
     gi = (uint32_t) (Y >> (LN_GBITS - LN_YSH));
 }
 
+// Integer carrier NCO (GPSIQ_CARRIER_INT32; the reference's #else branches, plutogpssim.c:2699, 2748): the phase is
+// a uint32 with 2^25 counts per cycle (index = bits 24:16), advanced by an integer step per sample -- EXACTLY a
+// line.  F = u << 39 puts the index into bits 63:55 like the float carrier's F, the counts above bit 24 fall off
+// the top (the reference masks them, & 0x1ff), and the low 39 bits of F and dF are zero, so both split-word
+// truncations are exact: this carrier needs no hazard test, no scan and no patch.
+GPSIQ_HD uint64_t ln_int_fixed(uint32_t u) { return (uint64_t) u << 39; }
+GPSIQ_HD uint64_t ln_carr_slope_mode(double carr_step, int int_carrier) {
+    return int_carrier ? (uint64_t) (int64_t) (int32_t) carr_step << 39 : ln_carr_slope(carr_step);
+}
+
 // ---- k_line_anchor ---------------------------------------------------------------
 // One warp per (epoch, slot).  Pass 1, chunk by chunk (32 tiles, lane = tile): the tile anchors
 //   anch[(e*ntiles + t)*C + c] = { F (carrier), G (code) + variant offset }
@@ -86,11 +96,15 @@ GPSIQ_HD void ln_kernel_index(uint64_t aF, uint64_t aG, uint64_t dF, uint64_t dG
 struct LineTile { uint64_t FA, GA, Fs, Gs; };
 
 __device__ __forceinline__ LineTile ln_tile_anchor(const gpsiq_chan_desc& d, const double* __restrict__ code_ck,
-                                                   const int* __restrict__ wrap_ck, const CarrLookup& carr, int e, int c,
+                                                   const int* __restrict__ wrap_ck, const CarrLookup& carr,
+                                                   const uint32_t* __restrict__ ustart, int e, int c,
                                                    int t, int C, int N, int ntiles, int dbg) {
     LineTile r;
     const size_t o = ((size_t) e * ntiles + t) * C + c;
-    r.FA = ln_carr_fixed(carr_lookup(carr, e, c, t, LN_TILE, N, C, ntiles));
+    if (ustart)  // integer carrier: closed form from the epoch's start phase
+        r.FA = ln_int_fixed(ustart[(size_t) e * C + c] + (uint32_t) (int32_t) d.carr_step * (uint32_t) (t * LN_TILE));
+    else
+        r.FA = ln_carr_fixed(carr_lookup(carr, e, c, t, LN_TILE, N, C, ntiles));
     r.GA = ln_code_fixed(code_ck[o]);
     // NAV polarity at the tile start and after the next code-period wrap (plutogpssim.c:2714-2733)
     const int wr = wrap_ck[o] + d.ms0 % 20;
@@ -104,7 +118,8 @@ __device__ __forceinline__ LineTile ln_tile_anchor(const gpsiq_chan_desc& d, con
 
 __global__ void __launch_bounds__(128)
 k_line_anchor(const gpsiq_chan_desc* __restrict__ desc, const double* __restrict__ code_ck,
-              const int* __restrict__ wrap_ck, const CarrLookup carr, const int* __restrict__ amp_sum,
+              const int* __restrict__ wrap_ck, const CarrLookup carr, const uint32_t* __restrict__ ustart,
+              const int* __restrict__ amp_sum,
               int* __restrict__ step_flag, ulonglong2* __restrict__ anch, uint32_t* __restrict__ hazlist,
               int* __restrict__ counters, int haz_cap, int E, int C, int N, int ntiles, int dbg) {
     const int lane = threadIdx.x & 31;
@@ -117,7 +132,8 @@ k_line_anchor(const gpsiq_chan_desc* __restrict__ desc, const double* __restrict
         for (int t = lane; t < ntiles; t += 32) anch[((size_t) e * ntiles + t) * C + c] = make_ulonglong2(0, 0);
         return;
     }
-    const uint64_t dF = ln_carr_slope(d.carr_step), dG = ln_code_slope(d.code_step);
+    const bool int_carrier = ustart != nullptr;  // exact line: the carrier half of the check is skipped
+    const uint64_t dF = ln_carr_slope_mode(d.carr_step, int_carrier), dG = ln_code_slope(d.code_step);
     const uint64_t gmask = (1ULL << LN_GBITS) - 1;
     const int64_t eF = ln_eps(1, LN_TILE), eG = ln_eps(0, LN_TILE);
     const bool force = (dbg & (LN_DBG_FORCE_CHUNK | LN_DBG_FORCE_TILE)) != 0;
@@ -131,7 +147,7 @@ k_line_anchor(const gpsiq_chan_desc* __restrict__ desc, const double* __restrict
             LineTile a;
             a.FA = a.GA = a.Fs = a.Gs = 0;
             if (valid) {
-                a = ln_tile_anchor(d, code_ck, wrap_ck, carr, e, c, t, C, N, ntiles, dbg);
+                a = ln_tile_anchor(d, code_ck, wrap_ck, carr, ustart, e, c, t, C, N, ntiles, dbg);
                 anch[((size_t) e * ntiles + t) * C + c] = make_ulonglong2(a.Fs, a.Gs);
             }
             const uint64_t F0 = __shfl_sync(0xffffffffu, a.FA, 0), G0 = __shfl_sync(0xffffffffu, a.GA, 0);
@@ -155,7 +171,7 @@ k_line_anchor(const gpsiq_chan_desc* __restrict__ desc, const double* __restrict
         const int j = lane & 15;
         if (j < nch && !force) {
             const int n_chunk = min(LN_CHUNK * LN_TILE, N - (ch0 + j) * LN_CHUNK * LN_TILE);
-            hz = (lane < 16) ? line_hazard(my_A, dF, LN_FBITS, (uint64_t) n_chunk, my_lo, my_hi)
+            hz = (lane < 16) ? (!int_carrier && line_hazard(my_A, dF, LN_FBITS, (uint64_t) n_chunk, my_lo, my_hi))
                              : line_hazard(my_A, dG, LN_GBITS, (uint64_t) n_chunk, my_lo, my_hi);
         }
         uint32_t flagged = __ballot_sync(0xffffffffu, hz);
@@ -168,9 +184,10 @@ k_line_anchor(const gpsiq_chan_desc* __restrict__ desc, const double* __restrict
             flagged &= flagged - 1;
             const int t = (ch0 + jj) * LN_CHUNK + lane;
             if (t >= ntiles) continue;
-            const LineTile a = ln_tile_anchor(d, code_ck, wrap_ck, carr, e, c, t, C, N, ntiles, dbg);
+            const LineTile a = ln_tile_anchor(d, code_ck, wrap_ck, carr, ustart, e, c, t, C, N, ntiles, dbg);
             const int len = min(LN_TILE, N - t * LN_TILE);
-            const bool hzt = (dbg & LN_DBG_FORCE_TILE) || line_hazard(a.FA, dF, LN_FBITS, (uint64_t) len, -eF - LN_KF, eF) ||
+            const bool hzt = (dbg & LN_DBG_FORCE_TILE) ||
+                             (!int_carrier && line_hazard(a.FA, dF, LN_FBITS, (uint64_t) len, -eF - LN_KF, eF)) ||
                              line_hazard(a.GA, dG, LN_GBITS, (uint64_t) len, -eG - LN_KG, eG);
             if (hzt) {
                 const int slot = atomicAdd(&counters[0], 1);
@@ -187,6 +204,7 @@ k_line_anchor(const gpsiq_chan_desc* __restrict__ desc, const double* __restrict
 __global__ void __launch_bounds__(128)
 k_line_patch(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict__ lutp,
              const double* __restrict__ code_ck, const int* __restrict__ wrap_ck, const CarrLookup carr,
+             const uint32_t* __restrict__ ustart,
              const ulonglong2* __restrict__ anch, const int8_t* __restrict__ chips4,
              const uint32_t* __restrict__ hazlist, int* __restrict__ counters, int haz_cap,
              LinePatch* __restrict__ patches, int patch_cap, int* __restrict__ step_flag, int C, int N, int ntiles) {
@@ -201,17 +219,21 @@ k_line_patch(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
         const size_t o = ((size_t) e * ntiles + t) * C + c;
         const int len = min(LN_TILE, N - t * LN_TILE);
         double cp = code_ck[o];
-        double ph = carr_lookup(carr, e, c, t, LN_TILE, N, C, ntiles);
+        const bool int_carrier = ustart != nullptr;
+        double ph = int_carrier ? 0.0 : carr_lookup(carr, e, c, t, LN_TILE, N, C, ntiles);
+        const uint32_t ustep = (uint32_t) (int32_t) d.carr_step;
+        uint32_t u = int_carrier ? ustart[ec] + ustep * (uint32_t) (t * LN_TILE) : 0u;
         const int wr = wrap_ck[o] + d.ms0 % 20;
         int kbit = wr / 20, icode = wr - kbit * 20;
         const ulonglong2 a = anch[o];
-        const uint64_t dF = ln_carr_slope(d.carr_step), dG = ln_code_slope(d.code_step);
+        const uint64_t dF = ln_carr_slope_mode(d.carr_step, int_carrier), dG = ln_code_slope(d.code_step);
         const int32_t* lut = lutp + ec * 512;
         const int8_t* chipv = chips4 + (size_t) d.prn * 4 * LN_VS;  // variants of this PRN
         const int8_t* chip0 = chips4 + (size_t) d.prn * 4 * LN_VS;  // variant 0 = polarity (0,0): +1 iff chip == 0
         for (int n = 0; n < len; n++) {
             // exact (plutogpssim.c:2697, 2701-2702, 2732, 2737)
-            const int it = min(__double2int_rd(__dmul_rn(ph, 512.0)), 511);
+            const int it = int_carrier ? (int) ((u >> 16) & 0x1ff)   // plutogpssim.c:2699
+                                       : min(__double2int_rd(__dmul_rn(ph, 512.0)), 511);
             const int chipi = __double2int_rz(cp);
             const int chipbit = chip0[chipi] > 0 ? 0 : 1;
             const int nav = (int) (d.navbits >> (kbit & 63)) & 1;
@@ -231,7 +253,8 @@ k_line_patch(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
             }
             int wdummy = 0;
             if (nco_step<NCO_CODE>(cp, d.code_step, wdummy)) { if (++icode >= 20) { icode = 0; kbit++; } }
-            nco_step<NCO_CARRIER>(ph, d.carr_step, wdummy);
+            if (int_carrier) u += ustep;                             // plutogpssim.c:2748
+            else nco_step<NCO_CARRIER>(ph, d.carr_step, wdummy);
         }
     }
 }
@@ -321,7 +344,7 @@ __global__ void __maxnreg__(48)
 k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict__ lutp,
              const int8_t* __restrict__ chips4, const ulonglong2* __restrict__ anch,
              const int* __restrict__ amp_sum, const int* __restrict__ step_flag, int16_t* __restrict__ iq,
-             int E, int C, int N, int ntiles, int* __restrict__ err) {
+             int E, int C, int N, int ntiles, int int_carrier, int* __restrict__ err) {
     extern __shared__ __align__(16) unsigned char ln_raw[];
     const int CG = ln_group_slots(C), ngroups = ln_groups(C);
     int8_t* s_chip = (int8_t*) ln_raw;                                   // [CG][4][LN_VS]
@@ -397,7 +420,7 @@ k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
                         const int prn = de[c0 + threadIdx.x].prn;
                         if (prn > 0 && prn <= 32) {
                             s_prn[threadIdx.x] = prn;
-                            st.x = ln_carr_slope(de[c0 + threadIdx.x].carr_step);
+                            st.x = ln_carr_slope_mode(de[c0 + threadIdx.x].carr_step, int_carrier);
                             st.y = ln_code_slope(de[c0 + threadIdx.x].code_step);  // > 0 for every active slot
                         }
                     }

@@ -195,6 +195,10 @@ class Synthesizer:
     def estimate_fold_device(self, advance_dev_ptr, stream_ptr=None):
         capi.check(capi.lib.gpsiq_estimate_fold_device(self._ctx, advance_dev_ptr, stream_ptr), self._ctx)
 
+    def carrier_fold_device(self, advance_dev_ptr, stream_ptr=None):
+        """Integer carrier only: exact carrier state <- fold(state, advance of a slice synthesized elsewhere)."""
+        capi.check(capi.lib.gpsiq_carrier_fold_device(self._ctx, advance_dev_ptr, stream_ptr), self._ctx)
+
     def estimate_anchor_device(self, stream_ptr=None):
         capi.check(capi.lib.gpsiq_estimate_anchor_device(self._ctx, stream_ptr), self._ctx)
 
