@@ -89,6 +89,9 @@ class GpuSliceEngine:
     def estimate_fold(self, adv):
         self.s.estimate_fold_device(adv.data_ptr(), self._stream())
 
+    def carrier_fold(self, adv):       # integer carrier: exact state <- fold(state, advance of a foreign slice)
+        self.s.carrier_fold_device(adv.data_ptr(), self._stream())
+
     def estimate_anchor(self):         # estimate <- exact carrier state
         self.s.estimate_anchor_device(self._stream())
 
@@ -98,8 +101,24 @@ class GpuSliceEngine:
     def chain(self, desc_dev, n_epochs):
         self.s.chain_device(desc_dev.data_ptr(), n_epochs, self._stream())
 
-    def render(self, desc_dev, n_epochs, out_dev):
-        self.s.render_device(desc_dev.data_ptr(), n_epochs, out_dev.data_ptr(), self._stream())
+    def render(self, desc_dev, n_epochs, out):
+        """out: a CUDA tensor (asynchronous, on the current stream) or a HOST address (int; pinned memory from
+        gpsiq_host_alloc): then the slice goes through the host-buffer call gpsiq_fetch -- rendered in sub-batches
+        whose device-to-host copies overlap the rendering, blocking until the host buffer is complete."""
+        if isinstance(out, int):
+            self.s.fetch_ptr(out)
+        else:
+            self.s.render_device(desc_dev.data_ptr(), n_epochs, out.data_ptr(), self._stream())
+
+    def upload(self, desc_host, index):
+        """Pinned host descriptors (uint8 tensor) -> device staging buffer (two, alternating), on the current stream.
+        A staging buffer is reused two slices later; the host-buffer render of the slice that used it has returned
+        by then (gpsiq_fetch blocks)."""
+        if not hasattr(self, "_stage"):
+            self._stage = [torch.empty(self.s.max_epochs * self.s.max_chan * 64, dtype=torch.uint8, device="cuda") for _ in range(2)]
+        d = self._stage[index & 1][: desc_host.numel()]
+        d.copy_(desc_host, non_blocking=True)
+        return d
 
     # ---- SM-free hand-off (gpsiq_mailbox_*): the sender's copy engine writes the carrier state into the next
     # rank's mailbox over NVLink peer memory and a stream memory operation publishes a sequence number; the
@@ -157,9 +176,14 @@ class TimeSliceRunner:
         self.prev_adv = None
         self.deferred = deferred_render
         self.pending = None
-        if handoff not in ("nccl", "mailbox"):
-            raise ValueError("handoff must be 'nccl' or 'mailbox'")
+        if handoff not in ("nccl", "mailbox", "prefix"):
+            raise ValueError("handoff must be 'nccl', 'mailbox' or 'prefix'")
         self.mailbox = handoff == "mailbox" and self.world > 1
+        # "prefix": the integer carrier NCO (GPSIQ_CARRIER_INT32; plutogpssim.c:2748) advances in closed form, so
+        # there is no ring at all: one all_gather of the slices' exact advances per step, and every rank folds the
+        # advances of the slices before its own into its carrier state (and the ones after it afterwards, so that
+        # all ranks hold the phase at the start of the next step).  SURVEY 8e: "truly parallel".
+        self.prefix = handoff == "prefix"
 
     def step(self, desc, n_epochs, out):
         """Synthesize this rank's slice of the next step.
@@ -171,6 +195,8 @@ class TimeSliceRunner:
         eng, r, n = self.engine, self.rank, self.world
         ctx = eng.scan_context(self.step_index == 0) if hasattr(eng, "scan_context") else contextlib.nullcontext()
         with ctx:
+            if isinstance(desc, torch.Tensor) and desc.device.type == "cpu" and hasattr(eng, "upload"):
+                desc = eng.upload(desc, self.step_index)        # host descriptors: H2D on the scan stream
             self._scan_phases(desc, n_epochs)
         if self.deferred:
             if self.pending is not None:
@@ -182,6 +208,19 @@ class TimeSliceRunner:
 
     def _scan_phases(self, desc, n_epochs):
         eng, r, n = self.engine, self.rank, self.world
+        if self.prefix:
+            eng.prepare(desc, n_epochs)
+            adv_all = [eng.adv]
+            if n > 1:
+                adv_all = [torch.empty_like(eng.adv) for _ in range(n)]
+                dist.all_gather(adv_all, eng.adv)
+            for a in adv_all[:r]:
+                eng.carrier_fold(a)
+            eng.speculate(desc, n_epochs)                       # (integer carrier: the code-NCO scan only)
+            eng.chain(desc, n_epochs)
+            for a in adv_all[r + 1:]:
+                eng.carrier_fold(a)
+            return
         have_exact = False
         if n > 1 and r == 0 and self.step_index > 0:            # close the previous step's ring first
             if self.mailbox:
@@ -227,7 +266,7 @@ class TimeSliceRunner:
         if self.pending is not None:
             self.engine.render(*self.pending)
             self.pending = None
-        if self.world > 1 and self.rank == 0 and self.step_index > 0:
+        if self.world > 1 and self.rank == 0 and self.step_index > 0 and not self.prefix:
             eng = self.engine
             ctx = eng.scan_context() if hasattr(eng, "scan_context") else contextlib.nullcontext()
             with ctx:

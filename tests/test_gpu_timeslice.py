@@ -21,20 +21,21 @@ STEPS = 9
 CIRCLE = os.path.join(ol.ORACLE_DIR, "_ref", "circle.csv")
 
 
-def _worker(rank, world, port, outdir, deferred=False, handoff="nccl", feed="golden"):
+def _worker(rank, world, port, outdir, deferred=False, handoff="nccl", feed="golden", golden="circle12"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from pluto_gps_sim_b200 import Synthesizer
     from pluto_gps_sim_b200.timeslice import GpuSliceEngine, TimeSliceRunner
 
-    desc = ol.load_golden_desc("circle12")
+    desc = ol.load_golden_desc(golden)
+    carrier_mode = 1 if handoff == "prefix" else 0
     feeder = None
     if feed == "navfile":   # every rank computes ONLY its own slices' descriptors from the navigation file (gpshost_skip)
         from pluto_gps_sim_b200 import hostapi
         feeder = hostapi.SliceFeeder(rank, world, E, nav=os.path.join(ol.GOLDEN, "brdc3540_synth.14n.gz"), motion=CIRCLE,
                                      sample_rate=2600000)
-    synth = Synthesizer(max_chan=12, max_epochs=E, device=rank)
+    synth = Synthesizer(max_chan=12, max_epochs=E, device=rank, carrier_mode=carrier_mode)
     engine = GpuSliceEngine(synth)
     if handoff == "mailbox":
         assert engine.mailbox_setup(rank, world)
@@ -75,6 +76,22 @@ def test_two_gpu_time_slices_match_reference(tmp_path, deferred, handoff):
     # the estimates handed around the ring are good enough that the serial fallback stays rare
     fb = sum(int(np.load(tmp_path / ("fb%d.npy" % r))[0]) for r in range(world))
     assert fb < world * STEPS * E * 12 // 10, fb
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("deferred", [False, True])
+def test_two_gpu_integer_carrier_slices_without_a_ring(tmp_path, deferred):
+    """GPSIQ_CARRIER_INT32: closed-form prefix hand-off (all_gather of the slices' exact advances), against the
+    stream of the reference built without FLOAT_CARR_PHASE, across the 30 s re-allocation."""
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(world, port, str(tmp_path), deferred, "prefix", "golden", "circle12int"), nprocs=world, join=True)
+    meta = ol.load_golden_meta("circle12int")
+    parts = [np.load(tmp_path / ("sums%d.npy" % r)) for r in range(world)]
+    got = np.concatenate([parts[r][s] for s in range(STEPS) for r in range(world)])
+    assert [int(x) for x in got] == meta["epoch_checksums"][: world * STEPS * E]
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2 or not os.path.exists(CIRCLE), reason="needs 2 GPUs and oracle/_ref/circle.csv")

@@ -23,8 +23,8 @@ STEPS = 3
 class OracleEngine:
     """Same interface as timeslice.GpuSliceEngine, arithmetic by the oracle."""
 
-    def __init__(self, max_chan, rank=0, world=1, n=N):
-        self.rank, self.world, self.n = rank, world, n
+    def __init__(self, max_chan, rank=0, world=1, n=N, carrier_mode=0):
+        self.rank, self.world, self.n, self.mode = rank, world, n, carrier_mode
         self.phase = torch.zeros(max_chan, dtype=torch.float64)
         self.adv = torch.zeros(2 * max_chan, dtype=torch.float64)
         self.state = np.zeros(max_chan)
@@ -33,6 +33,18 @@ class OracleEngine:
 
     def prepare(self, desc, n_epochs):        # closed-form advance of the slice (estimates only)
         d = desc[:n_epochs]
+        if self.mode == 1:                     # integer carrier: the EXACT advance (what k_int_carrier mode 1 computes)
+            Cn = d.shape[1]
+            for c in range(Cn):
+                u, seeded = 0, False
+                for e in range(n_epochs):
+                    if d[e, c]["prn"] <= 0:
+                        continue
+                    if d[e, c]["flags"] & 1:
+                        u, seeded = int(d[e, c]["carr_phase0"]), True
+                    u = (u + int(d[e, c]["carr_step"]) * self.n) % 2 ** 32
+                self.adv[c], self.adv[Cn + c] = float(u), float(seeded)
+            return
         self.adv[: d.shape[1]] = torch.from_numpy(np.mod((d["carr_step"] * self.n).sum(axis=0), 1.0))
         self.adv[d.shape[1]:] = torch.from_numpy(((d["flags"] & 1) != 0).any(axis=0).astype(np.float64))
 
@@ -41,6 +53,11 @@ class OracleEngine:
 
     def estimate_anchor(self):
         pass
+
+    def carrier_fold(self, adv):
+        Cn = self.state.size
+        a, f = adv[:Cn].numpy(), adv[Cn:].numpy()
+        self.state[:] = np.where(f != 0, a, np.mod(self.state + a, 2.0 ** 32))
 
     def speculate(self, desc, n_epochs):
         pass
@@ -64,14 +81,14 @@ class OracleEngine:
         self.state[:] = buf[1:].numpy()
 
     def chain(self, desc, n_epochs):          # advances the carrier state (and keeps the samples for render)
-        self.pending, _ = ol.oracle_synth(desc[:n_epochs], self.n, carr_state=self.state)
+        self.pending, _ = ol.oracle_synth(desc[:n_epochs], self.n, carrier_mode=self.mode, carr_state=self.state)
 
     def render(self, desc, n_epochs, out):
         out[...] = self.pending
 
 
-def _stream_desc(world):
-    d = ol.load_golden_desc("static12")
+def _stream_desc(world, name="static12"):
+    d = ol.load_golden_desc(name)
     d = np.concatenate([d, d])[: world * STEPS * E].copy()
     d["flags"] = 0
     d[0]["flags"] = 1
@@ -115,6 +132,48 @@ def test_time_slices_equal_sequential_stream(tmp_path, WORLD, handoff):
     assert np.array_equal(got, want)
     # rank 0 ends up holding the phases after the very last slice (ready for the next step)
     assert np.array_equal(np.load(tmp_path / "final_phase.npy"), st)
+
+
+# ---- integer carrier: closed-form prefix instead of a ring ------------------------------------------------------
+def _prefix_worker(rank, WORLD, port, outdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    from pluto_gps_sim_b200.timeslice import TimeSliceRunner
+
+    desc = _stream_desc(WORLD, "circle12int")
+    desc[WORLD * E + 1]["flags"][3] |= 1      # a slot re-seeded in the middle of a slice: its advance is absolute
+    eng = OracleEngine(desc.shape[1], rank, WORLD, carrier_mode=1)
+    runner = TimeSliceRunner(eng, rank, WORLD, handoff="prefix")
+    outs = []
+    for s in range(STEPS):
+        first = (s * WORLD + rank) * E
+        out = np.zeros((E, N, 2), np.int16)
+        runner.step(desc[first:first + E], E, out)
+        outs.append(out)
+    runner.finish()
+    np.save(os.path.join(outdir, "rank%d.npy" % rank), np.stack(outs))
+    np.save(os.path.join(outdir, "final_phase%d.npy" % rank), eng.state)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("WORLD", [2, 3])
+def test_integer_carrier_slices_need_no_ring(tmp_path, WORLD):
+    """GPSIQ_CARRIER_INT32 (plutogpssim.c:2748): the per-slice advance is exact modulo 2^32, so the hand-off is an
+    all_gather + local prefix; the slices still concatenate to the sequential stream, and EVERY rank ends up with
+    the phases after the last slice."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_prefix_worker, args=(WORLD, port, str(tmp_path)), nprocs=WORLD, join=True)
+    desc = _stream_desc(WORLD, "circle12int")
+    desc[WORLD * E + 1]["flags"][3] |= 1
+    st = np.zeros(desc.shape[1])
+    want, _ = ol.oracle_synth(desc, N, carrier_mode=1, carr_state=st)
+    parts = [np.load(tmp_path / ("rank%d.npy" % r)) for r in range(WORLD)]
+    got = np.concatenate([parts[r][s] for s in range(STEPS) for r in range(WORLD)])
+    assert np.array_equal(got, want)
+    for r in range(WORLD):
+        assert np.array_equal(np.load(tmp_path / ("final_phase%d.npy" % r)), st)
 
 
 # ---- the whole host side, per rank, from the navigation file ---------------------------------------------------
