@@ -78,22 +78,29 @@ struct TraceRec { cudaEvent_t ev; const char* label; int stream_id; };
 
 // Everything the scan phases produce for one batch and the render phase consumes.  There are two
 // sets so that gpsiq_submit_device can scan batch k+1 while gpsiq_fetch_device renders batch k;
-// the working pointers in gpsiq_ctx (d_lut, d_tab, ...) are switched to one set before enqueuing.
+// the working pointers in gpsiq_ctx (d_lut, d_carr_ck, ...) are switched to one set before enqueuing.
 struct ScanSet {
     gpsiq_chan_desc* d_descbuf;
     int2* d_lut; int32_t* d_lutp; int* d_flags; double* d_code_ck; int* d_wrap_ck; double* d_carr_ck;
-    BinadeTab* d_tab; double* d_drift; CarrSpec* d_spec; CarrSpec* d_specE; ChunkInfo* d_cinfo; CarrInfo* d_info;
+    double* d_drift; CarrSpec* d_spec; CarrSpec* d_specE; ChunkInfo* d_cinfo; CarrInfo* d_info;
     CarrSpec* d_specG; GroupInfo* d_ginfo; double* d_traceG;
     double* d_adv; double* d_carr_trace; uint32_t* d_ustart;
-    cudaEvent_t scan_done, render_done, spec_done;
+    double* d_est;                // [C] estimated phases at the first sample of the batch (pipelined submits)
+    double* d_exact_end;          // [C] exact phases after the batch's last sample (once its chain has run)
+    cudaStream_t stream;          // pipelined submits: each set scans on its own stream, so that the scans of
+                                  // consecutive batches overlap (only the exact chain is ordered batch after batch)
+    cudaEvent_t scan_done, render_done, spec_done, adv_done, est_done;
+    long long seq;                // number of the batch the set holds (-1: none yet)
     const gpsiq_chan_desc* desc;  // the batch's descriptors (device)
     int n_epochs;
     int phase;                    // 0 free, 1 prepared, 2 speculated, 3 chained (waiting to be rendered)
 };
 
+#define NSETS 3   // scan sets: gpsiq_submit* may run NSETS - 1 batches ahead of the one being rendered
+
 struct gpsiq_ctx {
     gpsiq_config cfg;
-    ScanSet sets[2];
+    ScanSet sets[NSETS];
     int set_wr, set_rd, set_pending;  // submit/fetch ring
     int set_cur;                      // set the working pointers currently point at
     cudaStream_t scan_stream;         // gpsiq_submit_device scans here, ahead of the caller's render stream
@@ -126,7 +133,7 @@ struct gpsiq_ctx {
     int line_grid_cap;    // GPSIQ_OPT_LINE_GRID_CAP: most CTAs of one k_synth_line launch (0: one CTA per unit)
     int use_line;         // k_synth_line (the production kernel) is eligible for this configuration
     int8_t* d_chips4;     // [33][4][LN_VS] +-1: chip/NAV sign tables in 4 polarity variants, extended past chip 1022
-    ulonglong2* d_anch[2];   // [E][ntiles][C] tile anchors {F, G} (one buffer per scan set)
+    ulonglong2* d_anch[NSETS];   // [E][ntiles][C] tile anchors {F, G} (one buffer per scan set)
     uint32_t* d_hazlist;  // (tile, slot) pairs k_line_anchor could not clear
     int haz_cap, patch_cap;
     int* d_line_counters; // [0] listed hazards, [1] patches, [2] flagged chunks (per batch)
@@ -137,7 +144,6 @@ struct gpsiq_ctx {
     int* d_wrap_ck;       // [E][ntiles][C]
     double* d_carr_ck;    // [5][E][ntiles][C] planes: 0,1 chunk speculation (parity variants), 2,3 stitched epoch-level
                           // trajectory P (variants), 4 exact (chain heads / fallbacks; INT32 mode: uint32 phase as double)
-    BinadeTab* d_tab;     // [E][C][2]  (0 = code NCO, 1 = carrier NCO)
     double* d_drift;      // [E][C] estimate aids only: closed-form phase advance of each epoch incl. predicted
                           // rounding drift (eadv), then [E][C] re-seed phase or -1 (ereset), then [E][C] the
                           // estimated phase at the start of each epoch (est_epoch)
@@ -159,7 +165,11 @@ struct gpsiq_ctx {
     uint32_t* d_ca;       // [33][CA_WORDS]
     int16_t* d_iq;        // [E][N][2]
     int16_t* d_iq2;       // second output buffer for the host streaming pair (allocated on first use)
-    gpsiq_chan_desc* h_stage[2];  // pinned staging of submitted host descriptors
+    gpsiq_chan_desc* h_stage[NSETS];
+    long long seq;                // batches begun so far
+    cudaEvent_t ev_final;         // the last exact chain enqueued (on any stream) has run
+    int fetch_count;              // host fetches so far (alternates the two device output buffers)
+    int render_waits_spec;        // see enqueue_render  // pinned staging of submitted host descriptors
     unsigned long long* d_sums;
     int* d_err;
     int last_epochs;
@@ -175,7 +185,7 @@ static void trace_mark(gpsiq_ctx* ctx, cudaStream_t st, const char* label) {
     TraceRec& r = ctx->trace[ctx->trace_n];
     if (!r.ev) cudaEventCreate(&r.ev);
     r.label = label;
-    r.stream_id = (st == ctx->scan_stream) ? 1 : (st == ctx->aux2_stream) ? 2 : (st == ctx->aux_stream) ? 3 : (st == ctx->copy_stream) ? 4 : 0;
+    r.stream_id = (st == ctx->sets[0].stream) ? 10 : (st == ctx->sets[1].stream) ? 11 : (st == ctx->sets[2].stream) ? 12 : (st == ctx->scan_stream) ? 1 : (st == ctx->aux2_stream) ? 2 : (st == ctx->aux_stream) ? 3 : (st == ctx->copy_stream) ? 4 : 0;
     cudaEventRecord(r.ev, st);
     ctx->trace_n++;
 }
@@ -202,7 +212,7 @@ static int fail(gpsiq_ctx* ctx, int code, const char* what, cudaError_t ce) {
 // k_prepare: amplitude LUT per (epoch, slot)
 // ---------------------------------------------------------------------------
 __global__ void k_prepare(const gpsiq_chan_desc* __restrict__ desc, int2* __restrict__ lut,
-                          int32_t* __restrict__ lutp, BinadeTab* __restrict__ tab, double* __restrict__ drift,
+                          int32_t* __restrict__ lutp, double* __restrict__ drift,
                           int* __restrict__ amp_sum, int* __restrict__ step_flag, int C, int N, int carrier_mode,
                           const double* __restrict__ bias_rate, double* __restrict__ eadv_frac, int* __restrict__ err) {
     const int ec = blockIdx.x;
@@ -212,12 +222,8 @@ __global__ void k_prepare(const gpsiq_chan_desc* __restrict__ desc, int2* __rest
         if (threadIdx.x == 0) { drift[ec] = 0.0; drift[(size_t) gridDim.x + ec] = -1.0; eadv_frac[ec] = 0.0; }
         return;
     }
-    // per-binade fixed-point increments of the two NCOs for this epoch's steps (nco_scan.cuh)
-    if (threadIdx.x == 0) build_binade_tab<NCO_CODE>(d.code_step, tab[(size_t) ec * 2]);
     if (threadIdx.x == 32 && carrier_mode == GPSIQ_CARRIER_FLOAT) {
-        BinadeTab& tp = tab[(size_t) ec * 2 + 1];
-        build_binade_tab<NCO_CARRIER>(d.carr_step, tp);
-        const double dest = carr_drift_estimate(d.carr_step, tp, N);
+        const double dest = carr_drift_estimate(d.carr_step, step_info(d.carr_step), N);
         drift[ec] = fma((double) N, d.carr_step, dest);   // eadv: whole-epoch advance in cycles (chunk interpolation)
         // The same advance modulo one cycle, to full precision: N*step is ~300 cycles, so its double carries only
         // ~5e-14 of absolute precision -- more than the per-epoch corrections that matter here.  Split the product
@@ -254,7 +260,7 @@ __global__ void k_prepare(const gpsiq_chan_desc* __restrict__ desc, int2* __rest
 // ---------------------------------------------------------------------------
 // k_scan_code: exact code phase + wrap count at every tile start
 // ---------------------------------------------------------------------------
-__global__ void k_scan_code(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
+__global__ void k_scan_code(const gpsiq_chan_desc* __restrict__ desc,
                             double* __restrict__ code_ck, int* __restrict__ wrap_ck, int EC, int C, int N, int T,
                             int ntiles) {
     // one chain per thread; the lanes of a warp hold the same slot for 32 consecutive epochs (same
@@ -268,7 +274,7 @@ __global__ void k_scan_code(const gpsiq_chan_desc* __restrict__ desc, const Bina
     if (d.prn <= 0) return;
     double x = d.code_phase0;
     int wraps = 0;
-    const BinadeTab tab = tabs[(size_t) ec * 2];
+    const StepInfo tab = step_info(d.code_step);
     for (int t = 0; t < ntiles; t++) {
         const size_t o = ((size_t) e * ntiles + t) * C + c;
         code_ck[o] = x;
@@ -281,7 +287,7 @@ __global__ void k_scan_code(const gpsiq_chan_desc* __restrict__ desc, const Bina
 // ---------------------------------------------------------------------------
 // k_scan_carrier: exact carrier phase at every tile start, chained over epochs
 // ---------------------------------------------------------------------------
-__global__ void k_scan_carrier(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
+__global__ void k_scan_carrier(const gpsiq_chan_desc* __restrict__ desc,
                                double* __restrict__ carr_ck,
                                double* __restrict__ carr_state, double* __restrict__ carr_trace,
                                CarrInfo* __restrict__ info, GroupInfo* __restrict__ ginfo, int GP, int E, int C, int N,
@@ -305,7 +311,7 @@ __global__ void k_scan_carrier(const gpsiq_chan_desc* __restrict__ desc, const B
             continue;
         }
         if (d.flags & GPSIQ_FLAG_RESET_CARRIER) x = d.carr_phase0;
-        const BinadeTab tab = tabs[((size_t) e * C + c) * 2 + 1];
+        const StepInfo tab = step_info(d.carr_step);
         for (int t = 0; t < ntiles; t++) {
             carr_ck[((size_t) e * ntiles + t) * C + c] = x;  // (carr_ck = the exact plane)
             const int len = min(T, N - t * T);
@@ -488,14 +494,15 @@ k_epoch_estimates(const double* __restrict__ eadv, const double* __restrict__ er
 }
 
 // One chain per (epoch, slot, chunk, parity variant): speculative scan of the chunk's tiles.
-__global__ void k_carr_speculate(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
+__global__ void k_carr_speculate(const gpsiq_chan_desc* __restrict__ desc,
                                  const double* __restrict__ eadv, const double* __restrict__ est_epoch,
                                  double* __restrict__ carr_ck, size_t ck_plane, CarrSpec* __restrict__ spec, int E,
                                  int C, int N, int T, int ntiles, int G, int J) {
     // one chain per THREAD; the lanes of a warp hold the same (slot, chunk, variant) for 32 consecutive
     // epochs: same satellite, nearly the same Doppler, so their segment walks stay mostly convergent
-    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
-    if (chain >= E * C * J * 2) return;
+    const int chain0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = chain0 < E * C * J * 2;
+    const int chain = in_range ? chain0 : 0;
     const int e = chain % E;
     const int rest = chain / E;
     const int v = rest & 1;
@@ -504,45 +511,38 @@ __global__ void k_carr_speculate(const gpsiq_chan_desc* __restrict__ desc, const
     const gpsiq_chan_desc d = desc[ec];
     CarrSpec out;
     out.margin = -1.0; out.n1 = -1; out.xw1 = 0.0; out.xend = 0.0; out.pad = 0;
-    if (d.prn > 0 && !(v == 1 && d.carr_step >= 0.0) && carr_step_speculable(d.carr_step)) {
+    const bool run = in_range && d.prn > 0 && !(v == 1 && d.carr_step >= 0.0) && carr_step_speculable(d.carr_step);
+    const unsigned mask = __ballot_sync(0xffffffffu, run);  // the lanes that walk together (lockstep loops, nco_scan.cuh)
+    if (run) {
         const int t0 = j * G, t1 = min(t0 + G, ntiles);
         // estimated phase at the chunk's first sample (chunk 0: the epoch estimate itself)
         double x = est_epoch[ec];
         if (j > 0) x = frac01(x + eadv[ec] * ((double) (t0 * T) / (double) N));
-        const BinadeTab tab = tabs[(size_t) ec * 2 + 1];
+        const StepInfo tab = step_info(d.carr_step);
         spec_scan_range(x, d.carr_step, tab, N, T, t0, t1, v,
-                        carr_ck + (size_t) v * ck_plane + (size_t) e * ntiles * C + c, (size_t) C, out);
+                        carr_ck + (size_t) v * ck_plane + (size_t) e * ntiles * C + c, (size_t) C, out, mask);
     }
-    spec[((size_t) ec * J + j) * 2 + v] = out;
+    if (in_range) spec[((size_t) ec * J + j) * 2 + v] = out;
 }
 
 #define SPEC_MAX_CHUNKS 16  // most chunks per epoch (level 1)
-// One chain per (epoch, slot, epoch-level variant): stitch the chunk runs into the epoch-level trajectory P.
-__global__ void k_carr_stitch(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
+// One chain per (epoch, slot, epoch-level variant), one per THREAD (lanes = 32 consecutive epochs of one satellite, like
+// the chunk speculation): stitch the chunk runs into the epoch-level trajectory P.
+__global__ void k_carr_stitch(const gpsiq_chan_desc* __restrict__ desc,
                               const double* __restrict__ est_epoch, const CarrSpec* __restrict__ spec,
                               double* __restrict__ carr_ck, size_t ck_plane, ChunkInfo* __restrict__ cinfo,
                               CarrSpec* __restrict__ specE, int E, int C, int N, int T, int ntiles, int G, int J) {
-    __shared__ BinadeTab s_tab[4];
-    __shared__ CarrSpec s_cs[4][2 * SPEC_MAX_CHUNKS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int chain = blockIdx.x * 4 + warp;
+    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
     if (chain >= E * C * 2) return;
-    const int V = chain & 1, ec = chain >> 1;
-    const int e = ec / C, c = ec - e * C;
+    const int e = chain % E;
+    const int rest = chain / E;
+    const int V = rest & 1, c = rest >> 1;
+    const int ec = e * C + c;
     const gpsiq_chan_desc d = desc[ec];
     CarrSpec out;
     out.margin = -1.0; out.n1 = -1; out.xw1 = 0.0; out.xend = 0.0; out.pad = 0;
-    const bool run = d.prn > 0 && !(V == 1 && d.carr_step >= 0.0) && carr_step_speculable(d.carr_step);
-    if (run) {  // stage this chain's table and chunk results (warp-cooperative, coalesced)
-        for (int i = lane; i < (int) (sizeof(BinadeTab) / 4); i += 32)
-            ((uint32_t*) &s_tab[warp])[i] = ((const uint32_t*) (tabs + (size_t) ec * 2 + 1))[i];
-        for (int i = lane; i < J * 2 * (int) (sizeof(CarrSpec) / 4); i += 32)
-            ((uint32_t*) s_cs[warp])[i] = ((const uint32_t*) (spec + (size_t) ec * J * 2))[i];
-    }
-    __syncwarp();
-    if (lane) return;
-    if (run)
-        stitch_epoch(est_epoch[ec], d.carr_step, s_tab[warp], N, T, G, V, s_cs[warp],
+    if (d.prn > 0 && !(V == 1 && d.carr_step >= 0.0) && carr_step_speculable(d.carr_step))
+        stitch_epoch(est_epoch[ec], d.carr_step, step_info(d.carr_step), N, T, G, V, spec + (size_t) ec * J * 2,
                      carr_ck + (size_t) (2 + V) * ck_plane + (size_t) e * ntiles * C + c, (size_t) C,
                      cinfo + ((size_t) ec * 2 + V) * J, out);
     specE[(size_t) ec * 2 + V] = out;
@@ -550,7 +550,7 @@ __global__ void k_carr_stitch(const gpsiq_chan_desc* __restrict__ desc, const Bi
 
 // Stage the per-epoch inputs of one group for one slot into shared memory (one lane per epoch).
 __device__ __forceinline__ void stage_group(GroupEpoch* ge, const gpsiq_chan_desc* __restrict__ desc,
-                                            const BinadeTab* __restrict__ tabs, const CarrSpec* __restrict__ specE,
+                                            const CarrSpec* __restrict__ specE,
                                             int first, int count, int c, int C, int lane) {
     for (int i = lane; i < count; i += 32) {
         const size_t ec = (size_t) (first + i) * C + c;
@@ -560,7 +560,6 @@ __device__ __forceinline__ void stage_group(GroupEpoch* ge, const gpsiq_chan_des
         g.phase0 = d.carr_phase0;
         g.active = d.prn > 0;
         g.reset = (d.flags & GPSIQ_FLAG_RESET_CARRIER) != 0;
-        g.tab = tabs[ec * 2 + 1];
         g.s0 = specE[ec * 2];
         g.s1 = specE[ec * 2 + 1];
     }
@@ -572,7 +571,7 @@ __device__ __forceinline__ void stage_group(GroupEpoch* ge, const gpsiq_chan_des
 // Level 3: one chain per (group, slot, variant): the group's epochs chained from the ESTIMATED group start.
 // One warp per block: 4.6 KB of shared memory, so that the blocks fit beside two resident k_synth_line CTAs.
 __global__ void __launch_bounds__(32)
-k_carr_group(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
+k_carr_group(const gpsiq_chan_desc* __restrict__ desc,
              const CarrSpec* __restrict__ specE, const double* __restrict__ est_epoch, double* __restrict__ carr_ck,
              size_t ck_plane, CarrInfo* __restrict__ infoG, size_t info_plane, double* __restrict__ traceG,
              CarrSpec* __restrict__ specG, int* __restrict__ fallbacks, int E, int C, int N, int T, int ntiles) {
@@ -584,7 +583,7 @@ k_carr_group(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restri
     const int V = chain & 1, gc = chain >> 1;
     const int g = gc / C, c = gc - g * C;
     const int first = g * GROUP_EPOCHS, count = min(GROUP_EPOCHS, E - first);
-    stage_group(s_ge, desc, tabs, specE, first, count, c, C, lane);
+    stage_group(s_ge, desc, specE, first, count, c, C, lane);
     if (lane) return;
     CarrSpec out;
     out.margin = -1.0; out.n1 = -1; out.xw1 = 0.0; out.xend = 0.0; out.pad = 0;
@@ -603,7 +602,7 @@ k_carr_group(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restri
 
 // Level 4: the exact chain, one chain per slot, serial over the groups: one head scan per group.
 __global__ void __launch_bounds__(32)
-k_carr_final(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restrict__ tabs,
+k_carr_final(const gpsiq_chan_desc* __restrict__ desc,
              const CarrSpec* __restrict__ specE, const CarrSpec* __restrict__ specG, double* __restrict__ carr_ck,
              size_t ck_plane, CarrInfo* __restrict__ infoG, size_t info_plane, const double* __restrict__ traceG,
              double* __restrict__ carr_state, double* __restrict__ carr_trace, GroupInfo* __restrict__ ginfo,
@@ -622,7 +621,7 @@ k_carr_final(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restri
         // Fast path (almost always taken): the group's first epoch is active, wraps, and the group trajectory
         // fits from there.  Only that epoch's inputs are staged; the serial work is its head scan, and the
         // lanes translate the post-epoch phases of the other epochs in parallel.
-        stage_group(s_ge, desc, tabs, specE, first, 1, c, C, lane);
+        stage_group(s_ge, desc, specE, first, 1, c, C, lane);
         const double x_start = x;
         GroupInfo gi;
         gi.delta = 0.0; gi.pos = 0x7fffffff; gi.variant = 0;
@@ -637,7 +636,7 @@ k_carr_final(const gpsiq_chan_desc* __restrict__ desc, const BinadeTab* __restri
             const double* tg = traceG + (v ? info_plane : 0) + o;
             for (int e2 = 1 + lane; e2 < count; e2 += 32) carr_trace[o + (size_t) e2 * C] = add_rn(tg[(size_t) e2 * C], diff);
         } else {        // anything else: the general chain over the whole group, from the group's start state
-            stage_group(s_ge, desc, tabs, specE, first, count, c, C, lane);
+            stage_group(s_ge, desc, specE, first, count, c, C, lane);
             if (lane == 0)
                 x = group_final(x_start, s_ge, count, N, T, sG0, sG1, ckX, (size_t) C, (size_t) ntiles * C,
                                 infoG + 2 * info_plane + o, (size_t) C, traceG + o, traceG + info_plane + o, carr_trace + o,
@@ -783,7 +782,7 @@ __global__ void k_checksum(const uint32_t* __restrict__ iq, unsigned long long* 
 static void use_set(gpsiq_ctx* ctx, int i) {
     const ScanSet& ss = ctx->sets[i];
     ctx->d_lut = ss.d_lut; ctx->d_lutp = ss.d_lutp; ctx->d_flags = ss.d_flags; ctx->d_code_ck = ss.d_code_ck;
-    ctx->d_wrap_ck = ss.d_wrap_ck; ctx->d_carr_ck = ss.d_carr_ck; ctx->d_tab = ss.d_tab; ctx->d_drift = ss.d_drift;
+    ctx->d_wrap_ck = ss.d_wrap_ck; ctx->d_carr_ck = ss.d_carr_ck; ctx->d_drift = ss.d_drift;
     ctx->d_spec = ss.d_spec; ctx->d_specE = ss.d_specE; ctx->d_cinfo = ss.d_cinfo; ctx->d_info = ss.d_info;
     ctx->d_specG = ss.d_specG; ctx->d_ginfo = ss.d_ginfo; ctx->d_traceG = ss.d_traceG;
     ctx->d_adv = ss.d_adv; ctx->d_carr_trace = ss.d_carr_trace; ctx->d_ustart = ss.d_ustart;
@@ -829,9 +828,7 @@ int gpsiq_nco_advance(int mode, double* phase, double step, int64_t count, int64
     double x = *phase;
     int w = 0;
     int64_t wtot = 0;
-    BinadeTab tab;
-    if (mode == NCO_CODE) build_binade_tab<NCO_CODE>(step, tab);
-    else build_binade_tab<NCO_CARRIER>(step, tab);
+    const StepInfo tab = step_info(step);
     while (count > 0) {
         const int chunk = count > (1 << 30) ? (1 << 30) : (int) count;
         w = 0;
@@ -867,8 +864,8 @@ int gpsiq_carrier_chain_host(const double* steps, int n_epochs, int N, int T, do
         const double d = steps[e];
         GroupEpoch& g = ge[e];
         g.d = d; g.phase0 = 0.0; g.active = 1; g.reset = 0;
-        build_binade_tab<NCO_CARRIER>(d, g.tab);
-        const double eadv = fma((double) N, d, carr_drift_estimate(d, g.tab, N));
+        const StepInfo si = step_info(d);
+        const double eadv = fma((double) N, d, carr_drift_estimate(d, si, N));
         double a0 = xe + est_err;                        // what the device would guess, plus injected error
         a0 -= floor(a0);
         est[e] = a0;
@@ -882,13 +879,13 @@ int gpsiq_carrier_chain_host(const double* steps, int n_epochs, int N, int T, do
                 const int t0 = j * G, t1 = (t0 + G < ntiles) ? t0 + G : ntiles;
                 double xs = a0;
                 if (j > 0) { xs = a0 + eadv * ((double) (t0 * T) / (double) N); xs -= floor(xs); if (!(xs >= 0.0 && xs < 1.0)) xs = 0.0; }
-                spec_scan_range(xs, d, g.tab, N, T, t0, t1, v, pl + (size_t) v * ntiles, 1, o);
+                spec_scan_range(xs, d, si, N, T, t0, t1, v, pl + (size_t) v * ntiles, 1, o);
             }
         CarrSpec* sE[2] = {&g.s0, &g.s1};
         for (int V = 0; V < 2; V++) {
             sE[V]->margin = -1.0; sE[V]->n1 = -1; sE[V]->xw1 = 0; sE[V]->xend = 0; sE[V]->pad = 0;
             if ((V == 1 && d >= 0.0) || !carr_step_speculable(d)) continue;
-            stitch_epoch(a0, d, g.tab, N, T, G, V, cs, pl + (size_t) (2 + V) * ntiles, 1, ci + ((size_t) e * 2 + V) * J, *sE[V]);
+            stitch_epoch(a0, d, si, N, T, G, V, cs, pl + (size_t) (2 + V) * ntiles, 1, ci + ((size_t) e * 2 + V) * J, *sE[V]);
         }
         double t2 = xe + eadv;
         t2 -= floor(t2);
@@ -940,6 +937,7 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
     ctx->cfg = *cfg;
     ctx->trace_on = getenv("GPSIQ_TRACE") != NULL;
     if (getenv("GPSIQ_LINE_GRID_CAP")) ctx->line_grid_cap = atoi(getenv("GPSIQ_LINE_GRID_CAP"));  // experiments
+    ctx->render_waits_spec = getenv("GPSIQ_RENDER_WAITS_SPEC") ? atoi(getenv("GPSIQ_RENDER_WAITS_SPEC")) : 0;
     if (ctx->trace_on) ctx->trace = (TraceRec*) calloc(TRACE_MAX, sizeof(TraceRec));
     ctx->sm_count = prop.multiProcessorCount;
     ctx->C = cfg->max_chan;
@@ -981,7 +979,7 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
         ctx->G = (ctx->ntiles + chunks - 1) / chunks;
     }
     ctx->J = (ctx->ntiles + ctx->G - 1) / ctx->G;
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < NSETS; i++) {
         ScanSet& ss = ctx->sets[i];
         CU(cudaMalloc(&ss.d_descbuf, EC * sizeof(gpsiq_chan_desc)));
         CU(cudaMalloc(&ss.d_lut, EC * 512 * sizeof(int2)));
@@ -993,7 +991,6 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
         CU(cudaMalloc(&ss.d_carr_ck, 7 * ck * sizeof(double)));
         CU(cudaMalloc(&ss.d_specE, EC * 2 * sizeof(CarrSpec)));
         CU(cudaMalloc(&ss.d_cinfo, EC * 2 * ctx->J * sizeof(ChunkInfo)));
-        CU(cudaMalloc(&ss.d_tab, EC * 2 * sizeof(BinadeTab)));
         CU(cudaMalloc(&ss.d_drift, 4 * EC * sizeof(double)));
         CU(cudaMalloc(&ss.d_spec, EC * 2 * ctx->J * sizeof(CarrSpec)));
         CU(cudaMalloc(&ss.d_info, 3 * EC * sizeof(CarrInfo)));
@@ -1006,6 +1003,11 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
         CU(cudaMalloc(&ss.d_adv, 2 * ctx->C * sizeof(double)));
         CU(cudaMalloc(&ss.d_carr_trace, EC * sizeof(double)));
         CU(cudaMalloc(&ss.d_ustart, EC * sizeof(uint32_t)));
+        CU(cudaMalloc(&ss.d_est, ctx->C * sizeof(double)));
+        CU(cudaMalloc(&ss.d_exact_end, ctx->C * sizeof(double)));
+        CU(cudaEventCreateWithFlags(&ss.adv_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ss.est_done, cudaEventDisableTiming));
+        ss.seq = -1;
         CU(cudaEventCreateWithFlags(&ss.scan_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ss.render_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ss.spec_done, cudaEventDisableTiming));
@@ -1019,6 +1021,8 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
         CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CU(cudaStreamCreateWithPriority(&ctx->scan_stream, cudaStreamNonBlocking, prio_hi));
         CU(cudaStreamCreateWithPriority(&ctx->aux2_stream, cudaStreamNonBlocking, prio_hi));
+        for (int i = 0; i < NSETS; i++) CU(cudaStreamCreateWithPriority(&ctx->sets[i].stream, cudaStreamNonBlocking, prio_hi));
+        CU(cudaEventCreateWithFlags(&ctx->ev_final, cudaEventDisableTiming));
     }
     CU(cudaMalloc(&ctx->d_fallbacks, sizeof(int)));
     CU(cudaMemset(ctx->d_fallbacks, 0, sizeof(int)));
@@ -1048,22 +1052,18 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
         // The kernels meant to run beside k_synth_line (the rest of the next batch's carrier chain) ask for the
         // same (maximum) shared-memory carve-out: an SM cannot change its L1/shared split while blocks are
         // resident, so a kernel preferring another split would wait for the sample kernel's persistent CTAs
-        // to leave.  The chunk speculation keeps the default split: it lives on L1 (per-thread tables).
+        // to leave.  No scan kernel keeps per-thread tables any more (nco_scan.cuh: binade_delta), so EVERY kernel
+        // of the pipeline asks for this split and any of them can be placed beside the sample kernel.
 #define CARVE(k) CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared))
         CARVE(k_synth_line); CARVE(k_carr_stitch); CARVE(k_carr_group); CARVE(k_carr_final); CARVE(k_line_apply);
         CARVE(k_synth_lanes);
-        // ... and the big latency-bound kernels ask for a split that still leaves ~32 KB of shared memory, so that
-        // the chain kernels of ANOTHER slice (k_carr_final: 19 KB per block; the ring of a time-sliced run must
-        // not wait for a speculation kernel to drain) fit beside them
-#define CARVE_PCT(k, pct) CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct))
-        CARVE_PCT(k_carr_speculate, 15); CARVE_PCT(k_scan_code, 15); CARVE_PCT(k_prepare, 15); CARVE_PCT(k_line_anchor, 15);
-        CARVE_PCT(k_line_patch, 15); CARVE_PCT(k_epoch_estimates, 15); CARVE_PCT(k_slice_advance, 15); CARVE_PCT(k_est_fold, 15);
-        CARVE_PCT(k_est_correct, 15);
-#undef CARVE_PCT
+        CARVE(k_carr_speculate); CARVE(k_scan_code); CARVE(k_prepare); CARVE(k_line_anchor); CARVE(k_line_patch);
+        CARVE(k_epoch_estimates); CARVE(k_slice_advance); CARVE(k_est_fold); CARVE(k_est_correct); CARVE(k_int_carrier);
+        CARVE(k_bias_update); CARVE(k_int_fold); CARVE(k_checksum);
 #undef CARVE
         CU(cudaFuncSetAttribute(k_synth_line, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ln_smem_bytes(ctx->C)));
         const size_t tiles = (size_t) ctx->E * ctx->ntiles;
-        for (int i = 0; i < 2; i++) CU(cudaMalloc(&ctx->d_anch[i], tiles * ctx->C * sizeof(ulonglong2)));
+        for (int i = 0; i < NSETS; i++) CU(cudaMalloc(&ctx->d_anch[i], tiles * ctx->C * sizeof(ulonglong2)));
         const int dbg = cfg->reserved[1];
         ctx->haz_cap = (dbg & LN_DBG_FORCE_TILE) ? (int) (tiles * ctx->C) : (int) (tiles * ctx->C / 64 + 1024);
         ctx->patch_cap = 1 << 20;
@@ -1147,32 +1147,35 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
     // (also called on a partly built context by gpsiq_create: every handle may still be NULL)
     cudaDeviceSynchronize();
     cudaFree(ctx->d_desc);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < NSETS; i++) {
         ScanSet& ss = ctx->sets[i];
         cudaFree(ss.d_descbuf); cudaFree(ss.d_lut); cudaFree(ss.d_lutp); cudaFree(ss.d_flags); cudaFree(ss.d_code_ck);
-        cudaFree(ss.d_wrap_ck); cudaFree(ss.d_carr_ck); cudaFree(ss.d_tab); cudaFree(ss.d_drift); cudaFree(ss.d_spec);
+        cudaFree(ss.d_wrap_ck); cudaFree(ss.d_carr_ck); cudaFree(ss.d_drift); cudaFree(ss.d_spec);
         cudaFree(ss.d_specE); cudaFree(ss.d_cinfo); cudaFree(ss.d_info); cudaFree(ss.d_adv); cudaFree(ss.d_carr_trace);
         cudaFree(ss.d_specG); cudaFree(ss.d_ginfo); cudaFree(ss.d_traceG); cudaFree(ss.d_ustart);
         if (ss.scan_done) cudaEventDestroy(ss.scan_done);
         if (ss.render_done) cudaEventDestroy(ss.render_done);
         if (ss.spec_done) cudaEventDestroy(ss.spec_done);
+        if (ss.adv_done) cudaEventDestroy(ss.adv_done);
+        if (ss.est_done) cudaEventDestroy(ss.est_done);
+        if (ss.stream) cudaStreamDestroy(ss.stream);
+        cudaFree(ss.d_est); cudaFree(ss.d_exact_end);
     }
-    cudaFree(ctx->d_chips4); cudaFree(ctx->d_anch[0]); cudaFree(ctx->d_anch[1]); cudaFree(ctx->d_hazlist);
+    cudaFree(ctx->d_chips4); cudaFree(ctx->d_hazlist);
+    for (int i = 0; i < NSETS; i++) { cudaFree(ctx->d_anch[i]); if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]); }
     cudaFree(ctx->d_patches); cudaFree(ctx->d_line_counters); cudaFree(ctx->d_line_totals);
     cudaFree(ctx->d_bias_rate); cudaFree(ctx->d_carr_start);
     if (ctx->d_mbox_peer) cudaIpcCloseMemHandle(ctx->d_mbox_peer);
     cudaFree(ctx->d_mbox);
     cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_est_state); cudaFree(ctx->d_ca);
     cudaFree(ctx->d_iq); cudaFree(ctx->d_iq2); cudaFree(ctx->d_sums); cudaFree(ctx->d_err);
-    if (ctx->h_stage[0]) cudaFreeHost(ctx->h_stage[0]);
-    if (ctx->h_stage[1]) cudaFreeHost(ctx->h_stage[1]);
 #define DROP_STREAM(s) do { if (s) cudaStreamDestroy(s); } while (0)
 #define DROP_EVENT(e) do { if (e) cudaEventDestroy(e); } while (0)
     DROP_STREAM(ctx->scan_stream); DROP_STREAM(ctx->aux2_stream); DROP_EVENT(ctx->ev_fork2); DROP_EVENT(ctx->ev_code2);
     for (int i = 0; i < TIMING_RING; i++)
         for (int j = 0; j < 5; j++) DROP_EVENT(ctx->ev[i][j]);
     DROP_STREAM(ctx->stream); DROP_STREAM(ctx->copy_stream); DROP_STREAM(ctx->aux_stream);
-    DROP_EVENT(ctx->ev_fork); DROP_EVENT(ctx->ev_chain);
+    DROP_EVENT(ctx->ev_fork); DROP_EVENT(ctx->ev_chain); DROP_EVENT(ctx->ev_final);
     for (int i = 0; i < 2; i++) { DROP_EVENT(ctx->ev_P[i]); DROP_EVENT(ctx->ev_F[i]); }
     DROP_EVENT(ctx->ev_sub[0]); DROP_EVENT(ctx->ev_sub[1]);
     if (ctx->trace) {
@@ -1191,8 +1194,8 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
 // render phase consumes the oldest chained one.  A plain gpsiq_synth_device uses the ring with one
 // batch in flight; submit/fetch and the time-slice runner keep two.
 static int begin_batch(gpsiq_ctx* ctx, cudaStream_t st) {
-    if (ctx->set_pending >= 2 || ctx->sets[ctx->set_wr].phase != 0)
-        return fail(ctx, GPSIQ_ERR_CAPACITY, "two batches already in flight (render one first)", cudaSuccess);
+    if (ctx->set_pending >= NSETS || ctx->sets[ctx->set_wr].phase != 0)
+        return fail(ctx, GPSIQ_ERR_CAPACITY, "every scan set is in flight (render a batch first)", cudaSuccess);
     CU(cudaStreamWaitEvent(st, ctx->sets[ctx->set_wr].render_done, 0));
     use_set(ctx, ctx->set_wr);
     return GPSIQ_OK;
@@ -1207,9 +1210,10 @@ static int enqueue_prepare(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int 
     set.desc = desc_dev;
     set.n_epochs = n_epochs;
     set.phase = 1;
+    set.seq = ctx->seq++;
     if (ctx->ev_count < TIMING_RING && st != ctx->scan_stream) CU(cudaEventRecord(ctx->ev[ctx->ev_count][0], st));
     CU(cudaMemsetAsync(ctx->d_flags, 0, 2 * (size_t) ctx->E * sizeof(int), st));
-    k_prepare<<<EC, 128, 0, st>>>(desc_dev, ctx->d_lut, ctx->d_lutp, ctx->d_tab, ctx->d_drift, ctx->d_flags,
+    k_prepare<<<EC, 128, 0, st>>>(desc_dev, ctx->d_lut, ctx->d_lutp, ctx->d_drift, ctx->d_flags,
                                   ctx->d_flags + ctx->E, C, N, ctx->cfg.carrier_mode, ctx->d_bias_rate,
                                   ctx->d_drift + 3 * (size_t) ctx->E * C, ctx->d_err);
     ctx->launches += 1;
@@ -1223,6 +1227,7 @@ static int enqueue_prepare(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int 
         ctx->launches += 1;
         trace_mark(ctx, st, "k_int_carrier(adv)");
     }
+    CU(cudaEventRecord(set.adv_done, st));
     ctx->last_epochs = n_epochs;
     CU(cudaGetLastError());
     return GPSIQ_OK;
@@ -1230,7 +1235,12 @@ static int enqueue_prepare(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int 
 
 // Phase 1b: everything that does NOT need the exact carrier phase: the code-NCO scan and the
 // speculative carrier scans from the context's start-phase estimate (advanced afterwards).
-static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, cudaStream_t st) {
+// est: the start-phase estimate to speculate from -- the context's running one (advanced by the batch's closed-form
+// advance afterwards: single-stream use and the phase API of time-sliced runs), or a set's own (pipelined submits).
+static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, cudaStream_t st,
+                             double* est = NULL) {
+    const bool own_est = est != NULL;
+    if (!est) est = ctx->d_est_state;
     cudaStream_t aux = ctx->aux2_stream;  // (aux_stream may be busy with the tile prologues of the batch being rendered)
     cudaEvent_t fork = ctx->ev_fork;
     use_set(ctx, ctx->set_wr);
@@ -1239,7 +1249,7 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
     // the code-NCO scan does not depend on the carrier chain: it runs beside it on the aux stream
     CU(cudaEventRecord(fork, st));
     CU(cudaStreamWaitEvent(aux, fork, 0));
-    k_scan_code<<<(EC + 63) / 64, 64, 0, aux>>>(desc_dev, ctx->d_tab, ctx->d_code_ck, ctx->d_wrap_ck, EC, C, N, T, ntiles);
+    k_scan_code<<<(EC + 63) / 64, 64, 0, aux>>>(desc_dev, ctx->d_code_ck, ctx->d_wrap_ck, EC, C, N, T, ntiles);
     CU(cudaEventRecord(ctx->ev_code2, aux));
     trace_mark(ctx, aux, "k_scan_code");
     ctx->launches += 1;
@@ -1249,28 +1259,28 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
         double* ereset = ctx->d_drift + (size_t) EC;      // k_prepare wrote it at [gridDim.x + ec] with gridDim.x = EC
         double* est_epoch = ctx->d_drift + 2 * ECmax;
         trace_mark(ctx, st, "(speculate begin)");
-        k_epoch_estimates<<<C, 32, 0, st>>>(ctx->d_drift + 3 * ECmax, ereset, ctx->d_est_state, est_epoch, n_epochs, C);
+        k_epoch_estimates<<<C, 32, 0, st>>>(ctx->d_drift + 3 * ECmax, ereset, est, est_epoch, n_epochs, C);
         trace_mark(ctx, st, "k_epoch_estimates");
         const int chains = EC * ctx->J * 2;
-        k_carr_speculate<<<(chains + 127) / 128, 128, 0, st>>>(desc_dev, ctx->d_tab, eadv, est_epoch, ctx->d_carr_ck,
+        k_carr_speculate<<<(chains + 127) / 128, 128, 0, st>>>(desc_dev, eadv, est_epoch, ctx->d_carr_ck,
                                                          ctx->ck_plane, ctx->d_spec, n_epochs, C, N, T, ntiles, ctx->G,
                                                          ctx->J);
         trace_mark(ctx, st, "k_carr_speculate");
         CU(cudaEventRecord(ctx->sets[ctx->set_wr].spec_done, st));
-        k_carr_stitch<<<(EC * 2 + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_tab, est_epoch, ctx->d_spec, ctx->d_carr_ck,
+        k_carr_stitch<<<(EC * 2 + 127) / 128, 128, 0, st>>>(desc_dev, est_epoch, ctx->d_spec, ctx->d_carr_ck,
                                                       ctx->ck_plane, ctx->d_cinfo, ctx->d_specE, n_epochs, C, N, T,
                                                       ntiles, ctx->G, ctx->J);
         trace_mark(ctx, st, "k_carr_stitch");
         {
             const int ngroups = (n_epochs + GROUP_EPOCHS - 1) / GROUP_EPOCHS;
-            k_carr_group<<<ngroups * C * 2, 32, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_specE, est_epoch,
+            k_carr_group<<<ngroups * C * 2, 32, 0, st>>>(desc_dev, ctx->d_specE, est_epoch,
                                                                    ctx->d_carr_ck, ctx->ck_plane, ctx->d_info, ECmax,
                                                                    ctx->d_traceG, ctx->d_specG, ctx->d_fallbacks, n_epochs,
                                                                    C, N, T, ntiles);
         }
         trace_mark(ctx, st, "k_carr_group");
-        k_est_fold<<<1, 32, 0, st>>>(ctx->d_est_state, ctx->d_adv, C);
-        ctx->launches += 5;
+        if (!own_est) { k_est_fold<<<1, 32, 0, st>>>(ctx->d_est_state, ctx->d_adv, C); ctx->launches += 1; }
+        ctx->launches += 4;
     }
     ctx->sets[ctx->set_wr].phase = 2;
     CU(cudaGetLastError());
@@ -1282,9 +1292,10 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
 static int enqueue_chain(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, cudaStream_t st) {
     const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
     use_set(ctx, ctx->set_wr);
+    CU(cudaStreamWaitEvent(st, ctx->ev_final, 0));  // the carrier state: after the previous batch's chain, whatever its stream
     if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && ctx->cfg.reserved[0] == 0) {
         CU(cudaMemcpyAsync(ctx->d_carr_start, ctx->d_carr_state, C * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        k_carr_final<<<C, 32, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_specE, ctx->d_specG, ctx->d_carr_ck, ctx->ck_plane,
+        k_carr_final<<<C, 32, 0, st>>>(desc_dev, ctx->d_specE, ctx->d_specG, ctx->d_carr_ck, ctx->ck_plane,
                                        ctx->d_info, (size_t) ctx->E * C, ctx->d_traceG, ctx->d_carr_state, ctx->d_carr_trace,
                                        ctx->d_ginfo, ctx->d_fallbacks, n_epochs, C, N, T, ntiles);
         k_bias_update<<<1, 32, 0, st>>>(ctx->d_adv, ctx->d_carr_start, ctx->d_carr_state, ctx->d_bias_rate, n_epochs, C);
@@ -1292,7 +1303,7 @@ static int enqueue_chain(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_
     } else if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_INT32) {  // closed form: one prefix sum over the epochs
         k_int_carrier<<<C, 32, 0, st>>>(desc_dev, ctx->d_ustart, ctx->d_carr_state, ctx->d_carr_trace, NULL, 0, n_epochs, C, N);
     } else {  // the serial float scan (cfg.reserved[0] = 1, cross-check)
-        k_scan_carrier<<<C, 32, 0, st>>>(desc_dev, ctx->d_tab, ctx->d_carr_ck + 6 * ctx->ck_plane, ctx->d_carr_state,
+        k_scan_carrier<<<C, 32, 0, st>>>(desc_dev, ctx->d_carr_ck + 6 * ctx->ck_plane, ctx->d_carr_state,
                                          ctx->d_carr_trace, ctx->d_info + 2 * (size_t) ctx->E * C, ctx->d_ginfo, GROUP_EPOCHS,
                                          n_epochs, C, N, T, ntiles, ctx->cfg.carrier_mode);
     }
@@ -1300,11 +1311,13 @@ static int enqueue_chain(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_
     trace_mark(ctx, st, "k_carr_final");
     if (!ctx->chain_keeps_estimate)  // re-anchor the estimate on the exact phase (single-stream use)
         CU(cudaMemcpyAsync(ctx->d_est_state, ctx->d_carr_state, C * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    CU(cudaStreamWaitEvent(st, ctx->ev_code2, 0));  // scan_done covers the code scan on the side stream too
     ScanSet& set = ctx->sets[ctx->set_wr];
+    CU(cudaMemcpyAsync(set.d_exact_end, ctx->d_carr_state, C * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CU(cudaEventRecord(ctx->ev_final, st));
+    CU(cudaStreamWaitEvent(st, ctx->ev_code2, 0));  // scan_done covers the code scan on the side stream too
     CU(cudaEventRecord(set.scan_done, st));
     set.phase = 3;
-    ctx->set_wr ^= 1;
+    ctx->set_wr = (ctx->set_wr + 1) % NSETS;
     ctx->set_pending++;
     CU(cudaGetLastError());
     return GPSIQ_OK;
@@ -1363,7 +1376,8 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
             ctx->d_line_counters, ctx->haz_cap, ctx->d_patches, ctx->patch_cap, ctx->d_flags + ctx->E, C, N, ntiles);
         CU(cudaEventRecord(ctx->ev_P[1], ctx->aux_stream));
         ctx->launches += 2;
-        if (ctx->set_pending >= 2 && ctx->sets[ctx->set_rd ^ 1].phase >= 2 && ctx->cfg.reserved[0] == 0 && !intc) {
+        if (ctx->render_waits_spec && ctx->set_pending >= 2 && ctx->sets[(ctx->set_rd + 1) % NSETS].phase >= 2 &&
+            ctx->cfg.reserved[0] == 0 && !intc) {
             // Another batch has been submitted ahead.  Its chunk speculation wants the whole GPU (one chain per
             // thread, as many resident as possible) while the sample kernel below is issue-bound and holds on to
             // the SMs it gets: let the speculation finish first (the anchor kernel above ran beside it); the rest
@@ -1372,7 +1386,7 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
             // exact step is a hop of the inter-GPU ring, and a hop beside the sample kernel is several times slower
             // (the chain kernel and the NCCL hand-off wait for SM resources) -- that delay multiplies by the ring
             // length, while waiting here costs this rank at most the ring's quiet length once.
-            ScanSet& nxt = ctx->sets[ctx->set_rd ^ 1];
+            ScanSet& nxt = ctx->sets[(ctx->set_rd + 1) % NSETS];
             CU(cudaStreamWaitEvent(st, (ctx->render_after_next_chain && nxt.phase >= 3) ? nxt.scan_done : nxt.spec_done, 0));
         }
         // device-resident output: one launch; host output: sub-batches so that the copies overlap the rendering
@@ -1426,7 +1440,7 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
     trace_mark(ctx, st, "(render end)");
     CU(cudaEventRecord(set.render_done, st));
     set.phase = 0;
-    ctx->set_rd ^= 1;
+    ctx->set_rd = (ctx->set_rd + 1) % NSETS;
     ctx->set_pending--;
     CU(cudaGetLastError());
     return GPSIQ_OK;
@@ -1477,24 +1491,64 @@ int gpsiq_synth_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_ep
 // Streaming pair: submit scans a batch ahead on the context's own stream (into the free scan set),
 // fetch renders the oldest submitted batch on the caller's stream.  With one batch of lookahead the
 // serial carrier chain of batch k+1 overlaps the sample kernels of batch k.
-int gpsiq_submit_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, void* after_stream) {
-    if (!ctx || !desc_dev || n_epochs < 1) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_submit_device: bad argument", cudaSuccess);
-    if (n_epochs > ctx->E) return fail(ctx, GPSIQ_ERR_CAPACITY, "gpsiq_submit_device: n_epochs > max_epochs", cudaSuccess);
-    CU(cudaSetDevice(ctx->cfg.device));
-    cudaStream_t ss = ctx->scan_stream;
-    if (after_stream != (void*) ss) {  // the descriptors are produced on the caller's stream
-        CU(cudaEventRecord(ctx->ev_fork2, (cudaStream_t) after_stream));
+// Start-phase estimate of a pipelined batch (estimates only ever affect speed: a poor one makes epochs fall back to
+// the serial scan).  Nothing in flight: the exact carrier state.  Otherwise the scans of consecutive batches overlap,
+// so the previous batch's exact end is not known yet: the estimate is the exact end of the batch BEFORE it (its chain
+// was enqueued a whole batch earlier) advanced by the previous batch's closed-form advance -- or, at the start of a
+// burst, the previous batch's own estimate advanced the same way.
+static int pipelined_estimate(gpsiq_ctx* ctx, ScanSet& set, cudaStream_t ss) {
+    const size_t bytes = ctx->C * sizeof(double);
+    if (ctx->set_pending == 0) {
+        CU(cudaStreamWaitEvent(ss, ctx->ev_final, 0));
+        CU(cudaMemcpyAsync(set.d_est, ctx->d_carr_state, bytes, cudaMemcpyDeviceToDevice, ss));
+    } else {
+        ScanSet& prev = ctx->sets[(ctx->set_wr + NSETS - 1) % NSETS];
+        ScanSet& prev2 = ctx->sets[(ctx->set_wr + NSETS - 2) % NSETS];
+        if (prev.seq != set.seq - 1) return fail(ctx, GPSIQ_ERR_ARG, "internal: scan set ring out of order", cudaSuccess);
+        if (NSETS >= 3 && prev2.seq == set.seq - 2 && prev2.phase != 1 && prev2.phase != 2) {
+            CU(cudaStreamWaitEvent(ss, prev2.scan_done, 0));
+            CU(cudaMemcpyAsync(set.d_est, prev2.d_exact_end, bytes, cudaMemcpyDeviceToDevice, ss));
+        } else {
+            CU(cudaStreamWaitEvent(ss, prev.est_done, 0));
+            CU(cudaMemcpyAsync(set.d_est, prev.d_est, bytes, cudaMemcpyDeviceToDevice, ss));
+        }
+        CU(cudaStreamWaitEvent(ss, prev.adv_done, 0));
+        k_est_fold<<<1, 32, 0, ss>>>(set.d_est, prev.d_adv, ctx->C);
+        ctx->launches += 1;
+    }
+    CU(cudaEventRecord(set.est_done, ss));
+    return GPSIQ_OK;
+}
+
+// desc_dev == NULL: the descriptors are already in the write set's own buffer (host submit)
+static int submit_common(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, cudaStream_t after) {
+    ScanSet& set = ctx->sets[ctx->set_wr];
+    cudaStream_t ss = set.stream;
+    if (after) {  // the descriptors are produced on the caller's stream
+        CU(cudaEventRecord(ctx->ev_fork2, after));
         CU(cudaStreamWaitEvent(ss, ctx->ev_fork2, 0));
     }
     int rc = begin_batch(ctx, ss);
     if (rc) return rc;
-    ScanSet& set = ctx->sets[ctx->set_wr];
-    CU(cudaMemcpyAsync(set.d_descbuf, desc_dev, (size_t) n_epochs * ctx->C * sizeof(gpsiq_chan_desc),
-                       cudaMemcpyDeviceToDevice, ss));
+    if (desc_dev)
+        CU(cudaMemcpyAsync(set.d_descbuf, desc_dev, (size_t) n_epochs * ctx->C * sizeof(gpsiq_chan_desc),
+                           cudaMemcpyDeviceToDevice, ss));
     rc = enqueue_prepare(ctx, set.d_descbuf, n_epochs, ss, true);
-    if (!rc) rc = enqueue_speculate(ctx, set.d_descbuf, n_epochs, ss);
+    const bool spec = ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && ctx->cfg.reserved[0] == 0;
+    if (!rc && spec) rc = pipelined_estimate(ctx, set, ss);
+    if (!rc) rc = enqueue_speculate(ctx, set.d_descbuf, n_epochs, ss, spec ? set.d_est : NULL);
     if (!rc) rc = enqueue_chain(ctx, set.d_descbuf, n_epochs, ss);
     return rc;
+}
+
+// Streaming pair: submit scans a batch ahead on one of the context's own streams (into the free scan set),
+// fetch renders the oldest submitted batch on the caller's stream.  Up to NSETS - 1 batches may be scanned ahead of
+// the one being rendered; their scans overlap each other and the sample kernels.
+int gpsiq_submit_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, void* after_stream) {
+    if (!ctx || !desc_dev || n_epochs < 1) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_submit_device: bad argument", cudaSuccess);
+    if (n_epochs > ctx->E) return fail(ctx, GPSIQ_ERR_CAPACITY, "gpsiq_submit_device: n_epochs > max_epochs", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    return submit_common(ctx, desc_dev, n_epochs, (cudaStream_t) after_stream);
 }
 
 int gpsiq_fetch_device(gpsiq_ctx* ctx, int16_t* iq_dev, void* stream) {
@@ -1507,22 +1561,25 @@ int gpsiq_fetch_device(gpsiq_ctx* ctx, int16_t* iq_dev, void* stream) {
 int gpsiq_submit(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc, int n_epochs) {
     if (!ctx || !desc || n_epochs < 1) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_submit: bad argument", cudaSuccess);
     if (n_epochs > ctx->E) return fail(ctx, GPSIQ_ERR_CAPACITY, "gpsiq_submit: n_epochs > max_epochs", cudaSuccess);
-    if (ctx->set_pending >= 2) return fail(ctx, GPSIQ_ERR_CAPACITY, "gpsiq_submit: two batches already in flight", cudaSuccess);
+    if (ctx->set_pending >= NSETS) return fail(ctx, GPSIQ_ERR_CAPACITY, "gpsiq_submit: every scan set is in flight (fetch a batch first)", cudaSuccess);
     CU(cudaSetDevice(ctx->cfg.device));
     const size_t bytes = (size_t) n_epochs * ctx->C * sizeof(gpsiq_chan_desc);
     const int w = ctx->set_wr;
     if (!ctx->h_stage[w]) CU(cudaHostAlloc(&ctx->h_stage[w], (size_t) ctx->E * ctx->C * sizeof(gpsiq_chan_desc), cudaHostAllocDefault));
     CU(cudaEventSynchronize(ctx->sets[w].scan_done));  // the staging buffer's previous upload has been consumed
     memcpy(ctx->h_stage[w], desc, bytes);
-    CU(cudaMemcpyAsync(ctx->d_desc, ctx->h_stage[w], bytes, cudaMemcpyHostToDevice, ctx->scan_stream));
-    return gpsiq_submit_device(ctx, ctx->d_desc, n_epochs, (void*) ctx->scan_stream);
+    // (the set's previous batch has been rendered: fetch is blocking, and a set is only rewritten after its fetch)
+    if (ctx->sets[w].phase != 0) return fail(ctx, GPSIQ_ERR_CAPACITY, "gpsiq_submit: every scan set is in flight (fetch a batch first)", cudaSuccess);
+    CU(cudaStreamWaitEvent(ctx->sets[w].stream, ctx->sets[w].render_done, 0));  // its previous batch no longer reads the buffer
+    CU(cudaMemcpyAsync(ctx->sets[w].d_descbuf, ctx->h_stage[w], bytes, cudaMemcpyHostToDevice, ctx->sets[w].stream));
+    return submit_common(ctx, NULL, n_epochs, NULL);
 }
 
 int gpsiq_fetch(gpsiq_ctx* ctx, int16_t* iq_out) {
     if (!ctx || !iq_out) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_fetch: bad argument", cudaSuccess);
     CU(cudaSetDevice(ctx->cfg.device));
     if (!ctx->d_iq2) CU(cudaMalloc(&ctx->d_iq2, (size_t) ctx->E * ctx->N * 4));
-    int16_t* dev = ctx->set_rd ? ctx->d_iq2 : ctx->d_iq;
+    int16_t* dev = (ctx->fetch_count++ & 1) ? ctx->d_iq2 : ctx->d_iq;
     int rc = enqueue_render(ctx, dev, ctx->stream, iq_out);
     if (rc) return rc;
     rc = check_device_error(ctx);

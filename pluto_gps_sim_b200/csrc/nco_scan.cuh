@@ -22,11 +22,10 @@
 // The subtractions x-1023.0 (x in [1023,1024.4)) and x-1.0 (x in [1,2)) are
 // exact; x+1.0 for a small negative x rounds to the 2^-53 grid.
 //
-// The per-binade increments D_b depend only on the step d, so they are
-// tabulated once per (epoch, channel, NCO) (BinadeTab) and every scan --
-// the per-epoch scan kernels and the per-tile prologue of the synthesis
-// kernel -- steps segment by segment: [k in-binade steps by one multiply-add]
-// [one true step].
+// The per-binade increment D_b is the step's own significand shifted to the
+// binade's ulp and rounded (binade_delta): two registers (StepInfo), no table,
+// no memory traffic.  Every scan steps segment by segment:
+// [k in-binade steps by one multiply-add] [one true step].
 //
 // This header is shared by the CUDA kernels (device) and by the host-side
 // entry points gpsiq_nco_advance / gpsiq_carrier_chain_host, which the tests
@@ -77,36 +76,57 @@ template <int MODE> struct NcoTraits;
 template <> struct NcoTraits<NCO_CODE> { static constexpr int64_t ETOP = 1032; static constexpr int64_t LIM = BITS_1023; };
 template <> struct NcoTraits<NCO_CARRIER> { static constexpr int64_t ETOP = 1022; static constexpr int64_t LIM = BITS_1; };
 
-// In-binade increments of the bit pattern for one step value d.
-// Binade index bi = ETOP - biased exponent: 0 is [512,1024) for the code NCO,
-// [0.5,1) for the carrier NCO; states in lower binades than NBINADE-1 take true steps.
-struct BinadeTab {
-    int64_t delta[NBINADE];  // D_b from an even mantissa (any mantissa if the binade has no tie)
-    float rcp[NBINADE];      // ~1/|D_b|
-    uint32_t valid;          // bit bi: delta[bi] is usable
-    uint32_t tie;            // bit bi: d/ulp_b is an exact half-integer: an odd mantissa steps differently once
+// What a scan keeps per chain about its step: the step itself and ~1/|d| (single precision: only ever used for a
+// first guess that exact integer arithmetic then corrects).
+struct StepInfo {
+    double d;
+    float rd;
 };
 
-template <int MODE>
-GPSIQ_HD void build_binade_tab(double d, BinadeTab& tab) {
-    tab.valid = 0;
-    tab.tie = 0;
-    for (int bi = 0; bi < NBINADE; bi++) {
-        const int64_t e = NcoTraits<MODE>::ETOP - bi;
-        const int64_t b_even = (e << 52) | (1LL << 51);  // 1.5 * 2^b, even mantissa
-        const double y0 = add_rn(bits_f64(b_even), d);
-        const double y1 = add_rn(bits_f64(b_even + 1), d);
-        const int64_t c0 = f64_bits(y0), c1 = f64_bits(y1);
-        tab.delta[bi] = 0;
-        tab.rcp[bi] = 0.f;
-        if ((c0 >> 52) != e || (c1 >> 52) != e || c0 >= NcoTraits<MODE>::LIM) continue;  // probe left the binade
-        const int64_t d0 = c0 - b_even, d1 = c1 - (b_even + 1);
-        tab.delta[bi] = d0;
-        const int64_t a = d0 < 0 ? -d0 : d0;
-        tab.rcp[bi] = a ? 1.0f / (float) a : 0.f;
-        tab.valid |= 1u << bi;
-        if (d1 != d0) tab.tie |= 1u << bi;
-    }
+GPSIQ_HD float fast_rcp(float v) {
+#if defined(__CUDA_ARCH__)
+    return __frcp_rn(v);
+#else
+    return 1.0f / v;
+#endif
+}
+GPSIQ_HD int64_t round_even_ll(double t) {  // |t| < 2^62; nearest integer, ties to even
+#if defined(__CUDA_ARCH__)
+    return __double2ll_rn(t);
+#else
+    return (int64_t) __builtin_rint(t);  // default rounding mode: to nearest even
+#endif
+}
+GPSIQ_HD float pow2f_of(int biased_exp) {  // 2^(biased_exp - 127), 1 <= biased_exp <= 254
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(biased_exp << 23);
+#else
+    union { float f; int32_t i; } u; u.i = biased_exp << 23; return u.f;
+#endif
+}
+GPSIQ_HD double abs_f64(double t) { return bits_f64(f64_bits(t) & 0x7fffffffffffffffLL); }
+
+GPSIQ_HD StepInfo step_info(double d) {
+    StepInfo s;
+    s.d = d;
+    const float a = (float) abs_f64(d);
+    s.rd = (a > 0.f) ? fast_rcp(a) : 0.f;
+    return s;
+}
+
+// In-binade increment of the bit pattern for a state with biased exponent ex (64 <= ex), from an EVEN mantissa (any
+// mantissa if the binade has no tie): D = RN(d / ulp_x), ulp_x = 2^(ex - 1075).  The division by the ulp is a
+// power-of-two scaling, exact in binary64, and round-to-nearest-even of the quotient is exactly what the reference's
+// addition does to the sum's mantissa (x even: ties go to the even D).  tie: d / ulp_x is an exact half-integer --
+// an odd mantissa then steps differently once.  false: no usable increment (|d| >= the binade, or not finite).
+GPSIQ_HD bool binade_delta(const StepInfo& si, int64_t ex, int64_t& delta, bool& tie) {
+    tie = false;
+    if (ex < 64 || ex > 2046) return false;
+    const double t = si.d * pow2_of(2098 - ex);  // d / ulp_x
+    if (!(abs_f64(t) < 0x1p52)) return false;
+    delta = round_even_ll(t);
+    tie = abs_f64(t - (double) delta) == 0.5;
+    return true;
 }
 
 // One literal step of the reference recurrence. Returns true if it wrapped.
@@ -130,15 +150,16 @@ GPSIQ_HD bool nco_step(double& x, double d, int& wraps) {
 // receives the distance, in ulps of the binade, between the last iterate and
 // the binade edge / wrap limit it is moving toward (>= 1).
 template <int MODE>
-GPSIQ_HD int run_in_binade(double& x, const BinadeTab& tab, int maxk, int64_t* edge_gap = nullptr) {
+GPSIQ_HD int run_in_binade(double& x, const StepInfo& si, int maxk, int64_t* edge_gap = nullptr, int64_t* delta_out = nullptr) {
     const int64_t b = f64_bits(x);
     const int64_t e = b >> 52;
-    const int64_t bi = NcoTraits<MODE>::ETOP - e;
     if (edge_gap) *edge_gap = 0;
-    if (bi < 0 || bi >= NBINADE || maxk <= 0) return 0;
-    if (!((tab.valid >> bi) & 1u)) return 0;
-    if (((tab.tie >> bi) & 1u) && (b & 1)) return 0;  // odd mantissa in a tie binade: take a true step first
-    const int64_t delta = tab.delta[bi];
+    if (e < 960 || e > NcoTraits<MODE>::ETOP || maxk <= 0) return 0;  // zero / tiny (< 2^-63: true steps) / negative / above the wrap limit
+    int64_t delta;
+    bool tie;
+    if (!binade_delta(si, e, delta, tie)) return 0;
+    if (tie && (b & 1)) return 0;  // odd mantissa in a tie binade: take a true step first
+    if (delta_out) *delta_out = delta;
     if (delta == 0) return maxk;  // |d| < ulp/2: the state no longer moves
     int64_t num, ad;
     if (delta > 0) {
@@ -153,7 +174,8 @@ GPSIQ_HD int run_in_binade(double& x, const BinadeTab& tab, int maxk, int64_t* e
     if (num < ad) return 0;
     // k = min(floor(num/ad), maxk) without an integer or FP64 division
     int64_t k;
-    const float qf = (float) num * tab.rcp[bi];
+    // first guess of num / ad: 1/ad = (1/|d|) * ulp_x up to rounding -- a power-of-two scaling of the chain's 1/|d|
+    const float qf = (float) num * (si.rd * pow2f_of((int) e - 1075 + 127));
     if (qf >= (float) maxk + 4.0f) {
         k = maxk;
     } else {
@@ -172,7 +194,7 @@ GPSIQ_HD int run_in_binade(double& x, const BinadeTab& tab, int maxk, int64_t* e
 // accumulates code-period wraps (NCO_CODE).  Exactly equivalent to calling
 // nco_step `count` times.
 template <int MODE>
-GPSIQ_HD void nco_advance(double& x, double d, const BinadeTab& tab, int count, int& wraps) {
+GPSIQ_HD void nco_advance(double& x, double d, const StepInfo& tab, int count, int& wraps) {
     while (count > 0) {
         count -= run_in_binade<MODE>(x, tab, count);
         if (count == 0) break;
@@ -253,7 +275,7 @@ GPSIQ_HD bool carr_step(double& x, double d, double& margin) {
 // Advance up to `count` carrier steps; with stop_at_wrap, return right after
 // the first step that wrapped.  Returns the number of steps taken.
 template <bool TRACK>
-GPSIQ_HD int carr_advance(double& x, double d, const BinadeTab& tab, int count, bool stop_at_wrap, bool& wrapped,
+GPSIQ_HD int carr_advance(double& x, double d, const StepInfo& tab, int count, bool stop_at_wrap, bool& wrapped,
                           double& margin) {
     const int count0 = count;
     wrapped = false;
@@ -275,16 +297,71 @@ GPSIQ_HD int carr_advance(double& x, double d, const BinadeTab& tab, int count, 
     return count0 - count;
 }
 
+// Flat segment walk: one loop iteration = [one in-binade run][one true step], whatever the tiling -- the lanes of a
+// warp (neighbouring epochs of one satellite) then execute nearly the same number of iterations.  The state at every
+// tile start passed (the state BEFORE that sample) goes to ck[tile * stride]; starts inside a run come from the run's
+// closed form on the bit pattern.  n, next: sample indices relative to the scanned range (tile starts = multiples of T
+// from its first sample); next = the next tile start not yet emitted (>= n), t = its tile number.
+struct CarrWalk { double x; int n; int next; int t; };
+
+// warp_any: on the device, with the ballot mask of the lanes that walk together, the loop runs in lockstep until the
+// LAST lane is done (a lane that is done idles): without it lanes that leave a loop at different iterations never
+// meet again (no reconvergence point inside a loop) and the warp degenerates into a dozen groups.  mask 0 / host: plain.
+GPSIQ_HD bool warp_any(unsigned mask, bool pred) {
+#if defined(__CUDA_ARCH__)
+    return mask ? (__any_sync(mask, pred) != 0) : pred;
+#else
+    (void) mask;
+    return pred;
+#endif
+}
+
+// Walks from w.n to n_end.  Returns true if it stopped right after a wrapping step (stop_at_wrap), false at n_end.
+template <bool TRACK>
+GPSIQ_HD bool carr_walk(CarrWalk& w, const StepInfo& si, int n_end, int T, bool stop_at_wrap, double* ck, size_t stride,
+                        double& margin, unsigned mask = 0) {
+    bool stopped = false;
+    while (warp_any(mask, w.n < n_end && !stopped)) {
+        if (!(w.n < n_end) || stopped) continue;
+        if (w.n == w.next) { ck[(size_t) w.t * stride] = w.x; w.t++; w.next += T; }
+        int64_t gap, delta = 0;
+        const int64_t b0 = f64_bits(w.x);
+        const int k = run_in_binade<NCO_CARRIER>(w.x, si, n_end - w.n, TRACK ? &gap : nullptr, &delta);
+        if (k > 0) {
+            const int n1 = w.n + k;
+            while (w.next < n1) {  // tile starts strictly inside the run
+                ck[(size_t) w.t * stride] = bits_f64(b0 + (int64_t) (w.next - w.n) * delta);
+                w.t++; w.next += T;
+            }
+            w.n = n1;
+            if (TRACK) {
+                // the last iterate of the run is the one closest to the edge it approaches;
+                // one ulp of slack for the rounding of its sum
+                const double m = (double) (gap - 1) * pow2_of((f64_bits(w.x) >> 52) - 52);
+                if (m < margin) margin = m;
+            }
+            if (w.n >= n_end) continue;
+            if (w.n == w.next) { ck[(size_t) w.t * stride] = w.x; w.t++; w.next += T; }
+        }
+        const bool wrapped = carr_step<TRACK>(w.x, si.d, margin);
+        w.n++;
+        if (wrapped && stop_at_wrap) stopped = true;
+    }
+    return stopped;
+}
+
 // Predicted systematic rounding drift of the carrier recurrence over n steps of
 // step d: inside binade bi every step errs by (D_b*ulp_b - d), and the phase
 // spends a fraction 2^-(bi+1) of its steps there.  Only used to improve the
 // START-PHASE ESTIMATES of the speculative scans (fewer serial fallbacks);
 // never part of an exact result.
-GPSIQ_HD double carr_drift_estimate(double d, const BinadeTab& tab, int n) {
+GPSIQ_HD double carr_drift_estimate(double d, const StepInfo& tab, int n) {
     double acc = 0.0;
     for (int bi = 0; bi < NBINADE; bi++) {
-        if (!((tab.valid >> bi) & 1u)) continue;
-        const double step_b = (double) tab.delta[bi] * pow2_of(1022 - bi - 52);  // exact: D_b * ulp_b
+        int64_t delta;
+        bool tie;
+        if (!binade_delta(tab, 1022 - bi, delta, tie) || !(abs_f64(d) < pow2_of(1022 - bi - 2))) continue;  // (|d| < a quarter of the binade)
+        const double step_b = (double) delta * pow2_of(1022 - bi - 52);  // exact: D_b * ulp_b
         acc += (step_b - d) * pow2_of(1022 - bi);                               // width of [2^-(bi+1), 2^-bi)
     }
     return acc * (double) n;
@@ -310,42 +387,30 @@ GPSIQ_HD bool carr_step_speculable(double d) {
 // phase at sample t0*T.  ck[t*ck_stride] receives the state at the start of tile
 // t (absolute tile index).  out.n1 is relative to sample t0*T; it equals the
 // range's sample count if the run never wraps.
-GPSIQ_HD void spec_scan_range(double x, double d, const BinadeTab& tab, int N, int T, int t0, int t1, int variant,
-                              double* ck, size_t ck_stride, CarrSpec& out) {
+GPSIQ_HD void spec_scan_range(double x, double d, const StepInfo& tab, int N, int T, int t0, int t1, int variant,
+                              double* ck, size_t ck_stride, CarrSpec& out, unsigned mask = 0) {
     const int m_total = ((t1 * T < N) ? t1 * T : N) - t0 * T;
-    double margin = 1.0;
-    bool seen_wrap = false;
-    int n = 0;
+    double margin = 1.0, dummy = 1.0;
+    CarrWalk w;
+    w.x = x; w.n = 0; w.next = 0; w.t = t0;
     out.n1 = m_total;
     out.xw1 = 0.0;
-    for (int t = t0; t < t1; t++) {
-        ck[(size_t) t * ck_stride] = x;
-        int remaining = (T < N - t * T) ? T : N - t * T;
-        while (remaining > 0) {
-            bool w;
-            int steps;
-            if (!seen_wrap) {
-                double dummy = 1.0;
-                steps = carr_advance<false>(x, d, tab, remaining, true, w, dummy);
-                if (w) {
-                    seen_wrap = true;
-                    if (variant == 1) x = (x + 0x1p-53 < 1.0) ? x + 0x1p-53 : x - 0x1p-53;  // other parity of the 2^-53 grid
-                    if (!(x >= 0.0 && x < 1.0)) margin = -1.0;
-                    out.n1 = n + steps;
-                    out.xw1 = x;
-                }
-            } else {
-                steps = carr_advance<true>(x, d, tab, remaining, false, w, margin);
-            }
-            remaining -= steps;
-            n += steps;
-        }
+    const bool seen_wrap = carr_walk<false>(w, tab, m_total, T, true, ck, ck_stride, dummy, mask);  // up to the first wrap
+    bool bad = false;
+    if (seen_wrap) {
+        if (variant == 1) w.x = (w.x + 0x1p-53 < 1.0) ? w.x + 0x1p-53 : w.x - 0x1p-53;  // other parity of the 2^-53 grid
+        if (!(w.x >= 0.0 && w.x < 1.0)) bad = true;
+        out.n1 = w.n;
+        out.xw1 = w.x;
     }
-    out.xend = x;
+    // the rest, margin-tracked (every lane of the mask calls it: a lane that never wrapped is already at the end)
+    carr_walk<true>(w, tab, m_total, T, false, ck, ck_stride, margin, mask);
+    if (bad) margin = -1.0;
+    out.xend = w.x;
     out.margin = (seen_wrap && carr_step_speculable(d)) ? margin : -1.0;
 }
 
-GPSIQ_HD void spec_scan_epoch(double x, double d, const BinadeTab& tab, int N, int T, int variant, double* ck,
+GPSIQ_HD void spec_scan_epoch(double x, double d, const StepInfo& tab, int N, int T, int variant, double* ck,
                               size_t ck_stride, CarrSpec& out) {
     spec_scan_range(x, d, tab, N, T, 0, (N + T - 1) / T, variant, ck, ck_stride, out);
 }
@@ -385,7 +450,7 @@ struct ChunkInfo {  // per (epoch, channel, epoch-level variant, chunk)
 
 // a0: estimated epoch start phase (the chunk-0 runs started from exactly this value).
 // cs: chunk results [J][2]; ckP: this trajectory's P plane for head/fallback tiles.
-GPSIQ_HD void stitch_epoch(double a0, double d, const BinadeTab& tab, int N, int T, int G, int V,
+GPSIQ_HD void stitch_epoch(double a0, double d, const StepInfo& tab, int N, int T, int G, int V,
                            const CarrSpec* cs, double* ckP, size_t ck_stride, ChunkInfo* ci, CarrSpec& outE) {
     const int ntiles = (N + T - 1) / T;
     const int J = (ntiles + G - 1) / G;
@@ -496,7 +561,7 @@ struct GroupInfo {    // per (group, channel): result of the final chain
 // scanned tile, or 0), writing the state at every tile start passed, until the first wrap or the epoch's
 // end.  TRACK: margin-track every decision.
 template <bool TRACK>
-GPSIQ_HD void scan_epoch_head(double& x, double d, const BinadeTab& tab, int N, int T, double* ck, size_t ck_stride,
+GPSIQ_HD void scan_epoch_head(double& x, double d, const StepInfo& tab, int N, int T, double* ck, size_t ck_stride,
                               int& t, int& n, int& remaining, bool& wrapped, bool stop_at_wrap, double& margin) {
     const int ntiles = (N + T - 1) / T;
     wrapped = false;
@@ -520,7 +585,7 @@ GPSIQ_HD void scan_epoch_head(double& x, double d, const BinadeTab& tab, int N, 
 // into g, each epoch's own translation costs margin, and variant V flips the parity at the chain's
 // first wrap.  eg = index of the epoch within its group.
 template <bool SPEC>
-GPSIQ_HD double group_chain_epoch(double x, double d, const BinadeTab& tab, int N, int T, const CarrSpec& s0,
+GPSIQ_HD double group_chain_epoch(double x, double d, const StepInfo& tab, int N, int T, const CarrSpec& s0,
                                   const CarrSpec& s1, double* ck0, size_t ck_stride, CarrInfo& info, int& fell_back,
                                   GroupTrack* g, int V, int eg) {
     int n = 0, t = 0, remaining = 0;
@@ -562,7 +627,6 @@ GPSIQ_HD double group_chain_epoch(double x, double d, const BinadeTab& tab, int 
 // Per-epoch inputs of the group-level chains, staged by the caller (shared memory on the device).
 struct GroupEpoch {
     double d, phase0;
-    BinadeTab tab;
     CarrSpec s0, s1;   // the epoch's stitched (epoch-level) speculation results, both variants
     int active, reset;
 };
@@ -581,7 +645,7 @@ GPSIQ_HD void group_chain(double x, const GroupEpoch* ge, int count, int N, int 
         if (ge[eg].active) {
             if (ge[eg].reset) { g.usable = 0; x = ge[eg].phase0; }       // re-seeded inside the group: not translatable
             if (!carr_step_speculable(ge[eg].d)) g.usable = 0;
-            x = group_chain_epoch<true>(x, ge[eg].d, ge[eg].tab, N, T, ge[eg].s0, ge[eg].s1,
+            x = group_chain_epoch<true>(x, ge[eg].d, step_info(ge[eg].d), N, T, ge[eg].s0, ge[eg].s1,
                                         ckHead + (size_t) eg * epoch_stride, tile_stride, inf, fb, &g, V, eg);
         }
         info[(size_t) eg * info_stride] = inf;
@@ -612,7 +676,7 @@ GPSIQ_HD double group_final(double x, const GroupEpoch* ge, int count, int N, in
         bool wrapped = false;
         double* ck = ckX + (size_t) eg * epoch_stride;
         const double x_epoch = x;  // exact phase at the first sample of this epoch
-        scan_epoch_head<false>(x, ge[eg].d, ge[eg].tab, N, T, ck, tile_stride, t, n, remaining, wrapped, true, dummy);
+        scan_epoch_head<false>(x, ge[eg].d, step_info(ge[eg].d), N, T, ck, tile_stride, t, n, remaining, wrapped, true, dummy);
         if (!wrapped) { trace[(size_t) eg * trace_stride] = x; continue; }
         const int pos = eg * N + n;
         int v;
@@ -632,7 +696,7 @@ GPSIQ_HD double group_final(double x, const GroupEpoch* ge, int count, int N, in
             CarrInfo inf = all_exact;
             if (ge[e2].active) {
                 if (e2 > eg && ge[e2].reset) x = ge[e2].phase0;
-                x = group_chain_epoch<false>(x, ge[e2].d, ge[e2].tab, N, T, ge[e2].s0, ge[e2].s1,
+                x = group_chain_epoch<false>(x, ge[e2].d, step_info(ge[e2].d), N, T, ge[e2].s0, ge[e2].s1,
                                              ckX + (size_t) e2 * epoch_stride, tile_stride, inf, fb, nullptr, 0, 0);
             }
             infoX[(size_t) e2 * info_stride] = inf;
@@ -690,7 +754,7 @@ GPSIQ_HD double carr_lookup(const CarrLookup& L, int e, int c, int t, int T, int
 }
 
 // (3) exact chaining of one epoch from the exact start x; returns the exact end state.
-GPSIQ_HD double chain_epoch(double x, double d, const BinadeTab& tab, int N, int T, const CarrSpec& s0,
+GPSIQ_HD double chain_epoch(double x, double d, const StepInfo& tab, int N, int T, const CarrSpec& s0,
                             const CarrSpec& s1, double* ck0, size_t ck_stride, CarrInfo& info, int& fell_back) {
     return group_chain_epoch<false>(x, d, tab, N, T, s0, s1, ck0, ck_stride, info, fell_back, nullptr, 0, 0);
 }
