@@ -259,7 +259,8 @@ int gpsiq_timing_sample_kernel(gpsiq_ctx *ctx, int *n_launches, float *kernel_ms
 int gpsiq_timing_sample_kernel_isolated(gpsiq_ctx *ctx, int reps, float *kernel_ms, int *epochs_per_launch);
 
 /* Line kernel diagnostics, accumulated over the context's life: (tile, slot) pairs that had to be
- * re-checked with the literal recurrence, samples patched, 32-tile chunks flagged by the first-level check. */
+ * re-checked with the literal recurrence, samples patched, (epoch, slot) pairs the epoch-level check could not
+ * clear (refined per 32-tile chunk, then per tile). */
 int gpsiq_line_stats(gpsiq_ctx *ctx, int64_t *hazard_tiles, int64_t *patches, int64_t *flagged_chunks);
 /* Host execution of the safety check's arithmetic (tests):
  * gpsiq_minmod_host: min over x in [0,n) of (b + a*x) mod m (may return any attained value < stop early).

@@ -134,7 +134,9 @@ struct gpsiq_ctx {
     int use_line;         // k_synth_line (the production kernel) is eligible for this configuration
     int8_t* d_chips4;     // [33][4][LN_VS] +-1: chip/NAV sign tables in 4 polarity variants, extended past chip 1022
     ulonglong2* d_anch[NSETS];   // [E][ntiles][C] tile anchors {F, G} (one buffer per scan set)
-    uint32_t* d_hazlist;  // (tile, slot) pairs k_line_anchor could not clear
+    LineEpoch* d_lrecs;   // [E][C] per-epoch line records of the batch being rendered (k_line_anchor -> k_line_check)
+    uint32_t* d_elist;    // (epoch, slot) pairs k_line_check could not clear
+    uint32_t* d_hazlist;  // (tile, slot) pairs k_line_refine could not clear
     int haz_cap, patch_cap;
     int* d_line_counters; // [0] listed hazards, [1] patches, [2] flagged chunks (per batch)
     unsigned long long* d_line_totals;  // the same, accumulated over the context's life
@@ -260,9 +262,11 @@ __global__ void k_prepare(const gpsiq_chan_desc* __restrict__ desc, int2* __rest
 // ---------------------------------------------------------------------------
 // k_scan_code: exact code phase + wrap count at every tile start
 // ---------------------------------------------------------------------------
+// Needed only by k_synth_lanes (the literal-recurrence kernel): k_synth_line's code anchors are closed form.
+// flags != NULL: only the epochs k_synth_lanes will render (amplitude / step contract, list overflows).
 __global__ void k_scan_code(const gpsiq_chan_desc* __restrict__ desc,
-                            double* __restrict__ code_ck, int* __restrict__ wrap_ck, int EC, int C, int N, int T,
-                            int ntiles) {
+                            double* __restrict__ code_ck, int* __restrict__ wrap_ck, const int* __restrict__ amp_sum,
+                            const int* __restrict__ step_flag, int EC, int C, int N, int T, int ntiles) {
     // one chain per thread; the lanes of a warp hold the same slot for 32 consecutive epochs (same
     // satellite, nearly the same code rate), so their segment walks stay mostly convergent
     const int chain = blockIdx.x * blockDim.x + threadIdx.x;
@@ -270,6 +274,7 @@ __global__ void k_scan_code(const gpsiq_chan_desc* __restrict__ desc,
     const int E = EC / C;
     const int e = chain % E, c = chain / E;
     const int ec = e * C + c;
+    if (amp_sum && !(amp_sum[e] > 32767 || step_flag[e])) return;
     const gpsiq_chan_desc d = desc[ec];
     if (d.prn <= 0) return;
     double x = d.code_phase0;
@@ -659,6 +664,7 @@ k_carr_final(const gpsiq_chan_desc* __restrict__ desc,
 // cross-check for k_synth_line and as the path for epochs outside its contract.
 // ---------------------------------------------------------------------------
 #define LANES_WARPS 4
+#define LANES_FLAGGED_CTAS 8   // CTAs per epoch of the fallback launch beside k_synth_line
 
 __global__ void __launch_bounds__(LANES_WARPS * 32)
 k_synth_lanes(const gpsiq_chan_desc* __restrict__ desc, const int2* __restrict__ lut,
@@ -666,13 +672,14 @@ k_synth_lanes(const gpsiq_chan_desc* __restrict__ desc, const int2* __restrict__
               const CarrLookup carr, const uint32_t* __restrict__ ustart,
               const uint32_t* __restrict__ ca, const int* __restrict__ amp_sum, const int* __restrict__ step_flag,
               int only_flagged, int16_t* __restrict__ iq, int e0,
-              int C, int N, int T, int ntiles, int tile_groups, int carrier_mode) {
+              int C, int N, int T, int ntiles, int tile_groups, int ctas_per_epoch, int carrier_mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int2* s_lut = reinterpret_cast<int2*>(smem_raw);                       // [C][512]
     uint32_t* s_ca = reinterpret_cast<uint32_t*>(s_lut + (size_t) C * 512); // [C][33]
 
-    const int e = e0 + blockIdx.x / tile_groups;
-    const int tg = blockIdx.x % tile_groups;
+    // ctas_per_epoch CTAs per epoch stride over its tile groups (the fallback launch beside k_synth_line keeps the grid
+    // small: normally every CTA returns at once)
+    const int e = e0 + blockIdx.x / ctas_per_epoch;
     if (only_flagged && !(amp_sum[e] > 32767 || step_flag[e])) return;  // rendered by k_synth_line
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const gpsiq_chan_desc* de = desc + (size_t) e * C;
@@ -685,8 +692,9 @@ k_synth_lanes(const gpsiq_chan_desc* __restrict__ desc, const int2* __restrict__
     }
     __syncthreads();
 
+  for (int tg = blockIdx.x % ctas_per_epoch; tg < tile_groups; tg += ctas_per_epoch) {
     const int t = tg * LANES_WARPS + warp;
-    if (t >= ntiles) return;
+    if (t >= ntiles) continue;
     const int n0 = t * T;
     const int len = min(T, N - n0);
 
@@ -754,6 +762,7 @@ k_synth_lanes(const gpsiq_chan_desc* __restrict__ desc, const int2* __restrict__
             if (base + lane <= n) out[base + lane] = keep;  // 128 B per warp, coalesced
         }
     }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -1019,9 +1028,10 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
         // kernel of the previous batch: highest priority
         int prio_lo = 0, prio_hi = 0;
         CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        CU(cudaStreamCreateWithPriority(&ctx->scan_stream, cudaStreamNonBlocking, prio_hi));
+        const int scan_prio = (getenv("GPSIQ_SCAN_PRIO") && !strcmp(getenv("GPSIQ_SCAN_PRIO"), "lo")) ? prio_lo : prio_hi;  // experiments
+        CU(cudaStreamCreateWithPriority(&ctx->scan_stream, cudaStreamNonBlocking, scan_prio));
         CU(cudaStreamCreateWithPriority(&ctx->aux2_stream, cudaStreamNonBlocking, prio_hi));
-        for (int i = 0; i < NSETS; i++) CU(cudaStreamCreateWithPriority(&ctx->sets[i].stream, cudaStreamNonBlocking, prio_hi));
+        for (int i = 0; i < NSETS; i++) CU(cudaStreamCreateWithPriority(&ctx->sets[i].stream, cudaStreamNonBlocking, scan_prio));
         CU(cudaEventCreateWithFlags(&ctx->ev_final, cudaEventDisableTiming));
     }
     CU(cudaMalloc(&ctx->d_fallbacks, sizeof(int)));
@@ -1059,7 +1069,7 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
         CARVE(k_synth_lanes);
         CARVE(k_carr_speculate); CARVE(k_scan_code); CARVE(k_prepare); CARVE(k_line_anchor); CARVE(k_line_patch);
         CARVE(k_epoch_estimates); CARVE(k_slice_advance); CARVE(k_est_fold); CARVE(k_est_correct); CARVE(k_int_carrier);
-        CARVE(k_bias_update); CARVE(k_int_fold); CARVE(k_checksum);
+        CARVE(k_bias_update); CARVE(k_int_fold); CARVE(k_checksum); CARVE(k_line_check); CARVE(k_line_refine);
 #undef CARVE
         CU(cudaFuncSetAttribute(k_synth_line, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ln_smem_bytes(ctx->C)));
         const size_t tiles = (size_t) ctx->E * ctx->ntiles;
@@ -1068,6 +1078,8 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
         ctx->haz_cap = (dbg & LN_DBG_FORCE_TILE) ? (int) (tiles * ctx->C) : (int) (tiles * ctx->C / 64 + 1024);
         ctx->patch_cap = 1 << 20;
         CU(cudaMalloc(&ctx->d_hazlist, (size_t) ctx->haz_cap * 4));
+        CU(cudaMalloc(&ctx->d_lrecs, (size_t) ctx->E * ctx->C * sizeof(LineEpoch)));
+        CU(cudaMalloc(&ctx->d_elist, (size_t) ctx->E * ctx->C * 4));
         CU(cudaMalloc(&ctx->d_patches, (size_t) ctx->patch_cap * sizeof(LinePatch)));
         CU(cudaMalloc(&ctx->d_line_counters, 4 * sizeof(int)));
         CU(cudaMalloc(&ctx->d_line_totals, 4 * sizeof(unsigned long long)));
@@ -1161,7 +1173,7 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
         if (ss.stream) cudaStreamDestroy(ss.stream);
         cudaFree(ss.d_est); cudaFree(ss.d_exact_end);
     }
-    cudaFree(ctx->d_chips4); cudaFree(ctx->d_hazlist);
+    cudaFree(ctx->d_chips4); cudaFree(ctx->d_hazlist); cudaFree(ctx->d_lrecs); cudaFree(ctx->d_elist);
     for (int i = 0; i < NSETS; i++) { cudaFree(ctx->d_anch[i]); if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]); }
     cudaFree(ctx->d_patches); cudaFree(ctx->d_line_counters); cudaFree(ctx->d_line_totals);
     cudaFree(ctx->d_bias_rate); cudaFree(ctx->d_carr_start);
@@ -1246,13 +1258,16 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
     use_set(ctx, ctx->set_wr);
     const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
     const int EC = n_epochs * C;
-    // the code-NCO scan does not depend on the carrier chain: it runs beside it on the aux stream
-    CU(cudaEventRecord(fork, st));
-    CU(cudaStreamWaitEvent(aux, fork, 0));
-    k_scan_code<<<(EC + 63) / 64, 64, 0, aux>>>(desc_dev, ctx->d_code_ck, ctx->d_wrap_ck, EC, C, N, T, ntiles);
-    CU(cudaEventRecord(ctx->ev_code2, aux));
-    trace_mark(ctx, aux, "k_scan_code");
-    ctx->launches += 1;
+    // the code-NCO scan (only k_synth_lanes needs one: k_synth_line's code anchors are closed form) does not depend on
+    // the carrier chain: it runs beside it on the aux stream
+    if (!ctx->use_line) {
+        CU(cudaEventRecord(fork, st));
+        CU(cudaStreamWaitEvent(aux, fork, 0));
+        k_scan_code<<<(EC + 63) / 64, 64, 0, aux>>>(desc_dev, ctx->d_code_ck, ctx->d_wrap_ck, NULL, NULL, EC, C, N, T, ntiles);
+        CU(cudaEventRecord(ctx->ev_code2, aux));
+        trace_mark(ctx, aux, "k_scan_code");
+        ctx->launches += 1;
+    }
     if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && ctx->cfg.reserved[0] == 0) {
         const size_t ECmax = (size_t) ctx->E * C;
         double* eadv = ctx->d_drift;
@@ -1314,7 +1329,7 @@ static int enqueue_chain(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_
     ScanSet& set = ctx->sets[ctx->set_wr];
     CU(cudaMemcpyAsync(set.d_exact_end, ctx->d_carr_state, C * sizeof(double), cudaMemcpyDeviceToDevice, st));
     CU(cudaEventRecord(ctx->ev_final, st));
-    CU(cudaStreamWaitEvent(st, ctx->ev_code2, 0));  // scan_done covers the code scan on the side stream too
+    if (!ctx->use_line) CU(cudaStreamWaitEvent(st, ctx->ev_code2, 0));  // scan_done covers the code scan on the side stream too
     CU(cudaEventRecord(set.scan_done, st));
     set.phase = 3;
     ctx->set_wr = (ctx->set_wr + 1) % NSETS;
@@ -1361,10 +1376,17 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
         const int warps = n_epochs * C;
         const int intc = ctx->cfg.carrier_mode == GPSIQ_CARRIER_INT32;
         const uint32_t* ustart = intc ? ctx->d_ustart : NULL;
-        k_line_anchor<<<(warps + 3) / 4, 128, 0, st>>>(desc_dev, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx), ustart,
-                                                       ctx->d_flags, ctx->d_flags + ctx->E, anch, ctx->d_hazlist,
-                                                       ctx->d_line_counters, ctx->haz_cap, n_epochs, C, N, ntiles, dbg);
+        k_line_anchor<<<(warps + 3) / 4, 128, 0, st>>>(desc_dev, make_lookup(ctx), ustart, ctx->d_flags, ctx->d_flags + ctx->E,
+                                                       anch, ctx->d_lrecs, ctx->d_hazlist, ctx->d_line_counters,
+                                                       ctx->haz_cap, n_epochs, C, N, ntiles, dbg);
         trace_mark(ctx, st, "k_line_anchor");
+        k_line_check<<<(warps + 127) / 128, 128, 0, st>>>(desc_dev, ctx->d_lrecs, ctx->d_elist, ctx->d_line_counters, warps, N,
+                                                          intc, dbg);
+        k_line_refine<<<(dbg & LN_DBG_FORCE_CHUNK) ? 1024 : 64, 128, 0, st>>>(
+            desc_dev, ctx->d_lrecs, make_lookup(ctx), ustart, ctx->d_elist, ctx->d_flags + ctx->E, ctx->d_hazlist,
+            ctx->d_line_counters, ctx->haz_cap, C, N, ntiles, dbg);
+        trace_mark(ctx, st, "k_line_refine");
+        ctx->launches += 2;
         // The (tile, slot) pairs the check could not clear (one or two per thousand epochs): literal recurrence,
         // compared with the anchors' lines.  A serial 1024-sample walk per pair (~150 us): on the side stream,
         // beside the sample kernel; k_line_apply joins it.  (If its patch list overflowed it flags the epoch and
@@ -1372,7 +1394,7 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
         CU(cudaEventRecord(ctx->ev_P[0], st));
         CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_P[0], 0));
         k_line_patch<<<(dbg & LN_DBG_FORCE_TILE) ? 1024 : 8, 128, 0, ctx->aux_stream>>>(
-            desc_dev, ctx->d_lutp, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx), ustart, anch, ctx->d_chips4, ctx->d_hazlist,
+            desc_dev, ctx->d_lutp, make_lookup(ctx), ustart, anch, ctx->d_chips4, ctx->d_hazlist,
             ctx->d_line_counters, ctx->haz_cap, ctx->d_patches, ctx->patch_cap, ctx->d_flags + ctx->E, C, N, ntiles);
         CU(cudaEventRecord(ctx->ev_P[1], ctx->aux_stream));
         ctx->launches += 2;
@@ -1407,14 +1429,20 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
             ctx->last_ln.desc = desc_dev + (size_t) e0 * C; ctx->last_ln.iq = iq_dev + (size_t) e0 * N * 2;
             ctx->last_ln.ne = ne; ctx->last_ln.set = ctx->set_cur;
             ctx->last_ln.e0 = e0;
-            if (k == 0) CU(cudaStreamWaitEvent(st, ctx->ev_P[1], 0));  // the patch list is complete
+            if (k == 0) {
+                CU(cudaStreamWaitEvent(st, ctx->ev_P[1], 0));  // the patch list is complete (and the epoch flags final)
+                // exact code-NCO states for the epochs k_synth_lanes has to render (normally none: every thread returns)
+                k_scan_code<<<(n_epochs * C + 63) / 64, 64, 0, st>>>(desc_dev, ctx->d_code_ck, ctx->d_wrap_ck, ctx->d_flags,
+                                                                      ctx->d_flags + ctx->E, n_epochs * C, C, N, T, ntiles);
+                ctx->launches += 1;
+            }
             k_line_apply<<<4, 128, 0, st>>>(ctx->d_patches, ctx->d_line_counters, ctx->patch_cap,
                                             reinterpret_cast<uint32_t*>(iq_dev), (unsigned long long) e0 * N,
                                             (unsigned long long) (e0 + ne) * N, e0 == 0 ? ctx->d_line_totals : NULL);
             // epochs outside the line kernel's contract (or whose hazard / patch lists overflowed)
-            k_synth_lanes<<<ne * tile_groups, LANES_WARPS * 32, smem, st>>>(
+            k_synth_lanes<<<ne * LANES_FLAGGED_CTAS, LANES_WARPS * 32, smem, st>>>(
                 desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx), ctx->d_ustart, ctx->d_ca, ctx->d_flags,
-                ctx->d_flags + ctx->E, 1, iq_dev, e0, C, N, T, ntiles, tile_groups, ctx->cfg.carrier_mode);
+                ctx->d_flags + ctx->E, 1, iq_dev, e0, C, N, T, ntiles, tile_groups, LANES_FLAGGED_CTAS, ctx->cfg.carrier_mode);
             ctx->launches += 3;
             if (iq_host) {
                 CU(cudaEventRecord(ctx->ev_F[k & 1], st));
@@ -1428,7 +1456,7 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
         CU(cudaStreamWaitEvent(st, ctx->ev_P[0], 0));
         k_synth_lanes<<<n_epochs * tile_groups, LANES_WARPS * 32, smem, st>>>(
             desc_dev, ctx->d_lut, ctx->d_code_ck, ctx->d_wrap_ck, make_lookup(ctx), ctx->d_ustart, ctx->d_ca, ctx->d_flags,
-            ctx->d_flags + ctx->E, 0, iq_dev, 0, C, N, T, ntiles, tile_groups, ctx->cfg.carrier_mode);
+            ctx->d_flags + ctx->E, 0, iq_dev, 0, C, N, T, ntiles, tile_groups, tile_groups, ctx->cfg.carrier_mode);
         ctx->launches += 1;
         if (iq_host)
             CU(cudaMemcpyAsync(iq_host, iq_dev, (size_t) n_epochs * N * 4, cudaMemcpyDeviceToHost, st));
@@ -1875,10 +1903,17 @@ int gpsiq_timing_sample_kernel_isolated(gpsiq_ctx* ctx, int reps, float* kernel_
             ctx->last_ln.iq, ne, C, N, ntiles, ctx->cfg.carrier_mode == GPSIQ_CARRIER_INT32, ctx->d_err);
     }
     CU(cudaEventRecord(e1, ctx->stream));
+    // the re-launches rewrote the samples WITHOUT the batch's patches (k_line_apply): put them back, so that the
+    // output buffer still holds the exact stream afterwards (the patch list of the last rendered batch is intact)
+    k_line_apply<<<4, 128, 0, ctx->stream>>>(ctx->d_patches, ctx->d_line_counters, ctx->patch_cap,
+                                              reinterpret_cast<uint32_t*>(ctx->last_ln.iq) - (size_t) ctx->last_ln.e0 * N,
+                                              (unsigned long long) ctx->last_ln.e0 * N,
+                                              (unsigned long long) (ctx->last_ln.e0 + ctx->last_ln.ne) * N, NULL);
     CU(cudaEventSynchronize(e1));
+    CU(cudaStreamSynchronize(ctx->stream));
     float t = 0.f;
     CU(cudaEventElapsedTime(&t, e0, e1));
-    ctx->launches += reps + 1;
+    ctx->launches += reps + 2;
     *kernel_ms = t / reps;
     if (epochs_per_launch) *epochs_per_launch = ctx->last_ln.ne;
     return GPSIQ_OK;
@@ -1987,17 +2022,24 @@ int gpsiq_line_verify_host(const gpsiq_chan_desc* desc, int n_epochs, int C, int
             if (!(d.code_step > 0.0 && d.code_step <= 0.5) || !(fabs(d.carr_step) <= 0x1p-8)) return GPSIQ_ERR_ARG;  // line kernel's contract
             double cp = d.code_phase0;
             const uint64_t dF = ln_carr_slope(d.carr_step), dG = ln_code_slope(d.code_step);
+            const uint64_t G0 = ln_code_fixed(d.code_phase0);
+            int wraps = 0;  // code-period wraps of the recurrence since the epoch's first sample
             for (int t0 = 0; t0 < N; t0 += LN_TILE) {
                 const int len = (N - t0 < LN_TILE) ? N - t0 : LN_TILE;
-                const uint64_t FA = ln_carr_fixed(ph), GA = ln_code_fixed(cp);
-                const int64_t eF = ln_eps(1, LN_TILE), eG = ln_eps(0, LN_TILE);
+                // carrier anchor: the exact tile-start phase; code anchor: closed form on the epoch's line (k_line_anchor)
+                const uint64_t FA = ln_carr_fixed(ph);
+                uint64_t GA;
+                int wl;
+                ln_code_line(G0, dG, (uint32_t) t0, GA, wl);
+                const int64_t eF = ln_eps(1, LN_TILE), eG = ln_eps(0, (int64_t) t0 + len);
                 const bool hz = line_hazard(FA, dF, LN_FBITS, (uint64_t) len, -eF - LN_KF, eF) ||
                                 line_hazard(GA, dG, LN_GBITS, (uint64_t) len, -eG - LN_KG, eG);
-                int wraps = 0, differ = 0;
+                int differ = 0;
                 for (int n = 0; n < len; n++) {
                     int it = (int) floor(ph * 512.0);
                     if (it > 511) it = 511;
-                    const uint32_t chip_true = (uint32_t) ((int) cp + 1023 * wraps);  // unwrapped inside the tile, like G
+                    // chips since the code period the LINE is in at the tile start (G is not wrapped inside a tile)
+                    const uint32_t chip_true = (uint32_t) ((int) cp + 1023 * (wraps - wl));
                     uint32_t ci, gi;
                     ln_kernel_index(FA, GA, dF, dG, (uint32_t) n, ci, gi);
                     if (ci != (uint32_t) it || gi != chip_true) differ++;

@@ -86,28 +86,52 @@ GPSIQ_HD uint64_t ln_carr_slope_mode(double carr_step, int int_carrier) {
     return int_carrier ? (uint64_t) (int64_t) (int32_t) carr_step << 39 : ln_carr_slope(carr_step);
 }
 
-// ---- k_line_anchor ---------------------------------------------------------------
-// One warp per (epoch, slot).  Pass 1, chunk by chunk (32 tiles, lane = tile): the tile anchors
-//   anch[(e*ntiles + t)*C + c] = { F (carrier), G (code) + variant offset }
-// and, per chunk, the spread of the anchors around ONE line from the chunk's first anchor.  Pass 2:
-// lane j checks the carrier line of chunk j, lane 16+j the code line of chunk j (line_hazard), all
-// chunks of the epoch at once.  Pass 3, only for flagged chunks: every tile against its own anchor;
-// the (tile, slot) pairs that still cannot be cleared go to hazlist.
+// ---- anchors and the safety check -----------------------------------------------------
+// k_line_anchor   one warp per (epoch, slot), lane = tile: the tile anchors
+//                   anch[(e*ntiles + t)*C + c] = { F (carrier), G (code) + chip-table variant offset }
+//                 and the spread [lo, hi] of the carrier anchors around ONE line over the whole epoch (from the
+//                 epoch's first anchor).  The carrier anchors are the exact tile-start phases of the scan phases (or
+//                 the integer carrier's closed form); the CODE anchors are closed form too: the code NCO restarts at
+//                 every epoch from an exactly known phase (computeCodePhase, plutogpssim.c:1770), so after n steps
+//                 the true phase lies within ln_eps(0, n) of the straight fixed-point line from code_phase0 -- no
+//                 code-NCO scan is needed at all, the bound simply widens the hazard window along the epoch.
+// k_line_check    one THREAD per (epoch, slot): both lines of the whole epoch against their windows (line_hazard,
+//                 the Euclid-like descent: ~10^4 instructions, so packed 32 per warp and run once per epoch instead
+//                 of once per 32-tile chunk).  The ~1 % of (epoch, slot) pairs it cannot clear go to a list.
+// k_line_refine   one warp per listed pair: per chunk of 32 tiles (lane = chunk), then per tile of the flagged chunks
+//                 (lane = tile, each from its own anchor); the (tile, slot) pairs that still cannot be cleared go to
+//                 hazlist for k_line_patch.
 struct LineTile { uint64_t FA, GA, Fs, Gs; };
+struct LineEpoch { uint64_t F0; int64_t lo, hi; int active, pad; };  // per (epoch, slot), written by k_line_anchor
 
-__device__ __forceinline__ LineTile ln_tile_anchor(const gpsiq_chan_desc& d, const double* __restrict__ code_ck,
-                                                   const int* __restrict__ wrap_ck, const CarrLookup& carr,
-                                                   const uint32_t* __restrict__ ustart, int e, int c,
+// Closed-form code anchor of tile-relative sample n0 (epoch sample index): the epoch's code line G0 + n0*dG in exact
+// 128-bit integer arithmetic, reduced to (chips in [0,1023)) * 2^47 + the number of code-period wraps so far.
+GPSIQ_HD void ln_code_line(uint64_t G0, uint64_t dG, uint32_t n0, uint64_t& GA, int& wraps) {
+#if defined(__CUDA_ARCH__)
+    const uint64_t plo = (uint64_t) n0 * dG, phi = __umul64hi((uint64_t) n0, dG);
+#else
+    const unsigned __int128 pr = (unsigned __int128) n0 * dG;
+    const uint64_t plo = (uint64_t) pr, phi = (uint64_t) (pr >> 64);
+#endif
+    const uint64_t lo = plo + G0, hi = phi + (lo < plo ? 1u : 0u);
+    const uint32_t chips = (uint32_t) ((hi << (64 - LN_GBITS)) | (lo >> LN_GBITS));  // < 2^30: n0 < 2^31, step <= 0.5
+    const uint32_t w = chips / 1023u;
+    wraps = (int) w;
+    GA = ((uint64_t) (chips - w * 1023u) << LN_GBITS) | (lo & ((1ULL << LN_GBITS) - 1));
+}
+
+__device__ __forceinline__ LineTile ln_tile_anchor(const gpsiq_chan_desc& d, const CarrLookup& carr,
+                                                   const uint32_t* __restrict__ ustart, uint64_t G0, uint64_t dG, int e, int c,
                                                    int t, int C, int N, int ntiles, int dbg) {
     LineTile r;
-    const size_t o = ((size_t) e * ntiles + t) * C + c;
     if (ustart)  // integer carrier: closed form from the epoch's start phase
         r.FA = ln_int_fixed(ustart[(size_t) e * C + c] + (uint32_t) (int32_t) d.carr_step * (uint32_t) (t * LN_TILE));
     else
         r.FA = ln_carr_fixed(carr_lookup(carr, e, c, t, LN_TILE, N, C, ntiles));
-    r.GA = ln_code_fixed(code_ck[o]);
+    int wraps;
+    ln_code_line(G0, dG, (uint32_t) t * LN_TILE, r.GA, wraps);
     // NAV polarity at the tile start and after the next code-period wrap (plutogpssim.c:2714-2733)
-    const int wr = wrap_ck[o] + d.ms0 % 20;
+    const int wr = wraps + d.ms0 % 20;
     const uint32_t pol0 = (uint32_t) (d.navbits >> ((wr / 20) & 63)) & 1u;
     const uint32_t pol1 = (uint32_t) (d.navbits >> (((wr + 1) / 20) & 63)) & 1u;
     r.Fs = r.FA;
@@ -117,82 +141,123 @@ __device__ __forceinline__ LineTile ln_tile_anchor(const gpsiq_chan_desc& d, con
 }
 
 __global__ void __launch_bounds__(128)
-k_line_anchor(const gpsiq_chan_desc* __restrict__ desc, const double* __restrict__ code_ck,
-              const int* __restrict__ wrap_ck, const CarrLookup carr, const uint32_t* __restrict__ ustart,
-              const int* __restrict__ amp_sum,
-              int* __restrict__ step_flag, ulonglong2* __restrict__ anch, uint32_t* __restrict__ hazlist,
-              int* __restrict__ counters, int haz_cap, int E, int C, int N, int ntiles, int dbg) {
+k_line_anchor(const gpsiq_chan_desc* __restrict__ desc, const CarrLookup carr, const uint32_t* __restrict__ ustart,
+              const int* __restrict__ amp_sum, int* __restrict__ step_flag, ulonglong2* __restrict__ anch,
+              LineEpoch* __restrict__ recs, uint32_t* __restrict__ hazlist, int* __restrict__ counters, int haz_cap,
+              int E, int C, int N, int ntiles, int dbg) {
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int c = w % C, e = w / C;
     if (e >= E) return;
     const gpsiq_chan_desc d = desc[(size_t) e * C + c];
-    const int chunks = (ntiles + LN_CHUNK - 1) / LN_CHUNK;
+    LineEpoch rec;
+    rec.F0 = 0; rec.lo = 0; rec.hi = 0; rec.active = 0; rec.pad = 0;
     if (d.prn <= 0 || amp_sum[e] > 32767 || step_flag[e]) {  // inactive slot / epoch rendered by k_synth_lanes
         for (int t = lane; t < ntiles; t += 32) anch[((size_t) e * ntiles + t) * C + c] = make_ulonglong2(0, 0);
+        if (lane == 0) recs[(size_t) e * C + c] = rec;
         return;
     }
-    const bool int_carrier = ustart != nullptr;  // exact line: the carrier half of the check is skipped
+    const bool int_carrier = ustart != nullptr;
     const uint64_t dF = ln_carr_slope_mode(d.carr_step, int_carrier), dG = ln_code_slope(d.code_step);
-    const uint64_t gmask = (1ULL << LN_GBITS) - 1;
-    const int64_t eF = ln_eps(1, LN_TILE), eG = ln_eps(0, LN_TILE);
-    const bool force = (dbg & (LN_DBG_FORCE_CHUNK | LN_DBG_FORCE_TILE)) != 0;
-    for (int ch0 = 0; ch0 < chunks; ch0 += 16) {  // rounds of 16 chunks (one round up to 524288 samples per epoch)
-        const int nch = min(16, chunks - ch0);
-        uint64_t my_A = 0;       // lane j: F0 of chunk j; lane 16+j: G0 of chunk j
-        int64_t my_lo = 0, my_hi = 0;
-        for (int j = 0; j < nch; j++) {
-            const int t = (ch0 + j) * LN_CHUNK + lane;
-            const bool valid = t < ntiles;
-            LineTile a;
-            a.FA = a.GA = a.Fs = a.Gs = 0;
-            if (valid) {
-                a = ln_tile_anchor(d, code_ck, wrap_ck, carr, ustart, e, c, t, C, N, ntiles, dbg);
-                anch[((size_t) e * ntiles + t) * C + c] = make_ulonglong2(a.Fs, a.Gs);
-            }
-            const uint64_t F0 = __shfl_sync(0xffffffffu, a.FA, 0), G0 = __shfl_sync(0xffffffffu, a.GA, 0);
-            const uint64_t off = (uint64_t) lane * LN_TILE;
-            const int64_t dlF = valid ? (int64_t) (a.FA - (F0 + off * dF)) : 0;
-            // code: only G mod 2^47 matters (wraps and variant offsets are multiples of 2^47)
-            const int64_t dlG = valid ? (int64_t) (((a.GA - G0 - off * dG) & gmask) << (64 - LN_GBITS)) >> (64 - LN_GBITS) : 0;
-            int64_t loF = dlF, hiF = dlF, loG = dlG, hiG = dlG;
+    const uint64_t G0 = ln_code_fixed(d.code_phase0);
+    uint64_t F0 = 0;
+    int64_t lo = 0, hi = 0;
+    for (int t0 = 0; t0 < ntiles; t0 += 32) {
+        const int t = t0 + lane;
+        LineTile a;
+        a.FA = 0;
+        if (t < ntiles) {
+            a = ln_tile_anchor(d, carr, ustart, G0, dG, e, c, t, C, N, ntiles, dbg);
+            anch[((size_t) e * ntiles + t) * C + c] = make_ulonglong2(a.Fs, a.Gs);
+        }
+        if (t0 == 0) F0 = __shfl_sync(0xffffffffu, a.FA, 0);
+        if (t < ntiles) {
+            const int64_t dl = (int64_t) (a.FA - (F0 + (uint64_t) t * LN_TILE * dF));
+            lo = min(lo, dl); hi = max(hi, dl);   // (tile 0 contributes 0)
+        }
+    }
 #pragma unroll
-            for (int s = 16; s; s >>= 1) {
-                loF = min(loF, (int64_t) __shfl_xor_sync(0xffffffffu, loF, s));
-                hiF = max(hiF, (int64_t) __shfl_xor_sync(0xffffffffu, hiF, s));
-                loG = min(loG, (int64_t) __shfl_xor_sync(0xffffffffu, loG, s));
-                hiG = max(hiG, (int64_t) __shfl_xor_sync(0xffffffffu, hiG, s));
+    for (int s = 16; s; s >>= 1) {
+        lo = min(lo, (int64_t) __shfl_xor_sync(0xffffffffu, lo, s));
+        hi = max(hi, (int64_t) __shfl_xor_sync(0xffffffffu, hi, s));
+    }
+    if (lane == 0) {
+        rec.F0 = F0; rec.lo = lo; rec.hi = hi; rec.active = 1;
+        recs[(size_t) e * C + c] = rec;
+    }
+    if (dbg & LN_DBG_FORCE_TILE) {  // test hook: every tile goes through the literal-recurrence patch path
+        for (int t = lane; t < ntiles; t += 32) {
+            const int slot = atomicAdd(&counters[0], 1);
+            if (slot < haz_cap) hazlist[slot] = (uint32_t) (e * ntiles + t) * 32u + (uint32_t) c;
+            else atomicOr(&step_flag[e], 4);
+        }
+    }
+}
+
+// windows of the two lines over samples [n0, n0 + n) of the epoch, relative to the epoch's lines
+__device__ __forceinline__ bool ln_range_hazard(const LineEpoch& r, uint64_t dF, uint64_t G0, uint64_t dG, bool int_carrier,
+                                                uint32_t n0, uint32_t n) {
+    const int64_t eF = ln_eps(1, LN_TILE);                  // inside a tile, from the tile's own exact carrier anchor
+    const int64_t eG = ln_eps(0, (int64_t) n0 + n);         // the code line runs from the epoch's first sample
+    if (!int_carrier && line_hazard(r.F0 + (uint64_t) n0 * dF, dF, LN_FBITS, n, r.lo - eF - LN_KF, r.hi + eF)) return true;
+    return line_hazard(G0 + (uint64_t) n0 * dG, dG, LN_GBITS, n, -eG - LN_KG, eG);  // (only G mod 2^47 matters)
+}
+
+__global__ void __launch_bounds__(128)
+k_line_check(const gpsiq_chan_desc* __restrict__ desc, const LineEpoch* __restrict__ recs, uint32_t* __restrict__ elist,
+             int* __restrict__ counters, int EC, int N, int int_carrier, int dbg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= EC) return;
+    const LineEpoch r = recs[i];
+    if (!r.active || (dbg & LN_DBG_FORCE_TILE)) return;
+    const gpsiq_chan_desc d = desc[i];
+    const uint64_t dF = ln_carr_slope_mode(d.carr_step, int_carrier), dG = ln_code_slope(d.code_step);
+    const bool hz = (dbg & LN_DBG_FORCE_CHUNK) || ln_range_hazard(r, dF, ln_code_fixed(d.code_phase0), dG, int_carrier, 0u, (uint32_t) N);
+    if (hz) elist[atomicAdd(&counters[3], 1)] = (uint32_t) i;
+}
+
+__global__ void __launch_bounds__(128)
+k_line_refine(const gpsiq_chan_desc* __restrict__ desc, const LineEpoch* __restrict__ recs, const CarrLookup carr,
+              const uint32_t* __restrict__ ustart, const uint32_t* __restrict__ elist, int* __restrict__ step_flag,
+              uint32_t* __restrict__ hazlist, int* __restrict__ counters, int haz_cap, int C, int N, int ntiles, int dbg) {
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * 4;
+    const int count = counters[3];
+    const bool int_carrier = ustart != nullptr;
+    const int chunks = (ntiles + LN_CHUNK - 1) / LN_CHUNK;
+    for (int it = blockIdx.x * 4 + (threadIdx.x >> 5); it < count; it += nwarps) {
+        const int i = (int) elist[it];
+        const int e = i / C, c = i - e * C;
+        const gpsiq_chan_desc d = desc[i];
+        const LineEpoch r = recs[i];
+        const uint64_t dF = ln_carr_slope_mode(d.carr_step, int_carrier), dG = ln_code_slope(d.code_step);
+        const uint64_t G0 = ln_code_fixed(d.code_phase0);
+        if (lane == 0) atomicAdd(&counters[2], 1);  // diagnostic: (epoch, slot) pairs refined
+        for (int ch0 = 0; ch0 < chunks; ch0 += 32) {
+            const int ch = ch0 + lane;
+            bool hz = false;
+            if (ch < chunks) {
+                const uint32_t n0 = (uint32_t) ch * LN_CHUNK * LN_TILE;
+                const uint32_t n = (uint32_t) min(LN_CHUNK * LN_TILE, N - (int) n0);
+                hz = (dbg & LN_DBG_FORCE_CHUNK) || ln_range_hazard(r, dF, G0, dG, int_carrier, n0, n);
             }
-            if (lane == j) { my_A = F0; my_lo = loF - eF - LN_KF; my_hi = hiF + eF; }
-            if (lane == 16 + j) { my_A = G0; my_lo = loG - eG - LN_KG; my_hi = hiG + eG; }
-        }
-        // ---- chunk-level check, all chunks of the round at once
-        bool hz = false;
-        const int j = lane & 15;
-        if (j < nch && !force) {
-            const int n_chunk = min(LN_CHUNK * LN_TILE, N - (ch0 + j) * LN_CHUNK * LN_TILE);
-            hz = (lane < 16) ? (!int_carrier && line_hazard(my_A, dF, LN_FBITS, (uint64_t) n_chunk, my_lo, my_hi))
-                             : line_hazard(my_A, dG, LN_GBITS, (uint64_t) n_chunk, my_lo, my_hi);
-        }
-        uint32_t flagged = __ballot_sync(0xffffffffu, hz);
-        flagged = (flagged | (flagged >> 16)) & 0xffffu;
-        if (force) flagged = (1u << nch) - 1u;
-        if (lane == 0 && flagged) atomicAdd(&counters[2], __popc(flagged));  // diagnostic: flagged chunks
-        // ---- tile-level check of the flagged chunks, each tile from its own exact anchor
-        while (flagged) {
-            const int jj = __ffs(flagged) - 1;
-            flagged &= flagged - 1;
-            const int t = (ch0 + jj) * LN_CHUNK + lane;
-            if (t >= ntiles) continue;
-            const LineTile a = ln_tile_anchor(d, code_ck, wrap_ck, carr, ustart, e, c, t, C, N, ntiles, dbg);
-            const int len = min(LN_TILE, N - t * LN_TILE);
-            const bool hzt = (dbg & LN_DBG_FORCE_TILE) ||
-                             (!int_carrier && line_hazard(a.FA, dF, LN_FBITS, (uint64_t) len, -eF - LN_KF, eF)) ||
-                             line_hazard(a.GA, dG, LN_GBITS, (uint64_t) len, -eG - LN_KG, eG);
-            if (hzt) {
-                const int slot = atomicAdd(&counters[0], 1);
-                if (slot < haz_cap) hazlist[slot] = (uint32_t) (e * ntiles + t) * 32u + (uint32_t) c;
-                else atomicOr(&step_flag[e], 4);  // list full: the epoch is re-rendered by k_synth_lanes
+            uint32_t flagged = __ballot_sync(0xffffffffu, hz);
+            // ---- tile-level check of the flagged chunks, each tile from its own anchor
+            while (flagged) {
+                const int jj = __ffs(flagged) - 1;
+                flagged &= flagged - 1;
+                const int t = (ch0 + jj) * LN_CHUNK + lane;
+                if (t >= ntiles) continue;
+                const LineTile a = ln_tile_anchor(d, carr, ustart, G0, dG, e, c, t, C, N, ntiles, 0);
+                const int len = min(LN_TILE, N - t * LN_TILE);
+                const int64_t eF = ln_eps(1, LN_TILE), eG = ln_eps(0, (int64_t) t * LN_TILE + len);
+                const bool hzt = (!int_carrier && line_hazard(a.FA, dF, LN_FBITS, (uint64_t) len, -eF - LN_KF, eF)) ||
+                                 line_hazard(a.GA, dG, LN_GBITS, (uint64_t) len, -eG - LN_KG, eG);
+                if (hzt) {
+                    const int slot = atomicAdd(&counters[0], 1);
+                    if (slot < haz_cap) hazlist[slot] = (uint32_t) (e * ntiles + t) * 32u + (uint32_t) c;
+                    else atomicOr(&step_flag[e], 4);  // list full: the epoch is re-rendered by k_synth_lanes
+                }
             }
         }
     }
@@ -202,8 +267,7 @@ k_line_anchor(const gpsiq_chan_desc* __restrict__ desc, const double* __restrict
 // One thread per listed (tile, slot): the literal recurrences of plutogpssim.c:2697-2746 from the exact
 // tile-start state, compared sample by sample with what k_synth_line computes from the anchors.
 __global__ void __launch_bounds__(128)
-k_line_patch(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict__ lutp,
-             const double* __restrict__ code_ck, const int* __restrict__ wrap_ck, const CarrLookup carr,
+k_line_patch(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict__ lutp, const CarrLookup carr,
              const uint32_t* __restrict__ ustart,
              const ulonglong2* __restrict__ anch, const int8_t* __restrict__ chips4,
              const uint32_t* __restrict__ hazlist, int* __restrict__ counters, int haz_cap,
@@ -218,12 +282,16 @@ k_line_patch(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict
         const gpsiq_chan_desc d = desc[ec];
         const size_t o = ((size_t) e * ntiles + t) * C + c;
         const int len = min(LN_TILE, N - t * LN_TILE);
-        double cp = code_ck[o];
+        // exact code-NCO state at the tile start: the recurrence restarts at every epoch (plutogpssim.c:1770), so it is
+        // the exact fast-forward over the t * 1024 samples before the tile
+        double cp = d.code_phase0;
+        int wraps0 = 0;
+        nco_advance<NCO_CODE>(cp, d.code_step, step_info(d.code_step), t * LN_TILE, wraps0);
         const bool int_carrier = ustart != nullptr;
         double ph = int_carrier ? 0.0 : carr_lookup(carr, e, c, t, LN_TILE, N, C, ntiles);
         const uint32_t ustep = (uint32_t) (int32_t) d.carr_step;
         uint32_t u = int_carrier ? ustart[ec] + ustep * (uint32_t) (t * LN_TILE) : 0u;
-        const int wr = wrap_ck[o] + d.ms0 % 20;
+        const int wr = wraps0 + d.ms0 % 20;
         int kbit = wr / 20, icode = wr - kbit * 20;
         const ulonglong2 a = anch[o];
         const uint64_t dF = ln_carr_slope_mode(d.carr_step, int_carrier), dG = ln_code_slope(d.code_step);

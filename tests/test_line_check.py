@@ -144,9 +144,10 @@ def test_generic_lines_are_not_flagged():
 @pytest.mark.parametrize("name,epochs", [("static12", 10), ("circle12", 12), ("allsky32", 4)])
 def test_line_kernel_indices_on_reference_descriptors(name, epochs):
     """Whole epochs of reference-derived descriptors (300000 samples each): every sample's table and chip index, as
-    k_synth_line evaluates it from exact tile anchors, equals the literal recurrence's in every tile the check
-    clears; and the check clears almost all tiles (the patch path must stay a rarity)."""
+    k_synth_line evaluates it from its tile anchors (carrier: exact tile-start phase; code: closed form on the epoch's
+    line, whose deviation bound grows along the epoch), equals the literal recurrence's in every tile the check
+    clears; and the check clears almost all tiles (the patch path must stay a rarity: ~1e-4 of the tiles)."""
     desc = ol.load_golden_desc(name)[:epochs]
     tiles, flagged, bad, _ = capi.line_verify(desc, 300000)
     assert tiles > 0 and bad == 0, (tiles, flagged, bad)
-    assert flagged <= max(2, tiles // 20000), (tiles, flagged)
+    assert flagged <= max(4, tiles // 4000), (tiles, flagged)
