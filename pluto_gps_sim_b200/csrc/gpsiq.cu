@@ -85,6 +85,9 @@ struct ScanSet {
     double* d_drift; CarrSpec* d_spec; CarrSpec* d_specE; ChunkInfo* d_cinfo; CarrInfo* d_info;
     CarrSpec* d_specG; GroupInfo* d_ginfo; double* d_traceG;
     double* d_adv; double* d_carr_trace; uint32_t* d_ustart;
+    LineEpoch* d_lrecs; uint32_t* d_elist; uint32_t* d_hazlist; int* d_line_counters; LinePatch* d_patches;
+    int anchored;                 // the batch's tile anchors, safety check and patch list have been enqueued
+    cudaEvent_t anch_ready, anchor_done;   // anchors written (the sample kernel may start) / patch list complete
     double* d_est;                // [C] estimated phases at the first sample of the batch (pipelined submits)
     double* d_exact_end;          // [C] exact phases after the batch's last sample (once its chain has run)
     cudaStream_t stream;          // pipelined submits: each set scans on its own stream, so that the scans of
@@ -795,6 +798,8 @@ static void use_set(gpsiq_ctx* ctx, int i) {
     ctx->d_spec = ss.d_spec; ctx->d_specE = ss.d_specE; ctx->d_cinfo = ss.d_cinfo; ctx->d_info = ss.d_info;
     ctx->d_specG = ss.d_specG; ctx->d_ginfo = ss.d_ginfo; ctx->d_traceG = ss.d_traceG;
     ctx->d_adv = ss.d_adv; ctx->d_carr_trace = ss.d_carr_trace; ctx->d_ustart = ss.d_ustart;
+    ctx->d_lrecs = ss.d_lrecs; ctx->d_elist = ss.d_elist; ctx->d_hazlist = ss.d_hazlist;
+    ctx->d_line_counters = ss.d_line_counters; ctx->d_patches = ss.d_patches;
     ctx->set_cur = i;
 }
 
@@ -965,7 +970,12 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
     CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&ctx->ev_sub[0], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_sub[1], cudaEventDisableTiming));
-    CU(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    {   // the patch walk of the batch being rendered runs beside its sample kernel and must be done when that ends:
+        // highest priority, so that its few blocks get SM slots at once
+        int plo = 0, phi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&plo, &phi));
+        CU(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, phi));
+    }
     CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming));
@@ -1077,11 +1087,17 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
         const int dbg = cfg->reserved[1];
         ctx->haz_cap = (dbg & LN_DBG_FORCE_TILE) ? (int) (tiles * ctx->C) : (int) (tiles * ctx->C / 64 + 1024);
         ctx->patch_cap = 1 << 20;
-        CU(cudaMalloc(&ctx->d_hazlist, (size_t) ctx->haz_cap * 4));
-        CU(cudaMalloc(&ctx->d_lrecs, (size_t) ctx->E * ctx->C * sizeof(LineEpoch)));
-        CU(cudaMalloc(&ctx->d_elist, (size_t) ctx->E * ctx->C * 4));
-        CU(cudaMalloc(&ctx->d_patches, (size_t) ctx->patch_cap * sizeof(LinePatch)));
-        CU(cudaMalloc(&ctx->d_line_counters, 4 * sizeof(int)));
+        for (int i = 0; i < NSETS; i++) {   // per scan set: a batch's anchors / check / patch list are made right after its chain
+            ScanSet& ss = ctx->sets[i];
+            CU(cudaMalloc(&ss.d_hazlist, (size_t) ctx->haz_cap * 4));
+            CU(cudaMalloc(&ss.d_lrecs, (size_t) ctx->E * ctx->C * sizeof(LineEpoch)));
+            CU(cudaMalloc(&ss.d_elist, (size_t) ctx->E * ctx->C * 4));
+            CU(cudaMalloc(&ss.d_patches, (size_t) ctx->patch_cap * sizeof(LinePatch)));
+            CU(cudaMalloc(&ss.d_line_counters, 4 * sizeof(int)));
+            CU(cudaEventCreateWithFlags(&ss.anchor_done, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ss.anch_ready, cudaEventDisableTiming));
+        }
+        use_set(ctx, 0);
         CU(cudaMalloc(&ctx->d_line_totals, 4 * sizeof(unsigned long long)));
         CU(cudaMemset(ctx->d_line_totals, 0, 4 * sizeof(unsigned long long)));
         // chip/NAV sign tables: variant v = pol0*2 + pol1; entry k < 1023: chip k under NAV bit pol0,
@@ -1172,10 +1188,13 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
         if (ss.est_done) cudaEventDestroy(ss.est_done);
         if (ss.stream) cudaStreamDestroy(ss.stream);
         cudaFree(ss.d_est); cudaFree(ss.d_exact_end);
+        cudaFree(ss.d_hazlist); cudaFree(ss.d_lrecs); cudaFree(ss.d_elist); cudaFree(ss.d_patches); cudaFree(ss.d_line_counters);
+        if (ss.anchor_done) cudaEventDestroy(ss.anchor_done);
+        if (ss.anch_ready) cudaEventDestroy(ss.anch_ready);
     }
-    cudaFree(ctx->d_chips4); cudaFree(ctx->d_hazlist); cudaFree(ctx->d_lrecs); cudaFree(ctx->d_elist);
+    cudaFree(ctx->d_chips4);
     for (int i = 0; i < NSETS; i++) { cudaFree(ctx->d_anch[i]); if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]); }
-    cudaFree(ctx->d_patches); cudaFree(ctx->d_line_counters); cudaFree(ctx->d_line_totals);
+    cudaFree(ctx->d_line_totals);
     cudaFree(ctx->d_bias_rate); cudaFree(ctx->d_carr_start);
     if (ctx->d_mbox_peer) cudaIpcCloseMemHandle(ctx->d_mbox_peer);
     cudaFree(ctx->d_mbox);
@@ -1222,6 +1241,7 @@ static int enqueue_prepare(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int 
     set.desc = desc_dev;
     set.n_epochs = n_epochs;
     set.phase = 1;
+    set.anchored = 0;
     set.seq = ctx->seq++;
     if (ctx->ev_count < TIMING_RING && st != ctx->scan_stream) CU(cudaEventRecord(ctx->ev[ctx->ev_count][0], st));
     CU(cudaMemsetAsync(ctx->d_flags, 0, 2 * (size_t) ctx->E * sizeof(int), st));
@@ -1353,6 +1373,46 @@ static CarrLookup make_lookup(const gpsiq_ctx* ctx) {
     return L;
 }
 
+// Phase 1d (line kernel): tile anchors, the safety check and the literal-recurrence walk of the tiles it cannot clear,
+// for the set the working pointers are on.  Everything here depends only on the scan results, so pipelined submits
+// enqueue it right behind the batch's chain on the set's own stream (long before the batch is rendered); the phase API
+// of time-sliced runs leaves it to the render call, so that a ring hop is not held up by it.
+static int enqueue_anchor(gpsiq_ctx* ctx, ScanSet& set, cudaStream_t st, cudaStream_t st_patch) {
+    const gpsiq_chan_desc* desc_dev = set.desc;
+    const int n_epochs = set.n_epochs;
+    const int C = ctx->C, N = ctx->N, ntiles = ctx->ntiles;
+    const int dbg = ctx->cfg.reserved[1];
+    ulonglong2* anch = ctx->d_anch[ctx->set_cur];
+    CU(cudaMemsetAsync(ctx->d_line_counters, 0, 4 * sizeof(int), st));
+    const int warps = n_epochs * C;
+    const int intc = ctx->cfg.carrier_mode == GPSIQ_CARRIER_INT32;
+    const uint32_t* ustart = intc ? ctx->d_ustart : NULL;
+    k_line_anchor<<<(warps + 3) / 4, 128, 0, st>>>(desc_dev, make_lookup(ctx), ustart, ctx->d_flags, ctx->d_flags + ctx->E,
+                                                   anch, ctx->d_lrecs, ctx->d_hazlist, ctx->d_line_counters,
+                                                   ctx->haz_cap, n_epochs, C, N, ntiles, dbg);
+    trace_mark(ctx, st, "k_line_anchor");
+    k_line_check<<<(warps + 127) / 128, 128, 0, st>>>(desc_dev, ctx->d_lrecs, ctx->d_elist, ctx->d_line_counters, warps, N,
+                                                      intc, dbg);
+    k_line_refine<<<(dbg & LN_DBG_FORCE_CHUNK) ? 1024 : 64, 128, 0, st>>>(
+        desc_dev, ctx->d_lrecs, make_lookup(ctx), ustart, ctx->d_elist, ctx->d_flags + ctx->E, ctx->d_hazlist,
+        ctx->d_line_counters, ctx->haz_cap, C, N, ntiles, dbg);
+    trace_mark(ctx, st, "k_line_refine");
+    // The (tile, slot) pairs the check could not clear (~1e-4 of them): exact code-NCO state from the epoch's start,
+    // then the literal recurrence over the tile, compared with the anchors' lines -> patch list.  (If a list
+    // overflows the epoch is flagged and k_synth_lanes, which runs last, re-renders it.)
+    CU(cudaEventRecord(set.anch_ready, st));
+    if (st_patch != st) CU(cudaStreamWaitEvent(st_patch, set.anch_ready, 0));
+    k_line_patch<<<(dbg & LN_DBG_FORCE_TILE) ? 1024 : 8, 128, 0, st_patch>>>(
+        desc_dev, ctx->d_lutp, make_lookup(ctx), ustart, anch, ctx->d_chips4, ctx->d_hazlist,
+        ctx->d_line_counters, ctx->haz_cap, ctx->d_patches, ctx->patch_cap, ctx->d_flags + ctx->E, C, N, ntiles);
+    trace_mark(ctx, st_patch, "k_line_patch");
+    CU(cudaEventRecord(set.anchor_done, st_patch));
+    set.anchored = 1;
+    ctx->launches += 4;
+    CU(cudaGetLastError());
+    return GPSIQ_OK;
+}
+
 static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int16_t* iq_host = NULL) {
     if (ctx->set_pending < 1 || ctx->sets[ctx->set_rd].phase != 3)
         return fail(ctx, GPSIQ_ERR_ARG, "nothing to render (scan phases of a batch must complete first)", cudaSuccess);
@@ -1370,34 +1430,13 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
     CU(cudaEventRecord(ctx->ev_chain, st));
     CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_chain, 0));
     if (ctx->use_line) {
-        const int dbg = ctx->cfg.reserved[1];
         ulonglong2* anch = ctx->d_anch[ctx->set_cur];
-        CU(cudaMemsetAsync(ctx->d_line_counters, 0, 4 * sizeof(int), st));
-        const int warps = n_epochs * C;
         const int intc = ctx->cfg.carrier_mode == GPSIQ_CARRIER_INT32;
-        const uint32_t* ustart = intc ? ctx->d_ustart : NULL;
-        k_line_anchor<<<(warps + 3) / 4, 128, 0, st>>>(desc_dev, make_lookup(ctx), ustart, ctx->d_flags, ctx->d_flags + ctx->E,
-                                                       anch, ctx->d_lrecs, ctx->d_hazlist, ctx->d_line_counters,
-                                                       ctx->haz_cap, n_epochs, C, N, ntiles, dbg);
-        trace_mark(ctx, st, "k_line_anchor");
-        k_line_check<<<(warps + 127) / 128, 128, 0, st>>>(desc_dev, ctx->d_lrecs, ctx->d_elist, ctx->d_line_counters, warps, N,
-                                                          intc, dbg);
-        k_line_refine<<<(dbg & LN_DBG_FORCE_CHUNK) ? 1024 : 64, 128, 0, st>>>(
-            desc_dev, ctx->d_lrecs, make_lookup(ctx), ustart, ctx->d_elist, ctx->d_flags + ctx->E, ctx->d_hazlist,
-            ctx->d_line_counters, ctx->haz_cap, C, N, ntiles, dbg);
-        trace_mark(ctx, st, "k_line_refine");
-        ctx->launches += 2;
-        // The (tile, slot) pairs the check could not clear (one or two per thousand epochs): literal recurrence,
-        // compared with the anchors' lines.  A serial 1024-sample walk per pair (~150 us): on the side stream,
-        // beside the sample kernel; k_line_apply joins it.  (If its patch list overflowed it flags the epoch and
-        // k_synth_lanes, which runs last, re-renders it.)
-        CU(cudaEventRecord(ctx->ev_P[0], st));
-        CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_P[0], 0));
-        k_line_patch<<<(dbg & LN_DBG_FORCE_TILE) ? 1024 : 8, 128, 0, ctx->aux_stream>>>(
-            desc_dev, ctx->d_lutp, make_lookup(ctx), ustart, anch, ctx->d_chips4, ctx->d_hazlist,
-            ctx->d_line_counters, ctx->haz_cap, ctx->d_patches, ctx->patch_cap, ctx->d_flags + ctx->E, C, N, ntiles);
-        CU(cudaEventRecord(ctx->ev_P[1], ctx->aux_stream));
-        ctx->launches += 2;
+        if (!set.anchored) {  // phase API: anchors here, the patch walk on the side stream beside the sample kernel
+            int rca = enqueue_anchor(ctx, set, st, ctx->aux_stream);
+            if (rca) return rca;
+        }
+        CU(cudaStreamWaitEvent(st, set.anch_ready, 0));
         if (ctx->render_waits_spec && ctx->set_pending >= 2 && ctx->sets[(ctx->set_rd + 1) % NSETS].phase >= 2 &&
             ctx->cfg.reserved[0] == 0 && !intc) {
             // Another batch has been submitted ahead.  Its chunk speculation wants the whole GPU (one chain per
@@ -1430,7 +1469,7 @@ static int enqueue_render(gpsiq_ctx* ctx, int16_t* iq_dev, cudaStream_t st, int1
             ctx->last_ln.ne = ne; ctx->last_ln.set = ctx->set_cur;
             ctx->last_ln.e0 = e0;
             if (k == 0) {
-                CU(cudaStreamWaitEvent(st, ctx->ev_P[1], 0));  // the patch list is complete (and the epoch flags final)
+                CU(cudaStreamWaitEvent(st, set.anchor_done, 0));  // the patch list is complete (and the epoch flags final)
                 // exact code-NCO states for the epochs k_synth_lanes has to render (normally none: every thread returns)
                 k_scan_code<<<(n_epochs * C + 63) / 64, 64, 0, st>>>(desc_dev, ctx->d_code_ck, ctx->d_wrap_ck, ctx->d_flags,
                                                                       ctx->d_flags + ctx->E, n_epochs * C, C, N, T, ntiles);
@@ -1566,6 +1605,9 @@ static int submit_common(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_
     if (!rc && spec) rc = pipelined_estimate(ctx, set, ss);
     if (!rc) rc = enqueue_speculate(ctx, set.d_descbuf, n_epochs, ss, spec ? set.d_est : NULL);
     if (!rc) rc = enqueue_chain(ctx, set.d_descbuf, n_epochs, ss);
+    // (enqueue_chain moved the write index on: the set is still the working one.)  The sample kernel needs the anchors
+    // (anch_ready); the patch list (anchor_done) only has to be complete when the sample kernel ends.
+    if (!rc && ctx->use_line) rc = enqueue_anchor(ctx, set, ss, ss);
     return rc;
 }
 
