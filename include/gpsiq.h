@@ -124,6 +124,25 @@ int gpsiq_submit(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc, int n_epochs);
 int gpsiq_fetch(gpsiq_ctx *ctx, int16_t *iq_out);
 int gpsiq_fetch_device(gpsiq_ctx *ctx, int16_t *iq_dev, void *cuda_stream);
 
+/* One stream over several GPUs of THIS process (the reference's epoch loop, plutogpssim.c:2655-2806, over N devices;
+ * time slices, the carrier phase handed from slice to slice).  Consecutive batches go to consecutive
+ * devices cfg->device, cfg->device + 1, ...; the exact carrier chain of a batch starts from the state the previous
+ * batch left on its device (two small asynchronous copies ordered by events; no host synchronisation, no kernel).
+ * Same contract as gpsiq_submit / gpsiq_fetch: host descriptors in, host I/Q out, results identical to one context
+ * fed batch by batch.  Up to 3 batches per device may be submitted ahead; gpsiq_multi_fetch_begin starts the rendering
+ * and the device-to-host copies of the oldest submitted batch without waiting (at most two begun per device),
+ * gpsiq_multi_fetch_end waits for the oldest begun one; gpsiq_multi_fetch = begin + end. */
+typedef struct gpsiq_multi gpsiq_multi;
+int gpsiq_multi_create(gpsiq_multi **m, const gpsiq_config *cfg, int n_devices);
+void gpsiq_multi_destroy(gpsiq_multi *m);
+int gpsiq_multi_submit(gpsiq_multi *m, const gpsiq_chan_desc *desc, int n_epochs);
+int gpsiq_multi_fetch_begin(gpsiq_multi *m, int16_t *iq_out);
+int gpsiq_multi_fetch_end(gpsiq_multi *m);
+int gpsiq_multi_fetch(gpsiq_multi *m, int16_t *iq_out);
+int gpsiq_multi_devices(const gpsiq_multi *m);
+int64_t gpsiq_multi_launch_count(const gpsiq_multi *m);
+const char *gpsiq_multi_last_error(const gpsiq_multi *m);
+
 /* Carrier phase per slot after the last synthesized epoch (max_chan values;
  * INT32 mode: the uint32 phase as a double) — chan[i].carr_phase after
  * plutogpssim.c:2741-2748.  Used for time-slice hand-off between GPUs. */

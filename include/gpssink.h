@@ -76,6 +76,12 @@ int gpssink_push(gpssink *s, const int16_t *iq, size_t pairs);
 int64_t gpssink_submit(gpssink *s, const int16_t *iq, size_t pairs);
 int gpssink_wait(gpssink *s, int64_t ticket);
 
+/* Stop as fast as the device allows: the writer finishes the push unit it is in (0.1 s of signal on the radio), every
+ * batch still queued -- and anything submitted later -- is discarded (its ticket completes with GPSSINK_OK), and
+ * gpssink_close then shuts the device down at once.  What the reference does on SIGINT: the TX thread leaves its loop
+ * after the current buffer and powers the TX LO down (plutogpssim.c:2014-2022, 2143-2178).  Async-signal-unsafe. */
+int gpssink_abort(gpssink *s);
+
 /* Totals so far: pairs accepted by the sink, device pushes (radio) / writes (file). */
 int gpssink_stats(gpssink *s, int64_t *pairs, int64_t *pushes);
 /* Drains the writer, shuts the radio down the way the reference does (TX LO off, buffer destroyed, channels

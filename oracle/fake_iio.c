@@ -18,6 +18,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "stubs/iio.h"
 #include "stubs/ad9361.h"
@@ -122,6 +123,10 @@ void *iio_buffer_start(const struct iio_buffer *b) { return b->data; }
 
 ssize_t iio_buffer_push(struct iio_buffer *b) {
     b->pushes++;
+    {   /* optional real-time pace (a Pluto takes 0.1 s per 300000-sample buffer at 3 MS/s): $FAKE_IIO_PUSH_SLEEP_MS */
+        const char *ms = getenv("FAKE_IIO_PUSH_SLEEP_MS");
+        if (ms && atoi(ms) > 0) { struct timespec ts = {atoi(ms) / 1000, (long) (atoi(ms) % 1000) * 1000000L}; nanosleep(&ts, NULL); }
+    }
     if (memcmp(b->data, b->prev, b->bytes) != 0) {   /* prev starts all-zero: zero pushes are dropped too */
         if (b->out) fwrite(b->data, 1, b->bytes, b->out);
         memcpy(b->prev, b->data, b->bytes);

@@ -86,6 +86,15 @@ SYMBOLS = {
     "gpsiq_prepare_device": (_i, [_vp, _vp, _i, _vp, _vp]),
     "gpsiq_speculate_device": (_i, [_vp, _vp, _i, _vp]),
     "gpsiq_chain_device": (_i, [_vp, _vp, _i, _vp]),
+    "gpsiq_multi_create": (_i, [C.POINTER(_vp), _vp, _i]),
+    "gpsiq_multi_destroy": (None, [_vp]),
+    "gpsiq_multi_submit": (_i, [_vp, _vp, _i]),
+    "gpsiq_multi_fetch_begin": (_i, [_vp, _vp]),
+    "gpsiq_multi_fetch_end": (_i, [_vp]),
+    "gpsiq_multi_fetch": (_i, [_vp, _vp]),
+    "gpsiq_multi_devices": (_i, [_vp]),
+    "gpsiq_multi_launch_count": (_i64, [_vp]),
+    "gpsiq_multi_last_error": (C.c_char_p, [_vp]),
     "gpsiq_estimate_fold_device": (_i, [_vp, _vp, _vp]),
     "gpsiq_carrier_fold_device": (_i, [_vp, _vp, _vp]),
     "gpsiq_estimate_anchor_device": (_i, [_vp, _vp]),

@@ -171,6 +171,7 @@ struct gpsiq_ctx {
     int16_t* d_iq;        // [E][N][2]
     int16_t* d_iq2;       // second output buffer for the host streaming pair (allocated on first use)
     gpsiq_chan_desc* h_stage[NSETS];
+    double* d_adv_prev;           // [2C] multi-device streams: the previous batch's closed-form advance, copied from its device
     long long seq;                // batches begun so far
     cudaEvent_t ev_final;         // the last exact chain enqueued (on any stream) has run
     int fetch_count;              // host fetches so far (alternates the two device output buffers)
@@ -239,7 +240,11 @@ __global__ void k_prepare(const gpsiq_chan_desc* __restrict__ desc, int2* __rest
         eadv_frac[ec] = (p - floor(p)) + ((pe + dest) - bias_rate[ec % C]);
         drift[(size_t) gridDim.x + ec] = (d.flags & GPSIQ_FLAG_RESET_CARRIER) ? d.carr_phase0 : -1.0;  // ereset
     }
-    if (d.prn > 32 || !(d.code_phase0 >= 0.0 && d.code_phase0 < 1023.0) || !(d.code_step > 0.0 && d.code_step < 1023.0)) {
+    // (the descriptor's NAV window is 64 bits: an epoch may not reach past it -- the kernels index it modulo 64 and the
+    // reference's own bit fetch, plutogpssim.c:2732, has no such limit)
+    const bool nav_window_ok = ((double) (d.ms0 % 20) + (double) N * d.code_step / 1023.0 + 1.0) / 20.0 < 64.0;
+    if (d.prn > 32 || !(d.code_phase0 >= 0.0 && d.code_phase0 < 1023.0) || !(d.code_step > 0.0 && d.code_step < 1023.0) ||
+        !nav_window_ok) {
         if (threadIdx.x == 0) atomicExch(err, 1 + ec);
         return;
     }
@@ -1052,6 +1057,7 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
     CU(cudaMalloc(&ctx->d_bias_rate, ctx->C * sizeof(double)));
     CU(cudaMemset(ctx->d_bias_rate, 0, ctx->C * sizeof(double)));
     CU(cudaMalloc(&ctx->d_carr_start, ctx->C * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_adv_prev, 2 * ctx->C * sizeof(double)));
     CU(cudaMalloc(&ctx->d_ca, 33 * CA_WORDS * sizeof(uint32_t)));
     CU(cudaMalloc(&ctx->d_iq, (size_t) ctx->E * ctx->N * 4));
     CU(cudaMalloc(&ctx->d_sums, (size_t) ctx->E * sizeof(unsigned long long)));
@@ -1195,7 +1201,7 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
     cudaFree(ctx->d_chips4);
     for (int i = 0; i < NSETS; i++) { cudaFree(ctx->d_anch[i]); if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]); }
     cudaFree(ctx->d_line_totals);
-    cudaFree(ctx->d_bias_rate); cudaFree(ctx->d_carr_start);
+    cudaFree(ctx->d_bias_rate); cudaFree(ctx->d_carr_start); cudaFree(ctx->d_adv_prev);
     if (ctx->d_mbox_peer) cudaIpcCloseMemHandle(ctx->d_mbox_peer);
     cudaFree(ctx->d_mbox);
     cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_est_state); cudaFree(ctx->d_ca);
@@ -1656,6 +1662,170 @@ int gpsiq_fetch(gpsiq_ctx* ctx, int16_t* iq_out) {
     CU(cudaStreamSynchronize(ctx->copy_stream));
     return rc;
 }
+
+// ---- one stream over several GPUs of this process ---------------------------------------------------------------
+// The C-level multi-GPU driver ("one process, N devices"; the reference's epoch loop, plutogpssim.c:2655-2806,
+// over N devices): consecutive batches of ONE stream go to consecutive devices, each through the ordinary pipelined
+// submit of its context.  The only state that crosses a batch boundary is the carrier phase (plutogpssim.c:2741-2746):
+// the exact chain of batch j starts from a copy of the carrier state batch j-1 left on ITS device, ordered by that
+// context's chain event (stream waits work across devices); start-phase estimates are folded from the batch before
+// last exactly as in one context.  No host synchronisation, no kernel for the hand-off: two small async copies.
+#define MULTI_MAX_DEV 16
+struct MultiSlot { ScanSet* set; int dev; long long seq; };
+struct gpsiq_multi {
+    int n;
+    gpsiq_ctx* sub[MULTI_MAX_DEV];
+    long long seq_submit, seq_begin, seq_end;
+    MultiSlot ring[MULTI_MAX_DEV * NSETS];
+    char err[256];
+};
+
+static int mfail(gpsiq_multi* m, int code, const char* what, gpsiq_ctx* c) {
+    snprintf(m ? m->err : g_err, 256, "%.60s%s%.180s", what, c ? ": " : "", c ? c->err : "");
+    return code;
+}
+
+int gpsiq_multi_create(gpsiq_multi** out, const gpsiq_config* cfg, int n_devices) {
+    if (!out || !cfg || n_devices < 1 || n_devices > MULTI_MAX_DEV) return fail(NULL, GPSIQ_ERR_ARG, "gpsiq_multi_create: bad argument", cudaSuccess);
+    *out = NULL;
+    gpsiq_multi* m = (gpsiq_multi*) calloc(1, sizeof *m);
+    if (!m) return fail(NULL, GPSIQ_ERR_NOMEM, "gpsiq_multi_create: out of host memory", cudaSuccess);
+    m->n = n_devices;
+    for (int i = 0; i < n_devices; i++) {
+        gpsiq_config c = *cfg;
+        c.device = cfg->device + i;
+        const int rc = gpsiq_create(&m->sub[i], &c);
+        if (rc != GPSIQ_OK) {  // (the message is in the global error text)
+            for (int k = 0; k < i; k++) gpsiq_destroy(m->sub[k]);
+            free(m);
+            return rc;
+        }
+    }
+    for (int i = 0; i < n_devices; i++)  // direct peer copies where the topology allows them (else the driver stages them)
+        for (int k = 0; k < n_devices; k++) {
+            int can = 0;
+            if (i != k && cudaDeviceCanAccessPeer(&can, cfg->device + i, cfg->device + k) == cudaSuccess && can) {
+                cudaSetDevice(cfg->device + i);
+                cudaDeviceEnablePeerAccess(cfg->device + k, 0);
+            }
+        }
+    cudaGetLastError();
+    *out = m;
+    return GPSIQ_OK;
+}
+
+void gpsiq_multi_destroy(gpsiq_multi* m) {
+    if (!m) return;
+    for (int i = 0; i < m->n; i++) gpsiq_destroy(m->sub[i]);
+    free(m);
+}
+
+const char* gpsiq_multi_last_error(const gpsiq_multi* m) { return m ? m->err : g_err; }
+int gpsiq_multi_devices(const gpsiq_multi* m) { return m ? m->n : 0; }
+int64_t gpsiq_multi_launch_count(const gpsiq_multi* m) {
+    int64_t t = 0;
+    for (int i = 0; m && i < m->n; i++) t += m->sub[i]->launches;
+    return t;
+}
+
+#define MCU(call)                                                                             \
+    do {                                                                                      \
+        cudaError_t ce_ = (call);                                                             \
+        if (ce_ != cudaSuccess) { fail(c, GPSIQ_ERR_CUDA, #call, ce_); return mfail(m, GPSIQ_ERR_CUDA, "gpsiq_multi", c); } \
+    } while (0)
+
+int gpsiq_multi_submit(gpsiq_multi* m, const gpsiq_chan_desc* desc, int n_epochs) {
+    if (!m || !desc || n_epochs < 1) return mfail(m, GPSIQ_ERR_ARG, "gpsiq_multi_submit: bad argument", NULL);
+    const long long j = m->seq_submit;
+    const int n = m->n, R = n * NSETS;
+    gpsiq_ctx* c = m->sub[j % n];
+    if (n_epochs > c->E) return mfail(m, GPSIQ_ERR_CAPACITY, "gpsiq_multi_submit: n_epochs > max_epochs", NULL);
+    if (c->set_pending >= NSETS || c->sets[c->set_wr].phase != 0)
+        return mfail(m, GPSIQ_ERR_CAPACITY, "gpsiq_multi_submit: every scan set of the next device is in flight (fetch a batch first)", NULL);
+    MCU(cudaSetDevice(c->cfg.device));
+    const int w = c->set_wr;
+    ScanSet& set = c->sets[w];
+    cudaStream_t ss = set.stream;
+    const size_t bytes = (size_t) n_epochs * c->C * sizeof(gpsiq_chan_desc), cbytes = c->C * sizeof(double);
+    if (!c->h_stage[w]) MCU(cudaHostAlloc(&c->h_stage[w], (size_t) c->E * c->C * sizeof(gpsiq_chan_desc), cudaHostAllocDefault));
+    MCU(cudaEventSynchronize(set.scan_done));       // the staging buffer's previous upload has been consumed
+    memcpy(c->h_stage[w], desc, bytes);
+    MCU(cudaStreamWaitEvent(ss, set.render_done, 0));
+    MCU(cudaMemcpyAsync(set.d_descbuf, c->h_stage[w], bytes, cudaMemcpyHostToDevice, ss));
+    int rc = begin_batch(c, ss);
+    if (!rc) rc = enqueue_prepare(c, set.d_descbuf, n_epochs, ss, true);
+    if (rc) return mfail(m, rc, "gpsiq_multi_submit", c);
+    const bool spec = c->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && c->cfg.reserved[0] == 0;
+    const MultiSlot* P = (j >= 1 && m->ring[(j - 1) % R].seq == j - 1) ? &m->ring[(j - 1) % R] : NULL;
+    const MultiSlot* P2 = (j >= 2 && m->ring[(j - 2) % R].seq == j - 2) ? &m->ring[(j - 2) % R] : NULL;
+    gpsiq_ctx* pc = (j >= 1) ? m->sub[(j - 1) % n] : NULL;   // the context holding the carrier state before this batch
+    if (spec) {
+        if (m->seq_submit == m->seq_begin || !P) {  // nothing in flight: the exact state
+            gpsiq_ctx* src = pc ? pc : c;
+            MCU(cudaStreamWaitEvent(ss, src->ev_final, 0));
+            MCU(cudaMemcpyAsync(set.d_est, src->d_carr_state, cbytes, cudaMemcpyDefault, ss));
+        } else {
+            if (P2) {
+                MCU(cudaStreamWaitEvent(ss, P2->set->scan_done, 0));
+                MCU(cudaMemcpyAsync(set.d_est, P2->set->d_exact_end, cbytes, cudaMemcpyDefault, ss));
+            } else {
+                MCU(cudaStreamWaitEvent(ss, P->set->est_done, 0));
+                MCU(cudaMemcpyAsync(set.d_est, P->set->d_est, cbytes, cudaMemcpyDefault, ss));
+            }
+            MCU(cudaStreamWaitEvent(ss, P->set->adv_done, 0));
+            MCU(cudaMemcpyAsync(c->d_adv_prev, P->set->d_adv, 2 * cbytes, cudaMemcpyDefault, ss));
+            k_est_fold<<<1, 32, 0, ss>>>(set.d_est, c->d_adv_prev, c->C);
+            c->launches += 1;
+        }
+        MCU(cudaEventRecord(set.est_done, ss));
+    }
+    rc = enqueue_speculate(c, set.d_descbuf, n_epochs, ss, spec ? set.d_est : NULL);
+    if (!rc && pc && pc != c) {  // hand-off: the carrier state the previous batch's chain left on its device
+        MCU(cudaStreamWaitEvent(ss, c->ev_final, 0));    // (this device's own older chain has consumed its state)
+        MCU(cudaStreamWaitEvent(ss, pc->ev_final, 0));
+        MCU(cudaMemcpyAsync(c->d_carr_state, pc->d_carr_state, cbytes, cudaMemcpyDefault, ss));
+    }
+    if (!rc) rc = enqueue_chain(c, set.d_descbuf, n_epochs, ss);
+    if (!rc && c->use_line) rc = enqueue_anchor(c, set, ss, ss);
+    if (rc) return mfail(m, rc, "gpsiq_multi_submit", c);
+    MultiSlot& slot = m->ring[j % R];
+    slot.set = &set; slot.dev = (int) (j % n); slot.seq = j;
+    m->seq_submit++;
+    return GPSIQ_OK;
+}
+
+// Render the oldest submitted batch into iq_out (HOST memory; pinned memory keeps the copies asynchronous) without
+// waiting; gpsiq_multi_fetch_end waits for the oldest begun batch.  At most two begun batches per device.
+int gpsiq_multi_fetch_begin(gpsiq_multi* m, int16_t* iq_out) {
+    if (!m || !iq_out) return mfail(m, GPSIQ_ERR_ARG, "gpsiq_multi_fetch_begin: bad argument", NULL);
+    if (m->seq_begin >= m->seq_submit) return mfail(m, GPSIQ_ERR_ARG, "gpsiq_multi_fetch_begin: nothing submitted", NULL);
+    if (m->seq_begin - m->seq_end >= 2LL * m->n) return mfail(m, GPSIQ_ERR_CAPACITY, "gpsiq_multi_fetch_begin: two batches per device already begun", NULL);
+    gpsiq_ctx* c = m->sub[m->seq_begin % m->n];
+    MCU(cudaSetDevice(c->cfg.device));
+    if (!c->d_iq2) MCU(cudaMalloc(&c->d_iq2, (size_t) c->E * c->N * 4));
+    int16_t* dev = (c->fetch_count++ & 1) ? c->d_iq2 : c->d_iq;
+    const int rc = enqueue_render(c, dev, c->stream, iq_out);
+    if (rc) return mfail(m, rc, "gpsiq_multi_fetch_begin", c);
+    m->seq_begin++;
+    return GPSIQ_OK;
+}
+
+int gpsiq_multi_fetch_end(gpsiq_multi* m) {
+    if (!m || m->seq_end >= m->seq_begin) return mfail(m, GPSIQ_ERR_ARG, "gpsiq_multi_fetch_end: nothing begun", NULL);
+    gpsiq_ctx* c = m->sub[m->seq_end % m->n];
+    MCU(cudaSetDevice(c->cfg.device));
+    const int rc = check_device_error(c);
+    MCU(cudaStreamSynchronize(c->copy_stream));
+    m->seq_end++;
+    if (rc) return mfail(m, rc, "gpsiq_multi_fetch_end", c);
+    return GPSIQ_OK;
+}
+
+int gpsiq_multi_fetch(gpsiq_multi* m, int16_t* iq_out) {
+    const int rc = gpsiq_multi_fetch_begin(m, iq_out);
+    return rc ? rc : gpsiq_multi_fetch_end(m);
+}
+#undef MCU
 
 int gpsiq_scan_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, void* stream) {
     if (!ctx || !desc_dev || n_epochs < 1) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_scan_device: bad argument", cudaSuccess);

@@ -36,10 +36,12 @@ namespace {
 
 constexpr int kSamplesPerEpoch = 300000;  // NUM_SAMPLES = TX_SAMPLE_FREQ/10, independent of -s (plutogpssim.c:43-44)
 
-// SIGINT / SIGTERM end the run after the batch in flight; the sink is then closed in order, which for the radio means
-// TX LO off before the context goes away (the reference's handle_sig + exit path, plutogpssim.c:2014-2022, 2160-2178).
+// SIGINT / SIGTERM / SIGQUIT (the three the reference handles, plutogpssim.c:2282-2284) end the run: no new batch is
+// submitted, the sink is told to stop after the push unit it is in (0.1 s of signal) and to discard what is queued,
+// and it is then closed in order -- for the radio: TX LO off before the context goes away (the reference's handle_sig +
+// exit path, plutogpssim.c:2014-2022, 2160-2178).  A second signal skips the orderly GPU drain as well.
 volatile sig_atomic_t g_stop = 0;
-void on_signal(int) { g_stop = 1; }
+void on_signal(int) { g_stop = g_stop + 1; }
 
 void usage() {
     fprintf(stderr,
@@ -64,7 +66,8 @@ void usage() {
             "  -r               Transmit through an ADALM-Pluto (libiio), as the reference does\n"
             "  -b <epochs>      0.1 s epochs per GPU batch (default 128)\n"
             "  -n <channels>    Channel slots (default 12 = MAX_CHAN; up to 32)\n"
-            "  -j <threads>     Host threads for the per-epoch orbit/range work (default min(8, cores); 1 = serial)\n");
+            "  -j <threads>     Host threads for the per-epoch orbit/range work (default min(8, cores); 1 = serial)\n"
+            "  -g <gpus>        GPUs of this node to spread the stream over, in time slices of one batch (default 1)\n");
 }
 
 }  // namespace
@@ -78,8 +81,8 @@ int main(int argc, char** argv) {
     hc.max_chan = 12;
     hc.carrier_mode = GPSIQ_CARRIER_FLOAT;
     double duration = 1.0;
-    int batch = 128;
-    bool verbose = false, have_pos = false, use_radio = false;
+    int batch = 128, gpus = 1;
+    bool verbose = false, have_pos = false, use_radio = false, batch_given = false, moving = false;
     gpssink_radio_config radio;
     gpssink_radio_defaults(&radio);
     const char* out_path = nullptr;
@@ -90,7 +93,9 @@ int main(int argc, char** argv) {
     while ((opt = getopt(argc, argv, "e:3:u:g:c:l:s:T:t:A:B:U:N:vfi?d:o:b:n:rj:")) != -1) {
         switch (opt) {
             case 'e': nav = optarg; break;
-            case 'u': motion = optarg; hc.pos_mode = GPSHOST_POS_MOTION; have_pos = true; break;
+            // -u clears the reference's staticLocationMode and -l / -c never set it again (plutogpssim.c:2301-2318, 2403):
+            // user motion wins whatever the option order; -l / -c then only store coordinates nobody reads
+            case 'u': motion = optarg; moving = true; have_pos = true; break;
             case '3': hc.rinex3 = 1; break;  // (takes and ignores an argument, like the reference's "3:" option string)
             case 'f': fprintf(stderr, "ERROR: FTP download is not available (no network code in this build).\n"); return 1;
             case 'c':
@@ -131,11 +136,12 @@ int main(int argc, char** argv) {
             case 'i': hc.iono_disable = 1; break;
             case 'v': verbose = true; break;
             case 'A': case 'B': case 'U': case 'N': gpssink_radio_option(&radio, opt, optarg); break;
-            case 'g': break;  // in the reference's option string, handled nowhere (plutogpssim.c:2296)
+            // 'g' is in the reference's option string and handled nowhere there (plutogpssim.c:2296); here: GPU count
+            case 'g': gpus = atoi(optarg); break;
             case 'r': use_radio = true; break;
             case 'd': duration = atof(optarg); break;
             case 'o': out_path = optarg; break;
-            case 'b': batch = atoi(optarg); break;
+            case 'b': batch = atoi(optarg); batch_given = true; break;
             case 'n': hc.max_chan = atoi(optarg); break;
             case 'j': hc.threads = atoi(optarg); break;
             default: usage(); return 1;
@@ -143,12 +149,15 @@ int main(int argc, char** argv) {
     }
     if (nav.empty()) { fprintf(stderr, "ERROR: GPS ephemeris file is not specified.\n"); return 1; }
     if (!have_pos) fprintf(stderr, "note: no -l/-c/-u given; using the default location (the reference leaves it uninitialised)\n");
-    if (batch < 1 || duration < 0.0) { usage(); return 1; }
+    if (moving) hc.pos_mode = GPSHOST_POS_MOTION;
+    // a transmitting run is paced by the radio (0.1 s per epoch): small batches keep what is in flight -- and so the time
+    // a stop request takes -- short; a batch the user asked for is respected up to 10 epochs (1 s)
+    if (use_radio) batch = batch_given ? std::min(batch, 10) : 5;
+    if (batch < 1 || duration < 0.0 || gpus < 1 || gpus > 16) { usage(); return 1; }
     hc.nav_path = nav.c_str();
     hc.motion_path = motion.empty() ? nullptr : motion.c_str();
 
     // the mode line comes after the motion file has been read and before the navigation file is (plutogpssim.c:2402-2420)
-    const bool moving = hc.pos_mode == GPSHOST_POS_MOTION;
     if (!moving) fprintf(stderr, "Using static location mode.\n");
     gpshost_scenario* sc = nullptr;
     const int opened = gpshost_open(&sc, &hc);
@@ -163,9 +172,20 @@ int main(int argc, char** argv) {
     gpshost_describe(sc, text, sizeof text);   // RINEX date, start time, channel table (plutogpssim.c:2572-2574, 2634-2639)
     fputs(text, stderr);
 
+    // From here on every exit goes through the cleanup block at the end: an open radio sink has its TX LO on, and only
+    // gpssink_close powers it down and releases the device (plutogpssim.c:2160-2178).
     gpssink* sink = nullptr;
-    int src = use_radio ? gpssink_open_radio(&sink, &radio) : out_path ? gpssink_open_file(&sink, out_path) : gpssink_open_null(&sink);
-    if (src != GPSSINK_OK) { fprintf(stderr, "ERROR: %s\n", gpssink_last_error()); return 1; }
+    gpsiq_multi* gq = nullptr;
+    gpsiq_chan_desc* desc = nullptr;
+    std::vector<int16_t*> iq;
+    bool ok = true, sink_refused = false;
+    std::string sink_err;
+    long produced = 0;
+    int64_t sunk_pairs = 0, pushes = 0;
+    const auto t_begin = std::chrono::steady_clock::now();
+
+    const int src = use_radio ? gpssink_open_radio(&sink, &radio) : out_path ? gpssink_open_file(&sink, out_path) : gpssink_open_null(&sink);
+    if (src != GPSSINK_OK) { fprintf(stderr, "ERROR: %s\n", gpssink_last_error()); gpshost_close(sc); return 1; }
 
     const long total_epochs = duration == 0.0 ? LONG_MAX : (long) (duration * 10.0 + 0.5);
     struct sigaction sa;
@@ -173,61 +193,78 @@ int main(int argc, char** argv) {
     sa.sa_handler = on_signal;
     sigaction(SIGINT, &sa, nullptr);
     sigaction(SIGTERM, &sa, nullptr);
+    sigaction(SIGQUIT, &sa, nullptr);
     if (batch > total_epochs) batch = (int) total_epochs;
-    gpsiq_config gc;
-    memset(&gc, 0, sizeof gc);
-    gc.device = 0; gc.max_chan = hc.max_chan; gc.samples_per_epoch = kSamplesPerEpoch;
-    gc.carrier_mode = hc.carrier_mode; gc.max_epochs = batch;
-    gpsiq_ctx* gq = nullptr;
-    if (gpsiq_create(&gq, &gc) != GPSIQ_OK) { fprintf(stderr, "ERROR: %s\n", gpsiq_last_error(nullptr)); return 1; }
+    do {  // (one pass; `break` = go to the cleanup)
+        gpsiq_config gc;
+        memset(&gc, 0, sizeof gc);
+        gc.device = 0; gc.max_chan = hc.max_chan; gc.samples_per_epoch = kSamplesPerEpoch;
+        gc.carrier_mode = hc.carrier_mode; gc.max_epochs = batch;
+        if (gpsiq_multi_create(&gq, &gc, gpus) != GPSIQ_OK) { fprintf(stderr, "ERROR: %s\n", gpsiq_last_error(nullptr)); ok = false; break; }
 
-    // two batches in flight: descriptors of batch k+1 are generated and scanned while batch k is rendered
-    const size_t desc_count = (size_t) batch * (size_t) hc.max_chan;
-    gpsiq_chan_desc* desc = (gpsiq_chan_desc*) gpsiq_host_alloc(desc_count * sizeof(gpsiq_chan_desc));
-    int16_t* iq[2] = {(int16_t*) gpsiq_host_alloc((size_t) batch * kSamplesPerEpoch * 4),
-                      (int16_t*) gpsiq_host_alloc((size_t) batch * kSamplesPerEpoch * 4)};
-    if (!desc || !iq[0] || !iq[1]) { fprintf(stderr, "ERROR: pinned host allocation failed\n"); return 1; }
+        // In flight at any time: up to `ahead` batches submitted (descriptors generated, scans running) beyond the ones whose
+        // rendering has begun, up to `gpus` batches being rendered / copied to the host (one per device), and the sink
+        // draining older ones.  One pinned host buffer per batch that can be between fetch_begin and the sink's release.
+        const int ahead = gpus + 1, inflight = gpus, nbuf = inflight + 2;
+        const size_t desc_count = (size_t) batch * (size_t) hc.max_chan;
+        desc = (gpsiq_chan_desc*) gpsiq_host_alloc(desc_count * sizeof(gpsiq_chan_desc));
+        for (int i = 0; i < nbuf; i++) iq.push_back((int16_t*) gpsiq_host_alloc((size_t) batch * kSamplesPerEpoch * 4));
+        if (!desc || std::find(iq.begin(), iq.end(), nullptr) != iq.end()) { fprintf(stderr, "ERROR: pinned host allocation failed\n"); ok = false; break; }
 
-    const auto t_begin = std::chrono::steady_clock::now();
-    std::deque<int> sizes;   // epochs of the batches submitted to the GPU and not yet fetched
-    long produced = 0;
-    auto submit_next = [&]() -> bool {
-        const int n = (int) std::min<long>(batch, total_epochs - produced);
-        if (n <= 0 || g_stop) return false;
-        if (gpshost_next(sc, desc, n) != GPSHOST_OK) { fprintf(stderr, "ERROR: %s\n", gpshost_last_error()); exit(1); }
-        if (gpsiq_submit(gq, desc, n) != GPSIQ_OK) { fprintf(stderr, "ERROR: %s\n", gpsiq_last_error(gq)); exit(1); }
-        sizes.push_back(n);
-        produced += n;
-        return true;
-    };
-    submit_next();
-    size_t k = 0;
-    bool ok = true;
-    int64_t ticket[2] = {0, 0};                // the sink's claim on each pinned buffer
-    while (!sizes.empty() && ok) {
-        submit_next();                         // (no-op at the end of the stream)
-        const int n_now = sizes.front();
-        sizes.pop_front();
-        int16_t* buf = iq[k & 1];
-        if (ticket[k & 1] > 0 && gpssink_wait(sink, ticket[k & 1]) != GPSSINK_OK) { ok = false; break; }   // batch k-2 drained
-        if (gpsiq_fetch(gq, buf) != GPSIQ_OK) { fprintf(stderr, "ERROR: %s\n", gpsiq_last_error(gq)); return 1; }
-        // n_now push units (one 300000-sample buffer each, plutogpssim.c:2146-2158), written while batch k+1 is fetched
-        ticket[k & 1] = gpssink_submit(sink, buf, (size_t) n_now * kSamplesPerEpoch);
-        if (ticket[k & 1] < 0) ok = false;
-        if (verbose) fprintf(stderr, "\rTime into run = %4.1f", (double) std::min<long>((long) (k + 1) * batch, produced) / 10.0);
-        k++;
+        std::deque<int> submitted;               // epochs of the batches submitted and not yet begun
+        std::deque<std::pair<int, int>> begun;   // (buffer, epochs) of the batches being rendered
+        std::vector<int64_t> ticket(nbuf, 0);    // the sink's claim on each pinned buffer
+        size_t k = 0;                            // batches begun so far (buffer = k % nbuf)
+        auto submit_next = [&]() -> bool {
+            const int n = (int) std::min<long>(batch, total_epochs - produced);
+            if (n <= 0 || g_stop || !ok) return false;
+            if (gpshost_next(sc, desc, n) != GPSHOST_OK) { fprintf(stderr, "ERROR: %s\n", gpshost_last_error()); ok = false; return false; }
+            if (gpsiq_multi_submit(gq, desc, n) != GPSIQ_OK) { fprintf(stderr, "ERROR: %s\n", gpsiq_multi_last_error(gq)); ok = false; return false; }
+            submitted.push_back(n);
+            produced += n;
+            return true;
+        };
+        while (ok) {
+            while ((int) (submitted.size() + begun.size()) < ahead + inflight && (int) submitted.size() < 2 * gpus && submit_next()) {}
+            if (g_stop) break;                       // stop request: nothing more is fetched or queued
+            while (ok && !submitted.empty() && (int) begun.size() < inflight) {   // start rendering on every idle device
+                const int b = (int) (k % nbuf);
+                if (ticket[b] > 0 && gpssink_wait(sink, ticket[b]) != GPSSINK_OK) { ok = false; sink_refused = true; break; }
+                ticket[b] = 0;
+                if (gpsiq_multi_fetch_begin(gq, iq[b]) != GPSIQ_OK) { fprintf(stderr, "ERROR: %s\n", gpsiq_multi_last_error(gq)); ok = false; break; }
+                begun.push_back({b, submitted.front()});
+                submitted.pop_front();
+                k++;
+            }
+            if (!ok || begun.empty()) break;
+            if (gpsiq_multi_fetch_end(gq) != GPSIQ_OK) { fprintf(stderr, "ERROR: %s\n", gpsiq_multi_last_error(gq)); ok = false; break; }
+            const int b = begun.front().first, n_now = begun.front().second;
+            begun.pop_front();
+            // n_now push units (one 300000-sample buffer each, plutogpssim.c:2146-2158), written while later batches are fetched
+            ticket[b] = gpssink_submit(sink, iq[b], (size_t) n_now * kSamplesPerEpoch);
+            if (ticket[b] < 0) { ok = false; sink_refused = true; }
+            if (verbose) fprintf(stderr, "\rTime into run = %4.1f", (double) (produced - (long) submitted.size() * batch) / 10.0);
+        }
+        if (g_stop) gpssink_abort(sink);             // finish the push unit in progress, discard the rest
+        if (g_stop < 2)                              // orderly: let the GPUs finish what was begun (the buffers stay valid)
+            while (!begun.empty()) { gpsiq_multi_fetch_end(gq); begun.pop_front(); }
+    } while (false);
+
+    // ---- cleanup: always the sink first (radio: TX LO off, buffer, channels, context), then the GPUs, then the host side
+    if (sink) {
+        if (!ok) gpssink_abort(sink);                // after a failure nothing queued is worth transmitting
+        gpssink_stats(sink, &sunk_pairs, &pushes);   // waits for the writer
+        if (sink_refused) sink_err = gpssink_last_error();
+        if (gpssink_close(sink) != GPSSINK_OK) { if (ok) sink_err = gpssink_last_error(); ok = false; sink_refused = true; }
     }
-    int64_t sunk_pairs = 0, pushes = 0;
-    gpssink_stats(sink, &sunk_pairs, &pushes);   // waits for the writer
-    std::string sink_err = ok ? "" : gpssink_last_error();
-    if (gpssink_close(sink) != GPSSINK_OK) { if (ok) sink_err = gpssink_last_error(); ok = false; }
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
-    if (!ok) fprintf(stderr, "\nERROR: sink refused data: %s\n", sink_err.c_str());
+    if (sink_refused) fprintf(stderr, "\nERROR: sink refused data: %s\n", sink_err.c_str());
     fprintf(stderr, "%s%ld epochs (%.1f s of signal, %.0f samples) in %.3f s: %.1f Msamples/s, %lld kernel launches, %lld buffers to the sink\n",
             verbose ? "\n" : "", produced, produced / 10.0, (double) produced * kSamplesPerEpoch, secs,
-            (double) produced * kSamplesPerEpoch / secs / 1e6, (long long) gpsiq_launch_count(gq), (long long) (sunk_pairs / kSamplesPerEpoch));
-    gpsiq_host_free(desc); gpsiq_host_free(iq[0]); gpsiq_host_free(iq[1]);
-    gpsiq_destroy(gq);
+            (double) produced * kSamplesPerEpoch / secs / 1e6, (long long) gpsiq_multi_launch_count(gq), (long long) (sunk_pairs / kSamplesPerEpoch));
+    gpsiq_host_free(desc);
+    for (int16_t* p : iq) gpsiq_host_free(p);
+    gpsiq_multi_destroy(gq);
     gpshost_close(sc);
     return ok ? 0 : 1;
 }

@@ -13,6 +13,7 @@
 #include <dlfcn.h>
 
 #include <cerrno>
+#include <atomic>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -40,6 +41,7 @@ int fail(int code, const char* fmt, ...) {
 
 struct Backend {
     int64_t pushes = 0;
+    std::atomic<bool> aborted{false};   // gpssink_abort: stop at the next push unit, discard the rest
     virtual ~Backend() {}
     virtual int write(const int16_t* iq, size_t pairs) = 0;
     virtual int finish() { return GPSSINK_OK; }
@@ -229,6 +231,7 @@ struct RadioBackend : Backend {
         const size_t unit = (size_t) cfg.pairs_per_push;
         if (pairs % unit) return fail(GPSSINK_ERR_ARG, "radio sink takes whole %zu-pair buffers (got %zu pairs)", unit, pairs);
         for (size_t done = 0; done < pairs; done += unit) {
+            if (aborted.load(std::memory_order_relaxed)) return GPSSINK_OK;   // stop within one 0.1 s push, like the reference
             memcpy(buffer_mem, iq + 2 * done, unit * 4);           // plutogpssim.c:2148
             const ssize_t n = api.buffer_push(buffer);              // plutogpssim.c:2152
             if (n < 0) return fail(GPSSINK_ERR_PUSH, "Error pushing buf %d", (int) n);
@@ -285,7 +288,7 @@ struct gpssink {
             const Job j = jobs.front();
             jobs.pop_front();
             int rc = status;
-            if (rc == GPSSINK_OK) {
+            if (rc == GPSSINK_OK && !be->aborted.load()) {   // (aborted: queued batches are discarded, not written)
                 lk.unlock();
                 rc = write_now(j.iq, j.pairs);
                 std::string msg = rc == GPSSINK_OK ? "" : g_err;  // g_err is per thread: carry it over to the waiter
@@ -417,6 +420,12 @@ int gpssink_wait(gpssink* s, int64_t ticket) {
     if (ticket <= 0 || ticket >= s->next_ticket) return fail(GPSSINK_ERR_ARG, "unknown ticket %lld", (long long) ticket);
     s->cv_done.wait(lk, [&] { return s->done_ticket >= ticket; });
     if (s->status != GPSSINK_OK) return fail(s->status, "%s", s->status_msg.c_str());
+    return GPSSINK_OK;
+}
+
+int gpssink_abort(gpssink* s) {
+    if (!s) return fail(GPSSINK_ERR_ARG, "null argument");
+    s->be->aborted.store(true);
     return GPSSINK_OK;
 }
 

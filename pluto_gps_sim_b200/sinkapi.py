@@ -31,6 +31,7 @@ SYMBOLS = {
     "gpssink_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "gpssink_submit": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "gpssink_wait": (C.c_int, [C.c_void_p, C.c_int64]),
+    "gpssink_abort": (C.c_int, [C.c_void_p]),
     "gpssink_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "gpssink_close": (C.c_int, [C.c_void_p]),
     "gpssink_last_error": (C.c_char_p, []),
@@ -111,6 +112,10 @@ class Sink:
         self._keep.pop(ticket, None)
         if rc != 0:
             raise SinkError(rc)
+
+    def abort(self):
+        """Stop after the push unit in progress; queued and later batches are discarded."""
+        lib.gpssink_abort(self._h)
 
     @property
     def stats(self):

@@ -73,3 +73,33 @@ int gpsiq_synth(gpsiq_ctx *c, const gpsiq_chan_desc *desc, int n_epochs, int16_t
     return oracle_synth(desc, n_epochs, c->cfg.max_chan, c->cfg.samples_per_epoch, c->cfg.carrier_mode, c->carr, iq_out, NULL) == 0
                ? GPSIQ_OK : GPSIQ_ERR_ARG;
 }
+
+/* the multi-device entry points the front end drives (gpsiq_sim -g N): here one queue whatever N -- the stream is the
+ * same by construction, which is exactly what the real library has to reproduce with N devices */
+struct gpsiq_multi { gpsiq_ctx *c; int n; struct pending *begun_head, *begun_tail; int16_t *out[64]; int nb, ne; };
+int gpsiq_multi_create(gpsiq_multi **m, const gpsiq_config *cfg, int n_devices) {
+    if (n_devices < 1 || n_devices > 16) return GPSIQ_ERR_ARG;
+    gpsiq_multi *x = calloc(1, sizeof *x);
+    x->n = n_devices;
+    gpsiq_create(&x->c, cfg);
+    *m = x;
+    return GPSIQ_OK;
+}
+void gpsiq_multi_destroy(gpsiq_multi *m) { if (m) { gpsiq_destroy(m->c); free(m); } }
+int gpsiq_multi_submit(gpsiq_multi *m, const gpsiq_chan_desc *desc, int n_epochs) { return gpsiq_submit(m->c, desc, n_epochs); }
+int gpsiq_multi_fetch_begin(gpsiq_multi *m, int16_t *iq_out) {
+    if (m->nb - m->ne >= 2 * m->n || m->nb - m->ne >= 64) return GPSIQ_ERR_CAPACITY;
+    m->out[m->nb++ % 64] = iq_out;
+    return GPSIQ_OK;
+}
+int gpsiq_multi_fetch_end(gpsiq_multi *m) {
+    if (m->ne >= m->nb) return GPSIQ_ERR_ARG;
+    return gpsiq_fetch(m->c, m->out[m->ne++ % 64]);
+}
+int gpsiq_multi_fetch(gpsiq_multi *m, int16_t *iq_out) {
+    const int rc = gpsiq_multi_fetch_begin(m, iq_out);
+    return rc ? rc : gpsiq_multi_fetch_end(m);
+}
+int gpsiq_multi_devices(const gpsiq_multi *m) { return m->n; }
+int64_t gpsiq_multi_launch_count(const gpsiq_multi *m) { (void) m; return 0; }
+const char *gpsiq_multi_last_error(const gpsiq_multi *m) { (void) m; return "mock_gpsiq (test infrastructure)"; }

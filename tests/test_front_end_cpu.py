@@ -228,3 +228,56 @@ def test_fatal_errors_are_worded_and_ordered_like_the_reference_s(sim, tmp_path,
     got = sim(args, check=False)
     assert ref.returncode == 1 and got.returncode == 1
     assert got.stderr.splitlines() == ref.stderr.splitlines()
+
+
+def test_user_motion_wins_whatever_the_option_order(sim, tmp_path):
+    """-u clears the reference's staticLocationMode and -l / -c never set it again (plutogpssim.c:2301-2318, 2403):
+    `-u file -l ...` is a user-motion run, byte for byte the same stream as `-u file` alone."""
+    circle = os.path.join(ol.ORACLE_DIR, "_ref", "circle.csv")
+    if not os.path.exists(circle):
+        pytest.skip("oracle/_ref/circle.csv (the reference's motion fixture) not present")
+    outs = []
+    for extra in ([], ["-l", "10.0,20.0,30"], ["-c", "1.0,2.0,3.0"]):
+        out = tmp_path / ("iq%d.bin" % len(outs))
+        r = sim(["-e", NAV12, "-o", str(out), "-u", circle] + extra + ["-s", "2600000", "-d", "0.3", "-b", "2"])
+        assert "Using user motion mode." in r.stderr and "static location" not in r.stderr
+        outs.append(out.read_bytes())
+    assert outs[0] == outs[1] == outs[2]
+    iq = np.frombuffer(outs[0], np.int16).reshape(3, N, 2)
+    assert [int(checksum_host(iq[e])) for e in range(3)] == ol.load_golden_meta("circle12")["epoch_checksums"][:3]
+
+
+@pytest.mark.parametrize("gpus,batch", [("2", "3"), ("3", "1"), ("4", "128")])
+def test_several_gpus_same_stream(sim, tmp_path, gpus, batch):
+    """-g N: the front end's multi-device loop (several batches submitted ahead, several being fetched, buffers
+    recycled through the sink) must deliver the same bytes in the same order."""
+    out = tmp_path / "iq.bin"
+    r = sim(["-e", NAV12, "-o", str(out), "-d", "1.0", "-b", batch, "-g", gpus] + STATIC)
+    assert hashlib.sha256(out.read_bytes()).hexdigest() == ol.load_golden_meta("static12")["iq_sha256"], r.stderr
+    assert "10 buffers to the sink" in r.stderr
+
+
+@pytest.mark.parametrize("sig", ["SIGINT", "SIGQUIT"])
+def test_stop_request_while_transmitting_is_fast_and_powers_the_lo_down(sim, tmp_path, sig):
+    """With -r the batches are small and a stop request makes the sink discard what is queued: the process ends within
+    about a second (the reference: one 0.1 s epoch), through the orderly radio shut-down, for every signal the reference
+    handles (SIGINT, SIGTERM, SIGQUIT; plutogpssim.c:2282-2284)."""
+    import signal
+    import time
+    log, out = tmp_path / "calls.log", tmp_path / "pushed.bin"
+    env = {"GPSSINK_IIO_LIB": FAKE_IIO, "FAKE_IIO_LOG": str(log), "FAKE_IIO_OUT": str(out), "FAKE_IIO_EPOCHS": "100000",
+           "FAKE_IIO_NO_DEFAULT": "0", "FAKE_IIO_PUSH_SLEEP_MS": "100"}
+    p = sim.popen(["-e", NAV12, "-r", "-d", "0", "-b", "128"] + STATIC, env=env)
+    time.sleep(3.0)
+    t0 = time.time()
+    p.send_signal(getattr(signal, sig))
+    try:
+        _, err = p.communicate(timeout=30)
+    except subprocess.TimeoutExpired:
+        p.kill()
+        raise
+    dt = time.time() - t0
+    assert p.returncode == 0, err.decode(errors="replace")
+    assert dt < 5.0, dt                       # (-b 128 is capped for the radio; nothing queued is transmitted)
+    calls = log.read_text().splitlines()
+    assert calls[-1].startswith("context_destroy") and any("powerdown" in c for c in calls[-5:])

@@ -306,6 +306,74 @@ def test_out_of_contract_descriptor_is_rejected():
         assert ei.value.status == capi.ERR_CAPACITY
 
 
+def test_epoch_longer_than_the_nav_window_is_refused():
+    """The descriptor carries 64 NAV bits (1.28 s): an epoch that would reach past them is out of contract and must be
+    refused (GPSIQ_ERR_ARG), not rendered with a wrapped-around window."""
+    desc = ol.load_golden_desc("static12")[:1].copy()
+    with Synthesizer(max_chan=12, samples_per_epoch=3400000, max_epochs=1) as s:      # 1.31 s of signal at 2.6 MS/s
+        with pytest.raises(capi.GpsiqError) as ei:
+            s.synth(desc)
+        assert ei.value.status == capi.ERR_ARG
+    with Synthesizer(max_chan=12, samples_per_epoch=3200000, max_epochs=1) as s:      # 1.23 s: inside the window
+        got = s.synth(desc)
+    want, _ = ol.oracle_synth(desc, 3200000)
+    assert first_diff(got, want) is None
+
+
+def test_two_batches_of_lookahead_and_the_multi_device_entry_points():
+    """Deeper pipelining (three scan sets: two batches scanned ahead of the one being rendered, scans of consecutive
+    batches overlapping on their own streams), and the same stream through gpsiq_multi_* on one device."""
+    import ctypes as C
+    import torch
+
+    meta = ol.load_golden_meta("circle12")
+    desc = ol.load_golden_desc("circle12")
+    sizes = [40, 64, 64, 1, 64, 64, 13]
+    st = torch.cuda.Stream()
+    sums = []
+    with torch.cuda.stream(st), Synthesizer(max_chan=12, max_epochs=64) as s:
+        bufs = [torch.empty(64 * 300000 * 2, dtype=torch.int16, device="cuda") for _ in range(2)]
+        descs, e = [], 0
+        for n in sizes:
+            descs.append(torch.from_numpy(desc[e:e + n].copy().view(np.uint8).reshape(-1)).cuda())
+            e += n
+        torch.cuda.synchronize()
+        sub = 0
+        for k in range(len(sizes)):
+            while sub < len(sizes) and sub <= k + 2:
+                s.submit_device(descs[sub].data_ptr(), sizes[sub], st.cuda_stream)
+                sub += 1
+            s.fetch_device(bufs[k & 1].data_ptr(), st.cuda_stream)
+            st.synchronize()
+            sums += [int(x) for x in s.checksum_device(bufs[k & 1].data_ptr(), sizes[k])]
+    assert sums == meta["epoch_checksums"]
+
+    # gpsiq_multi_* with one device: host descriptors in, host I/Q out, begin/end pairs
+    cfg = capi.Config()
+    cfg.device, cfg.max_chan, cfg.samples_per_epoch, cfg.carrier_mode, cfg.max_epochs = 0, 12, 300000, 0, 64
+    m = C.c_void_p()
+    capi.check(capi.lib.gpsiq_multi_create(C.byref(m), C.byref(cfg), 1))
+    try:
+        outs = [np.empty((n, 300000, 2), np.int16) for n in sizes]
+        e = 0
+        parts = []
+        for n in sizes:
+            parts.append(np.ascontiguousarray(desc[e:e + n]))
+            e += n
+        sub = 0
+        got = []
+        for k in range(len(sizes)):
+            while sub < len(sizes) and sub <= k + 2:
+                assert capi.lib.gpsiq_multi_submit(m, parts[sub].ctypes.data, sizes[sub]) == 0, capi.lib.gpsiq_multi_last_error(m)
+                sub += 1
+            assert capi.lib.gpsiq_multi_fetch_begin(m, outs[k].ctypes.data) == 0, capi.lib.gpsiq_multi_last_error(m)
+            assert capi.lib.gpsiq_multi_fetch_end(m) == 0, capi.lib.gpsiq_multi_last_error(m)
+            got += [int(checksum_host(outs[k][i])) for i in range(sizes[k])]
+        assert got == meta["epoch_checksums"]
+    finally:
+        capi.lib.gpsiq_multi_destroy(m)
+
+
 def test_streaming_submit_fetch_matches_reference():
     """submit/fetch with one batch of lookahead over the 310-epoch user-motion golden (uneven batches)."""
     import torch
@@ -380,6 +448,7 @@ def test_host_orchestrator_descriptors_drive_the_kernels():
     ("static12", ["-l", "30.286502,120.032669,100", "-s", "2600000", "-d", "1.0"], 10),
     ("static12", ["-l", "30.286502,120.032669,100", "-s", "2600000", "-d", "1.0", "-b", "3"], 10),
     ("allsky32", ["-l", "30.286502,120.032669,100", "-s", "10000000", "-d", "2.0", "-n", "32", "-b", "8"], 20),
+    ("static12", ["-l", "30.286502,120.032669,100", "-s", "2600000", "-d", "1.0", "-b", "1", "-g", "2"], 10),
 ])
 def test_command_line_front_end_reproduces_the_reference_stream(tmp_path, scenario, args, epochs):
     """gpsiq_sim with the reference's options writes byte for byte what the reference pushes to the SDR."""
@@ -387,6 +456,9 @@ def test_command_line_front_end_reproduces_the_reference_stream(tmp_path, scenar
     import subprocess
     from pluto_gps_sim_b200 import hostapi
 
+    import torch
+    if "-g" in args and torch.cuda.device_count() < int(args[args.index("-g") + 1]):
+        pytest.skip("needs %s GPUs" % args[args.index("-g") + 1])
     meta = ol.load_golden_meta(scenario)
     nav = os.path.join(ol.GOLDEN, "brdc3540_synth.14n.gz" if scenario == "static12" else "allsky32_synth.14n.gz")
     out = tmp_path / "iq.bin"
@@ -421,7 +493,8 @@ def test_front_end_radio_sink_pushes_the_reference_stream_once_each(tmp_path):
     assert hashlib.sha256(out.read_bytes()).hexdigest() == ol.load_golden_meta("static12")["iq_sha256"], r.stderr
 
 
-def test_config2_full_300s_user_motion_stream_through_the_front_end():
+@pytest.mark.parametrize("gpus", [1, 2])
+def test_config2_full_300s_user_motion_stream_through_the_front_end(gpus):
     """BASELINE config[2] in full: 3000 epochs (300 s, 3.6 GB) of circle.csv user motion, navigation file in,
     bytes out, SHA-256 against the reference's own 300 s run (tools/gen_golden_long.py).  Crosses ten 30 s
     refreshes (NAV frame rebuild, re-allocation) and exercises ~3 of the line kernel's patch-path tiles."""
@@ -431,13 +504,17 @@ def test_config2_full_300s_user_motion_stream_through_the_front_end():
     import refdump
     from pluto_gps_sim_b200 import hostapi
 
+    import torch
     circle = os.path.join(refdump.REF_DIR, "circle.csv")
     if not os.path.exists(circle):
         pytest.skip("needs the reference's circle.csv (oracle/_ref)")
+    if torch.cuda.device_count() < gpus:
+        pytest.skip("needs %d GPUs" % gpus)
     with open(os.path.join(ol.GOLDEN, "circle12_300s_meta.json")) as f:
         meta = json.load(f)
     nav = os.path.join(ol.GOLDEN, "brdc3540_synth.14n.gz")
-    p = subprocess.Popen([hostapi.SIM_PATH, "-e", nav, "-u", circle, "-s", "2600000", "-d", "300", "-b", "250", "-o", "-"],
+    p = subprocess.Popen([hostapi.SIM_PATH, "-e", nav, "-u", circle, "-s", "2600000", "-d", "300", "-b", "250", "-o", "-",
+                          "-g", str(gpus)],
                          stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     sha, total = hashlib.sha256(), 0
     while True:

@@ -199,3 +199,29 @@ def test_call_log_golden_is_what_the_reference_does_now():
     for name, (opts, dflt) in gg.CASES.items():
         assert gg.reference_log(opts, dflt) == GOLDEN_CALLS[name]["calls"], name
     assert gg.reference_banner() == _GOLDEN_FILE["_banner_v"]["stderr"]
+
+
+def test_abort_discards_what_is_queued_and_still_shuts_the_radio_down(tmp_path):
+    """gpssink_abort (what gpsiq_sim does on SIGINT / SIGTERM / SIGQUIT): the writer stops at the next 300000-pair push
+    unit, queued batches are dropped (their tickets complete), and close still runs the reference's shut-down sequence
+    (TX LO powered down, buffer destroyed, channels disabled, context destroyed: plutogpssim.c:2160-2178)."""
+    log, out = tmp_path / "calls.log", tmp_path / "pushed.bin"
+    code = """
+import sys, numpy as np
+sys.path.insert(0, %r)
+from pluto_gps_sim_b200 import sinkapi
+N = sinkapi.PUSH_PAIRS
+data = np.zeros((6, N, 2), np.int16)
+s = sinkapi.Sink(radio=sinkapi.radio_config(iio_lib=%r))
+s.abort()
+t1 = s.submit(data[:3]); t2 = s.submit(data[3:])
+s.wait(t1); s.wait(t2)
+print("stats", *s.stats)
+s.close()
+""" % (ol.REPO, FAKE_IIO)
+    env = dict(os.environ, FAKE_IIO_LOG=str(log), FAKE_IIO_OUT=str(out), FAKE_IIO_EPOCHS="1000", FAKE_IIO_NO_DEFAULT="0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "stats 0 0" in r.stdout                     # nothing submitted after the abort was pushed
+    calls = log.read_text().splitlines()
+    assert calls[-5:] == GOLDEN_CALLS["defaults_local_context"]["calls"][-5:]   # LO off ... context destroyed still run
