@@ -52,6 +52,10 @@ import time
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
+# The pipeline keeps a dozen streams busy per GPU (render, per-set scan streams, ring, side streams, copies); with
+# the default of 8 hardware work queues several streams share one, and a stream blocked in a wait (the ring's
+# stream-memory wait on the next hand-off, an event wait) holds up unrelated work queued behind it.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 N_SAMPLES = 300000
 GOLDEN = os.path.join(REPO, "tests", "golden")
@@ -455,6 +459,10 @@ def ours_arm(args):
         kiso_ms, kiso_ep = 0.0, 0
 
     # ---- end to end through host buffers (e2e)
+    if args.no_e2e:
+        if world > 1:
+            dist.destroy_process_group()
+        return
     h_desc = capi.lib.gpsiq_host_alloc(nbytes_desc)
     outs = [capi.lib.gpsiq_host_alloc(samples_per_step * 4) for _ in range(2)]
     assert h_desc and all(outs)
@@ -600,9 +608,10 @@ def main():
     ap.add_argument("--epochs", type=int, default=1024, help="epochs per step per GPU (1024 -> 1228.8 MB of output)")
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--tile", type=int, default=0)
-    ap.add_argument("--lookahead", type=int, default=int(os.environ.get("GPSIQ_LOOKAHEAD", "1")),
+    ap.add_argument("--lookahead", type=int, default=int(os.environ.get("GPSIQ_LOOKAHEAD", "2")),
                     help="batches scanned ahead of the one being rendered (N = 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling / trace runs)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the rendered batch (profiling runs)")
     ap.add_argument("--parity-stride", type=int, default=0)
     ap.add_argument("--carrier", choices=["float", "int32"], default="float",

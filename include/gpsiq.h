@@ -204,7 +204,11 @@ void gpsiq_host_free(void *p);
  *                previous slice's owner); O(one carrier cycle) per epoch;
  *   render    -> the per-sample synthesis.
  * gpsiq_scan_device = prepare + speculate + chain.  Estimates only affect speed:
- * a bad one makes epochs fall back to the serial scan, never changes a result. */
+ * a bad one makes epochs fall back to the serial scan, never changes a result.
+ * Batches move through the phases in order, each phase with its own cursor over the context's three scan sets:
+ * prepare / speculate of later batches may be enqueued (on another stream) before the chain of an earlier one --
+ * time-sliced runs speculate slice k+1 while the ring still carries the exact phases of slice k.  With the chain on
+ * another stream than the speculation, set GPSIQ_OPT_CHAIN_KEEPS_ESTIMATE. */
 int gpsiq_prepare_device(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc_dev, int n_epochs, double *advance_dev,
                          void *cuda_stream);
 int gpsiq_speculate_device(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc_dev, int n_epochs, void *cuda_stream);
@@ -219,6 +223,9 @@ int gpsiq_estimate_fold_device(gpsiq_ctx *ctx, const double *advance_dev, void *
  * advance modulo 2^32, or an absolute phase when the slice re-seeded the slot).  With it the time slices of the
  * integer-carrier mode need no ring: every rank folds the advances of the slices before its own. */
 int gpsiq_carrier_fold_device(gpsiq_ctx *ctx, const double *advance_dev, void *cuda_stream);
+/* estimate <- max_chan doubles in DEVICE memory (e.g. an exact phase saved earlier with gpsiq_carrier_to_device, to be
+ * advanced with gpsiq_estimate_fold_device over the slices since) */
+int gpsiq_estimate_from_device(gpsiq_ctx *ctx, const double *src_dev, void *cuda_stream);
 /* estimate <- the context's exact carrier state (e.g. right after gpsiq_carrier_from_device) */
 int gpsiq_estimate_anchor_device(gpsiq_ctx *ctx, void *cuda_stream);
 /* Copy the carrier state (max_chan doubles) to / from DEVICE memory on a stream

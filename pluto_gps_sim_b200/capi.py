@@ -17,7 +17,7 @@ ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_CAPACITY = -1, -2, -3, -4
 CARRIER_FLOAT, CARRIER_INT32 = 0, 1
 FLAG_RESET_CARRIER = 1
 KERNEL_AUTO, KERNEL_LANE_PER_CHANNEL, KERNEL_LINE = 0, 1, 3   # (2 was the retired segment-list kernel)
-MAX_LOOKAHEAD = 2   # batches gpsiq_submit* may run ahead of the one being fetched (scan sets - 1)
+MAX_LOOKAHEAD = 3   # batches gpsiq_submit* may run ahead of the one being fetched (scan sets - 1)
 LINE_DBG_FORCE_CHUNK, LINE_DBG_FORCE_TILE, LINE_DBG_PERTURB = 1, 2, 4
 MAX_CHAN = 32
 NCO_CODE, NCO_CARRIER = 0, 1
@@ -98,6 +98,7 @@ SYMBOLS = {
     "gpsiq_estimate_fold_device": (_i, [_vp, _vp, _vp]),
     "gpsiq_carrier_fold_device": (_i, [_vp, _vp, _vp]),
     "gpsiq_estimate_anchor_device": (_i, [_vp, _vp]),
+    "gpsiq_estimate_from_device": (_i, [_vp, _vp, _vp]),
     "gpsiq_render_device": (_i, [_vp, _vp, _i, _vp, _vp]),
     "gpsiq_set_option": (_i, [_vp, _i, _i]),
     "gpsiq_estimate_to_device": (_i, [_vp, _vp, _vp]),

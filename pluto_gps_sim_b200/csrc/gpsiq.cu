@@ -93,18 +93,22 @@ struct ScanSet {
     cudaStream_t stream;          // pipelined submits: each set scans on its own stream, so that the scans of
                                   // consecutive batches overlap (only the exact chain is ordered batch after batch)
     cudaEvent_t scan_done, render_done, spec_done, adv_done, est_done;
+    cudaEvent_t spec_all;         // every speculative level of the batch has run (the chain may be enqueued on another stream)
     long long seq;                // number of the batch the set holds (-1: none yet)
     const gpsiq_chan_desc* desc;  // the batch's descriptors (device)
     int n_epochs;
     int phase;                    // 0 free, 1 prepared, 2 speculated, 3 chained (waiting to be rendered)
 };
 
-#define NSETS 3   // scan sets: gpsiq_submit* may run NSETS - 1 batches ahead of the one being rendered
+#define NSETS 4   // scan sets: gpsiq_submit* may run NSETS - 1 batches ahead of the one being rendered
 
 struct gpsiq_ctx {
     gpsiq_config cfg;
     ScanSet sets[NSETS];
-    int set_wr, set_rd, set_pending;  // submit/fetch ring
+    // the ring of scan sets, one cursor per phase: a batch is prepared (set_prep), speculated (set_spec), chained (set_wr)
+    // and rendered (set_rd), in that order; the phase API of time-sliced runs may prepare / speculate batches ahead of
+    // the one being chained (on another stream), the pipelined submits move the first three cursors together
+    int set_prep, set_spec, set_wr, set_rd, set_pending;
     int set_cur;                      // set the working pointers currently point at
     cudaStream_t scan_stream;         // gpsiq_submit_device scans here, ahead of the caller's render stream
     cudaStream_t aux2_stream;         // its code-NCO scan (aux_stream is busy with the tile prologues of the batch being rendered)
@@ -191,7 +195,17 @@ static void trace_mark(gpsiq_ctx* ctx, cudaStream_t st, const char* label) {
     TraceRec& r = ctx->trace[ctx->trace_n];
     if (!r.ev) cudaEventCreate(&r.ev);
     r.label = label;
-    r.stream_id = (st == ctx->sets[0].stream) ? 10 : (st == ctx->sets[1].stream) ? 11 : (st == ctx->sets[2].stream) ? 12 : (st == ctx->scan_stream) ? 1 : (st == ctx->aux2_stream) ? 2 : (st == ctx->aux_stream) ? 3 : (st == ctx->copy_stream) ? 4 : 0;
+    r.stream_id = -1;
+    for (int i = 0; i < NSETS; i++) if (st == ctx->sets[i].stream) r.stream_id = 10 + i;
+    if (r.stream_id < 0) r.stream_id = (st == ctx->scan_stream) ? 1 : (st == ctx->aux2_stream) ? 2 : (st == ctx->aux_stream) ? 3 : (st == ctx->copy_stream) ? 4 : -1;
+    if (r.stream_id < 0) {  // a caller's stream: numbered 20, 21, ... in order of first appearance
+        static cudaStream_t seen[16];
+        static int nseen = 0;
+        int k = 0;
+        while (k < nseen && seen[k] != st) k++;
+        if (k == nseen && nseen < 16) seen[nseen++] = st;
+        r.stream_id = 20 + k;
+    }
     cudaEventRecord(r.ev, st);
     ctx->trace_n++;
 }
@@ -1031,6 +1045,7 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
         CU(cudaMalloc(&ss.d_exact_end, ctx->C * sizeof(double)));
         CU(cudaEventCreateWithFlags(&ss.adv_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ss.est_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ss.spec_all, cudaEventDisableTiming));
         ss.seq = -1;
         CU(cudaEventCreateWithFlags(&ss.scan_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ss.render_done, cudaEventDisableTiming));
@@ -1192,6 +1207,7 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
         if (ss.spec_done) cudaEventDestroy(ss.spec_done);
         if (ss.adv_done) cudaEventDestroy(ss.adv_done);
         if (ss.est_done) cudaEventDestroy(ss.est_done);
+        if (ss.spec_all) cudaEventDestroy(ss.spec_all);
         if (ss.stream) cudaStreamDestroy(ss.stream);
         cudaFree(ss.d_est); cudaFree(ss.d_exact_end);
         cudaFree(ss.d_hazlist); cudaFree(ss.d_lrecs); cudaFree(ss.d_elist); cudaFree(ss.d_patches); cudaFree(ss.d_line_counters);
@@ -1231,10 +1247,10 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
 // render phase consumes the oldest chained one.  A plain gpsiq_synth_device uses the ring with one
 // batch in flight; submit/fetch and the time-slice runner keep two.
 static int begin_batch(gpsiq_ctx* ctx, cudaStream_t st) {
-    if (ctx->set_pending >= NSETS || ctx->sets[ctx->set_wr].phase != 0)
+    if (ctx->sets[ctx->set_prep].phase != 0)
         return fail(ctx, GPSIQ_ERR_CAPACITY, "every scan set is in flight (render a batch first)", cudaSuccess);
-    CU(cudaStreamWaitEvent(st, ctx->sets[ctx->set_wr].render_done, 0));
-    use_set(ctx, ctx->set_wr);
+    CU(cudaStreamWaitEvent(st, ctx->sets[ctx->set_prep].render_done, 0));
+    use_set(ctx, ctx->set_prep);
     return GPSIQ_OK;
 }
 
@@ -1243,7 +1259,8 @@ static int enqueue_prepare(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int 
     const int C = ctx->C, N = ctx->N;
     const int EC = n_epochs * C;
     if (!begun) { int rc0 = begin_batch(ctx, st); if (rc0) return rc0; }
-    ScanSet& set = ctx->sets[ctx->set_wr];
+    ScanSet& set = ctx->sets[ctx->set_prep];
+    ctx->set_prep = (ctx->set_prep + 1) % NSETS;
     set.desc = desc_dev;
     set.n_epochs = n_epochs;
     set.phase = 1;
@@ -1281,7 +1298,9 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
     if (!est) est = ctx->d_est_state;
     cudaStream_t aux = ctx->aux2_stream;  // (aux_stream may be busy with the tile prologues of the batch being rendered)
     cudaEvent_t fork = ctx->ev_fork;
-    use_set(ctx, ctx->set_wr);
+    ScanSet& sset = ctx->sets[ctx->set_spec];
+    if (sset.phase != 1) return fail(ctx, GPSIQ_ERR_ARG, "speculate: the next batch in line has not been prepared", cudaSuccess);
+    use_set(ctx, ctx->set_spec);
     const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
     const int EC = n_epochs * C;
     // the code-NCO scan (only k_synth_lanes needs one: k_synth_line's code anchors are closed form) does not depend on
@@ -1307,7 +1326,7 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
                                                          ctx->ck_plane, ctx->d_spec, n_epochs, C, N, T, ntiles, ctx->G,
                                                          ctx->J);
         trace_mark(ctx, st, "k_carr_speculate");
-        CU(cudaEventRecord(ctx->sets[ctx->set_wr].spec_done, st));
+        CU(cudaEventRecord(sset.spec_done, st));
         k_carr_stitch<<<(EC * 2 + 127) / 128, 128, 0, st>>>(desc_dev, est_epoch, ctx->d_spec, ctx->d_carr_ck,
                                                       ctx->ck_plane, ctx->d_cinfo, ctx->d_specE, n_epochs, C, N, T,
                                                       ntiles, ctx->G, ctx->J);
@@ -1323,16 +1342,22 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
         if (!own_est) { k_est_fold<<<1, 32, 0, st>>>(ctx->d_est_state, ctx->d_adv, C); ctx->launches += 1; }
         ctx->launches += 4;
     }
-    ctx->sets[ctx->set_wr].phase = 2;
+    CU(cudaEventRecord(sset.spec_all, st));
+    sset.phase = 2;
+    ctx->set_spec = (ctx->set_spec + 1) % NSETS;
     CU(cudaGetLastError());
     return GPSIQ_OK;
 }
+
+static int enqueue_anchor(gpsiq_ctx* ctx, ScanSet& set, cudaStream_t st, cudaStream_t st_patch);
 
 // Phase 1c: the serial part -- chain the exact carrier phase through the batch (advances the carrier
 // state) and re-anchor the estimate on it.
 static int enqueue_chain(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, cudaStream_t st) {
     const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
+    if (ctx->sets[ctx->set_wr].phase != 2) return fail(ctx, GPSIQ_ERR_ARG, "chain: the next batch in line has not been speculated", cudaSuccess);
     use_set(ctx, ctx->set_wr);
+    CU(cudaStreamWaitEvent(st, ctx->sets[ctx->set_wr].spec_all, 0));  // (a no-op when the speculation ran on this stream)
     CU(cudaStreamWaitEvent(st, ctx->ev_final, 0));  // the carrier state: after the previous batch's chain, whatever its stream
     if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && ctx->cfg.reserved[0] == 0) {
         CU(cudaMemcpyAsync(ctx->d_carr_start, ctx->d_carr_state, C * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -1361,6 +1386,13 @@ static int enqueue_chain(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_
     ctx->set_wr = (ctx->set_wr + 1) % NSETS;
     ctx->set_pending++;
     CU(cudaGetLastError());
+    // Line kernel: tile anchors, safety check and patch walk depend only on the scan results: right behind the chain, on
+    // the set's own stream -- long before the batch is rendered, and beside (not in front of) whatever the caller puts
+    // on `st` next (in time-sliced runs: the hand-off of the exact phases to the next GPU).
+    if (ctx->use_line) {
+        if (st != set.stream) CU(cudaStreamWaitEvent(set.stream, set.scan_done, 0));
+        return enqueue_anchor(ctx, set, set.stream, set.stream);
+    }
     return GPSIQ_OK;
 }
 
@@ -1380,9 +1412,7 @@ static CarrLookup make_lookup(const gpsiq_ctx* ctx) {
 }
 
 // Phase 1d (line kernel): tile anchors, the safety check and the literal-recurrence walk of the tiles it cannot clear,
-// for the set the working pointers are on.  Everything here depends only on the scan results, so pipelined submits
-// enqueue it right behind the batch's chain on the set's own stream (long before the batch is rendered); the phase API
-// of time-sliced runs leaves it to the render call, so that a ring hop is not held up by it.
+// for the set the working pointers are on (enqueue_chain calls it).
 static int enqueue_anchor(gpsiq_ctx* ctx, ScanSet& set, cudaStream_t st, cudaStream_t st_patch) {
     const gpsiq_chan_desc* desc_dev = set.desc;
     const int n_epochs = set.n_epochs;
@@ -1569,14 +1599,14 @@ int gpsiq_synth_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_ep
 // so the previous batch's exact end is not known yet: the estimate is the exact end of the batch BEFORE it (its chain
 // was enqueued a whole batch earlier) advanced by the previous batch's closed-form advance -- or, at the start of a
 // burst, the previous batch's own estimate advanced the same way.
-static int pipelined_estimate(gpsiq_ctx* ctx, ScanSet& set, cudaStream_t ss) {
+static int pipelined_estimate(gpsiq_ctx* ctx, ScanSet& set, int idx, cudaStream_t ss) {
     const size_t bytes = ctx->C * sizeof(double);
     if (ctx->set_pending == 0) {
         CU(cudaStreamWaitEvent(ss, ctx->ev_final, 0));
         CU(cudaMemcpyAsync(set.d_est, ctx->d_carr_state, bytes, cudaMemcpyDeviceToDevice, ss));
     } else {
-        ScanSet& prev = ctx->sets[(ctx->set_wr + NSETS - 1) % NSETS];
-        ScanSet& prev2 = ctx->sets[(ctx->set_wr + NSETS - 2) % NSETS];
+        ScanSet& prev = ctx->sets[(idx + NSETS - 1) % NSETS];
+        ScanSet& prev2 = ctx->sets[(idx + NSETS - 2) % NSETS];
         if (prev.seq != set.seq - 1) return fail(ctx, GPSIQ_ERR_ARG, "internal: scan set ring out of order", cudaSuccess);
         if (NSETS >= 3 && prev2.seq == set.seq - 2 && prev2.phase != 1 && prev2.phase != 2) {
             CU(cudaStreamWaitEvent(ss, prev2.scan_done, 0));
@@ -1595,7 +1625,10 @@ static int pipelined_estimate(gpsiq_ctx* ctx, ScanSet& set, cudaStream_t ss) {
 
 // desc_dev == NULL: the descriptors are already in the write set's own buffer (host submit)
 static int submit_common(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, cudaStream_t after) {
-    ScanSet& set = ctx->sets[ctx->set_wr];
+    if (ctx->set_prep != ctx->set_wr || ctx->set_spec != ctx->set_wr)
+        return fail(ctx, GPSIQ_ERR_ARG, "a batch begun through the phase calls is still waiting for its chain", cudaSuccess);
+    const int idx = ctx->set_wr;
+    ScanSet& set = ctx->sets[idx];
     cudaStream_t ss = set.stream;
     if (after) {  // the descriptors are produced on the caller's stream
         CU(cudaEventRecord(ctx->ev_fork2, after));
@@ -1608,13 +1641,10 @@ static int submit_common(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_
                            cudaMemcpyDeviceToDevice, ss));
     rc = enqueue_prepare(ctx, set.d_descbuf, n_epochs, ss, true);
     const bool spec = ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && ctx->cfg.reserved[0] == 0;
-    if (!rc && spec) rc = pipelined_estimate(ctx, set, ss);
+    if (!rc && spec) rc = pipelined_estimate(ctx, set, idx, ss);
     if (!rc) rc = enqueue_speculate(ctx, set.d_descbuf, n_epochs, ss, spec ? set.d_est : NULL);
     if (!rc) rc = enqueue_chain(ctx, set.d_descbuf, n_epochs, ss);
-    // (enqueue_chain moved the write index on: the set is still the working one.)  The sample kernel needs the anchors
-    // (anch_ready); the patch list (anchor_done) only has to be complete when the sample kernel ends.
-    if (!rc && ctx->use_line) rc = enqueue_anchor(ctx, set, ss, ss);
-    return rc;
+    return rc;   // (the anchors follow the chain on the set's stream: enqueue_chain)
 }
 
 // Streaming pair: submit scans a batch ahead on one of the context's own streams (into the free scan set),
@@ -1637,7 +1667,8 @@ int gpsiq_fetch_device(gpsiq_ctx* ctx, int16_t* iq_dev, void* stream) {
 int gpsiq_submit(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc, int n_epochs) {
     if (!ctx || !desc || n_epochs < 1) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_submit: bad argument", cudaSuccess);
     if (n_epochs > ctx->E) return fail(ctx, GPSIQ_ERR_CAPACITY, "gpsiq_submit: n_epochs > max_epochs", cudaSuccess);
-    if (ctx->set_pending >= NSETS) return fail(ctx, GPSIQ_ERR_CAPACITY, "gpsiq_submit: every scan set is in flight (fetch a batch first)", cudaSuccess);
+    if (ctx->set_prep != ctx->set_wr || ctx->set_spec != ctx->set_wr)
+        return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_submit: a batch begun through the phase calls is still waiting for its chain", cudaSuccess);
     CU(cudaSetDevice(ctx->cfg.device));
     const size_t bytes = (size_t) n_epochs * ctx->C * sizeof(gpsiq_chan_desc);
     const int w = ctx->set_wr;
@@ -1740,7 +1771,7 @@ int gpsiq_multi_submit(gpsiq_multi* m, const gpsiq_chan_desc* desc, int n_epochs
     const int n = m->n, R = n * NSETS;
     gpsiq_ctx* c = m->sub[j % n];
     if (n_epochs > c->E) return mfail(m, GPSIQ_ERR_CAPACITY, "gpsiq_multi_submit: n_epochs > max_epochs", NULL);
-    if (c->set_pending >= NSETS || c->sets[c->set_wr].phase != 0)
+    if (c->sets[c->set_wr].phase != 0 || c->set_prep != c->set_wr || c->set_spec != c->set_wr)
         return mfail(m, GPSIQ_ERR_CAPACITY, "gpsiq_multi_submit: every scan set of the next device is in flight (fetch a batch first)", NULL);
     MCU(cudaSetDevice(c->cfg.device));
     const int w = c->set_wr;
@@ -1786,7 +1817,6 @@ int gpsiq_multi_submit(gpsiq_multi* m, const gpsiq_chan_desc* desc, int n_epochs
         MCU(cudaMemcpyAsync(c->d_carr_state, pc->d_carr_state, cbytes, cudaMemcpyDefault, ss));
     }
     if (!rc) rc = enqueue_chain(c, set.d_descbuf, n_epochs, ss);
-    if (!rc && c->use_line) rc = enqueue_anchor(c, set, ss, ss);
     if (rc) return mfail(m, rc, "gpsiq_multi_submit", c);
     MultiSlot& slot = m->ring[j % R];
     slot.set = &set; slot.dev = (int) (j % n); slot.seq = j;
@@ -1846,7 +1876,7 @@ int gpsiq_prepare_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_
 }
 
 int gpsiq_speculate_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, void* stream) {
-    if (!ctx || !desc_dev || n_epochs != ctx->sets[ctx->set_wr].n_epochs || ctx->sets[ctx->set_wr].phase != 1)
+    if (!ctx || !desc_dev || n_epochs != ctx->sets[ctx->set_spec].n_epochs || ctx->sets[ctx->set_spec].phase != 1)
         return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_speculate_device: must follow gpsiq_prepare_device of the same batch", cudaSuccess);
     CU(cudaSetDevice(ctx->cfg.device));
     return enqueue_speculate(ctx, desc_dev, n_epochs, (cudaStream_t) stream);
@@ -1876,6 +1906,13 @@ int gpsiq_carrier_fold_device(gpsiq_ctx* ctx, const double* advance_dev, void* s
     k_int_fold<<<1, 32, 0, (cudaStream_t) stream>>>(ctx->d_carr_state, advance_dev, ctx->C);
     ctx->launches += 1;
     CU(cudaGetLastError());
+    return GPSIQ_OK;
+}
+
+int gpsiq_estimate_from_device(gpsiq_ctx* ctx, const double* src_dev, void* stream) {
+    if (!ctx || !src_dev) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_estimate_from_device: bad argument", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaMemcpyAsync(ctx->d_est_state, src_dev, ctx->C * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t) stream));
     return GPSIQ_OK;
 }
 

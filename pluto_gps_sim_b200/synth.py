@@ -199,6 +199,9 @@ class Synthesizer:
         """Integer carrier only: exact carrier state <- fold(state, advance of a slice synthesized elsewhere)."""
         capi.check(capi.lib.gpsiq_carrier_fold_device(self._ctx, advance_dev_ptr, stream_ptr), self._ctx)
 
+    def estimate_from_device(self, src_dev_ptr, stream_ptr=None):
+        capi.check(capi.lib.gpsiq_estimate_from_device(self._ctx, src_dev_ptr, stream_ptr), self._ctx)
+
     def estimate_anchor_device(self, stream_ptr=None):
         capi.check(capi.lib.gpsiq_estimate_anchor_device(self._ctx, stream_ptr), self._ctx)
 
