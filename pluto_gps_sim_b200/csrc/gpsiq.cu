@@ -520,36 +520,39 @@ k_epoch_estimates(const double* __restrict__ eadv, const double* __restrict__ er
     }
 }
 
-// One chain per (epoch, slot, chunk, parity variant): speculative scan of the chunk's tiles.
+// One chain per (epoch, slot, chunk): speculative scan of the chunk's tiles, both parity variants (the second one is
+// derived from the first, nco_scan.cuh: spec_scan_chunk).
 __global__ void k_carr_speculate(const gpsiq_chan_desc* __restrict__ desc,
                                  const double* __restrict__ eadv, const double* __restrict__ est_epoch,
                                  double* __restrict__ carr_ck, size_t ck_plane, CarrSpec* __restrict__ spec, int E,
                                  int C, int N, int T, int ntiles, int G, int J) {
-    // one chain per THREAD; the lanes of a warp hold the same (slot, chunk, variant) for 32 consecutive
+    // one chain per THREAD; the lanes of a warp hold the same (slot, chunk) for 32 consecutive
     // epochs: same satellite, nearly the same Doppler, so their segment walks stay mostly convergent
     const int chain0 = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool in_range = chain0 < E * C * J * 2;
+    const bool in_range = chain0 < E * C * J;
     const int chain = in_range ? chain0 : 0;
     const int e = chain % E;
     const int rest = chain / E;
-    const int v = rest & 1;
-    const int j = (rest >> 1) % J, c = (rest >> 1) / J;
+    const int j = rest % J, c = rest / J;
     const int ec = e * C + c;
     const gpsiq_chan_desc d = desc[ec];
-    CarrSpec out;
-    out.margin = -1.0; out.n1 = -1; out.xw1 = 0.0; out.xend = 0.0; out.pad = 0;
-    const bool run = in_range && d.prn > 0 && !(v == 1 && d.carr_step >= 0.0) && carr_step_speculable(d.carr_step);
+    CarrSpec out0, out1;
+    out0.margin = -1.0; out0.n1 = -1; out0.xw1 = 0.0; out0.xend = 0.0; out0.pad = 0;
+    out1 = out0;
+    const bool run = in_range && d.prn > 0 && carr_step_speculable(d.carr_step);
     const unsigned mask = __ballot_sync(0xffffffffu, run);  // the lanes that walk together (lockstep loops, nco_scan.cuh)
     if (run) {
         const int t0 = j * G, t1 = min(t0 + G, ntiles);
         // estimated phase at the chunk's first sample (chunk 0: the epoch estimate itself)
         double x = est_epoch[ec];
         if (j > 0) x = frac01(x + eadv[ec] * ((double) (t0 * T) / (double) N));
-        const StepInfo tab = step_info(d.carr_step);
-        spec_scan_range(x, d.carr_step, tab, N, T, t0, t1, v,
-                        carr_ck + (size_t) v * ck_plane + (size_t) e * ntiles * C + c, (size_t) C, out, mask);
+        double* ck0 = carr_ck + (size_t) e * ntiles * C + c;
+        spec_scan_chunk(x, d.carr_step, step_info(d.carr_step), N, T, t0, t1, ck0, ck0 + ck_plane, (size_t) C, out0, out1, mask);
     }
-    if (in_range) spec[((size_t) ec * J + j) * 2 + v] = out;
+    if (in_range) {
+        spec[((size_t) ec * J + j) * 2] = out0;
+        spec[((size_t) ec * J + j) * 2 + 1] = out1;
+    }
 }
 
 #define SPEC_MAX_CHUNKS 16  // most chunks per epoch (level 1)
@@ -889,7 +892,8 @@ int gpsiq_carrier_chain_host(const double* steps, int n_epochs, int N, int T, do
     CarrInfo* infG = (CarrInfo*) malloc(sizeof(CarrInfo) * 3 * E);   // [0],[1] group variants, [2] exact
     double* trace = (double*) malloc(sizeof(double) * 3 * E);
     double* est = (double*) malloc(sizeof(double) * E);
-    if (!planes || !ge || !ci || !infG || !trace || !est) return GPSIQ_ERR_NOMEM;
+    CarrSpec* cs_all = (CarrSpec*) malloc(sizeof(CarrSpec) * 2 * SPEC_MAX_CHUNKS * E);   // chunk results of every epoch
+    if (!planes || !ge || !ci || !infG || !trace || !est || !cs_all) return GPSIQ_ERR_NOMEM;
     int fb = 0;
     double xe = x0;
     // levels 1 + 2 per epoch: chunk speculation, stitch
@@ -903,17 +907,18 @@ int gpsiq_carrier_chain_host(const double* steps, int n_epochs, int N, int T, do
         a0 -= floor(a0);
         est[e] = a0;
         double* pl = planes + ep * e;
-        CarrSpec cs[2 * SPEC_MAX_CHUNKS];
-        for (int j = 0; j < J; j++)
-            for (int v = 0; v < 2; v++) {
-                CarrSpec& o = cs[j * 2 + v];
-                o.margin = -1.0; o.n1 = -1; o.xw1 = 0; o.xend = 0; o.pad = 0;
-                if ((v == 1 && d >= 0.0) || !carr_step_speculable(d)) continue;
-                const int t0 = j * G, t1 = (t0 + G < ntiles) ? t0 + G : ntiles;
-                double xs = a0;
-                if (j > 0) { xs = a0 + eadv * ((double) (t0 * T) / (double) N); xs -= floor(xs); if (!(xs >= 0.0 && xs < 1.0)) xs = 0.0; }
-                spec_scan_range(xs, d, si, N, T, t0, t1, v, pl + (size_t) v * ntiles, 1, o);
-            }
+        CarrSpec* cs = cs_all + (size_t) e * 2 * SPEC_MAX_CHUNKS;
+        for (int j = 0; j < J; j++) {
+            CarrSpec& o0 = cs[j * 2];
+            CarrSpec& o1 = cs[j * 2 + 1];
+            o0.margin = -1.0; o0.n1 = -1; o0.xw1 = 0; o0.xend = 0; o0.pad = 0;
+            o1 = o0;
+            if (!carr_step_speculable(d)) continue;
+            const int t0 = j * G, t1 = (t0 + G < ntiles) ? t0 + G : ntiles;
+            double xs = a0;
+            if (j > 0) { xs = a0 + eadv * ((double) (t0 * T) / (double) N); xs -= floor(xs); if (!(xs >= 0.0 && xs < 1.0)) xs = 0.0; }
+            spec_scan_chunk(xs, d, si, N, T, t0, t1, pl, pl + (size_t) ntiles, 1, o0, o1);
+        }
         CarrSpec* sE[2] = {&g.s0, &g.s1};
         for (int V = 0; V < 2; V++) {
             sE[V]->margin = -1.0; sE[V]->n1 = -1; sE[V]->xw1 = 0; sE[V]->xend = 0; sE[V]->pad = 0;
@@ -946,10 +951,10 @@ int gpsiq_carrier_chain_host(const double* steps, int n_epochs, int N, int T, do
             for (int t = 0; t < ntiles; t++)
                 ck_out[(size_t) e * ntiles + t] = carr_tile_phase(planes + ep * e, (size_t) ntiles, 1, t, T, N, G, J, k, gi,
                                                                   infG[e], infG[(size_t) E + e], infG[(size_t) 2 * E + e],
-                                                                  ci + (size_t) e * 2 * J);
+                                                                  ci + (size_t) e * 2 * J, cs_all + (size_t) e * 2 * SPEC_MAX_CHUNKS);
         }
     }
-    free(planes); free(ge); free(ci); free(infG); free(trace); free(est);
+    free(planes); free(ge); free(ci); free(infG); free(trace); free(est); free(cs_all);
     if (x_end_out) *x_end_out = x;
     if (n_fallback) *n_fallback = fb;
     return GPSIQ_OK;
@@ -1321,7 +1326,7 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
         trace_mark(ctx, st, "(speculate begin)");
         k_epoch_estimates<<<C, 32, 0, st>>>(ctx->d_drift + 3 * ECmax, ereset, est, est_epoch, n_epochs, C);
         trace_mark(ctx, st, "k_epoch_estimates");
-        const int chains = EC * ctx->J * 2;
+        const int chains = EC * ctx->J;
         k_carr_speculate<<<(chains + 127) / 128, 128, 0, st>>>(desc_dev, eadv, est_epoch, ctx->d_carr_ck,
                                                          ctx->ck_plane, ctx->d_spec, n_epochs, C, N, T, ntiles, ctx->G,
                                                          ctx->J);
@@ -1407,7 +1412,7 @@ static int enqueue_scan(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_e
 static CarrLookup make_lookup(const gpsiq_ctx* ctx) {
     CarrLookup L;
     L.ck = ctx->d_carr_ck; L.plane = ctx->ck_plane; L.ginfo = ctx->d_ginfo; L.infoG = ctx->d_info;
-    L.info_plane = (size_t) ctx->E * ctx->C; L.cinfo = ctx->d_cinfo; L.G = ctx->G; L.J = ctx->J; L.GP = GROUP_EPOCHS;
+    L.info_plane = (size_t) ctx->E * ctx->C; L.cinfo = ctx->d_cinfo; L.spec = ctx->d_spec; L.G = ctx->G; L.J = ctx->J; L.GP = GROUP_EPOCHS;
     return L;
 }
 

@@ -254,18 +254,27 @@ struct CarrSpec {   // result of one speculative epoch scan
     double xend;    // state after the last sample of the epoch
     double margin;  // decision margin from n1 on; <= 0: unusable
     int n1;         // index of the first sample whose state follows a wrap; N if the run never wraps
-    int pad;
+    int pad;        // variant 0: 0.  Variant 1 of a chunk run: -1 = scanned for real (plane 1 holds its tile starts);
+                    // >= 0 = DERIVED from variant 0 (spec_derive_variant1): ((tie_n + 1) << 2) | (tie_up << 1) | (s < 0)
 };
 
 // One carrier step with margin tracking (TRACK) -- same arithmetic as nco_step<NCO_CARRIER>.
+// tie (if not null): set to 1 / 2 when a NEGATIVE wrap's y + 1.0 was an exact rounding tie on the 2^-53 grid and was
+// rounded down / up (to the even neighbour): the one event at which a run shifted by an odd multiple of 2^-53 stops
+// being an exact translate of this one (spec_derive_variant1).
 template <bool TRACK>
-GPSIQ_HD bool carr_step(double& x, double d, double& margin) {
+GPSIQ_HD bool carr_step(double& x, double d, double& margin, int* tie = nullptr) {
     double y = add_rn(x, d);
     bool w = false;
     if (TRACK) { const double m = binade_margin(y); if (m < margin) margin = m; }
     if (y >= 1.0) { y = add_rn(y, -1.0); w = true; }
     else if (y < 0.0) {
-        y = add_rn(y, 1.0); w = true;
+        const double z = add_rn(y, 1.0);
+        if (TRACK && tie) {
+            const double err = add_rn(add_rn(z, -1.0), -y);   // both differences are exact: the rounding error of y + 1.0
+            if (err == 0x1p-54) *tie = 2; else if (err == -0x1p-54) *tie = 1;
+        }
+        y = z; w = true;
         if (TRACK) { const double m = ((1.0 - y < y - 0.5) ? 1.0 - y : y - 0.5) - 0x1p-53; if (m < margin) margin = m; }
     }
     x = y;
@@ -302,7 +311,8 @@ GPSIQ_HD int carr_advance(double& x, double d, const StepInfo& tab, int count, b
 // tile start passed (the state BEFORE that sample) goes to ck[tile * stride]; starts inside a run come from the run's
 // closed form on the bit pattern.  n, next: sample indices relative to the scanned range (tile starts = multiples of T
 // from its first sample); next = the next tile start not yet emitted (>= n), t = its tile number.
-struct CarrWalk { double x; int n; int next; int t; };
+struct CarrWalk { double x; int n; int next; int t; int tie_n; int tie_up; };  // tie_n: sample index right after the
+                                                                               // first tie-wrap of the tracked walk (-1: none)
 
 // warp_any: on the device, with the ballot mask of the lanes that walk together, the loop runs in lockstep until the
 // LAST lane is done (a lane that is done idles): without it lanes that leave a loop at different iterations never
@@ -343,8 +353,10 @@ GPSIQ_HD bool carr_walk(CarrWalk& w, const StepInfo& si, int n_end, int T, bool 
             if (w.n >= n_end) continue;
             if (w.n == w.next) { ck[(size_t) w.t * stride] = w.x; w.t++; w.next += T; }
         }
-        const bool wrapped = carr_step<TRACK>(w.x, si.d, margin);
+        int tie = 0;
+        const bool wrapped = carr_step<TRACK>(w.x, si.d, margin, &tie);
         w.n++;
+        if (TRACK && tie && w.tie_n < 0) { w.tie_n = w.n; w.tie_up = tie == 2; }
         if (wrapped && stop_at_wrap) stopped = true;
     }
     return stopped;
@@ -388,11 +400,12 @@ GPSIQ_HD bool carr_step_speculable(double d) {
 // t (absolute tile index).  out.n1 is relative to sample t0*T; it equals the
 // range's sample count if the run never wraps.
 GPSIQ_HD void spec_scan_range(double x, double d, const StepInfo& tab, int N, int T, int t0, int t1, int variant,
-                              double* ck, size_t ck_stride, CarrSpec& out, unsigned mask = 0) {
+                              double* ck, size_t ck_stride, CarrSpec& out, unsigned mask = 0, int* tie_n = nullptr,
+                              int* tie_up = nullptr) {
     const int m_total = ((t1 * T < N) ? t1 * T : N) - t0 * T;
     double margin = 1.0, dummy = 1.0;
     CarrWalk w;
-    w.x = x; w.n = 0; w.next = 0; w.t = t0;
+    w.x = x; w.n = 0; w.next = 0; w.t = t0; w.tie_n = -1; w.tie_up = 0;
     out.n1 = m_total;
     out.xw1 = 0.0;
     const bool seen_wrap = carr_walk<false>(w, tab, m_total, T, true, ck, ck_stride, dummy, mask);  // up to the first wrap
@@ -408,6 +421,64 @@ GPSIQ_HD void spec_scan_range(double x, double d, const StepInfo& tab, int N, in
     if (bad) margin = -1.0;
     out.xend = w.x;
     out.margin = (seen_wrap && carr_step_speculable(d)) ? margin : -1.0;
+    out.pad = (variant == 1) ? -1 : 0;
+    if (tie_n) { *tie_n = w.tie_n; *tie_up = w.tie_up; }
+}
+
+// A negative step needs both parities of the 2^-53 grid speculated (the parity of the true post-wrap state is not
+// known in advance), but the second run need not be scanned: shifted by s * 2^-53 at the first wrap it stays an exact
+// translate of the first one -- every grid below 0.5 is finer (the shift is an even multiple of it), and on the 2^-53
+// grid of [0.5, 1) a shift by one grid unit commutes with round-to-nearest except on an exact tie -- until the first
+// wrap whose y + 1.0 IS an exact tie: there both runs round to the EVEN neighbour, and from then on they differ by
+// 0 or by 2 * 2^-53 (an even shift, which commutes with everything from there on).  Ties of ordinary additions in
+// [0.5, 1) need |d| == 2^-54 (mod 2^-53): such steps are scanned for real (carr_step_odd_shift_safe).
+GPSIQ_HD bool carr_step_odd_shift_safe(double d) {
+    const int64_t b = f64_bits(d) & 0x7fffffffffffffffLL;
+    const int64_t e = b >> 52;
+    if (e == 0) return false;
+    const int64_t m = (b & 0xfffffffffffffLL) | (1LL << 52);
+    int tz = 0;
+    while (!((m >> tz) & 1)) tz++;
+    return (int) e - 1075 + tz != -54;   // the lowest set bit of |d| is not exactly 2^-54
+}
+
+// shift of the derived variant-1 run against variant 0, in units of 2^-53, at chunk-relative sample index n
+GPSIQ_HD int derived_shift(const CarrSpec& s1, int n) {
+    const int tie_n = (s1.pad >> 2) - 1, s = (s1.pad & 1) ? -1 : 1;
+    if (n < s1.n1) return 0;                          // before the first wrap the two runs are the same run
+    if (tie_n < 0 || n < tie_n) return s;
+    const bool up = (s1.pad & 2) != 0;                // the tie was rounded up: 1 + y = (k + 1/2) * 2^-53 with k odd
+    return s > 0 ? (up ? 0 : 2) : (up ? -2 : 0);
+}
+
+GPSIQ_HD void spec_derive_variant1(const CarrSpec& s0, int m_total, int tie_n, int tie_up, CarrSpec& s1) {
+    s1.margin = -1.0; s1.n1 = -1; s1.xw1 = 0.0; s1.xend = 0.0; s1.pad = 0;
+    if (!(s0.margin > 0.0) || s0.n1 >= m_total) return;            // never wrapped / unusable: so is its shifted twin
+    const int s = (s0.xw1 + 0x1p-53 < 1.0) ? 1 : -1;               // other parity of the 2^-53 grid (as spec_scan_range)
+    s1.n1 = s0.n1;
+    s1.xw1 = s0.xw1 + (double) s * 0x1p-53;
+    s1.pad = ((tie_n + 1) << 2) | (tie_up ? 2 : 0) | (s < 0 ? 1 : 0);
+    s1.xend = add_rn(s0.xend, (double) derived_shift(s1, m_total) * 0x1p-53);
+    s1.margin = s0.margin - 0x1p-51;                               // the shift itself eats into every decision's margin
+    if (!(s1.xw1 >= 0.0 && s1.xw1 < 1.0) || !(s1.xend >= 0.0 && s1.xend < 1.0)) s1.margin = -1.0;
+}
+
+// Both parity variants of one chunk: variant 0 scanned, variant 1 derived from it (or scanned, for the rare steps
+// whose ordinary additions can tie).  ck0 / ck1: the chunk planes of the two variants.
+GPSIQ_HD void spec_scan_chunk(double x, double d, const StepInfo& tab, int N, int T, int t0, int t1, double* ck0, double* ck1,
+                              size_t ck_stride, CarrSpec& out0, CarrSpec& out1, unsigned mask = 0) {
+    int tie_n = -1, tie_up = 0;
+    spec_scan_range(x, d, tab, N, T, t0, t1, 0, ck0, ck_stride, out0, mask, &tie_n, &tie_up);
+    out1.margin = -1.0; out1.n1 = -1; out1.xw1 = 0.0; out1.xend = 0.0; out1.pad = 0;
+    const bool neg = d < 0.0;
+    const bool real = neg && !carr_step_odd_shift_safe(d);
+#if defined(__CUDA_ARCH__)
+    const unsigned m1 = mask ? __ballot_sync(mask, real) : 0u;
+#else
+    const unsigned m1 = 0u;
+#endif
+    if (real) spec_scan_range(x, d, tab, N, T, t0, t1, 1, ck1, ck_stride, out1, m1);
+    else if (neg) spec_derive_variant1(out0, ((t1 * T < N) ? t1 * T : N) - t0 * T, tie_n, tie_up, out1);
 }
 
 GPSIQ_HD void spec_scan_epoch(double x, double d, const StepInfo& tab, int N, int T, int variant, double* ck,
@@ -716,7 +787,7 @@ GPSIQ_HD double group_final(double x, const GroupEpoch* ge, int count, int N, in
 // infG[0], infG[1]: the epoch's CarrInfo from the two group-chain variants; infX: from the exact fallback chain.
 GPSIQ_HD double carr_tile_phase(const double* ck, size_t plane, size_t stride, int t, int T, int N, int G, int J, int eg,
                                 const GroupInfo& gi, const CarrInfo& infG0, const CarrInfo& infG1, const CarrInfo& infX,
-                                const ChunkInfo* ci) {
+                                const ChunkInfo* ci, const CarrSpec* cs) {
     const int n0 = t * T;
     const size_t o = (size_t) t * stride;
     const bool all_exact = gi.pos == 0x7fffffff;
@@ -729,7 +800,17 @@ GPSIQ_HD double carr_tile_phase(const double* ck, size_t plane, size_t stride, i
     } else {
         const int V = inf.variant;
         const ChunkInfo c = ci[V * J + t / G];
-        p = (n0 < c.n1) ? ck[(size_t) (2 + V) * plane + o] : add_rn(ck[(size_t) c.variant * plane + o], c.delta);
+        if (n0 < c.n1) {
+            p = ck[(size_t) (2 + V) * plane + o];
+        } else {
+            const int j = t / G;
+            double q;
+            if (c.variant == 1 && cs[j * 2 + 1].pad >= 0)   // derived variant: plane 0 shifted (cs = the chunk results [J][2])
+                q = add_rn(ck[o], (double) derived_shift(cs[j * 2 + 1], n0 - j * G * T) * 0x1p-53);
+            else
+                q = ck[(size_t) c.variant * plane + o];
+            p = add_rn(q, c.delta);
+        }
         p = add_rn(p, inf.delta);
     }
     return all_exact ? p : add_rn(p, gi.delta);
@@ -743,6 +824,7 @@ struct CarrLookup {
     const CarrInfo* infoG;   // [3][Ecap][C]: group-chain variants 0, 1 and the exact fallback chain
     size_t info_plane;       // Ecap * C
     const ChunkInfo* cinfo;  // [E][C][2][J]
+    const CarrSpec* spec;    // [E][C][J][2] chunk results (the derived variant-1 planes are evaluated from them)
     int G, J, GP;            // chunk length (tiles), chunks per epoch, epochs per group
 };
 
@@ -750,7 +832,7 @@ GPSIQ_HD double carr_lookup(const CarrLookup& L, int e, int c, int t, int T, int
     const size_t ec = (size_t) e * C + c;
     return carr_tile_phase(L.ck + (size_t) e * ntiles * C + c, L.plane, (size_t) C, t, T, N, L.G, L.J, e % L.GP,
                            L.ginfo[(size_t) (e / L.GP) * C + c], L.infoG[ec], L.infoG[L.info_plane + ec],
-                           L.infoG[2 * L.info_plane + ec], L.cinfo + ec * 2 * L.J);
+                           L.infoG[2 * L.info_plane + ec], L.cinfo + ec * 2 * L.J, L.spec + ec * 2 * L.J);
 }
 
 // (3) exact chaining of one epoch from the exact start x; returns the exact end state.

@@ -122,3 +122,32 @@ def test_parallel_carrier_scan_unspeculable_steps():
         got, gx, fb = capi.carrier_chain_host([d, d, d], N, T, 0.123456789, 0.0)
         assert np.array_equal(got.view(np.int64), want.view(np.int64)), d
         assert bits(gx) == bits(wx)
+
+
+def test_negative_doppler_uses_the_derived_parity_variant():
+    """step < 0: the second parity variant of every chunk run is DERIVED from the first (shifted by 2^-53 until the first
+    wrap whose y + 1.0 is an exact tie, then by 0 or 2^-52; nco_scan.cuh: spec_derive_variant1).  Many negative steps,
+    random phases (both parities of the true post-wrap state occur), long epochs (dozens of tie-wraps): every tile-start
+    phase equals the literal recurrence, and nearly every epoch is translated, not re-scanned."""
+    rng = random.Random(2024)
+    fb_total, epochs = 0, 0
+    for trial in range(24):
+        fs = rng.choice([2.6e6, 1e7])
+        f0 = -rng.uniform(300, 5000)
+        E, N, T = rng.choice([6, 12]), 300000, 1024
+        steps = [(f0 + rng.uniform(-1, 1)) * (1.0 / fs) for _ in range(E)]
+        x0 = rng.random()
+        err = rng.choice([0.0, 3e-13, 1e-11])
+        want, wx = _literal_checkpoints(steps, N, T, x0)
+        got, gx, fb = capi.carrier_chain_host(steps, N, T, x0, err)
+        assert np.array_equal(got.view(np.int64), want.view(np.int64)), (trial, f0, err)
+        assert bits(gx) == bits(wx)
+        fb_total += fb
+        epochs += E
+    assert fb_total <= epochs // 10, (fb_total, epochs)
+
+    # a step whose ordinary additions in [0.5, 1) can tie (lowest set bit exactly 2^-54): scanned for real, still exact
+    d = -(1234567 * 2.0 ** -30 + 2.0 ** -54)
+    want, wx = _literal_checkpoints([d] * 4, 100000, 1024, 0.3141592653589793)
+    got, gx, fb = capi.carrier_chain_host([d] * 4, 100000, 1024, 0.3141592653589793, 1e-12)
+    assert np.array_equal(got.view(np.int64), want.view(np.int64)) and bits(gx) == bits(wx)
