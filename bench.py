@@ -459,15 +459,14 @@ def ours_arm(args):
         kiso_ms, kiso_ep = 0.0, 0
 
     # ---- end to end through host buffers (e2e)
-    if args.no_e2e:
-        if world > 1:
-            dist.destroy_process_group()
-        return
     h_desc = capi.lib.gpsiq_host_alloc(nbytes_desc)
     outs = [capi.lib.gpsiq_host_alloc(samples_per_step * 4) for _ in range(2)]
     assert h_desc and all(outs)
-    synth2 = make_synth()
-    if world == 1:
+    synth2 = make_synth() if not args.no_e2e else None
+    e2e_s, e2e_how = float("inf"), "skipped (--no-e2e)"
+    if args.no_e2e:
+        pass
+    elif world == 1:
         def run_host_batches(count, first_d=None):
             """`count` batches through the host-buffer streaming pair gpsiq_submit / gpsiq_fetch: every batch's
             descriptors go host->device and its full int16 stream comes device->host inside this call sequence."""

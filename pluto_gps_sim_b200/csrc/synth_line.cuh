@@ -29,10 +29,19 @@
 
 #include "line_check.cuh"
 
-#define LN_RUN 16
+// Geometry (measured on B200, profiles/r02_r_geometry_sweep.txt): a lane renders LN_RUN = 32 samples of a slot before it
+// moves to the next slot, so a warp-block is a whole 1024-sample tile and the ~20 instructions of per-slot set-up are
+// paid once per 32 samples instead of once per 16 (round 1: LN_RUN 16, 512 threads, 48 registers: 1.35 ms per 1024-epoch
+// launch; now 1.14 ms).  The 32 accumulators need 64 registers: 448 threads per CTA, two CTAs per SM = 7/8 of the
+// register file, the rest is left to the scan kernels that run beside it.  (-D overrides for experiments.)
+#ifndef LN_RUN
+#define LN_RUN 32
+#endif
 #define LN_WB (32 * LN_RUN)       // samples per warp-block
 #define LN_TILE 1024
-#define LN_THREADS 512
+#ifndef LN_THREADS
+#define LN_THREADS 448
+#endif
 #define LN_WARPS (LN_THREADS / 32)
 #define LN_CG 12                  // slots resident at a time
 #define LN_VS 1536                // chip-sign entries per variant: 1023 + 512 (code_step <= 0.5) + 1
@@ -404,11 +413,16 @@ __device__ __forceinline__ bool ln_mbar_wait(uint32_t bar, uint32_t parity) {
 // they retire every ~100 us, so the hardware block scheduler can place the small latency-bound kernels of
 // the next batch's carrier chain (launched on higher-priority streams) beside this kernel as slots free up.
 // A persistent variant with its own tile scheduler was ~3 % faster alone but starved those kernels.
-#define LN_UNIT 32
+#ifndef LN_UNIT
+#define LN_UNIT 42   // tiles per CTA: three per warp
+#endif
+#ifndef LN_MAXNREG
+#define LN_MAXNREG 64
+#endif
 
 // 48 registers: two CTAs use 3/4 of an SM's register file, so that the small latency-bound kernels of the
 // next batch's carrier chain (stitch / group / final, code scan) can run beside it
-__global__ void __maxnreg__(48)
+__global__ void __maxnreg__(LN_MAXNREG)
 k_synth_line(const gpsiq_chan_desc* __restrict__ desc, const int32_t* __restrict__ lutp,
              const int8_t* __restrict__ chips4, const ulonglong2* __restrict__ anch,
              const int* __restrict__ amp_sum, const int* __restrict__ step_flag, int16_t* __restrict__ iq,
