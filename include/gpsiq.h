@@ -186,6 +186,17 @@ int gpsiq_nco_advance(int mode, double *phase, double step, int64_t count, int64
 int gpsiq_carrier_chain_host(const double *steps, int n_epochs, int N, int T, double x0, double est_err,
                              double *ck_out, double *x_end_out, int *n_fallback);
 
+/* The same through the fifth level (csrc/nco_scan.cuh: slice_chain_group / slice_verify), as the device chains a
+ * batch: the groups chained speculatively from the ESTIMATED batch start, ONE exact head scan matched against that
+ * trajectory, then every group chained on its own from its translated start phase (the device does these in parallel,
+ * after the hand-off of a time-sliced run).  *how_out: 1 = passed by translation, 0 = chained serially (no usable
+ * slice-level speculation), -2 = a group ended somewhere else than the translation predicts (internal error).
+ * ties_out (2 ints, may be NULL): [0] usable group trajectories that contain a tie-wrap of a tie-capable step
+ * (csrc/nco_scan.cuh: TieEvent), [1] translations that changed at such an event (groups + 1000 * slice level).
+ * Diagnostic aid. */
+int gpsiq_carrier_slice_host(const double *steps, int n_epochs, int N, int T, double x0, double est_err,
+                             double *ck_out, double *x_end_out, int *n_fallback, int *how_out, int *ties_out);
+
 /* Pinned host memory for descriptors / I/Q (cudaHostAlloc). */
 void *gpsiq_host_alloc(size_t bytes);
 void gpsiq_host_free(void *p);
@@ -267,6 +278,14 @@ int gpsiq_carrier_from_device(gpsiq_ctx *ctx, const double *src_dev, void *cuda_
 int64_t gpsiq_launch_count(const gpsiq_ctx *ctx);
 /* (epoch, slot) pairs whose carrier scan fell back to the serial path so far. */
 int gpsiq_carrier_fallbacks(gpsiq_ctx *ctx, int64_t *count);
+/* Float carrier: (slot, batch) chains whose exact chain was ONE head scan + a translation of the slice-level
+ * speculative trajectory (csrc/nco_scan.cuh, level 5), and the ones chained serially group by group (stream start,
+ * re-seeded slots, a poor start-phase estimate).  Speed only: both give the same phases. */
+int gpsiq_slice_stats(gpsiq_ctx *ctx, int64_t *translated, int64_t *serial);
+/* Waits for the device and reports an error a kernel has flagged since the last check (an out-of-contract descriptor,
+ * a table copy that never completed, an internal inconsistency of the carrier chain) -- what gpsiq_synth / gpsiq_fetch
+ * check by themselves; for callers of the device-pointer API.  GPSIQ_OK if there is none. */
+int gpsiq_device_status(gpsiq_ctx *ctx);
 /* Device-side timing (CUDA events on the launching stream).  After
  * gpsiq_timing_begin every synth call records events around its scan phase and
  * its synthesis kernel (up to 64 calls); gpsiq_timing_collect waits for them and

@@ -70,10 +70,13 @@ SYMBOLS = {
     "gpsiq_make_desc": (_i, [_vp, _i, _i, _d, _d, _d, _d, _d, _vp, _i, _i, _i, _d, _i]),
     "gpsiq_nco_advance": (_i, [_i, C.POINTER(_d), _d, _i64, C.POINTER(_i64)]),
     "gpsiq_carrier_chain_host": (_i, [_vp, _i, _i, _i, _d, _d, _vp, C.POINTER(_d), C.POINTER(_i)]),
+    "gpsiq_carrier_slice_host": (_i, [_vp, _i, _i, _i, _d, _d, _vp, C.POINTER(_d), C.POINTER(_i), C.POINTER(_i), _vp]),
     "gpsiq_host_alloc": (_vp, [C.c_size_t]),
     "gpsiq_host_free": (None, [_vp]),
     "gpsiq_launch_count": (_i64, [_vp]),
     "gpsiq_carrier_fallbacks": (_i, [_vp, C.POINTER(_i64)]),
+    "gpsiq_slice_stats": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "gpsiq_device_status": (_i, [_vp]),
     "gpsiq_timing_begin": (_i, [_vp]),
     "gpsiq_timing_collect": (_i, [_vp, C.POINTER(_i), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "gpsiq_timing_sample_kernel": (_i, [_vp, C.POINTER(_i), C.POINTER(C.c_float), C.POINTER(_i)]),
@@ -207,6 +210,19 @@ def carrier_chain_host(steps, N, T, x0, est_err=0.0):
     check(lib.gpsiq_carrier_chain_host(st.ctypes.data, st.size, N, T, float(x0), float(est_err), ck.ctypes.data,
                                        C.byref(xe), C.byref(fb)))
     return ck, xe.value, fb.value
+
+
+def carrier_slice_host(steps, N, T, x0, est_err=0.0, ties=None):
+    """Host run of the carrier scan through the slice level (one exact head scan per batch, groups chained from their
+    translated starts) -> (ck [E][ntiles], x_end, n_fallback, how): how 1 translated, 0 serial, -2 internal error.
+    ties: optional int32 array of 2 -> [group trajectories holding a tie event, translations changed by one]."""
+    st = np.ascontiguousarray(steps, dtype=np.float64)
+    ntiles = (N + T - 1) // T
+    ck = np.zeros((st.size, ntiles), np.float64)
+    xe, fb, how = _d(0), _i(0), _i(0)
+    check(lib.gpsiq_carrier_slice_host(st.ctypes.data, st.size, N, T, float(x0), float(est_err), ck.ctypes.data,
+                                       C.byref(xe), C.byref(fb), C.byref(how), None if ties is None else ties.ctypes.data))
+    return ck, xe.value, fb.value, how.value
 
 
 def make_desc(carrier_mode, prn, f_carr, f_code, delt, carr_phase, code_phase, dwrd60, iword, ibit, icode, gain,

@@ -79,11 +79,15 @@ struct TraceRec { cudaEvent_t ev; const char* label; int stream_id; };
 // Everything the scan phases produce for one batch and the render phase consumes.  There are two
 // sets so that gpsiq_submit_device can scan batch k+1 while gpsiq_fetch_device renders batch k;
 // the working pointers in gpsiq_ctx (d_lut, d_carr_ck, ...) are switched to one set before enqueuing.
+struct SliceRes;
 struct ScanSet {
     gpsiq_chan_desc* d_descbuf;
     int2* d_lut; int32_t* d_lutp; int* d_flags; double* d_code_ck; int* d_wrap_ck; double* d_carr_ck;
     double* d_drift; CarrSpec* d_spec; CarrSpec* d_specE; ChunkInfo* d_cinfo; CarrInfo* d_info;
     CarrSpec* d_specG; GroupInfo* d_ginfo; double* d_traceG;
+    CarrSpec* d_specS; double* d_startS; SliceRes* d_sres;   // level 5: slice-level speculation, group entry phases, match result
+    TieEvent* d_tieG; TieEvent* d_tieS;                      // first tie-wrap of every group- / slice-level trajectory
+    double* d_start0;             // [C] exact phases at the first sample of the batch (once its chain has run)
     double* d_adv; double* d_carr_trace; uint32_t* d_ustart;
     LineEpoch* d_lrecs; uint32_t* d_elist; uint32_t* d_hazlist; int* d_line_counters; LinePatch* d_patches;
     int anchored;                 // the batch's tile anchors, safety check and patch list have been enqueued
@@ -130,6 +134,7 @@ struct gpsiq_ctx {
     double* d_bias_rate;  // [C] measured residual of the closed-form epoch advance (cycles per epoch), see k_bias_update
     double* d_carr_start; // [C] exact phases at the start of the batch being chained
     int chain_keeps_estimate;  // GPSIQ_OPT_CHAIN_KEEPS_ESTIMATE
+    int slice_spec;            // level 5 (slice-level speculation: one head scan per batch on the chain's critical path); GPSIQ_SLICE_SPEC=0 turns it off
     int render_after_next_chain;  // GPSIQ_OPT_RENDER_AFTER_NEXT_CHAIN
     // SM-free carrier hand-off between the GPUs of one node (gpsiq_mailbox_*)
     unsigned char* d_mbox;      // own mailbox: [2][MBOX_SLOT] state slots, sequence flag at MBOX_FLAG
@@ -164,7 +169,14 @@ struct gpsiq_ctx {
     CarrSpec* d_specG;    // [groups][C][2] group-level speculation results
     GroupInfo* d_ginfo;   // [groups][C]    final chain results
     double* d_traceG;     // [2][E][C]      post-epoch phases of the group chains
+    CarrSpec* d_specS;    // [C][2]         slice-level speculation results (level 5)
+    double* d_startS;     // [2][groups][C] phase of the slice-level trajectories at every group start
+    SliceRes* d_sres;     // [C]            how k_carr_final passed the batch (translated / serial)
+    TieEvent* d_tieG;     // [groups][C][2] first tie-wrap of the group-level trajectories (nco_scan.cuh: TieEvent)
+    TieEvent* d_tieS;     // [C][2]         ... of the slice-level trajectories (pos = group index)
+    double* d_start0;     // [C]            exact phases at the batch's first sample
     int* d_fallbacks;     // epochs that fell back to the serial carrier scan (diagnostic counter)
+    unsigned long long* d_slice_stats;  // [2] (slot, batch) chains passed by the slice-level translation / chained serially
     size_t ck_plane;      // elements per plane
     double* d_carr_state; // [C]  exact carrier phase per slot after the last chained epoch
     double* d_est_state;  // [C]  ESTIMATED phase at the start of the next batch to speculate (never part of a result)
@@ -604,7 +616,8 @@ __global__ void __launch_bounds__(32)
 k_carr_group(const gpsiq_chan_desc* __restrict__ desc,
              const CarrSpec* __restrict__ specE, const double* __restrict__ est_epoch, double* __restrict__ carr_ck,
              size_t ck_plane, CarrInfo* __restrict__ infoG, size_t info_plane, double* __restrict__ traceG,
-             CarrSpec* __restrict__ specG, int* __restrict__ fallbacks, int E, int C, int N, int T, int ntiles) {
+             CarrSpec* __restrict__ specG, TieEvent* __restrict__ tieG, int* __restrict__ fallbacks, int E, int C, int N,
+             int T, int ntiles) {
     __shared__ GroupEpoch s_ge[GROUP_EPOCHS];
     const int lane = threadIdx.x;
     const int ngroups = (E + GROUP_EPOCHS - 1) / GROUP_EPOCHS;
@@ -617,6 +630,8 @@ k_carr_group(const gpsiq_chan_desc* __restrict__ desc,
     if (lane) return;
     CarrSpec out;
     out.margin = -1.0; out.n1 = -1; out.xw1 = 0.0; out.xend = 0.0; out.pad = 0;
+    TieEvent tie;
+    tie.pos = -1; tie.k = 0;
     bool any_neg = false;
     for (int k = 0; k < count; k++) any_neg |= s_ge[k].active && s_ge[k].d < 0.0;
     if (V == 0 || any_neg) {
@@ -624,59 +639,198 @@ k_carr_group(const gpsiq_chan_desc* __restrict__ desc,
         group_chain(est_epoch[(size_t) first * C + c], s_ge, count, N, T, V,
                     carr_ck + (size_t) (4 + V) * ck_plane + (size_t) first * ntiles * C + c, (size_t) C, (size_t) ntiles * C,
                     infoG + (size_t) V * info_plane + (size_t) first * C + c, (size_t) C,
-                    traceG + (size_t) V * info_plane + (size_t) first * C + c, (size_t) C, out, fb);
+                    traceG + (size_t) V * info_plane + (size_t) first * C + c, (size_t) C, out, tie, fb);
         if (fb && V == 0) atomicAdd(fallbacks, fb);
     }
     specG[(size_t) gc * 2 + V] = out;
+    tieG[(size_t) gc * 2 + V] = tie;
 }
 
-// Level 4: the exact chain, one chain per slot, serial over the groups: one head scan per group.
+// One group of the exact chain (level 4), executed by one warp: one head scan by lane 0 (fast path: only the group's
+// first epoch is staged), the lanes translate the post-epoch phases of the other epochs in parallel.  x_start: the exact
+// phase at the group's first sample (lane 0's value counts).  Returns the exact phase after the group (on lane 0).
+__device__ __forceinline__ double final_group_warp(GroupEpoch* s_ge, double x_start, int g, const gpsiq_chan_desc* __restrict__ desc,
+                                                   const CarrSpec* __restrict__ specE, const CarrSpec* __restrict__ specG,
+                                                   const TieEvent* __restrict__ tieG, double* __restrict__ carr_ck, size_t ck_plane, CarrInfo* __restrict__ infoG,
+                                                   size_t info_plane, const double* __restrict__ traceG,
+                                                   double* __restrict__ carr_trace, GroupInfo* __restrict__ ginfo, int& fb,
+                                                   int E, int C, int c, int N, int T, int ntiles, int lane) {
+    const int first = g * GROUP_EPOCHS, count = min(GROUP_EPOCHS, E - first);
+    const size_t o = (size_t) first * C + c;
+    const CarrSpec sG0 = specG[((size_t) g * C + c) * 2], sG1 = specG[((size_t) g * C + c) * 2 + 1];
+    const TieEvent tG0 = tieG[((size_t) g * C + c) * 2], tG1 = tieG[((size_t) g * C + c) * 2 + 1];
+    double* ckX = carr_ck + 6 * ck_plane + (size_t) first * ntiles * C + c;
+    // Fast path (almost always taken): the group's first epoch is active, wraps, and the group trajectory
+    // fits from there.  Only that epoch's inputs are staged; the serial work is its head scan, and the
+    // lanes translate the post-epoch phases of the other epochs in parallel.
+    stage_group(s_ge, desc, specE, first, 1, c, C, lane);
+    double x = x_start;
+    GroupInfo gi;
+    gi.delta = 0.0; gi.delta2 = 0.0; gi.pos = 0x7fffffff; gi.variant = 0; gi.tie_pos = 0x7fffffff; gi.pad = 0;
+    int fb_try = 0;
+    if (lane == 0)
+        x = group_final(x_start, s_ge, 1, N, T, sG0, sG1, ckX, (size_t) C, (size_t) ntiles * C, infoG + 2 * info_plane + o,
+                        (size_t) C, traceG + o, traceG + info_plane + o, carr_trace + o, (size_t) C, gi, fb_try, tG0, tG1);
+    const int pos = __shfl_sync(0xffffffffu, gi.pos, 0);
+    if (pos < N) {  // translated inside the first epoch
+        const double diff = __shfl_sync(0xffffffffu, gi.delta, 0), diff2 = __shfl_sync(0xffffffffu, gi.delta2, 0);
+        const int tie_pos = __shfl_sync(0xffffffffu, gi.tie_pos, 0);
+        const int v = __shfl_sync(0xffffffffu, gi.variant, 0);
+        const double* tg = traceG + (v ? info_plane : 0) + o;
+        for (int e2 = 1 + lane; e2 < count; e2 += 32)   // (as group_final translates them: the shift after a tie event is diff2)
+            carr_trace[o + (size_t) e2 * C] = add_rn(tg[(size_t) e2 * C], ((long long) tie_pos <= (long long) (e2 + 1) * N) ? diff2 : diff);
+    } else {        // anything else: the general chain over the whole group, from the group's start state
+        stage_group(s_ge, desc, specE, first, count, c, C, lane);
+        if (lane == 0)
+            x = group_final(x_start, s_ge, count, N, T, sG0, sG1, ckX, (size_t) C, (size_t) ntiles * C,
+                            infoG + 2 * info_plane + o, (size_t) C, traceG + o, traceG + info_plane + o, carr_trace + o,
+                            (size_t) C, gi, fb, tG0, tG1);
+    }
+    if (lane == 0) ginfo[(size_t) g * C + c] = gi;
+    __syncwarp();
+    return x;
+}
+
+// Result of the slice-level match of one slot (k_carr_final -> k_carr_final_groups)
+struct SliceRes {     // how: 0 chained serially, 1 translated, 2 slot inactive in the whole batch
+    double diff, diff2;   // translation of the slice-level trajectory; diff2: for the groups after group tie_g (TieEvent)
+    int variant, how, tie_g, pad;
+};
+#define GPSIQ_DEVERR_SLICE 0x10000000   // error word: the parallel group chain disagreed with the slice-level translation
+
+// Level 5, speculative (nco_scan.cuh: slice_chain_group): one chain per (slot, variant), serial over the batch's groups
+// from the ESTIMATED batch start -- in the speculation phase, off the hand-off path of time-sliced runs.
+// startS [2][ngroups][C]: the phase at which the chain enters every group; specS [C][2]: first wrap, end, margin.
+__global__ void __launch_bounds__(32)
+k_carr_slice(const gpsiq_chan_desc* __restrict__ desc, const CarrSpec* __restrict__ specE,
+             const CarrSpec* __restrict__ specG, const TieEvent* __restrict__ tieG, const double* __restrict__ est_epoch,
+             double* __restrict__ startS, CarrSpec* __restrict__ specS, TieEvent* __restrict__ tieS, int E, int C, int N) {
+    __shared__ GroupEpoch s_ge[GROUP_EPOCHS];
+    const int lane = threadIdx.x;
+    const int V = blockIdx.x & 1, c = blockIdx.x >> 1;
+    if (c >= C) return;
+    const int ngroups = (E + GROUP_EPOCHS - 1) / GROUP_EPOCHS;
+    double x = est_epoch[c];
+    GroupTrack tr;
+    tr.margin = 1.0; tr.xw1 = 0.0; tr.pos = -1; tr.usable = 1; tr.tie.pos = -1; tr.tie.k = 0;
+    int any_active = 0;
+    for (int g = 0; g < ngroups && tr.usable; g++) {
+        const int first = g * GROUP_EPOCHS, count = min(GROUP_EPOCHS, E - first);
+        const CarrSpec sG0 = specG[((size_t) g * C + c) * 2], sG1 = specG[((size_t) g * C + c) * 2 + 1];
+        const TieEvent tG0 = tieG[((size_t) g * C + c) * 2], tG1 = tieG[((size_t) g * C + c) * 2 + 1];
+        if (lane == 0) startS[((size_t) V * ngroups + g) * C + c] = x;
+        stage_group(s_ge, desc, specE, first, 1, c, C, lane);       // fast path: the group's first epoch wraps
+        int r = 0;
+        if (lane == 0) r = slice_chain_group(x, s_ge, 1, N, sG0, sG1, tG0, tG1, tr, V, first, g, 0);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        any_active |= __shfl_sync(0xffffffffu, s_ge[0].active, 0);
+        if (r == 0 && count > 1) {                                   // it did not: the rest of the group, epoch by epoch
+            __syncwarp();
+            stage_group(s_ge, desc, specE, first, count, c, C, lane);
+            for (int k = 1; k < count; k++) any_active |= s_ge[k].active;
+            if (lane == 0) r = slice_chain_group(x, s_ge + 1, count - 1, N, sG0, sG1, tG0, tG1, tr, V, first, g, 1);
+            r = __shfl_sync(0xffffffffu, r, 0);
+        }
+        if (r < 0) tr.usable = 0;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        CarrSpec out;
+        out.xw1 = tr.xw1; out.xend = x; out.n1 = tr.pos; out.pad = any_active ? 0 : 1;
+        out.margin = (tr.pos >= 0 && tr.usable) ? tr.margin : -1.0;
+        specS[(size_t) c * 2 + V] = out;
+        tieS[(size_t) c * 2 + V] = tr.tie;
+    }
+}
+
+// Levels 5 + 4: the exact chain of a batch, one warp per slot.  With a usable slice-level speculation: ONE head scan
+// (up to the batch's first wrap) + a translation, and k_carr_final_groups then chains the groups in parallel.  Otherwise
+// serial over the groups: one head scan per group.  start_out / end_out: the exact phases before / after the batch.
 __global__ void __launch_bounds__(32)
 k_carr_final(const gpsiq_chan_desc* __restrict__ desc,
              const CarrSpec* __restrict__ specE, const CarrSpec* __restrict__ specG, double* __restrict__ carr_ck,
              size_t ck_plane, CarrInfo* __restrict__ infoG, size_t info_plane, const double* __restrict__ traceG,
              double* __restrict__ carr_state, double* __restrict__ carr_trace, GroupInfo* __restrict__ ginfo,
-             int* __restrict__ fallbacks, int E, int C, int N, int T, int ntiles) {
+             int* __restrict__ fallbacks, const TieEvent* __restrict__ tieG, const CarrSpec* __restrict__ specS,
+             const TieEvent* __restrict__ tieS, SliceRes* __restrict__ sres, unsigned long long* __restrict__ slice_stats,
+             double* __restrict__ start_out, double* __restrict__ end_out, double* __restrict__ est_out,
+             int E, int C, int N, int T, int ntiles) {
     __shared__ GroupEpoch s_ge[GROUP_EPOCHS];
     const int c = blockIdx.x, lane = threadIdx.x;
     if (c >= C) return;
     const int ngroups = (E + GROUP_EPOCHS - 1) / GROUP_EPOCHS;
     double x = carr_state[c];
-    int fb = 0;
-    for (int g = 0; g < ngroups; g++) {
-        const int first = g * GROUP_EPOCHS, count = min(GROUP_EPOCHS, E - first);
-        const size_t o = (size_t) first * C + c;
-        const CarrSpec sG0 = specG[((size_t) g * C + c) * 2], sG1 = specG[((size_t) g * C + c) * 2 + 1];
-        double* ckX = carr_ck + 6 * ck_plane + (size_t) first * ntiles * C + c;
-        // Fast path (almost always taken): the group's first epoch is active, wraps, and the group trajectory
-        // fits from there.  Only that epoch's inputs are staged; the serial work is its head scan, and the
-        // lanes translate the post-epoch phases of the other epochs in parallel.
-        stage_group(s_ge, desc, specE, first, 1, c, C, lane);
-        const double x_start = x;
-        GroupInfo gi;
-        gi.delta = 0.0; gi.pos = 0x7fffffff; gi.variant = 0;
-        int fb_try = 0;
-        if (lane == 0)
-            x = group_final(x_start, s_ge, 1, N, T, sG0, sG1, ckX, (size_t) C, (size_t) ntiles * C, infoG + 2 * info_plane + o,
-                            (size_t) C, traceG + o, traceG + info_plane + o, carr_trace + o, (size_t) C, gi, fb_try);
-        const int pos = __shfl_sync(0xffffffffu, gi.pos, 0);
-        if (pos < N) {  // translated inside the first epoch
-            const double diff = __shfl_sync(0xffffffffu, gi.delta, 0);
-            const int v = __shfl_sync(0xffffffffu, gi.variant, 0);
-            const double* tg = traceG + (v ? info_plane : 0) + o;
-            for (int e2 = 1 + lane; e2 < count; e2 += 32) carr_trace[o + (size_t) e2 * C] = add_rn(tg[(size_t) e2 * C], diff);
-        } else {        // anything else: the general chain over the whole group, from the group's start state
-            stage_group(s_ge, desc, specE, first, count, c, C, lane);
-            if (lane == 0)
-                x = group_final(x_start, s_ge, count, N, T, sG0, sG1, ckX, (size_t) C, (size_t) ntiles * C,
-                                infoG + 2 * info_plane + o, (size_t) C, traceG + o, traceG + info_plane + o, carr_trace + o,
-                                (size_t) C, gi, fb);
+    if (lane == 0) start_out[c] = x;
+    SliceRes res;
+    res.diff = 0.0; res.diff2 = 0.0; res.variant = 0; res.how = 0; res.tie_g = 0x7fffffff; res.pad = 0;
+    if (specS) {
+        const CarrSpec sS0 = specS[(size_t) c * 2], sS1 = specS[(size_t) c * 2 + 1];
+        const TieEvent tS0 = tieS[(size_t) c * 2], tS1 = tieS[(size_t) c * 2 + 1];
+        if (sS0.pad == 1) {
+            res.how = 2;                                            // nothing to chain: the phase passes through
+        } else if (sS0.margin > 0.0) {
+            const int count = min(GROUP_EPOCHS, E);
+            stage_group(s_ge, desc, specE, 0, 1, c, C, lane);
+            int r = 0;
+            if (lane == 0) r = slice_verify(x, s_ge, 1, N, sS0, sS1, tS0, tS1, res.variant, res.diff, res.diff2, 0);
+            r = __shfl_sync(0xffffffffu, r, 0);
+            if (r == 0 && count > 1) {                              // no wrap in the first epoch: on through the first group
+                __syncwarp();
+                stage_group(s_ge, desc, specE, 0, count, c, C, lane);
+                if (lane == 0) r = slice_verify(x, s_ge + 1, count - 1, N, sS0, sS1, tS0, tS1, res.variant, res.diff, res.diff2, 1);
+                r = __shfl_sync(0xffffffffu, r, 0);
+            }
+            if (r == 1) { res.how = 1; const TieEvent& tv = res.variant ? tS1 : tS0; if (tv.pos >= 0) res.tie_g = tv.pos; }
+            else x = carr_state[c];                                 // (slice_verify leaves x advanced over the head on failure)
+            __syncwarp();
         }
-        if (lane == 0) ginfo[(size_t) g * C + c] = gi;
-        __syncwarp();
+    }
+    int fb = 0;
+    if (res.how == 0) {
+        for (int g = 0; g < ngroups; g++)
+            x = final_group_warp(s_ge, x, g, desc, specE, specG, tieG, carr_ck, ck_plane, infoG, info_plane, traceG, carr_trace,
+                                 ginfo, fb, E, C, c, N, T, ntiles, lane);
     }
     if (lane == 0) {
+        if (sres) sres[c] = res;
+        if (slice_stats && res.how != 2) atomicAdd(slice_stats + (res.how == 1 ? 0 : 1), 1ULL);
         carr_state[c] = x;
+        end_out[c] = x;
+        if (est_out) est_out[c] = x;
+        if (fb) atomicAdd(fallbacks, fb);
+    }
+}
+
+// Level 4 for the slots k_carr_final passed by translation: every group's exact start phase is known (the slice-level
+// trajectory's phase at the group start + the translation), so the groups are chained in PARALLEL, one warp per
+// (group, slot) -- after the hand-off of the end phases, not in front of it.  Writes exactly what the serial chain
+// writes (exact plane, per-epoch results, post-epoch phases, GroupInfo) and checks that every group ends where the
+// next one starts: a disagreement is an internal error, reported through the context's error word.
+__global__ void __launch_bounds__(32)
+k_carr_final_groups(const gpsiq_chan_desc* __restrict__ desc,
+                    const CarrSpec* __restrict__ specE, const CarrSpec* __restrict__ specG, double* __restrict__ carr_ck,
+                    size_t ck_plane, CarrInfo* __restrict__ infoG, size_t info_plane, const double* __restrict__ traceG,
+                    double* __restrict__ carr_trace, GroupInfo* __restrict__ ginfo, int* __restrict__ fallbacks,
+                    const TieEvent* __restrict__ tieG, const double* __restrict__ startS, const SliceRes* __restrict__ sres, const double* __restrict__ start,
+                    const double* __restrict__ end, int* __restrict__ err, int E, int C, int N, int T, int ntiles) {
+    __shared__ GroupEpoch s_ge[GROUP_EPOCHS];
+    const int lane = threadIdx.x;
+    const int ngroups = (E + GROUP_EPOCHS - 1) / GROUP_EPOCHS;
+    const int g = blockIdx.x / C, c = blockIdx.x - g * C;
+    if (g >= ngroups) return;
+    const SliceRes res = sres[c];
+    if (res.how == 0) return;                                       // chained serially by k_carr_final
+    const double* sS = startS + (size_t) res.variant * ngroups * C + c;
+    // the slice-level first wrap lies inside group 0 (slice_chain_group), so every later group start is translatable
+    // (the groups after the one holding the trajectory's tie event start from the second translation: TieEvent)
+    const double x_start = (g == 0 || res.how == 2) ? start[c] : add_rn(sS[(size_t) g * C], g > res.tie_g ? res.diff2 : res.diff);
+    int fb = 0;
+    const double x = final_group_warp(s_ge, x_start, g, desc, specE, specG, tieG, carr_ck, ck_plane, infoG, info_plane, traceG,
+                                      carr_trace, ginfo, fb, E, C, c, N, T, ntiles, lane);
+    if (lane == 0) {
+        const double want = (g + 1 < ngroups) ? (res.how == 2 ? start[c] : add_rn(sS[(size_t) (g + 1) * C], g + 1 > res.tie_g ? res.diff2 : res.diff))
+                                              : end[c];
+        if (x != want) atomicOr(err, GPSIQ_DEVERR_SLICE);
         if (fb) atomicAdd(fallbacks, fb);
     }
 }
@@ -819,6 +973,8 @@ static void use_set(gpsiq_ctx* ctx, int i) {
     ctx->d_wrap_ck = ss.d_wrap_ck; ctx->d_carr_ck = ss.d_carr_ck; ctx->d_drift = ss.d_drift;
     ctx->d_spec = ss.d_spec; ctx->d_specE = ss.d_specE; ctx->d_cinfo = ss.d_cinfo; ctx->d_info = ss.d_info;
     ctx->d_specG = ss.d_specG; ctx->d_ginfo = ss.d_ginfo; ctx->d_traceG = ss.d_traceG;
+    ctx->d_specS = ss.d_specS; ctx->d_startS = ss.d_startS; ctx->d_sres = ss.d_sres; ctx->d_start0 = ss.d_start0;
+    ctx->d_tieG = ss.d_tieG; ctx->d_tieS = ss.d_tieS;
     ctx->d_adv = ss.d_adv; ctx->d_carr_trace = ss.d_carr_trace; ctx->d_ustart = ss.d_ustart;
     ctx->d_lrecs = ss.d_lrecs; ctx->d_elist = ss.d_elist; ctx->d_hazlist = ss.d_hazlist;
     ctx->d_line_counters = ss.d_line_counters; ctx->d_patches = ss.d_patches;
@@ -878,8 +1034,11 @@ int gpsiq_nco_advance(int mode, double* phase, double step, int64_t count, int64
     return GPSIQ_OK;
 }
 
-int gpsiq_carrier_chain_host(const double* steps, int n_epochs, int N, int T, double x0, double est_err, double* ck_out,
-                             double* x_end_out, int* n_fallback) {
+// use_slice: chain through level 5 as the device does (slice-level speculation from the estimated start, one exact head
+// scan, the groups chained independently from their translated start phases).  how_out: 1 translated, 0 serial,
+// -2 = the groups' ends disagreed with the translation (an internal error: must never happen).
+static int carrier_chain_host_impl(const double* steps, int n_epochs, int N, int T, double x0, double est_err, double* ck_out,
+                                   double* x_end_out, int* n_fallback, int use_slice, int* how_out, int* ties_out) {
     if (!steps || !ck_out || n_epochs < 1 || N < 1 || T < 1) return GPSIQ_ERR_ARG;
     const int ntiles = (N + T - 1) / T;
     const int G = (ntiles + 7) / 8, J = (ntiles + G - 1) / G;
@@ -929,23 +1088,79 @@ int gpsiq_carrier_chain_host(const double* steps, int n_epochs, int N, int T, do
         t2 -= floor(t2);
         xe = (t2 >= 0.0 && t2 < 1.0) ? t2 : 0.0;
     }
-    // levels 3 + 4 per group
-    double x = x0;
+    // level 3 per group
+    const int ngroups = (E + GP - 1) / GP;
+    CarrSpec* sGall = (CarrSpec*) malloc(sizeof(CarrSpec) * 2 * ngroups);
+    double* startS = (double*) malloc(sizeof(double) * 2 * ngroups);
+    TieEvent* tGall = (TieEvent*) malloc(sizeof(TieEvent) * 2 * ngroups);
+    if (!sGall || !startS || !tGall) return GPSIQ_ERR_NOMEM;
+    int ties_seen = 0, ties_applied = 0;
     for (int first = 0; first < E; first += GP) {
         const int count = (E - first < GP) ? E - first : GP;
-        CarrSpec sG[2];
+        CarrSpec* sG = sGall + 2 * (first / GP);
         bool any_neg = false;
         for (int k = 0; k < count; k++) any_neg |= ge[first + k].d < 0.0;
         for (int V = 0; V < 2; V++) {
             sG[V].margin = -1.0; sG[V].n1 = -1; sG[V].xw1 = 0; sG[V].xend = 0; sG[V].pad = 0;
+            TieEvent& tG = tGall[2 * (first / GP) + V];
+            tG.pos = -1; tG.k = 0;
             if (V == 1 && !any_neg) continue;
             group_chain(est[first], ge + first, count, N, T, V, planes + ep * first + (size_t) (4 + V) * ntiles, 1, ep,
-                        infG + (size_t) V * E + first, 1, trace + (size_t) V * E + first, 1, sG[V], fb);
+                        infG + (size_t) V * E + first, 1, trace + (size_t) V * E + first, 1, sG[V], tG, fb);
+            if (tG.pos >= 0 && sG[V].margin > 0.0) ties_seen++;
+        }
+    }
+    // level 5: slice-level speculation from the estimated start, then the exact head scan
+    int how = 0, vS = 0, tie_g = 0x7fffffff;
+    double diffS = 0.0, diffS2 = 0.0, x_end_slice = 0.0;
+    if (use_slice) {
+        CarrSpec sS[2];
+        TieEvent tS[2];
+        for (int V = 0; V < 2; V++) {
+            GroupTrack tr;
+            tr.margin = 1.0; tr.xw1 = 0.0; tr.pos = -1; tr.usable = 1; tr.tie.pos = -1; tr.tie.k = 0;
+            double xs = est[0];
+            for (int g = 0; g < ngroups && tr.usable; g++) {
+                const int first = g * GP, count = (E - first < GP) ? E - first : GP;
+                startS[V * ngroups + g] = xs;
+                // as the device does it: the group's first epoch alone, then the rest
+                int r = slice_chain_group(xs, ge + first, 1, N, sGall[2 * g], sGall[2 * g + 1], tGall[2 * g], tGall[2 * g + 1],
+                                          tr, V, first, g, 0);
+                if (r == 0 && count > 1)
+                    r = slice_chain_group(xs, ge + first + 1, count - 1, N, sGall[2 * g], sGall[2 * g + 1], tGall[2 * g],
+                                          tGall[2 * g + 1], tr, V, first, g, 1);
+                if (r < 0) tr.usable = 0;
+            }
+            sS[V].xw1 = tr.xw1; sS[V].xend = xs; sS[V].n1 = tr.pos; sS[V].pad = 0;
+            sS[V].margin = (tr.pos >= 0 && tr.usable) ? tr.margin : -1.0;
+            tS[V] = tr.tie;
+        }
+        double xv = x0;
+        const int count0 = (E < GP) ? E : GP;
+        int r = slice_verify(xv, ge, 1, N, sS[0], sS[1], tS[0], tS[1], vS, diffS, diffS2, 0);
+        if (r == 0 && count0 > 1) r = slice_verify(xv, ge + 1, count0 - 1, N, sS[0], sS[1], tS[0], tS[1], vS, diffS, diffS2, 1);
+        if (r == 1) {
+            how = 1; x_end_slice = xv;
+            if (tS[vS].pos >= 0) tie_g = tS[vS].pos;
+            if (diffS2 != diffS) ties_applied += 1000;
+        }
+    }
+    // level 4 per group: serially, or -- after a slice-level match -- every group from its own translated start phase
+    double x = x0;
+    for (int first = 0; first < E; first += GP) {
+        const int count = (E - first < GP) ? E - first : GP;
+        const CarrSpec* sG = sGall + 2 * (first / GP);
+        const TieEvent* tG = tGall + 2 * (first / GP);
+        if (how == 1 && first > 0) {
+            const double xs = add_rn(startS[vS * ngroups + first / GP], first / GP > tie_g ? diffS2 : diffS);
+            if (xs != x) how = -2;     // the previous group did not end where the translation says this one starts
+            x = xs;
         }
         GroupInfo gi;
         x = group_final(x, ge + first, count, N, T, sG[0], sG[1], planes + ep * first + (size_t) 6 * ntiles, 1, ep,
                         infG + (size_t) 2 * E + first, 1, trace + first, trace + (size_t) E + first,
-                        trace + (size_t) 2 * E + first, 1, gi, fb);
+                        trace + (size_t) 2 * E + first, 1, gi, fb, tG[0], tG[1]);
+        if (gi.pos != 0x7fffffff && gi.delta2 != gi.delta) ties_applied++;
         for (int k = 0; k < count; k++) {
             const int e = first + k;
             for (int t = 0; t < ntiles; t++)
@@ -954,10 +1169,23 @@ int gpsiq_carrier_chain_host(const double* steps, int n_epochs, int N, int T, do
                                                                   ci + (size_t) e * 2 * J, cs_all + (size_t) e * 2 * SPEC_MAX_CHUNKS);
         }
     }
-    free(planes); free(ge); free(ci); free(infG); free(trace); free(est); free(cs_all);
+    if (how == 1 && x != x_end_slice) how = -2;
+    free(planes); free(ge); free(ci); free(infG); free(trace); free(est); free(cs_all); free(sGall); free(startS); free(tGall);
     if (x_end_out) *x_end_out = x;
     if (n_fallback) *n_fallback = fb;
+    if (how_out) *how_out = how;
+    if (ties_out) { ties_out[0] = ties_seen; ties_out[1] = ties_applied; }
     return GPSIQ_OK;
+}
+
+int gpsiq_carrier_chain_host(const double* steps, int n_epochs, int N, int T, double x0, double est_err, double* ck_out,
+                             double* x_end_out, int* n_fallback) {
+    return carrier_chain_host_impl(steps, n_epochs, N, T, x0, est_err, ck_out, x_end_out, n_fallback, 0, NULL, NULL);
+}
+
+int gpsiq_carrier_slice_host(const double* steps, int n_epochs, int N, int T, double x0, double est_err, double* ck_out,
+                             double* x_end_out, int* n_fallback, int* how_out, int* ties_out) {
+    return carrier_chain_host_impl(steps, n_epochs, N, T, x0, est_err, ck_out, x_end_out, n_fallback, 1, how_out, ties_out);
 }
 
 void* gpsiq_host_alloc(size_t bytes) {
@@ -1022,6 +1250,7 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
         ctx->G = (ctx->ntiles + chunks - 1) / chunks;
     }
     ctx->J = (ctx->ntiles + ctx->G - 1) / ctx->G;
+    ctx->slice_spec = !(getenv("GPSIQ_SLICE_SPEC") && atoi(getenv("GPSIQ_SLICE_SPEC")) == 0);
     for (int i = 0; i < NSETS; i++) {
         ScanSet& ss = ctx->sets[i];
         CU(cudaMalloc(&ss.d_descbuf, EC * sizeof(gpsiq_chan_desc)));
@@ -1042,6 +1271,13 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
             CU(cudaMalloc(&ss.d_specG, ng * ctx->C * 2 * sizeof(CarrSpec)));
             CU(cudaMalloc(&ss.d_ginfo, ng * ctx->C * sizeof(GroupInfo)));
             CU(cudaMalloc(&ss.d_traceG, 2 * EC * sizeof(double)));
+            CU(cudaMalloc(&ss.d_specS, (size_t) ctx->C * 2 * sizeof(CarrSpec)));
+            CU(cudaMalloc(&ss.d_startS, 2 * ng * ctx->C * sizeof(double)));
+            CU(cudaMalloc(&ss.d_sres, (size_t) ctx->C * sizeof(SliceRes)));
+            CU(cudaMemset(ss.d_sres, 0, (size_t) ctx->C * sizeof(SliceRes)));
+            CU(cudaMalloc(&ss.d_start0, ctx->C * sizeof(double)));
+            CU(cudaMalloc(&ss.d_tieG, ng * ctx->C * 2 * sizeof(TieEvent)));
+            CU(cudaMalloc(&ss.d_tieS, (size_t) ctx->C * 2 * sizeof(TieEvent)));
         }
         CU(cudaMalloc(&ss.d_adv, 2 * ctx->C * sizeof(double)));
         CU(cudaMalloc(&ss.d_carr_trace, EC * sizeof(double)));
@@ -1071,6 +1307,8 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
     }
     CU(cudaMalloc(&ctx->d_fallbacks, sizeof(int)));
     CU(cudaMemset(ctx->d_fallbacks, 0, sizeof(int)));
+    CU(cudaMalloc(&ctx->d_slice_stats, 2 * sizeof(unsigned long long)));
+    CU(cudaMemset(ctx->d_slice_stats, 0, 2 * sizeof(unsigned long long)));
     CU(cudaMalloc(&ctx->d_carr_state, ctx->C * sizeof(double)));
     CU(cudaMalloc(&ctx->d_est_state, ctx->C * sizeof(double)));
     CU(cudaMemset(ctx->d_est_state, 0, ctx->C * sizeof(double)));
@@ -1101,7 +1339,7 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
         // to leave.  No scan kernel keeps per-thread tables any more (nco_scan.cuh: binade_delta), so EVERY kernel
         // of the pipeline asks for this split and any of them can be placed beside the sample kernel.
 #define CARVE(k) CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared))
-        CARVE(k_synth_line); CARVE(k_carr_stitch); CARVE(k_carr_group); CARVE(k_carr_final); CARVE(k_line_apply);
+        CARVE(k_synth_line); CARVE(k_carr_stitch); CARVE(k_carr_group); CARVE(k_carr_final); CARVE(k_carr_slice); CARVE(k_carr_final_groups); CARVE(k_line_apply);
         CARVE(k_synth_lanes);
         CARVE(k_carr_speculate); CARVE(k_scan_code); CARVE(k_prepare); CARVE(k_line_anchor); CARVE(k_line_patch);
         CARVE(k_epoch_estimates); CARVE(k_slice_advance); CARVE(k_est_fold); CARVE(k_est_correct); CARVE(k_int_carrier);
@@ -1207,6 +1445,8 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
         cudaFree(ss.d_wrap_ck); cudaFree(ss.d_carr_ck); cudaFree(ss.d_drift); cudaFree(ss.d_spec);
         cudaFree(ss.d_specE); cudaFree(ss.d_cinfo); cudaFree(ss.d_info); cudaFree(ss.d_adv); cudaFree(ss.d_carr_trace);
         cudaFree(ss.d_specG); cudaFree(ss.d_ginfo); cudaFree(ss.d_traceG); cudaFree(ss.d_ustart);
+        cudaFree(ss.d_specS); cudaFree(ss.d_startS); cudaFree(ss.d_sres); cudaFree(ss.d_start0);
+        cudaFree(ss.d_tieG); cudaFree(ss.d_tieS);
         if (ss.scan_done) cudaEventDestroy(ss.scan_done);
         if (ss.render_done) cudaEventDestroy(ss.render_done);
         if (ss.spec_done) cudaEventDestroy(ss.spec_done);
@@ -1226,7 +1466,7 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
     if (ctx->d_mbox_peer) cudaIpcCloseMemHandle(ctx->d_mbox_peer);
     cudaFree(ctx->d_mbox);
     cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_est_state); cudaFree(ctx->d_ca);
-    cudaFree(ctx->d_iq); cudaFree(ctx->d_iq2); cudaFree(ctx->d_sums); cudaFree(ctx->d_err);
+    cudaFree(ctx->d_iq); cudaFree(ctx->d_iq2); cudaFree(ctx->d_sums); cudaFree(ctx->d_err); cudaFree(ctx->d_slice_stats);
 #define DROP_STREAM(s) do { if (s) cudaStreamDestroy(s); } while (0)
 #define DROP_EVENT(e) do { if (e) cudaEventDestroy(e); } while (0)
     DROP_STREAM(ctx->scan_stream); DROP_STREAM(ctx->aux2_stream); DROP_EVENT(ctx->ev_fork2); DROP_EVENT(ctx->ev_code2);
@@ -1340,10 +1580,16 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
             const int ngroups = (n_epochs + GROUP_EPOCHS - 1) / GROUP_EPOCHS;
             k_carr_group<<<ngroups * C * 2, 32, 0, st>>>(desc_dev, ctx->d_specE, est_epoch,
                                                                    ctx->d_carr_ck, ctx->ck_plane, ctx->d_info, ECmax,
-                                                                   ctx->d_traceG, ctx->d_specG, ctx->d_fallbacks, n_epochs,
-                                                                   C, N, T, ntiles);
+                                                                   ctx->d_traceG, ctx->d_specG, ctx->d_tieG, ctx->d_fallbacks,
+                                                                   n_epochs, C, N, T, ntiles);
         }
         trace_mark(ctx, st, "k_carr_group");
+        if (ctx->slice_spec) {
+            k_carr_slice<<<C * 2, 32, 0, st>>>(desc_dev, ctx->d_specE, ctx->d_specG, ctx->d_tieG, est_epoch, ctx->d_startS,
+                                               ctx->d_specS, ctx->d_tieS, n_epochs, C, N);
+            trace_mark(ctx, st, "k_carr_slice");
+            ctx->launches += 1;
+        }
         if (!own_est) { k_est_fold<<<1, 32, 0, st>>>(ctx->d_est_state, ctx->d_adv, C); ctx->launches += 1; }
         ctx->launches += 4;
     }
@@ -1362,15 +1608,20 @@ static int enqueue_chain(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_
     const int C = ctx->C, N = ctx->N, T = ctx->T, ntiles = ctx->ntiles;
     if (ctx->sets[ctx->set_wr].phase != 2) return fail(ctx, GPSIQ_ERR_ARG, "chain: the next batch in line has not been speculated", cudaSuccess);
     use_set(ctx, ctx->set_wr);
+    ScanSet& wset = ctx->sets[ctx->set_wr];
+    bool float_chain = false;
     CU(cudaStreamWaitEvent(st, ctx->sets[ctx->set_wr].spec_all, 0));  // (a no-op when the speculation ran on this stream)
     CU(cudaStreamWaitEvent(st, ctx->ev_final, 0));  // the carrier state: after the previous batch's chain, whatever its stream
     if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_FLOAT && ctx->cfg.reserved[0] == 0) {
-        CU(cudaMemcpyAsync(ctx->d_carr_start, ctx->d_carr_state, C * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        // one kernel on the path of the hand-off: it also leaves the batch's exact start / end phases in the set (and
+        // re-anchors the estimate), so that nothing else has to be enqueued between the chain and the caller's send
         k_carr_final<<<C, 32, 0, st>>>(desc_dev, ctx->d_specE, ctx->d_specG, ctx->d_carr_ck, ctx->ck_plane,
                                        ctx->d_info, (size_t) ctx->E * C, ctx->d_traceG, ctx->d_carr_state, ctx->d_carr_trace,
-                                       ctx->d_ginfo, ctx->d_fallbacks, n_epochs, C, N, T, ntiles);
-        k_bias_update<<<1, 32, 0, st>>>(ctx->d_adv, ctx->d_carr_start, ctx->d_carr_state, ctx->d_bias_rate, n_epochs, C);
-        ctx->launches += 1;
+                                       ctx->d_ginfo, ctx->d_fallbacks, ctx->d_tieG, ctx->slice_spec ? ctx->d_specS : NULL,
+                                       ctx->d_tieS, ctx->d_sres, ctx->d_slice_stats,
+                                       ctx->d_start0, wset.d_exact_end, ctx->chain_keeps_estimate ? NULL : ctx->d_est_state,
+                                       n_epochs, C, N, T, ntiles);
+        float_chain = true;
     } else if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_INT32) {  // closed form: one prefix sum over the epochs
         k_int_carrier<<<C, 32, 0, st>>>(desc_dev, ctx->d_ustart, ctx->d_carr_state, ctx->d_carr_trace, NULL, 0, n_epochs, C, N);
     } else {  // the serial float scan (cfg.reserved[0] = 1, cross-check)
@@ -1380,13 +1631,35 @@ static int enqueue_chain(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_
     }
     ctx->launches += 1;
     trace_mark(ctx, st, "k_carr_final");
-    if (!ctx->chain_keeps_estimate)  // re-anchor the estimate on the exact phase (single-stream use)
-        CU(cudaMemcpyAsync(ctx->d_est_state, ctx->d_carr_state, C * sizeof(double), cudaMemcpyDeviceToDevice, st));
     ScanSet& set = ctx->sets[ctx->set_wr];
-    CU(cudaMemcpyAsync(set.d_exact_end, ctx->d_carr_state, C * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (!float_chain) {
+        if (!ctx->chain_keeps_estimate)  // re-anchor the estimate on the exact phase (single-stream use)
+            CU(cudaMemcpyAsync(ctx->d_est_state, ctx->d_carr_state, C * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(set.d_exact_end, ctx->d_carr_state, C * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
     CU(cudaEventRecord(ctx->ev_final, st));
-    if (!ctx->use_line) CU(cudaStreamWaitEvent(st, ctx->ev_code2, 0));  // scan_done covers the code scan on the side stream too
-    CU(cudaEventRecord(set.scan_done, st));
+    // everything below is off the hand-off path: on the set's own stream (time-sliced runs: the caller's next
+    // operation on `st` is the send of the end phases)
+    cudaStream_t st2 = (ctx->use_line || float_chain) ? set.stream : st;
+    if (st2 != st) {
+        CU(cudaEventRecord(ctx->ev_chain, st));
+        CU(cudaStreamWaitEvent(st2, ctx->ev_chain, 0));
+    }
+    if (float_chain) {
+        if (ctx->slice_spec) {
+            const int ngroups = (n_epochs + GROUP_EPOCHS - 1) / GROUP_EPOCHS;
+            k_carr_final_groups<<<ngroups * C, 32, 0, st2>>>(desc_dev, ctx->d_specE, ctx->d_specG, ctx->d_carr_ck, ctx->ck_plane,
+                                                            ctx->d_info, (size_t) ctx->E * C, ctx->d_traceG, ctx->d_carr_trace,
+                                                            ctx->d_ginfo, ctx->d_fallbacks, ctx->d_tieG, ctx->d_startS, ctx->d_sres,
+                                                            ctx->d_start0, set.d_exact_end, ctx->d_err, n_epochs, C, N, T, ntiles);
+            trace_mark(ctx, st2, "k_carr_final_groups");
+            ctx->launches += 1;
+        }
+        k_bias_update<<<1, 32, 0, st2>>>(ctx->d_adv, ctx->d_start0, set.d_exact_end, ctx->d_bias_rate, n_epochs, C);
+        ctx->launches += 1;
+    }
+    if (!ctx->use_line) CU(cudaStreamWaitEvent(st2, ctx->ev_code2, 0));  // scan_done covers the code scan on the side stream too
+    CU(cudaEventRecord(set.scan_done, st2));   // (the batch's scan results are complete only now)
     set.phase = 3;
     ctx->set_wr = (ctx->set_wr + 1) % NSETS;
     ctx->set_pending++;
@@ -1395,7 +1668,7 @@ static int enqueue_chain(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_
     // the set's own stream -- long before the batch is rendered, and beside (not in front of) whatever the caller puts
     // on `st` next (in time-sliced runs: the hand-off of the exact phases to the next GPU).
     if (ctx->use_line) {
-        if (st != set.stream) CU(cudaStreamWaitEvent(set.stream, set.scan_done, 0));
+        if (st2 != set.stream) CU(cudaStreamWaitEvent(set.stream, set.scan_done, 0));
         return enqueue_anchor(ctx, set, set.stream, set.stream);
     }
     return GPSIQ_OK;
@@ -1567,6 +1840,12 @@ static int check_device_error(gpsiq_ctx* ctx) {
     CU(cudaStreamSynchronize(ctx->stream));
     if (h) {
         CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+        if (h & 0x70000000) {
+            snprintf(ctx->err, sizeof ctx->err, "internal device error 0x%x (%s)", h,
+                     (h & GPSIQ_DEVERR_SLICE) ? "the parallel group chain disagrees with the slice-level translation"
+                                              : "a table copy did not complete");
+            return GPSIQ_ERR_CUDA;
+        }
         snprintf(ctx->err, sizeof ctx->err, "descriptor %d (epoch*max_chan+slot) is out of contract", h - 1);
         return GPSIQ_ERR_ARG;
     }
@@ -2109,6 +2388,24 @@ int gpsiq_carrier_fallbacks(gpsiq_ctx* ctx, int64_t* count) {
     CU(cudaMemcpy(&h, ctx->d_fallbacks, sizeof h, cudaMemcpyDeviceToHost));
     *count = h;
     return GPSIQ_OK;
+}
+
+int gpsiq_slice_stats(gpsiq_ctx* ctx, int64_t* translated, int64_t* serial) {
+    if (!ctx || !translated || !serial) return GPSIQ_ERR_ARG;
+    unsigned long long h[2] = {0, 0};
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(h, ctx->d_slice_stats, sizeof h, cudaMemcpyDeviceToHost));
+    *translated = (int64_t) h[0];
+    *serial = (int64_t) h[1];
+    return GPSIQ_OK;
+}
+
+int gpsiq_device_status(gpsiq_ctx* ctx) {
+    if (!ctx) return GPSIQ_ERR_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaDeviceSynchronize());
+    return check_device_error(ctx);
 }
 
 int gpsiq_timing_begin(gpsiq_ctx* ctx) {

@@ -249,6 +249,25 @@ GPSIQ_HD double binade_margin(double r) {
     return m - pow2_of(e - 52);
 }
 
+// A positive step that is a multiple of 2^-53 ("tie-capable": 1 epoch in ~2^9) can produce exact ties in [1, 2), where
+// a translation by an ODD multiple of 2^-52 does not commute with round-to-nearest-even.  The chunk- and epoch-level
+// speculations leave such epochs out (carr_step_speculable); the chains of levels 3-5 scan them serially as part of
+// their own speculative trajectory and record the FIRST tie-wrap after the trajectory's first wrap: a true run that is
+// that trajectory + D follows it exactly up to the event, and from the event on is the trajectory + D + k * 2^-52 if
+// D is an odd multiple of 2^-52 (the two runs round the tie in opposite directions; the new shift is an even multiple,
+// which commutes with every later rounding, ties included), and + D throughout if D is an even multiple.
+struct TieEvent {
+    int pos;   // position (in the trajectory's own units) of the first sample whose state follows the tie-wrap; -1: none
+    int k;     // +1: the trajectory rounded the tie down (an odd-shifted run rounds up), -1: the other way round
+};
+// shift (translation) in force after the event, given the shift D before it
+GPSIQ_HD double tie_shift(double D, const TieEvent& t) {
+    if (t.pos < 0) return D;
+    const double q = D * 0x1p52;                                   // exact: D is a small multiple of 2^-52
+    const bool odd = ((long long) q) & 1;
+    return odd ? D + (double) t.k * 0x1p-52 : D;                   // exact
+}
+
 struct CarrSpec {   // result of one speculative epoch scan
     double xw1;     // state right after the first wrap of the run (sample index n1)
     double xend;    // state after the last sample of the epoch
@@ -262,12 +281,23 @@ struct CarrSpec {   // result of one speculative epoch scan
 // tie (if not null): set to 1 / 2 when a NEGATIVE wrap's y + 1.0 was an exact rounding tie on the 2^-53 grid and was
 // rounded down / up (to the even neighbour): the one event at which a run shifted by an odd multiple of 2^-53 stops
 // being an exact translate of this one (spec_derive_variant1).
+// ptie (if not null): set to +1 / -1 when a POSITIVE wrap's sum x + d was an exact rounding tie on the 2^-52 grid of
+// [1, 2) and was rounded down / up (to the even neighbour): the one event at which a run shifted by an ODD multiple of
+// 2^-52 stops being an exact translate of this one -- it rounds the other way, and from then on the shift is larger /
+// smaller by 2^-52 (even, so it commutes with every later rounding).  Needs d == 0 (mod 2^-53): see TieEvent.
 template <bool TRACK>
-GPSIQ_HD bool carr_step(double& x, double d, double& margin, int* tie = nullptr) {
+GPSIQ_HD bool carr_step(double& x, double d, double& margin, int* tie = nullptr, int* ptie = nullptr) {
     double y = add_rn(x, d);
     bool w = false;
     if (TRACK) { const double m = binade_margin(y); if (m < margin) margin = m; }
-    if (y >= 1.0) { y = add_rn(y, -1.0); w = true; }
+    if (y >= 1.0) {
+        if (TRACK && ptie) {
+            const double bb = add_rn(y, -x);                                   // TwoSum: y + t == x + d exactly
+            const double t = add_rn(add_rn(x, -add_rn(y, -bb)), add_rn(d, -bb));
+            if (t == 0x1p-53) *ptie = 1; else if (t == -0x1p-53) *ptie = -1;   // rounded down / up
+        }
+        y = add_rn(y, -1.0); w = true;
+    }
     else if (y < 0.0) {
         const double z = add_rn(y, 1.0);
         if (TRACK && tie) {
@@ -283,9 +313,11 @@ GPSIQ_HD bool carr_step(double& x, double d, double& margin, int* tie = nullptr)
 
 // Advance up to `count` carrier steps; with stop_at_wrap, return right after
 // the first step that wrapped.  Returns the number of steps taken.
+// pt (if not null, TRACK only): receives the first positive tie-wrap (TieEvent), its position = pos_base + the number of
+// steps taken up to and including the tying step.
 template <bool TRACK>
 GPSIQ_HD int carr_advance(double& x, double d, const StepInfo& tab, int count, bool stop_at_wrap, bool& wrapped,
-                          double& margin) {
+                          double& margin, TieEvent* pt = nullptr, int pos_base = 0) {
     const int count0 = count;
     wrapped = false;
     while (count > 0) {
@@ -299,8 +331,10 @@ GPSIQ_HD int carr_advance(double& x, double d, const StepInfo& tab, int count, b
             if (m < margin) margin = m;
         }
         if (count == 0) break;
-        const bool w = carr_step<TRACK>(x, d, margin);
+        int ptie = 0;
+        const bool w = carr_step<TRACK>(x, d, margin, nullptr, (TRACK && pt) ? &ptie : nullptr);
         count--;
+        if (TRACK && pt && ptie && pt->pos < 0) { pt->pos = pos_base + (count0 - count); pt->k = ptie; }
         if (w) { wrapped = true; if (stop_at_wrap) break; }
     }
     return count0 - count;
@@ -379,7 +413,13 @@ GPSIQ_HD double carr_drift_estimate(double d, const StepInfo& tab, int n) {
     return acc * (double) n;
 }
 
-// true if an epoch with this step may be speculated
+// true if a run with this step can be translated at all (levels 3-5; ties are handled through TieEvent)
+GPSIQ_HD bool carr_step_translatable(double d) {
+    const int64_t e = (f64_bits(d) & 0x7fffffffffffffffLL) >> 52;
+    return e != 0 && e < 1021;  // not zero/denormal, |d| < 0.25
+}
+
+// true if an epoch with this step may be speculated (levels 1-2)
 GPSIQ_HD bool carr_step_speculable(double d) {
     const int64_t b = f64_bits(d) & 0x7fffffffffffffffLL;
     const int64_t e = b >> 52;
@@ -619,13 +659,17 @@ struct GroupTrack {   // running state of a group-level speculative chain
     double xw1;       // state right after that wrap
     int pos;          // its position: (epoch index within the group) * N + sample; -1: none yet
     int usable;
+    TieEvent tie;     // first positive tie-wrap after pos (same units)
 };
 
 struct GroupInfo {    // per (group, channel): result of the final chain
     double delta;     // translation of the group trajectory onto the exact one
+    double delta2;    // the same from tie_pos on (TieEvent)
     int pos;          // tiles at or after this (epoch-in-group * N + sample) are translated; earlier ones
                       // read the exact plane.  0x7fffffff: the whole group was chained exactly (fallback)
     int variant;
+    int tie_pos;      // 0x7fffffff: none
+    int pad;
 };
 
 // Scan from x over the tiles of one epoch starting at tile t (remaining = samples left of a partially
@@ -633,13 +677,14 @@ struct GroupInfo {    // per (group, channel): result of the final chain
 // end.  TRACK: margin-track every decision.
 template <bool TRACK>
 GPSIQ_HD void scan_epoch_head(double& x, double d, const StepInfo& tab, int N, int T, double* ck, size_t ck_stride,
-                              int& t, int& n, int& remaining, bool& wrapped, bool stop_at_wrap, double& margin) {
+                              int& t, int& n, int& remaining, bool& wrapped, bool stop_at_wrap, double& margin,
+                              TieEvent* pt = nullptr, int pos_base = 0) {
     const int ntiles = (N + T - 1) / T;
     wrapped = false;
     for (;;) {
         while (remaining > 0 && !(wrapped && stop_at_wrap)) {
             bool w;
-            const int steps = carr_advance<TRACK>(x, d, tab, remaining, stop_at_wrap, w, margin);
+            const int steps = carr_advance<TRACK>(x, d, tab, remaining, stop_at_wrap, w, margin, pt, pos_base + n);
             remaining -= steps;
             n += steps;
             if (w) wrapped = true;
@@ -662,7 +707,7 @@ GPSIQ_HD double group_chain_epoch(double x, double d, const StepInfo& tab, int N
     int n = 0, t = 0, remaining = 0;
     bool wrapped = false;
     double dummy = 1.0;
-    if (SPEC && g->pos >= 0) scan_epoch_head<true>(x, d, tab, N, T, ck0, ck_stride, t, n, remaining, wrapped, true, g->margin);
+    if (SPEC && g->pos >= 0) scan_epoch_head<true>(x, d, tab, N, T, ck0, ck_stride, t, n, remaining, wrapped, true, g->margin, &g->tie, eg * N);
     else scan_epoch_head<false>(x, d, tab, N, T, ck0, ck_stride, t, n, remaining, wrapped, true, dummy);
     info.delta = 0.0;
     info.n1 = N;
@@ -690,7 +735,7 @@ GPSIQ_HD double group_chain_epoch(double x, double d, const StepInfo& tab, int N
     }
     // the epoch's speculation does not fit: finish the epoch with the exact scan
     fell_back++;
-    if (SPEC) scan_epoch_head<true>(x, d, tab, N, T, ck0, ck_stride, t, n, remaining, wrapped, false, g->margin);
+    if (SPEC) scan_epoch_head<true>(x, d, tab, N, T, ck0, ck_stride, t, n, remaining, wrapped, false, g->margin, &g->tie, eg * N);
     else scan_epoch_head<false>(x, d, tab, N, T, ck0, ck_stride, t, n, remaining, wrapped, false, dummy);
     return x;
 }
@@ -707,15 +752,15 @@ struct GroupEpoch {
 // outG.n1 holds the first-wrap position as (epoch-in-group * N + sample), count*N if the chain never wraps.
 GPSIQ_HD void group_chain(double x, const GroupEpoch* ge, int count, int N, int T, int V, double* ckHead,
                           size_t tile_stride, size_t epoch_stride, CarrInfo* info, size_t info_stride, double* trace,
-                          size_t trace_stride, CarrSpec& outG, int& fb) {
+                          size_t trace_stride, CarrSpec& outG, TieEvent& tieG, int& fb) {
     GroupTrack g;
-    g.margin = 1.0; g.xw1 = 0.0; g.pos = -1; g.usable = 1;
+    g.margin = 1.0; g.xw1 = 0.0; g.pos = -1; g.usable = 1; g.tie.pos = -1; g.tie.k = 0;
     for (int eg = 0; eg < count; eg++) {
         CarrInfo inf;
         inf.delta = 0.0; inf.n1 = N; inf.variant = 0;
         if (ge[eg].active) {
             if (ge[eg].reset) { g.usable = 0; x = ge[eg].phase0; }       // re-seeded inside the group: not translatable
-            if (!carr_step_speculable(ge[eg].d)) g.usable = 0;
+            if (!carr_step_translatable(ge[eg].d)) g.usable = 0;             // (a tie-capable step is scanned serially
             x = group_chain_epoch<true>(x, ge[eg].d, step_info(ge[eg].d), N, T, ge[eg].s0, ge[eg].s1,
                                         ckHead + (size_t) eg * epoch_stride, tile_stride, inf, fb, &g, V, eg);
         }
@@ -727,6 +772,7 @@ GPSIQ_HD void group_chain(double x, const GroupEpoch* ge, int count, int N, int 
     outG.margin = (g.pos >= 0 && g.usable) ? g.margin : -1.0;
     outG.n1 = g.pos < 0 ? count * N : g.pos;
     outG.pad = 0;
+    tieG = g.tie;
 }
 
 // Level 4: the final, exact chain over one group from the exact phase x: one head scan up to the group's
@@ -735,7 +781,7 @@ GPSIQ_HD void group_chain(double x, const GroupEpoch* ge, int count, int N, int 
 GPSIQ_HD double group_final(double x, const GroupEpoch* ge, int count, int N, int T, const CarrSpec& sG0,
                             const CarrSpec& sG1, double* ckX, size_t tile_stride, size_t epoch_stride, CarrInfo* infoX,
                             size_t info_stride, const double* traceG0, const double* traceG1, double* trace,
-                            size_t trace_stride, GroupInfo& gi, int& fb) {
+                            size_t trace_stride, GroupInfo& gi, int& fb, const TieEvent& tG0, const TieEvent& tG1) {
     double dummy = 1.0;
     CarrInfo all_exact;
     all_exact.delta = 0.0; all_exact.n1 = N; all_exact.variant = 0;
@@ -753,10 +799,15 @@ GPSIQ_HD double group_final(double x, const GroupEpoch* ge, int count, int N, in
         int v;
         double diff;
         if (spec_match(x, pos, ge[eg].d, sG0, sG1, v, diff)) {
-            gi.delta = diff; gi.pos = pos; gi.variant = v;
+            const TieEvent& tv = v ? tG1 : tG0;
+            const double diff2 = tie_shift(diff, tv);
+            gi.delta = diff; gi.delta2 = diff2; gi.pos = pos; gi.variant = v; gi.pad = 0;
+            gi.tie_pos = tv.pos < 0 ? 0x7fffffff : tv.pos;
             const double* tg = v ? traceG1 : traceG0;
-            for (int e2 = eg; e2 < count; e2++) trace[(size_t) e2 * trace_stride] = add_rn(tg[(size_t) e2 * trace_stride], diff);
-            return add_rn(v ? sG1.xend : sG0.xend, diff);
+            // the phase after epoch e2 follows the tie-wrap iff the event lies at or before that epoch's last step
+            for (int e2 = eg; e2 < count; e2++)
+                trace[(size_t) e2 * trace_stride] = add_rn(tg[(size_t) e2 * trace_stride], (gi.tie_pos <= (e2 + 1) * N) ? diff2 : diff);
+            return add_rn(v ? sG1.xend : sG0.xend, diff2);
         }
         // The group's speculation does not fit: chain this and the remaining epochs exactly, each through its
         // own epoch-level speculation (one head scan + translation per epoch; an epoch scans serially only if
@@ -773,11 +824,98 @@ GPSIQ_HD double group_final(double x, const GroupEpoch* ge, int count, int N, in
             infoX[(size_t) e2 * info_stride] = inf;
             trace[(size_t) e2 * trace_stride] = x;
         }
-        gi.delta = 0.0; gi.pos = 0x7fffffff; gi.variant = 0;
+        gi.delta = 0.0; gi.delta2 = 0.0; gi.pos = 0x7fffffff; gi.variant = 0; gi.tie_pos = 0x7fffffff; gi.pad = 0;
         return x;
     }
-    gi.delta = 0.0; gi.pos = count * N; gi.variant = 0;  // the group never wraps: every tile is in the exact plane
+    gi.delta = 0.0; gi.delta2 = 0.0; gi.pos = count * N; gi.variant = 0; gi.tie_pos = 0x7fffffff; gi.pad = 0;  // the group never wraps: every tile is in the exact plane
     return x;
+}
+
+// ---- fifth level: the whole batch ("slice") ---------------------------------------
+// In a time-sliced multi-GPU run the exact chain of a slice sits on the ring: the next GPU cannot chain before this
+// one has.  Level 4 costs one head scan per GROUP there (16 for a 1024-epoch slice).  The same step once more makes it
+// ONE head scan per slice: the groups are chained from the ESTIMATED slice start (slice_chain_group, in the speculation
+// phase, off the ring) into a slice-level speculative trajectory S' with its own first-wrap state and margin, recording
+// the phase at which S' enters every group.  On the ring, slice_verify scans from the exact start phase up to the
+// slice's first wrap only, matches it against S' and returns the exact end phase as xend' + D; the exact phase at the
+// start of every group is then start'_g + D -- all groups at once -- and level 4 (group_final) is run for all groups in
+// PARALLEL from those, after the hand-off, producing exactly what the serial chain would have produced.
+// A slice whose trajectory does not wrap inside its first group, re-seeds a slot, or has a group whose speculation does
+// not fit is not translatable (margin <= 0): it is chained serially, group by group, as before.
+
+// Part of one group of the speculative slice-level chain: epochs ge[0..count) = the group's epochs eg0, eg0+1, ...
+// x: phase of S' at the first sample of ge[0].  g: running state (GroupTrack.pos = slice-relative position of the
+// slice's first wrap, epoch * N + sample; -1: none yet; GroupTrack.tie.pos = index of the GROUP holding S' first
+// tie-wrap after that).  epoch0: index of the group's first epoch within the slice, gidx: index of the group.
+// sG0 / sG1, tG0 / tG1: the group's own speculation (level 3), both variants.
+// -> 1: the group's speculation was matched, x = phase of S' after the group's LAST sample;
+//    0: none of these epochs wrapped (all head), x = phase after ge[count-1];
+//   -1: the chain is not translatable from here on.
+GPSIQ_HD int slice_chain_group(double& x, const GroupEpoch* ge, int count, int N, const CarrSpec& sG0, const CarrSpec& sG1,
+                               const TieEvent& tG0, const TieEvent& tG1, GroupTrack& g, int V, int epoch0, int gidx, int eg0) {
+    for (int k = 0; k < count; k++) {
+        if (!ge[k].active) continue;
+        if (ge[k].reset) return -1;                                  // re-seeded inside the slice: not translatable
+        if (!carr_step_translatable(ge[k].d)) return -1;
+        const StepInfo si = step_info(ge[k].d);
+        bool wrapped = false;
+        double dummy = 1.0;
+        TieEvent th;
+        th.pos = -1; th.k = 0;
+        int n = 0;
+        while (n < N && !wrapped)
+            n += (g.pos >= 0) ? carr_advance<true>(x, ge[k].d, si, N - n, true, wrapped, g.margin, &th, 0)
+                              : carr_advance<false>(x, ge[k].d, si, N - n, true, wrapped, dummy);
+        if (th.pos >= 0 && g.tie.pos < 0) { g.tie.pos = gidx; g.tie.k = th.k; }   // (the wrap ending a head scan can tie)
+        if (!wrapped) continue;                                      // the whole epoch was part of the head
+        const int pos = (eg0 + k) * N + n;                           // group-relative, as group_chain records it
+        if (g.pos < 0) {                                             // the slice's first wrap
+            if (epoch0 != 0) return -1;                              // (it must lie inside the first group: slice_verify)
+            if (V == 1) x = (x + 0x1p-53 < 1.0) ? x + 0x1p-53 : x - 0x1p-53;
+            if (!(x >= 0.0 && x < 1.0)) return -1;
+            g.pos = pos;
+            g.xw1 = x;
+        }
+        int v;
+        double diff;
+        if (!spec_match(x, pos, ge[k].d, sG0, sG1, v, diff)) return -1;
+        const double m = (v ? sG1.margin : sG0.margin) - (diff < 0.0 ? -diff : diff);
+        if (m < g.margin) g.margin = m;
+        // S' = G' + diff up to G's first tie-wrap, G' + diff2 after it; S' itself rounds that tie like G' if diff is
+        // an even multiple of 2^-52 and the other way if it is odd
+        const TieEvent& tv = v ? tG1 : tG0;
+        const double diff2 = tie_shift(diff, tv);
+        if (tv.pos >= 0 && g.tie.pos < 0) { g.tie.pos = gidx; g.tie.k = (diff2 != diff) ? -tv.k : tv.k; }
+        x = add_rn(v ? sG1.xend : sG0.xend, diff2);
+        return 1;
+    }
+    return 0;
+}
+
+// Exact head scan of a slice from its exact start phase over epochs ge[0..count) = epochs eg0, eg0+1, ... of its FIRST
+// group, matched against the slice-level speculation (sS0 / sS1, tS0 / tS1: both variants).
+// -> 1: matched; v = variant, diff / diff2 = translation before / after the trajectory's tie event (TieEvent.pos = a
+//       GROUP index: the groups after it start from diff2), x = the exact phase after the slice's LAST sample;
+//    0: none of these epochs wrapped, x = the exact phase after ge[count-1];
+//   -1: no match (x is then somewhere inside the head: the caller restarts from the slice's start phase).
+GPSIQ_HD int slice_verify(double& x, const GroupEpoch* ge, int count, int N, const CarrSpec& sS0, const CarrSpec& sS1,
+                          const TieEvent& tS0, const TieEvent& tS1, int& v, double& diff, double& diff2, int eg0) {
+    if (!(sS0.margin > 0.0)) return -1;
+    double dummy = 1.0;
+    for (int k = 0; k < count; k++) {
+        if (!ge[k].active) continue;
+        if (ge[k].reset) return -1;
+        const StepInfo si = step_info(ge[k].d);
+        bool wrapped = false;
+        int n = 0;
+        while (n < N && !wrapped) n += carr_advance<false>(x, ge[k].d, si, N - n, true, wrapped, dummy);
+        if (!wrapped) continue;
+        if (!spec_match(x, (eg0 + k) * N + n, ge[k].d, sS0, sS1, v, diff)) return -1;
+        diff2 = tie_shift(diff, v ? tS1 : tS0);
+        x = add_rn(v ? sS1.xend : sS0.xend, diff2);
+        return 1;
+    }
+    return 0;
 }
 
 // Exact carrier phase at the start of tile t of epoch e (eg = its index within its group), composing the
@@ -813,7 +951,7 @@ GPSIQ_HD double carr_tile_phase(const double* ck, size_t plane, size_t stride, i
         }
         p = add_rn(p, inf.delta);
     }
-    return all_exact ? p : add_rn(p, gi.delta);
+    return all_exact ? p : add_rn(p, (eg * N + n0 >= gi.tie_pos) ? gi.delta2 : gi.delta);
 }
 
 // Everything a renderer needs to compose exact tile-start carrier phases (device pointers, one batch).

@@ -152,6 +152,17 @@ class Synthesizer:
         return n.value
 
     @property
+    def slice_stats(self):
+        """-> ((slot, batch) carrier chains passed by the slice-level translation, chained serially)."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        capi.check(capi.lib.gpsiq_slice_stats(self._ctx, C.byref(a), C.byref(b)), self._ctx)
+        return a.value, b.value
+
+    def check_device(self):
+        """Wait for the device; raise if a kernel flagged an error since the last check."""
+        capi.check(capi.lib.gpsiq_device_status(self._ctx), self._ctx)
+
+    @property
     def line_stats(self):
         """-> (tile-slot pairs re-checked with the literal recurrence, samples patched, chunks flagged)."""
         a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)

@@ -527,3 +527,101 @@ def test_config2_full_300s_user_motion_stream_through_the_front_end(gpus):
     assert p.wait() == 0, err
     assert total == 3000 * 300000 * 4
     assert sha.hexdigest() == meta["iq_sha256"], err
+
+
+def _stream_checksums(s, desc, sizes, ahead=2):
+    """The golden stream through the pipelined submit / fetch pair -> per-epoch device checksums."""
+    import torch
+
+    st = torch.cuda.Stream()
+    sums = []
+    with torch.cuda.stream(st):
+        cap = max(sizes)
+        bufs = [torch.empty(cap * 300000 * 2, dtype=torch.int16, device="cuda") for _ in range(2)]
+        descs, e = [], 0
+        for n in sizes:
+            descs.append(torch.from_numpy(desc[e:e + n].copy().view(np.uint8).reshape(-1)).cuda())
+            e += n
+        torch.cuda.synchronize()
+        sub = 0
+        for k in range(len(sizes)):
+            while sub < len(sizes) and sub <= k + ahead:
+                s.submit_device(descs[sub].data_ptr(), sizes[sub], st.cuda_stream)
+                sub += 1
+            s.fetch_device(bufs[k & 1].data_ptr(), st.cuda_stream)
+            st.synchronize()
+            sums += [int(x) for x in s.checksum_device(bufs[k & 1].data_ptr(), sizes[k])]
+    s.check_device()
+    return sums
+
+
+def test_slice_level_chain_one_head_scan_per_batch(monkeypatch):
+    """Level 5 of the carrier scan (csrc/nco_scan.cuh: slice_chain_group / slice_verify; k_carr_slice, k_carr_final,
+    k_carr_final_groups): a batch's exact chain is ONE head scan + a translation, its groups are chained in parallel
+    afterwards.  The 310-epoch user-motion golden (5 tie-capable steps, a re-allocation at 30 s, negative and positive
+    Doppler) in batches of several groups: the reference's per-epoch checksums, most (slot, batch) chains passed by
+    translation, no internal inconsistency flagged; and the same stream with the level switched off."""
+    meta = ol.load_golden_meta("circle12")
+    desc = ol.load_golden_desc("circle12")
+    sizes = [100, 128, 82]
+    with Synthesizer(max_chan=12, max_epochs=128) as s:
+        sums = _stream_checksums(s, desc, sizes)
+        translated, serial = s.slice_stats
+        trace_on = s.carrier_trace(sizes[-1])
+    assert sums == meta["epoch_checksums"]
+    # the first batch starts from re-seeded phases (serial by construction); afterwards translation is the rule
+    assert translated >= 8 and serial >= 10, (translated, serial)     # (10 of the 12 slots are active)
+    monkeypatch.setenv("GPSIQ_SLICE_SPEC", "0")
+    with Synthesizer(max_chan=12, max_epochs=128) as s:
+        sums_off = _stream_checksums(s, desc, sizes)
+        assert s.slice_stats[0] == 0
+        trace_off = s.carrier_trace(sizes[-1])
+    assert sums_off == meta["epoch_checksums"]
+    assert np.array_equal(trace_on, trace_off)
+
+
+def test_slice_level_chain_with_a_poor_estimate_falls_back_to_the_serial_chain():
+    """Exactness never depends on the start-phase estimate: a batch speculated from a deliberately wrong estimate is
+    chained serially (slice_verify finds no match), a good one is translated -- same samples, same end phases."""
+    import torch
+
+    base = ol.load_golden_desc("static12")
+    E = 200                                            # 4 groups of 64 epochs, the last one ragged
+    desc = np.concatenate([base] * 20)[:E].copy()
+    desc["flags"] = 0
+    first = desc.copy()
+    first[0]["flags"] = capi.FLAG_RESET_CARRIER
+    stride = 25
+    want_sums, want_end = None, None
+    for wrong in (0.0, 3e-7):
+        with Synthesizer(max_chan=12, max_epochs=E) as s:
+            d0 = torch.from_numpy(first.view(np.uint8).reshape(-1)).cuda()
+            d1 = torch.from_numpy(desc.view(np.uint8).reshape(-1)).cuda()
+            out = torch.empty(E * 300000 * 2, dtype=torch.int16, device="cuda")
+            s.synth_device(d0.data_ptr(), E, out.data_ptr())            # batch 0: from the allocation phases
+            torch.cuda.synchronize()
+            t0, s0 = s.slice_stats
+            est = torch.from_numpy(s.carrier.copy()).cuda()
+            est = torch.remainder(est + wrong, 1.0)
+            s.prepare_device(d1.data_ptr(), E)
+            s.estimate_from_device(est.data_ptr())
+            s.speculate_device(d1.data_ptr(), E)
+            s.chain_device(d1.data_ptr(), E)
+            s.render_device(d1.data_ptr(), E, out.data_ptr())
+            torch.cuda.synchronize()
+            s.check_device()
+            t1, s1 = s.slice_stats
+            sums = [int(x) for x in s.checksum_device(out.data_ptr(), E)]
+            end = s.carrier.copy()
+            trace = s.carrier_trace(E)
+        if wrong == 0.0:
+            assert t1 - t0 >= 10 and (t1 - t0) + (s1 - s0) == 12, (t0, s0, t1, s1)   # (nearly) every slot translated
+            want_sums, want_end, want_trace = sums, end, trace
+            # against the oracle: a stride of epochs, each from the chain's own start phase
+            for e in range(stride, E, stride):
+                ref, ph = ol.oracle_synth(desc[e:e + 1], 300000, carr_state=trace[e - 1].copy())
+                assert int(checksum_host(ref[0])) == sums[e], e
+                assert np.array_equal(ph[0], trace[e]), e
+        else:
+            assert s1 - s0 == 12 and t1 == t0, (t0, s0, t1, s1)       # nothing fits: all serial
+            assert sums == want_sums and np.array_equal(end, want_end) and np.array_equal(trace, want_trace)

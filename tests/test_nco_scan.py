@@ -151,3 +151,83 @@ def test_negative_doppler_uses_the_derived_parity_variant():
     want, wx = _literal_checkpoints([d] * 4, 100000, 1024, 0.3141592653589793)
     got, gx, fb = capi.carrier_chain_host([d] * 4, 100000, 1024, 0.3141592653589793, 1e-12)
     assert np.array_equal(got.view(np.int64), want.view(np.int64)) and bits(gx) == bits(wx)
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_slice_level_speculation_one_head_scan_per_batch(seed):
+    """Level 5 (nco_scan.cuh: slice_chain_group / slice_verify): the groups of a batch are chained speculatively from
+    the ESTIMATED batch start, one exact head scan is matched against that trajectory, and every group is then chained
+    on its own from its translated start phase.  Whatever the estimate error, every tile-start phase and the end phase
+    equal the literal recurrence; the groups' ends always agree with the translation (how != -2); with a good estimate
+    the batch is passed by translation (how == 1), with a poor one it is chained serially (how == 0)."""
+    rng = random.Random(seed)
+    passed = serial = 0
+    for trial in range(36):
+        fs = rng.choice([2.6e6, 1e7])
+        E = rng.choice([5, 12, 17])                      # host groups hold 4 epochs: 2 to 5 groups, ragged last one
+        N = rng.choice([260000, 100000, 4097])
+        T = rng.choice([1024, 2048])
+        f0 = rng.uniform(-5000, 5000) if trial % 4 else rng.uniform(-40, 40)   # incl. epochs that never wrap
+        steps = [(f0 + rng.uniform(-2, 2)) * (1.0 / fs) for _ in range(E)]
+        x0 = rng.random()
+        err = rng.choice([0.0, 0.0, 2e-14, 1e-12, 1e-10, 1e-6, 1e-3])
+        want, wx = _literal_checkpoints(steps, N, T, x0)
+        got, gx, fb, how = capi.carrier_slice_host(steps, N, T, x0, err)
+        assert how in (0, 1), (trial, how)
+        assert np.array_equal(got.view(np.int64), want.view(np.int64)), (trial, f0, E, N, T, err, how)
+        assert bits(gx) == bits(wx)
+        passed += how == 1
+        serial += how == 0
+        if err <= 1e-12 and abs(f0) > 300:
+            assert how == 1, (trial, f0, err)            # a good estimate must take the fast path
+    assert passed >= 12 and serial >= 3, (passed, serial)
+
+
+def test_slice_level_speculation_negative_steps_both_parities():
+    """Negative Doppler: the exact post-wrap state may sit on either parity of the 2^-53 grid; the slice-level chain is
+    speculated for both and the matching one is used."""
+    rng = random.Random(77)
+    hows = []
+    for trial in range(24):
+        f0 = -rng.uniform(300, 5000)
+        steps = [(f0 + rng.uniform(-1, 1)) / 2.6e6 for _ in range(9)]
+        x0 = rng.random()
+        want, wx = _literal_checkpoints(steps, 260000, 1024, x0)
+        got, gx, fb, how = capi.carrier_slice_host(steps, 260000, 1024, x0, rng.choice([0.0, 5e-14, 3e-13]))
+        assert np.array_equal(got.view(np.int64), want.view(np.int64)) and bits(gx) == bits(wx) and how in (0, 1)
+        hows.append(how)
+    assert sum(hows) >= 20, hows
+
+
+def test_tie_capable_steps_are_translated_through_their_tie_event():
+    """A positive step that is a multiple of 2^-53 (1 epoch in ~2^9 of a real run) can tie in [1, 2), where a translation
+    by an odd multiple of 2^-52 does not commute with rounding.  Levels 3-5 translate THROUGH such epochs: up to the
+    trajectory's first tie-wrap by D, after it by D +- 2^-52 if D is odd (nco_scan.cuh: TieEvent).  Epoch runs with
+    one or two tie-capable epochs, random phases and estimate errors (so that D takes both parities): every tile-start
+    phase equals the literal recurrence, group trajectories holding a tie event stay usable, and the changed shift is
+    actually applied at the group level and at the slice level."""
+    rng = random.Random(4242)
+    seen = applied_g = applied_s = passed = 0
+    ties = np.zeros(2, np.int32)
+    for trial in range(60):
+        fs = rng.choice([2.6e6, 1e7])
+        f0 = rng.uniform(300, 5000)
+        E, N, T = rng.choice([8, 12, 16]), rng.choice([260000, 100000]), 1024
+        steps = [(f0 + rng.uniform(-1, 1)) / fs for _ in range(E)]
+        for e in rng.sample(range(E), rng.choice([1, 2])):
+            steps[e] = np.ldexp(float(round(np.ldexp(steps[e], 53))), -53)      # tie-capable: a multiple of 2^-53
+        x0 = rng.random()
+        err = rng.choice([0.0, 2.0 ** -52, 3 * 2.0 ** -52, 1e-13, 7e-13, 1e-11])
+        want, wx = _literal_checkpoints(steps, N, T, x0)
+        got, gx, fb, how = capi.carrier_slice_host(steps, N, T, x0, err, ties)
+        assert how in (0, 1), (trial, how)
+        assert np.array_equal(got.view(np.int64), want.view(np.int64)), (trial, f0, E, N, err, how)
+        assert bits(gx) == bits(wx)
+        seen += int(ties[0])
+        applied_g += int(ties[1]) % 1000
+        applied_s += int(ties[1]) // 1000
+        passed += how == 1
+        # the plain chain (levels 1-4 only) goes through the same group code
+        got2, gx2, _ = capi.carrier_chain_host(steps, N, T, x0, err)
+        assert np.array_equal(got2.view(np.int64), want.view(np.int64)) and bits(gx2) == bits(wx)
+    assert seen >= 40 and applied_g >= 5 and applied_s >= 3 and passed >= 30, (seen, applied_g, applied_s, passed)
