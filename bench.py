@@ -357,7 +357,10 @@ def ours_arm(args):
             handoff = args.handoff if world > 1 else "nccl"
             if handoff == "mailbox" and not engine.mailbox_setup(rank, world):
                 handoff = "nccl"                              # decided collectively: every rank falls back alike
-        return TimeSliceRunner(engine, rank, world, deferred_render=True, handoff=handoff), handoff
+        # the mailbox hand-off never blocks the host, so the ranks need not run in lockstep: pipelined runner (rank 0
+        # speculates from an estimate too; the next slice is prepared and its advances all-gathered one step ahead)
+        pipelined = handoff == "mailbox" and not args.lockstep
+        return TimeSliceRunner(engine, rank, world, deferred_render=True, handoff=handoff, pipelined=pipelined), handoff
 
     synth = make_synth()
     d_first = torch.from_numpy(first.view(np.uint8).reshape(-1)).cuda()
@@ -395,7 +398,7 @@ def ours_arm(args):
         run_batches(max(args.warmup, 1), d_first)
     else:
         for i in range(args.warmup):
-            runner.step(d_first if (i == 0 and rank == 0) else d_desc, E, d_out)
+            runner.step(d_first if (i == 0 and rank == 0) else d_desc, E, d_out, next_desc=d_desc)
     barrier()
     l0 = synth.launch_count
     synth.timing_begin()
@@ -405,8 +408,8 @@ def ours_arm(args):
     if world == 1:
         run_batches(args.steps)                              # exactly `steps` batches scanned AND rendered in here
     else:
-        for i in range(args.steps):
-            runner.step(d_desc, E, d_out)
+        for i in range(args.steps):                          # (every step prepares the following one: one prepare per step)
+            runner.step(d_desc, E, d_out, next_desc=d_desc)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -418,6 +421,11 @@ def ours_arm(args):
     nrec, scan_ms, synth_ms = synth.timing_collect()
     kn, kms, kep = synth.timing_sample_kernel()
     fallbacks = synth.carrier_fallbacks
+    synth.check_device()                                     # a kernel-flagged error (incl. the chain's self-check) ends the run
+    sl = torch.tensor([float(v) for v in synth.slice_stats], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(sl, op=dist.ReduceOp.SUM)
+    slice_translated, slice_serial = int(sl[0]), int(sl[1])
     t = torch.tensor([ms, float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
         tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -493,13 +501,13 @@ def ours_arm(args):
         hd = torch.from_numpy(np.ctypeslib.as_array(ctypes.cast(h_desc, ctypes.POINTER(ctypes.c_uint8)), shape=(nbytes_desc,)))
         for i in range(max(args.warmup, 1)):
             ctypes.memmove(h_desc, (first if (i == 0 and rank == 0) else desc).ctypes.data, nbytes_desc)
-            runner2.step(hd, E, outs[i & 1])
+            runner2.step(hd, E, outs[i & 1], next_desc=None if (i == 0 and rank == 0) else hd)
             torch.cuda.synchronize()                             # (the upload of the staging buffer is done)
         ctypes.memmove(h_desc, desc.ctypes.data, nbytes_desc)
         barrier()
         t0 = time.perf_counter()
         for i in range(args.steps):                              # each step: scan slice k (+ H2D), render slice k-1 (+ D2H, blocking)
-            runner2.step(hd, E, outs[i & 1])
+            runner2.step(hd, E, outs[i & 1], next_desc=hd)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         runner2.finish()
@@ -568,6 +576,9 @@ def ours_arm(args):
                                     % (samples_per_step * 4 / 1e6, nbytes_desc),
                        "kernel": args.kernel, "tile_samples": args.tile, "lookahead_batches": ahead if world == 1 else 1,
                        "carrier_scan_serial_fallbacks": fallbacks,
+                       "slice_chains_translated": slice_translated, "slice_chains_serial": slice_serial,
+                       "runner": ("pipelined" if (world > 1 and handoff == "mailbox" and not args.lockstep) else
+                                  "lockstep" if world > 1 else "submit/fetch"),
                        "carrier_scan_chains": (args.warmup + args.steps) * E * C,
                        "numa_bound_cpus": numa_cpus},
             "e2e": {"value": round(e2e_value, 3), "unit": "Msamples/s", "h2d_bytes_per_step": nbytes_desc,
@@ -616,6 +627,8 @@ def main():
     ap.add_argument("--carrier", choices=["float", "int32"], default="float",
                     help="float: the shipped build (FLOAT_CARR_PHASE, plutogpssim.h:12); int32: the reference's integer "
                          "carrier NCO (its #else branches), closed form")
+    ap.add_argument("--lockstep", action="store_true",
+                    help="N > 1: the round-1/2 runner (rank 0 waits for the ring before it speculates, advances gathered inside the step)")
     ap.add_argument("--handoff", choices=["nccl", "mailbox"], default=os.environ.get("GPSIQ_HANDOFF", "mailbox"),
                     help="float-carrier phase hand-off between time slices (N > 1): the SM-free peer-memory mailbox "
                          "(copy engine + stream memory operations; falls back to NCCL if unavailable), or NCCL send/recv")

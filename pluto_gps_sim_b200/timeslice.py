@@ -55,6 +55,25 @@ class GpuSliceEngine:
         # for it later, and is subtracted from the next estimate.  Speed only: never part of a result.
         z = lambda: torch.zeros(synth.max_chan, dtype=torch.float64, device="cuda")
         self.bias, self.est_start, self.zero = z(), z(), z()
+        # pipelined runner: the NEXT slice's prepare + all_gather run on their own stream beside this slice's
+        # speculation and hand-off (nothing in them depends on the ring)
+        self.prep_stream = torch.cuda.Stream(priority=-1)
+        self.prep_event = torch.cuda.Event()
+
+    def prep_context(self, first=False):
+        """Stream context for the next slice's prepare + all_gather.  Nothing in them depends on what the scan stream
+        is doing (the library orders the reuse of a scan set behind its last render by itself); only the very first
+        call is ordered behind the scan stream, which at that point has waited for the caller's stream (descriptors
+        created there right before the first step)."""
+        if first:
+            self.prep_stream.wait_stream(self.scan_stream)
+        return torch.cuda.stream(self.prep_stream)
+
+    def prep_done(self):
+        self.prep_event.record(self.prep_stream)
+
+    def wait_prep(self):
+        self.scan_stream.wait_event(self.prep_event)
 
     def scan_context(self, order_after_caller=False):
         # The scan stream must not be ordered after the caller's stream in steady state (that would
@@ -111,12 +130,12 @@ class GpuSliceEngine:
             self.s.render_device(desc_dev.data_ptr(), n_epochs, out.data_ptr(), self._stream())
 
     def upload(self, desc_host, index):
-        """Pinned host descriptors (uint8 tensor) -> device staging buffer (two, alternating), on the current stream.
-        A staging buffer is reused two slices later; the host-buffer render of the slice that used it has returned
+        """Pinned host descriptors (uint8 tensor) -> device staging buffer (three, in turn), on the current stream.
+        A staging buffer is reused three slices later; the host-buffer render of the slice that used it has returned
         by then (gpsiq_fetch blocks)."""
-        if not hasattr(self, "_stage"):
-            self._stage = [torch.empty(self.s.max_epochs * self.s.max_chan * 64, dtype=torch.uint8, device="cuda") for _ in range(2)]
-        d = self._stage[index & 1][: desc_host.numel()]
+        if not hasattr(self, "_stage"):   # three: slices k-1 (render pending), k and -- pipelined runner -- k+1 are alive at once
+            self._stage = [torch.empty(self.s.max_epochs * self.s.max_chan * 64, dtype=torch.uint8, device="cuda") for _ in range(3)]
+        d = self._stage[index % 3][: desc_host.numel()]
         d.copy_(desc_host, non_blocking=True)
         return d
 
@@ -161,14 +180,22 @@ class GpuSliceEngine:
 
 
 class TimeSliceRunner:
-    def __init__(self, engine, rank=None, world=None, deferred_render=False, handoff="nccl"):
+    def __init__(self, engine, rank=None, world=None, deferred_render=False, handoff="nccl", pipelined=False):
         """handoff: "nccl" (dist.send / dist.recv of the phases) or "mailbox" (the engine's SM-free peer-memory
         hand-off, GpuSliceEngine.mailbox_setup must have run; same node only).
         deferred_render: step k enqueues the scan phases of slice k and then the rendering of slice k-1
         (the last slice is rendered by finish()).  The device then sees the next slice's chunk speculation
         before this slice's sample kernel, which is the order gpsiq_submit/gpsiq_fetch produce on one GPU:
         the speculation runs first at full occupancy and the rest of the chain beside the sample kernel.
-        An `out` buffer passed to step k is complete only after step k+1 (or finish) has been enqueued."""
+        An `out` buffer passed to step k is complete only after step k+1 (or finish) has been enqueued.
+        pipelined (float carrier, a hand-off that does not block the host: "mailbox"): the ranks are not kept in
+        lockstep.  Rank 0 does not wait for the previous step's ring before it speculates -- like every other rank it
+        estimates its start phase from the exact end of its own previous slice and the closed-form advances of the
+        N - 1 slices in between, and receives the exact phases only in front of its chain -- and when step() is given
+        the NEXT slice's descriptors, that slice is prepared and its advances all-gathered on a side stream beside
+        this slice's speculation, so that no rank's speculation waits for the slowest rank of the ring.  The ring of
+        step k then only orders [receive, one head scan + translation, send] per rank, and the step time is the
+        larger of one rank's own scan work and N hops instead of their sum."""
         self.engine = engine
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
@@ -184,20 +211,32 @@ class TimeSliceRunner:
         # advances of the slices before its own into its carrier state (and the ones after it afterwards, so that
         # all ranks hold the phase at the start of the next step).  SURVEY 8e: "truly parallel".
         self.prefix = handoff == "prefix"
+        self.pipelined = bool(pipelined) and not self.prefix and self.world > 1
+        self.next_adv = None           # advances of the NEXT step's slices, all-gathered one step ahead (pipelined)
+        self.next_desc = None          # ... and that slice's device descriptors (host descriptors are uploaded once)
 
-    def step(self, desc, n_epochs, out):
+    def step(self, desc, n_epochs, out, next_desc=None, next_epochs=None):
         """Synthesize this rank's slice of the next step.
 
         Every rank issues its communication in the same global order -- hand-off into
         rank 0 (closing the previous step's ring), all_gather of this step, then the
         hand-offs 0->1->...->N-1 -- so in-order streams (NCCL) and blocking calls
-        (gloo) cannot deadlock."""
+        (gloo) cannot deadlock.  (pipelined: all_gather of the NEXT step, hand-off into this rank, hand-off out of
+        it; the hand-off must not block the host.)
+
+        next_desc / next_epochs (pipelined runners): the descriptors of this rank's slice of the FOLLOWING step, if
+        the caller has them -- that step() call must then be given the same slice."""
         eng, r, n = self.engine, self.rank, self.world
         ctx = eng.scan_context(self.step_index == 0) if hasattr(eng, "scan_context") else contextlib.nullcontext()
         with ctx:
-            if isinstance(desc, torch.Tensor) and desc.device.type == "cpu" and hasattr(eng, "upload"):
+            if self.pipelined and self.next_adv is not None:
+                desc = self.next_desc                           # prepared (and uploaded) one step ahead
+            elif isinstance(desc, torch.Tensor) and desc.device.type == "cpu" and hasattr(eng, "upload"):
                 desc = eng.upload(desc, self.step_index)        # host descriptors: H2D on the scan stream
-            self._scan_phases(desc, n_epochs)
+            if self.pipelined:
+                self._scan_phases_pipelined(desc, n_epochs, next_desc, next_epochs if next_epochs else n_epochs)
+            else:
+                self._scan_phases(desc, n_epochs)
         if self.deferred:
             if self.pending is not None:
                 eng.render(*self.pending)
@@ -259,6 +298,53 @@ class TimeSliceRunner:
             else:
                 eng.store_carrier()
                 dist.send(eng.phase, dst=(r + 1) % n)
+
+    def _prepare_and_gather(self, desc, n_epochs, index):
+        """prepare + all_gather of the slices' closed-form advances, into one of four preallocated buffer sets (they
+        are written on one stream and read on another: nothing here is left to the caching allocator)."""
+        eng, n = self.engine, self.world
+        eng.prepare(desc, n_epochs)
+        if not hasattr(self, "_adv_ring"):
+            self._adv_ring = [[torch.empty_like(eng.adv) for _ in range(n)] for _ in range(4)]
+        adv_all = self._adv_ring[index % 4]
+        dist.all_gather(adv_all, eng.adv)
+        return adv_all
+
+    def _scan_phases_pipelined(self, desc, n_epochs, next_desc, next_epochs):
+        eng, r, n, k = self.engine, self.rank, self.world, self.step_index
+        if self.next_adv is not None:                           # prepared and gathered during the previous step
+            adv_all, self.next_adv, self.next_desc = self.next_adv, None, None
+            if hasattr(eng, "wait_prep"):
+                eng.wait_prep()
+        else:
+            adv_all = self._prepare_and_gather(desc, n_epochs, k)
+        # start-phase estimate: the exact end of this rank's previous slice (the chain left the estimate there)
+        # advanced by the closed-form advances of the N - 1 slices owned by the other ranks in between
+        skipped = ([] if self.prev_adv is None else self.prev_adv[r + 1:]) + adv_all[:r]
+        for a in skipped:
+            eng.estimate_fold(a)
+        if hasattr(eng, "apply_bias"):
+            eng.apply_bias()
+        self.prev_adv = adv_all
+        eng.speculate(desc, n_epochs)
+        # the next slice's prepare + all_gather: beside this slice's speculation and hand-off
+        if next_desc is not None:
+            side = eng.prep_context(k == 0) if hasattr(eng, "prep_context") else contextlib.nullcontext()
+            with side:
+                if isinstance(next_desc, torch.Tensor) and next_desc.device.type == "cpu" and hasattr(eng, "upload"):
+                    next_desc = eng.upload(next_desc, k + 1)
+                self.next_adv = self._prepare_and_gather(next_desc, next_epochs, k + 1)
+                self.next_desc = next_desc
+                if hasattr(eng, "prep_done"):
+                    eng.prep_done()
+        # the ring: exact phases in, one head scan + translation (or the serial chain), exact phases out
+        received = not (k == 0 and r == 0)                      # (the stream starts at rank 0 from re-seeded phases)
+        if received:
+            eng.handoff_recv(k + 1 if r > 0 else k)             # message number = sender's step index + 1
+        eng.chain(desc, n_epochs)
+        eng.handoff_send(k + 1)
+        if received and hasattr(eng, "update_bias"):            # estimate feedback: off the ring's critical path
+            eng.update_bias()
 
     def finish(self):
         """Render the slice still pending (deferred_render) and drain the last hand-off (rank 0 receives

@@ -21,7 +21,8 @@ STEPS = 9
 CIRCLE = os.path.join(ol.ORACLE_DIR, "_ref", "circle.csv")
 
 
-def _worker(rank, world, port, outdir, deferred=False, handoff="nccl", feed="golden", golden="circle12"):
+def _worker(rank, world, port, outdir, deferred=False, handoff="nccl", feed="golden", golden="circle12", pipelined=False,
+            E=E, STEPS=STEPS):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -39,14 +40,21 @@ def _worker(rank, world, port, outdir, deferred=False, handoff="nccl", feed="gol
     engine = GpuSliceEngine(synth)
     if handoff == "mailbox":
         assert engine.mailbox_setup(rank, world)
-    runner = TimeSliceRunner(engine, rank, world, deferred_render=deferred, handoff=handoff)
+    runner = TimeSliceRunner(engine, rank, world, deferred_render=deferred, handoff=handoff, pipelined=pipelined)
     outs = [torch.empty(E * 300000 * 2, dtype=torch.int16, device="cuda") for _ in range(2)]
     sums = []
+    keep = []                                                  # (descriptor tensors stay alive until their slice is rendered)
     for s in range(STEPS):
         first = (s * world + rank) * E
         mine = feeder.next_slice() if feeder else desc[first:first + E].copy()
         d = torch.from_numpy(mine.view(np.uint8).reshape(-1)).cuda()
-        runner.step(d, E, outs[s & 1])
+        nxt = None
+        if pipelined and not feeder and s + 1 < STEPS:         # the next slice's descriptors: prepared one step ahead
+            f2 = ((s + 1) * world + rank) * E
+            nxt = torch.from_numpy(desc[f2:f2 + E].copy().view(np.uint8).reshape(-1)).cuda()
+            keep.append(nxt)
+        keep.append(d)
+        runner.step(d, E, outs[s & 1], next_desc=nxt)
         torch.cuda.synchronize()
         if not deferred:
             sums.append(synth.checksum_device(outs[s & 1].data_ptr(), E))
@@ -57,7 +65,9 @@ def _worker(rank, world, port, outdir, deferred=False, handoff="nccl", feed="gol
     if deferred:
         sums.append(synth.checksum_device(outs[(STEPS - 1) & 1].data_ptr(), E))
     np.save(os.path.join(outdir, "sums%d.npy" % rank), np.stack(sums))
+    synth.check_device()
     np.save(os.path.join(outdir, "fb%d.npy" % rank), np.array([synth.carrier_fallbacks]))
+    np.save(os.path.join(outdir, "slice%d.npy" % rank), np.array(synth.slice_stats))
     dist.destroy_process_group()
 
 
@@ -76,6 +86,28 @@ def test_two_gpu_time_slices_match_reference(tmp_path, deferred, handoff):
     # the estimates handed around the ring are good enough that the serial fallback stays rare
     fb = sum(int(np.load(tmp_path / ("fb%d.npy" % r))[0]) for r in range(world))
     assert fb < world * STEPS * E * 12 // 10, fb
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("slice_epochs,steps", [(16, 9), (70, 2)])
+def test_two_gpu_pipelined_time_slices_match_reference(tmp_path, slice_epochs, steps):
+    """TimeSliceRunner(pipelined=True) over the mailbox hand-off: no lockstep between the ranks (rank 0 speculates
+    from an estimate, the next slice is prepared and its advances all-gathered one step ahead on a side stream), the
+    exact chain of a slice is one head scan + a translation (slices of one and of two groups of 64 epochs).  The
+    reference's per-epoch checksums, and the slice-level translation is what actually ran."""
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(world, port, str(tmp_path), True, "mailbox", "golden", "circle12", True, slice_epochs, steps),
+             nprocs=world, join=True)
+    meta = ol.load_golden_meta("circle12")
+    parts = [np.load(tmp_path / ("sums%d.npy" % r)) for r in range(world)]
+    got = np.concatenate([parts[r][s] for s in range(steps) for r in range(world)])
+    assert [int(x) for x in got] == meta["epoch_checksums"][: world * steps * slice_epochs]
+    translated = sum(int(np.load(tmp_path / ("slice%d.npy" % r))[0]) for r in range(world))
+    serial = sum(int(np.load(tmp_path / ("slice%d.npy" % r))[1]) for r in range(world))
+    assert translated >= serial, (translated, serial)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")

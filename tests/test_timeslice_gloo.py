@@ -134,6 +134,85 @@ def test_time_slices_equal_sequential_stream(tmp_path, WORLD, handoff):
     assert np.array_equal(np.load(tmp_path / "final_phase.npy"), st)
 
 
+# ---- pipelined runner: no lockstep between the ranks ---------------------------------------------------------------
+class AsyncOracleEngine(OracleEngine):
+    """The mailbox hand-off never blocks the sender (a copy engine write + a flag): isend here."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.inflight = []
+        self.prepared = []
+
+    def prepare(self, desc, n_epochs):
+        super().prepare(desc, n_epochs)
+        self.prepared.append(desc[:n_epochs].copy())
+
+    def handoff_send(self, seq):
+        buf = torch.cat([torch.tensor([float(seq)], dtype=torch.float64), torch.from_numpy(self.state.copy())])
+        self.inflight.append((dist.isend(buf, dst=(self.rank + 1) % self.world), buf))
+
+    def drain(self):
+        for w, _ in self.inflight:
+            w.wait()
+
+    # deferred rendering: slices are rendered one step after they were chained, in order
+    def chain(self, desc, n_epochs):
+        super().chain(desc, n_epochs)
+        self.queue = getattr(self, "queue", []) + [self.pending]
+
+    def render(self, desc, n_epochs, out):
+        out[...] = self.queue.pop(0)
+
+
+def _pipelined_worker(rank, WORLD, port, outdir, lookahead):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    from pluto_gps_sim_b200.timeslice import TimeSliceRunner
+
+    desc = _stream_desc(WORLD)
+    eng = AsyncOracleEngine(desc.shape[1], rank, WORLD)
+    runner = TimeSliceRunner(eng, rank, WORLD, handoff="mailbox", pipelined=True, deferred_render=True)
+    outs = []
+    for s in range(STEPS):
+        first = (s * WORLD + rank) * E
+        nxt = ((s + 1) * WORLD + rank) * E
+        out = np.zeros((E, N, 2), np.int16)
+        give_next = lookahead == "always" or (lookahead == "sometimes" and s == 0)
+        runner.step(desc[first:first + E], E, out, next_desc=desc[nxt:nxt + E] if (give_next and s + 1 < STEPS) else None)
+        outs.append(out)
+    runner.finish()
+    eng.drain()
+    # every rank -- rank 0 included -- estimates its start phase by folding the N - 1 foreign slices in between
+    assert eng.folds == rank + (STEPS - 1) * (WORLD - 1), (rank, eng.folds)
+    # every slice was prepared exactly once, in stream order, whether ahead of its step or inside it
+    assert len(eng.prepared) == STEPS
+    for s in range(STEPS):
+        first = (s * WORLD + rank) * E
+        assert np.array_equal(eng.prepared[s], desc[first:first + E])
+    np.save(os.path.join(outdir, "rank%d.npy" % rank), np.stack(outs))
+    if rank == 0:
+        np.save(os.path.join(outdir, "final_phase.npy"), eng.state)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("WORLD,lookahead", [(2, "always"), (3, "always"), (3, "sometimes"), (2, "never")])
+def test_pipelined_time_slices_equal_sequential_stream(tmp_path, WORLD, lookahead):
+    """TimeSliceRunner(pipelined=True): rank 0 speculates from an estimate like everyone else and receives the exact
+    phases only in front of its chain; the next slice is prepared and its advances all-gathered one step ahead (when
+    the caller hands its descriptors over); rendering is deferred by one step.  Same stream as one sequential run."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_pipelined_worker, args=(WORLD, port, str(tmp_path), lookahead), nprocs=WORLD, join=True)
+    desc = _stream_desc(WORLD)
+    st = np.zeros(desc.shape[1])
+    want, _ = ol.oracle_synth(desc, N, carr_state=st)
+    parts = [np.load(tmp_path / ("rank%d.npy" % r)) for r in range(WORLD)]
+    got = np.concatenate([parts[r][s] for s in range(STEPS) for r in range(WORLD)])
+    assert np.array_equal(got, want)
+    assert np.array_equal(np.load(tmp_path / "final_phase.npy"), st)
+
+
 # ---- integer carrier: closed-form prefix instead of a ring ------------------------------------------------------
 def _prefix_worker(rank, WORLD, port, outdir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
