@@ -269,6 +269,15 @@ int gpsiq_mailbox_create(gpsiq_ctx *ctx, void *ipc_handle_out_64_bytes);
 int gpsiq_mailbox_open(gpsiq_ctx *ctx, const void *ipc_handle_64_bytes, int peer_device);
 int gpsiq_mailbox_send(gpsiq_ctx *ctx, uint64_t seq, void *cuda_stream);
 int gpsiq_mailbox_recv(gpsiq_ctx *ctx, uint64_t seq, void *cuda_stream);
+/* The hand-off FUSED into the chain kernel (one kernel per hop of a time-sliced run): the kernel waits for message
+ * recv_seq in this context's mailbox (acquire load of the sequence flag the previous GPU writes over NVLink peer
+ * memory), chains the batch from the phases it finds there, and stores its end phases as message send_seq into the
+ * next GPU's mailbox (peer stores, system-scope fence, release store of the flag).  recv_seq == 0: start from the
+ * context's carrier state (as gpsiq_chain_device); send_seq == 0: no send.  start_copy_dev (may be NULL) receives the
+ * exact start phases.  The wait is bounded (~10 s): a message that never arrives sets the context's error word.
+ * Replaces gpsiq_mailbox_recv + gpsiq_chain_device + gpsiq_mailbox_send; messages are interchangeable with theirs. */
+int gpsiq_chain_handoff_device(gpsiq_ctx *ctx, const gpsiq_chan_desc *desc_dev, int n_epochs, uint64_t recv_seq,
+                               uint64_t send_seq, double *start_copy_dev, void *cuda_stream);
 int gpsiq_estimate_correct_device(gpsiq_ctx *ctx, const double *exact_old_dev, const double *est_old_dev, double gain,
                                   void *cuda_stream);
 int gpsiq_carrier_to_device(gpsiq_ctx *ctx, double *dst_dev, void *cuda_stream);

@@ -112,6 +112,7 @@ SYMBOLS = {
     "gpsiq_mailbox_open": (_i, [_vp, _vp, _i]),
     "gpsiq_mailbox_send": (_i, [_vp, C.c_uint64, _vp]),
     "gpsiq_mailbox_recv": (_i, [_vp, C.c_uint64, _vp]),
+    "gpsiq_chain_handoff_device": (_i, [_vp, _vp, _i, C.c_uint64, C.c_uint64, _vp, _vp]),
     "gpsiq_trace_dump": (_i, [_vp, _i]),
     "gpsiq_line_stats": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "gpsiq_minmod_host": (C.c_uint64, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),

@@ -24,6 +24,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "../../include/gpsiq.h"
 #include "../../include/gpsiq_desc.h"
@@ -73,12 +74,24 @@ static void ca_generate(int prn, uint8_t* chips) {
 // Optional timeline trace (GPSIQ_TRACE=1 in the environment): an event after every kernel launch,
 // dumped by gpsiq_trace_dump as milliseconds since the first one.  Diagnostics only.
 #define TRACE_MAX 4096
-struct TraceRec { cudaEvent_t ev; const char* label; int stream_id; };
+struct TraceRec { cudaEvent_t ev; const char* label; int stream_id; double host_ms; };   // host_ms: when the host enqueued it
 
 
 // Everything the scan phases produce for one batch and the render phase consumes.  There are two
 // sets so that gpsiq_submit_device can scan batch k+1 while gpsiq_fetch_device renders batch k;
 // the working pointers in gpsiq_ctx (d_lut, d_carr_ck, ...) are switched to one set before enqueuing.
+// (see k_carr_final)
+struct Handoff {
+    const unsigned long long* in_flag;   // own mailbox flag (NULL: start from carr_state)
+    unsigned long long in_seq;
+    const double* in_slot;               // own mailbox slot holding message in_seq
+    double* out_slot;                    // next GPU's mailbox slot for message out_seq (NULL: no send)
+    unsigned long long* out_flag;        // next GPU's flag
+    unsigned long long out_seq;
+    unsigned int* counter;               // own: slots that have stored their end phase (reset by the last one)
+    double* start_copy;                  // optional: the exact start phases, for the caller's estimate feedback
+    int* err;
+};
 struct SliceRes;
 struct ScanSet {
     gpsiq_chan_desc* d_descbuf;
@@ -134,6 +147,7 @@ struct gpsiq_ctx {
     double* d_bias_rate;  // [C] measured residual of the closed-form epoch advance (cycles per epoch), see k_bias_update
     double* d_carr_start; // [C] exact phases at the start of the batch being chained
     int chain_keeps_estimate;  // GPSIQ_OPT_CHAIN_KEEPS_ESTIMATE
+    Handoff handoff;           // what the next enqueue_chain fuses into its kernel (gpsiq_chain_handoff_device); cleared after use
     int slice_spec;            // level 5 (slice-level speculation: one head scan per batch on the chain's critical path); GPSIQ_SLICE_SPEC=0 turns it off
     int render_after_next_chain;  // GPSIQ_OPT_RENDER_AFTER_NEXT_CHAIN
     // SM-free carrier hand-off between the GPUs of one node (gpsiq_mailbox_*)
@@ -217,6 +231,11 @@ static void trace_mark(gpsiq_ctx* ctx, cudaStream_t st, const char* label) {
         while (k < nseen && seen[k] != st) k++;
         if (k == nseen && nseen < 16) seen[nseen++] = st;
         r.stream_id = 20 + k;
+    }
+    {
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        r.host_ms = (double) ts.tv_sec * 1e3 + (double) ts.tv_nsec * 1e-6;
     }
     cudaEventRecord(r.ev, st);
     ctx->trace_n++;
@@ -743,6 +762,22 @@ k_carr_slice(const gpsiq_chan_desc* __restrict__ desc, const CarrSpec* __restric
     }
 }
 
+// Hand-off fused into the chain kernel (time-sliced multi-GPU runs, gpsiq_chain_handoff_device): the kernel itself
+// waits for the previous slice's end phases in this GPU's mailbox (acquire load of a sequence flag the previous GPU
+// writes over NVLink peer memory), chains, and stores its own end phases + sequence flag into the NEXT GPU's mailbox
+// (peer stores, system-scope fence, release store by the last slot to finish).  One kernel per hop: no copy engine,
+// no stream memory operation, nothing between the arrival of the phases and the head scan.
+#define GPSIQ_DEVERR_HANDOFF 0x08000000  // error word: the previous slice's phases never arrived (bounded wait)
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 // Levels 5 + 4: the exact chain of a batch, one warp per slot.  With a usable slice-level speculation: ONE head scan
 // (up to the batch's first wrap) + a translation, and k_carr_final_groups then chains the groups in parallel.  Otherwise
 // serial over the groups: one head scan per group.  start_out / end_out: the exact phases before / after the batch.
@@ -754,13 +789,29 @@ k_carr_final(const gpsiq_chan_desc* __restrict__ desc,
              int* __restrict__ fallbacks, const TieEvent* __restrict__ tieG, const CarrSpec* __restrict__ specS,
              const TieEvent* __restrict__ tieS, SliceRes* __restrict__ sres, unsigned long long* __restrict__ slice_stats,
              double* __restrict__ start_out, double* __restrict__ end_out, double* __restrict__ est_out,
-             int E, int C, int N, int T, int ntiles) {
+             const Handoff h, int E, int C, int N, int T, int ntiles) {
     __shared__ GroupEpoch s_ge[GROUP_EPOCHS];
     const int c = blockIdx.x, lane = threadIdx.x;
     if (c >= C) return;
     const int ngroups = (E + GROUP_EPOCHS - 1) / GROUP_EPOCHS;
-    double x = carr_state[c];
-    if (lane == 0) start_out[c] = x;
+    double x = 0.0;
+    if (h.in_flag) {   // the start phases come from the previous slice's owner: wait for its message
+        if (lane == 0) {
+            const long long t0 = clock64();
+            bool timed_out = false;
+            while (ld_acquire_sys_u64(h.in_flag) < h.in_seq) {
+                __nanosleep(100);
+                if (clock64() - t0 > 20000000000LL) { timed_out = true; break; }   // ~10 s: give up loudly, never hang
+            }
+            if (timed_out) atomicOr(h.err, GPSIQ_DEVERR_HANDOFF);
+            x = *(const volatile double*) (h.in_slot + c);
+        }
+        x = __shfl_sync(0xffffffffu, x, 0);
+    } else {
+        x = carr_state[c];
+    }
+    const double x_first = x;
+    if (lane == 0) { start_out[c] = x; if (h.start_copy) h.start_copy[c] = x; }
     SliceRes res;
     res.diff = 0.0; res.diff2 = 0.0; res.variant = 0; res.how = 0; res.tie_g = 0x7fffffff; res.pad = 0;
     if (specS) {
@@ -781,7 +832,7 @@ k_carr_final(const gpsiq_chan_desc* __restrict__ desc,
                 r = __shfl_sync(0xffffffffu, r, 0);
             }
             if (r == 1) { res.how = 1; const TieEvent& tv = res.variant ? tS1 : tS0; if (tv.pos >= 0) res.tie_g = tv.pos; }
-            else x = carr_state[c];                                 // (slice_verify leaves x advanced over the head on failure)
+            else x = x_first;                                 // (slice_verify leaves x advanced over the head on failure)
             __syncwarp();
         }
     }
@@ -794,6 +845,15 @@ k_carr_final(const gpsiq_chan_desc* __restrict__ desc,
     if (lane == 0) {
         if (sres) sres[c] = res;
         if (slice_stats && res.how != 2) atomicAdd(slice_stats + (res.how == 1 ? 0 : 1), 1ULL);
+        if (h.out_slot) {   // end phases -> the next GPU's mailbox; the last slot to get here publishes the sequence number
+            *(volatile double*) (h.out_slot + c) = x;
+            __threadfence_system();
+            if (atomicAdd(h.counter, 1u) == (unsigned) C - 1u) {
+                __threadfence_system();   // (the other slots' stores, ordered before their increments, before the flag)
+                *h.counter = 0u;
+                st_release_sys_u64(h.out_flag, h.out_seq);
+            }
+        }
         carr_state[c] = x;
         end_out[c] = x;
         if (est_out) est_out[c] = x;
@@ -1430,9 +1490,10 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     if (ctx->trace_on && getenv("GPSIQ_TRACE")[0] == '2') {  // GPSIQ_TRACE=2: dump the last records at destruction
-        if (ctx->trace_n > 120) {  // keep the tail
-            for (int i = 0; i < 120; i++) { TraceRec t = ctx->trace[i]; ctx->trace[i] = ctx->trace[ctx->trace_n - 120 + i]; ctx->trace[ctx->trace_n - 120 + i] = t; }
-            ctx->trace_n = 120;
+        const int keep = 360;
+        if (ctx->trace_n > keep) {  // keep the tail
+            for (int i = 0; i < keep; i++) { TraceRec t = ctx->trace[i]; ctx->trace[i] = ctx->trace[ctx->trace_n - keep + i]; ctx->trace[ctx->trace_n - keep + i] = t; }
+            ctx->trace_n = keep;
         }
         gpsiq_trace_dump(ctx, 1);
     }
@@ -1620,7 +1681,8 @@ static int enqueue_chain(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_
                                        ctx->d_ginfo, ctx->d_fallbacks, ctx->d_tieG, ctx->slice_spec ? ctx->d_specS : NULL,
                                        ctx->d_tieS, ctx->d_sres, ctx->d_slice_stats,
                                        ctx->d_start0, wset.d_exact_end, ctx->chain_keeps_estimate ? NULL : ctx->d_est_state,
-                                       n_epochs, C, N, T, ntiles);
+                                       ctx->handoff, n_epochs, C, N, T, ntiles);
+        memset(&ctx->handoff, 0, sizeof ctx->handoff);
         float_chain = true;
     } else if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_INT32) {  // closed form: one prefix sum over the epochs
         k_int_carrier<<<C, 32, 0, st>>>(desc_dev, ctx->d_ustart, ctx->d_carr_state, ctx->d_carr_trace, NULL, 0, n_epochs, C, N);
@@ -1840,10 +1902,11 @@ static int check_device_error(gpsiq_ctx* ctx) {
     CU(cudaStreamSynchronize(ctx->stream));
     if (h) {
         CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
-        if (h & 0x70000000) {
+        if (h & 0x78000000) {
             snprintf(ctx->err, sizeof ctx->err, "internal device error 0x%x (%s)", h,
                      (h & GPSIQ_DEVERR_SLICE) ? "the parallel group chain disagrees with the slice-level translation"
-                                              : "a table copy did not complete");
+                     : (h & GPSIQ_DEVERR_HANDOFF) ? "the previous slice's carrier phases never arrived in the mailbox"
+                                                  : "a table copy did not complete");
             return GPSIQ_ERR_CUDA;
         }
         snprintf(ctx->err, sizeof ctx->err, "descriptor %d (epoch*max_chan+slot) is out of contract", h - 1);
@@ -2268,6 +2331,7 @@ int gpsiq_carrier_from_device(gpsiq_ctx* ctx, const double* src_dev, void* strea
 // stream waits on that number with a stream memory operation.
 #define MBOX_SLOT 1024
 #define MBOX_FLAG 2048
+#define MBOX_COUNTER 3072
 #define MBOX_BYTES 4096
 typedef CUresult (*mbox_fn64)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);
 
@@ -2320,18 +2384,53 @@ int gpsiq_mailbox_send(gpsiq_ctx* ctx, uint64_t seq, void* stream) {
                        cudaMemcpyDefault, (cudaStream_t) stream));
     const CUresult r = ((mbox_fn64) ctx->fn_write64)((CUstream) stream, (CUdeviceptr) (ctx->d_mbox_peer + MBOX_FLAG), seq, 0);
     if (r != CUDA_SUCCESS) return fail(ctx, GPSIQ_ERR_CUDA, "gpsiq_mailbox_send: cuStreamWriteValue64 failed", cudaSuccess);
+    trace_mark(ctx, (cudaStream_t) stream, "mbox_send(flag written)");
     return GPSIQ_OK;
+}
+
+// The hand-off fused into the chain kernel: [wait for message recv_seq in the own mailbox] -> chain -> [end phases as
+// message send_seq into the next GPU's mailbox].  recv_seq / send_seq 0: that side is not wanted.
+int gpsiq_chain_handoff_device(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_epochs, uint64_t recv_seq,
+                               uint64_t send_seq, double* start_copy_dev, void* stream) {
+    if (!ctx || !desc_dev || n_epochs < 1 || n_epochs > ctx->E) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_chain_handoff_device: bad argument", cudaSuccess);
+    if (ctx->cfg.carrier_mode != GPSIQ_CARRIER_FLOAT || ctx->cfg.reserved[0] != 0)
+        return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_chain_handoff_device: float carrier with the parallel scan only", cudaSuccess);
+    if ((recv_seq && !ctx->d_mbox) || (send_seq && !ctx->d_mbox_peer))
+        return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_chain_handoff_device: no mailbox (gpsiq_mailbox_create / _open first)", cudaSuccess);
+    CU(cudaSetDevice(ctx->cfg.device));
+    Handoff h;
+    memset(&h, 0, sizeof h);
+    if (recv_seq) {
+        h.in_flag = (const unsigned long long*) (ctx->d_mbox + MBOX_FLAG);
+        h.in_seq = recv_seq;
+        h.in_slot = (const double*) (ctx->d_mbox + (recv_seq & 1) * MBOX_SLOT);
+    }
+    if (send_seq) {
+        h.out_slot = (double*) (ctx->d_mbox_peer + (send_seq & 1) * MBOX_SLOT);
+        h.out_flag = (unsigned long long*) (ctx->d_mbox_peer + MBOX_FLAG);
+        h.out_seq = send_seq;
+        h.counter = (unsigned int*) (ctx->d_mbox + MBOX_COUNTER);
+    }
+    h.start_copy = start_copy_dev;
+    h.err = ctx->d_err;
+    ctx->handoff = h;
+    const int rc = enqueue_chain(ctx, desc_dev, n_epochs, (cudaStream_t) stream);
+    memset(&ctx->handoff, 0, sizeof ctx->handoff);
+    return rc;
 }
 
 // wait until the own mailbox's flag >= seq, then slot (seq & 1) -> carrier state (the estimate is not touched)
 int gpsiq_mailbox_recv(gpsiq_ctx* ctx, uint64_t seq, void* stream) {
     if (!ctx || !ctx->d_mbox) return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_mailbox_recv: no mailbox", cudaSuccess);
     CU(cudaSetDevice(ctx->cfg.device));
+    trace_mark(ctx, (cudaStream_t) stream, "mbox_recv(wait enqueued behind this)");
     const unsigned int flags = CU_STREAM_WAIT_VALUE_GEQ | (ctx->mbox_flush ? CU_STREAM_WAIT_VALUE_FLUSH : 0);
     const CUresult r = ((mbox_fn64) ctx->fn_wait64)((CUstream) stream, (CUdeviceptr) (ctx->d_mbox + MBOX_FLAG), seq, flags);
     if (r != CUDA_SUCCESS) return fail(ctx, GPSIQ_ERR_CUDA, "gpsiq_mailbox_recv: cuStreamWaitValue64 failed", cudaSuccess);
+    trace_mark(ctx, (cudaStream_t) stream, "mbox_recv(flag seen)");
     CU(cudaMemcpyAsync(ctx->d_carr_state, ctx->d_mbox + (seq & 1) * MBOX_SLOT, ctx->C * sizeof(double),
                        cudaMemcpyDeviceToDevice, (cudaStream_t) stream));
+    trace_mark(ctx, (cudaStream_t) stream, "mbox_recv(copied)");
     return GPSIQ_OK;
 }
 
@@ -2496,7 +2595,8 @@ int gpsiq_trace_dump(gpsiq_ctx* ctx, int reset) {
     for (int i = 0; i < ctx->trace_n; i++) {
         float t = 0.f;
         cudaEventElapsedTime(&t, ctx->trace[0].ev, ctx->trace[i].ev);
-        fprintf(stderr, "trace dev %d %9.3f ms  stream %d  %s\n", ctx->cfg.device, t, ctx->trace[i].stream_id, ctx->trace[i].label);
+        fprintf(stderr, "trace dev %d %9.3f ms  stream %d  %s  (enqueued by the host at %.3f ms)\n", ctx->cfg.device, t,
+                ctx->trace[i].stream_id, ctx->trace[i].label, ctx->trace[i].host_ms - ctx->trace[0].host_ms);
     }
     if (reset) ctx->trace_n = 0;
     return GPSIQ_OK;

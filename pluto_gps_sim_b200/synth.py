@@ -251,6 +251,11 @@ class Synthesizer:
     def mailbox_send(self, seq, stream_ptr=None):
         capi.check(capi.lib.gpsiq_mailbox_send(self._ctx, int(seq), stream_ptr), self._ctx)
 
+    def chain_handoff_device(self, desc_dev_ptr, n_epochs, recv_seq, send_seq, start_copy_ptr=None, stream_ptr=None):
+        """gpsiq_chain_handoff_device: [wait for message recv_seq] -> chain -> [send message send_seq], one kernel."""
+        capi.check(capi.lib.gpsiq_chain_handoff_device(self._ctx, desc_dev_ptr, n_epochs, int(recv_seq), int(send_seq),
+                                                       start_copy_ptr, stream_ptr), self._ctx)
+
     def mailbox_recv(self, seq, stream_ptr=None):
         capi.check(capi.lib.gpsiq_mailbox_recv(self._ctx, int(seq), stream_ptr), self._ctx)
 

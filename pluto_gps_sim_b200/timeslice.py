@@ -31,6 +31,7 @@ serial scan inside `chain`, it never changes a sample.
 an oracle-backed stand-in in the gloo/CPU tests of this logic.
 """
 import contextlib
+import os
 
 import torch
 import torch.distributed as dist
@@ -171,6 +172,11 @@ class GpuSliceEngine:
             return False
         return True
 
+    def chain_handoff(self, desc_dev, n_epochs, recv_seq, send_seq):
+        """The hop as ONE kernel (gpsiq_chain_handoff_device): wait for message recv_seq (0: none) in the own mailbox,
+        chain, end phases as message send_seq (0: none) into the next rank's.  self.phase <- the exact start phases."""
+        self.s.chain_handoff_device(desc_dev.data_ptr(), n_epochs, recv_seq, send_seq, self.phase.data_ptr(), self._stream())
+
     def handoff_send(self, seq):       # engine state -> next rank's mailbox
         self.s.mailbox_send(seq, self._stream())
 
@@ -212,6 +218,11 @@ class TimeSliceRunner:
         # all ranks hold the phase at the start of the next step).  SURVEY 8e: "truly parallel".
         self.prefix = handoff == "prefix"
         self.pipelined = bool(pipelined) and not self.prefix and self.world > 1
+        # experiments: GPSIQ_TS_LOOKAHEAD=0 ignores next_desc, GPSIQ_TS_SIDE=0 keeps the look-ahead on the scan stream
+        self.use_lookahead = os.environ.get("GPSIQ_TS_LOOKAHEAD", "1") != "0"
+        self.use_side = os.environ.get("GPSIQ_TS_SIDE", "1") != "0"
+        # GPSIQ_HANDOFF_FUSED=0: the hop as stream operations (wait value, copies, chain kernel, copy, write value)
+        self.fused = self.mailbox and os.environ.get("GPSIQ_HANDOFF_FUSED", "1") != "0"
         self.next_adv = None           # advances of the NEXT step's slices, all-gathered one step ahead (pipelined)
         self.next_desc = None          # ... and that slice's device descriptors (host descriptors are uploaded once)
 
@@ -281,6 +292,11 @@ class TimeSliceRunner:
                     eng.apply_bias()
             self.prev_adv = adv_all
         eng.speculate(desc, n_epochs)
+        if n > 1 and self.mailbox and self.fused and hasattr(eng, "chain_handoff"):   # the hop as one kernel
+            eng.chain_handoff(desc, n_epochs, self.step_index + 1 if r > 0 else 0, self.step_index + 1)
+            if r > 0 and hasattr(eng, "update_bias"):
+                eng.update_bias()
+            return
         if n > 1 and r > 0:
             if self.mailbox:
                 eng.handoff_recv(self.step_index + 1)
@@ -314,7 +330,7 @@ class TimeSliceRunner:
         eng, r, n, k = self.engine, self.rank, self.world, self.step_index
         if self.next_adv is not None:                           # prepared and gathered during the previous step
             adv_all, self.next_adv, self.next_desc = self.next_adv, None, None
-            if hasattr(eng, "wait_prep"):
+            if hasattr(eng, "wait_prep") and self.use_side:
                 eng.wait_prep()
         else:
             adv_all = self._prepare_and_gather(desc, n_epochs, k)
@@ -328,21 +344,25 @@ class TimeSliceRunner:
         self.prev_adv = adv_all
         eng.speculate(desc, n_epochs)
         # the next slice's prepare + all_gather: beside this slice's speculation and hand-off
-        if next_desc is not None:
-            side = eng.prep_context(k == 0) if hasattr(eng, "prep_context") else contextlib.nullcontext()
+        if next_desc is not None and self.use_lookahead:
+            side = eng.prep_context(k == 0) if (hasattr(eng, "prep_context") and self.use_side) else contextlib.nullcontext()
             with side:
                 if isinstance(next_desc, torch.Tensor) and next_desc.device.type == "cpu" and hasattr(eng, "upload"):
                     next_desc = eng.upload(next_desc, k + 1)
                 self.next_adv = self._prepare_and_gather(next_desc, next_epochs, k + 1)
                 self.next_desc = next_desc
-                if hasattr(eng, "prep_done"):
+                if hasattr(eng, "prep_done") and self.use_side:
                     eng.prep_done()
         # the ring: exact phases in, one head scan + translation (or the serial chain), exact phases out
         received = not (k == 0 and r == 0)                      # (the stream starts at rank 0 from re-seeded phases)
-        if received:
-            eng.handoff_recv(k + 1 if r > 0 else k)             # message number = sender's step index + 1
-        eng.chain(desc, n_epochs)
-        eng.handoff_send(k + 1)
+        recv_seq = (k + 1 if r > 0 else k) if received else 0   # message number = sender's step index + 1
+        if self.fused and hasattr(eng, "chain_handoff"):        # the whole hop is one kernel
+            eng.chain_handoff(desc, n_epochs, recv_seq, k + 1)
+        else:
+            if received:
+                eng.handoff_recv(recv_seq)
+            eng.chain(desc, n_epochs)
+            eng.handoff_send(k + 1)
         if received and hasattr(eng, "update_bias"):            # estimate feedback: off the ring's critical path
             eng.update_bias()
 

@@ -89,12 +89,15 @@ def test_two_gpu_time_slices_match_reference(tmp_path, deferred, handoff):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("slice_epochs,steps", [(16, 9), (70, 2)])
-def test_two_gpu_pipelined_time_slices_match_reference(tmp_path, slice_epochs, steps):
+@pytest.mark.parametrize("slice_epochs,steps,fused", [(16, 9, "1"), (70, 2, "1"), (16, 9, "0")])
+def test_two_gpu_pipelined_time_slices_match_reference(tmp_path, monkeypatch, slice_epochs, steps, fused):
     """TimeSliceRunner(pipelined=True) over the mailbox hand-off: no lockstep between the ranks (rank 0 speculates
     from an estimate, the next slice is prepared and its advances all-gathered one step ahead on a side stream), the
-    exact chain of a slice is one head scan + a translation (slices of one and of two groups of 64 epochs).  The
-    reference's per-epoch checksums, and the slice-level translation is what actually ran."""
+    exact chain of a slice is one head scan + a translation (slices of one and of two groups of 64 epochs).  The hop
+    is ONE kernel (gpsiq_chain_handoff_device: acquire-wait on the mailbox flag, chain, peer stores + release of the
+    next rank's flag) or -- GPSIQ_HANDOFF_FUSED=0 -- stream operations around the chain kernel.  The reference's
+    per-epoch checksums, and the slice-level translation is what actually ran."""
+    monkeypatch.setenv("GPSIQ_HANDOFF_FUSED", fused)
     world = 2
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
