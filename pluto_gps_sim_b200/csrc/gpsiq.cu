@@ -101,6 +101,7 @@ struct ScanSet {
     CarrSpec* d_specS; double* d_startS; SliceRes* d_sres;   // level 5: slice-level speculation, group entry phases, match result
     TieEvent* d_tieG; TieEvent* d_tieS;                      // first tie-wrap of every group- / slice-level trajectory
     double* d_start0;             // [C] exact phases at the first sample of the batch (once its chain has run)
+    double* d_rate_used;          // [C] the residual-rate estimate the batch was prepared with (k_bias_update)
     double* d_adv; double* d_carr_trace; uint32_t* d_ustart;
     LineEpoch* d_lrecs; uint32_t* d_elist; uint32_t* d_hazlist; int* d_line_counters; LinePatch* d_patches;
     int anchored;                 // the batch's tile anchors, safety check and patch list have been enqueued
@@ -499,13 +500,22 @@ k_slice_advance(const double* __restrict__ eadv, const double* __restrict__ eres
 // is integrated into rate[c], which k_prepare subtracts from later predictions: the predictor's systematic error
 // (~1e-14 cycles per epoch) otherwise grows along a batch until group-level speculations stop fitting.
 // Estimates only: never part of a result.
+// OPEN LOOP: what is measured is the residual of the UNCORRECTED closed form (the correction the batch was prepared with,
+// rate_used, is added back), and rate[c] is a filter of that measurement -- not an integrator of the corrected error.
+// Batches are prepared one or two batches ahead of their chain (pipelined submits, the pipelined time-slice runner);
+// an integrator with that much delay in its loop oscillates (gain 0.7, two batches of delay: unstable), a filter of an
+// open-loop measurement does not care.
 __global__ void k_bias_update(const double* __restrict__ adv, const double* __restrict__ start,
-                              const double* __restrict__ end, double* __restrict__ rate, int n_epochs, int C) {
+                              const double* __restrict__ end, double* __restrict__ rate,
+                              const double* __restrict__ rate_used, int n_epochs, int C) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C || adv[C + c] != 0.0) return;  // re-seeded inside the batch: adv is an absolute phase
     double err = adv[c] - (end[c] - start[c]);
     err -= rint(err);
-    if (fabs(err) < 1e-8) rate[c] += 0.7 * err / (double) n_epochs;
+    if (fabs(err) < 1e-8) {
+        const double raw = err / (double) n_epochs + rate_used[c];   // residual per epoch of the closed form itself
+        rate[c] += 0.9 * (raw - rate[c]);   // (the measurement is exact arithmetic over the whole batch: little to smooth)
+    }
 }
 
 // est = fold(est, adv): est <- adv (absolute) or frac(est + adv)
@@ -1336,6 +1346,8 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
             CU(cudaMalloc(&ss.d_sres, (size_t) ctx->C * sizeof(SliceRes)));
             CU(cudaMemset(ss.d_sres, 0, (size_t) ctx->C * sizeof(SliceRes)));
             CU(cudaMalloc(&ss.d_start0, ctx->C * sizeof(double)));
+            CU(cudaMalloc(&ss.d_rate_used, ctx->C * sizeof(double)));
+            CU(cudaMemset(ss.d_rate_used, 0, ctx->C * sizeof(double)));
             CU(cudaMalloc(&ss.d_tieG, ng * ctx->C * 2 * sizeof(TieEvent)));
             CU(cudaMalloc(&ss.d_tieS, (size_t) ctx->C * 2 * sizeof(TieEvent)));
         }
@@ -1507,7 +1519,7 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
         cudaFree(ss.d_specE); cudaFree(ss.d_cinfo); cudaFree(ss.d_info); cudaFree(ss.d_adv); cudaFree(ss.d_carr_trace);
         cudaFree(ss.d_specG); cudaFree(ss.d_ginfo); cudaFree(ss.d_traceG); cudaFree(ss.d_ustart);
         cudaFree(ss.d_specS); cudaFree(ss.d_startS); cudaFree(ss.d_sres); cudaFree(ss.d_start0);
-        cudaFree(ss.d_tieG); cudaFree(ss.d_tieS);
+        cudaFree(ss.d_tieG); cudaFree(ss.d_tieS); cudaFree(ss.d_rate_used);
         if (ss.scan_done) cudaEventDestroy(ss.scan_done);
         if (ss.render_done) cudaEventDestroy(ss.render_done);
         if (ss.spec_done) cudaEventDestroy(ss.spec_done);
@@ -1574,8 +1586,10 @@ static int enqueue_prepare(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int 
     set.seq = ctx->seq++;
     if (ctx->ev_count < TIMING_RING && st != ctx->scan_stream) CU(cudaEventRecord(ctx->ev[ctx->ev_count][0], st));
     CU(cudaMemsetAsync(ctx->d_flags, 0, 2 * (size_t) ctx->E * sizeof(int), st));
+    // the batch is prepared with a snapshot of the residual-rate estimate (k_bias_update needs to know which)
+    CU(cudaMemcpyAsync(set.d_rate_used, ctx->d_bias_rate, C * sizeof(double), cudaMemcpyDeviceToDevice, st));
     k_prepare<<<EC, 128, 0, st>>>(desc_dev, ctx->d_lut, ctx->d_lutp, ctx->d_drift, ctx->d_flags,
-                                  ctx->d_flags + ctx->E, C, N, ctx->cfg.carrier_mode, ctx->d_bias_rate,
+                                  ctx->d_flags + ctx->E, C, N, ctx->cfg.carrier_mode, set.d_rate_used,
                                   ctx->d_drift + 3 * (size_t) ctx->E * C, ctx->d_err);
     ctx->launches += 1;
     trace_mark(ctx, st, "k_prepare");
@@ -1717,7 +1731,7 @@ static int enqueue_chain(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_
             trace_mark(ctx, st2, "k_carr_final_groups");
             ctx->launches += 1;
         }
-        k_bias_update<<<1, 32, 0, st2>>>(ctx->d_adv, ctx->d_start0, set.d_exact_end, ctx->d_bias_rate, n_epochs, C);
+        k_bias_update<<<1, 32, 0, st2>>>(ctx->d_adv, ctx->d_start0, set.d_exact_end, ctx->d_bias_rate, set.d_rate_used, n_epochs, C);
         ctx->launches += 1;
     }
     if (!ctx->use_line) CU(cudaStreamWaitEvent(st2, ctx->ev_code2, 0));  // scan_done covers the code scan on the side stream too
