@@ -255,6 +255,13 @@ int gpsiq_estimate_anchor_device(gpsiq_ctx *ctx, void *cuda_stream);
  * 0 (default): one CTA per unit.  A cap just below 2 x the SM count leaves a few half-empty SMs to the small
  * latency-bound kernels that run beside the sample kernel (the next batch's chain, a ring hop). */
 #define GPSIQ_OPT_LINE_GRID_CAP 3
+/* Time-sliced runs whose speculation must not wait for the ring: the running start-phase estimate is no longer
+ * re-anchored on the exact phase by the chain.  After every gpsiq_speculate_device it becomes the END of that
+ * batch's slice-level speculative trajectory (an exact advance from the estimated start), the caller folds in the
+ * advances of the slices other GPUs own (gpsiq_estimate_fold_device), and the accumulated error is corrected open
+ * loop from what each exact chain measures later (csrc/gpsiq.cu: k_est_open_loop).  The chain of a batch may then run
+ * on another stream, any time after its speculation. */
+#define GPSIQ_OPT_FREE_RUNNING_ESTIMATE 4
 int gpsiq_set_option(gpsiq_ctx *ctx, int option, int value);
 int gpsiq_estimate_to_device(gpsiq_ctx *ctx, double *dst_dev, void *cuda_stream);
 /* SM-free hand-off of the carrier state between the GPUs of one node (time-sliced runs; replaces the NCCL

@@ -21,7 +21,7 @@ MAX_LOOKAHEAD = 3   # batches gpsiq_submit* may run ahead of the one being fetch
 LINE_DBG_FORCE_CHUNK, LINE_DBG_FORCE_TILE, LINE_DBG_PERTURB = 1, 2, 4
 MAX_CHAN = 32
 NCO_CODE, NCO_CARRIER = 0, 1
-OPT_CHAIN_KEEPS_ESTIMATE, OPT_RENDER_AFTER_NEXT_CHAIN = 1, 2
+OPT_CHAIN_KEEPS_ESTIMATE, OPT_RENDER_AFTER_NEXT_CHAIN, OPT_LINE_GRID_CAP, OPT_FREE_RUNNING_ESTIMATE = 1, 2, 3, 4
 
 # numpy view of gpsiq_chan_desc (64 bytes, include/gpsiq.h)
 DESC_DTYPE = np.dtype(

@@ -102,6 +102,7 @@ struct ScanSet {
     TieEvent* d_tieG; TieEvent* d_tieS;                      // first tie-wrap of every group- / slice-level trajectory
     double* d_start0;             // [C] exact phases at the first sample of the batch (once its chain has run)
     double* d_rate_used;          // [C] the residual-rate estimate the batch was prepared with (k_bias_update)
+    double* d_ccum_used;          // [C] free-running estimates: the total correction the batch's start estimate had received
     double* d_adv; double* d_carr_trace; uint32_t* d_ustart;
     LineEpoch* d_lrecs; uint32_t* d_elist; uint32_t* d_hazlist; int* d_line_counters; LinePatch* d_patches;
     int anchored;                 // the batch's tile anchors, safety check and patch list have been enqueued
@@ -149,6 +150,9 @@ struct gpsiq_ctx {
     double* d_carr_start; // [C] exact phases at the start of the batch being chained
     int chain_keeps_estimate;  // GPSIQ_OPT_CHAIN_KEEPS_ESTIMATE
     Handoff handoff;           // what the next enqueue_chain fuses into its kernel (gpsiq_chain_handoff_device); cleared after use
+    int free_running;          // GPSIQ_OPT_FREE_RUNNING_ESTIMATE
+    double* d_est_meas;        // [C] latest open-loop measurement of the estimate's accumulated error
+    double* d_est_ccum;        // [C] total correction the running estimate has received
     int slice_spec;            // level 5 (slice-level speculation: one head scan per batch on the chain's critical path); GPSIQ_SLICE_SPEC=0 turns it off
     int render_after_next_chain;  // GPSIQ_OPT_RENDER_AFTER_NEXT_CHAIN
     // SM-free carrier hand-off between the GPUs of one node (gpsiq_mailbox_*)
@@ -536,6 +540,37 @@ __global__ void k_est_correct(double* __restrict__ est, const double* __restrict
     est[c] = frac01(est[c] - gain * diff);
 }
 
+// ---- free-running start-phase estimates (GPSIQ_OPT_FREE_RUNNING_ESTIMATE; time-sliced runs) ----------------------
+// The speculation of a rank's NEXT slice must not wait for the exact chain of this one (the chain is a hop of the
+// inter-GPU ring).  So the estimate runs on its own: after a slice has been speculated it becomes the END of that
+// slice's own slice-level speculative trajectory (k_est_from_slice: an exact advance from the estimated start), the
+// caller folds in the closed-form advances of the slices other GPUs own, and the error this accumulates is taken out
+// OPEN LOOP: every exact chain measures eps = (estimate its slice started from) - (exact start phase), adds back the
+// total correction that estimate had already received (ccum_used) and publishes M = eps + ccum_used -- a measurement of
+// the raw accumulated error that does not depend on what was corrected when; the next speculation subtracts
+// (M - ccum) and sets ccum = M.  No integrator, so the two-slice delay between measurement and use cannot oscillate.
+// Estimates only: never part of a result.
+__global__ void k_est_open_loop(double* __restrict__ est, const double* __restrict__ meas, double* __restrict__ ccum,
+                                double* __restrict__ ccum_used, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double m = meas[c];
+    est[c] = frac01(est[c] - (m - ccum[c]));
+    ccum[c] = m;
+    ccum_used[c] = m;
+}
+
+// est <- the end of the slice-level speculative trajectory of the batch just speculated (variant 0; a parity shift of
+// 2^-53 does not matter to an estimate), or -- if that chain did not run to the end -- its start advanced in closed form
+__global__ void k_est_from_slice(double* __restrict__ est, const CarrSpec* __restrict__ specS,
+                                 const double* __restrict__ startS, const double* __restrict__ adv, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const CarrSpec s0 = specS[(size_t) c * 2];
+    if (s0.pad & 2) est[c] = s0.xend;                                  // the chain ran through every group
+    else est[c] = frac01((adv[C + c] != 0.0) ? adv[c] : startS[c] + adv[c]);
+}
+
 // Estimated phase at the start of every epoch of the batch, from the context's batch-start estimate.
 __global__ void __launch_bounds__(32)
 k_epoch_estimates(const double* __restrict__ eadv, const double* __restrict__ ereset,
@@ -765,7 +800,8 @@ k_carr_slice(const gpsiq_chan_desc* __restrict__ desc, const CarrSpec* __restric
     }
     if (lane == 0) {
         CarrSpec out;
-        out.xw1 = tr.xw1; out.xend = x; out.n1 = tr.pos; out.pad = any_active ? 0 : 1;
+        out.xw1 = tr.xw1; out.xend = x; out.n1 = tr.pos;
+        out.pad = (any_active ? 0 : 1) | (tr.usable ? 2 : 0);   // bit 0: slot inactive in the whole batch; bit 1: the chain ran to the end
         out.margin = (tr.pos >= 0 && tr.usable) ? tr.margin : -1.0;
         specS[(size_t) c * 2 + V] = out;
         tieS[(size_t) c * 2 + V] = tr.tie;
@@ -799,7 +835,8 @@ k_carr_final(const gpsiq_chan_desc* __restrict__ desc,
              int* __restrict__ fallbacks, const TieEvent* __restrict__ tieG, const CarrSpec* __restrict__ specS,
              const TieEvent* __restrict__ tieS, SliceRes* __restrict__ sres, unsigned long long* __restrict__ slice_stats,
              double* __restrict__ start_out, double* __restrict__ end_out, double* __restrict__ est_out,
-             const Handoff h, int E, int C, int N, int T, int ntiles) {
+             const Handoff h, const double* __restrict__ est_start, const double* __restrict__ ccum_used,
+             double* __restrict__ est_meas, int E, int C, int N, int T, int ntiles) {
     __shared__ GroupEpoch s_ge[GROUP_EPOCHS];
     const int c = blockIdx.x, lane = threadIdx.x;
     if (c >= C) return;
@@ -821,13 +858,21 @@ k_carr_final(const gpsiq_chan_desc* __restrict__ desc,
         x = carr_state[c];
     }
     const double x_first = x;
-    if (lane == 0) { start_out[c] = x; if (h.start_copy) h.start_copy[c] = x; }
+    if (lane == 0) {
+        start_out[c] = x;
+        if (h.start_copy) h.start_copy[c] = x;
+        if (est_meas) {   // free-running estimates: the raw accumulated error of the estimate this batch started from
+            double eps = est_start[c] - x;
+            eps -= rint(eps);
+            if (fabs(eps) < 1e-8) est_meas[c] = eps + ccum_used[c];
+        }
+    }
     SliceRes res;
     res.diff = 0.0; res.diff2 = 0.0; res.variant = 0; res.how = 0; res.tie_g = 0x7fffffff; res.pad = 0;
     if (specS) {
         const CarrSpec sS0 = specS[(size_t) c * 2], sS1 = specS[(size_t) c * 2 + 1];
         const TieEvent tS0 = tieS[(size_t) c * 2], tS1 = tieS[(size_t) c * 2 + 1];
-        if (sS0.pad == 1) {
+        if (sS0.pad & 1) {
             res.how = 2;                                            // nothing to chain: the phase passes through
         } else if (sS0.margin > 0.0) {
             const int count = min(GROUP_EPOCHS, E);
@@ -1347,6 +1392,8 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
             CU(cudaMemset(ss.d_sres, 0, (size_t) ctx->C * sizeof(SliceRes)));
             CU(cudaMalloc(&ss.d_start0, ctx->C * sizeof(double)));
             CU(cudaMalloc(&ss.d_rate_used, ctx->C * sizeof(double)));
+            CU(cudaMalloc(&ss.d_ccum_used, ctx->C * sizeof(double)));
+            CU(cudaMemset(ss.d_ccum_used, 0, ctx->C * sizeof(double)));
             CU(cudaMemset(ss.d_rate_used, 0, ctx->C * sizeof(double)));
             CU(cudaMalloc(&ss.d_tieG, ng * ctx->C * 2 * sizeof(TieEvent)));
             CU(cudaMalloc(&ss.d_tieS, (size_t) ctx->C * 2 * sizeof(TieEvent)));
@@ -1379,6 +1426,10 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
     }
     CU(cudaMalloc(&ctx->d_fallbacks, sizeof(int)));
     CU(cudaMemset(ctx->d_fallbacks, 0, sizeof(int)));
+    CU(cudaMalloc(&ctx->d_est_meas, ctx->C * sizeof(double)));
+    CU(cudaMemset(ctx->d_est_meas, 0, ctx->C * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_est_ccum, ctx->C * sizeof(double)));
+    CU(cudaMemset(ctx->d_est_ccum, 0, ctx->C * sizeof(double)));
     CU(cudaMalloc(&ctx->d_slice_stats, 2 * sizeof(unsigned long long)));
     CU(cudaMemset(ctx->d_slice_stats, 0, 2 * sizeof(unsigned long long)));
     CU(cudaMalloc(&ctx->d_carr_state, ctx->C * sizeof(double)));
@@ -1411,7 +1462,7 @@ static int create_body(gpsiq_ctx* ctx, const gpsiq_config* cfg, const cudaDevice
         // to leave.  No scan kernel keeps per-thread tables any more (nco_scan.cuh: binade_delta), so EVERY kernel
         // of the pipeline asks for this split and any of them can be placed beside the sample kernel.
 #define CARVE(k) CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared))
-        CARVE(k_synth_line); CARVE(k_carr_stitch); CARVE(k_carr_group); CARVE(k_carr_final); CARVE(k_carr_slice); CARVE(k_carr_final_groups); CARVE(k_line_apply);
+        CARVE(k_synth_line); CARVE(k_carr_stitch); CARVE(k_carr_group); CARVE(k_carr_final); CARVE(k_carr_slice); CARVE(k_carr_final_groups); CARVE(k_est_open_loop); CARVE(k_est_from_slice); CARVE(k_line_apply);
         CARVE(k_synth_lanes);
         CARVE(k_carr_speculate); CARVE(k_scan_code); CARVE(k_prepare); CARVE(k_line_anchor); CARVE(k_line_patch);
         CARVE(k_epoch_estimates); CARVE(k_slice_advance); CARVE(k_est_fold); CARVE(k_est_correct); CARVE(k_int_carrier);
@@ -1519,7 +1570,7 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
         cudaFree(ss.d_specE); cudaFree(ss.d_cinfo); cudaFree(ss.d_info); cudaFree(ss.d_adv); cudaFree(ss.d_carr_trace);
         cudaFree(ss.d_specG); cudaFree(ss.d_ginfo); cudaFree(ss.d_traceG); cudaFree(ss.d_ustart);
         cudaFree(ss.d_specS); cudaFree(ss.d_startS); cudaFree(ss.d_sres); cudaFree(ss.d_start0);
-        cudaFree(ss.d_tieG); cudaFree(ss.d_tieS); cudaFree(ss.d_rate_used);
+        cudaFree(ss.d_tieG); cudaFree(ss.d_tieS); cudaFree(ss.d_rate_used); cudaFree(ss.d_ccum_used);
         if (ss.scan_done) cudaEventDestroy(ss.scan_done);
         if (ss.render_done) cudaEventDestroy(ss.render_done);
         if (ss.spec_done) cudaEventDestroy(ss.spec_done);
@@ -1539,7 +1590,7 @@ void gpsiq_destroy(gpsiq_ctx* ctx) {
     if (ctx->d_mbox_peer) cudaIpcCloseMemHandle(ctx->d_mbox_peer);
     cudaFree(ctx->d_mbox);
     cudaFree(ctx->d_fallbacks); cudaFree(ctx->d_carr_state); cudaFree(ctx->d_est_state); cudaFree(ctx->d_ca);
-    cudaFree(ctx->d_iq); cudaFree(ctx->d_iq2); cudaFree(ctx->d_sums); cudaFree(ctx->d_err); cudaFree(ctx->d_slice_stats);
+    cudaFree(ctx->d_iq); cudaFree(ctx->d_iq2); cudaFree(ctx->d_sums); cudaFree(ctx->d_err); cudaFree(ctx->d_slice_stats); cudaFree(ctx->d_est_meas); cudaFree(ctx->d_est_ccum);
 #define DROP_STREAM(s) do { if (s) cudaStreamDestroy(s); } while (0)
 #define DROP_EVENT(e) do { if (e) cudaEventDestroy(e); } while (0)
     DROP_STREAM(ctx->scan_stream); DROP_STREAM(ctx->aux2_stream); DROP_EVENT(ctx->ev_fork2); DROP_EVENT(ctx->ev_code2);
@@ -1639,6 +1690,11 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
         double* ereset = ctx->d_drift + (size_t) EC;      // k_prepare wrote it at [gridDim.x + ec] with gridDim.x = EC
         double* est_epoch = ctx->d_drift + 2 * ECmax;
         trace_mark(ctx, st, "(speculate begin)");
+        const bool free_run = ctx->free_running && ctx->slice_spec && !own_est;
+        if (free_run) {
+            k_est_open_loop<<<1, 32, 0, st>>>(est, ctx->d_est_meas, ctx->d_est_ccum, sset.d_ccum_used, C);
+            ctx->launches += 1;
+        }
         k_epoch_estimates<<<C, 32, 0, st>>>(ctx->d_drift + 3 * ECmax, ereset, est, est_epoch, n_epochs, C);
         trace_mark(ctx, st, "k_epoch_estimates");
         const int chains = EC * ctx->J;
@@ -1665,7 +1721,8 @@ static int enqueue_speculate(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, in
             trace_mark(ctx, st, "k_carr_slice");
             ctx->launches += 1;
         }
-        if (!own_est) { k_est_fold<<<1, 32, 0, st>>>(ctx->d_est_state, ctx->d_adv, C); ctx->launches += 1; }
+        if (free_run) { k_est_from_slice<<<1, 32, 0, st>>>(ctx->d_est_state, ctx->d_specS, ctx->d_startS, ctx->d_adv, C); ctx->launches += 1; }
+        else if (!own_est) { k_est_fold<<<1, 32, 0, st>>>(ctx->d_est_state, ctx->d_adv, C); ctx->launches += 1; }
         ctx->launches += 4;
     }
     CU(cudaEventRecord(sset.spec_all, st));
@@ -1694,8 +1751,10 @@ static int enqueue_chain(gpsiq_ctx* ctx, const gpsiq_chan_desc* desc_dev, int n_
                                        ctx->d_info, (size_t) ctx->E * C, ctx->d_traceG, ctx->d_carr_state, ctx->d_carr_trace,
                                        ctx->d_ginfo, ctx->d_fallbacks, ctx->d_tieG, ctx->slice_spec ? ctx->d_specS : NULL,
                                        ctx->d_tieS, ctx->d_sres, ctx->d_slice_stats,
-                                       ctx->d_start0, wset.d_exact_end, ctx->chain_keeps_estimate ? NULL : ctx->d_est_state,
-                                       ctx->handoff, n_epochs, C, N, T, ntiles);
+                                       ctx->d_start0, wset.d_exact_end,
+                                       (ctx->chain_keeps_estimate || ctx->free_running) ? NULL : ctx->d_est_state,
+                                       ctx->handoff, ctx->d_startS, wset.d_ccum_used,
+                                       (ctx->free_running && ctx->slice_spec) ? ctx->d_est_meas : NULL, n_epochs, C, N, T, ntiles);
         memset(&ctx->handoff, 0, sizeof ctx->handoff);
         float_chain = true;
     } else if (ctx->cfg.carrier_mode == GPSIQ_CARRIER_INT32) {  // closed form: one prefix sum over the epochs
@@ -2289,6 +2348,7 @@ int gpsiq_set_option(gpsiq_ctx* ctx, int option, int value) {
     if (!ctx) return GPSIQ_ERR_ARG;
     if (option == GPSIQ_OPT_CHAIN_KEEPS_ESTIMATE) { ctx->chain_keeps_estimate = value != 0; return GPSIQ_OK; }
     if (option == GPSIQ_OPT_RENDER_AFTER_NEXT_CHAIN) { ctx->render_after_next_chain = value != 0; return GPSIQ_OK; }
+    if (option == GPSIQ_OPT_FREE_RUNNING_ESTIMATE) { ctx->free_running = value != 0; return GPSIQ_OK; }
     if (option == GPSIQ_OPT_LINE_GRID_CAP) { ctx->line_grid_cap = value > 0 ? value : 0; return GPSIQ_OK; }
     return fail(ctx, GPSIQ_ERR_ARG, "gpsiq_set_option: unknown option", cudaSuccess);
 }

@@ -60,6 +60,18 @@ class GpuSliceEngine:
         # speculation and hand-off (nothing in them depends on the ring)
         self.prep_stream = torch.cuda.Stream(priority=-1)
         self.prep_event = torch.cuda.Event()
+        # free-running runner: the hop (one fused kernel per slice) has a stream of its own, so that the speculation of
+        # the next slice does not queue behind a hop that is still waiting for the previous GPU
+        self.hop_stream = torch.cuda.Stream(priority=-1)
+
+    def set_free_running(self, on=True):
+        """GPSIQ_OPT_FREE_RUNNING_ESTIMATE: the start-phase estimate follows the slice-level speculation instead of
+        being re-anchored by the exact chain (the library corrects its accumulated error open loop)."""
+        from . import capi
+        self.s.set_option(capi.OPT_FREE_RUNNING_ESTIMATE, 1 if on else 0)
+
+    def hop_context(self):
+        return torch.cuda.stream(self.hop_stream)
 
     def prep_context(self, first=False):
         """Stream context for the next slice's prepare + all_gather.  Nothing in them depends on what the scan stream
@@ -218,6 +230,16 @@ class TimeSliceRunner:
         # all ranks hold the phase at the start of the next step).  SURVEY 8e: "truly parallel".
         self.prefix = handoff == "prefix"
         self.pipelined = bool(pipelined) and not self.prefix and self.world > 1
+        # free-running (pipelined runners over the fused mailbox hop; GPSIQ_TS_FREE=0 turns it off): a rank's
+        # speculation of slice k+1 does not wait for its hop of slice k.  The estimate it starts from is the end of
+        # slice k's own slice-level speculative trajectory + the closed-form advances of the foreign slices in between,
+        # corrected open loop by the library; the hop runs on its own stream whenever the previous GPU's phases arrive.
+        # The ring then has slack: a late hop delays nobody's speculation, only (at worst) a render.
+        self.free_running = (self.pipelined and self.mailbox and hasattr(engine, "set_free_running")
+                             and os.environ.get("GPSIQ_TS_FREE", "1") != "0"
+                             and os.environ.get("GPSIQ_HANDOFF_FUSED", "1") != "0")
+        if self.free_running:
+            engine.set_free_running(True)
         # experiments: GPSIQ_TS_LOOKAHEAD=0 ignores next_desc, GPSIQ_TS_SIDE=0 keeps the look-ahead on the scan stream
         self.use_lookahead = os.environ.get("GPSIQ_TS_LOOKAHEAD", "1") != "0"
         self.use_side = os.environ.get("GPSIQ_TS_SIDE", "1") != "0"
@@ -339,7 +361,7 @@ class TimeSliceRunner:
         skipped = ([] if self.prev_adv is None else self.prev_adv[r + 1:]) + adv_all[:r]
         for a in skipped:
             eng.estimate_fold(a)
-        if hasattr(eng, "apply_bias"):
+        if hasattr(eng, "apply_bias") and not self.free_running:
             eng.apply_bias()
         self.prev_adv = adv_all
         eng.speculate(desc, n_epochs)
@@ -356,6 +378,10 @@ class TimeSliceRunner:
         # the ring: exact phases in, one head scan + translation (or the serial chain), exact phases out
         received = not (k == 0 and r == 0)                      # (the stream starts at rank 0 from re-seeded phases)
         recv_seq = (k + 1 if r > 0 else k) if received else 0   # message number = sender's step index + 1
+        if self.free_running:                                   # ... on its own stream, behind this slice's speculation
+            with eng.hop_context():
+                eng.chain_handoff(desc, n_epochs, recv_seq, k + 1)
+            return
         if self.fused and hasattr(eng, "chain_handoff"):        # the whole hop is one kernel
             eng.chain_handoff(desc, n_epochs, recv_seq, k + 1)
         else:
@@ -374,7 +400,8 @@ class TimeSliceRunner:
             self.pending = None
         if self.world > 1 and self.rank == 0 and self.step_index > 0 and not self.prefix:
             eng = self.engine
-            ctx = eng.scan_context() if hasattr(eng, "scan_context") else contextlib.nullcontext()
+            ctx = (eng.hop_context() if getattr(self, "free_running", False) else
+                   eng.scan_context() if hasattr(eng, "scan_context") else contextlib.nullcontext())
             with ctx:
                 if self.mailbox:
                     eng.handoff_recv(self.step_index)
