@@ -230,13 +230,15 @@ class TimeSliceRunner:
         # all ranks hold the phase at the start of the next step).  SURVEY 8e: "truly parallel".
         self.prefix = handoff == "prefix"
         self.pipelined = bool(pipelined) and not self.prefix and self.world > 1
-        # free-running (pipelined runners over the fused mailbox hop; GPSIQ_TS_FREE=0 turns it off): a rank's
+        # free-running (GPSIQ_TS_FREE=1; pipelined runners over the fused mailbox hop; NOT the default): a rank's
         # speculation of slice k+1 does not wait for its hop of slice k.  The estimate it starts from is the end of
         # slice k's own slice-level speculative trajectory + the closed-form advances of the foreign slices in between,
         # corrected open loop by the library; the hop runs on its own stream whenever the previous GPU's phases arrive.
-        # The ring then has slack: a late hop delays nobody's speculation, only (at worst) a render.
+        # Measured at 2 GPUs (profiles/r02_y_*): parity-clean, but 2.25 ms per step against 2.07 -- the corrections
+        # (residual rate, accumulated estimate error) arrive two slices later, more slices are speculated from poor
+        # estimates at the start of a run, and each of those chains serially ON the ring.
         self.free_running = (self.pipelined and self.mailbox and hasattr(engine, "set_free_running")
-                             and os.environ.get("GPSIQ_TS_FREE", "1") != "0"
+                             and os.environ.get("GPSIQ_TS_FREE", "0") == "1"
                              and os.environ.get("GPSIQ_HANDOFF_FUSED", "1") != "0")
         if self.free_running:
             engine.set_free_running(True)
