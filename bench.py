@@ -349,6 +349,11 @@ def ours_arm(args):
         return Synthesizer(max_chan=C, max_epochs=E, device=local, kernel=args.kernel, tile_samples=args.tile,
                            carrier_mode=carrier_mode)
 
+    def use_pipelined(handoff):
+        if handoff != "mailbox" or args.lockstep:
+            return False
+        return True if args.pipelined else world <= 4
+
     def make_runner(synth):
         engine = GpuSliceEngine(synth)
         if carrier_mode == capi.CARRIER_INT32:
@@ -358,9 +363,13 @@ def ours_arm(args):
             if handoff == "mailbox" and not engine.mailbox_setup(rank, world):
                 handoff = "nccl"                              # decided collectively: every rank falls back alike
         # the mailbox hand-off never blocks the host, so the ranks need not run in lockstep: pipelined runner (rank 0
-        # speculates from an estimate too; the next slice is prepared and its advances all-gathered one step ahead)
-        pipelined = handoff == "mailbox" and not args.lockstep
-        return TimeSliceRunner(engine, rank, world, deferred_render=True, handoff=handoff, pipelined=pipelined), handoff
+        # speculates from an estimate too; the next slice is prepared and its advances all-gathered one step ahead).
+        # Measured on this pool's 8-GPU box (profiles/r02_v/x): 2.07 / 2.35 ms per step at 2 / 4 GPUs against 2.23 /
+        # 2.44 for the lockstep runner, but 3.71 against 3.53 at 8 (every rank's estimate then rests on seven closed-form
+        # advances, a slice speculated from a poor one chains serially on a ring that has no slack): pipelined up to
+        # 4 GPUs, lockstep beyond, unless forced either way.
+        return TimeSliceRunner(engine, rank, world, deferred_render=True, handoff=handoff,
+                               pipelined=use_pipelined(handoff)), handoff
 
     synth = make_synth()
     d_first = torch.from_numpy(first.view(np.uint8).reshape(-1)).cuda()
@@ -577,7 +586,7 @@ def ours_arm(args):
                        "kernel": args.kernel, "tile_samples": args.tile, "lookahead_batches": ahead if world == 1 else 1,
                        "carrier_scan_serial_fallbacks": fallbacks,
                        "slice_chains_translated": slice_translated, "slice_chains_serial": slice_serial,
-                       "runner": ("pipelined" if (world > 1 and handoff == "mailbox" and not args.lockstep) else
+                       "runner": ("pipelined" if (world > 1 and use_pipelined(handoff)) else
                                   "lockstep" if world > 1 else "submit/fetch"),
                        "carrier_scan_chains": (args.warmup + args.steps) * E * C,
                        "numa_bound_cpus": numa_cpus},
@@ -628,7 +637,9 @@ def main():
                     help="float: the shipped build (FLOAT_CARR_PHASE, plutogpssim.h:12); int32: the reference's integer "
                          "carrier NCO (its #else branches), closed form")
     ap.add_argument("--lockstep", action="store_true",
-                    help="N > 1: the round-1/2 runner (rank 0 waits for the ring before it speculates, advances gathered inside the step)")
+                    help="N > 1: force the lockstep runner (rank 0 waits for the ring before it speculates, advances gathered inside the step)")
+    ap.add_argument("--pipelined", action="store_true",
+                    help="N > 1: force the pipelined runner (default: pipelined up to 4 GPUs, lockstep beyond)")
     ap.add_argument("--handoff", choices=["nccl", "mailbox"], default=os.environ.get("GPSIQ_HANDOFF", "mailbox"),
                     help="float-carrier phase hand-off between time slices (N > 1): the SM-free peer-memory mailbox "
                          "(copy engine + stream memory operations; falls back to NCCL if unavailable), or NCCL send/recv")
