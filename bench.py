@@ -410,6 +410,7 @@ def ours_arm(args):
             runner.step(d_first if (i == 0 and rank == 0) else d_desc, E, d_out, next_desc=d_desc)
     barrier()
     l0 = synth.launch_count
+    fb0, sl0 = synth.carrier_fallbacks, synth.slice_stats   # (the device is idle here: reading the counters costs nothing)
     synth.timing_begin()
     sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -431,10 +432,12 @@ def ours_arm(args):
     kn, kms, kep = synth.timing_sample_kernel()
     fallbacks = synth.carrier_fallbacks
     synth.check_device()                                     # a kernel-flagged error (incl. the chain's self-check) ends the run
-    sl = torch.tensor([float(v) for v in synth.slice_stats], dtype=torch.float64, device="cuda")
+    sl1 = synth.slice_stats
+    sl = torch.tensor([float(sl1[0]), float(sl1[1]), float(sl1[0] - sl0[0]), float(sl1[1] - sl0[1]), float(fallbacks),
+                       float(fallbacks - fb0)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(sl, op=dist.ReduceOp.SUM)
-    slice_translated, slice_serial = int(sl[0]), int(sl[1])
+    slice_translated, slice_serial, slice_translated_timed, slice_serial_timed, fallbacks, fallbacks_timed = (int(v) for v in sl)
     t = torch.tensor([ms, float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
         tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -586,9 +589,14 @@ def ours_arm(args):
                        "kernel": args.kernel, "tile_samples": args.tile, "lookahead_batches": ahead if world == 1 else 1,
                        "carrier_scan_serial_fallbacks": fallbacks,
                        "slice_chains_translated": slice_translated, "slice_chains_serial": slice_serial,
+                       # the same counters over the timed region only (all ranks): what a poor start-phase estimate
+                       # cost INSIDE the measurement -- a serially chained slice or epoch sits on the inter-GPU ring
+                       "timed_region": {"slice_chains_translated": slice_translated_timed,
+                                        "slice_chains_serial": slice_serial_timed,
+                                        "carrier_scan_serial_fallbacks": fallbacks_timed},
                        "runner": ("pipelined" if (world > 1 and use_pipelined(handoff)) else
                                   "lockstep" if world > 1 else "submit/fetch"),
-                       "carrier_scan_chains": (args.warmup + args.steps) * E * C,
+                       "carrier_scan_chains": (args.warmup + args.steps) * E * C * world,
                        "numa_bound_cpus": numa_cpus},
             "e2e": {"value": round(e2e_value, 3), "unit": "Msamples/s", "h2d_bytes_per_step": nbytes_desc,
                     "d2h_bytes_per_step": samples_per_step * 4, "how": e2e_how},
