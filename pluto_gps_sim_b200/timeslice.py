@@ -127,6 +127,15 @@ class GpuSliceEngine:
     def estimate_anchor(self):         # estimate <- exact carrier state
         self.s.estimate_anchor_device(self._stream())
 
+    def estimate_from(self, phases):   # estimate <- max_chan phases in a device tensor (e.g. another rank's exact start)
+        self.s.estimate_from_device(phases.data_ptr(), self._stream())
+
+    def gather_payload(self):
+        """What a rank contributes to the per-step all_gather of the lockstep runner: its slice's closed-form advance
+        and flags (2 * max_chan) + the exact phases it last received (max_chan; rank 0's are the exact start of the
+        step, which every other rank anchors its estimate on)."""
+        return torch.cat([self.adv, self.phase])
+
     def speculate(self, desc_dev, n_epochs):
         self.s.speculate_device(desc_dev.data_ptr(), n_epochs, self._stream())
 
@@ -247,6 +256,7 @@ class TimeSliceRunner:
         self.use_side = os.environ.get("GPSIQ_TS_SIDE", "1") != "0"
         # GPSIQ_HANDOFF_FUSED=0: the hop as stream operations (wait value, copies, chain kernel, copy, write value)
         self.fused = self.mailbox and os.environ.get("GPSIQ_HANDOFF_FUSED", "1") != "0"
+        self.anchor0 = os.environ.get("GPSIQ_TS_ANCHOR0", "1") != "0"   # lockstep runner: estimates anchored on rank 0's exact start
         self.next_adv = None           # advances of the NEXT step's slices, all-gathered one step ahead (pipelined)
         self.next_desc = None          # ... and that slice's device descriptors (host descriptors are uploaded once)
 
@@ -306,10 +316,22 @@ class TimeSliceRunner:
             have_exact = True
         eng.prepare(desc, n_epochs)
         if n > 1:
-            adv_all = [torch.empty_like(eng.adv) for _ in range(n)]
-            dist.all_gather(adv_all, eng.adv)
-            if not have_exact:                                  # slices owned by other ranks since my last one
-                skipped = ([] if self.prev_adv is None else self.prev_adv[r + 1:]) + adv_all[:r]
+            # Rank 0 has just received the exact phases at the start of this step: it shares them with the advances, and
+            # rank r anchors its estimate THERE, r closed-form advances away -- instead of on the exact end of its own
+            # previous slice, N - 1 advances away (fewer and fresher terms: fewer slices speculated from a poor
+            # estimate, each of which chains serially on the ring).  Step 0 has no such phases: the old way.
+            anchor0 = self.anchor0 and hasattr(eng, "gather_payload") and hasattr(eng, "estimate_from")
+            payload = eng.gather_payload() if anchor0 else eng.adv
+            got = [torch.empty_like(payload) for _ in range(n)]
+            dist.all_gather(got, payload)
+            na = eng.adv.numel()
+            adv_all = [g[:na] for g in got]
+            if not have_exact:
+                if anchor0 and self.step_index > 0:
+                    eng.estimate_from(got[0][na:])              # rank 0's exact start of this step
+                    skipped = adv_all[:r]
+                else:                                           # slices owned by other ranks since my last one
+                    skipped = ([] if self.prev_adv is None else self.prev_adv[r + 1:]) + adv_all[:r]
                 for a in skipped:
                     eng.estimate_fold(a)
                 if hasattr(eng, "apply_bias"):

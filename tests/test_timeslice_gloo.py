@@ -134,6 +134,74 @@ def test_time_slices_equal_sequential_stream(tmp_path, WORLD, handoff):
     assert np.array_equal(np.load(tmp_path / "final_phase.npy"), st)
 
 
+# ---- lockstep runner, estimates anchored on rank 0's exact start ----------------------------------------------------
+class AnchorOracleEngine(OracleEngine):
+    """Adds what GpuSliceEngine offers for the rank-0 anchor: the gather payload (advance, flags, last exact phases
+    received) and estimate_from; keeps a shadow 'estimate' so that the test can check what it would be anchored on."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.anchors = []
+
+    def gather_payload(self):
+        return torch.cat([self.adv, self.phase])
+
+    def estimate_from(self, phases):
+        assert phases.numel() == self.state.size and phases.is_contiguous()
+        self.anchors.append(phases.clone())
+
+    def handoff_recv(self, seq):
+        super().handoff_recv(seq)
+        self.phase.copy_(torch.from_numpy(self.state.copy()))   # (GpuSliceEngine: carrier_to_device(self.phase))
+
+
+def _anchor_worker(rank, WORLD, port, outdir, handoff):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    from pluto_gps_sim_b200.timeslice import TimeSliceRunner
+
+    desc = _stream_desc(WORLD)
+    eng = AnchorOracleEngine(desc.shape[1], rank, WORLD)
+    runner = TimeSliceRunner(eng, rank, WORLD, handoff=handoff)
+    outs, starts = [], []
+    for s in range(STEPS):
+        first = (s * WORLD + rank) * E
+        out = np.zeros((E, N, 2), np.int16)
+        runner.step(desc[first:first + E], E, out)
+        outs.append(out)
+    runner.finish()
+    # rank r > 0: step 0 folds the r slices before it (no exact start yet); every later step anchors on rank 0's exact
+    # start and folds r advances -- not the N - 1 of the old scheme
+    assert eng.folds == (0 if rank == 0 else rank * STEPS), (rank, eng.folds)
+    assert len(eng.anchors) == (0 if rank == 0 else STEPS - 1)
+    np.save(os.path.join(outdir, "rank%d.npy" % rank), np.stack(outs))
+    np.save(os.path.join(outdir, "anchors%d.npy" % rank), np.stack([a.numpy() for a in eng.anchors]) if eng.anchors else np.zeros((0, desc.shape[1])))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("WORLD,handoff", [(2, "mailbox"), (3, "mailbox"), (3, "nccl")])
+def test_lockstep_estimates_anchor_on_rank0_exact_start(tmp_path, WORLD, handoff):
+    """Lockstep runner: rank 0 shares the exact phases it received at the start of the step in the per-step all_gather;
+    the other ranks anchor their start-phase estimates there.  The stream is unchanged (estimates never touch a
+    sample), and what the ranks anchor on IS the exact phase at the start of each step."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_anchor_worker, args=(WORLD, port, str(tmp_path), handoff), nprocs=WORLD, join=True)
+    desc = _stream_desc(WORLD)
+    st = np.zeros(desc.shape[1])
+    want, _ = ol.oracle_synth(desc, N, carr_state=st)
+    parts = [np.load(tmp_path / ("rank%d.npy" % r)) for r in range(WORLD)]
+    got = np.concatenate([parts[r][s] for s in range(STEPS) for r in range(WORLD)])
+    assert np.array_equal(got, want)
+    # the exact phase at the start of step s = the sequential run's state after s * WORLD * E epochs
+    st2 = np.zeros(desc.shape[1])
+    for s in range(1, STEPS):
+        ol.oracle_synth(desc[(s - 1) * WORLD * E: s * WORLD * E], N, carr_state=st2)
+        for r in range(1, WORLD):
+            assert np.array_equal(np.load(tmp_path / ("anchors%d.npy" % r))[s - 1], st2), (s, r)
+
+
 # ---- pipelined runner: no lockstep between the ranks ---------------------------------------------------------------
 class AsyncOracleEngine(OracleEngine):
     """The mailbox hand-off never blocks the sender (a copy engine write + a flag): isend here."""
