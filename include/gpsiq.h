@@ -196,6 +196,12 @@ int gpsiq_carrier_chain_host(const double *steps, int n_epochs, int N, int T, do
  * Diagnostic aid. */
 int gpsiq_carrier_slice_host(const double *steps, int n_epochs, int N, int T, double x0, double est_err,
                              double *ck_out, double *x_end_out, int *n_fallback, int *how_out, int *ties_out);
+/* Study aid (tools/margin_study.py): the same run with the device's group size (group_epochs, 64 on the device) and a
+ * residual rate subtracted from every closed-form epoch advance (what k_prepare does with its measured rate), reporting
+ * out5 = { decision margin of the slice-level trajectory, variant 0; variant 1; closed-form end estimate minus the exact
+ * end phase (cycles); smallest usable group-level margin; number of unusable groups }.  Diagnostic aid. */
+int gpsiq_carrier_study_host(const double *steps, int n_epochs, int N, int T, double x0, double est_err, double est_rate,
+                             int group_epochs, double *out5, int *how_out, int *n_fallback);
 
 /* Pinned host memory for descriptors / I/Q (cudaHostAlloc). */
 void *gpsiq_host_alloc(size_t bytes);

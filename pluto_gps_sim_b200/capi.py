@@ -71,6 +71,7 @@ SYMBOLS = {
     "gpsiq_nco_advance": (_i, [_i, C.POINTER(_d), _d, _i64, C.POINTER(_i64)]),
     "gpsiq_carrier_chain_host": (_i, [_vp, _i, _i, _i, _d, _d, _vp, C.POINTER(_d), C.POINTER(_i)]),
     "gpsiq_carrier_slice_host": (_i, [_vp, _i, _i, _i, _d, _d, _vp, C.POINTER(_d), C.POINTER(_i), C.POINTER(_i), _vp]),
+    "gpsiq_carrier_study_host": (_i, [_vp, _i, _i, _i, _d, _d, _d, _i, _vp, C.POINTER(_i), C.POINTER(_i)]),
     "gpsiq_host_alloc": (_vp, [C.c_size_t]),
     "gpsiq_host_free": (None, [_vp]),
     "gpsiq_launch_count": (_i64, [_vp]),

@@ -1152,12 +1152,18 @@ int gpsiq_nco_advance(int mode, double* phase, double step, int64_t count, int64
 // use_slice: chain through level 5 as the device does (slice-level speculation from the estimated start, one exact head
 // scan, the groups chained independently from their translated start phases).  how_out: 1 translated, 0 serial,
 // -2 = the groups' ends disagreed with the translation (an internal error: must never happen).
+// study (may be NULL): group size, a residual rate subtracted from every closed-form epoch advance (what the device's
+// k_prepare does with its measured rate), and where to report the margins (gpsiq_carrier_study_host).
+struct HostStudy { int group_epochs; double est_rate; double* out; };
+
 static int carrier_chain_host_impl(const double* steps, int n_epochs, int N, int T, double x0, double est_err, double* ck_out,
-                                   double* x_end_out, int* n_fallback, int use_slice, int* how_out, int* ties_out) {
+                                   double* x_end_out, int* n_fallback, int use_slice, int* how_out, int* ties_out,
+                                   const HostStudy* study = NULL) {
     if (!steps || !ck_out || n_epochs < 1 || N < 1 || T < 1) return GPSIQ_ERR_ARG;
     const int ntiles = (N + T - 1) / T;
     const int G = (ntiles + 7) / 8, J = (ntiles + G - 1) / G;
-    const int GP = 4;                                   // epochs per group (the device uses 16)
+    const int GP = (study && study->group_epochs > 0) ? study->group_epochs : 4;   // epochs per group (the device: 64)
+    const double est_rate = study ? study->est_rate : 0.0;
     const int E = n_epochs;
     const size_t ep = (size_t) 7 * ntiles;              // planes of one epoch: [7][ntiles]
     double* planes = (double*) malloc(sizeof(double) * ep * E);
@@ -1176,7 +1182,13 @@ static int carrier_chain_host_impl(const double* steps, int n_epochs, int N, int
         GroupEpoch& g = ge[e];
         g.d = d; g.phase0 = 0.0; g.active = 1; g.reset = 0;
         const StepInfo si = step_info(d);
-        const double eadv = fma((double) N, d, carr_drift_estimate(d, si, N));
+        // the epoch's closed-form advance modulo one cycle, as k_prepare computes it (exact product split: N*d is ~300
+        // cycles, its double alone carries only ~5e-14 of absolute precision)
+        const double dest = carr_drift_estimate(d, si, N);
+        const double eadv = fma((double) N, d, dest);    // whole-epoch advance (chunk interpolation)
+        volatile double pbig = (double) N * d;
+        const double pe = fma((double) N, d, -pbig);
+        const double eadv_frac = (pbig - floor(pbig)) + ((pe + dest) - est_rate);
         double a0 = xe + est_err;                        // what the device would guess, plus injected error
         a0 -= floor(a0);
         est[e] = a0;
@@ -1199,7 +1211,7 @@ static int carrier_chain_host_impl(const double* steps, int n_epochs, int N, int
             if ((V == 1 && d >= 0.0) || !carr_step_speculable(d)) continue;
             stitch_epoch(a0, d, si, N, T, G, V, cs, pl + (size_t) (2 + V) * ntiles, 1, ci + ((size_t) e * 2 + V) * J, *sE[V]);
         }
-        double t2 = xe + eadv;
+        double t2 = xe + eadv_frac;
         t2 -= floor(t2);
         xe = (t2 >= 0.0 && t2 < 1.0) ? t2 : 0.0;
     }
@@ -1249,6 +1261,7 @@ static int carrier_chain_host_impl(const double* steps, int n_epochs, int N, int
             sS[V].xw1 = tr.xw1; sS[V].xend = xs; sS[V].n1 = tr.pos; sS[V].pad = 0;
             sS[V].margin = (tr.pos >= 0 && tr.usable) ? tr.margin : -1.0;
             tS[V] = tr.tie;
+            if (study && study->out) study->out[V] = sS[V].margin;
         }
         double xv = x0;
         const int count0 = (E < GP) ? E : GP;
@@ -1285,6 +1298,16 @@ static int carrier_chain_host_impl(const double* steps, int n_epochs, int N, int
         }
     }
     if (how == 1 && x != x_end_slice) how = -2;
+    if (study && study->out) {
+        double e = xe - x;                               // closed-form end estimate (from the exact start) - exact end
+        e -= rint(e);
+        study->out[2] = e;
+        double mg = 1.0;                                 // smallest usable group-level margin (variant 0)
+        int unusable = 0;
+        for (int g = 0; g < ngroups; g++) { const double m = sGall[2 * g].margin; if (m > 0.0) { if (m < mg) mg = m; } else unusable++; }
+        study->out[3] = mg;
+        study->out[4] = (double) unusable;
+    }
     free(planes); free(ge); free(ci); free(infG); free(trace); free(est); free(cs_all); free(sGall); free(startS); free(tGall);
     if (x_end_out) *x_end_out = x;
     if (n_fallback) *n_fallback = fb;
@@ -1296,6 +1319,20 @@ static int carrier_chain_host_impl(const double* steps, int n_epochs, int N, int
 int gpsiq_carrier_chain_host(const double* steps, int n_epochs, int N, int T, double x0, double est_err, double* ck_out,
                              double* x_end_out, int* n_fallback) {
     return carrier_chain_host_impl(steps, n_epochs, N, T, x0, est_err, ck_out, x_end_out, n_fallback, 0, NULL, NULL);
+}
+
+int gpsiq_carrier_study_host(const double* steps, int n_epochs, int N, int T, double x0, double est_err, double est_rate,
+                             int group_epochs, double* out5, int* how_out, int* n_fallback) {
+    if (!out5) return GPSIQ_ERR_ARG;
+    const int ntiles = (N + T - 1) / T;
+    double* ck = (double*) malloc(sizeof(double) * (size_t) n_epochs * ntiles);
+    if (!ck) return GPSIQ_ERR_NOMEM;
+    for (int i = 0; i < 5; i++) out5[i] = 0.0;
+    HostStudy st;
+    st.group_epochs = group_epochs; st.est_rate = est_rate; st.out = out5;
+    const int rc = carrier_chain_host_impl(steps, n_epochs, N, T, x0, est_err, ck, NULL, n_fallback, 1, how_out, NULL, &st);
+    free(ck);
+    return rc;
 }
 
 int gpsiq_carrier_slice_host(const double* steps, int n_epochs, int N, int T, double x0, double est_err, double* ck_out,
