@@ -193,9 +193,12 @@ int gpsiq_carrier_chain_host(const double *steps, int n_epochs, int N, int T, do
  * slice-level speculation), -2 = a group ended somewhere else than the translation predicts (internal error).
  * ties_out (2 ints, may be NULL): [0] usable group trajectories that contain a tie-wrap of a tie-capable step
  * (csrc/nco_scan.cuh: TieEvent), [1] translations that changed at such an event (groups + 1000 * slice level).
- * Diagnostic aid. */
+ * Diagnostic aid.
+ * flags / phase0 (may be NULL): per epoch, bit 0 = the slot is inactive in that epoch (the phase passes through),
+ * bit 1 = the slot is re-seeded with phase0[e] at its first sample (a slice with a re-seed is chained serially). */
 int gpsiq_carrier_slice_host(const double *steps, int n_epochs, int N, int T, double x0, double est_err,
-                             double *ck_out, double *x_end_out, int *n_fallback, int *how_out, int *ties_out);
+                             double *ck_out, double *x_end_out, int *n_fallback, int *how_out, int *ties_out,
+                             const int *flags, const double *phase0);
 /* Study aid (tools/margin_study.py): the same run with the device's group size (group_epochs, 64 on the device) and a
  * residual rate subtracted from every closed-form epoch advance (what k_prepare does with its measured rate), reporting
  * out5 = { decision margin of the slice-level trajectory, variant 0; variant 1; closed-form end estimate minus the exact

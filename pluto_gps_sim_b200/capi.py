@@ -70,7 +70,7 @@ SYMBOLS = {
     "gpsiq_make_desc": (_i, [_vp, _i, _i, _d, _d, _d, _d, _d, _vp, _i, _i, _i, _d, _i]),
     "gpsiq_nco_advance": (_i, [_i, C.POINTER(_d), _d, _i64, C.POINTER(_i64)]),
     "gpsiq_carrier_chain_host": (_i, [_vp, _i, _i, _i, _d, _d, _vp, C.POINTER(_d), C.POINTER(_i)]),
-    "gpsiq_carrier_slice_host": (_i, [_vp, _i, _i, _i, _d, _d, _vp, C.POINTER(_d), C.POINTER(_i), C.POINTER(_i), _vp]),
+    "gpsiq_carrier_slice_host": (_i, [_vp, _i, _i, _i, _d, _d, _vp, C.POINTER(_d), C.POINTER(_i), C.POINTER(_i), _vp, _vp, _vp]),
     "gpsiq_carrier_study_host": (_i, [_vp, _i, _i, _i, _d, _d, _d, _i, _vp, C.POINTER(_i), C.POINTER(_i)]),
     "gpsiq_host_alloc": (_vp, [C.c_size_t]),
     "gpsiq_host_free": (None, [_vp]),
@@ -214,7 +214,7 @@ def carrier_chain_host(steps, N, T, x0, est_err=0.0):
     return ck, xe.value, fb.value
 
 
-def carrier_slice_host(steps, N, T, x0, est_err=0.0, ties=None):
+def carrier_slice_host(steps, N, T, x0, est_err=0.0, ties=None, flags=None, phase0=None):
     """Host run of the carrier scan through the slice level (one exact head scan per batch, groups chained from their
     translated starts) -> (ck [E][ntiles], x_end, n_fallback, how): how 1 translated, 0 serial, -2 internal error.
     ties: optional int32 array of 2 -> [group trajectories holding a tie event, translations changed by one]."""
@@ -222,8 +222,11 @@ def carrier_slice_host(steps, N, T, x0, est_err=0.0, ties=None):
     ntiles = (N + T - 1) // T
     ck = np.zeros((st.size, ntiles), np.float64)
     xe, fb, how = _d(0), _i(0), _i(0)
+    fl = None if flags is None else np.ascontiguousarray(flags, dtype=np.int32)
+    p0 = None if phase0 is None else np.ascontiguousarray(phase0, dtype=np.float64)
     check(lib.gpsiq_carrier_slice_host(st.ctypes.data, st.size, N, T, float(x0), float(est_err), ck.ctypes.data,
-                                       C.byref(xe), C.byref(fb), C.byref(how), None if ties is None else ties.ctypes.data))
+                                       C.byref(xe), C.byref(fb), C.byref(how), None if ties is None else ties.ctypes.data,
+                                       None if fl is None else fl.ctypes.data, None if p0 is None else p0.ctypes.data))
     return ck, xe.value, fb.value, how.value
 
 

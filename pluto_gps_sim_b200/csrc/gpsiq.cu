@@ -1154,7 +1154,7 @@ int gpsiq_nco_advance(int mode, double* phase, double step, int64_t count, int64
 // -2 = the groups' ends disagreed with the translation (an internal error: must never happen).
 // study (may be NULL): group size, a residual rate subtracted from every closed-form epoch advance (what the device's
 // k_prepare does with its measured rate), and where to report the margins (gpsiq_carrier_study_host).
-struct HostStudy { int group_epochs; double est_rate; double* out; };
+struct HostStudy { int group_epochs; double est_rate; double* out; const int* flags; const double* phase0; };   // flags[e]: bit 0 = slot inactive in epoch e, bit 1 = re-seeded with phase0[e]
 
 static int carrier_chain_host_impl(const double* steps, int n_epochs, int N, int T, double x0, double est_err, double* ck_out,
                                    double* x_end_out, int* n_fallback, int use_slice, int* how_out, int* ties_out,
@@ -1181,6 +1181,11 @@ static int carrier_chain_host_impl(const double* steps, int n_epochs, int N, int
         const double d = steps[e];
         GroupEpoch& g = ge[e];
         g.d = d; g.phase0 = 0.0; g.active = 1; g.reset = 0;
+        if (study && study->flags) {
+            g.active = !(study->flags[e] & 1);
+            g.reset = g.active && (study->flags[e] & 2) != 0;
+            if (g.reset) { g.phase0 = study->phase0 ? study->phase0[e] : 0.0; xe = g.phase0; }   // (the device: ereset)
+        }
         const StepInfo si = step_info(d);
         // the epoch's closed-form advance modulo one cycle, as k_prepare computes it (exact product split: N*d is ~300
         // cycles, its double alone carries only ~5e-14 of absolute precision)
@@ -1189,7 +1194,7 @@ static int carrier_chain_host_impl(const double* steps, int n_epochs, int N, int
         volatile double pbig = (double) N * d;
         const double pe = fma((double) N, d, -pbig);
         const double eadv_frac = (pbig - floor(pbig)) + ((pe + dest) - est_rate);
-        double a0 = xe + est_err;                        // what the device would guess, plus injected error
+        double a0 = xe + (g.reset ? 0.0 : est_err);      // what the device would guess, plus injected error
         a0 -= floor(a0);
         est[e] = a0;
         double* pl = planes + ep * e;
@@ -1199,7 +1204,7 @@ static int carrier_chain_host_impl(const double* steps, int n_epochs, int N, int
             CarrSpec& o1 = cs[j * 2 + 1];
             o0.margin = -1.0; o0.n1 = -1; o0.xw1 = 0; o0.xend = 0; o0.pad = 0;
             o1 = o0;
-            if (!carr_step_speculable(d)) continue;
+            if (!g.active || !carr_step_speculable(d)) continue;
             const int t0 = j * G, t1 = (t0 + G < ntiles) ? t0 + G : ntiles;
             double xs = a0;
             if (j > 0) { xs = a0 + eadv * ((double) (t0 * T) / (double) N); xs -= floor(xs); if (!(xs >= 0.0 && xs < 1.0)) xs = 0.0; }
@@ -1208,9 +1213,10 @@ static int carrier_chain_host_impl(const double* steps, int n_epochs, int N, int
         CarrSpec* sE[2] = {&g.s0, &g.s1};
         for (int V = 0; V < 2; V++) {
             sE[V]->margin = -1.0; sE[V]->n1 = -1; sE[V]->xw1 = 0; sE[V]->xend = 0; sE[V]->pad = 0;
-            if ((V == 1 && d >= 0.0) || !carr_step_speculable(d)) continue;
+            if (!g.active || (V == 1 && d >= 0.0) || !carr_step_speculable(d)) continue;
             stitch_epoch(a0, d, si, N, T, G, V, cs, pl + (size_t) (2 + V) * ntiles, 1, ci + ((size_t) e * 2 + V) * J, *sE[V]);
         }
+        if (!g.active) continue;                          // (the phase passes through an inactive epoch)
         double t2 = xe + eadv_frac;
         t2 -= floor(t2);
         xe = (t2 >= 0.0 && t2 < 1.0) ? t2 : 0.0;
@@ -1226,7 +1232,7 @@ static int carrier_chain_host_impl(const double* steps, int n_epochs, int N, int
         const int count = (E - first < GP) ? E - first : GP;
         CarrSpec* sG = sGall + 2 * (first / GP);
         bool any_neg = false;
-        for (int k = 0; k < count; k++) any_neg |= ge[first + k].d < 0.0;
+        for (int k = 0; k < count; k++) any_neg |= ge[first + k].active && ge[first + k].d < 0.0;
         for (int V = 0; V < 2; V++) {
             sG[V].margin = -1.0; sG[V].n1 = -1; sG[V].xw1 = 0; sG[V].xend = 0; sG[V].pad = 0;
             TieEvent& tG = tGall[2 * (first / GP) + V];
@@ -1329,15 +1335,19 @@ int gpsiq_carrier_study_host(const double* steps, int n_epochs, int N, int T, do
     if (!ck) return GPSIQ_ERR_NOMEM;
     for (int i = 0; i < 5; i++) out5[i] = 0.0;
     HostStudy st;
-    st.group_epochs = group_epochs; st.est_rate = est_rate; st.out = out5;
+    st.group_epochs = group_epochs; st.est_rate = est_rate; st.out = out5; st.flags = NULL; st.phase0 = NULL;
     const int rc = carrier_chain_host_impl(steps, n_epochs, N, T, x0, est_err, ck, NULL, n_fallback, 1, how_out, NULL, &st);
     free(ck);
     return rc;
 }
 
 int gpsiq_carrier_slice_host(const double* steps, int n_epochs, int N, int T, double x0, double est_err, double* ck_out,
-                             double* x_end_out, int* n_fallback, int* how_out, int* ties_out) {
-    return carrier_chain_host_impl(steps, n_epochs, N, T, x0, est_err, ck_out, x_end_out, n_fallback, 1, how_out, ties_out);
+                             double* x_end_out, int* n_fallback, int* how_out, int* ties_out, const int* flags,
+                             const double* phase0) {
+    HostStudy st;
+    st.group_epochs = 0; st.est_rate = 0.0; st.out = NULL; st.flags = flags; st.phase0 = phase0;
+    return carrier_chain_host_impl(steps, n_epochs, N, T, x0, est_err, ck_out, x_end_out, n_fallback, 1, how_out, ties_out,
+                                   flags ? &st : NULL);
 }
 
 void* gpsiq_host_alloc(size_t bytes) {

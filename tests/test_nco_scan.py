@@ -231,3 +231,60 @@ def test_tie_capable_steps_are_translated_through_their_tie_event():
         got2, gx2, _ = capi.carrier_chain_host(steps, N, T, x0, err)
         assert np.array_equal(got2.view(np.int64), want.view(np.int64)) and bits(gx2) == bits(wx)
     assert seen >= 40 and applied_g >= 5 and applied_s >= 3 and passed >= 30, (seen, applied_g, applied_s, passed)
+
+
+def _literal_with_flags(steps, flags, phase0, N, T, x0):
+    nt = (N + T - 1) // T
+    ck = np.zeros((len(steps), nt))
+    x = x0
+    for e, d in enumerate(steps):
+        if flags[e] & 1:                       # inactive: the phase passes through, no tile phases
+            continue
+        if flags[e] & 2:
+            x = phase0[e]
+        for t in range(nt):
+            ck[e, t] = x
+            x = ol.oracle_carr_nco(x, d, min(T, N - t * T))
+    return ck, x
+
+
+def test_slice_level_chain_with_inactive_and_reseeded_epochs():
+    """A slot may be inactive for some epochs of a batch (the phase passes through: plutogpssim.c:2690 skips the
+    channel) and may be re-seeded inside it (allocation, plutogpssim.c:1964).  Inactive epochs -- at the start of the
+    batch, at the start of a group, whole groups -- are translated through; a re-seed makes the slice untranslatable
+    and it is chained serially.  Every active tile-start phase and the end phase equal the literal recurrence."""
+    rng = random.Random(909)
+    translated = serial = 0
+    for trial in range(40):
+        fs = rng.choice([2.6e6, 1e7])
+        f0 = rng.uniform(-5000, 5000)
+        E, N, T = rng.choice([9, 12, 16]), rng.choice([260000, 100000]), 1024
+        steps = [(f0 + rng.uniform(-1, 1)) / fs for _ in range(E)]
+        flags = np.zeros(E, np.int32)
+        phase0 = np.zeros(E)
+        kind = trial % 4
+        if kind == 0:                          # inactive at the start of the batch (incl. its whole first group)
+            flags[: rng.choice([1, 3, 4, 5])] = 1
+        elif kind == 1:                        # scattered inactive epochs, incl. first epochs of groups
+            for e in rng.sample(range(E), 3):
+                flags[e] = 1
+            flags[4] = 1
+        elif kind == 2:                        # a whole group in the middle inactive
+            flags[4:8] = 1
+        else:                                  # a re-seed somewhere after the first epoch
+            e = rng.randrange(1, E)
+            flags[e] = 2
+            phase0[e] = rng.random()
+        x0 = rng.random()
+        err = rng.choice([0.0, 1e-13, 1e-12])
+        want, wx = _literal_with_flags(steps, flags, phase0, N, T, x0)
+        got, gx, fb, how = capi.carrier_slice_host(steps, N, T, x0, err, flags=flags, phase0=phase0)
+        assert how in (0, 1), (trial, how)
+        act = (flags & 1) == 0
+        assert np.array_equal(got[act].view(np.int64), want[act].view(np.int64)), (trial, kind, how)
+        assert bits(gx) == bits(wx), (trial, kind, how)
+        if kind == 3:
+            assert how == 0, trial             # re-seeded inside the slice: never translated
+        translated += how == 1
+        serial += how == 0
+    assert translated >= 12 and serial >= 10, (translated, serial)
