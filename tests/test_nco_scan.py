@@ -288,3 +288,33 @@ def test_slice_level_chain_with_inactive_and_reseeded_epochs():
         translated += how == 1
         serial += how == 0
     assert translated >= 12 and serial >= 10, (translated, serial)
+
+
+def test_tie_events_adversarial_steps_and_phases():
+    """Ties at every wrap (steps that are small multiples of 2^-53 of very different magnitudes), mixed with ordinary and
+    negative steps, start phases on grid points (0, 0.5, 1 - 2^-53, small multiples of 2^-52) and estimate errors of a
+    few units of 2^-52 of either sign: the translated chains stay exact, with and without the slice level."""
+    rng = random.Random(2025)
+    ties = np.zeros(2, np.int32)
+    applied = 0
+    mags = [2.0 ** -9, 3 * 2.0 ** -12, 5 * 2.0 ** -11, 2.0 ** -10 + 2.0 ** -53, 2.0 ** -10 + 3 * 2.0 ** -53,
+            7 * 2.0 ** -14 + 2.0 ** -52, 2.0 ** -12 + 2.0 ** -40, 1.1e-3]
+    for trial in range(120):
+        E, N, T = rng.choice([5, 8, 12]), rng.choice([4097, 30000]), rng.choice([512, 1024])
+        base = rng.choice(mags)
+        steps = []
+        for _ in range(E):
+            m = (rng.choice(mags) if rng.random() < 0.5 else base) * (1 + rng.uniform(-1e-3, 1e-3))
+            d = float(np.ldexp(float(round(np.ldexp(m, 53))), -53)) if rng.random() < 0.6 else m
+            steps.append(-d if rng.random() < 0.15 else d)
+        x0 = rng.choice([rng.random(), 0.0, 0.5, 1 - 2.0 ** -53, 2.0 ** -52 * rng.randrange(1, 1000)])
+        err = rng.choice([0.0, 2.0 ** -52, -2.0 ** -52, 3 * 2.0 ** -52, -5 * 2.0 ** -52, 2.0 ** -53, 1e-13, -7e-13, 1e-11])
+        want, wx = _literal_checkpoints(steps, N, T, x0)
+        got, gx, fb, how = capi.carrier_slice_host(steps, N, T, x0, err, ties)
+        assert how in (0, 1), (trial, how)
+        assert np.array_equal(got.view(np.int64), want.view(np.int64)), (trial, steps, x0, err, how)
+        assert bits(gx) == bits(wx)
+        got2, gx2, _ = capi.carrier_chain_host(steps, N, T, x0, err)
+        assert np.array_equal(got2.view(np.int64), want.view(np.int64)) and bits(gx2) == bits(wx), trial
+        applied += int(ties[1])
+    assert applied % 1000 >= 30 and applied // 1000 >= 10, applied
